@@ -1,0 +1,162 @@
+/*
+ * rcsb.h — C ABI of the batched B200 path of rcs_b200.
+ *
+ * The reference (HRI-EU/Rcs) has no FFI seam on this path: its boundary is the extern "C"
+ * API of libRcsCore itself, one state per call on one RcsGraph. The entry points below are
+ * the batched equivalents; each evaluates N independent joint states in hand-written
+ * sm_100a CUDA kernels and returns, per state, exactly what the cited reference function
+ * leaves in the graph / output matrices for that state. Layouts are the reference's
+ * (HTr = org[3] + row-major rot[3][3]; matrices row-major), with the state index slowest.
+ *
+ *   rcsb_fk              RcsGraph_setState / RcsGraph_computeForwardKinematics
+ *                        src/RcsCore/Rcs_graph.c:231, :301 (kernel: :61-226)
+ *   rcsb_fk_jacobians    + RcsGraph_bodyPointJacobian  src/RcsCore/Rcs_kinematics.c:200
+ *                        + RcsGraph_rotationJacobian   src/RcsCore/Rcs_kinematics.c:416
+ *   rcsb_kinetic_terms   RcsGraph_computeKineticTerms  src/RcsCore/Rcs_dynamics.c:439
+ *   rcsb_ik_rmr          ControllerBase::computeDX / computeJ / computeJointlimitGradient
+ *                        (src/RcsCore/ControllerBase.cpp:776, :896, :1332) +
+ *                        IkSolverRMR::solveRightInverse (src/RcsCore/IkSolverRMR.cpp:403)
+ *                        iterated as in examples/ExampleIK.cpp:154-177
+ *
+ * Conventions
+ *  - Every call returns 0 on success, a negative RCSB_E* code otherwise; the message is
+ *    available from rcsb_last_error() (thread-local). Nothing here calls exit().
+ *  - q / q_dot rows have qdim entries, qdim == dof (full state, joint order = jointIndex)
+ *    or qdim == nJ (IK state, order = jacobiIndex; constrained joints then take the value
+ *    the graph held when the model was created). Kinematically coupled (slave) joints are
+ *    overwritten from their master, as RcsGraph_setState does (Rcs_graph.c:2756).
+ *  - Array arguments are DEVICE pointers unless RCSB_HOST_PTRS is set; with RCSB_HOST_PTRS
+ *    they are host pointers (pinned memory from rcsb_host_alloc() is fastest) and the call
+ *    copies inputs in and results out, pipelined with the kernels, and returns when the
+ *    results are in host memory. Selector arrays (bodySel, effBody, effPt) are always small
+ *    host arrays.
+ *  - stream is a cudaStream_t (NULL = default stream). Device-pointer calls are
+ *    asynchronous on that stream. A model is immutable and may be shared by threads.
+ *  - There is no CPU fallback: without a CUDA device every compute call fails with
+ *    RCSB_ENODEVICE.
+ */
+#ifndef RCSB_H
+#define RCSB_H
+
+#include "rcsb_graph.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCSB_OK 0
+#define RCSB_EINVAL (-1)     /* bad argument / shape */
+#define RCSB_ENODEVICE (-2)  /* no CUDA device / driver */
+#define RCSB_ECUDA (-3)      /* CUDA runtime error */
+#define RCSB_ENOMEM (-4)
+#define RCSB_EUNSUPPORTED (-5)
+
+#define RCSB_HOST_PTRS 1u    /* array arguments are host pointers */
+
+/* task kinds of rcsb_ik_rmr, named after the reference's controlVariable strings
+ * (src/RcsCore/TaskPosition3D.cpp:49, TaskEuler3D.cpp:52) */
+#define RCSB_TASK_XYZ 1
+#define RCSB_TASK_ABC 2
+
+typedef struct RcsbModel RcsbModel;
+
+typedef struct
+{
+  int kind;         /* RCSB_TASK_* */
+  int effector;     /* depth-first body index of the effector */
+} RcsbTask;
+
+/* ---- model ---------------------------------------------------------------------------- */
+
+/* Flattens the graph (depth-first structure-of-arrays: parents, joint types and axes,
+ * relative transforms, mass properties, coupling rules, joint metric) and uploads it to
+ * `device`. The graph is not referenced afterwards. */
+int rcsb_model_create(const RcsGraph* graph, int device, RcsbModel** model);
+void rcsb_model_destroy(RcsbModel* model);
+int rcsb_model_dof(const RcsbModel* model);
+int rcsb_model_nj(const RcsbModel* model);
+int rcsb_model_nbodies(const RcsbModel* model);
+int rcsb_model_device(const RcsbModel* model);
+
+/* ---- forward kinematics ---------------------------------------------------------------- */
+
+/*
+ * q [N x qdim], qd [N x qdim] or NULL.
+ * bodySel: nSel depth-first body indices, or NULL with nSel == 0 for "all bodies".
+ * Outputs (each may be NULL): A_BI [N x nSel x 12], A_JI [N x dof x 12] (all joints, by
+ * jointIndex), xdot / omega [N x nSel x 3] (need qd), qOut [N x dof] the full state after
+ * expansion and coupling.
+ */
+int rcsb_fk(const RcsbModel* model, long N, int qdim, const double* q, const double* qd,
+            int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
+            double* omega, double* qOut, unsigned flags, void* stream);
+
+/*
+ * Forward kinematics plus, for each of nEff effectors, the translation Jacobian of the
+ * body-fixed point effPt[e] (NULL = body origins) and the rotation Jacobian of the body:
+ * JT, JR [N x nEff x 3 x nJ], world frame, columns of non-ancestor or constrained joints
+ * exactly 0. A_BI as in rcsb_fk (NULL to skip the frames).
+ */
+int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q, int nSel,
+                      const int* bodySel, double* A_BI, int nEff, const int* effBody,
+                      const double* effPt, double* JT, double* JR, unsigned flags,
+                      void* stream);
+
+/* ---- dynamics --------------------------------------------------------------------------- */
+
+/*
+ * M [N x nJ x nJ], h [N x nJ], Fg [N x nJ], E [N]; any may be NULL. Sign conventions are
+ * the reference's: M qdd = Fg + h + ..., i.e. h = -C(q,qd) qd and Fg = -G(q)
+ * (src/RcsCore/Rcs_dynamics.c:718-731). qd may be NULL (zero velocities).
+ */
+int rcsb_kinetic_terms(const RcsbModel* model, long N, int qdim, const double* q,
+                       const double* qd, double* M, double* h, double* Fg, double* E,
+                       unsigned flags, void* stream);
+
+/* ---- inverse kinematics ----------------------------------------------------------------- */
+
+/*
+ * `iters` resolved-motion-rate steps per state, all tasks active:
+ *   dx = computeDX(x_des); dH = alpha * jointLimitGradient; dq = J# dx + N invWq (-dH);
+ *   q += dq; setState.
+ * q [N x dof] in/out. xDes [N x nx], nx = 3 per task (XYZ: position, ABC: x-y-z Euler
+ * angles). Optional outputs of the LAST iteration: dx [N x nx] (task error before the
+ * step), dq [N x dof], det [N] (determinant of J invWq J^T + lambda I; 0 = singular, the
+ * step is then zero as in the reference).
+ */
+int rcsb_ik_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, long N, double* q,
+                const double* xDes, double lambda, double alpha, int iters, double* dx,
+                double* dq, double* det, unsigned flags, void* stream);
+
+/* ---- utilities -------------------------------------------------------------------------- */
+
+const char* rcsb_last_error(void);
+int rcsb_device_count(void);
+/* pinned host memory for RCSB_HOST_PTRS calls */
+void* rcsb_host_alloc(size_t bytes);
+void rcsb_host_free(void* p);
+/* number of kernels launched by this library in this process (all threads) */
+unsigned long long rcsb_kernel_launch_count(void);
+
+/* ---- single-state reference API (N = 1 through the kernels above) ---------------------- */
+
+/* src/RcsCore/Rcs_graph.c:231. q / q_dot: dof x 1, nJ x 1 or NULL (use graph->q). Fills
+ * A_BI / A_JI / x_dot / omega of every body and joint. Returns true if a slave joint's
+ * value had to be changed by more than 1e-8. Wrong dimensions are fatal (see
+ * Rcs_setFatalMode). */
+bool RcsGraph_setState(RcsGraph* self, const MatNd* q, const MatNd* q_dot);
+/* src/RcsCore/Rcs_graph.c:301 */
+void RcsGraph_computeForwardKinematics(RcsGraph* self, const MatNd* q, const MatNd* q_dot);
+/* src/RcsCore/Rcs_kinematics.c:200, :416 — world frame only (A_BI must be NULL). */
+void RcsGraph_bodyPointJacobian(const RcsGraph* self, const RcsBody* body, const double B_pt[3],
+                                double A_BI[3][3], MatNd* J);
+void RcsGraph_rotationJacobian(const RcsGraph* self, const RcsBody* body, double A_BI[3][3],
+                               MatNd* J);
+/* src/RcsCore/Rcs_dynamics.c:439 */
+double RcsGraph_computeKineticTerms(const RcsGraph* self, MatNd* M, MatNd* h, MatNd* F_gravity);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,686 @@
+/*
+ * ref_api — C entry points that drive the UNMODIFIED reference (HRI-EU/Rcs RcsCore,
+ * compiled from /root/reference by oracle/ref_build/Makefile) over batches of states.
+ *
+ * TEST INFRASTRUCTURE ONLY. This file is the parity anchor ("oracle/_ref") and the
+ * "reference" CPU baseline of bench.py. It contains no algorithm of its own: every
+ * number it returns is produced by a reference function, one state at a time, exactly as
+ * the reference's own apps call them:
+ *   RcsGraph_create / RcsGraph_clone         src/RcsCore/Rcs_graph.c:398, :2193
+ *   RcsGraph_setState                        src/RcsCore/Rcs_graph.c:231
+ *   RcsGraph_bodyPointJacobian               src/RcsCore/Rcs_kinematics.c:200
+ *   RcsGraph_rotationJacobian                src/RcsCore/Rcs_kinematics.c:416
+ *   RcsGraph_COG / RcsGraph_COGJacobian      src/RcsCore/Rcs_kinematics.c:904, :973
+ *   RcsGraph_computeKineticTerms             src/RcsCore/Rcs_dynamics.c:439
+ *   RcsGraph_computeMassMatrix               src/RcsCore/Rcs_dynamics.c:610
+ *   ControllerBase::computeDX/computeJ/...   src/RcsCore/ControllerBase.cpp:776-1332
+ *   IkSolverRMR::solveRightInverse           src/RcsCore/IkSolverRMR.cpp:403
+ * The loop of ref_ik_rmr mirrors examples/ExampleIK.cpp:154-177.
+ *
+ * Threading: batches are cut into contiguous slices, one std::thread per slice, one
+ * RcsGraph_clone (or ControllerBase copy + IkSolverRMR) per thread.
+ */
+#include <Rcs_typedef.h>
+#include <Rcs_graph.h>
+#include <Rcs_body.h>
+#include <Rcs_joint.h>
+#include <Rcs_kinematics.h>
+#include <Rcs_dynamics.h>
+#include <Rcs_macros.h>
+#include <Rcs_MatNd.h>
+#include <Rcs_Mat3d.h>
+#include <Rcs_Vec3d.h>
+#include <Rcs_resourcePath.h>
+#include <ControllerBase.h>
+#include <IkSolverRMR.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace
+{
+
+int g_threads = 1;
+
+template <class F>
+double parallelSlices(long N, F body)
+{
+  int nt = g_threads < 1 ? 1 : g_threads;
+  if ((long) nt > N)
+  {
+    nt = N > 0 ? (int) N : 1;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  if (nt == 1)
+  {
+    body(0, 0L, N);
+  }
+  else
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+    {
+      long lo = N * t / nt, hi = N * (t + 1) / nt;
+      th.emplace_back([=]() { body(t, lo, hi); });
+    }
+    for (auto& x : th)
+    {
+      x.join();
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+std::vector<RcsBody*> dfsBodies(const RcsGraph* g)
+{
+  std::vector<RcsBody*> v;
+  RCSGRAPH_TRAVERSE_BODIES(g)
+  {
+    v.push_back(BODY);
+  }
+  return v;
+}
+
+int bodyIndex(const std::vector<RcsBody*>& v, const RcsBody* b)
+{
+  if (!b)
+  {
+    return -1;
+  }
+  for (size_t i = 0; i < v.size(); ++i)
+  {
+    if (v[i] == b)
+    {
+      return (int) i;
+    }
+  }
+  return -1;
+}
+
+void putDouble(std::ostringstream& o, double x)
+{
+  char buf[40];
+  snprintf(buf, sizeof(buf), "%.17g", x);
+  // JSON has no inf/nan; DBL_MAX prints fine.
+  o << buf;
+}
+
+void putHTr(std::ostringstream& o, const HTr* A)
+{
+  if (!A)
+  {
+    o << "null";
+    return;
+  }
+  o << "[";
+  for (int i = 0; i < 3; ++i)
+  {
+    putDouble(o, A->org[i]);
+    o << ",";
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+    {
+      putDouble(o, A->rot[i][j]);
+      if (i * 3 + j < 8)
+      {
+        o << ",";
+      }
+    }
+  o << "]";
+}
+
+void setQ(RcsGraph* g, MatNd* qv, MatNd* qdv, int qdim, const double* q, const double* qd)
+{
+  MatNd_reshape(qv, qdim, 1);
+  memcpy(qv->ele, q, sizeof(double) * qdim);
+  if (qd)
+  {
+    MatNd_reshape(qdv, qdim, 1);
+    memcpy(qdv->ele, qd, sizeof(double) * qdim);
+  }
+  RcsGraph_setState(g, qv, qd ? qdv : NULL);
+}
+
+struct IkHandle
+{
+  Rcs::ControllerBase* controller;
+  std::string xml;
+};
+
+}   // namespace
+
+extern "C" {
+
+void ref_set_threads(int n)
+{
+  g_threads = n;
+}
+
+void ref_set_log_level(int l)
+{
+  RcsLogLevel = l;
+}
+
+void ref_add_resource_path(const char* p)
+{
+  Rcs_addResourcePath(p);
+}
+
+void* ref_graph_create(const char* xmlFile)
+{
+  return RcsGraph_create(xmlFile);
+}
+
+void ref_graph_destroy(void* g)
+{
+  RcsGraph_destroy((RcsGraph*) g);
+}
+
+int ref_graph_dof(void* g)
+{
+  return (int) ((RcsGraph*) g)->dof;
+}
+
+int ref_graph_nj(void* g)
+{
+  return (int) ((RcsGraph*) g)->nJ;
+}
+
+int ref_graph_nbodies(void* g)
+{
+  return (int) dfsBodies((RcsGraph*) g).size();
+}
+
+int ref_graph_check(void* g, int* nErrors, int* nWarnings)
+{
+  return RcsGraph_check((RcsGraph*) g, nErrors, nWarnings) ? 1 : 0;
+}
+
+int ref_body_index(void* g, const char* name)
+{
+  RcsGraph* graph = (RcsGraph*) g;
+  return bodyIndex(dfsBodies(graph), RcsGraph_getBodyByName(graph, name));
+}
+
+void ref_free(void* p)
+{
+  free(p);
+}
+
+/* Canonical JSON dump of everything the hot path reads from the loaded graph. */
+char* ref_graph_layout_json(void* g)
+{
+  RcsGraph* graph = (RcsGraph*) g;
+  std::vector<RcsBody*> bodies = dfsBodies(graph);
+  std::ostringstream o;
+  o << "{\"dof\":" << graph->dof << ",\"nJ\":" << graph->nJ
+    << ",\"nBodies\":" << bodies.size() << ",\"bodies\":[";
+
+  for (size_t i = 0; i < bodies.size(); ++i)
+  {
+    RcsBody* b = bodies[i];
+    o << (i ? "," : "") << "{\"name\":\"" << b->name << "\",\"parent\":"
+      << bodyIndex(bodies, b->parent) << ",\"firstChild\":" << bodyIndex(bodies, b->firstChild)
+      << ",\"lastChild\":" << bodyIndex(bodies, b->lastChild)
+      << ",\"next\":" << bodyIndex(bodies, b->next) << ",\"prev\":" << bodyIndex(bodies, b->prev)
+      << ",\"m\":";
+    putDouble(o, b->m);
+    o << ",\"rigid_body_joints\":" << (b->rigid_body_joints ? "true" : "false")
+      << ",\"physicsSim\":" << b->physicsSim << ",\"A_BP\":";
+    putHTr(o, b->A_BP);
+    o << ",\"Inertia\":";
+    putHTr(o, b->Inertia);
+    o << ",\"joints\":[";
+    bool first = true;
+    for (RcsJoint* j = b->jnt; j; j = j->next)
+    {
+      o << (first ? "" : ",") << j->jointIndex;
+      first = false;
+    }
+    int nShapes = 0;
+    if (b->shape)
+    {
+      for (RcsShape** s = b->shape; *s; ++s)
+      {
+        nShapes++;
+      }
+    }
+    o << "],\"nShapes\":" << nShapes << "}";
+  }
+  o << "],\"joints\":[";
+
+  bool firstJ = true;
+  RCSGRAPH_TRAVERSE_JOINTS(graph)
+  {
+    RcsJoint* j = JNT;
+    int bIdx = -1;
+    for (size_t i = 0; i < bodies.size() && bIdx < 0; ++i)
+      for (RcsJoint* k = bodies[i]->jnt; k; k = k->next)
+        if (k == j)
+        {
+          bIdx = (int) i;
+        }
+    o << (firstJ ? "" : ",") << "{\"name\":\"" << j->name << "\",\"body\":" << bIdx
+      << ",\"type\":" << j->type << ",\"dirIdx\":" << j->dirIdx
+      << ",\"jointIndex\":" << j->jointIndex << ",\"jacobiIndex\":" << j->jacobiIndex
+      << ",\"constrained\":" << (j->constrained ? "true" : "false")
+      << ",\"ctrlType\":" << j->ctrlType
+      << ",\"prev\":" << (j->prev ? j->prev->jointIndex : -1)
+      << ",\"coupledTo\":" << (j->coupledTo ? j->coupledTo->jointIndex : -1);
+    const char* names[] = {"q0", "q_init", "q_min", "q_max", "weightJL", "weightCA",
+                           "weightMetric", "maxTorque", "speedLimit", "accLimit", "decLimit"};
+    const double vals[] = {j->q0, j->q_init, j->q_min, j->q_max, j->weightJL, j->weightCA,
+                           j->weightMetric, j->maxTorque, j->speedLimit, j->accLimit, j->decLimit};
+    for (int k = 0; k < 11; ++k)
+    {
+      o << ",\"" << names[k] << "\":";
+      putDouble(o, vals[k]);
+    }
+    o << ",\"couplingFactors\":[";
+    if (j->couplingFactors)
+    {
+      for (unsigned int k = 0; k < j->couplingFactors->m * j->couplingFactors->n; ++k)
+      {
+        o << (k ? "," : "");
+        putDouble(o, j->couplingFactors->ele[k]);
+      }
+    }
+    o << "],\"A_JP\":";
+    putHTr(o, j->A_JP);
+    o << "}";
+    firstJ = false;
+  }
+  o << "],\"q\":[";
+  for (unsigned int i = 0; i < graph->dof; ++i)
+  {
+    o << (i ? "," : "");
+    putDouble(o, graph->q->ele[i]);
+  }
+  o << "]}";
+  return strdup(o.str().c_str());
+}
+
+/* FK over a batch. q: N x qdim (qdim == dof or nJ), qd: NULL or N x qdim. Outputs may be
+ * NULL. A_BI: N x nb x 12, A_JI: N x dof x 12, xdot/omega: N x nb x 3, qOut: N x dof. */
+double ref_fk(void* g, long N, int qdim, const double* q, const double* qd, double* A_BI,
+              double* A_JI, double* xdot, double* omega, double* qOut)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    std::vector<RcsBody*> bodies = dfsBodies(graph);
+    const size_t nb = bodies.size();
+    const unsigned int dof = graph->dof;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* qdv = MatNd_create(dof, 1);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
+      if (A_BI)
+      {
+        for (size_t b = 0; b < nb; ++b)
+        {
+          memcpy(A_BI + (i * nb + b) * 12, bodies[b]->A_BI, 12 * sizeof(double));
+        }
+      }
+      if (xdot)
+      {
+        for (size_t b = 0; b < nb; ++b)
+        {
+          memcpy(xdot + (i * nb + b) * 3, bodies[b]->x_dot, 3 * sizeof(double));
+        }
+      }
+      if (omega)
+      {
+        for (size_t b = 0; b < nb; ++b)
+        {
+          memcpy(omega + (i * nb + b) * 3, bodies[b]->omega, 3 * sizeof(double));
+        }
+      }
+      if (A_JI)
+      {
+        RCSGRAPH_TRAVERSE_JOINTS(graph)
+        {
+          memcpy(A_JI + (i * dof + JNT->jointIndex) * 12, &JNT->A_JI, 12 * sizeof(double));
+        }
+      }
+      if (qOut)
+      {
+        memcpy(qOut + i * dof, graph->q->ele, dof * sizeof(double));
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(qdv);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* FK + per-effector translation / rotation Jacobians. effPt: nEff x 3 body-fixed points
+ * or NULL (body origin). JT, JR: N x nEff x 3 x nJ (either may be NULL). A_BI as ref_fk. */
+double ref_fk_jacobians(void* g, long N, int qdim, const double* q, int nEff, const int* effBody,
+                        const double* effPt, double* A_BI, double* JT, double* JR)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    std::vector<RcsBody*> bodies = dfsBodies(graph);
+    const size_t nb = bodies.size();
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* J = MatNd_create(3, nJ);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      if (A_BI)
+      {
+        for (size_t b = 0; b < nb; ++b)
+        {
+          memcpy(A_BI + (i * nb + b) * 12, bodies[b]->A_BI, 12 * sizeof(double));
+        }
+      }
+      for (int e = 0; e < nEff; ++e)
+      {
+        const RcsBody* eb = bodies[effBody[e]];
+        if (JT)
+        {
+          RcsGraph_bodyPointJacobian(graph, eb, effPt ? effPt + 3 * e : NULL, NULL, J);
+          memcpy(JT + ((size_t) i * nEff + e) * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
+        }
+        if (JR)
+        {
+          RcsGraph_rotationJacobian(graph, eb, NULL, J);
+          memcpy(JR + ((size_t) i * nEff + e) * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
+        }
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(J);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* Center of gravity and its Jacobian. cog: N x 3, Jcog: N x 3 x nJ. */
+double ref_cog(void* g, long N, int qdim, const double* q, double* cog, double* Jcog)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* J = MatNd_create(3, nJ);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      if (cog)
+      {
+        RcsGraph_COG(graph, cog + 3 * i);
+      }
+      if (Jcog)
+      {
+        RcsGraph_COGJacobian(graph, J);
+        memcpy(Jcog + (size_t) i * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(J);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* Kinetic terms. M: N x nJ x nJ, h: N x nJ, Fg: N x nJ, E: N (any may be NULL). */
+double ref_kinetic_terms(void* g, long N, int qdim, const double* q, const double* qd,
+                         double* M, double* h, double* Fg, double* E)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* qdv = MatNd_create(dof, 1);
+    MatNd* Mm = MatNd_create(nJ, nJ);
+    MatNd* hm = MatNd_create(nJ, 1);
+    MatNd* gm = MatNd_create(nJ, 1);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
+      double e = RcsGraph_computeKineticTerms(graph, M ? Mm : NULL, h ? hm : NULL, Fg ? gm : NULL);
+      if (M)
+      {
+        memcpy(M + (size_t) i * nJ * nJ, Mm->ele, sizeof(double) * nJ * nJ);
+      }
+      if (h)
+      {
+        memcpy(h + (size_t) i * nJ, hm->ele, sizeof(double) * nJ);
+      }
+      if (Fg)
+      {
+        memcpy(Fg + (size_t) i * nJ, gm->ele, sizeof(double) * nJ);
+      }
+      if (E)
+      {
+        E[i] = e;
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(qdv);
+    MatNd_destroy(Mm);
+    MatNd_destroy(hm);
+    MatNd_destroy(gm);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* Mass matrix through RcsGraph_computeMassMatrix. */
+double ref_mass_matrix(void* g, long N, int qdim, const double* q, double* M)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* Mm = MatNd_create(nJ, nJ);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      RcsGraph_computeMassMatrix(graph, Mm);
+      memcpy(M + (size_t) i * nJ * nJ, Mm->ele, sizeof(double) * nJ * nJ);
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(Mm);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* Joint metric and joint limit gradient (IK state space). invWq: nJ, dH: N x nJ, cost: N. */
+void ref_inv_wq(void* g, double* invWq)
+{
+  RcsGraph* graph = (RcsGraph*) g;
+  MatNd* w = MatNd_create(graph->nJ, 1);
+  RcsGraph_getInvWq(graph, w, RcsStateIK);
+  memcpy(invWq, w->ele, sizeof(double) * graph->nJ);
+  MatNd_destroy(w);
+}
+
+double ref_joint_limit_gradient(void* g, long N, int qdim, const double* q, double* dH,
+                                double* cost)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* d = MatNd_create(1, nJ);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      double c = RcsGraph_jointLimitGradient(graph, d, RcsStateIK);
+      memcpy(dH + (size_t) i * nJ, d->ele, sizeof(double) * nJ);
+      if (cost)
+      {
+        cost[i] = c;
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(d);
+    RcsGraph_destroy(graph);
+  });
+}
+
+/* ---- Controller + IkSolverRMR ------------------------------------------------------- */
+
+/* tasks: newline-free list "XYZ:BallTip;ABC:BallTip" → <Task controlVariable= effector=> */
+void* ref_ik_create(const char* graphFile, const char* taskSpec)
+{
+  std::ostringstream x;
+  x << "<Controller graph=\"" << graphFile << "\">";
+  std::string spec(taskSpec);
+  size_t pos = 0;
+  int k = 0;
+  while (pos < spec.size())
+  {
+    size_t end = spec.find(';', pos);
+    if (end == std::string::npos)
+    {
+      end = spec.size();
+    }
+    std::string item = spec.substr(pos, end - pos);
+    size_t c = item.find(':');
+    if (c != std::string::npos)
+    {
+      x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << item.substr(0, c)
+        << "\" effector=\"" << item.substr(c + 1) << "\" active=\"true\"/>";
+    }
+    pos = end + 1;
+  }
+  x << "</Controller>";
+  IkHandle* h = new IkHandle;
+  h->xml = x.str();
+  h->controller = new Rcs::ControllerBase(h->xml, true);
+  return h;
+}
+
+void ref_ik_destroy(void* ik)
+{
+  IkHandle* h = (IkHandle*) ik;
+  delete h->controller;
+  delete h;
+}
+
+int ref_ik_task_dim(void* ik)
+{
+  return (int) ((IkHandle*) ik)->controller->getTaskDim();
+}
+
+void* ref_ik_graph(void* ik)
+{
+  return ((IkHandle*) ik)->controller->getGraph();
+}
+
+/* Task vector x (N x nx) and stacked task Jacobian (N x nx x nJ) at states q. */
+double ref_ik_task_kinematics(void* ik, long N, int qdim, const double* q, double* x, double* J)
+{
+  IkHandle* h = (IkHandle*) ik;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*h->controller);
+    RcsGraph* graph = c.getGraph();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* xm = MatNd_create(nx, 1);
+    MatNd* Jm = MatNd_create(nx, nJ);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      if (x)
+      {
+        c.computeX(xm);
+        memcpy(x + (size_t) i * nx, xm->ele, sizeof(double) * nx);
+      }
+      if (J)
+      {
+        c.computeJ(Jm);
+        memcpy(J + (size_t) i * nx * nJ, Jm->ele, sizeof(double) * nx * nJ);
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(xm);
+    MatNd_destroy(Jm);
+  });
+}
+
+/*
+ * RMR iterations as in examples/ExampleIK.cpp:154-177.
+ *   q     : N x dof, in: start state, out: state after `iters` steps
+ *   xDes  : N x nx task-space targets
+ *   dxOut : N x nx task error computed in the LAST iteration (before its step), or NULL
+ *   dqOut : N x dof  joint displacement of the LAST iteration, or NULL
+ *   det   : N determinant of (J W J^T + lambda I) in the LAST iteration, or NULL
+ */
+double ref_ik_rmr(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
+                  int iters, double* dxOut, double* dqOut, double* det)
+{
+  IkHandle* h = (IkHandle*) ik;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*h->controller);
+    Rcs::IkSolverRMR solver(&c);
+    RcsGraph* graph = c.getGraph();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* dq = MatNd_create(dof, 1);
+    MatNd* a = MatNd_create(c.getNumberOfTasks(), 1);
+    MatNd* xd = MatNd_create(nx, 1);
+    MatNd* dx = MatNd_create(nx, 1);
+    MatNd* dH = MatNd_create(1, nJ);
+    MatNd_setElementsTo(a, 1.0);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, dof, q + i * dof, NULL);
+      memcpy(xd->ele, xDes + (size_t) i * nx, sizeof(double) * nx);
+      for (int it = 0; it < iters; ++it)
+      {
+        c.computeDX(dx, xd);
+        c.computeJointlimitGradient(dH);
+        MatNd_constMulSelf(dH, alpha);
+        solver.solveRightInverse(dq, dx, dH, a, lambda);
+        MatNd_addSelf(graph->q, dq);
+        RcsGraph_setState(graph, NULL, NULL);
+      }
+      memcpy(q + i * dof, graph->q->ele, sizeof(double) * dof);
+      if (dxOut)
+      {
+        memcpy(dxOut + (size_t) i * nx, dx->ele, sizeof(double) * nx);
+      }
+      if (dqOut)
+      {
+        memcpy(dqOut + (size_t) i * dof, dq->ele, sizeof(double) * dof);
+      }
+      if (det)
+      {
+        det[i] = solver.getDeterminant();
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(dq);
+    MatNd_destroy(a);
+    MatNd_destroy(xd);
+    MatNd_destroy(dx);
+    MatNd_destroy(dH);
+  });
+}
+
+}   // extern "C"

@@ -1,0 +1,30 @@
+"""rcs_b200 — batched rigid-body kinematics / dynamics of HRI-EU/Rcs graphs on B200.
+
+The product is the C library ``rcs_b200/librcsb.so`` (host C loader + hand-written sm_100a
+CUDA kernels behind the C ABI of ``include/rcsb.h``). This package is a thin ctypes binding
+used by the tests and ``bench.py``; it adds no computation of its own and raises if the
+library is missing — there is no Python or CPU fallback for the compute path.
+"""
+from .api import (  # noqa: F401
+    Graph,
+    Model,
+    RcsbError,
+    TASK_ABC,
+    TASK_XYZ,
+    build_library,
+    kernel_launch_count,
+    lib,
+    library_path,
+)
+
+__all__ = [
+    "Graph",
+    "Model",
+    "RcsbError",
+    "TASK_ABC",
+    "TASK_XYZ",
+    "build_library",
+    "kernel_launch_count",
+    "lib",
+    "library_path",
+]

@@ -1,0 +1,386 @@
+"""ctypes binding of ``librcsb.so`` (C ABI: include/rcsb.h, include/rcsb_graph.h).
+
+Mirrors the reference's host interface for the hot path: a ``Graph`` is an ``RcsGraph``
+loaded from the reference's XML files (src/RcsCore/Rcs_graph.c:398), a ``Model`` is its
+flattened device copy, and the methods of ``Model`` are the batched counterparts of
+``RcsGraph_setState`` / ``RcsGraph_bodyPointJacobian`` / ``RcsGraph_rotationJacobian`` /
+``RcsGraph_computeKineticTerms`` / ``IkSolverRMR::solveRightInverse``.
+
+Array arguments may be torch CUDA tensors (device pointers, asynchronous on the current
+torch stream) or numpy arrays (host pointers: the library copies in / out itself).
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+TASK_XYZ = 1
+TASK_ABC = 2
+_HOST_PTRS = 1
+
+
+class RcsbError(RuntimeError):
+    """Raised when a librcsb call returns a non-zero status."""
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "librcsb.so")
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile librcsb.so in-tree (nvcc, sm_100a). Used by __graft_entry__.build()."""
+    res = subprocess.run(
+        ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"],
+        stdout=subprocess.PIPE,
+        stderr=subprocess.STDOUT,
+        text=True,
+    )
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("building librcsb.so failed")
+    return library_path()
+
+
+class _RcsbTask(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("effector", ctypes.c_int)]
+
+
+def lib() -> ctypes.CDLL:
+    """Loads librcsb.so once. Fails loudly if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RcsbError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (rcs_b200 has no fallback implementation)"
+        )
+    L = ctypes.CDLL(path)
+    c_void, c_int, c_long, c_dbl_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p
+
+    def sig(name, restype, *argtypes):
+        fn = getattr(L, name)
+        fn.restype = restype
+        fn.argtypes = list(argtypes)
+
+    sig("RcsGraph_create", c_void, ctypes.c_char_p)
+    sig("RcsGraph_createFromBuffer", c_void, ctypes.c_char_p, ctypes.c_uint)
+    sig("RcsGraph_destroy", None, c_void)
+    sig("RcsGraph_clone", c_void, c_void)
+    sig("RcsGraph_check", ctypes.c_bool, c_void, ctypes.POINTER(c_int), ctypes.POINTER(c_int))
+    sig("RcsGraph_layoutJSON", c_void, c_void)
+    sig("RcsGraph_writeXML", c_int, c_void, ctypes.c_char_p)
+    sig("RcsGraph_numBodies", ctypes.c_uint, c_void)
+    sig("RcsGraph_getBodyByName", c_void, c_void, ctypes.c_char_p)
+    sig("RcsGraph_bodyIndex", c_int, c_void, c_void)
+    sig("RcsGraph_mass", ctypes.c_double, c_void)
+    sig("Rcs_addResourcePath", ctypes.c_bool, ctypes.c_char_p)
+    sig("Rcs_clearResourcePath", None)
+    sig("Rcs_setFatalMode", None, c_int)
+    sig("rcsb_last_error", ctypes.c_char_p)
+    sig("rcsb_device_count", c_int)
+    sig("rcsb_host_alloc", c_void, ctypes.c_size_t)
+    sig("rcsb_host_free", None, c_void)
+    sig("rcsb_kernel_launch_count", ctypes.c_ulonglong)
+    sig("rcsb_model_create", c_int, c_void, c_int, ctypes.POINTER(c_void))
+    sig("rcsb_model_destroy", None, c_void)
+    sig("rcsb_model_dof", c_int, c_void)
+    sig("rcsb_model_nj", c_int, c_void)
+    sig("rcsb_model_nbodies", c_int, c_void)
+    sig("rcsb_fk", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_int, c_void, c_dbl_p,
+        c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_fk_jacobians", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
+        c_int, c_void, c_void, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_kinetic_terms", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+        c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
+        ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("RcsGraph_setState", ctypes.c_bool, c_void, c_void, c_void)
+    sig("MatNd_create", c_void, ctypes.c_uint, ctypes.c_uint)
+    sig("MatNd_destroy", None, c_void)
+    # Contract violations return errors instead of abort()ing the interpreter.
+    L.Rcs_setFatalMode(0)
+    _LIB = L
+    return L
+
+
+def kernel_launch_count() -> int:
+    return int(lib().rcsb_kernel_launch_count())
+
+
+def _err(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().rcsb_last_error()
+        raise RcsbError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+class Graph:
+    """An RcsGraph loaded by librcsb's own XML loader (host only, no GPU needed)."""
+
+    def __init__(self, source: str, _handle: Optional[int] = None):
+        L = lib()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            self._h = L.RcsGraph_create(source.encode())
+        if not self._h:
+            msg = L.rcsb_last_error()
+            raise RcsbError(f"RcsGraph_create({source!r}) failed: {msg.decode() if msg else ''}")
+        self._layout = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.RcsGraph_destroy(h)
+            self._h = None
+
+    @property
+    def handle(self) -> int:
+        return self._h
+
+    def layout(self) -> Dict:
+        if self._layout is None:
+            L = lib()
+            p = L.RcsGraph_layoutJSON(self._h)
+            self._layout = json.loads(ctypes.string_at(p).decode())
+            ctypes.CDLL(None).free(ctypes.c_void_p(p))
+        return self._layout
+
+    @property
+    def dof(self) -> int:
+        return self.layout()["dof"]
+
+    @property
+    def nJ(self) -> int:
+        return self.layout()["nJ"]
+
+    @property
+    def n_bodies(self) -> int:
+        return self.layout()["nBodies"]
+
+    def body_names(self):
+        return [b["name"] for b in self.layout()["bodies"]]
+
+    def body_index(self, name: str) -> int:
+        L = lib()
+        b = L.RcsGraph_getBodyByName(self._h, name.encode())
+        if not b:
+            raise KeyError(name)
+        return L.RcsGraph_bodyIndex(self._h, b)
+
+    def clone(self) -> "Graph":
+        return Graph("", _handle=lib().RcsGraph_clone(self._h))
+
+    def check(self):
+        ne, nw = ctypes.c_int(0), ctypes.c_int(0)
+        ok = lib().RcsGraph_check(self._h, ctypes.byref(ne), ctypes.byref(nw))
+        return bool(ok), ne.value, nw.value
+
+    def mass(self) -> float:
+        return float(lib().RcsGraph_mass(self._h))
+
+    def write_xml(self, path: str) -> None:
+        if lib().RcsGraph_writeXML(self._h, path.encode()) != 0:
+            raise RcsbError(f"RcsGraph_writeXML({path!r}) failed")
+
+
+def _is_torch(x) -> bool:
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+class _Args:
+    """Collects pointers for one call and decides host vs device mode."""
+
+    def __init__(self, model: "Model"):
+        self.model = model
+        self.mode = None  # "device" | "host"
+        self.keep = []
+
+    def ptr(self, x, name: str):
+        if x is None:
+            return None
+        if _is_torch(x):
+            import torch
+
+            if x.dtype != torch.float64 or not x.is_contiguous():
+                raise RcsbError(f"{name}: need a contiguous float64 tensor")
+            if x.is_cuda:
+                if x.device.index != self.model.device:
+                    raise RcsbError(f"{name}: tensor is on {x.device}, model on cuda:{self.model.device}")
+                self._set("device", name)
+            else:
+                self._set("host", name)
+            self.keep.append(x)
+            return ctypes.c_void_p(x.data_ptr())
+        a = x
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise RcsbError(f"{name}: need a C-contiguous float64 numpy array")
+        self._set("host", name)
+        self.keep.append(a)
+        return ctypes.c_void_p(a.ctypes.data)
+
+    def _set(self, mode: str, name: str):
+        if self.mode is None:
+            self.mode = mode
+        elif self.mode != mode:
+            raise RcsbError(f"{name}: host and device arrays mixed in one call")
+
+    def flags(self) -> int:
+        return _HOST_PTRS if self.mode == "host" else 0
+
+    def stream(self):
+        if self.mode == "device":
+            import torch
+
+            return ctypes.c_void_p(torch.cuda.current_stream(self.model.device).cuda_stream)
+        return None
+
+
+def _int_array(values: Optional[Iterable[int]]):
+    if values is None:
+        return None, 0
+    v = list(values)
+    arr = (ctypes.c_int * max(len(v), 1))(*v)
+    return arr, len(v)
+
+
+class Model:
+    """Flattened, device-resident copy of a Graph (immutable)."""
+
+    def __init__(self, graph: Graph, device: int = 0):
+        L = lib()
+        h = ctypes.c_void_p()
+        _err(L.rcsb_model_create(graph.handle, device, ctypes.byref(h)), "rcsb_model_create")
+        self._h = h
+        self.device = device
+        self.dof = L.rcsb_model_dof(h)
+        self.nJ = L.rcsb_model_nj(h)
+        self.n_bodies = L.rcsb_model_nbodies(h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.rcsb_model_destroy(h)
+            self._h = None
+
+    # -- helpers -------------------------------------------------------------------------
+    def _alloc(self, like, shape):
+        if _is_torch(like):
+            import torch
+
+            return torch.empty(shape, dtype=torch.float64, device=like.device)
+        return np.empty(shape, dtype=np.float64)
+
+    @staticmethod
+    def _batch(q):
+        if q.ndim != 2:
+            raise RcsbError("q must be N x qdim")
+        return int(q.shape[0]), int(q.shape[1])
+
+    # -- forward kinematics --------------------------------------------------------------
+    def fk(self, q, qd=None, bodies: Optional[Sequence[int]] = None, want=("A_BI",), out=None):
+        """RcsGraph_setState over a batch. want ⊆ {A_BI, A_JI, xdot, omega, q}."""
+        N, qdim = self._batch(q)
+        nsel = self.n_bodies if bodies is None else len(bodies)
+        shapes = {
+            "A_BI": (N, nsel, 12),
+            "A_JI": (N, self.dof, 12),
+            "xdot": (N, nsel, 3),
+            "omega": (N, nsel, 3),
+            "q": (N, self.dof),
+        }
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        a = _Args(self)
+        sel, ns = _int_array(bodies)
+        rc = lib().rcsb_fk(
+            self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), ns, sel,
+            a.ptr(out.get("A_BI"), "A_BI"), a.ptr(out.get("A_JI"), "A_JI"),
+            a.ptr(out.get("xdot"), "xdot"), a.ptr(out.get("omega"), "omega"),
+            a.ptr(out.get("q"), "q_out"), a.flags(), a.stream(),
+        )
+        _err(rc, "rcsb_fk")
+        return out
+
+    def fk_jacobians(self, q, effectors: Sequence[int], points=None,
+                     bodies: Optional[Sequence[int]] = None, want=("A_BI", "JT", "JR"), out=None):
+        """FK + RcsGraph_bodyPointJacobian / RcsGraph_rotationJacobian per effector."""
+        N, qdim = self._batch(q)
+        nsel = self.n_bodies if bodies is None else len(bodies)
+        neff = len(effectors)
+        shapes = {"A_BI": (N, nsel, 12), "JT": (N, neff, 3, self.nJ), "JR": (N, neff, 3, self.nJ)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        a = _Args(self)
+        sel, ns = _int_array(bodies)
+        eff, ne = _int_array(effectors)
+        pts = None
+        if points is not None:
+            pa = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(neff, 3))
+            a.keep.append(pa)
+            pts = ctypes.c_void_p(pa.ctypes.data)
+        rc = lib().rcsb_fk_jacobians(
+            self._h, N, qdim, a.ptr(q, "q"), ns, sel, a.ptr(out.get("A_BI"), "A_BI"), ne, eff, pts,
+            a.ptr(out.get("JT"), "JT"), a.ptr(out.get("JR"), "JR"), a.flags(), a.stream(),
+        )
+        _err(rc, "rcsb_fk_jacobians")
+        return out
+
+    # -- dynamics ------------------------------------------------------------------------
+    def kinetic_terms(self, q, qd=None, want=("M", "h", "Fg", "E"), out=None):
+        """RcsGraph_computeKineticTerms over a batch."""
+        N, qdim = self._batch(q)
+        shapes = {"M": (N, self.nJ, self.nJ), "h": (N, self.nJ), "Fg": (N, self.nJ), "E": (N,)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        a = _Args(self)
+        rc = lib().rcsb_kinetic_terms(
+            self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), a.ptr(out.get("M"), "M"),
+            a.ptr(out.get("h"), "h"), a.ptr(out.get("Fg"), "Fg"), a.ptr(out.get("E"), "E"),
+            a.flags(), a.stream(),
+        )
+        _err(rc, "rcsb_kinetic_terms")
+        return out
+
+    # -- inverse kinematics --------------------------------------------------------------
+    def ik_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1,
+               want=("det",), out=None):
+        """`iters` IkSolverRMR::solveRightInverse steps per state; q is updated in place.
+
+        tasks: sequence of (TASK_XYZ | TASK_ABC, effector body index).
+        """
+        N, qdim = self._batch(q)
+        if qdim != self.dof:
+            raise RcsbError("ik_rmr: q must be N x dof")
+        nx = 3 * len(tasks)
+        shapes = {"dx": (N, nx), "dq": (N, self.dof), "det": (N,)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        tarr = (_RcsbTask * max(len(tasks), 1))(*[_RcsbTask(int(k), int(e)) for k, e in tasks])
+        a = _Args(self)
+        rc = lib().rcsb_ik_rmr(
+            self._h, len(tasks), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam),
+            float(alpha), int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"),
+            a.ptr(out.get("det"), "det"), a.flags(), a.stream(),
+        )
+        _err(rc, "rcsb_ik_rmr")
+        return out

@@ -1,0 +1,686 @@
+/*
+ * C ABI of rcs_b200 (include/rcsb.h): models, query plans, launches, host-buffer staging.
+ *
+ * This layer contains no kinematics: it validates shapes, flattens/uploads models, builds
+ * the small per-query plans the kernels read, and enqueues the kernels of rcsb_fk.cu,
+ * rcsb_kinetic.cu and rcsb_ik.cu. If there is no CUDA device every compute entry point
+ * fails with RCSB_ENODEVICE — there is deliberately no host implementation to fall back to.
+ */
+#include "rcsb.h"
+#include "rcsb_internal.h"
+#include "rcsb_kernels.h"
+#include "rcsb_model.h"
+#include "rcsb_plan.h"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+extern "C" int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut);
+
+namespace
+{
+
+std::atomic<unsigned long long> g_launches(0);
+
+struct DevicePlan
+{
+  char* dev = nullptr;
+  int bytes = 0;
+  int nScrRows = 0;
+  int nSel = 0;
+  int nEff = 0;
+  int aux0 = 0;
+  int aux1 = 0;
+};
+
+/* double-buffered device workspace of the RCSB_HOST_PTRS path */
+struct StagePipe
+{
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  char* buf[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+};
+
+}   // namespace
+
+struct RcsbModel
+{
+  int device = 0;
+  std::vector<char> host;        /* flat model blob */
+  char* dev = nullptr;
+  RcsbFlatHeader hdr;
+  std::mutex mtx;                /* guards the plan caches and the staging pipe */
+  std::map<std::string, DevicePlan> fkPlans;
+  std::map<std::string, DevicePlan> ikPlans;
+  DevicePlan ktPlan;
+  bool ktPlanBuilt = false;
+  double* ktScratch = nullptr;
+  size_t ktScratchDoubles = 0;
+  StagePipe pipe;
+
+  const int* iarr(int a) const
+  {
+    return reinterpret_cast<const int*>(host.data() + hdr.off[a]);
+  }
+  const double* darr(int a) const
+  {
+    return reinterpret_cast<const double*>(host.data() + hdr.off[a]);
+  }
+};
+
+namespace
+{
+
+int cudaFail(cudaError_t e, const char* what)
+{
+  rcsb_set_error("%s: %s", what, cudaGetErrorString(e));
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+  {
+    return RCSB_ENODEVICE;
+  }
+  return RCSB_ECUDA;
+}
+
+#define RCSB_CUDA(call)                     \
+  do                                        \
+  {                                         \
+    cudaError_t e_ = (call);                \
+    if (e_ != cudaSuccess)                  \
+    {                                       \
+      return cudaFail(e_, #call);           \
+    }                                       \
+  } while (0)
+
+int align16(int x)
+{
+  return (x + 15) & ~15;
+}
+
+/* ---- FK plan ---------------------------------------------------------------------------- */
+
+int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int* effBody,
+                const double* effPt, const DevicePlan** out)
+{
+  const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
+
+  if (nSel < 0 || nEff < 0 || (nSel > 0 && !bodySel) || (nEff > 0 && !effBody))
+  {
+    rcsb_set_error("invalid body / effector selection");
+    return RCSB_EINVAL;
+  }
+  for (int i = 0; i < nSel; ++i)
+  {
+    if (bodySel[i] < 0 || bodySel[i] >= nb)
+    {
+      rcsb_set_error("bodySel[%d] = %d out of range [0, %d)", i, bodySel[i], nb);
+      return RCSB_EINVAL;
+    }
+  }
+  for (int i = 0; i < nEff; ++i)
+  {
+    if (effBody[i] < 0 || effBody[i] >= nb)
+    {
+      rcsb_set_error("effBody[%d] = %d out of range [0, %d)", i, effBody[i], nb);
+      return RCSB_EINVAL;
+    }
+  }
+
+  std::string key;
+  key.append(reinterpret_cast<const char*>(&nSel), sizeof(int));
+  key.append(reinterpret_cast<const char*>(&nEff), sizeof(int));
+  if (nSel > 0)
+  {
+    key.append(reinterpret_cast<const char*>(bodySel), sizeof(int) * nSel);
+  }
+  if (nEff > 0)
+  {
+    key.append(reinterpret_cast<const char*>(effBody), sizeof(int) * nEff);
+    if (effPt)
+    {
+      key.append(reinterpret_cast<const char*>(effPt), sizeof(double) * 3 * nEff);
+    }
+  }
+
+  std::lock_guard<std::mutex> lock(m->mtx);
+  auto it = m->fkPlans.find(key);
+  if (it != m->fkPlans.end())
+  {
+    *out = &it->second;
+    return RCSB_OK;
+  }
+
+  const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* jntFlags = m->iarr(RCSB_A_JNT_FLAGS);
+  const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
+
+  /* output slots: a body selected several times keeps its first slot only */
+  const int nOut = (nSel == 0) ? nb : nSel;
+  std::vector<int> bodyOut(nb, -1);
+  if (nSel == 0)
+  {
+    for (int b = 0; b < nb; ++b)
+    {
+      bodyOut[b] = b;
+    }
+  }
+  else
+  {
+    for (int i = 0; i < nSel; ++i)
+    {
+      if (bodyOut[bodySel[i]] >= 0)
+      {
+        rcsb_set_error("body %d selected twice", bodySel[i]);
+        return RCSB_EINVAL;
+      }
+      bodyOut[bodySel[i]] = i;
+    }
+  }
+
+  /* scratch slots for unconstrained joints on effector chains */
+  std::vector<int> jntScr(dof, -1);
+  int nChain = 0;
+  for (int e = 0; e < nEff; ++e)
+  {
+    for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
+    {
+      if (jntJacobi[j] >= 0 && jntScr[j] < 0)
+      {
+        jntScr[j] = nChain++;
+      }
+    }
+  }
+  if (nChain > 0xffff || nEff > 2047)
+  {
+    rcsb_set_error("too many chain joints / effectors");
+    return RCSB_EUNSUPPORTED;
+  }
+
+  const int rec = nEff * 3 * nJ;
+  std::vector<int> jtab(rec > 0 ? rec : 1, -1);
+  for (int e = 0; e < nEff; ++e)
+  {
+    for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
+    {
+      const int col = jntJacobi[j];
+      if (col < 0)
+      {
+        continue;
+      }
+      for (int r = 0; r < 3; ++r)
+      {
+        jtab[(e * 3 + r) * nJ + col] =
+          jntScr[j] | (r << 16) | ((jntFlags[j] & RCSB_JF_ROT) ? (1 << 18) : 0) | (e << 20);
+      }
+    }
+  }
+
+  std::vector<int> effStart(nb + 1, 0), effList(nEff > 0 ? nEff : 1, 0);
+  for (int e = 0; e < nEff; ++e)
+  {
+    effStart[effBody[e] + 1]++;
+  }
+  for (int b = 0; b < nb; ++b)
+  {
+    effStart[b + 1] += effStart[b];
+  }
+  {
+    std::vector<int> fill(effStart.begin(), effStart.end() - 1);
+    for (int e = 0; e < nEff; ++e)
+    {
+      effList[fill[effBody[e]]++] = e;
+    }
+  }
+
+  RcsbFkPlanHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.nSel = nOut;
+  ph.nEff = nEff;
+  ph.nChain = nChain;
+  ph.nScrRows = (nEff > 0) ? 6 * nChain + 3 * nEff : 0;
+  ph.jacRecord = rec;
+  ph.invJacRecord = rec > 0 ? 1.0f / (float) rec : 0.0f;
+  int off = align16((int) sizeof(ph));
+  ph.offBodyOut = off;
+  off = align16(off + nb * 4);
+  ph.offJntScr = off;
+  off = align16(off + dof * 4);
+  ph.offBodyEffStart = off;
+  off = align16(off + (nb + 1) * 4);
+  ph.offBodyEffList = off;
+  off = align16(off + (int) effList.size() * 4);
+  ph.offEffPt = off;
+  off = align16(off + (nEff > 0 ? nEff : 1) * 24);
+  ph.offJTab = off;
+  off = align16(off + (int) jtab.size() * 4);
+  ph.totalBytes = off;
+
+  std::vector<char> blob(ph.totalBytes, 0);
+  memcpy(blob.data(), &ph, sizeof(ph));
+  memcpy(blob.data() + ph.offBodyOut, bodyOut.data(), nb * 4);
+  memcpy(blob.data() + ph.offJntScr, jntScr.data(), dof * 4);
+  memcpy(blob.data() + ph.offBodyEffStart, effStart.data(), (nb + 1) * 4);
+  memcpy(blob.data() + ph.offBodyEffList, effList.data(), effList.size() * 4);
+  if (nEff > 0 && effPt)
+  {
+    memcpy(blob.data() + ph.offEffPt, effPt, sizeof(double) * 3 * nEff);
+  }
+  memcpy(blob.data() + ph.offJTab, jtab.data(), jtab.size() * 4);
+
+  DevicePlan dp;
+  RCSB_CUDA(cudaSetDevice(m->device));
+  RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
+  RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  dp.bytes = ph.totalBytes;
+  dp.nScrRows = ph.nScrRows;
+  dp.nSel = nOut;
+  dp.nEff = nEff;
+
+  auto ins = m->fkPlans.emplace(key, dp);
+  *out = &ins.first->second;
+  return RCSB_OK;
+}
+
+/* ---- staging pipe for host-pointer calls ------------------------------------------------- */
+
+int pipeReserve(RcsbModel* m, int slot, size_t bytes)
+{
+  StagePipe& p = m->pipe;
+  if (!p.stream[slot])
+  {
+    RCSB_CUDA(cudaStreamCreateWithFlags(&p.stream[slot], cudaStreamNonBlocking));
+  }
+  if (p.cap[slot] < bytes)
+  {
+    if (p.buf[slot])
+    {
+      RCSB_CUDA(cudaFree(p.buf[slot]));
+      p.buf[slot] = nullptr;
+      p.cap[slot] = 0;
+    }
+    RCSB_CUDA(cudaMalloc(&p.buf[slot], bytes));
+    p.cap[slot] = bytes;
+  }
+  return RCSB_OK;
+}
+
+struct Carver
+{
+  char* base;
+  size_t off = 0;
+  explicit Carver(char* b) : base(b) {}
+  double* take(size_t doubles)
+  {
+    double* p = reinterpret_cast<double*>(base + off);
+    off += (doubles * sizeof(double) + 255) & ~(size_t) 255;
+    return p;
+  }
+};
+
+size_t carveBytes(size_t doubles)
+{
+  return (doubles * sizeof(double) + 255) & ~(size_t) 255;
+}
+
+int checkModel(const RcsbModel* m, long N, int qdim, const double* q)
+{
+  if (!m)
+  {
+    rcsb_set_error("model is NULL");
+    return RCSB_EINVAL;
+  }
+  if (N < 0 || (N > 0 && !q))
+  {
+    rcsb_set_error("invalid batch: N = %ld, q = %p", N, (const void*) q);
+    return RCSB_EINVAL;
+  }
+  if (qdim != m->hdr.dof && qdim != m->hdr.nJ)
+  {
+    /* the reference aborts here: "q has wrong dimensions" (Rcs_graph.c:250) */
+    rcsb_set_error("q has wrong dimensions: qdim = %d, dof is %d, nJ is %d", qdim, m->hdr.dof,
+                   m->hdr.nJ);
+    return RCSB_EINVAL;
+  }
+  return RCSB_OK;
+}
+
+/* FK (+ Jacobians) on device pointers */
+int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const double* q,
+             const double* qd, double* A_BI, double* A_JI, double* xdot, double* omega,
+             double* qOut, double* JT, double* JR, cudaStream_t stream)
+{
+  rcsb::FkArgs a;
+  a.model = m->dev;
+  a.plan = plan->dev;
+  a.modelBytes = m->hdr.totalBytes;
+  a.planBytes = plan->bytes;
+  a.N = N;
+  a.qdim = qdim;
+  a.q = q;
+  a.qd = qd;
+  a.A_BI = A_BI;
+  a.A_JI = A_JI;
+  a.xdot = xdot;
+  a.omega = omega;
+  a.qOut = qOut;
+  a.JT = JT;
+  a.JR = JR;
+  RCSB_CUDA(cudaSetDevice(m->device));
+  RCSB_CUDA(rcsb_launch_fk(&a, m->hdr.nSlots, plan->nScrRows, stream));
+  if (N > 0)
+  {
+    g_launches.fetch_add(1);
+  }
+  return RCSB_OK;
+}
+
+const long kStageChunk = 1L << 16;   /* states per pipeline stage of the host-pointer path */
+
+}   // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+/* utilities                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+extern "C" const char* rcsb_last_error(void)
+{
+  return rcsb_error_string();
+}
+
+extern "C" int rcsb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" void* rcsb_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+  {
+    cudaGetLastError();
+    rcsb_set_error("cudaHostAlloc of %zu bytes failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void rcsb_host_free(void* p)
+{
+  if (p)
+  {
+    cudaFreeHost(p);
+  }
+}
+
+extern "C" unsigned long long rcsb_kernel_launch_count(void)
+{
+  return g_launches.load();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* model                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+extern "C" int rcsb_model_create(const RcsGraph* graph, int device, RcsbModel** out)
+{
+  if (!graph || !out)
+  {
+    rcsb_set_error("rcsb_model_create: NULL argument");
+    return RCSB_EINVAL;
+  }
+  *out = nullptr;
+
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  if (e != cudaSuccess || nDev == 0)
+  {
+    cudaGetLastError();
+    rcsb_set_error("no CUDA device available (%s); rcs_b200 has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return RCSB_ENODEVICE;
+  }
+  if (device < 0 || device >= nDev)
+  {
+    rcsb_set_error("device %d out of range [0, %d)", device, nDev);
+    return RCSB_EINVAL;
+  }
+
+  void* blob = nullptr;
+  size_t bytes = 0;
+  if (rcsb_flatten(graph, &blob, &bytes) != 0)
+  {
+    return RCSB_EINVAL;
+  }
+
+  RcsbModel* m = new RcsbModel;
+  m->device = device;
+  m->host.assign(static_cast<char*>(blob), static_cast<char*>(blob) + bytes);
+  free(blob);
+  memcpy(&m->hdr, m->host.data(), sizeof(RcsbFlatHeader));
+
+  if (m->hdr.nSlots > RCSB_MAX_FRAME_SLOTS)
+  {
+    rcsb_set_error("tree needs %d parent-frame slots, at most %d supported", m->hdr.nSlots,
+                   RCSB_MAX_FRAME_SLOTS);
+    delete m;
+    return RCSB_EUNSUPPORTED;
+  }
+
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce == cudaSuccess)
+  {
+    ce = cudaMalloc(&m->dev, bytes);
+  }
+  if (ce == cudaSuccess)
+  {
+    ce = cudaMemcpy(m->dev, m->host.data(), bytes, cudaMemcpyHostToDevice);
+  }
+  if (ce != cudaSuccess)
+  {
+    delete m;
+    return cudaFail(ce, "model upload");
+  }
+
+  *out = m;
+  return RCSB_OK;
+}
+
+extern "C" void rcsb_model_destroy(RcsbModel* m)
+{
+  if (!m)
+  {
+    return;
+  }
+  cudaSetDevice(m->device);
+  for (auto& kv : m->fkPlans)
+  {
+    cudaFree(kv.second.dev);
+  }
+  for (auto& kv : m->ikPlans)
+  {
+    cudaFree(kv.second.dev);
+  }
+  cudaFree(m->ktPlan.dev);
+  cudaFree(m->ktScratch);
+  for (int i = 0; i < 2; ++i)
+  {
+    if (m->pipe.buf[i])
+    {
+      cudaFree(m->pipe.buf[i]);
+    }
+    if (m->pipe.stream[i])
+    {
+      cudaStreamDestroy(m->pipe.stream[i]);
+    }
+  }
+  cudaFree(m->dev);
+  delete m;
+}
+
+extern "C" int rcsb_model_dof(const RcsbModel* m)
+{
+  return m ? m->hdr.dof : -1;
+}
+
+extern "C" int rcsb_model_nj(const RcsbModel* m)
+{
+  return m ? m->hdr.nJ : -1;
+}
+
+extern "C" int rcsb_model_nbodies(const RcsbModel* m)
+{
+  return m ? m->hdr.nb : -1;
+}
+
+extern "C" int rcsb_model_device(const RcsbModel* m)
+{
+  return m ? m->device : -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* forward kinematics + Jacobians                                                              */
+/* ------------------------------------------------------------------------------------------ */
+
+static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
+                    int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
+                    double* omega, double* qOut, int nEff, const int* effBody,
+                    const double* effPt, double* JT, double* JR, unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  int rc = checkModel(m, N, qdim, q);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  if ((xdot || omega) && !qd)
+  {
+    rcsb_set_error("xdot / omega requested without q_dot");
+    return RCSB_EINVAL;
+  }
+  if ((JT || JR) && nEff <= 0)
+  {
+    rcsb_set_error("Jacobians requested without effectors");
+    return RCSB_EINVAL;
+  }
+
+  const DevicePlan* plan = nullptr;
+  rc = buildFkPlan(m, nSel, bodySel, (JT || JR) ? nEff : 0, effBody, effPt, &plan);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  if (N == 0)
+  {
+    return RCSB_OK;
+  }
+
+  if (!(flags & RCSB_HOST_PTRS))
+  {
+    return fkDevice(m, plan, N, qdim, q, qd, A_BI, A_JI, xdot, omega, qOut, JT, JR,
+                    static_cast<cudaStream_t>(stream));
+  }
+
+  /* host pointers: chunks alternate between two streams so that the copies of one chunk
+   * overlap the kernel of the other */
+  const int dof = m->hdr.dof, nOut = plan->nSel;
+  const size_t recJ = (size_t) plan->nEff * 3 * m->hdr.nJ;
+  std::lock_guard<std::mutex> lock(m->mtx);
+  RCSB_CUDA(cudaSetDevice(m->device));
+
+  const long chunk = N < kStageChunk ? N : kStageChunk;
+  size_t need = carveBytes((size_t) chunk * qdim) * (qd ? 2 : 1);
+  need += A_BI ? carveBytes((size_t) chunk * nOut * 12) : 0;
+  need += A_JI ? carveBytes((size_t) chunk * dof * 12) : 0;
+  need += xdot ? carveBytes((size_t) chunk * nOut * 3) : 0;
+  need += omega ? carveBytes((size_t) chunk * nOut * 3) : 0;
+  need += qOut ? carveBytes((size_t) chunk * dof) : 0;
+  need += JT ? carveBytes((size_t) chunk * recJ) : 0;
+  need += JR ? carveBytes((size_t) chunk * recJ) : 0;
+
+  int slot = 0;
+  for (long s0 = 0; s0 < N; s0 += chunk, slot ^= 1)
+  {
+    const long n = (N - s0 < chunk) ? (N - s0) : chunk;
+    rc = pipeReserve(m, slot, need);
+    if (rc != RCSB_OK)
+    {
+      return rc;
+    }
+    cudaStream_t st = m->pipe.stream[slot];
+    Carver cv(m->pipe.buf[slot]);
+    double* dq = cv.take((size_t) chunk * qdim);
+    double* dqd = qd ? cv.take((size_t) chunk * qdim) : nullptr;
+    double* dA = A_BI ? cv.take((size_t) chunk * nOut * 12) : nullptr;
+    double* dAJ = A_JI ? cv.take((size_t) chunk * dof * 12) : nullptr;
+    double* dxd = xdot ? cv.take((size_t) chunk * nOut * 3) : nullptr;
+    double* dom = omega ? cv.take((size_t) chunk * nOut * 3) : nullptr;
+    double* dqo = qOut ? cv.take((size_t) chunk * dof) : nullptr;
+    double* dJT = JT ? cv.take((size_t) chunk * recJ) : nullptr;
+    double* dJR = JR ? cv.take((size_t) chunk * recJ) : nullptr;
+
+    RCSB_CUDA(cudaMemcpyAsync(dq, q + s0 * qdim, sizeof(double) * n * qdim,
+                              cudaMemcpyHostToDevice, st));
+    if (qd)
+    {
+      RCSB_CUDA(cudaMemcpyAsync(dqd, qd + s0 * qdim, sizeof(double) * n * qdim,
+                                cudaMemcpyHostToDevice, st));
+    }
+    rc = fkDevice(m, plan, n, qdim, dq, dqd, dA, dAJ, dxd, dom, dqo, dJT, dJR, st);
+    if (rc != RCSB_OK)
+    {
+      return rc;
+    }
+#define RCSB_D2H(hostPtr, devPtr, perState)                                                   \
+  if (hostPtr)                                                                                \
+  {                                                                                           \
+    RCSB_CUDA(cudaMemcpyAsync(hostPtr + (size_t) s0 * (perState), devPtr,                     \
+                              sizeof(double) * (size_t) n * (perState), cudaMemcpyDeviceToHost, \
+                              st));                                                           \
+  }
+    RCSB_D2H(A_BI, dA, (size_t) nOut * 12)
+    RCSB_D2H(A_JI, dAJ, (size_t) dof * 12)
+    RCSB_D2H(xdot, dxd, (size_t) nOut * 3)
+    RCSB_D2H(omega, dom, (size_t) nOut * 3)
+    RCSB_D2H(qOut, dqo, (size_t) dof)
+    RCSB_D2H(JT, dJT, recJ)
+    RCSB_D2H(JR, dJR, recJ)
+#undef RCSB_D2H
+  }
+  for (int i = 0; i < 2; ++i)
+  {
+    if (m->pipe.stream[i])
+    {
+      RCSB_CUDA(cudaStreamSynchronize(m->pipe.stream[i]));
+    }
+  }
+  return RCSB_OK;
+}
+
+extern "C" int rcsb_fk(const RcsbModel* model, long N, int qdim, const double* q,
+                       const double* qd, int nSel, const int* bodySel, double* A_BI,
+                       double* A_JI, double* xdot, double* omega, double* qOut, unsigned flags,
+                       void* stream)
+{
+  return fkCommon(model, N, qdim, q, qd, nSel, bodySel, A_BI, A_JI, xdot, omega, qOut, 0,
+                  nullptr, nullptr, nullptr, nullptr, flags, stream);
+}
+
+extern "C" int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q,
+                                 int nSel, const int* bodySel, double* A_BI, int nEff,
+                                 const int* effBody, const double* effPt, double* JT,
+                                 double* JR, unsigned flags, void* stream)
+{
+  return fkCommon(model, N, qdim, q, nullptr, nSel, bodySel, A_BI, nullptr, nullptr, nullptr,
+                  nullptr, nEff, effBody, effPt, JT, JR, flags, stream);
+}

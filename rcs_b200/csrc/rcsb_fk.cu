@@ -1,0 +1,419 @@
+/*
+ * Batched forward kinematics + world-point / rotation Jacobians for sm_100a.
+ *
+ * What it computes, per state (reference, one state per call on one RcsGraph):
+ *   RcsGraph_setState / RcsGraph_internalBodyKinematics   src/RcsCore/Rcs_graph.c:61-296
+ *   RcsGraph_bodyPointJacobian / worldPointJacobian       src/RcsCore/Rcs_kinematics.c:80-215
+ *   RcsGraph_rotationJacobian                             src/RcsCore/Rcs_kinematics.c:416-458
+ *
+ * How: one thread per state walks the flattened tree depth first. The walk is the same for
+ * every state, so all model reads are warp-uniform shared-memory broadcasts and there is no
+ * divergence. The running frame lives in registers; a body whose parent is not the body
+ * visited just before reloads the parent frame from a small per-thread frame stack (only
+ * bodies with several children are parked there). Body frames leave as three 32-byte
+ * stores per frame (STG.E.256: full sectors, nothing to merge). Joint axes and origins on
+ * an effector's chain are parked in padded shared memory; once the walk is over the warp
+ * turns them into Jacobian elements cooperatively, so that the 3 x nJ rows of 32
+ * consecutive states leave as one contiguous, fully coalesced stream.
+ *
+ * Bound: HBM (output stream); see DESIGN.md for the byte counts.
+ */
+#include "rcsb_device.cuh"
+#include "rcsb_kernels.h"
+#include "rcsb_plan.h"
+
+namespace rcsb
+{
+
+struct PlanView
+{
+  const RcsbFkPlanHeader* hdr;
+  const int* bodyOut;
+  const int* jntScr;
+  const int* bodyEffStart;
+  const int* bodyEffList;
+  const double* effPt;
+  const int* jtab;
+
+  __device__ __forceinline__ void bind(const char* blob)
+  {
+    hdr = reinterpret_cast<const RcsbFkPlanHeader*>(blob);
+    bodyOut = reinterpret_cast<const int*>(blob + hdr->offBodyOut);
+    jntScr = reinterpret_cast<const int*>(blob + hdr->offJntScr);
+    bodyEffStart = reinterpret_cast<const int*>(blob + hdr->offBodyEffStart);
+    bodyEffList = reinterpret_cast<const int*>(blob + hdr->offBodyEffList);
+    effPt = reinterpret_cast<const double*>(blob + hdr->offEffPt);
+    jtab = reinterpret_cast<const int*>(blob + hdr->offJTab);
+  }
+};
+
+template <bool VEL, bool ALIGNED32, int NSLOTS>
+__global__ void __launch_bounds__(RCSB_FK_THREADS)
+fkKernel(const FkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  double* scr = reinterpret_cast<double*>(sPlan + a.planBytes);
+
+  stageBlob(sModel, a.model, a.modelBytes);
+  stageBlob(sPlan, a.plan, a.planBytes);
+  __syncthreads();
+
+  ModelView m;
+  m.bind(sModel);
+  PlanView p;
+  p.bind(sPlan);
+
+  const int tid = threadIdx.x;
+  const int scrStride = RCSB_FK_THREADS + 1;   /* odd stride: conflict-free transposed reads */
+  const long s = (long) blockIdx.x * RCSB_FK_THREADS + tid;
+  const bool active = s < a.N;
+  const long sc = active ? s : a.N - 1;        /* idle lanes shadow the last state, no stores */
+
+  const int nb = m.hdr->nb;
+  const int dof = m.hdr->dof;
+  const int nSel = p.hdr->nSel;
+  const int nChain = p.hdr->nChain;
+
+  StateReader rd;
+  rd.full = (a.qdim == dof);
+  rd.q = a.q + sc * a.qdim;
+  rd.qd = VEL ? a.qd + sc * a.qdim : nullptr;
+
+  constexpr int SLOT_DOUBLES = VEL ? 18 : 12;
+  double stk[NSLOTS * SLOT_DOUBLES];
+
+  Frame f;
+  double xd[3] = {0.0, 0.0, 0.0};
+  double om[3] = {0.0, 0.0, 0.0};
+  setIdentity(f);
+
+  for (int b = 0; b < nb; ++b)
+  {
+    /* ---- parent frame ---------------------------------------------------------------- */
+    const int ld = m.bodyLoad[b];
+    if (ld == RCSB_LOAD_IDENT)
+    {
+      setIdentity(f);
+      if (VEL)
+      {
+        xd[0] = xd[1] = xd[2] = 0.0;
+        om[0] = om[1] = om[2] = 0.0;
+      }
+    }
+    else if (ld >= 0)
+    {
+      const double* sp = stk + ld * SLOT_DOUBLES;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        f.o[i] = sp[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        f.R[i] = sp[3 + i];
+      }
+      if (VEL)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          xd[i] = sp[12 + i];
+          om[i] = sp[15 + i];
+        }
+      }
+    }
+
+    double op[3], w[3], c[3], vt[3];
+    if (VEL)
+    {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        op[i] = f.o[i];
+        w[i] = c[i] = vt[i] = 0.0;
+      }
+    }
+
+    /* ---- joints of the body ------------------------------------------------------------ */
+    const int j0 = m.bodyJntStart[b];
+    const int j1 = j0 + m.bodyJntCount[b];
+    for (int j = j0; j < j1; ++j)
+    {
+      const int jf = m.jntFlags[j];
+      if (jf & RCSB_JF_HAS_AJP)
+      {
+        applyRel(f, m.jntAJP + 12 * j);
+      }
+
+      const double qj = rd.jointQ(m, j);
+      const int dir = m.jntType[j] % 3;
+      double ax[3];
+
+      if (jf & RCSB_JF_ROT)
+      {
+        double sn, cs;
+        sincos(qj, &sn, &cs);
+        rotateAboutAxis(f, dir, sn, cs);
+        axisOf(f, dir, ax);
+      }
+      else
+      {
+        axisOf(f, dir, ax);
+        f.o[0] += qj * ax[0];
+        f.o[1] += qj * ax[1];
+        f.o[2] += qj * ax[2];
+      }
+
+      if (VEL)
+      {
+        /* x_dot += sum_trans a qd + sum_rot (a qd) x (r_b - o_j), omega += sum_rot a qd;
+         * r_b is only known after the last joint, so the cross products are split into
+         * w x r_b - sum (a qd) x o_j. */
+        const double qdj = rd.jointQd(m, j);
+        const double aq[3] = {ax[0] * qdj, ax[1] * qdj, ax[2] * qdj};
+        if (jf & RCSB_JF_ROT)
+        {
+          double t[3];
+          cross3(t, aq, f.o);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            w[i] += aq[i];
+            c[i] += t[i];
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            vt[i] += aq[i];
+          }
+        }
+      }
+
+      if (a.qOut && active)
+      {
+        a.qOut[s * dof + j] = qj;
+      }
+      if (a.A_JI && active)
+      {
+        storeFrame<ALIGNED32>(a.A_JI + (s * dof + j) * 12, f);
+      }
+
+      const int slot = p.jntScr[j];
+      if (slot >= 0)
+      {
+        double* col = scr + (6 * slot) * scrStride + tid;
+        col[0] = ax[0];
+        col[scrStride] = ax[1];
+        col[2 * scrStride] = ax[2];
+        col[3 * scrStride] = f.o[0];
+        col[4 * scrStride] = f.o[1];
+        col[5 * scrStride] = f.o[2];
+      }
+    }
+
+    /* ---- body frame ---------------------------------------------------------------------- */
+    if (m.bodyFlags[b] & RCSB_BF_HAS_ABP)
+    {
+      applyRel(f, m.bodyABP + 12 * b);
+    }
+
+    if (VEL)
+    {
+      if (ld != RCSB_LOAD_IDENT)
+      {
+        const double d[3] = {f.o[0] - op[0], f.o[1] - op[1], f.o[2] - op[2]};
+        double t[3];
+        cross3(t, om, d);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          xd[i] += t[i];
+        }
+      }
+      double t[3];
+      cross3(t, w, f.o);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        xd[i] += vt[i] + (t[i] - c[i]);
+        om[i] += w[i];
+      }
+    }
+
+    const int sv = m.bodySave[b];
+    if (sv >= 0)
+    {
+      double* sp = stk + sv * SLOT_DOUBLES;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        sp[i] = f.o[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        sp[3 + i] = f.R[i];
+      }
+      if (VEL)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          sp[12 + i] = xd[i];
+          sp[15 + i] = om[i];
+        }
+      }
+    }
+
+    const int out = p.bodyOut[b];
+    if (out >= 0 && active)
+    {
+      if (a.A_BI)
+      {
+        storeFrame<ALIGNED32>(a.A_BI + (s * nSel + out) * 12, f);
+      }
+      if (VEL)
+      {
+        if (a.xdot)
+        {
+          double* d = a.xdot + (s * nSel + out) * 3;
+          d[0] = xd[0]; d[1] = xd[1]; d[2] = xd[2];
+        }
+        if (a.omega)
+        {
+          double* d = a.omega + (s * nSel + out) * 3;
+          d[0] = om[0]; d[1] = om[1]; d[2] = om[2];
+        }
+      }
+    }
+
+    /* effector points attached to this body: I_p = o + R^T B_p */
+    for (int k = p.bodyEffStart[b]; k < p.bodyEffStart[b + 1]; ++k)
+    {
+      const int e = p.bodyEffList[k];
+      const double* pt = p.effPt + 3 * e;
+      double* col = scr + (6 * nChain + 3 * e) * scrStride + tid;
+      col[0] = f.o[0] + (f.R[0] * pt[0] + f.R[3] * pt[1] + f.R[6] * pt[2]);
+      col[scrStride] = f.o[1] + (f.R[1] * pt[0] + f.R[4] * pt[1] + f.R[7] * pt[2]);
+      col[2 * scrStride] = f.o[2] + (f.R[2] * pt[0] + f.R[5] * pt[1] + f.R[8] * pt[2]);
+    }
+  }
+
+  /* ---- Jacobians: warp-cooperative, coalesced ------------------------------------------- */
+  const int rec = p.hdr->jacRecord;
+  if (rec > 0 && (a.JT || a.JR))
+  {
+    __syncwarp();
+    const int lane = tid & 31;
+    const long w0 = s - lane;                      /* first state of this warp */
+    long nv = a.N - w0;
+    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+    const int total = (int) nv * rec;
+    const float invRec = p.hdr->invJacRecord;
+    const double* scrWarp = scr + (tid - lane);
+    double* JTw = a.JT ? a.JT + w0 * rec : nullptr;
+    double* JRw = a.JR ? a.JR + w0 * rec : nullptr;
+
+    for (int e = lane; e < total; e += 32)
+    {
+      const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
+      const int rem = e - sl * rec;
+      const int t = p.jtab[rem];
+      double vT = 0.0, vR = 0.0;
+      if (t >= 0)
+      {
+        const int slot = RCSB_JTAB_SLOT(t);
+        const int r = RCSB_JTAB_ROW(t);
+        const double* col = scrWarp + sl;
+        const double* ja = col + (6 * slot) * scrStride;
+        if (RCSB_JTAB_ISROT(t))
+        {
+          /* column = axis x (I_p - joint origin), component r */
+          const int r1 = r == 2 ? 0 : r + 1;
+          const int r2 = r == 0 ? 2 : r - 1;
+          const double* pe = col + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride;
+          const double a1 = ja[r1 * scrStride], a2 = ja[r2 * scrStride];
+          const double d1 = pe[r1 * scrStride] - ja[(3 + r1) * scrStride];
+          const double d2 = pe[r2 * scrStride] - ja[(3 + r2) * scrStride];
+          vT = a1 * d2 - a2 * d1;
+          vR = ja[r * scrStride];
+        }
+        else
+        {
+          vT = ja[r * scrStride];
+        }
+      }
+      if (JTw)
+      {
+        JTw[e] = vT;
+      }
+      if (JRw)
+      {
+        JRw[e] = vR;
+      }
+    }
+  }
+}
+
+template <bool VEL, bool ALIGNED32>
+static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t smemBytes,
+                               cudaStream_t stream)
+{
+#define RCSB_LAUNCH(NS)                                                                        \
+  {                                                                                            \
+    auto k = fkKernel<VEL, ALIGNED32, NS>;                                                     \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, RCSB_FK_THREADS, smemBytes, stream>>>(a);                                        \
+    return cudaGetLastError();                                                                 \
+  }
+  if (nSlots <= 1)
+  {
+    RCSB_LAUNCH(1)
+  }
+  else if (nSlots <= 4)
+  {
+    RCSB_LAUNCH(4)
+  }
+  else
+  {
+    RCSB_LAUNCH(RCSB_MAX_FRAME_SLOTS)
+  }
+#undef RCSB_LAUNCH
+}
+
+}   // namespace rcsb
+
+extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows,
+                                      cudaStream_t stream)
+{
+  using namespace rcsb;
+  if (a->N <= 0)
+  {
+    return cudaSuccess;
+  }
+  const size_t smemBytes = (size_t) a->modelBytes + (size_t) a->planBytes +
+                           (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double);
+  const dim3 grid((unsigned int) ((a->N + RCSB_FK_THREADS - 1) / RCSB_FK_THREADS));
+  const bool vel = (a->qd != nullptr);
+  const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &
+                   31u) == 0;
+
+  if (vel)
+  {
+    return al ? launchSlots<true, true>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<true, false>(*a, nSlots, grid, smemBytes, stream);
+  }
+  return al ? launchSlots<false, true>(*a, nSlots, grid, smemBytes, stream)
+            : launchSlots<false, false>(*a, nSlots, grid, smemBytes, stream);
+}

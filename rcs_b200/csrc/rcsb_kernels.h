@@ -1,0 +1,79 @@
+/*
+ * Kernel argument blocks and launch entry points (host <-> .cu translation units).
+ */
+#ifndef RCSB_KERNELS_H
+#define RCSB_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#define RCSB_FK_THREADS 128
+#define RCSB_MAX_FRAME_SLOTS 8
+#define RCSB_KT_THREADS 64
+#define RCSB_IK_THREADS 128
+
+namespace rcsb
+{
+
+struct FkArgs
+{
+  const char* model;   /* device flat model */
+  const char* plan;    /* device FK plan */
+  int modelBytes;
+  int planBytes;
+  long N;
+  int qdim;
+  const double* q;
+  const double* qd;
+  double* A_BI;
+  double* A_JI;
+  double* xdot;
+  double* omega;
+  double* qOut;
+  double* JT;
+  double* JR;
+};
+
+struct KtArgs
+{
+  const char* model;
+  const char* plan;    /* kinetic-terms plan (joint relation table, link slots) */
+  int modelBytes;
+  int planBytes;
+  long N;
+  int qdim;
+  const double* q;
+  const double* qd;
+  double* M;
+  double* h;
+  double* Fg;
+  double* E;
+  double* scratch;     /* per-thread workspace in global memory (L2 resident) */
+  long scratchStride;  /* doubles between consecutive workspace elements = threads in flight */
+};
+
+struct IkArgs
+{
+  const char* model;
+  const char* plan;    /* IK plan: tasks, chains, joint metric */
+  int modelBytes;
+  int planBytes;
+  long N;
+  double* q;           /* N x dof in/out */
+  const double* xDes;  /* N x nx */
+  double lambda;
+  double alpha;
+  int iters;
+  double* dx;
+  double* dq;
+  double* det;
+};
+
+}   // namespace rcsb
+
+extern "C" {
+cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cudaStream_t stream);
+cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, cudaStream_t stream);
+cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, cudaStream_t stream);
+}
+
+#endif

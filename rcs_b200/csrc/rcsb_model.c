@@ -1,0 +1,266 @@
+/*
+ * Flattener: RcsGraph -> flat model blob (rcsb_model.h).
+ *
+ * Besides copying parameters into depth-first arrays it precomputes what the kernels would
+ * otherwise have to chase pointers for:
+ *  - where each body finds its parent frame during a depth-first walk (registers if the
+ *    parent was visited just before, else a slot of a small per-state frame stack) and
+ *    which bodies must park their frame in such a slot (bodies with more than one child);
+ *  - the backward joint chain of every body (RcsBody_lastJointBeforeBody + jnt->prev,
+ *    src/RcsCore/Rcs_body.c:1706, Rcs_graph.c:2604-2655) as integer links.
+ */
+#include "rcsb_internal.h"
+#include "rcsb_model.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+static int alignUp8(int x)
+{
+  return (x + 7) & ~7;
+}
+
+int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
+{
+  if (!graph || !blobOut || !bytesOut)
+  {
+    rcsb_set_error("rcsb_flatten: NULL argument");
+    return -1;
+  }
+
+  const int nb = (int) RcsGraph_numBodies(graph);
+  const int dof = (int) graph->dof;
+
+  RcsBody** bodies = (RcsBody**) calloc((size_t) nb + 1, sizeof(RcsBody*));
+  int nCpl = 0, k = 0;
+  RCSGRAPH_TRAVERSE_BODIES(graph)
+  {
+    bodies[k++] = BODY;
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      if (JNT->coupledTo)
+      {
+        nCpl++;
+      }
+    }
+  }
+
+  /* layout */
+  RcsbFlatHeader hdr;
+  memset(&hdr, 0, sizeof(hdr));
+  hdr.nb = nb;
+  hdr.dof = dof;
+  hdr.nJ = (int) graph->nJ;
+  hdr.nCpl = nCpl;
+
+  int sizes[RCSB_A_COUNT];
+  for (int a = 0; a < RCSB_A_COUNT; ++a)
+  {
+    if (a <= RCSB_A_BODY_LASTJNT)
+    {
+      sizes[a] = nb * (int) sizeof(int);
+    }
+    else if (a <= RCSB_A_JNT_BODY)
+    {
+      sizes[a] = dof * (int) sizeof(int);
+    }
+    else
+    {
+      sizes[a] = 0;
+    }
+  }
+  sizes[RCSB_A_BODY_ABP] = nb * 12 * (int) sizeof(double);
+  sizes[RCSB_A_BODY_MASS] = nb * (int) sizeof(double);
+  sizes[RCSB_A_BODY_COM] = nb * 3 * (int) sizeof(double);
+  sizes[RCSB_A_BODY_INERTIA] = nb * 9 * (int) sizeof(double);
+  sizes[RCSB_A_JNT_AJP] = dof * 12 * (int) sizeof(double);
+  for (int a = RCSB_A_JNT_QREF; a <= RCSB_A_JNT_WMETRIC; ++a)
+  {
+    sizes[a] = dof * (int) sizeof(double);
+  }
+  sizes[RCSB_A_CPL] = nCpl * (int) sizeof(RcsbCoupling);
+
+  int off = alignUp8((int) sizeof(RcsbFlatHeader));
+  for (int a = 0; a < RCSB_A_COUNT; ++a)
+  {
+    hdr.off[a] = off;
+    off = alignUp8(off + sizes[a]);
+  }
+  hdr.totalBytes = alignUp8(off + 8);   /* multiple of 16 for vector copies */
+  hdr.totalBytes = (hdr.totalBytes + 15) & ~15;
+
+  char* blob = (char*) calloc(1, (size_t) hdr.totalBytes);
+#define IARR(a) ((int*) (blob + hdr.off[a]))
+#define DARR(a) ((double*) (blob + hdr.off[a]))
+
+  int* nChildren = (int*) calloc((size_t) nb + 1, sizeof(int));
+  int* slotOf = (int*) calloc((size_t) nb + 1, sizeof(int));
+  int* branchDepth = (int*) calloc((size_t) nb + 1, sizeof(int));
+  int nSlots = 0;
+
+  for (int b = 0; b < nb; ++b)
+  {
+    const int p = RcsGraph_bodyIndex(graph, bodies[b]->parent);
+    IARR(RCSB_A_BODY_PARENT)[b] = p;
+    if (p >= 0)
+    {
+      nChildren[p]++;
+    }
+  }
+
+  /* frame-stack slots: a body with several children parks its frame at the depth given by
+   * the number of branching ancestors, which a depth-first walk uses like a stack */
+  for (int b = 0; b < nb; ++b)
+  {
+    const int p = IARR(RCSB_A_BODY_PARENT)[b];
+    const int inherited = p >= 0 ? branchDepth[p] : 0;
+    if (nChildren[b] >= 2)
+    {
+      slotOf[b] = inherited;
+      branchDepth[b] = inherited + 1;
+      if (branchDepth[b] > nSlots)
+      {
+        nSlots = branchDepth[b];
+      }
+    }
+    else
+    {
+      slotOf[b] = -1;
+      branchDepth[b] = inherited;
+    }
+  }
+  hdr.nSlots = nSlots;
+
+  int ci = 0;
+  for (int b = 0; b < nb; ++b)
+  {
+    const RcsBody* B = bodies[b];
+    const int p = IARR(RCSB_A_BODY_PARENT)[b];
+    int flags = 0;
+
+    IARR(RCSB_A_BODY_SAVE)[b] = slotOf[b];
+    if (p < 0)
+    {
+      IARR(RCSB_A_BODY_LOAD)[b] = RCSB_LOAD_IDENT;
+    }
+    else if (p == b - 1)
+    {
+      IARR(RCSB_A_BODY_LOAD)[b] = RCSB_LOAD_CONT;
+    }
+    else
+    {
+      IARR(RCSB_A_BODY_LOAD)[b] = slotOf[p];
+    }
+
+    double* abp = DARR(RCSB_A_BODY_ABP) + 12 * b;
+    if (B->A_BP)
+    {
+      flags |= RCSB_BF_HAS_ABP;
+      memcpy(abp, B->A_BP, sizeof(HTr));
+    }
+    else
+    {
+      abp[3] = abp[7] = abp[11] = 1.0;
+    }
+
+    if (B->m != 0.0)
+    {
+      flags |= RCSB_BF_HAS_MASS;
+      hdr.nMassive++;
+    }
+    DARR(RCSB_A_BODY_MASS)[b] = B->m;
+    if (B->Inertia)
+    {
+      memcpy(DARR(RCSB_A_BODY_COM) + 3 * b, B->Inertia->org, 3 * sizeof(double));
+      memcpy(DARR(RCSB_A_BODY_INERTIA) + 9 * b, B->Inertia->rot, 9 * sizeof(double));
+    }
+    IARR(RCSB_A_BODY_FLAGS)[b] = flags;
+
+    const RcsJoint* last = RcsBody_lastJointBeforeBody(B);
+    IARR(RCSB_A_BODY_LASTJNT)[b] = last ? last->jointIndex : -1;
+
+    IARR(RCSB_A_BODY_JNT_START)[b] = B->jnt ? B->jnt->jointIndex : 0;
+    int cnt = 0;
+    for (const RcsJoint* J = B->jnt; J; J = J->next)
+    {
+      const int j = J->jointIndex;
+      if (j != IARR(RCSB_A_BODY_JNT_START)[b] + cnt || j < 0 || j >= dof)
+      {
+        rcsb_set_error("rcsb_flatten: joints of body \"%s\" are not contiguous in jointIndex "
+                       "order (call RcsGraph_makeJointsConsistent first)", B->name);
+        free(blob);
+        free(bodies);
+        free(nChildren);
+        free(slotOf);
+        free(branchDepth);
+        return -1;
+      }
+      cnt++;
+
+      int jf = 0;
+      IARR(RCSB_A_JNT_TYPE)[j] = J->type;
+      if (J->type <= RCSJOINT_ROT_Z)
+      {
+        jf |= RCSB_JF_ROT;
+      }
+      if (J->constrained)
+      {
+        jf |= RCSB_JF_CONSTRAINED;
+      }
+      double* ajp = DARR(RCSB_A_JNT_AJP) + 12 * j;
+      if (J->A_JP)
+      {
+        jf |= RCSB_JF_HAS_AJP;
+        memcpy(ajp, J->A_JP, sizeof(HTr));
+      }
+      else
+      {
+        ajp[3] = ajp[7] = ajp[11] = 1.0;
+      }
+      IARR(RCSB_A_JNT_FLAGS)[j] = jf;
+      IARR(RCSB_A_JNT_JACOBI)[j] = J->jacobiIndex;
+      IARR(RCSB_A_JNT_PREV)[j] = J->prev ? J->prev->jointIndex : -1;
+      IARR(RCSB_A_JNT_BODY)[j] = b;
+      IARR(RCSB_A_JNT_CPL)[j] = -1;
+
+      DARR(RCSB_A_JNT_QREF)[j] = graph->q->ele[j];
+      DARR(RCSB_A_JNT_Q0)[j] = J->q0;
+      DARR(RCSB_A_JNT_QMIN)[j] = J->q_min;
+      DARR(RCSB_A_JNT_QMAX)[j] = J->q_max;
+      DARR(RCSB_A_JNT_WJL)[j] = J->weightJL;
+      DARR(RCSB_A_JNT_WMETRIC)[j] = J->weightMetric;
+
+      if (J->coupledTo)
+      {
+        RcsbCoupling* c = ((RcsbCoupling*) (blob + hdr.off[RCSB_A_CPL])) + ci;
+        IARR(RCSB_A_JNT_CPL)[j] = ci++;
+        c->slave = j;
+        c->master = J->coupledTo->jointIndex;
+        c->nCoef = (int) J->couplingFactors->size;
+        for (int i = 0; i < c->nCoef && i < 9; ++i)
+        {
+          c->coef[i] = J->couplingFactors->ele[i];
+        }
+        c->sQInit = J->q_init;
+        c->sQMin = J->q_min;
+        c->sQMax = J->q_max;
+        c->mQInit = J->coupledTo->q_init;
+        c->mQMin = J->coupledTo->q_min;
+        c->mQMax = J->coupledTo->q_max;
+      }
+    }
+    IARR(RCSB_A_BODY_JNT_COUNT)[b] = cnt;
+  }
+#undef IARR
+#undef DARR
+
+  memcpy(blob, &hdr, sizeof(hdr));
+  *blobOut = blob;
+  *bytesOut = (size_t) hdr.totalBytes;
+
+  free(bodies);
+  free(nChildren);
+  free(slotOf);
+  free(branchDepth);
+  return 0;
+}
