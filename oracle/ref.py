@@ -1,0 +1,245 @@
+"""ctypes wrapper of oracle/_ref/librcsref.so — the UNMODIFIED reference (HRI-EU/Rcs RcsCore)
+compiled by oracle/ref_build/Makefile, driven one state at a time.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py. Nothing under rcs_b200/ may import this module.
+
+Every function returns exactly what the reference functions produce (see the citations in
+oracle/ref_build/ref_api.cpp); this is the anchor the numpy restatement (oracle/rcs_oracle.py)
+and the CUDA path are pinned against.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "_ref", "librcsref.so")
+
+
+def available() -> bool:
+    return os.path.exists(library_path())
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(library_path())
+        vp, ci, cl, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_double
+        L.ref_graph_create.restype = vp
+        L.ref_graph_create.argtypes = [ctypes.c_char_p]
+        L.ref_graph_destroy.argtypes = [vp]
+        L.ref_graph_layout_json.restype = vp
+        L.ref_graph_layout_json.argtypes = [vp]
+        L.ref_free.argtypes = [vp]
+        for n in ("ref_graph_dof", "ref_graph_nj", "ref_graph_nbodies"):
+            getattr(L, n).restype = ci
+            getattr(L, n).argtypes = [vp]
+        L.ref_body_index.restype = ci
+        L.ref_body_index.argtypes = [vp, ctypes.c_char_p]
+        L.ref_graph_check.restype = ci
+        L.ref_graph_check.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.ref_fk.restype = cd
+        L.ref_fk.argtypes = [vp, cl, ci] + [vp] * 7
+        L.ref_fk_jacobians.restype = cd
+        L.ref_fk_jacobians.argtypes = [vp, cl, ci, vp, ci, vp, vp, vp, vp, vp]
+        L.ref_cog.restype = cd
+        L.ref_cog.argtypes = [vp, cl, ci, vp, vp, vp]
+        L.ref_kinetic_terms.restype = cd
+        L.ref_kinetic_terms.argtypes = [vp, cl, ci] + [vp] * 6
+        L.ref_mass_matrix.restype = cd
+        L.ref_mass_matrix.argtypes = [vp, cl, ci, vp, vp]
+        L.ref_inv_wq.argtypes = [vp, vp]
+        L.ref_joint_limit_gradient.restype = cd
+        L.ref_joint_limit_gradient.argtypes = [vp, cl, ci, vp, vp, vp]
+        L.ref_ik_create.restype = vp
+        L.ref_ik_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        L.ref_ik_destroy.argtypes = [vp]
+        L.ref_ik_task_dim.restype = ci
+        L.ref_ik_task_dim.argtypes = [vp]
+        L.ref_ik_graph.restype = vp
+        L.ref_ik_graph.argtypes = [vp]
+        L.ref_ik_task_kinematics.restype = cd
+        L.ref_ik_task_kinematics.argtypes = [vp, cl, ci, vp, vp, vp]
+        L.ref_ik_rmr.restype = cd
+        L.ref_ik_rmr.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
+        L.ref_set_threads.argtypes = [ci]
+        L.ref_set_log_level.argtypes = [ci]
+        _LIB = L
+    return _LIB
+
+
+def set_threads(n: int) -> None:
+    lib().ref_set_threads(int(n))
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class RefGraph:
+    """RcsGraph created by the reference's own loader (src/RcsCore/Rcs_graph.c:398)."""
+
+    def __init__(self, xml_file: str, _handle=None, _owner=None):
+        L = lib()
+        self._owner = _owner
+        self._h = _handle if _handle is not None else L.ref_graph_create(xml_file.encode())
+        if not self._h:
+            raise RuntimeError(f"reference failed to load {xml_file}")
+        self.dof = L.ref_graph_dof(self._h)
+        self.nJ = L.ref_graph_nj(self._h)
+        self.n_bodies = L.ref_graph_nbodies(self._h)
+        self.last_seconds = 0.0
+
+    def layout(self) -> dict:
+        L = lib()
+        p = L.ref_graph_layout_json(self._h)
+        s = ctypes.string_at(p).decode()
+        L.ref_free(p)
+        return json.loads(s)
+
+    def body_index(self, name: str) -> int:
+        return lib().ref_body_index(self._h, name.encode())
+
+    def check(self):
+        ne, nw = ctypes.c_int(0), ctypes.c_int(0)
+        ok = lib().ref_graph_check(self._h, ctypes.byref(ne), ctypes.byref(nw))
+        return bool(ok), ne.value, nw.value
+
+    # RcsGraph_setState (Rcs_graph.c:231)
+    def fk(self, q, qd=None, want=("A_BI",)):
+        q = _c(q)
+        qd = None if qd is None else _c(qd)
+        N, qdim = q.shape
+        out = {}
+        if "A_BI" in want:
+            out["A_BI"] = np.empty((N, self.n_bodies, 12))
+        if "A_JI" in want:
+            out["A_JI"] = np.empty((N, self.dof, 12))
+        if "xdot" in want:
+            out["xdot"] = np.empty((N, self.n_bodies, 3))
+        if "omega" in want:
+            out["omega"] = np.empty((N, self.n_bodies, 3))
+        if "q" in want:
+            out["q"] = np.empty((N, self.dof))
+        self.last_seconds = lib().ref_fk(
+            self._h, N, qdim, _p(q), _p(qd), _p(out.get("A_BI")), _p(out.get("A_JI")),
+            _p(out.get("xdot")), _p(out.get("omega")), _p(out.get("q")))
+        return out
+
+    # + RcsGraph_bodyPointJacobian / RcsGraph_rotationJacobian (Rcs_kinematics.c:200, :416)
+    def fk_jacobians(self, q, effectors: Sequence[int], points=None, want=("A_BI", "JT", "JR")):
+        q = _c(q)
+        N, qdim = q.shape
+        ne = len(effectors)
+        eff = (ctypes.c_int * max(ne, 1))(*effectors)
+        pts = None if points is None else _c(np.asarray(points).reshape(ne, 3))
+        out = {}
+        if "A_BI" in want:
+            out["A_BI"] = np.empty((N, self.n_bodies, 12))
+        if "JT" in want:
+            out["JT"] = np.empty((N, ne, 3, self.nJ))
+        if "JR" in want:
+            out["JR"] = np.empty((N, ne, 3, self.nJ))
+        self.last_seconds = lib().ref_fk_jacobians(
+            self._h, N, qdim, _p(q), ne, eff, _p(pts), _p(out.get("A_BI")), _p(out.get("JT")),
+            _p(out.get("JR")))
+        return out
+
+    def cog(self, q):
+        q = _c(q)
+        N, qdim = q.shape
+        cog = np.empty((N, 3))
+        J = np.empty((N, 3, self.nJ))
+        self.last_seconds = lib().ref_cog(self._h, N, qdim, _p(q), _p(cog), _p(J))
+        return cog, J
+
+    # RcsGraph_computeKineticTerms (Rcs_dynamics.c:439)
+    def kinetic_terms(self, q, qd=None, want=("M", "h", "Fg", "E")):
+        q = _c(q)
+        qd = None if qd is None else _c(qd)
+        N, qdim = q.shape
+        out = {}
+        if "M" in want:
+            out["M"] = np.empty((N, self.nJ, self.nJ))
+        if "h" in want:
+            out["h"] = np.empty((N, self.nJ))
+        if "Fg" in want:
+            out["Fg"] = np.empty((N, self.nJ))
+        if "E" in want:
+            out["E"] = np.empty((N,))
+        self.last_seconds = lib().ref_kinetic_terms(
+            self._h, N, qdim, _p(q), _p(qd), _p(out.get("M")), _p(out.get("h")),
+            _p(out.get("Fg")), _p(out.get("E")))
+        return out
+
+    def mass_matrix(self, q):
+        q = _c(q)
+        N, qdim = q.shape
+        M = np.empty((N, self.nJ, self.nJ))
+        self.last_seconds = lib().ref_mass_matrix(self._h, N, qdim, _p(q), _p(M))
+        return M
+
+    def inv_wq(self):
+        w = np.empty((self.nJ,))
+        lib().ref_inv_wq(self._h, _p(w))
+        return w
+
+    def joint_limit_gradient(self, q):
+        q = _c(q)
+        N, qdim = q.shape
+        dH = np.empty((N, self.nJ))
+        cost = np.empty((N,))
+        lib().ref_joint_limit_gradient(self._h, N, qdim, _p(q), _p(dH), _p(cost))
+        return dH, cost
+
+
+class RefIk:
+    """ControllerBase + IkSolverRMR of the reference with XYZ / ABC tasks, all active."""
+
+    def __init__(self, graph_file: str, tasks: Sequence):
+        """tasks: sequence of ("XYZ" | "ABC", effector body name)."""
+        L = lib()
+        spec = ";".join(f"{k}:{e}" for k, e in tasks)
+        self._h = L.ref_ik_create(graph_file.encode(), spec.encode())
+        if not self._h:
+            raise RuntimeError("reference controller creation failed")
+        self.nx = L.ref_ik_task_dim(self._h)
+        self.graph = RefGraph("", _handle=L.ref_ik_graph(self._h), _owner=self)
+        self.last_seconds = 0.0
+
+    def task_kinematics(self, q):
+        q = _c(q)
+        N, qdim = q.shape
+        x = np.empty((N, self.nx))
+        J = np.empty((N, self.nx, self.graph.nJ))
+        lib().ref_ik_task_kinematics(self._h, N, qdim, _p(q), _p(x), _p(J))
+        return x, J
+
+    def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1):
+        """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp."""
+        q = _c(q).copy()
+        x_des = _c(x_des)
+        N = q.shape[0]
+        dx = np.empty((N, self.nx))
+        dq = np.empty((N, self.graph.dof))
+        det = np.empty((N,))
+        self.last_seconds = lib().ref_ik_rmr(
+            self._h, N, _p(q), _p(x_des), float(lam), float(alpha), int(iters), _p(dx), _p(dq),
+            _p(det))
+        return q, dx, dq, det

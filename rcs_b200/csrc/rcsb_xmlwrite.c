@@ -75,7 +75,9 @@ static void putJoint(FILE* f, const RcsJoint* j)
   }
   else
   {
-    double r[3] = {j->q_min, j->q0, j->q_max};
+    /* q_init is the range centre of the file; q0 differs from it only through a
+     * model_state, which is written at the end of the file */
+    double r[3] = {j->q_min, j->q_init, j->q_max};
     if (rot)
     {
       for (int i = 0; i < 3; ++i)
@@ -152,7 +154,7 @@ int RcsGraph_writeXML(const RcsGraph* self, const char* fileName)
   }
 
   static const char* physNames[4] = {"none", "kinematic", "dynamic", "fixed"};
-  fprintf(f, "<Graph>\n\n");
+  fprintf(f, "<Graph name=\"rcsb_export\" >\n\n");
 
   RCSGRAPH_TRAVERSE_BODIES(self)
   {
@@ -195,7 +197,7 @@ int RcsGraph_writeXML(const RcsGraph* self, const char* fileName)
       {
         if (k < 6)
         {
-          q[k] = k >= 3 ? exactDegrees(JNT->q0) : JNT->q0;
+          q[k] = k >= 3 ? exactDegrees(JNT->q_init) : JNT->q_init;
           w[k] = JNT->weightMetric;
           unitWeights = unitWeights && (w[k] == 1.0);
         }
@@ -229,6 +231,22 @@ int RcsGraph_writeXML(const RcsGraph* self, const char* fileName)
     }
     fprintf(f, "\n");
   }
+
+  /* joints whose centre was moved by a model_state (src/RcsCore/Rcs_graphParser.c:55-140):
+   * q0 is restored the same way; slaves follow their master on load */
+  fprintf(f, "  <model_state model=\"rcsb_export\" time_stamp=\"\" >\n");
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      if (!JNT->coupledTo && JNT->q0 != JNT->q_init)
+      {
+        fprintf(f, "    <joint_state joint=\"%s\" position=\"%.17g\" />\n", JNT->name,
+                RcsJoint_isRotation(JNT) ? exactDegrees(JNT->q0) : JNT->q0);
+      }
+    }
+  }
+  fprintf(f, "  </model_state>\n\n");
 
   fprintf(f, "</Graph>\n");
   fclose(f);

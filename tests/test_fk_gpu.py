@@ -1,0 +1,122 @@
+"""GPU parity: batched FK / Jacobians through the C ABI vs the reference library.
+
+Reference calls: RcsGraph_setState (Rcs_graph.c:231), RcsGraph_bodyPointJacobian
+(Rcs_kinematics.c:200), RcsGraph_rotationJacobian (Rcs_kinematics.c:416).
+Tolerance: 1e-12 relative to the array's inf-norm (floor 1), as BASELINE.json states.
+"""
+import numpy as np
+import pytest
+
+import rcs_b200
+from rcs_b200 import workload
+from conftest import GRAPHS, assert_close, assert_structural_zeros, graph_file
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(name, refmod, cuda_device):
+    g = rcs_b200.Graph(graph_file(name))
+    return g, rcs_b200.Model(g, cuda_device), refmod.RefGraph(graph_file(name))
+
+
+@pytest.mark.parametrize("name", GRAPHS)
+def test_fk_all_bodies_host_pointers(name, refmod, cuda_device):
+    g, m, r = _models(name, refmod, cuda_device)
+    q, qd = workload.sample_states(g.layout(), 777, with_velocity=True)
+    ours = m.fk(q, qd, want=("A_BI", "A_JI", "xdot", "omega", "q"))
+    ref = r.fk(q, qd, want=("A_BI", "A_JI", "xdot", "omega", "q"))
+    for k in ("A_BI", "A_JI", "xdot", "omega", "q"):
+        assert_close(ours[k], ref[k], what=f"{name}:{k}")
+
+
+@pytest.mark.parametrize("name", ["wam_arm", "wam_scenario", "humanoid"])
+def test_fk_ik_state_vector(name, refmod, cuda_device):
+    """q of size nJ is expanded like RcsGraph_stateVectorFromIK (Rcs_graph.c:628)."""
+    g, m, r = _models(name, refmod, cuda_device)
+    lay = g.layout()
+    q = workload.sample_states(lay, 300)
+    cols = [j["jointIndex"] for j in lay["joints"] if j["jacobiIndex"] >= 0]
+    q_ik = np.ascontiguousarray(q[:, cols])
+    ours = m.fk(q_ik, want=("A_BI", "q"))
+    ref = r.fk(q_ik, want=("A_BI", "q"))
+    assert_close(ours["A_BI"], ref["A_BI"], what=f"{name}:A_BI")
+    assert_close(ours["q"], ref["q"], what=f"{name}:q")
+
+
+@pytest.mark.parametrize("name,effs", [
+    ("wam_arm", ["BallTip"]),
+    ("wam_scenario", ["Hand", "PowerGrip", "Base"]),
+    ("humanoid", ["RightHandTip", "LeftHandTip", "Helmet", "FootL"]),
+    ("dexbot", None),
+    ("husky", None),
+])
+def test_fk_jacobians_device_pointers(name, effs, refmod, cuda_device):
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    if effs is None:
+        effs = [g.body_names()[-1], g.body_names()[len(g.body_names()) // 2]]
+    eff = [g.body_index(e) for e in effs]
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-0.2, 0.2, size=(len(eff), 3))
+    q = workload.sample_states(g.layout(), 1000 + 17)
+    qd_dev = torch.from_numpy(q).to(f"cuda:{cuda_device}")
+    ours = m.fk_jacobians(qd_dev, eff, points=pts)
+    torch.cuda.synchronize()
+    ref = r.fk_jacobians(q, eff, points=pts)
+    for k in ("A_BI", "JT", "JR"):
+        o = ours[k].cpu().numpy()
+        assert_close(o, ref[k], what=f"{name}:{k}")
+        if k != "A_BI":
+            assert_structural_zeros(o, ref[k], what=f"{name}:{k}")
+
+
+def test_body_selection_and_origin_points(refmod, cuda_device):
+    g, m, r = _models("humanoid", refmod, cuda_device)
+    sel = [g.body_index(n) for n in ("RightHandTip", "UpperBody", "FootR")]
+    q = workload.sample_states(g.layout(), 129)
+    ours = m.fk_jacobians(q, [sel[0]], bodies=sel)
+    ref = r.fk_jacobians(q, [sel[0]])
+    assert_close(ours["A_BI"], ref["A_BI"][:, sel, :], what="selected frames")
+    assert_close(ours["JT"], ref["JT"], what="JT at body origin")
+    assert_close(ours["JR"], ref["JR"], what="JR")
+
+
+def test_empty_and_ragged_batches(refmod, cuda_device):
+    g, m, r = _models("wam_arm", refmod, cuda_device)
+    eff = [g.body_index("BallTip")]
+    assert m.fk(np.empty((0, g.dof)))["A_BI"].shape == (0, g.n_bodies, 12)
+    for n in (1, 31, 33, 127, 129):
+        q = workload.sample_states(g.layout(), n, first=n)
+        ours = m.fk_jacobians(q, eff)
+        ref = r.fk_jacobians(q, eff)
+        for k in ("A_BI", "JT", "JR"):
+            assert_close(ours[k], ref[k], what=f"N={n}:{k}")
+
+
+def test_wrong_dimensions_is_an_error(cuda_device):
+    """The reference aborts with 'q has wrong dimensions' (Rcs_graph.c:250); we return it."""
+    g = rcs_b200.Graph(graph_file("wam_arm"))
+    m = rcs_b200.Model(g, cuda_device)
+    with pytest.raises(rcs_b200.RcsbError, match="wrong dimensions"):
+        m.fk(np.zeros((4, g.dof + 1)))
+
+
+def test_known_answers_wam_default_state(cuda_device):
+    """Values recorded from the reference at survey time."""
+    g = rcs_b200.Graph(graph_file("wam_arm"))
+    m = rcs_b200.Model(g, cuda_device)
+    q = np.array([g.layout()["q"]])
+    tip = g.body_index("BallTip")
+    out = m.fk_jacobians(q, [tip])
+    org = out["A_BI"][0, tip, :3]
+    np.testing.assert_allclose(
+        org, [0.83632952411278927, 0.30514499825747998, 0.83766965256912063], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(
+        out["JT"][0, 0, 0],
+        [-0.16514499825747997, 0.47491641541908702, -0.14053874149066872,
+         -0.040723861313878298, 6.9e-18, 0.033210789380311002, 1.7e-17], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(
+        out["JR"][0, 0, 0],
+        [0, -0.25881904510252074, 0.16773125949652062, -0.25881904510252074,
+         0.95125124256419769, 0.25881904510252085, 0.95125124256419769], rtol=0, atol=1e-14)
