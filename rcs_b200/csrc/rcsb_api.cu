@@ -182,17 +182,27 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
     }
   }
 
-  /* scratch slots for unconstrained joints on effector chains */
-  std::vector<int> jntScr(dof, -1);
+  /* scratch slots for unconstrained joints on effector chains, ascending with the Jacobian
+   * column so that neighbouring columns sit in neighbouring shared-memory rows */
+  std::vector<int> jntScr(dof, -1), useCount(dof, 0);
   int nChain = 0;
   for (int e = 0; e < nEff; ++e)
   {
     for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
     {
-      if (jntJacobi[j] >= 0 && jntScr[j] < 0)
+      if (jntJacobi[j] >= 0)
       {
-        jntScr[j] = nChain++;
+        useCount[j]++;
       }
+    }
+  }
+  bool inPlace = true;
+  for (int j = 0; j < dof; ++j)
+  {
+    if (useCount[j] > 0)
+    {
+      jntScr[j] = nChain++;
+      inPlace = inPlace && (useCount[j] == 1);
     }
   }
   if (nChain > 0xffff || nEff > 2047)
@@ -202,7 +212,8 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   }
 
   const int rec = nEff * 3 * nJ;
-  std::vector<int> jtab(rec > 0 ? rec : 1, -1);
+  std::vector<int> jtab(rec > 0 ? rec : 1, -1), jtabR(rec > 0 ? rec : 1, -1);
+  std::vector<int> effChainStart(nEff + 1, 0), effChain;
   for (int e = 0; e < nEff; ++e)
   {
     for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
@@ -212,12 +223,27 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
       {
         continue;
       }
+      const bool isRot = (jntFlags[j] & RCSB_JF_ROT) != 0;
+      effChain.push_back(jntScr[j] | (isRot ? (1 << 16) : 0));
       for (int r = 0; r < 3; ++r)
       {
-        jtab[(e * 3 + r) * nJ + col] =
-          jntScr[j] | (r << 16) | ((jntFlags[j] & RCSB_JF_ROT) ? (1 << 18) : 0) | (e << 20);
+        const int idx = (e * 3 + r) * nJ + col;
+        if (inPlace)
+        {
+          jtab[idx] = (3 + r) * nChain + jntScr[j];        /* JT column (was: joint origin) */
+          jtabR[idx] = isRot ? r * nChain + jntScr[j] : -1; /* JR column = axis */
+        }
+        else
+        {
+          jtab[idx] = jntScr[j] | (r << 16) | (isRot ? (1 << 18) : 0) | (e << 20);
+        }
       }
     }
+    effChainStart[e + 1] = (int) effChain.size();
+  }
+  if (effChain.empty())
+  {
+    effChain.push_back(0);
   }
 
   std::vector<int> effStart(nb + 1, 0), effList(nEff > 0 ? nEff : 1, 0);
@@ -244,6 +270,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   ph.nChain = nChain;
   ph.nScrRows = (nEff > 0) ? 6 * nChain + 3 * nEff : 0;
   ph.jacRecord = rec;
+  ph.inPlace = inPlace ? 1 : 0;
   ph.invJacRecord = rec > 0 ? 1.0f / (float) rec : 0.0f;
   int off = align16((int) sizeof(ph));
   ph.offBodyOut = off;
@@ -258,6 +285,12 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   off = align16(off + (nEff > 0 ? nEff : 1) * 24);
   ph.offJTab = off;
   off = align16(off + (int) jtab.size() * 4);
+  ph.offJTabR = off;
+  off = align16(off + (int) jtabR.size() * 4);
+  ph.offEffChainStart = off;
+  off = align16(off + (nEff + 1) * 4);
+  ph.offEffChain = off;
+  off = align16(off + (int) effChain.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob(ph.totalBytes, 0);
@@ -271,6 +304,9 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
     memcpy(blob.data() + ph.offEffPt, effPt, sizeof(double) * 3 * nEff);
   }
   memcpy(blob.data() + ph.offJTab, jtab.data(), jtab.size() * 4);
+  memcpy(blob.data() + ph.offJTabR, jtabR.data(), jtabR.size() * 4);
+  memcpy(blob.data() + ph.offEffChainStart, effChainStart.data(), (nEff + 1) * 4);
+  memcpy(blob.data() + ph.offEffChain, effChain.data(), effChain.size() * 4);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));

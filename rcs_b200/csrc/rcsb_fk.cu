@@ -7,14 +7,15 @@
  *   RcsGraph_rotationJacobian                             src/RcsCore/Rcs_kinematics.c:416-458
  *
  * How: one thread per state walks the flattened tree depth first. The walk is the same for
- * every state, so all model reads are warp-uniform shared-memory broadcasts and there is no
- * divergence. The running frame lives in registers; a body whose parent is not the body
- * visited just before reloads the parent frame from a small per-thread frame stack (only
- * bodies with several children are parked there). Body frames leave as three 32-byte
- * stores per frame (STG.E.256: full sectors, nothing to merge). Joint axes and origins on
- * an effector's chain are parked in padded shared memory; once the walk is over the warp
- * turns them into Jacobian elements cooperatively, so that the 3 x nJ rows of 32
- * consecutive states leave as one contiguous, fully coalesced stream.
+ * every state, so all model reads are warp-uniform shared-memory broadcasts (128-bit) and
+ * there is no divergence. The running frame lives in registers. Leaf bodies are evaluated
+ * on a register copy; a body whose parent frame is not in registers reloads it from a small
+ * per-thread frame stack (only bodies that need it are parked there). Body frames leave as
+ * three 32-byte stores per frame (STG.E.256, L1 no-allocate: full sectors, nothing to
+ * merge, nothing displaced). Joint axes and origins on an effector's chain are parked in
+ * padded shared memory; once the effector point is known the owning thread turns the
+ * origins into Jacobian columns in place, and the warp streams the 3 x nJ records of its
+ * 32 consecutive states to global memory as one contiguous, coalesced run.
  *
  * Bound: HBM (output stream); see DESIGN.md for the byte counts.
  */
@@ -34,6 +35,9 @@ struct PlanView
   const int* bodyEffList;
   const double* effPt;
   const int* jtab;
+  const int* jtabR;
+  const int* effChainStart;
+  const int* effChain;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -44,6 +48,9 @@ struct PlanView
     bodyEffList = reinterpret_cast<const int*>(blob + hdr->offBodyEffList);
     effPt = reinterpret_cast<const double*>(blob + hdr->offEffPt);
     jtab = reinterpret_cast<const int*>(blob + hdr->offJTab);
+    jtabR = reinterpret_cast<const int*>(blob + hdr->offJTabR);
+    effChainStart = reinterpret_cast<const int*>(blob + hdr->offEffChainStart);
+    effChain = reinterpret_cast<const int*>(blob + hdr->offEffChain);
   }
 };
 
@@ -82,17 +89,19 @@ fkKernel(const FkArgs a)
   rd.qd = VEL ? a.qd + sc * a.qdim : nullptr;
 
   constexpr int SLOT_DOUBLES = VEL ? 18 : 12;
-  double stk[NSLOTS * SLOT_DOUBLES];
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * SLOT_DOUBLES];
 
-  Frame f;
-  double xd[3] = {0.0, 0.0, 0.0};
-  double om[3] = {0.0, 0.0, 0.0};
+  Frame f, keep;
+  double xd[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
+  double keepXd[3] = {0.0, 0.0, 0.0}, keepOm[3] = {0.0, 0.0, 0.0};
   setIdentity(f);
+  setIdentity(keep);
 
   for (int b = 0; b < nb; ++b)
   {
     /* ---- parent frame ---------------------------------------------------------------- */
     const int ld = m.bodyLoad[b];
+    const int bflags = m.bodyFlags[b];
     if (ld == RCSB_LOAD_IDENT)
     {
       setIdentity(f);
@@ -102,7 +111,7 @@ fkKernel(const FkArgs a)
         om[0] = om[1] = om[2] = 0.0;
       }
     }
-    else if (ld >= 0)
+    else if (NSLOTS > 0 && ld >= 0)
     {
       const double* sp = stk + ld * SLOT_DOUBLES;
 #pragma unroll
@@ -122,6 +131,21 @@ fkKernel(const FkArgs a)
         {
           xd[i] = sp[12 + i];
           om[i] = sp[15 + i];
+        }
+      }
+    }
+
+    /* a leaf does not advance the walk: remember the parent frame in registers */
+    if (bflags & RCSB_BF_LEAF)
+    {
+      keep = f;
+      if (VEL)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          keepXd[i] = xd[i];
+          keepOm[i] = om[i];
         }
       }
     }
@@ -207,18 +231,19 @@ fkKernel(const FkArgs a)
       const int slot = p.jntScr[j];
       if (slot >= 0)
       {
-        double* col = scr + (6 * slot) * scrStride + tid;
+        double* col = scr + slot * scrStride + tid;
+        const int rs = nChain * scrStride;
         col[0] = ax[0];
-        col[scrStride] = ax[1];
-        col[2 * scrStride] = ax[2];
-        col[3 * scrStride] = f.o[0];
-        col[4 * scrStride] = f.o[1];
-        col[5 * scrStride] = f.o[2];
+        col[rs] = ax[1];
+        col[2 * rs] = ax[2];
+        col[3 * rs] = f.o[0];
+        col[4 * rs] = f.o[1];
+        col[5 * rs] = f.o[2];
       }
     }
 
     /* ---- body frame ---------------------------------------------------------------------- */
-    if (m.bodyFlags[b] & RCSB_BF_HAS_ABP)
+    if (bflags & RCSB_BF_HAS_ABP)
     {
       applyRel(f, m.bodyABP + 12 * b);
     }
@@ -246,27 +271,30 @@ fkKernel(const FkArgs a)
       }
     }
 
-    const int sv = m.bodySave[b];
-    if (sv >= 0)
+    if (NSLOTS > 0)
     {
-      double* sp = stk + sv * SLOT_DOUBLES;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
+      const int sv = m.bodySave[b];
+      if (sv >= 0)
       {
-        sp[i] = f.o[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 9; ++i)
-      {
-        sp[3 + i] = f.R[i];
-      }
-      if (VEL)
-      {
+        double* sp = stk + sv * SLOT_DOUBLES;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
         {
-          sp[12 + i] = xd[i];
-          sp[15 + i] = om[i];
+          sp[i] = f.o[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          sp[3 + i] = f.R[i];
+        }
+        if (VEL)
+        {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            sp[12 + i] = xd[i];
+            sp[15 + i] = om[i];
+          }
         }
       }
     }
@@ -303,12 +331,58 @@ fkKernel(const FkArgs a)
       col[scrStride] = f.o[1] + (f.R[1] * pt[0] + f.R[4] * pt[1] + f.R[7] * pt[2]);
       col[2 * scrStride] = f.o[2] + (f.R[2] * pt[0] + f.R[5] * pt[1] + f.R[8] * pt[2]);
     }
+
+    if (bflags & RCSB_BF_LEAF)
+    {
+      f = keep;
+      if (VEL)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          xd[i] = keepXd[i];
+          om[i] = keepOm[i];
+        }
+      }
+    }
   }
 
-  /* ---- Jacobians: warp-cooperative, coalesced ------------------------------------------- */
+  /* ---- Jacobians --------------------------------------------------------------------------- */
   const int rec = p.hdr->jacRecord;
   if (rec > 0 && (a.JT || a.JR))
   {
+    const int rs = nChain * scrStride;
+    const bool inPlace = p.hdr->inPlace != 0;
+
+    if (inPlace)
+    {
+      /* own column: joint origin -> axis x (I_p - origin), or the axis for a translation */
+      for (int e = 0; e < p.hdr->nEff; ++e)
+      {
+        const double* pe = scr + (6 * nChain + 3 * e) * scrStride + tid;
+        const double px = pe[0], py = pe[scrStride], pz = pe[2 * scrStride];
+        for (int k = p.effChainStart[e]; k < p.effChainStart[e + 1]; ++k)
+        {
+          const int ent = p.effChain[k];
+          double* col = scr + (ent & 0xffff) * scrStride + tid;
+          const double a0 = col[0], a1 = col[rs], a2 = col[2 * rs];
+          if (ent >> 16)
+          {
+            const double d0 = px - col[3 * rs], d1 = py - col[4 * rs], d2 = pz - col[5 * rs];
+            col[3 * rs] = a1 * d2 - a2 * d1;
+            col[4 * rs] = a2 * d0 - a0 * d2;
+            col[5 * rs] = a0 * d1 - a1 * d0;
+          }
+          else
+          {
+            col[3 * rs] = a0;
+            col[4 * rs] = a1;
+            col[5 * rs] = a2;
+          }
+        }
+      }
+    }
+
     __syncwarp();
     const int lane = tid & 31;
     const long w0 = s - lane;                      /* first state of this warp */
@@ -320,42 +394,62 @@ fkKernel(const FkArgs a)
     double* JTw = a.JT ? a.JT + w0 * rec : nullptr;
     double* JRw = a.JR ? a.JR + w0 * rec : nullptr;
 
-    for (int e = lane; e < total; e += 32)
+    if (inPlace)
     {
-      const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
-      const int rem = e - sl * rec;
-      const int t = p.jtab[rem];
-      double vT = 0.0, vR = 0.0;
-      if (t >= 0)
+      /* plain gather: one shared-memory read per element, coalesced global writes */
+      for (int e = lane; e < total; e += 32)
       {
-        const int slot = RCSB_JTAB_SLOT(t);
-        const int r = RCSB_JTAB_ROW(t);
-        const double* col = scrWarp + sl;
-        const double* ja = col + (6 * slot) * scrStride;
-        if (RCSB_JTAB_ISROT(t))
+        const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
+        const int rem = e - sl * rec;
+        if (JTw)
         {
-          /* column = axis x (I_p - joint origin), component r */
-          const int r1 = r == 2 ? 0 : r + 1;
-          const int r2 = r == 0 ? 2 : r - 1;
-          const double* pe = col + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride;
-          const double a1 = ja[r1 * scrStride], a2 = ja[r2 * scrStride];
-          const double d1 = pe[r1 * scrStride] - ja[(3 + r1) * scrStride];
-          const double d2 = pe[r2 * scrStride] - ja[(3 + r2) * scrStride];
-          vT = a1 * d2 - a2 * d1;
-          vR = ja[r * scrStride];
+          const int t = p.jtab[rem];
+          JTw[e] = t >= 0 ? scrWarp[t * scrStride + sl] : 0.0;
         }
-        else
+        if (JRw)
         {
-          vT = ja[r * scrStride];
+          const int t = p.jtabR[rem];
+          JRw[e] = t >= 0 ? scrWarp[t * scrStride + sl] : 0.0;
         }
       }
-      if (JTw)
+    }
+    else
+    {
+      for (int e = lane; e < total; e += 32)
       {
-        JTw[e] = vT;
-      }
-      if (JRw)
-      {
-        JRw[e] = vR;
+        const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
+        const int rem = e - sl * rec;
+        const int t = p.jtab[rem];
+        double vT = 0.0, vR = 0.0;
+        if (t >= 0)
+        {
+          const int r = RCSB_JTAB_ROW(t);
+          const double* ja = scrWarp + RCSB_JTAB_SLOT(t) * scrStride + sl;
+          if (RCSB_JTAB_ISROT(t))
+          {
+            /* column = axis x (I_p - joint origin), component r */
+            const int r1 = r == 2 ? 0 : r + 1;
+            const int r2 = r == 0 ? 2 : r - 1;
+            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
+            const double a1 = ja[r1 * rs], a2 = ja[r2 * rs];
+            const double d1 = pe[r1 * scrStride] - ja[(3 + r1) * rs];
+            const double d2 = pe[r2 * scrStride] - ja[(3 + r2) * rs];
+            vT = a1 * d2 - a2 * d1;
+            vR = ja[r * rs];
+          }
+          else
+          {
+            vT = ja[r * rs];
+          }
+        }
+        if (JTw)
+        {
+          JTw[e] = vT;
+        }
+        if (JRw)
+        {
+          JRw[e] = vR;
+        }
       }
     }
   }
@@ -377,13 +471,13 @@ static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t sm
     k<<<grid, RCSB_FK_THREADS, smemBytes, stream>>>(a);                                        \
     return cudaGetLastError();                                                                 \
   }
-  if (nSlots <= 1)
+  if (nSlots <= 0)
   {
-    RCSB_LAUNCH(1)
+    RCSB_LAUNCH(0)
   }
-  else if (nSlots <= 4)
+  else if (nSlots <= 2)
   {
-    RCSB_LAUNCH(4)
+    RCSB_LAUNCH(2)
   }
   else
   {

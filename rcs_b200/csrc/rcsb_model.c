@@ -15,9 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-static int alignUp8(int x)
+static int alignUp16(int x)
 {
-  return (x + 7) & ~7;
+  return (x + 15) & ~15;
 }
 
 int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
@@ -80,13 +80,13 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
   }
   sizes[RCSB_A_CPL] = nCpl * (int) sizeof(RcsbCoupling);
 
-  int off = alignUp8((int) sizeof(RcsbFlatHeader));
+  int off = alignUp16((int) sizeof(RcsbFlatHeader));
   for (int a = 0; a < RCSB_A_COUNT; ++a)
   {
     hdr.off[a] = off;
-    off = alignUp8(off + sizes[a]);
+    off = alignUp16(off + sizes[a]);
   }
-  hdr.totalBytes = alignUp8(off + 8);   /* multiple of 16 for vector copies */
+  hdr.totalBytes = alignUp16(off + 8);   /* multiple of 16 for vector copies */
   hdr.totalBytes = (hdr.totalBytes + 15) & ~15;
 
   char* blob = (char*) calloc(1, (size_t) hdr.totalBytes);
@@ -108,13 +108,40 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
     }
   }
 
-  /* frame-stack slots: a body with several children parks its frame at the depth given by
-   * the number of branching ancestors, which a depth-first walk uses like a stack */
+  /* Where does each body find its parent frame? Simulate the depth-first walk. A leaf body
+   * is evaluated on a register copy, so after it the registers hold its parent's frame
+   * again; after any other body they hold that body's frame. A parent whose frame is not
+   * in registers when one of its children comes up has to park it in a frame-stack slot. */
+  int* needSlot = (int*) calloc((size_t) nb + 1, sizeof(int));
+  int* loadKind = (int*) calloc((size_t) nb + 1, sizeof(int));
+  {
+    int cur = -1;   /* body whose frame the registers hold */
+    for (int b = 0; b < nb; ++b)
+    {
+      const int p = IARR(RCSB_A_BODY_PARENT)[b];
+      if (p < 0)
+      {
+        loadKind[b] = RCSB_LOAD_IDENT;
+      }
+      else if (cur == p)
+      {
+        loadKind[b] = RCSB_LOAD_CONT;
+      }
+      else
+      {
+        loadKind[b] = 0;   /* from the parent's slot */
+        needSlot[p] = 1;
+      }
+      cur = (nChildren[b] == 0 && p >= 0) ? p : b;
+    }
+  }
+
+  /* slots are used like a stack: depth = number of slot-holding ancestors */
   for (int b = 0; b < nb; ++b)
   {
     const int p = IARR(RCSB_A_BODY_PARENT)[b];
     const int inherited = p >= 0 ? branchDepth[p] : 0;
-    if (nChildren[b] >= 2)
+    if (needSlot[b])
     {
       slotOf[b] = inherited;
       branchDepth[b] = inherited + 1;
@@ -139,17 +166,10 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
     int flags = 0;
 
     IARR(RCSB_A_BODY_SAVE)[b] = slotOf[b];
-    if (p < 0)
+    IARR(RCSB_A_BODY_LOAD)[b] = (loadKind[b] == 0) ? slotOf[p] : loadKind[b];
+    if (nChildren[b] == 0 && p >= 0)
     {
-      IARR(RCSB_A_BODY_LOAD)[b] = RCSB_LOAD_IDENT;
-    }
-    else if (p == b - 1)
-    {
-      IARR(RCSB_A_BODY_LOAD)[b] = RCSB_LOAD_CONT;
-    }
-    else
-    {
-      IARR(RCSB_A_BODY_LOAD)[b] = slotOf[p];
+      flags |= RCSB_BF_LEAF;
     }
 
     double* abp = DARR(RCSB_A_BODY_ABP) + 12 * b;
@@ -193,6 +213,8 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
         free(nChildren);
         free(slotOf);
         free(branchDepth);
+        free(needSlot);
+        free(loadKind);
         return -1;
       }
       cnt++;
@@ -262,5 +284,7 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
   free(nChildren);
   free(slotOf);
   free(branchDepth);
+  free(needSlot);
+  free(loadKind);
   return 0;
 }

@@ -18,6 +18,7 @@ extern "C" {
 /* body flags */
 #define RCSB_BF_HAS_ABP 1      /* A_BP is not the identity */
 #define RCSB_BF_HAS_MASS 2     /* m != 0: contributes to the kinetic terms */
+#define RCSB_BF_LEAF 4         /* no children (and not a root): evaluated on a register copy */
 /* joint flags */
 #define RCSB_JF_HAS_AJP 1
 #define RCSB_JF_CONSTRAINED 2
