@@ -1,105 +1,150 @@
 /*
- * C ABI of rcs_b200 (include/rcsb.h): models, query plans, launches, host-buffer staging.
+ * C ABI of rcs_b200 (include/rcsb.h), part 1: utilities, models, the forward-kinematics /
+ * Jacobian entry points and the host-buffer staging pipe.
  *
  * This layer contains no kinematics: it validates shapes, flattens/uploads models, builds
  * the small per-query plans the kernels read, and enqueues the kernels of rcsb_fk.cu,
  * rcsb_kinetic.cu and rcsb_ik.cu. If there is no CUDA device every compute entry point
  * fails with RCSB_ENODEVICE — there is deliberately no host implementation to fall back to.
  */
-#include "rcsb.h"
-#include "rcsb_internal.h"
-#include "rcsb_kernels.h"
-#include "rcsb_model.h"
-#include "rcsb_plan.h"
-
-#include <atomic>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <mutex>
-#include <string>
-#include <vector>
+#include "rcsb_priv.h"
 
 extern "C" int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut);
 
-namespace
+namespace rcsbhost
 {
 
 std::atomic<unsigned long long> g_launches(0);
 
-struct DevicePlan
+int checkModel(const RcsbModel* m, long N, int qdim, const double* q)
 {
-  char* dev = nullptr;
-  int bytes = 0;
-  int nScrRows = 0;
-  int nSel = 0;
-  int nEff = 0;
-  int aux0 = 0;
-  int aux1 = 0;
-};
-
-/* double-buffered device workspace of the RCSB_HOST_PTRS path */
-struct StagePipe
-{
-  cudaStream_t stream[2] = {nullptr, nullptr};
-  char* buf[2] = {nullptr, nullptr};
-  size_t cap[2] = {0, 0};
-};
-
-}   // namespace
-
-struct RcsbModel
-{
-  int device = 0;
-  std::vector<char> host;        /* flat model blob */
-  char* dev = nullptr;
-  RcsbFlatHeader hdr;
-  std::mutex mtx;                /* guards the plan caches and the staging pipe */
-  std::map<std::string, DevicePlan> fkPlans;
-  std::map<std::string, DevicePlan> ikPlans;
-  DevicePlan ktPlan;
-  bool ktPlanBuilt = false;
-  double* ktScratch = nullptr;
-  size_t ktScratchDoubles = 0;
-  StagePipe pipe;
-
-  const int* iarr(int a) const
+  if (!m)
   {
-    return reinterpret_cast<const int*>(host.data() + hdr.off[a]);
+    rcsb_set_error("model is NULL");
+    return RCSB_EINVAL;
   }
-  const double* darr(int a) const
+  if (N < 0 || (N > 0 && !q))
   {
-    return reinterpret_cast<const double*>(host.data() + hdr.off[a]);
+    rcsb_set_error("invalid batch: N = %ld, q = %p", N, (const void*) q);
+    return RCSB_EINVAL;
   }
-};
+  if (qdim != m->hdr.dof && qdim != m->hdr.nJ)
+  {
+    /* the reference aborts here: "q has wrong dimensions" (Rcs_graph.c:250) */
+    rcsb_set_error("q has wrong dimensions: qdim = %d, dof is %d, nJ is %d", qdim, m->hdr.dof,
+                   m->hdr.nJ);
+    return RCSB_EINVAL;
+  }
+  return RCSB_OK;
+}
+
+/* ---- staging pipe for host-pointer calls ------------------------------------------------- */
+
+static int pipeReserve(RcsbModel* m, int slot, size_t bytes)
+{
+  StagePipe& p = m->pipe;
+  if (!p.stream[slot])
+  {
+    RCSB_CUDA(cudaStreamCreateWithFlags(&p.stream[slot], cudaStreamNonBlocking));
+  }
+  if (p.cap[slot] < bytes)
+  {
+    if (p.buf[slot])
+    {
+      RCSB_CUDA(cudaFree(p.buf[slot]));
+      p.buf[slot] = nullptr;
+      p.cap[slot] = 0;
+    }
+    RCSB_CUDA(cudaMalloc(&p.buf[slot], bytes));
+    p.cap[slot] = bytes;
+  }
+  return RCSB_OK;
+}
+
+static size_t carveBytes(size_t doubles)
+{
+  return (doubles * sizeof(double) + 255) & ~(size_t) 255;
+}
+
+static const long kStageChunk = 1L << 16;   /* states per pipeline stage */
+
+int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
+              const std::vector<int>& aliasOutToIn,
+              const std::function<int(long n, cudaStream_t st, int slot)>& launch)
+{
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
+  RCSB_CUDA(cudaSetDevice(m->device));
+
+  const long chunk = N < kStageChunk ? N : kStageChunk;
+  std::vector<size_t> offs(arrays.size(), 0);
+  size_t need = 0;
+  for (size_t i = 0; i < arrays.size(); ++i)
+  {
+    const int al = i < aliasOutToIn.size() ? aliasOutToIn[i] : -1;
+    if (al >= 0)
+    {
+      offs[i] = offs[(size_t) al];
+    }
+    else
+    {
+      offs[i] = need;
+      need += carveBytes((size_t) chunk * arrays[i].perState);
+    }
+  }
+
+  int slot = 0;
+  for (long s0 = 0; s0 < N; s0 += chunk, slot ^= 1)
+  {
+    const long n = (N - s0 < chunk) ? (N - s0) : chunk;
+    int rc = pipeReserve(m, slot, need);
+    if (rc != RCSB_OK)
+    {
+      return rc;
+    }
+    cudaStream_t st = m->pipe.stream[slot];
+    for (size_t i = 0; i < arrays.size(); ++i)
+    {
+      StagedArray& A = arrays[i];
+      A.dev = reinterpret_cast<double*>(m->pipe.buf[slot] + offs[i]);
+      if (A.hostIn)
+      {
+        RCSB_CUDA(cudaMemcpyAsync(A.dev, A.hostIn + (size_t) s0 * A.perState,
+                                  sizeof(double) * (size_t) n * A.perState,
+                                  cudaMemcpyHostToDevice, st));
+      }
+    }
+    rc = launch(n, st, slot);
+    if (rc != RCSB_OK)
+    {
+      return rc;
+    }
+    for (size_t i = 0; i < arrays.size(); ++i)
+    {
+      StagedArray& A = arrays[i];
+      if (A.hostOut)
+      {
+        RCSB_CUDA(cudaMemcpyAsync(A.hostOut + (size_t) s0 * A.perState, A.dev,
+                                  sizeof(double) * (size_t) n * A.perState,
+                                  cudaMemcpyDeviceToHost, st));
+      }
+    }
+  }
+  for (int i = 0; i < 2; ++i)
+  {
+    if (m->pipe.stream[i])
+    {
+      RCSB_CUDA(cudaStreamSynchronize(m->pipe.stream[i]));
+    }
+  }
+  return RCSB_OK;
+}
+
+}   // namespace rcsbhost
+
+using namespace rcsbhost;
 
 namespace
 {
-
-int cudaFail(cudaError_t e, const char* what)
-{
-  rcsb_set_error("%s: %s", what, cudaGetErrorString(e));
-  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
-  {
-    return RCSB_ENODEVICE;
-  }
-  return RCSB_ECUDA;
-}
-
-#define RCSB_CUDA(call)                     \
-  do                                        \
-  {                                         \
-    cudaError_t e_ = (call);                \
-    if (e_ != cudaSuccess)                  \
-    {                                       \
-      return cudaFail(e_, #call);           \
-    }                                       \
-  } while (0)
-
-int align16(int x)
-{
-  return (x + 15) & ~15;
-}
 
 /* ---- FK plan ---------------------------------------------------------------------------- */
 
@@ -146,7 +191,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
     }
   }
 
-  std::lock_guard<std::mutex> lock(m->mtx);
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
   auto it = m->fkPlans.find(key);
   if (it != m->fkPlans.end())
   {
@@ -322,69 +367,6 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   return RCSB_OK;
 }
 
-/* ---- staging pipe for host-pointer calls ------------------------------------------------- */
-
-int pipeReserve(RcsbModel* m, int slot, size_t bytes)
-{
-  StagePipe& p = m->pipe;
-  if (!p.stream[slot])
-  {
-    RCSB_CUDA(cudaStreamCreateWithFlags(&p.stream[slot], cudaStreamNonBlocking));
-  }
-  if (p.cap[slot] < bytes)
-  {
-    if (p.buf[slot])
-    {
-      RCSB_CUDA(cudaFree(p.buf[slot]));
-      p.buf[slot] = nullptr;
-      p.cap[slot] = 0;
-    }
-    RCSB_CUDA(cudaMalloc(&p.buf[slot], bytes));
-    p.cap[slot] = bytes;
-  }
-  return RCSB_OK;
-}
-
-struct Carver
-{
-  char* base;
-  size_t off = 0;
-  explicit Carver(char* b) : base(b) {}
-  double* take(size_t doubles)
-  {
-    double* p = reinterpret_cast<double*>(base + off);
-    off += (doubles * sizeof(double) + 255) & ~(size_t) 255;
-    return p;
-  }
-};
-
-size_t carveBytes(size_t doubles)
-{
-  return (doubles * sizeof(double) + 255) & ~(size_t) 255;
-}
-
-int checkModel(const RcsbModel* m, long N, int qdim, const double* q)
-{
-  if (!m)
-  {
-    rcsb_set_error("model is NULL");
-    return RCSB_EINVAL;
-  }
-  if (N < 0 || (N > 0 && !q))
-  {
-    rcsb_set_error("invalid batch: N = %ld, q = %p", N, (const void*) q);
-    return RCSB_EINVAL;
-  }
-  if (qdim != m->hdr.dof && qdim != m->hdr.nJ)
-  {
-    /* the reference aborts here: "q has wrong dimensions" (Rcs_graph.c:250) */
-    rcsb_set_error("q has wrong dimensions: qdim = %d, dof is %d, nJ is %d", qdim, m->hdr.dof,
-                   m->hdr.nJ);
-    return RCSB_EINVAL;
-  }
-  return RCSB_OK;
-}
-
 /* FK (+ Jacobians) on device pointers */
 int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const double* q,
              const double* qd, double* A_BI, double* A_JI, double* xdot, double* omega,
@@ -414,8 +396,6 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   }
   return RCSB_OK;
 }
-
-const long kStageChunk = 1L << 16;   /* states per pipeline stage of the host-pointer path */
 
 }   // namespace
 
@@ -522,6 +502,10 @@ extern "C" int rcsb_model_create(const RcsGraph* graph, int device, RcsbModel** 
   {
     ce = cudaMemcpy(m->dev, m->host.data(), bytes, cudaMemcpyHostToDevice);
   }
+  if (ce == cudaSuccess)
+  {
+    ce = cudaDeviceGetAttribute(&m->smCount, cudaDevAttrMultiProcessorCount, device);
+  }
   if (ce != cudaSuccess)
   {
     delete m;
@@ -548,7 +532,8 @@ extern "C" void rcsb_model_destroy(RcsbModel* m)
     cudaFree(kv.second.dev);
   }
   cudaFree(m->ktPlan.dev);
-  cudaFree(m->ktScratch);
+  cudaFree(m->ktScratch[0]);
+  cudaFree(m->ktScratch[1]);
   for (int i = 0; i < 2; ++i)
   {
     if (m->pipe.buf[i])
@@ -587,6 +572,7 @@ extern "C" int rcsb_model_device(const RcsbModel* m)
 /* ------------------------------------------------------------------------------------------ */
 /* forward kinematics + Jacobians                                                              */
 /* ------------------------------------------------------------------------------------------ */
+
 
 static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
                     int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
@@ -627,80 +613,26 @@ static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
                     static_cast<cudaStream_t>(stream));
   }
 
-  /* host pointers: chunks alternate between two streams so that the copies of one chunk
-   * overlap the kernel of the other */
-  const int dof = m->hdr.dof, nOut = plan->nSel;
+  const size_t dof = (size_t) m->hdr.dof, nOut = (size_t) plan->nSel;
   const size_t recJ = (size_t) plan->nEff * 3 * m->hdr.nJ;
-  std::lock_guard<std::mutex> lock(m->mtx);
-  RCSB_CUDA(cudaSetDevice(m->device));
+  std::vector<StagedArray> arr;
+  enum { I_Q, I_QD, I_A, I_AJ, I_XD, I_OM, I_QO, I_JT, I_JR };
+  arr.push_back({q, nullptr, (size_t) qdim, nullptr});
+  arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
+  arr.push_back({nullptr, A_BI, A_BI ? nOut * 12 : 0, nullptr});
+  arr.push_back({nullptr, A_JI, A_JI ? dof * 12 : 0, nullptr});
+  arr.push_back({nullptr, xdot, xdot ? nOut * 3 : 0, nullptr});
+  arr.push_back({nullptr, omega, omega ? nOut * 3 : 0, nullptr});
+  arr.push_back({nullptr, qOut, qOut ? dof : 0, nullptr});
+  arr.push_back({nullptr, JT, JT ? recJ : 0, nullptr});
+  arr.push_back({nullptr, JR, JR ? recJ : 0, nullptr});
 
-  const long chunk = N < kStageChunk ? N : kStageChunk;
-  size_t need = carveBytes((size_t) chunk * qdim) * (qd ? 2 : 1);
-  need += A_BI ? carveBytes((size_t) chunk * nOut * 12) : 0;
-  need += A_JI ? carveBytes((size_t) chunk * dof * 12) : 0;
-  need += xdot ? carveBytes((size_t) chunk * nOut * 3) : 0;
-  need += omega ? carveBytes((size_t) chunk * nOut * 3) : 0;
-  need += qOut ? carveBytes((size_t) chunk * dof) : 0;
-  need += JT ? carveBytes((size_t) chunk * recJ) : 0;
-  need += JR ? carveBytes((size_t) chunk * recJ) : 0;
-
-  int slot = 0;
-  for (long s0 = 0; s0 < N; s0 += chunk, slot ^= 1)
-  {
-    const long n = (N - s0 < chunk) ? (N - s0) : chunk;
-    rc = pipeReserve(m, slot, need);
-    if (rc != RCSB_OK)
-    {
-      return rc;
-    }
-    cudaStream_t st = m->pipe.stream[slot];
-    Carver cv(m->pipe.buf[slot]);
-    double* dq = cv.take((size_t) chunk * qdim);
-    double* dqd = qd ? cv.take((size_t) chunk * qdim) : nullptr;
-    double* dA = A_BI ? cv.take((size_t) chunk * nOut * 12) : nullptr;
-    double* dAJ = A_JI ? cv.take((size_t) chunk * dof * 12) : nullptr;
-    double* dxd = xdot ? cv.take((size_t) chunk * nOut * 3) : nullptr;
-    double* dom = omega ? cv.take((size_t) chunk * nOut * 3) : nullptr;
-    double* dqo = qOut ? cv.take((size_t) chunk * dof) : nullptr;
-    double* dJT = JT ? cv.take((size_t) chunk * recJ) : nullptr;
-    double* dJR = JR ? cv.take((size_t) chunk * recJ) : nullptr;
-
-    RCSB_CUDA(cudaMemcpyAsync(dq, q + s0 * qdim, sizeof(double) * n * qdim,
-                              cudaMemcpyHostToDevice, st));
-    if (qd)
-    {
-      RCSB_CUDA(cudaMemcpyAsync(dqd, qd + s0 * qdim, sizeof(double) * n * qdim,
-                                cudaMemcpyHostToDevice, st));
-    }
-    rc = fkDevice(m, plan, n, qdim, dq, dqd, dA, dAJ, dxd, dom, dqo, dJT, dJR, st);
-    if (rc != RCSB_OK)
-    {
-      return rc;
-    }
-#define RCSB_D2H(hostPtr, devPtr, perState)                                                   \
-  if (hostPtr)                                                                                \
-  {                                                                                           \
-    RCSB_CUDA(cudaMemcpyAsync(hostPtr + (size_t) s0 * (perState), devPtr,                     \
-                              sizeof(double) * (size_t) n * (perState), cudaMemcpyDeviceToHost, \
-                              st));                                                           \
-  }
-    RCSB_D2H(A_BI, dA, (size_t) nOut * 12)
-    RCSB_D2H(A_JI, dAJ, (size_t) dof * 12)
-    RCSB_D2H(xdot, dxd, (size_t) nOut * 3)
-    RCSB_D2H(omega, dom, (size_t) nOut * 3)
-    RCSB_D2H(qOut, dqo, (size_t) dof)
-    RCSB_D2H(JT, dJT, recJ)
-    RCSB_D2H(JR, dJR, recJ)
-#undef RCSB_D2H
-  }
-  for (int i = 0; i < 2; ++i)
-  {
-    if (m->pipe.stream[i])
-    {
-      RCSB_CUDA(cudaStreamSynchronize(m->pipe.stream[i]));
-    }
-  }
-  return RCSB_OK;
+  return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int) {
+    auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    return fkDevice(m, plan, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_A, A_BI), dv(I_AJ, A_JI),
+                    dv(I_XD, xdot), dv(I_OM, omega), dv(I_QO, qOut), dv(I_JT, JT), dv(I_JR, JR),
+                    st);
+  });
 }
 
 extern "C" int rcsb_fk(const RcsbModel* model, long N, int qdim, const double* q,

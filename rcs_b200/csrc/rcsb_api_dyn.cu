@@ -1,0 +1,232 @@
+/*
+ * C ABI of rcs_b200 (include/rcsb.h), part 2: kinetic terms and resolved-motion-rate IK —
+ * plan construction (host) and launches. No arithmetic on states happens here.
+ */
+#include "rcsb_priv.h"
+
+using namespace rcsbhost;
+
+namespace
+{
+
+/* ---- kinetic-terms plan ------------------------------------------------------------------- */
+
+int buildKtPlan(RcsbModel* m)
+{
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
+  if (m->ktPlanBuilt)
+  {
+    return RCSB_OK;
+  }
+
+  const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
+  const int* bodyParent = m->iarr(RCSB_A_BODY_PARENT);
+  const int* bodyJntStart = m->iarr(RCSB_A_BODY_JNT_START);
+  const int* bodyJntCount = m->iarr(RCSB_A_BODY_JNT_COUNT);
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
+  const int* jntFlags = m->iarr(RCSB_A_JNT_FLAGS);
+  const int* jntBody = m->iarr(RCSB_A_JNT_BODY);
+
+  /* links: bodies owning at least one unconstrained joint, numbered depth first */
+  std::vector<int> bodyLink(nb, -1), linkOfBody(nb, -1), linkParent;
+  int nLinks = 0;
+  for (int b = 0; b < nb; ++b)
+  {
+    bool owns = false;
+    for (int j = bodyJntStart[b]; j < bodyJntStart[b] + bodyJntCount[b]; ++j)
+    {
+      owns = owns || (jntJacobi[j] >= 0);
+    }
+    const int inherited = bodyParent[b] >= 0 ? bodyLink[bodyParent[b]] : -1;
+    if (owns)
+    {
+      linkOfBody[b] = nLinks;
+      bodyLink[b] = nLinks++;
+      linkParent.push_back(inherited);
+    }
+    else
+    {
+      bodyLink[b] = inherited;
+    }
+  }
+
+  std::vector<int> colJoint(nJ > 0 ? nJ : 1, 0), colLink(nJ > 0 ? nJ : 1, 0),
+    colIsRot(nJ > 0 ? nJ : 1, 0);
+  for (int j = 0; j < dof; ++j)
+  {
+    const int c = jntJacobi[j];
+    if (c >= 0)
+    {
+      colJoint[c] = j;
+      colLink[c] = linkOfBody[jntBody[j]];
+      colIsRot[c] = (jntFlags[j] & RCSB_JF_ROT) ? 1 : 0;
+    }
+  }
+
+  /* relation table from the backward joint chains (jnt->prev links) */
+  std::vector<unsigned char> rel((size_t) (nJ > 0 ? nJ * nJ : 1), 0);
+  for (int k = 0; k < nJ; ++k)
+  {
+    rel[(size_t) k * nJ + k] = 1;
+    for (int j = jntPrev[colJoint[k]]; j >= 0; j = jntPrev[j])
+    {
+      const int i = jntJacobi[j];
+      if (i >= 0)
+      {
+        rel[(size_t) i * nJ + k] = 1;   /* column k is moved by row joint i */
+        rel[(size_t) k * nJ + i] = 2;   /* column i is a proper ancestor of row joint k */
+      }
+    }
+  }
+
+  RcsbKtPlanHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.nLinks = nLinks;
+  ph.nJ = nJ;
+  ph.scrComp = 0;
+  ph.scrWr = 13 * nLinks;
+  ph.scrJa = 19 * nLinks;
+  ph.scrPl = 19 * nLinks + 6 * nJ;
+  ph.scrQd = 19 * nLinks + 15 * nJ;
+  ph.scratchDoubles = 19 * nLinks + 16 * nJ;
+  ph.invNJ = nJ > 0 ? 1.0f / (float) nJ : 0.0f;
+  int off = align16((int) sizeof(ph));
+  ph.offBodyLink = off;
+  off = align16(off + nb * 4);
+  ph.offLinkParent = off;
+  off = align16(off + (nLinks > 0 ? nLinks : 1) * 4);
+  ph.offColJoint = off;
+  off = align16(off + (int) colJoint.size() * 4);
+  ph.offColLink = off;
+  off = align16(off + (int) colLink.size() * 4);
+  ph.offColIsRot = off;
+  off = align16(off + (int) colIsRot.size() * 4);
+  ph.offRel = off;
+  off = align16(off + (int) rel.size());
+  ph.totalBytes = off;
+
+  std::vector<char> blob((size_t) ph.totalBytes, 0);
+  memcpy(blob.data(), &ph, sizeof(ph));
+  memcpy(blob.data() + ph.offBodyLink, bodyLink.data(), (size_t) nb * 4);
+  if (nLinks > 0)
+  {
+    memcpy(blob.data() + ph.offLinkParent, linkParent.data(), (size_t) nLinks * 4);
+  }
+  memcpy(blob.data() + ph.offColJoint, colJoint.data(), colJoint.size() * 4);
+  memcpy(blob.data() + ph.offColLink, colLink.data(), colLink.size() * 4);
+  memcpy(blob.data() + ph.offColIsRot, colIsRot.data(), colIsRot.size() * 4);
+  memcpy(blob.data() + ph.offRel, rel.data(), rel.size());
+
+  RCSB_CUDA(cudaSetDevice(m->device));
+  RCSB_CUDA(cudaMalloc(&m->ktPlan.dev, blob.size()));
+  RCSB_CUDA(cudaMemcpy(m->ktPlan.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  m->ktPlan.bytes = ph.totalBytes;
+  m->ktPlan.aux0 = ph.scratchDoubles;
+  m->ktPlanBuilt = true;
+  return RCSB_OK;
+}
+
+/* Threads in flight: the per-thread workspace (scratchDoubles x 8 B) of all of them should
+ * stay resident in L2 (126 MB on B200); RCSB_KT_BLOCKS_PER_SM overrides the choice. */
+int ktBlocks(const RcsbModel* m, int scratchDoubles)
+{
+  int perSm = 0;
+  const char* env = getenv("RCSB_KT_BLOCKS_PER_SM");
+  if (env)
+  {
+    perSm = atoi(env);
+  }
+  if (perSm <= 0)
+  {
+    /* measured on B200 (humanoid, 256K states): 1 block/SM 12.6, 2: 19.6, 3: 25.1, 4: 31.4,
+     * 6: 26.3, 8: 31.3 M states/s — latency, not L2 capacity, is what limits this kernel */
+    (void) scratchDoubles;
+    perSm = 4;
+  }
+  return perSm * m->smCount;
+}
+
+int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
+             double* h, double* Fg, double* E, cudaStream_t stream, int ws)
+{
+  const int blocks = ktBlocks(m, m->ktPlan.aux0);
+  const size_t T = (size_t) blocks * RCSB_KT_THREADS;
+  const size_t need = T * (size_t) (m->ktPlan.aux0 > 0 ? m->ktPlan.aux0 : 1);
+  RCSB_CUDA(cudaSetDevice(m->device));
+  {
+    /* one workspace per staging stream: kernels of the two streams may overlap */
+    std::lock_guard<std::recursive_mutex> lock(m->mtx);
+    if (m->ktScratchDoubles[ws] < need)
+    {
+      if (m->ktScratch[ws])
+      {
+        RCSB_CUDA(cudaFree(m->ktScratch[ws]));
+        m->ktScratch[ws] = nullptr;
+        m->ktScratchDoubles[ws] = 0;
+      }
+      RCSB_CUDA(cudaMalloc(&m->ktScratch[ws], need * sizeof(double)));
+      m->ktScratchDoubles[ws] = need;
+    }
+  }
+
+  rcsb::KtArgs a;
+  a.model = m->dev;
+  a.plan = m->ktPlan.dev;
+  a.modelBytes = m->hdr.totalBytes;
+  a.planBytes = m->ktPlan.bytes;
+  a.N = N;
+  a.qdim = qdim;
+  a.q = q;
+  a.qd = qd;
+  a.M = M;
+  a.h = h;
+  a.Fg = Fg;
+  a.E = E;
+  a.scratch = m->ktScratch[ws];
+  a.scratchStride = (long) T;
+  RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, blocks, stream));
+  g_launches.fetch_add(1);
+  return RCSB_OK;
+}
+
+}   // namespace
+
+extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const double* q,
+                                  const double* qd, double* M, double* h, double* Fg, double* E,
+                                  unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  int rc = checkModel(m, N, qdim, q);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  rc = buildKtPlan(m);
+  if (rc != RCSB_OK || N == 0)
+  {
+    return rc;
+  }
+
+  if (!(flags & RCSB_HOST_PTRS))
+  {
+    /* the workspace is shared: device-pointer calls on one model must use one stream at a
+     * time (documented in rcsb.h) */
+    return ktDevice(m, N, qdim, q, qd, M, h, Fg, E, static_cast<cudaStream_t>(stream), 0);
+  }
+
+  const size_t nJ = (size_t) m->hdr.nJ;
+  std::vector<StagedArray> arr;
+  enum { I_Q, I_QD, I_M, I_H, I_G, I_E };
+  arr.push_back({q, nullptr, (size_t) qdim, nullptr});
+  arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
+  arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
+  arr.push_back({nullptr, h, h ? nJ : 0, nullptr});
+  arr.push_back({nullptr, Fg, Fg ? nJ : 0, nullptr});
+  arr.push_back({nullptr, E, (size_t) (E ? 1 : 0), nullptr});
+  return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int slot) {
+    auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    return ktDevice(m, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_M, M), dv(I_H, h), dv(I_G, Fg),
+                    dv(I_E, E), st, slot);
+  });
+}

@@ -50,6 +50,37 @@ typedef struct
   int pad;
 } RcsbFkPlanHeader;
 
+/*
+ * Kinetic-terms plan. "Links" are the bodies that own at least one unconstrained joint;
+ * every massive body is lumped into its nearest ancestor-or-self link, so that subtree
+ * (composite) quantities only have to be kept per link.
+ *
+ * Per-thread workspace layout (doubles, element k of thread t at scratch[k * stride + t]):
+ *   comp  13 * nLinks   composite m, m c (3), inertia about the world origin (9, row-major,
+ *                       not symmetrised: the reference uses the tensor of the file as given)
+ *   wr     6 * nLinks   composite bias wrench F (3), N about the world origin (3)
+ *   ja     6 * nJ       per Jacobian column: joint axis (3), joint origin (3)
+ *   pl     9 * nJ       per column: momentum of its composite under unit joint rate p (3),
+ *                       L (3), and L with the transposed inertia (3)
+ *   qd         nJ       joint rates in IK order
+ */
+typedef struct
+{
+  int nLinks;
+  int nJ;
+  int totalBytes;
+  int scratchDoubles;   /* 19 nLinks + 16 nJ */
+  int offBodyLink;      /* int[nb]: link the body is lumped into, -1 = none (no joint moves it) */
+  int offLinkParent;    /* int[nLinks]: nearest proper ancestor link, -1 = none */
+  int offColJoint;      /* int[nJ]: jointIndex of Jacobian column */
+  int offColLink;       /* int[nJ]: link of the column's joint */
+  int offColIsRot;      /* int[nJ] */
+  int offRel;           /* unsigned char[nJ * nJ]: 0 unrelated, 1 col is descendant-or-equal of
+                           row, 2 col is a proper ancestor of row */
+  int scrComp, scrWr, scrJa, scrPl, scrQd;   /* offsets (in doubles) into the workspace */
+  float invNJ;
+} RcsbKtPlanHeader;
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,129 @@
+/*
+ * Private host-side declarations shared by the translation units that implement the C ABI
+ * (rcsb_api.cu, rcsb_api_dyn.cu, rcsb_single.cu).
+ */
+#ifndef RCSB_PRIV_H
+#define RCSB_PRIV_H
+
+#include "rcsb.h"
+#include "rcsb_internal.h"
+#include "rcsb_kernels.h"
+#include "rcsb_model.h"
+#include "rcsb_plan.h"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace rcsbhost
+{
+
+extern std::atomic<unsigned long long> g_launches;
+
+struct DevicePlan
+{
+  char* dev = nullptr;
+  int bytes = 0;
+  int nScrRows = 0;
+  int nSel = 0;
+  int nEff = 0;
+  int aux0 = 0;
+  int aux1 = 0;
+};
+
+/* double-buffered device workspace of the RCSB_HOST_PTRS path */
+struct StagePipe
+{
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  char* buf[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+};
+
+}   // namespace rcsbhost
+
+struct RcsbModel
+{
+  int device = 0;
+  int smCount = 0;
+  std::vector<char> host;        /* flat model blob */
+  char* dev = nullptr;
+  RcsbFlatHeader hdr;
+  std::recursive_mutex mtx;               /* guards the plan caches, workspaces and the staging pipe */
+  std::map<std::string, rcsbhost::DevicePlan> fkPlans;
+  std::map<std::string, rcsbhost::DevicePlan> ikPlans;
+  rcsbhost::DevicePlan ktPlan;
+  bool ktPlanBuilt = false;
+  double* ktScratch[2] = {nullptr, nullptr};
+  size_t ktScratchDoubles[2] = {0, 0};
+  rcsbhost::StagePipe pipe;
+
+  const int* iarr(int a) const
+  {
+    return reinterpret_cast<const int*>(host.data() + hdr.off[a]);
+  }
+  const double* darr(int a) const
+  {
+    return reinterpret_cast<const double*>(host.data() + hdr.off[a]);
+  }
+};
+
+namespace rcsbhost
+{
+
+inline int cudaFail(cudaError_t e, const char* what)
+{
+  rcsb_set_error("%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+  {
+    return RCSB_ENODEVICE;
+  }
+  return RCSB_ECUDA;
+}
+
+#define RCSB_CUDA(call)                        \
+  do                                           \
+  {                                            \
+    cudaError_t e_ = (call);                   \
+    if (e_ != cudaSuccess)                     \
+    {                                          \
+      return rcsbhost::cudaFail(e_, #call);    \
+    }                                          \
+  } while (0)
+
+inline int align16(int x)
+{
+  return (x + 15) & ~15;
+}
+
+int checkModel(const RcsbModel* m, long N, int qdim, const double* q);
+
+/* One array of a staged (host-pointer) call: `perState` doubles per state; exactly one of
+ * hostIn / hostOut is set; dev receives the device address of the current chunk. */
+struct StagedArray
+{
+  const double* hostIn;
+  double* hostOut;
+  size_t perState;
+  double* dev;
+};
+
+/*
+ * Runs `launch(n, stream)` over chunks of the batch: inputs are copied host -> device,
+ * the kernel is enqueued, outputs are copied device -> host, alternating between two
+ * streams so that the copies of one chunk overlap the kernel of the other. In-out arrays
+ * are listed twice (once as input, once as output, same perState) and share a buffer when
+ * `aliasOutToIn` names the input's index. Returns after all results are in host memory.
+ */
+int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
+              const std::vector<int>& aliasOutToIn,
+              const std::function<int(long n, cudaStream_t st, int slot)>& launch);
+
+}   // namespace rcsbhost
+
+#endif
