@@ -230,3 +230,242 @@ extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const d
                     dv(I_E, E), st, slot);
   });
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* resolved-motion-rate IK                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+namespace
+{
+
+int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePlan** out)
+{
+  const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
+  if (nTasks <= 0 || !tasks)
+  {
+    rcsb_set_error("rcsb_ik_rmr: no tasks");
+    return RCSB_EINVAL;
+  }
+  for (int t = 0; t < nTasks; ++t)
+  {
+    if (tasks[t].kind != RCSB_TASK_XYZ && tasks[t].kind != RCSB_TASK_ABC)
+    {
+      rcsb_set_error("task %d: unknown kind %d", t, tasks[t].kind);
+      return RCSB_EINVAL;
+    }
+    if (tasks[t].effector < 0 || tasks[t].effector >= nb)
+    {
+      rcsb_set_error("task %d: effector %d out of range [0, %d)", t, tasks[t].effector, nb);
+      return RCSB_EINVAL;
+    }
+  }
+
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
+  const int* jntFlags = m->iarr(RCSB_A_JNT_FLAGS);
+  const int* jntCpl = m->iarr(RCSB_A_JNT_CPL);
+  const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
+
+  /* RcsGraph_countCoupledJoints (Rcs_graph.c:2804): slaves that are not constrained */
+  for (int j = 0; j < dof; ++j)
+  {
+    if (jntCpl[j] >= 0 && jntJacobi[j] >= 0)
+    {
+      rcsb_set_error("rcsb_ik_rmr: graphs with kinematically coupled joints are not supported "
+                     "(coupled-joint projection of IkSolverRMR.cpp:424-443)");
+      return RCSB_EUNSUPPORTED;
+    }
+  }
+
+  std::string key(reinterpret_cast<const char*>(tasks), sizeof(RcsbTask) * (size_t) nTasks);
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
+  auto it = m->ikPlans.find(key);
+  if (it != m->ikPlans.end())
+  {
+    *out = &it->second;
+    return RCSB_OK;
+  }
+
+  std::vector<int> kind(nTasks), body(nTasks), needed(dof, 0), chainStart(nTasks + 1, 0), chain;
+  std::vector<int> taskStart(nb + 1, 0), taskList(nTasks, 0);
+  for (int t = 0; t < nTasks; ++t)
+  {
+    kind[t] = tasks[t].kind;
+    body[t] = tasks[t].effector;
+    taskStart[body[t] + 1]++;
+    for (int j = bodyLastJnt[body[t]]; j >= 0; j = jntPrev[j])
+    {
+      if (jntJacobi[j] >= 0)
+      {
+        needed[j] = 1;
+        chain.push_back(jntJacobi[j] | ((jntFlags[j] & RCSB_JF_ROT) ? (1 << 16) : 0));
+      }
+    }
+    chainStart[t + 1] = (int) chain.size();
+  }
+  for (int b = 0; b < nb; ++b)
+  {
+    taskStart[b + 1] += taskStart[b];
+  }
+  {
+    std::vector<int> fill(taskStart.begin(), taskStart.end() - 1);
+    for (int t = 0; t < nTasks; ++t)
+    {
+      taskList[fill[body[t]]++] = t;
+    }
+  }
+  if (chain.empty())
+  {
+    chain.push_back(0);
+  }
+
+  const double* qmin = m->darr(RCSB_A_JNT_QMIN);
+  const double* qmax = m->darr(RCSB_A_JNT_QMAX);
+  const double* q0 = m->darr(RCSB_A_JNT_Q0);
+  const double* wjl = m->darr(RCSB_A_JNT_WJL);
+  const double* wmetric = m->darr(RCSB_A_JNT_WMETRIC);
+  std::vector<int> colJoint(nJ > 0 ? nJ : 1, 0);
+  std::vector<double> invWq(nJ > 0 ? nJ : 1, 0.0), jlGain(nJ > 0 ? nJ : 1, 0.0),
+    q0c(nJ > 0 ? nJ : 1, 0.0);
+  for (int j = 0; j < dof; ++j)
+  {
+    const int c = jntJacobi[j];
+    if (c >= 0)
+    {
+      const double range = qmax[j] - qmin[j];
+      colJoint[c] = j;
+      invWq[c] = wmetric[j] * range;
+      jlGain[c] = range > 0.0 ? wjl[j] / (range * range) : 0.0;
+      q0c[c] = q0[j];
+    }
+  }
+
+  RcsbIkPlanHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.nTasks = nTasks;
+  ph.nx = 3 * nTasks;
+  ph.nJ = nJ;
+  int off = align16((int) sizeof(ph));
+  auto place = [&](int& field, size_t bytes) {
+    field = off;
+    off = align16(off + (int) bytes);
+  };
+  place(ph.offTaskKind, kind.size() * 4);
+  place(ph.offTaskBody, body.size() * 4);
+  place(ph.offBodyTaskStart, taskStart.size() * 4);
+  place(ph.offBodyTaskList, taskList.size() * 4);
+  place(ph.offJntNeeded, (needed.empty() ? 1 : needed.size()) * 4);
+  place(ph.offChainStart, chainStart.size() * 4);
+  place(ph.offChain, chain.size() * 4);
+  place(ph.offColJoint, colJoint.size() * 4);
+  place(ph.offInvWq, invWq.size() * 8);
+  place(ph.offJlGain, jlGain.size() * 8);
+  place(ph.offQ0, q0c.size() * 8);
+  ph.totalBytes = off;
+
+  std::vector<char> blob((size_t) ph.totalBytes, 0);
+  memcpy(blob.data(), &ph, sizeof(ph));
+  memcpy(blob.data() + ph.offTaskKind, kind.data(), kind.size() * 4);
+  memcpy(blob.data() + ph.offTaskBody, body.data(), body.size() * 4);
+  memcpy(blob.data() + ph.offBodyTaskStart, taskStart.data(), taskStart.size() * 4);
+  memcpy(blob.data() + ph.offBodyTaskList, taskList.data(), taskList.size() * 4);
+  if (!needed.empty())
+  {
+    memcpy(blob.data() + ph.offJntNeeded, needed.data(), needed.size() * 4);
+  }
+  memcpy(blob.data() + ph.offChainStart, chainStart.data(), chainStart.size() * 4);
+  memcpy(blob.data() + ph.offChain, chain.data(), chain.size() * 4);
+  memcpy(blob.data() + ph.offColJoint, colJoint.data(), colJoint.size() * 4);
+  memcpy(blob.data() + ph.offInvWq, invWq.data(), invWq.size() * 8);
+  memcpy(blob.data() + ph.offJlGain, jlGain.data(), jlGain.size() * 8);
+  memcpy(blob.data() + ph.offQ0, q0c.data(), q0c.size() * 8);
+
+  DevicePlan dp;
+  RCSB_CUDA(cudaSetDevice(m->device));
+  RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
+  RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  dp.bytes = ph.totalBytes;
+  dp.aux0 = ph.nx;
+  auto ins = m->ikPlans.emplace(key, dp);
+  *out = &ins.first->second;
+  return RCSB_OK;
+}
+
+int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const double* xDes,
+             double lambda, double alpha, int iters, double* dx, double* dq, double* det,
+             cudaStream_t stream)
+{
+  rcsb::IkArgs a;
+  a.model = m->dev;
+  a.plan = plan->dev;
+  a.modelBytes = m->hdr.totalBytes;
+  a.planBytes = plan->bytes;
+  a.N = N;
+  a.q = q;
+  a.xDes = xDes;
+  a.lambda = lambda;
+  a.alpha = alpha;
+  a.iters = iters;
+  a.dx = dx;
+  a.dq = dq;
+  a.det = det;
+  RCSB_CUDA(cudaSetDevice(m->device));
+  cudaError_t e = rcsb_launch_ik(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, stream);
+  if (e == cudaErrorInvalidValue)
+  {
+    cudaGetLastError();
+    rcsb_set_error("rcsb_ik_rmr: problem too large (nx %d, nJ %d, dof %d; limits 12 / 40 / 72)",
+                   plan->aux0, m->hdr.nJ, m->hdr.dof);
+    return RCSB_EUNSUPPORTED;
+  }
+  RCSB_CUDA(e);
+  g_launches.fetch_add(1);
+  return RCSB_OK;
+}
+
+}   // namespace
+
+extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, long N,
+                           double* q, const double* xDes, double lambda, double alpha, int iters,
+                           double* dx, double* dq, double* det, unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  if (!m)
+  {
+    rcsb_set_error("model is NULL");
+    return RCSB_EINVAL;
+  }
+  if (N < 0 || (N > 0 && (!q || !xDes)) || iters < 0)
+  {
+    rcsb_set_error("rcsb_ik_rmr: invalid batch (N = %ld, q = %p, xDes = %p, iters = %d)", N,
+                   (void*) q, (const void*) xDes, iters);
+    return RCSB_EINVAL;
+  }
+  const DevicePlan* plan = nullptr;
+  int rc = buildIkPlan(m, nTasks, tasks, &plan);
+  if (rc != RCSB_OK || N == 0)
+  {
+    return rc;
+  }
+
+  if (!(flags & RCSB_HOST_PTRS))
+  {
+    return ikDevice(m, plan, N, q, xDes, lambda, alpha, iters, dx, dq, det,
+                    static_cast<cudaStream_t>(stream));
+  }
+
+  const size_t dof = (size_t) m->hdr.dof, nx = (size_t) plan->aux0;
+  std::vector<StagedArray> arr;
+  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET };
+  arr.push_back({q, nullptr, dof, nullptr});
+  arr.push_back({xDes, nullptr, nx, nullptr});
+  arr.push_back({nullptr, q, dof, nullptr});          /* in-out: shares the input buffer */
+  arr.push_back({nullptr, dx, dx ? nx : 0, nullptr});
+  arr.push_back({nullptr, dq, dq ? dof : 0, nullptr});
+  arr.push_back({nullptr, det, (size_t) (det ? 1 : 0), nullptr});
+  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
+    auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    return ikDevice(m, plan, n, arr[I_QIN].dev, arr[I_X].dev, lambda, alpha, iters,
+                    dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), st);
+  });
+}

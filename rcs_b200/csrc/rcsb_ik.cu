@@ -1,6 +1,632 @@
+/*
+ * Batched resolved-motion-rate inverse kinematics for sm_100a: K damped-least-squares steps
+ * per state, one thread per state.
+ *
+ * One iteration reproduces, per state, the loop of examples/ExampleIK.cpp:154-177:
+ *   controller.computeDX(dx, x_des)            src/RcsCore/ControllerBase.cpp:896
+ *     XYZ: x_des - x                           src/RcsCore/TaskGenericIK.cpp:80
+ *     ABC: Euler error below 1 deg, else axis * angle
+ *                                              src/RcsCore/TaskEuler3D.cpp:243-262,
+ *                                              Rcs_Mat3d.c:956, :1044, :1152, :1227, :1613,
+ *                                              external/Rcs_thirdPartyMath.c:90
+ *   controller.computeJointlimitGradient(dH)   src/RcsCore/Rcs_kinematics.c:1496, dH *= alpha
+ *   ikSolver.solveRightInverse(dq, dx, dH, a, lambda)
+ *                                              src/RcsCore/IkSolverRMR.cpp:415-596
+ *     J        stacked task Jacobians          ControllerBase.cpp:776, Rcs_kinematics.c:200, :416
+ *     invWq    weightMetric (q_max - q_min)    Rcs_graph.c:1087
+ *     J#     = invWq J^T (J invWq J^T + lambda 1)^-1   Rcs_MatNd.c:1833 (MatNd_rwPinv)
+ *              via Banachiewicz Cholesky, in-place inverse of L, L^-T L^-1
+ *                                              Rcs_linAlg.c:66-101, :210-227, :270-307
+ *     dq     = J# dx + (1 - J# J) invWq (-dH); singular (a pivot <= 0): det = 0, dq = 0
+ *   q += dq; RcsGraph_setState
+ * All tasks are active (activation 1). Graphs with kinematically coupled joints take the
+ * reference's coupled-joint projection, which is not implemented here: the host rejects
+ * them (RCSB_EUNSUPPORTED).
+ *
+ * The small dense algebra (6 x 7 for the arm) stays in per-thread local arrays (L1), the
+ * tree walk is the one of rcsb_fk.cu. Bound: FP64 pipe / L1, not HBM (176 B per solve).
+ */
+#include "rcsb_device.cuh"
 #include "rcsb_kernels.h"
-extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, cudaStream_t stream)
+#include "rcsb_plan.h"
+
+#include "rcsb.h"
+
+#include <cfloat>
+
+namespace rcsb
 {
-  (void) a; (void) nSlots; (void) stream;
-  return cudaErrorNotSupported;
+
+struct IkPlanView
+{
+  const RcsbIkPlanHeader* hdr;
+  const int* taskKind;
+  const int* taskBody;
+  const int* bodyTaskStart;
+  const int* bodyTaskList;
+  const int* jntNeeded;
+  const int* chainStart;
+  const int* chain;
+  const int* colJoint;
+  const double* invWq;
+  const double* jlGain;
+  const double* q0;
+
+  __device__ __forceinline__ void bind(const char* blob)
+  {
+    hdr = reinterpret_cast<const RcsbIkPlanHeader*>(blob);
+    taskKind = reinterpret_cast<const int*>(blob + hdr->offTaskKind);
+    taskBody = reinterpret_cast<const int*>(blob + hdr->offTaskBody);
+    bodyTaskStart = reinterpret_cast<const int*>(blob + hdr->offBodyTaskStart);
+    bodyTaskList = reinterpret_cast<const int*>(blob + hdr->offBodyTaskList);
+    jntNeeded = reinterpret_cast<const int*>(blob + hdr->offJntNeeded);
+    chainStart = reinterpret_cast<const int*>(blob + hdr->offChainStart);
+    chain = reinterpret_cast<const int*>(blob + hdr->offChain);
+    colJoint = reinterpret_cast<const int*>(blob + hdr->offColJoint);
+    invWq = reinterpret_cast<const double*>(blob + hdr->offInvWq);
+    jlGain = reinterpret_cast<const double*>(blob + hdr->offJlGain);
+    q0 = reinterpret_cast<const double*>(blob + hdr->offQ0);
+  }
+};
+
+/* x-y-z Euler angles <-> rotation matrix (src/RcsCore/Rcs_Mat3d.c:956, :1152) */
+__device__ __forceinline__ void toEuler(double ea[3], const double A[9])
+{
+  const double cy = sqrt(A[0] * A[0] + A[3] * A[3]);
+  if (cy > 16.0 * (double) FLT_EPSILON)
+  {
+    ea[0] = -atan2(A[7], A[8]);
+    ea[1] = -atan2(-A[6], cy);
+    ea[2] = -atan2(A[3], A[0]);
+  }
+  else
+  {
+    ea[0] = -atan2(-A[5], A[4]);
+    ea[1] = -atan2(-A[6], cy);
+    ea[2] = 0.0;
+  }
+}
+
+__device__ __forceinline__ void fromEuler(double A[9], const double ea[3])
+{
+  double sa, ca, sb, cb, sg, cg;
+  sincos(ea[0], &sa, &ca);
+  sincos(ea[1], &sb, &cb);
+  sincos(ea[2], &sg, &cg);
+  A[0] = cb * cg;
+  A[1] = ca * sg + sa * sb * cg;
+  A[2] = sa * sg - ca * sb * cg;
+  A[3] = -cb * sg;
+  A[4] = ca * cg - sa * sb * sg;
+  A[5] = sa * cg + ca * sb * sg;
+  A[6] = sb;
+  A[7] = -sa * cb;
+  A[8] = ca * cb;
+}
+
+/* Orientation error of TaskEuler3D::computeDX (src/RcsCore/TaskEuler3D.cpp:243-262) */
+__device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3],
+                                               const double xCurr[3])
+{
+  double Ac[9], Ad[9];
+  fromEuler(Ac, xCurr);
+  fromEuler(Ad, xDes);
+
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+  {
+    tr += Ad[i] * Ac[i];   /* trace(A_des A_curr^T) */
+  }
+  double cs = 0.5 * (tr - 1.0);
+  cs = cs > 1.0 ? 1.0 : (cs < -1.0 ? -1.0 : cs);
+  const double angle = acos(cs);
+
+  if (angle < 1.0 * (M_PI / 180.0))
+  {
+    /* e = 0.5 (n x nd + s x sd + a x ad), rows of A_curr against rows of A_des */
+    double e[3] = {0.0, 0.0, 0.0}, t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+      cross3(t, Ac + 3 * r, Ad + 3 * r);
+      e[0] += t[0];
+      e[1] += t[1];
+      e[2] += t[2];
+    }
+    dx[0] = 0.5 * e[0];
+    dx[1] = 0.5 * e[1];
+    dx[2] = 0.5 * e[2];
+    return;
+  }
+
+  /* axis of A_21 = A_des A_curr^T, expressed in the 1 (current) frame */
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+    {
+      R[3 * i + j] = Ad[3 * i] * Ac[3 * j] + Ad[3 * i + 1] * Ac[3 * j + 1] + Ad[3 * i + 2] * Ac[3 * j + 2];
+    }
+
+  double ax[3];
+  if (angle < M_PI)
+  {
+    ax[0] = R[5] - R[7];
+    ax[1] = R[6] - R[2];
+    ax[2] = R[1] - R[3];
+    const double len = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    if (len > 0.0)
+    {
+      ax[0] /= len;
+      ax[1] /= len;
+      ax[2] /= len;
+    }
+  }
+  else
+  {
+    /* angle is pi: axis from the largest diagonal term
+     * (external/Rcs_thirdPartyMath.c:107-150) */
+    if (R[0] >= R[4] && R[0] >= R[8])
+    {
+      ax[0] = 0.5 * sqrt(1.0 + R[0] - R[4] - R[8]);
+      const double hi = 0.5 / ax[0];
+      ax[1] = hi * R[3];
+      ax[2] = hi * R[6];
+    }
+    else if (R[4] > R[0] && R[4] >= R[8])
+    {
+      ax[1] = 0.5 * sqrt(1.0 + R[4] - R[0] - R[8]);
+      const double hi = 0.5 / ax[1];
+      ax[0] = hi * R[3];
+      ax[2] = hi * R[7];
+    }
+    else
+    {
+      ax[2] = 0.5 * sqrt(1.0 + R[8] - R[0] - R[4]);
+      const double hi = 0.5 / ax[2];
+      ax[0] = hi * R[6];
+      ax[1] = hi * R[7];
+    }
+  }
+
+  /* rotate into the world frame (A_curr^T axis) and scale by the angle */
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    dx[i] = (Ac[i] * ax[0] + Ac[3 + i] * ax[1] + Ac[6 + i] * ax[2]) * angle;
+  }
+}
+
+template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS>
+__global__ void __launch_bounds__(RCSB_IK_THREADS)
+ikKernel(const IkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  stageBlob(sModel, a.model, a.modelBytes);
+  stageBlob(sPlan, a.plan, a.planBytes);
+  __syncthreads();
+
+  ModelView m;
+  m.bind(sModel);
+  IkPlanView p;
+  p.bind(sPlan);
+
+  const long s = (long) blockIdx.x * RCSB_IK_THREADS + threadIdx.x;
+  if (s >= a.N)
+  {
+    return;
+  }
+
+  const int nb = m.hdr->nb;
+  const int dof = m.hdr->dof;
+  const int nJ = p.hdr->nJ;
+  const int nx = p.hdr->nx;
+  const int nTasks = p.hdr->nTasks;
+  constexpr int MAXT = MAXNX / 3;
+
+  double qv[MAXDOF];
+  double ja[6 * MAXNJ];       /* axis, origin per Jacobian column */
+  double ef[12 * MAXT];       /* effector frame per task */
+  double J[MAXNX * MAXNJ];    /* nx x nJ */
+  double P[MAXNJ * MAXNX];    /* nJ x nx: invWq J^T, then J# */
+  double A[MAXNX * MAXNX];    /* J invWq J^T + lambda 1 -> L -> L^-1 */
+  double Ai[MAXNX * MAXNX];   /* inverse */
+  double dx[MAXNX], g[MAXNJ], Jg[MAXNX], dq[MAXNJ], row[MAXNX];
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
+  double det = 0.0;
+
+  for (int j = 0; j < dof; ++j)
+  {
+    qv[j] = a.q[s * dof + j];
+  }
+  for (int i = 0; i < nJ; ++i)
+  {
+    dq[i] = 0.0;
+  }
+  for (int i = 0; i < nx; ++i)
+  {
+    dx[i] = 0.0;
+  }
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    /* ---- forward kinematics (RcsGraph_setState) ------------------------------------------ */
+    Frame f, keep;
+    setIdentity(f);
+    keep = f;
+    for (int b = 0; b < nb; ++b)
+    {
+      const int ld = m.bodyLoad[b];
+      const int bflags = m.bodyFlags[b];
+      if (ld == RCSB_LOAD_IDENT)
+      {
+        setIdentity(f);
+      }
+      else if (NSLOTS > 0 && ld >= 0)
+      {
+        const double* sp = stk + ld * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          f.o[i] = sp[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          f.R[i] = sp[3 + i];
+        }
+      }
+      if (bflags & RCSB_BF_LEAF)
+      {
+        keep = f;
+      }
+
+      const int j0 = m.bodyJntStart[b];
+      const int j1 = j0 + m.bodyJntCount[b];
+      for (int j = j0; j < j1; ++j)
+      {
+        const int jf = m.jntFlags[j];
+        if (jf & RCSB_JF_HAS_AJP)
+        {
+          applyRel(f, m.jntAJP + 12 * j);
+        }
+        const double qj = qv[j];
+        const int dir = m.jntType[j] % 3;
+        double ax[3];
+        if (jf & RCSB_JF_ROT)
+        {
+          double sn, cs;
+          sincos(qj, &sn, &cs);
+          rotateAboutAxis(f, dir, sn, cs);
+          axisOf(f, dir, ax);
+        }
+        else
+        {
+          axisOf(f, dir, ax);
+          f.o[0] += qj * ax[0];
+          f.o[1] += qj * ax[1];
+          f.o[2] += qj * ax[2];
+        }
+        if (p.jntNeeded[j])
+        {
+          double* d = ja + 6 * m.jntJacobi[j];
+          d[0] = ax[0];
+          d[1] = ax[1];
+          d[2] = ax[2];
+          d[3] = f.o[0];
+          d[4] = f.o[1];
+          d[5] = f.o[2];
+        }
+      }
+      if (bflags & RCSB_BF_HAS_ABP)
+      {
+        applyRel(f, m.bodyABP + 12 * b);
+      }
+      if (NSLOTS > 0)
+      {
+        const int sv = m.bodySave[b];
+        if (sv >= 0)
+        {
+          double* sp = stk + sv * 12;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            sp[i] = f.o[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+          {
+            sp[3 + i] = f.R[i];
+          }
+        }
+      }
+      for (int k = p.bodyTaskStart[b]; k < p.bodyTaskStart[b + 1]; ++k)
+      {
+        double* d = ef + 12 * p.bodyTaskList[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          d[i] = f.o[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          d[3 + i] = f.R[i];
+        }
+      }
+      if (bflags & RCSB_BF_LEAF)
+      {
+        f = keep;
+      }
+    }
+
+    /* ---- task error and stacked Jacobian ---------------------------------------------------- */
+    for (int i = 0; i < nx * nJ; ++i)
+    {
+      J[i] = 0.0;
+    }
+    for (int t = 0; t < nTasks; ++t)
+    {
+      const double* e = ef + 12 * t;
+      const double* xd = a.xDes + s * nx + 3 * t;
+      const bool pos = p.taskKind[t] == RCSB_TASK_XYZ;
+      if (pos)
+      {
+        dx[3 * t] = xd[0] - e[0];
+        dx[3 * t + 1] = xd[1] - e[1];
+        dx[3 * t + 2] = xd[2] - e[2];
+      }
+      else
+      {
+        double xc[3];
+        const double xdl[3] = {xd[0], xd[1], xd[2]};
+        toEuler(xc, e + 3);
+        eulerTaskError(dx + 3 * t, xdl, xc);
+      }
+      for (int k = p.chainStart[t]; k < p.chainStart[t + 1]; ++k)
+      {
+        const int ent = p.chain[k];
+        const int col = ent & 0xffff;
+        const bool isRot = (ent >> 16) != 0;
+        const double* jc = ja + 6 * col;
+        double c0, c1, c2;
+        if (pos)
+        {
+          if (isRot)
+          {
+            const double d0 = e[0] - jc[3], d1 = e[1] - jc[4], d2 = e[2] - jc[5];
+            c0 = jc[1] * d2 - jc[2] * d1;
+            c1 = jc[2] * d0 - jc[0] * d2;
+            c2 = jc[0] * d1 - jc[1] * d0;
+          }
+          else
+          {
+            c0 = jc[0];
+            c1 = jc[1];
+            c2 = jc[2];
+          }
+        }
+        else
+        {
+          c0 = isRot ? jc[0] : 0.0;
+          c1 = isRot ? jc[1] : 0.0;
+          c2 = isRot ? jc[2] : 0.0;
+        }
+        J[(3 * t) * nJ + col] = c0;
+        J[(3 * t + 1) * nJ + col] = c1;
+        J[(3 * t + 2) * nJ + col] = c2;
+      }
+    }
+
+    /* ---- J# = invWq J^T (J invWq J^T + lambda 1)^-1 ------------------------------------------ */
+    for (int i = 0; i < nJ; ++i)
+    {
+      const double w = p.invWq[i];
+      for (int k = 0; k < nx; ++k)
+      {
+        P[i * nx + k] = w * J[k * nJ + i];
+      }
+    }
+    for (int r = 0; r < nx; ++r)
+    {
+      for (int c = 0; c < nx; ++c)
+      {
+        double sum = 0.0;
+        for (int i = 0; i < nJ; ++i)
+        {
+          sum += J[r * nJ + i] * P[i * nx + c];
+        }
+        A[r * nx + c] = sum + (r == c ? a.lambda : 0.0);
+      }
+    }
+
+    /* Banachiewicz Cholesky, lower triangle in place; det = prod L_ii^2 */
+    det = 1.0;
+    for (int i = 0; i < nx && det != 0.0; ++i)
+    {
+      for (int k = 0; k <= i; ++k)
+      {
+        double sum = A[i * nx + k];
+        for (int t = 0; t < k; ++t)
+        {
+          sum -= A[i * nx + t] * A[k * nx + t];
+        }
+        if (i > k)
+        {
+          A[i * nx + k] = sum / A[k * nx + k];
+        }
+        else if (sum > 0.0)
+        {
+          A[i * nx + i] = sqrt(sum);
+          det *= A[i * nx + i] * A[i * nx + i];
+        }
+        else
+        {
+          det = 0.0;
+          break;
+        }
+      }
+    }
+
+    if (det == 0.0)
+    {
+      /* singular: the reference returns zero displacements and leaves q untouched */
+      for (int i = 0; i < nJ; ++i)
+      {
+        dq[i] = 0.0;
+      }
+      continue;
+    }
+
+    /* L <- L^-1 in place */
+    for (int k = 0; k < nx; ++k)
+    {
+      A[k * nx + k] = 1.0 / A[k * nx + k];
+      for (int i = k + 1; i < nx; ++i)
+      {
+        double sum = 0.0;
+        for (int t = k; t < i; ++t)
+        {
+          sum += A[i * nx + t] * A[t * nx + k];
+        }
+        A[i * nx + k] = -sum / A[i * nx + i];
+      }
+    }
+    /* inverse = L^-T L^-1 */
+    for (int r = 0; r < nx; ++r)
+    {
+      for (int c = r; c < nx; ++c)
+      {
+        double sum = 0.0;
+        for (int t = c; t < nx; ++t)
+        {
+          sum += A[t * nx + r] * A[t * nx + c];
+        }
+        Ai[r * nx + c] = sum;
+        Ai[c * nx + r] = sum;
+      }
+    }
+    /* J# = (invWq J^T) inverse, row by row in place */
+    for (int i = 0; i < nJ; ++i)
+    {
+      for (int k = 0; k < nx; ++k)
+      {
+        row[k] = P[i * nx + k];
+      }
+      for (int c = 0; c < nx; ++c)
+      {
+        double sum = 0.0;
+        for (int k = 0; k < nx; ++k)
+        {
+          sum += row[k] * Ai[k * nx + c];
+        }
+        P[i * nx + c] = sum;
+      }
+    }
+
+    /* ---- dq = J# dx + (1 - J# J) invWq (-alpha dH) ------------------------------------------- */
+    for (int i = 0; i < nJ; ++i)
+    {
+      const double delta = qv[p.colJoint[i]] - p.q0[i];
+      g[i] = p.invWq[i] * (-(a.alpha * (p.jlGain[i] * delta)));
+    }
+    for (int r = 0; r < nx; ++r)
+    {
+      double sum = 0.0;
+      for (int i = 0; i < nJ; ++i)
+      {
+        sum += J[r * nJ + i] * g[i];
+      }
+      Jg[r] = sum;
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      double ts = 0.0, ns = 0.0;
+      for (int c = 0; c < nx; ++c)
+      {
+        ts += P[i * nx + c] * dx[c];
+        ns += P[i * nx + c] * Jg[c];
+      }
+      dq[i] = ts + (g[i] - ns);
+      qv[p.colJoint[i]] += dq[i];
+    }
+  }
+
+  /* ---- results ---------------------------------------------------------------------------------- */
+  for (int j = 0; j < dof; ++j)
+  {
+    a.q[s * dof + j] = qv[j];
+  }
+  if (a.dx)
+  {
+    for (int i = 0; i < nx; ++i)
+    {
+      a.dx[s * nx + i] = dx[i];
+    }
+  }
+  if (a.dq)
+  {
+    for (int j = 0; j < dof; ++j)
+    {
+      const int c = m.jntJacobi[j];
+      a.dq[s * dof + j] = c >= 0 ? dq[c] : 0.0;
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = det;
+  }
+}
+
+template <int MAXNX, int MAXNJ, int MAXDOF>
+static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes;
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
+#define RCSB_LAUNCH(NS)                                                                        \
+  {                                                                                            \
+    auto k = ikKernel<MAXNX, MAXNJ, MAXDOF, NS>;                                               \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);                                        \
+    return cudaGetLastError();                                                                 \
+  }
+  if (nSlots <= 0)
+  {
+    RCSB_LAUNCH(0)
+  }
+  else
+  {
+    RCSB_LAUNCH(RCSB_MAX_FRAME_SLOTS)
+  }
+#undef RCSB_LAUNCH
+}
+
+}   // namespace rcsb
+
+extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
+                                      cudaStream_t stream)
+{
+  using namespace rcsb;
+  if (a->N <= 0)
+  {
+    return cudaSuccess;
+  }
+  if (nx <= 6 && nJ <= 8 && dof <= 8)
+  {
+    return launchIk<6, 8, 8>(*a, nSlots, stream);
+  }
+  if (nx <= 12 && nJ <= 40 && dof <= 72)
+  {
+    return launchIk<12, 40, 72>(*a, nSlots, stream);
+  }
+  return cudaErrorInvalidValue;
 }

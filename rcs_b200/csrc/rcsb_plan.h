@@ -81,6 +81,31 @@ typedef struct
   float invNJ;
 } RcsbKtPlanHeader;
 
+/*
+ * IK plan: tasks (all active), their effectors' joint chains and the per-column constants
+ * of the resolved-motion-rate step.
+ */
+typedef struct
+{
+  int nTasks;
+  int nx;               /* 3 per task */
+  int nJ;
+  int totalBytes;
+  int offTaskKind;      /* int[nTasks]: RCSB_TASK_XYZ / RCSB_TASK_ABC */
+  int offTaskBody;      /* int[nTasks] */
+  int offBodyTaskStart; /* int[nb + 1]: CSR over tasks attached to each body */
+  int offBodyTaskList;  /* int[nTasks] */
+  int offJntNeeded;     /* int[dof]: 1 if the joint lies on some task's chain */
+  int offChainStart;    /* int[nTasks + 1]: CSR over (column | isRot << 16) per task */
+  int offChain;         /* int[sum of chain lengths] */
+  int offColJoint;      /* int[nJ] jointIndex of each Jacobian column */
+  int offInvWq;         /* double[nJ]: weightMetric (q_max - q_min)   (Rcs_graph.c:1087) */
+  int offJlGain;        /* double[nJ]: weightJL / (q_max - q_min)^2, 0 if the range is not
+                           positive (Rcs_kinematics.c:1496) */
+  int offQ0;            /* double[nJ] */
+  int pad;
+} RcsbIkPlanHeader;
+
 #ifdef __cplusplus
 }
 #endif
