@@ -370,7 +370,8 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
 /* FK (+ Jacobians) on device pointers */
 int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const double* q,
              const double* qd, double* A_BI, double* A_JI, double* xdot, double* omega,
-             double* qOut, double* JT, double* JR, cudaStream_t stream)
+             double* qOut, double* JT, double* JR, double* qdOut, bool noCoupling,
+             cudaStream_t stream)
 {
   rcsb::FkArgs a;
   a.model = m->dev;
@@ -388,6 +389,8 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.qOut = qOut;
   a.JT = JT;
   a.JR = JR;
+  a.qdOut = qdOut;
+  a.noCoupling = noCoupling ? 1 : 0;
   RCSB_CUDA(cudaSetDevice(m->device));
   RCSB_CUDA(rcsb_launch_fk(&a, m->hdr.nSlots, plan->nScrRows, stream));
   if (N > 0)
@@ -573,11 +576,11 @@ extern "C" int rcsb_model_device(const RcsbModel* m)
 /* forward kinematics + Jacobians                                                              */
 /* ------------------------------------------------------------------------------------------ */
 
-
-static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
-                    int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
-                    double* omega, double* qOut, int nEff, const int* effBody,
-                    const double* effPt, double* JT, double* JR, unsigned flags, void* stream)
+int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
+                       int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
+                       double* omega, double* qOut, int nEff, const int* effBody,
+                       const double* effPt, double* JT, double* JR, double* qdOut,
+                       bool noCoupling, unsigned flags, void* stream)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   int rc = checkModel(m, N, qdim, q);
@@ -585,9 +588,9 @@ static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
   {
     return rc;
   }
-  if ((xdot || omega) && !qd)
+  if ((xdot || omega || qdOut) && !qd)
   {
-    rcsb_set_error("xdot / omega requested without q_dot");
+    rcsb_set_error("xdot / omega / q_dot output requested without q_dot");
     return RCSB_EINVAL;
   }
   if ((JT || JR) && nEff <= 0)
@@ -609,14 +612,14 @@ static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
 
   if (!(flags & RCSB_HOST_PTRS))
   {
-    return fkDevice(m, plan, N, qdim, q, qd, A_BI, A_JI, xdot, omega, qOut, JT, JR,
-                    static_cast<cudaStream_t>(stream));
+    return fkDevice(m, plan, N, qdim, q, qd, A_BI, A_JI, xdot, omega, qOut, JT, JR, qdOut,
+                    noCoupling, static_cast<cudaStream_t>(stream));
   }
 
   const size_t dof = (size_t) m->hdr.dof, nOut = (size_t) plan->nSel;
   const size_t recJ = (size_t) plan->nEff * 3 * m->hdr.nJ;
   std::vector<StagedArray> arr;
-  enum { I_Q, I_QD, I_A, I_AJ, I_XD, I_OM, I_QO, I_JT, I_JR };
+  enum { I_Q, I_QD, I_A, I_AJ, I_XD, I_OM, I_QO, I_JT, I_JR, I_QDO };
   arr.push_back({q, nullptr, (size_t) qdim, nullptr});
   arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
   arr.push_back({nullptr, A_BI, A_BI ? nOut * 12 : 0, nullptr});
@@ -626,12 +629,13 @@ static int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
   arr.push_back({nullptr, qOut, qOut ? dof : 0, nullptr});
   arr.push_back({nullptr, JT, JT ? recJ : 0, nullptr});
   arr.push_back({nullptr, JR, JR ? recJ : 0, nullptr});
+  arr.push_back({nullptr, qdOut, qdOut ? dof : 0, nullptr});
 
   return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
     return fkDevice(m, plan, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_A, A_BI), dv(I_AJ, A_JI),
                     dv(I_XD, xdot), dv(I_OM, omega), dv(I_QO, qOut), dv(I_JT, JT), dv(I_JR, JR),
-                    st);
+                    dv(I_QDO, qdOut), noCoupling, st);
   });
 }
 
@@ -641,7 +645,7 @@ extern "C" int rcsb_fk(const RcsbModel* model, long N, int qdim, const double* q
                        void* stream)
 {
   return fkCommon(model, N, qdim, q, qd, nSel, bodySel, A_BI, A_JI, xdot, omega, qOut, 0,
-                  nullptr, nullptr, nullptr, nullptr, flags, stream);
+                  nullptr, nullptr, nullptr, nullptr, nullptr, false, flags, stream);
 }
 
 extern "C" int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q,
@@ -650,5 +654,5 @@ extern "C" int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const
                                  double* JR, unsigned flags, void* stream)
 {
   return fkCommon(model, N, qdim, q, nullptr, nSel, bodySel, A_BI, nullptr, nullptr, nullptr,
-                  nullptr, nEff, effBody, effPt, JT, JR, flags, stream);
+                  nullptr, nEff, effBody, effPt, JT, JR, nullptr, false, flags, stream);
 }

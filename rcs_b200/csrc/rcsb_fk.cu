@@ -87,6 +87,7 @@ fkKernel(const FkArgs a)
   rd.full = (a.qdim == dof);
   rd.q = a.q + sc * a.qdim;
   rd.qd = VEL ? a.qd + sc * a.qdim : nullptr;
+  rd.couple = (a.noCoupling == 0);
 
   constexpr int SLOT_DOUBLES = VEL ? 18 : 12;
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * SLOT_DOUBLES];
@@ -197,6 +198,10 @@ fkKernel(const FkArgs a)
          * r_b is only known after the last joint, so the cross products are split into
          * w x r_b - sum (a qd) x o_j. */
         const double qdj = rd.jointQd(m, j);
+        if (a.qdOut && active)
+        {
+          a.qdOut[s * dof + j] = qdj;
+        }
         const double aq[3] = {ax[0] * qdj, ax[1] * qdj, ax[2] * qdj};
         if (jf & RCSB_JF_ROT)
         {

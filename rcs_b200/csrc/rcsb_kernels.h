@@ -31,6 +31,8 @@ struct FkArgs
   double* qOut;
   double* JT;
   double* JR;
+  double* qdOut;       /* N x dof joint rates after expansion and coupling (needs qd) */
+  int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
 };
 
 struct KtArgs

@@ -124,6 +124,13 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
               const std::vector<int>& aliasOutToIn,
               const std::function<int(long n, cudaStream_t st, int slot)>& launch);
 
+/* Forward kinematics (+ Jacobians) behind rcsb_fk / rcsb_fk_jacobians and the single-state
+ * RcsGraph_* wrappers; qdOut and noCoupling are only reachable from the latter. */
+int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd, int nSel,
+             const int* bodySel, double* A_BI, double* A_JI, double* xdot, double* omega,
+             double* qOut, int nEff, const int* effBody, const double* effPt, double* JT,
+             double* JR, double* qdOut, bool noCoupling, unsigned flags, void* stream);
+
 }   // namespace rcsbhost
 
 #endif

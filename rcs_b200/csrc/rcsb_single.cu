@@ -1,4 +1,356 @@
-/* placeholder: single-state RcsGraph_* wrappers */
-#include "rcsb.h"
-#include "rcsb_internal.h"
-extern "C" bool RcsGraph_setState(RcsGraph*, const MatNd*, const MatNd*) { return false; }
+/*
+ * Single-state reference API (include/rcsb.h, bottom): the reference's own entry points
+ *   RcsGraph_setState                  src/RcsCore/Rcs_graph.c:231
+ *   RcsGraph_computeForwardKinematics  src/RcsCore/Rcs_graph.c:301
+ *   RcsGraph_bodyPointJacobian         src/RcsCore/Rcs_kinematics.c:200
+ *   RcsGraph_rotationJacobian          src/RcsCore/Rcs_kinematics.c:416
+ *   RcsGraph_computeKineticTerms       src/RcsCore/Rcs_dynamics.c:439
+ * as N = 1 calls into the batched kernels, so that code (and tests) written against the
+ * reference run unchanged on this library. Nothing is evaluated on the host: the wrappers
+ * only move the state in and the results back into the RcsGraph / MatNd structures.
+ *
+ * The reference keeps "the state of the last forward kinematics" in the graph (A_BI, A_JI,
+ * BODY->omega) and its Jacobian / dynamics functions read it. Here the graph's device cache
+ * remembers the joint state of the last forward-kinematics call instead, and the Jacobian /
+ * dynamics wrappers evaluate at that state.
+ *
+ * The flattened device model is created on first use (current CUDA device) from the graph's
+ * parameters at that moment and released by RcsGraph_destroy().
+ */
+#include "rcsb_priv.h"
+
+using namespace rcsbhost;
+
+namespace
+{
+
+struct GraphCache
+{
+  RcsbModel* model = nullptr;
+  std::vector<double> q, qd;      /* state of the last forward kinematics (dof each) */
+  bool haveVel = false;
+  bool coupled = true;            /* last FK applied the coupling rules */
+  std::vector<double> frames, jframes, xdot, omega, qOut, qdOut;
+};
+
+GraphCache* cacheOf(RcsGraph* self)
+{
+  GraphCache* c = static_cast<GraphCache*>(self->userData);
+  if (!c)
+  {
+    c = new GraphCache;
+    self->userData = c;
+  }
+  if (!c->model)
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+    {
+      cudaGetLastError();
+      dev = 0;
+    }
+    if (rcsb_model_create(self, dev, &c->model) != RCSB_OK)
+    {
+      c->model = nullptr;
+      return nullptr;
+    }
+    c->q.assign(self->q->ele, self->q->ele + self->dof);
+    c->qd.assign(self->dof, 0.0);
+  }
+  return c;
+}
+
+/* One forward-kinematics pass at (q, qd) [dof each], results into the graph. */
+bool runFk(RcsGraph* self, GraphCache* c, const double* q, const double* qd, bool noCoupling,
+           bool writeBack)
+{
+  const unsigned int dof = self->dof, nb = RcsGraph_numBodies(self);
+  c->frames.resize((size_t) nb * 12);
+  c->jframes.resize((size_t) (dof > 0 ? dof : 1) * 12);
+  c->qOut.resize(dof > 0 ? dof : 1);
+  if (qd)
+  {
+    c->xdot.resize((size_t) nb * 3);
+    c->omega.resize((size_t) nb * 3);
+    c->qdOut.resize(dof > 0 ? dof : 1);
+  }
+  const int rc = fkCommon(c->model, 1, (int) dof, q, qd, 0, nullptr, c->frames.data(),
+                          dof > 0 ? c->jframes.data() : nullptr, qd ? c->xdot.data() : nullptr,
+                          qd ? c->omega.data() : nullptr, c->qOut.data(), 0, nullptr, nullptr,
+                          nullptr, nullptr, qd ? c->qdOut.data() : nullptr, noCoupling,
+                          RCSB_HOST_PTRS, nullptr);
+  if (rc != RCSB_OK)
+  {
+    RCSB_FATAL("forward kinematics failed: %s", rcsb_last_error());
+    return false;
+  }
+
+  unsigned int b = 0, nJ = 0;
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    memcpy(BODY->A_BI, &c->frames[(size_t) b * 12], sizeof(HTr));
+    if (qd)
+    {
+      memcpy(BODY->x_dot, &c->xdot[(size_t) b * 3], 3 * sizeof(double));
+      memcpy(BODY->omega, &c->omega[(size_t) b * 3], 3 * sizeof(double));
+    }
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      memcpy(&JNT->A_JI, &c->jframes[(size_t) JNT->jointIndex * 12], sizeof(HTr));
+      /* RcsGraph_internalBodyKinematics renumbers the Jacobian columns while it walks
+       * (Rcs_graph.c:131-140) */
+      JNT->jacobiIndex = JNT->constrained ? -1 : (int) nJ++;
+    }
+    ++b;
+  }
+  if (self->nJ != nJ)
+  {
+    self->nJ = nJ;
+  }
+
+  c->q.assign(c->qOut.begin(), c->qOut.begin() + dof);
+  c->haveVel = (qd != nullptr);
+  c->coupled = !noCoupling;
+  if (qd)
+  {
+    c->qd.assign(c->qdOut.begin(), c->qdOut.begin() + dof);
+  }
+  if (writeBack)
+  {
+    memcpy(self->q->ele, c->q.data(), dof * sizeof(double));
+    if (qd)
+    {
+      memcpy(self->q_dot->ele, c->qd.data(), dof * sizeof(double));
+    }
+  }
+  return true;
+}
+
+}   // namespace
+
+extern "C" void rcsb_graph_release_device_cache(RcsGraph* self)
+{
+  GraphCache* c = self ? static_cast<GraphCache*>(self->userData) : nullptr;
+  if (c)
+  {
+    rcsb_model_destroy(c->model);
+    delete c;
+    self->userData = nullptr;
+  }
+}
+
+extern "C" bool RcsGraph_setState(RcsGraph* self, const MatNd* q_, const MatNd* q_dot_)
+{
+  if (!self)
+  {
+    RCSB_FATAL("RcsGraph_setState: graph is NULL");
+    return false;
+  }
+  const unsigned int dof = self->dof;
+
+  if (q_)
+  {
+    if (q_->m == self->nJ && q_->m != dof)
+    {
+      RcsGraph_stateVectorFromIK(self, q_, self->q);
+    }
+    else if (q_->m == dof)
+    {
+      if (self->q != q_)
+      {
+        memcpy(self->q->ele, q_->ele, dof * sizeof(double));
+      }
+    }
+    else
+    {
+      RCSB_FATAL("q has wrong dimensions: [%d x %d], dof is %d, nJ is %d", q_->m, q_->n, dof,
+                 self->nJ);
+      return false;
+    }
+  }
+  if (q_dot_)
+  {
+    if (q_dot_->m == self->nJ && q_dot_->m != dof)
+    {
+      RcsGraph_stateVectorFromIK(self, q_dot_, self->q_dot);
+    }
+    else if (q_dot_->m == dof)
+    {
+      if (self->q_dot != q_dot_)
+      {
+        memcpy(self->q_dot->ele, q_dot_->ele, dof * sizeof(double));
+      }
+    }
+    else
+    {
+      RCSB_FATAL("q_dot has wrong dimensions: [%d x %d], dof is %d, nJ is %d", q_dot_->m,
+                 q_dot_->n, dof, self->nJ);
+      return false;
+    }
+  }
+
+  GraphCache* c = cacheOf(self);
+  if (!c)
+  {
+    RCSB_FATAL("RcsGraph_setState: %s", rcsb_last_error());
+    return false;
+  }
+
+  std::vector<double> qIn(self->q->ele, self->q->ele + dof);
+  if (!runFk(self, c, qIn.data(), q_dot_ ? self->q_dot->ele : nullptr, false, true))
+  {
+    return false;
+  }
+
+  /* "changed" as in RcsGraph_updateSlaveJoints (Rcs_graph.c:2756): a slave joint had to be
+   * moved by more than 1e-8 */
+  bool changed = false;
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      if (JNT->coupledTo)
+      {
+        const double d = c->q[(size_t) JNT->jointIndex] - qIn[(size_t) JNT->jointIndex];
+        changed = changed || (d > 1.0e-8) || (d < -1.0e-8);
+      }
+    }
+  }
+  return changed;
+}
+
+extern "C" void RcsGraph_computeForwardKinematics(RcsGraph* self, const MatNd* q,
+                                                  const MatNd* q_dot)
+{
+  if (!self)
+  {
+    RCSB_FATAL("RcsGraph_computeForwardKinematics: graph is NULL");
+    return;
+  }
+  if ((q && q->m != self->dof) || (q_dot && q_dot->m != self->dof))
+  {
+    RCSB_FATAL("RcsGraph_computeForwardKinematics: q / q_dot must have dof = %d rows", self->dof);
+    return;
+  }
+  GraphCache* c = cacheOf(self);
+  if (!c)
+  {
+    RCSB_FATAL("RcsGraph_computeForwardKinematics: %s", rcsb_last_error());
+    return;
+  }
+  /* no slave update, always with velocities, graph->q untouched (Rcs_graph.c:301-322) */
+  runFk(self, c, q ? q->ele : self->q->ele, q_dot ? q_dot->ele : self->q_dot->ele, true, false);
+}
+
+namespace
+{
+
+void jacobianCommon(const RcsGraph* cself, const RcsBody* body, const double* B_pt,
+                    double A_BI[3][3], MatNd* J, bool rotation, const char* who)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  if (!self || !J)
+  {
+    RCSB_FATAL("%s: NULL argument", who);
+    return;
+  }
+  if (J->size < 3 * self->nJ)
+  {
+    RCSB_FATAL("%s: Jacobian has room for %u doubles, 3 x %u needed", who, J->size, self->nJ);
+    return;
+  }
+  MatNd_reshapeAndSetZero(J, 3, self->nJ);
+  if (!body || self->nJ == 0)
+  {
+    return;   /* NULL body = world frame: zero Jacobian (Rcs_kinematics.c:188-191, :424-427) */
+  }
+  if (A_BI)
+  {
+    RCSB_FATAL("%s: rotation into a frame A_BI is not supported, pass NULL (world frame)", who);
+    return;
+  }
+  GraphCache* c = cacheOf(self);
+  if (!c)
+  {
+    RCSB_FATAL("%s: %s", who, rcsb_last_error());
+    return;
+  }
+  const int eff = RcsGraph_bodyIndex(self, body);
+  if (eff < 0)
+  {
+    RCSB_FATAL("%s: body \"%s\" does not belong to the graph", who, body->name ? body->name : "?");
+    return;
+  }
+  const int bodySel[1] = {eff};
+  const int rc = fkCommon(c->model, 1, (int) self->dof, c->q.data(), nullptr, 1, bodySel, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, 1, bodySel, B_pt,
+                          rotation ? nullptr : J->ele, rotation ? J->ele : nullptr, nullptr,
+                          !c->coupled, RCSB_HOST_PTRS, nullptr);
+  if (rc != RCSB_OK)
+  {
+    RCSB_FATAL("%s: %s", who, rcsb_last_error());
+  }
+}
+
+}   // namespace
+
+extern "C" void RcsGraph_bodyPointJacobian(const RcsGraph* self, const RcsBody* body,
+                                           const double B_pt[3], double A_BI[3][3], MatNd* J)
+{
+  jacobianCommon(self, body, B_pt, A_BI, J, false, "RcsGraph_bodyPointJacobian");
+}
+
+extern "C" void RcsGraph_rotationJacobian(const RcsGraph* self, const RcsBody* body,
+                                          double A_BI[3][3], MatNd* J)
+{
+  jacobianCommon(self, body, nullptr, A_BI, J, true, "RcsGraph_rotationJacobian");
+}
+
+extern "C" double RcsGraph_computeKineticTerms(const RcsGraph* cself, MatNd* M, MatNd* h,
+                                               MatNd* F_gravity)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  if (!self)
+  {
+    RCSB_FATAL("RcsGraph_computeKineticTerms: graph is NULL");
+    return 0.0;
+  }
+  const unsigned int n = self->nJ;
+  if ((M && M->size < n * n) || (h && h->size < n) || (F_gravity && F_gravity->size < n))
+  {
+    RCSB_FATAL("RcsGraph_computeKineticTerms: an output matrix is too small for nJ = %u", n);
+    return 0.0;
+  }
+  GraphCache* c = cacheOf(self);
+  if (!c)
+  {
+    RCSB_FATAL("RcsGraph_computeKineticTerms: %s", rcsb_last_error());
+    return 0.0;
+  }
+  if (M)
+  {
+    MatNd_reshapeAndSetZero(M, n, n);
+  }
+  if (h)
+  {
+    MatNd_reshapeAndSetZero(h, n, 1);
+  }
+  if (F_gravity)
+  {
+    MatNd_reshapeAndSetZero(F_gravity, n, 1);
+  }
+  double E = 0.0;
+  /* the reference reads graph->q_dot and the body velocities of the last FK (Rcs_dynamics.c:
+   * 449-451, :346-377); both follow from the cached joint state */
+  const int rc = rcsb_kinetic_terms(c->model, 1, (int) self->dof, c->q.data(),
+                                    c->haveVel ? c->qd.data() : self->q_dot->ele,
+                                    M ? M->ele : nullptr, h ? h->ele : nullptr,
+                                    F_gravity ? F_gravity->ele : nullptr, &E, RCSB_HOST_PTRS,
+                                    nullptr);
+  if (rc != RCSB_OK)
+  {
+    RCSB_FATAL("RcsGraph_computeKineticTerms: %s", rcsb_last_error());
+    return 0.0;
+  }
+  return E;
+}

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Records golden input/output vectors from the UNMODIFIED reference (oracle/_ref/librcsref.so,
+built from /root/reference by oracle/ref_build/Makefile) into tests/golden/*.npz.
+
+The reference itself has no stored vectors for this path, and /root/reference
+does not exist on the GPU box; these small fixtures pin the numpy oracle and the CUDA path
+there. Re-run in the CPU container after changing graphs or cases:
+
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref  # noqa: E402
+from rcs_b200 import workload  # noqa: E402
+
+GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
+CASES = {
+    "wam_arm": dict(n=24, effectors=["BallTip", "Link4"]),
+    "wam_scenario": dict(n=16, effectors=["Hand", "PowerGrip"]),
+    "humanoid": dict(n=12, effectors=["RightHandTip", "LeftHandTip", "FootL"]),
+    "husky": dict(n=8, effectors=None),
+}
+
+
+def main():
+    ref.set_threads(1)
+    for name, case in CASES.items():
+        f = os.path.join(GRAPHS, name + ".xml")
+        g = ref.RefGraph(f)
+        lay = g.layout()
+        n = case["n"]
+        q, qd = workload.sample_states(lay, n, first=1000, with_velocity=True)
+        names = [b["name"] for b in lay["bodies"]]
+        effs = case["effectors"] or [names[-1], names[len(names) // 2]]
+        eff = [names.index(e) for e in effs]
+        pts = np.random.default_rng(3).uniform(-0.1, 0.1, size=(len(eff), 3))
+        fk = g.fk(q, qd, want=("A_BI", "A_JI", "xdot", "omega", "q"))
+        jac = g.fk_jacobians(q, eff, points=pts, want=("JT", "JR"))
+        kt = g.kinetic_terms(q, qd)
+        cog, jcog = g.cog(q)
+        out = dict(q=q, qd=qd, eff=np.array(eff), pts=pts, cog=cog, Jcog=jcog,
+                   **{"fk_" + k: v for k, v in fk.items()},
+                   **{"jac_" + k: v for k, v in jac.items()},
+                   **{"kt_" + k: v for k, v in kt.items()})
+        if name in ("wam_arm", "humanoid"):
+            tip = "BallTip" if name == "wam_arm" else "RightHandTip"
+            ik = ref.RefIk(f, [("XYZ", tip), ("ABC", tip)])
+            q_goal = workload.sample_states(lay, n, first=2000, margin=0.2)
+            x_des, J = ik.task_kinematics(q_goal)
+            q_start = q_goal + 0.1 * np.random.default_rng(5).uniform(-1, 1, size=q_goal.shape)
+            q1, dx1, dq1, det1 = ik.rmr(q_start, x_des, iters=1)
+            q10, dx10, dq10, det10 = ik.rmr(q_start, x_des, iters=10)
+            out.update(ik_tip=np.array(names.index(tip)), ik_q_start=q_start, ik_x_des=x_des,
+                       ik_J_goal=J, ik_q1=q1, ik_dx1=dx1, ik_dq1=dq1, ik_det1=det1, ik_q10=q10,
+                       ik_dx10=dx10, ik_det10=det10)
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
