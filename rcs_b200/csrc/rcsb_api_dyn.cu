@@ -340,11 +340,107 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
     }
   }
 
+  /* ---- single-chain program (fast path) -------------------------------------------------- */
+  const int* bodyParent = m->iarr(RCSB_A_BODY_PARENT);
+  const int* bodyJntStart = m->iarr(RCSB_A_BODY_JNT_START);
+  const int* bodyJntCount = m->iarr(RCSB_A_BODY_JNT_COUNT);
+  const int* bodyFlags = m->iarr(RCSB_A_BODY_FLAGS);
+  const int* jntType = m->iarr(RCSB_A_JNT_TYPE);
+  std::vector<int> progStart, prog, chainType, chainJoint, otherJoint;
+  std::vector<double> chainW, chainGain, chainQ0, otherW, otherGain, otherQ0;
+  int chainNc = 0;
+  {
+    bool eligible = (nTasks <= 2);
+    for (int t = 1; t < nTasks; ++t)
+    {
+      eligible = eligible && (body[t] == body[0]) && (kind[t] != kind[0]);
+    }
+    if (eligible)
+    {
+      std::vector<int> path;
+      for (int b = body[0]; b >= 0; b = bodyParent[b])
+      {
+        path.push_back(b);
+      }
+      progStart.push_back(0);
+      for (auto it = path.rbegin(); it != path.rend(); ++it)
+      {
+        const int b = *it;
+        for (int j = bodyJntStart[b]; j < bodyJntStart[b] + bodyJntCount[b]; ++j)
+        {
+          if (jntFlags[j] & RCSB_JF_HAS_AJP)
+          {
+            const int step[4] = {0, m->hdr.off[RCSB_A_JNT_AJP] + 96 * j, 0, 0};
+            prog.insert(prog.end(), step, step + 4);
+          }
+          if (jntJacobi[j] >= 0)
+          {
+            chainType.push_back(jntType[j]);
+            chainJoint.push_back(j);
+            progStart.push_back((int) prog.size() / 4);
+          }
+          else
+          {
+            const int step[4] = {1, jntType[j], j, 0};
+            prog.insert(prog.end(), step, step + 4);
+          }
+        }
+        if (bodyFlags[b] & RCSB_BF_HAS_ABP)
+        {
+          const int step[4] = {0, m->hdr.off[RCSB_A_BODY_ABP] + 96 * b, 0, 0};
+          prog.insert(prog.end(), step, step + 4);
+        }
+      }
+      progStart.push_back((int) prog.size() / 4);
+      chainNc = (int) chainJoint.size();
+      if (chainNc < 1 || chainNc > 8)
+      {
+        chainNc = 0;
+      }
+    }
+    if (chainNc > 0)
+    {
+      std::vector<char> onChain((size_t) dof, 0);
+      for (int c = 0; c < chainNc; ++c)
+      {
+        const int col = jntJacobi[chainJoint[c]];
+        onChain[(size_t) chainJoint[c]] = 1;
+        chainW.push_back(invWq[col]);
+        chainGain.push_back(jlGain[col]);
+        chainQ0.push_back(q0c[col]);
+      }
+      for (int j = 0; j < dof; ++j)
+      {
+        const int col = jntJacobi[j];
+        if (col >= 0 && !onChain[(size_t) j])
+        {
+          otherJoint.push_back(j);
+          otherW.push_back(invWq[col]);
+          otherGain.push_back(jlGain[col]);
+          otherQ0.push_back(q0c[col]);
+        }
+      }
+    }
+    else
+    {
+      progStart.assign(2, 0);
+      prog.clear();
+      chainType.clear();
+      chainJoint.clear();
+    }
+    if (prog.empty())
+    {
+      prog.assign(4, 0);
+    }
+  }
+
   RcsbIkPlanHeader ph;
   memset(&ph, 0, sizeof(ph));
   ph.nTasks = nTasks;
   ph.nx = 3 * nTasks;
   ph.nJ = nJ;
+  ph.chainNc = chainNc;
+  ph.nOther = (int) otherJoint.size();
   int off = align16((int) sizeof(ph));
   auto place = [&](int& field, size_t bytes) {
     field = off;
@@ -361,6 +457,18 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   place(ph.offInvWq, invWq.size() * 8);
   place(ph.offJlGain, jlGain.size() * 8);
   place(ph.offQ0, q0c.size() * 8);
+  auto atLeast1 = [](size_t n) { return n > 0 ? n : (size_t) 1; };
+  place(ph.offProgStart, progStart.size() * 4);
+  place(ph.offProg, prog.size() * 4);
+  place(ph.offChainType, atLeast1(chainType.size()) * 4);
+  place(ph.offChainJoint, atLeast1(chainJoint.size()) * 4);
+  place(ph.offChainW, atLeast1(chainW.size()) * 8);
+  place(ph.offChainGain, atLeast1(chainGain.size()) * 8);
+  place(ph.offChainQ0, atLeast1(chainQ0.size()) * 8);
+  place(ph.offOtherJoint, atLeast1(otherJoint.size()) * 4);
+  place(ph.offOtherW, atLeast1(otherW.size()) * 8);
+  place(ph.offOtherGain, atLeast1(otherGain.size()) * 8);
+  place(ph.offOtherQ0, atLeast1(otherQ0.size()) * 8);
   ph.totalBytes = off;
 
   std::vector<char> blob((size_t) ph.totalBytes, 0);
@@ -379,6 +487,23 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   memcpy(blob.data() + ph.offInvWq, invWq.data(), invWq.size() * 8);
   memcpy(blob.data() + ph.offJlGain, jlGain.data(), jlGain.size() * 8);
   memcpy(blob.data() + ph.offQ0, q0c.data(), q0c.size() * 8);
+  auto put = [&](int offset, const void* src, size_t bytes) {
+    if (bytes > 0)
+    {
+      memcpy(blob.data() + offset, src, bytes);
+    }
+  };
+  put(ph.offProgStart, progStart.data(), progStart.size() * 4);
+  put(ph.offProg, prog.data(), prog.size() * 4);
+  put(ph.offChainType, chainType.data(), chainType.size() * 4);
+  put(ph.offChainJoint, chainJoint.data(), chainJoint.size() * 4);
+  put(ph.offChainW, chainW.data(), chainW.size() * 8);
+  put(ph.offChainGain, chainGain.data(), chainGain.size() * 8);
+  put(ph.offChainQ0, chainQ0.data(), chainQ0.size() * 8);
+  put(ph.offOtherJoint, otherJoint.data(), otherJoint.size() * 4);
+  put(ph.offOtherW, otherW.data(), otherW.size() * 8);
+  put(ph.offOtherGain, otherGain.data(), otherGain.size() * 8);
+  put(ph.offOtherQ0, otherQ0.data(), otherQ0.size() * 8);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -386,6 +511,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   dp.bytes = ph.totalBytes;
   dp.aux0 = ph.nx;
+  dp.aux1 = ph.chainNc;
   auto ins = m->ikPlans.emplace(key, dp);
   *out = &ins.first->second;
   return RCSB_OK;
@@ -410,7 +536,10 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
   a.dq = dq;
   a.det = det;
   RCSB_CUDA(cudaSetDevice(m->device));
-  cudaError_t e = rcsb_launch_ik(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, stream);
+  const char* noFast = getenv("RCSB_IK_GENERAL");   /* force the general kernel (tests) */
+  const int chainNc = (noFast && noFast[0] == '1') || iters > 64 ? 0 : plan->aux1;
+  cudaError_t e = rcsb_launch_ik(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, chainNc,
+                                 stream);
   if (e == cudaErrorInvalidValue)
   {
     cudaGetLastError();

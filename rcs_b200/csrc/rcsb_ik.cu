@@ -51,10 +51,32 @@ struct IkPlanView
   const double* invWq;
   const double* jlGain;
   const double* q0;
+  const int* progStart;
+  const int4* prog;
+  const int* chainType;
+  const int* chainJoint;
+  const double* chainW;
+  const double* chainGain;
+  const double* chainQ0;
+  const int* otherJoint;
+  const double* otherW;
+  const double* otherGain;
+  const double* otherQ0;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
     hdr = reinterpret_cast<const RcsbIkPlanHeader*>(blob);
+    progStart = reinterpret_cast<const int*>(blob + hdr->offProgStart);
+    prog = reinterpret_cast<const int4*>(blob + hdr->offProg);
+    chainType = reinterpret_cast<const int*>(blob + hdr->offChainType);
+    chainJoint = reinterpret_cast<const int*>(blob + hdr->offChainJoint);
+    chainW = reinterpret_cast<const double*>(blob + hdr->offChainW);
+    chainGain = reinterpret_cast<const double*>(blob + hdr->offChainGain);
+    chainQ0 = reinterpret_cast<const double*>(blob + hdr->offChainQ0);
+    otherJoint = reinterpret_cast<const int*>(blob + hdr->offOtherJoint);
+    otherW = reinterpret_cast<const double*>(blob + hdr->offOtherW);
+    otherGain = reinterpret_cast<const double*>(blob + hdr->offOtherGain);
+    otherQ0 = reinterpret_cast<const double*>(blob + hdr->offOtherQ0);
     taskKind = reinterpret_cast<const int*>(blob + hdr->offTaskKind);
     taskBody = reinterpret_cast<const int*>(blob + hdr->offTaskBody);
     bodyTaskStart = reinterpret_cast<const int*>(blob + hdr->offBodyTaskStart);
@@ -104,14 +126,11 @@ __device__ __forceinline__ void fromEuler(double A[9], const double ea[3])
   A[8] = ca * cb;
 }
 
-/* Orientation error of TaskEuler3D::computeDX (src/RcsCore/TaskEuler3D.cpp:243-262) */
-__device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3],
-                                               const double xCurr[3])
+/* Orientation error of TaskEuler3D::computeDX (src/RcsCore/TaskEuler3D.cpp:243-262) between
+ * the current rotation Ac and the desired rotation Ad (both row-major A_KI). */
+__device__ __forceinline__ void rotationTaskError(double dx[3], const double Ad[9],
+                                                  const double Ac[9])
 {
-  double Ac[9], Ad[9];
-  fromEuler(Ac, xCurr);
-  fromEuler(Ad, xDes);
-
   double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i)
@@ -197,6 +216,17 @@ __device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3
   {
     dx[i] = (Ac[i] * ax[0] + Ac[3 + i] * ax[1] + Ac[6 + i] * ax[2]) * angle;
   }
+}
+
+/* The reference goes through the Euler angles of both frames (x = Mat3d_toEulerAngles(A_curr),
+ * then Mat3d_fromEulerAngles of x and x_des inside computeDX). */
+__device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3],
+                                               const double xCurr[3])
+{
+  double Ac[9], Ad[9];
+  fromEuler(Ac, xCurr);
+  fromEuler(Ad, xDes);
+  rotationTaskError(dx, Ad, Ac);
 }
 
 template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS>
@@ -582,6 +612,440 @@ ikKernel(const IkArgs a)
   }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Single-chain fast path                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One step of the root-to-effector program: a constant relative transform, or the motion of a
+ * joint that is not a Jacobian column (constrained: its value never changes during the solve). */
+__device__ __forceinline__ void chainStep(Frame& f, const int4 st, const char* sModel,
+                                          const double* __restrict__ qRow)
+{
+  if (st.x == 0)
+  {
+    applyRel(f, reinterpret_cast<const double*>(sModel + st.y));
+    return;
+  }
+  const double qj = qRow[st.z];
+  const int dir = st.y % 3;
+  if (st.y < 3)
+  {
+    double sn, cs;
+    sincos(qj, &sn, &cs);
+    rotateAboutAxis(f, dir, sn, cs);
+  }
+  else
+  {
+    double ax[3];
+    axisOf(f, dir, ax);
+    f.o[0] += qj * ax[0];
+    f.o[1] += qj * ax[1];
+    f.o[2] += qj * ax[2];
+  }
+}
+
+/*
+ * All tasks on one effector, NC <= 8 Jacobian columns on its chain: everything the iteration
+ * needs stays in registers (column axes and Jacobian columns 6 NC doubles, the lower triangle
+ * of J invWq J^T + lambda 1, NX (NX + 1) / 2 doubles), all loops over columns and task rows
+ * are unrolled at compile time, bodies off the chain are never visited.
+ *
+ * Same step as the general kernel, evaluated as
+ *     dq = g + invWq J^T y,   (J invWq J^T + lambda 1) y = dx - J g,   g = invWq (-alpha dH)
+ * which equals J# dx + (1 - J# J) g of IkSolverRMR.cpp:415-596 without forming J# and the
+ * null-space projector; y comes from the same Cholesky factor (forward / backward
+ * substitution instead of the explicit inverse L^-T L^-1). The orientation error uses the
+ * effector's rotation matrix directly instead of rebuilding it from its Euler angles
+ * (TaskEuler3D.cpp:110, :243): identical up to rounding away from gimbal lock.
+ */
+template <int NC, int NX>
+__global__ void __launch_bounds__(RCSB_IK_THREADS)
+ikChainKernel(const IkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [9][RCSB_IK_THREADS] */
+  stageBlob(sModel, a.model, a.modelBytes);
+  stageBlob(sPlan, a.plan, a.planBytes);
+  __syncthreads();
+
+  ModelView m;
+  m.bind(sModel);
+  IkPlanView p;
+  p.bind(sPlan);
+
+  const int tid = threadIdx.x;
+  const long s = (long) blockIdx.x * RCSB_IK_THREADS + tid;
+  if (s >= a.N)
+  {
+    return;
+  }
+
+  constexpr int NT = NX / 3;
+  constexpr int NA = NX * (NX + 1) / 2;
+  const int dof = m.hdr->dof;
+  const bool xyzFirst = p.taskKind[0] == RCSB_TASK_XYZ;
+  const bool hasAbc = (NT == 2) || !xyzFirst;
+  const bool hasXyz = (NT == 2) || xyzFirst;
+  double* qRow = a.q + s * dof;
+  const double* xd = a.xDes + s * NX;
+
+  double qc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+  {
+    qc[c] = qRow[p.chainJoint[c]];
+  }
+
+  /* desired position / rotation; the rotation is parked in shared memory */
+  double xPos[3] = {0.0, 0.0, 0.0};
+  if (hasXyz)
+  {
+    const int o = (NT == 2 && !xyzFirst) ? 3 : 0;
+    xPos[0] = xd[o];
+    xPos[1] = xd[o + 1];
+    xPos[2] = xd[o + 2];
+  }
+  if (hasAbc)
+  {
+    const int o = (NT == 2 && xyzFirst) ? 3 : 0;
+    const double ea[3] = {xd[o], xd[o + 1], xd[o + 2]};
+    double Ad[9];
+    fromEuler(Ad, ea);
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+    {
+      sAd[i * RCSB_IK_THREADS + tid] = Ad[i];
+    }
+  }
+
+  double dx[NX], dq[NC];
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+    dx[i] = 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+  {
+    dq[c] = 0.0;
+  }
+  double det = 0.0;
+  unsigned long long singular = 0ull;
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    /* ---- forward kinematics along the chain ------------------------------------------------ */
+    Frame f;
+    setIdentity(f);
+    double ax[NC][3], jo[NC][3];
+    bool isRot[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
+      {
+        chainStep(f, p.prog[k], sModel, qRow);
+      }
+      const int type = p.chainType[c];
+      const int dir = type % 3;
+      isRot[c] = type < 3;
+      if (isRot[c])
+      {
+        double sn, cs;
+        sincos(qc[c], &sn, &cs);
+        rotateAboutAxis(f, dir, sn, cs);
+        axisOf(f, dir, ax[c]);
+      }
+      else
+      {
+        axisOf(f, dir, ax[c]);
+        f.o[0] += qc[c] * ax[c][0];
+        f.o[1] += qc[c] * ax[c][1];
+        f.o[2] += qc[c] * ax[c][2];
+      }
+      jo[c][0] = f.o[0];
+      jo[c][1] = f.o[1];
+      jo[c][2] = f.o[2];
+    }
+    for (int k = p.progStart[NC]; k < p.progStart[NC + 1]; ++k)
+    {
+      chainStep(f, p.prog[k], sModel, qRow);
+    }
+
+    /* ---- task error (ControllerBase::computeDX) ---------------------------------------------- */
+    double ePos[3] = {0.0, 0.0, 0.0}, eRot[3] = {0.0, 0.0, 0.0};
+    if (hasXyz)
+    {
+      ePos[0] = xPos[0] - f.o[0];
+      ePos[1] = xPos[1] - f.o[1];
+      ePos[2] = xPos[2] - f.o[2];
+    }
+    if (hasAbc)
+    {
+      double Ad[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        Ad[i] = sAd[i * RCSB_IK_THREADS + tid];
+      }
+      rotationTaskError(eRot, Ad, f.R);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+      dx[i] = xyzFirst ? ePos[i] : eRot[i];
+      if (NT == 2)
+      {
+        dx[3 + i] = xyzFirst ? eRot[i] : ePos[i];
+      }
+    }
+
+    /* ---- Jacobian columns in place: jo <- translation rows, ax <- rotation rows ------------- */
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      if (isRot[c])
+      {
+        const double d0 = f.o[0] - jo[c][0], d1 = f.o[1] - jo[c][1], d2 = f.o[2] - jo[c][2];
+        jo[c][0] = ax[c][1] * d2 - ax[c][2] * d1;
+        jo[c][1] = ax[c][2] * d0 - ax[c][0] * d2;
+        jo[c][2] = ax[c][0] * d1 - ax[c][1] * d0;
+      }
+      else
+      {
+        jo[c][0] = ax[c][0];
+        jo[c][1] = ax[c][1];
+        jo[c][2] = ax[c][2];
+        ax[c][0] = ax[c][1] = ax[c][2] = 0.0;
+      }
+    }
+
+    /* ---- A = J invWq J^T + lambda 1 (lower triangle), r = dx - J g ---------------------------- */
+    double A[NA], r[NX], g[NC];
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+    {
+      A[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      r[i] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      const double w = p.chainW[c];
+      g[c] = w * (-(a.alpha * (p.chainGain[c] * (qc[c] - p.chainQ0[c]))));
+      double u[NX];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        u[i] = xyzFirst ? jo[c][i] : ax[c][i];
+        if (NT == 2)
+        {
+          u[3 + i] = xyzFirst ? ax[c][i] : jo[c][i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        const double wu = w * u[i];
+#pragma unroll
+        for (int k = 0; k <= i; ++k)
+        {
+          A[i * (i + 1) / 2 + k] += u[k] * wu;
+        }
+        r[i] += u[i] * g[c];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      A[i * (i + 1) / 2 + i] += a.lambda;
+      r[i] = dx[i] - r[i];
+    }
+
+    /* ---- Banachiewicz Cholesky (Rcs_linAlg.c:66-101), det = prod L_ii^2 ------------------------ */
+    double invd[NX];
+    bool ok = true;
+    det = 1.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+#pragma unroll
+      for (int k = 0; k <= i; ++k)
+      {
+        double sum = A[i * (i + 1) / 2 + k];
+#pragma unroll
+        for (int t = 0; t < k; ++t)
+        {
+          sum -= A[i * (i + 1) / 2 + t] * A[k * (k + 1) / 2 + t];
+        }
+        if (k < i)
+        {
+          A[i * (i + 1) / 2 + k] = sum * invd[k];
+        }
+        else
+        {
+          ok = ok && (sum > 0.0);
+          const double d = sqrt(ok ? sum : 1.0);
+          A[i * (i + 1) / 2 + i] = d;
+          invd[i] = 1.0 / d;
+          det *= d * d;
+        }
+      }
+    }
+    if (!ok)
+    {
+      /* singular: zero displacement, q untouched (Rcs_MatNd.c:1833, IkSolverRMR.cpp:470-480) */
+      det = 0.0;
+      singular |= 1ull << it;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+      {
+        dq[c] = 0.0;
+      }
+      continue;
+    }
+
+    /* ---- y = (L L^T)^-1 r ------------------------------------------------------------------------ */
+    double y[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      double sum = r[i];
+#pragma unroll
+      for (int t = 0; t < i; ++t)
+      {
+        sum -= A[i * (i + 1) / 2 + t] * y[t];
+      }
+      y[i] = sum * invd[i];
+    }
+#pragma unroll
+    for (int i = NX - 1; i >= 0; --i)
+    {
+      double sum = y[i];
+#pragma unroll
+      for (int t = i + 1; t < NX; ++t)
+      {
+        sum -= A[t * (t + 1) / 2 + i] * y[t];
+      }
+      y[i] = sum * invd[i];
+    }
+
+    /* ---- dq = g + invWq J^T y; q += dq ----------------------------------------------------------- */
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        sum += (xyzFirst ? jo[c][i] : ax[c][i]) * y[i];
+      }
+      if (NT == 2)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          sum += (xyzFirst ? ax[c][i] : jo[c][i]) * y[3 + i];
+        }
+      }
+      dq[c] = g[c] + p.chainW[c] * sum;
+      qc[c] += dq[c];
+    }
+  }
+
+  /* ---- results ---------------------------------------------------------------------------------- */
+  const bool lastSingular = a.iters > 0 && ((singular >> (a.iters - 1)) & 1ull);
+  if (a.dq)
+  {
+    for (int j = 0; j < dof; ++j)
+    {
+      a.dq[s * dof + j] = 0.0;
+    }
+  }
+  /* unconstrained joints off the chain have zero Jacobian columns: they only follow the
+   * joint-limit gradient, dq_i = g_i, in every non-singular iteration */
+  for (int k = 0; k < p.hdr->nOther; ++k)
+  {
+    const int j = p.otherJoint[k];
+    double qj = qRow[j], step = 0.0;
+    for (int it = 0; it < a.iters; ++it)
+    {
+      step = 0.0;
+      if (!((singular >> it) & 1ull))
+      {
+        step = p.otherW[k] * (-(a.alpha * (p.otherGain[k] * (qj - p.otherQ0[k]))));
+        qj += step;
+      }
+    }
+    qRow[j] = qj;
+    if (a.dq)
+    {
+      a.dq[s * dof + j] = step;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+  {
+    qRow[p.chainJoint[c]] = qc[c];
+    if (a.dq)
+    {
+      a.dq[s * dof + p.chainJoint[c]] = lastSingular ? 0.0 : dq[c];
+    }
+  }
+  if (a.dx)
+  {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      a.dx[s * NX + i] = dx[i];
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = det;
+  }
+}
+
+template <int NC, int NX>
+static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
+                           9 * RCSB_IK_THREADS * sizeof(double);
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
+  auto k = ikChainKernel<NC, NX>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smemBytes);
+  if (e != cudaSuccess)
+  {
+    return e;
+  }
+  k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int NX>
+static cudaError_t launchChainNc(const IkArgs& a, int nc, cudaStream_t stream)
+{
+  switch (nc)
+  {
+    case 1: return launchChain<1, NX>(a, stream);
+    case 2: return launchChain<2, NX>(a, stream);
+    case 3: return launchChain<3, NX>(a, stream);
+    case 4: return launchChain<4, NX>(a, stream);
+    case 5: return launchChain<5, NX>(a, stream);
+    case 6: return launchChain<6, NX>(a, stream);
+    case 7: return launchChain<7, NX>(a, stream);
+    case 8: return launchChain<8, NX>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <int MAXNX, int MAXNJ, int MAXDOF>
 static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
 {
@@ -613,12 +1077,16 @@ static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
 }   // namespace rcsb
 
 extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
-                                      cudaStream_t stream)
+                                      int chainNc, cudaStream_t stream)
 {
   using namespace rcsb;
   if (a->N <= 0)
   {
     return cudaSuccess;
+  }
+  if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
+  {
+    return nx == 3 ? launchChainNc<3>(*a, chainNc, stream) : launchChainNc<6>(*a, chainNc, stream);
   }
   if (nx <= 6 && nJ <= 8 && dof <= 8)
   {

@@ -75,7 +75,7 @@ struct IkArgs
 extern "C" {
 cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cudaStream_t stream);
 cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int blocks, cudaStream_t stream);
-cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
+cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            cudaStream_t stream);
 }
 

@@ -103,6 +103,28 @@ typedef struct
   int offJlGain;        /* double[nJ]: weightJL / (q_max - q_min)^2, 0 if the range is not
                            positive (Rcs_kinematics.c:1496) */
   int offQ0;            /* double[nJ] */
+  /*
+   * Single-chain fast path (rcsb_ik.cu, ikChainKernel): all tasks sit on one effector whose
+   * backward joint chain has chainNc <= 8 unconstrained joints. The walk from the root to the
+   * effector is a straight-line program: per chain column c the steps progStart[c] ..
+   * progStart[c + 1] (constant transforms and constrained joints) precede the column's own
+   * joint motion; the steps progStart[chainNc] .. progStart[chainNc + 1] lead on to the
+   * effector body. chainNc == 0: not eligible, the general kernel runs.
+   */
+  int chainNc;
+  int nOther;           /* unconstrained joints that are not on the chain */
+  int offProgStart;     /* int[chainNc + 2] */
+  int offProg;          /* int4[nSteps]: {op, a, b, 0}; op 0: relative transform at byte offset a
+                           of the flat model; op 1: joint of type a, jointIndex b, value from q */
+  int offChainType;     /* int[chainNc]: RCSJOINT_TYPE of the column's joint */
+  int offChainJoint;    /* int[chainNc]: jointIndex */
+  int offChainW;        /* double[chainNc]: invWq */
+  int offChainGain;     /* double[chainNc]: joint-limit gain */
+  int offChainQ0;       /* double[chainNc] */
+  int offOtherJoint;    /* int[nOther] jointIndex */
+  int offOtherW;        /* double[nOther] */
+  int offOtherGain;     /* double[nOther] */
+  int offOtherQ0;       /* double[nOther] */
   int pad;
 } RcsbIkPlanHeader;
 

@@ -59,8 +59,13 @@ def _targets(g, rik, n, seed_first=0, perturb=0.15):
     return np.ascontiguousarray(q_start), np.ascontiguousarray(x_des)
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["chain-kernel", "general-kernel"])
 @pytest.mark.parametrize("kinds", [("XYZ", "ABC"), ("XYZ",), ("ABC",), ("ABC", "XYZ")])
-def test_one_iteration_matches_reference(kinds, refmod, cuda_device):
+def test_one_iteration_matches_reference(kinds, general, refmod, cuda_device, monkeypatch):
+    """The single-effector chains take the register-resident ikChainKernel; RCSB_IK_GENERAL=1
+    forces the general kernel that serves multi-effector task sets and long chains."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
     g, m, rik, tasks = _setup("wam_arm", "BallTip", refmod, cuda_device, kinds)
     q0, x_des = _targets(g, rik, 2000)
     q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
@@ -155,3 +160,36 @@ def test_coupled_joints_are_rejected(cuda_device):
     m = rcs_b200.Model(g, cuda_device)
     with pytest.raises(rcs_b200.RcsbError, match="coupled"):
         m.ik_rmr([(TASK_XYZ, g.body_index("Hand"))], np.zeros((1, g.dof)), np.zeros((1, 3)))
+
+
+def test_chain_and_general_kernels_agree_over_ten_iterations(refmod, cuda_device, monkeypatch):
+    g, m, rik, tasks = _setup("wam_arm", "BallTip", refmod, cuda_device)
+    q0, x_des = _targets(g, rik, 2048, seed_first=500, perturb=0.1)
+    qa, qb = q0.copy(), q0.copy()
+    oa = m.ik_rmr(tasks, qa, x_des, iters=10, want=("dx", "dq", "det"))
+    monkeypatch.setenv("RCSB_IK_GENERAL", "1")
+    ob = m.ik_rmr(tasks, qb, x_des, iters=10, want=("dx", "dq", "det"))
+    cond = step_condition(rik, q0)
+    ok = cond < 1.0e4
+    assert_step_close(qa[ok] - q0[ok], qb[ok] - q0[ok], 10.0 * cond[ok], "q: chain vs general")
+
+
+@pytest.mark.parametrize("eff,kinds", [("Helmet", ("XYZ", "ABC")), ("FootL", ("ABC", "XYZ")),
+                                       ("HeadPan", ("XYZ",))])
+def test_short_chains_on_the_humanoid(eff, kinds, refmod, cuda_device):
+    """Chains of 7-8 columns inside a 34-column graph: the joints off the chain only follow the
+    joint-limit gradient (zero Jacobian columns)."""
+    g, m, rik, tasks = _setup("humanoid", eff, refmod, cuda_device, kinds)
+    q0, x_des = _targets(g, rik, 400, seed_first=21, perturb=0.05)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx")
+    cond = step_condition(rik, q0)
+    assert_step_close(out["dq"], dq_ref, cond, "dq")
+    assert_step_close(q - q0, q_ref - q0, cond, "q")
+    q3_ref, _, _, _ = rik.rmr(q0, x_des, iters=3)
+    q3 = q0.copy()
+    m.ik_rmr(tasks, q3, x_des, iters=3)
+    ok = cond < 1.0e4
+    assert_step_close(q3[ok] - q0[ok], q3_ref[ok] - q0[ok], 3.0 * cond[ok], "q after 3 iterations")
