@@ -80,82 +80,153 @@ int buildKtPlan(RcsbModel* m)
     }
   }
 
+  /* walk bookkeeping: the accumulator is emitted as a run whenever the walk moves to a body of
+   * another link; every record of the state gets its offset in the order of production */
+  const int* bodyFlagsArr = m->iarr(RCSB_A_BODY_FLAGS);
+  std::vector<int> bodyEmit((size_t) nb + 1, 0), runLink, runRec;
+  std::vector<int> colRec(nJ > 0 ? nJ : 1, 0);
+  int rec = 0;
+  {
+    int cur = -1;
+    bool dirty = false;
+    for (int b = 0; b < nb; ++b)
+    {
+      if (bodyLink[b] != cur)
+      {
+        if (cur >= 0 && dirty)
+        {
+          bodyEmit[b] = 1;
+          runLink.push_back(cur);
+          runRec.push_back(rec);
+          rec += RCSB_KT_LINK_REC;
+        }
+        cur = bodyLink[b];
+        dirty = false;
+      }
+      for (int j = bodyJntStart[b]; j < bodyJntStart[b] + bodyJntCount[b]; ++j)
+      {
+        if (jntJacobi[j] >= 0)
+        {
+          colRec[jntJacobi[j]] = rec;
+          rec += RCSB_KT_COL_REC;
+        }
+      }
+      if (cur >= 0 && (bodyFlagsArr[b] & RCSB_BF_HAS_MASS))
+      {
+        dirty = true;
+      }
+    }
+    if (cur >= 0 && dirty)
+    {
+      bodyEmit[nb] = 1;
+      runLink.push_back(cur);
+      runRec.push_back(rec);
+      rec += RCSB_KT_LINK_REC;
+    }
+  }
+  const int nRuns = (int) runLink.size();
+
+  /* structurally non-zero entries of the upper triangle: (ancestor column, column) */
+  std::vector<int> pairs;
+  for (int k = 0; k < nJ; ++k)
+  {
+    for (int i = 0; i <= k; ++i)
+    {
+      if (rel[(size_t) i * nJ + k] == 1)
+      {
+        pairs.push_back(i | (k << 16));
+      }
+    }
+  }
+  bool symmetric = true;
+  {
+    const double* I = m->darr(RCSB_A_BODY_INERTIA);
+    for (int b = 0; b < nb; ++b)
+    {
+      symmetric = symmetric && I[9 * b + 1] == I[9 * b + 3] && I[9 * b + 2] == I[9 * b + 6] &&
+                  I[9 * b + 5] == I[9 * b + 7];
+    }
+  }
+
   RcsbKtPlanHeader ph;
   memset(&ph, 0, sizeof(ph));
   ph.nLinks = nLinks;
   ph.nJ = nJ;
-  ph.scrComp = 0;
-  ph.scrWr = 13 * nLinks;
-  ph.scrJa = 19 * nLinks;
-  ph.scrPl = 19 * nLinks + 6 * nJ;
-  ph.scrQd = 19 * nLinks + 15 * nJ;
-  ph.scratchDoubles = 19 * nLinks + 16 * nJ;
-  ph.invNJ = nJ > 0 ? 1.0f / (float) nJ : 0.0f;
+  ph.nRuns = nRuns;
+  ph.nPairs = (int) pairs.size();
+  ph.symmetric = symmetric ? 1 : 0;
+  ph.recV = rec;
+  ph.recDoubles = (rec + 1 + 3) & ~3;
   int off = align16((int) sizeof(ph));
-  ph.offBodyLink = off;
-  off = align16(off + nb * 4);
-  ph.offLinkParent = off;
-  off = align16(off + (nLinks > 0 ? nLinks : 1) * 4);
-  ph.offColJoint = off;
-  off = align16(off + (int) colJoint.size() * 4);
-  ph.offColLink = off;
-  off = align16(off + (int) colLink.size() * 4);
-  ph.offColIsRot = off;
-  off = align16(off + (int) colIsRot.size() * 4);
-  ph.offRel = off;
-  off = align16(off + (int) rel.size());
+  auto place = [&](int& field, size_t bytes) {
+    field = off;
+    off = align16(off + (int) (bytes > 0 ? bytes : 4));
+  };
+  place(ph.offBodyLink, (size_t) nb * 4);
+  place(ph.offBodyEmit, ((size_t) nb + 1) * 4);
+  place(ph.offLinkParent, (size_t) nLinks * 4);
+  place(ph.offColJoint, colJoint.size() * 4);
+  place(ph.offColLink, colLink.size() * 4);
+  place(ph.offColIsRot, colIsRot.size() * 4);
+  place(ph.offColRec, colRec.size() * 4);
+  place(ph.offRunLink, (size_t) nRuns * 4);
+  place(ph.offRunRec, (size_t) nRuns * 4);
+  place(ph.offPairs, pairs.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob((size_t) ph.totalBytes, 0);
+  auto put = [&](int offset, const void* src, size_t bytes) {
+    if (bytes > 0)
+    {
+      memcpy(blob.data() + offset, src, bytes);
+    }
+  };
   memcpy(blob.data(), &ph, sizeof(ph));
-  memcpy(blob.data() + ph.offBodyLink, bodyLink.data(), (size_t) nb * 4);
-  if (nLinks > 0)
-  {
-    memcpy(blob.data() + ph.offLinkParent, linkParent.data(), (size_t) nLinks * 4);
-  }
-  memcpy(blob.data() + ph.offColJoint, colJoint.data(), colJoint.size() * 4);
-  memcpy(blob.data() + ph.offColLink, colLink.data(), colLink.size() * 4);
-  memcpy(blob.data() + ph.offColIsRot, colIsRot.data(), colIsRot.size() * 4);
-  memcpy(blob.data() + ph.offRel, rel.data(), rel.size());
+  put(ph.offBodyLink, bodyLink.data(), (size_t) nb * 4);
+  put(ph.offBodyEmit, bodyEmit.data(), ((size_t) nb + 1) * 4);
+  put(ph.offLinkParent, linkParent.data(), (size_t) nLinks * 4);
+  put(ph.offColJoint, colJoint.data(), colJoint.size() * 4);
+  put(ph.offColLink, colLink.data(), colLink.size() * 4);
+  put(ph.offColIsRot, colIsRot.data(), colIsRot.size() * 4);
+  put(ph.offColRec, colRec.data(), colRec.size() * 4);
+  put(ph.offRunLink, runLink.data(), (size_t) nRuns * 4);
+  put(ph.offRunRec, runRec.data(), (size_t) nRuns * 4);
+  put(ph.offPairs, pairs.data(), pairs.size() * 4);
 
   RCSB_CUDA(cudaSetDevice(m->device));
   RCSB_CUDA(cudaMalloc(&m->ktPlan.dev, blob.size()));
   RCSB_CUDA(cudaMemcpy(m->ktPlan.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   m->ktPlan.bytes = ph.totalBytes;
-  m->ktPlan.aux0 = ph.scratchDoubles;
+  m->ktPlan.aux0 = ph.recDoubles;
+  m->ktPlan.aux1 = ph.nLinks;
   m->ktPlanBuilt = true;
   return RCSB_OK;
 }
 
-/* Threads in flight: the per-thread workspace (scratchDoubles x 8 B) of all of them should
- * stay resident in L2 (126 MB on B200); RCSB_KT_BLOCKS_PER_SM overrides the choice. */
-int ktBlocks(const RcsbModel* m, int scratchDoubles)
+/* States per pass: the records of one pass (recDoubles x 8 B per state) are written by the walk
+ * kernel and read back by the assembly kernel right after. RCSB_KT_CHUNK overrides. */
+long ktChunk(const RcsbModel* m, int recDoubles)
 {
-  int perSm = 0;
-  const char* env = getenv("RCSB_KT_BLOCKS_PER_SM");
-  if (env)
+  const char* env = getenv("RCSB_KT_CHUNK");
+  long chunk = env ? atol(env) : 0;
+  if (chunk <= 0)
   {
-    perSm = atoi(env);
+    /* enough walk blocks to fill every SM twice over; see DESIGN.md for the measurements */
+    (void) recDoubles;
+    chunk = (long) m->smCount * 4 * RCSB_KT_WALK_THREADS;
   }
-  if (perSm <= 0)
-  {
-    /* measured on B200 (humanoid, 256K states): 1 block/SM 12.6, 2: 19.6, 3: 25.1, 4: 31.4,
-     * 6: 26.3, 8: 31.3 M states/s — latency, not L2 capacity, is what limits this kernel */
-    (void) scratchDoubles;
-    perSm = 4;
-  }
-  return perSm * m->smCount;
+  return (chunk + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS * RCSB_KT_WALK_THREADS;
 }
 
 int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
              double* h, double* Fg, double* E, cudaStream_t stream, int ws)
 {
-  const int blocks = ktBlocks(m, m->ktPlan.aux0);
-  const size_t T = (size_t) blocks * RCSB_KT_THREADS;
-  const size_t need = T * (size_t) (m->ktPlan.aux0 > 0 ? m->ktPlan.aux0 : 1);
+  const int recDoubles = m->ktPlan.aux0;
+  const long chunk = ktChunk(m, recDoubles) < N ? ktChunk(m, recDoubles) : N;
+  const size_t need = (size_t) chunk * (size_t) recDoubles;
   RCSB_CUDA(cudaSetDevice(m->device));
   {
-    /* one workspace per staging stream: kernels of the two streams may overlap */
+    /* one record buffer per staging stream: kernels of the two streams may overlap */
     std::lock_guard<std::recursive_mutex> lock(m->mtx);
     if (m->ktScratchDoubles[ws] < need)
     {
@@ -170,23 +241,28 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     }
   }
 
-  rcsb::KtArgs a;
-  a.model = m->dev;
-  a.plan = m->ktPlan.dev;
-  a.modelBytes = m->hdr.totalBytes;
-  a.planBytes = m->ktPlan.bytes;
-  a.N = N;
-  a.qdim = qdim;
-  a.q = q;
-  a.qd = qd;
-  a.M = M;
-  a.h = h;
-  a.Fg = Fg;
-  a.E = E;
-  a.scratch = m->ktScratch[ws];
-  a.scratchStride = (long) T;
-  RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, blocks, stream));
-  g_launches.fetch_add(1);
+  const long nJ = m->hdr.nJ;
+  for (long s0 = 0; s0 < N; s0 += chunk)
+  {
+    const long n = (N - s0 < chunk) ? (N - s0) : chunk;
+    rcsb::KtArgs a;
+    a.model = m->dev;
+    a.plan = m->ktPlan.dev;
+    a.modelBytes = m->hdr.totalBytes;
+    a.planBytes = m->ktPlan.bytes;
+    a.N = n;
+    a.qdim = qdim;
+    a.q = q + s0 * qdim;
+    a.qd = qd ? qd + s0 * qdim : nullptr;
+    a.M = M ? M + s0 * nJ * nJ : nullptr;
+    a.h = h ? h + s0 * nJ : nullptr;
+    a.Fg = Fg ? Fg + s0 * nJ : nullptr;
+    a.E = E ? E + s0 : nullptr;
+    a.rec = m->ktScratch[ws];
+    a.recDoubles = recDoubles;
+    RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, m->ktPlan.aux1, m->smCount, stream));
+    g_launches.fetch_add(2);
+  }
   return RCSB_OK;
 }
 

@@ -8,7 +8,8 @@
 
 #define RCSB_FK_THREADS 128
 #define RCSB_MAX_FRAME_SLOTS 8
-#define RCSB_KT_THREADS 64
+#define RCSB_KT_WALK_THREADS 64
+#define RCSB_KT_ASM_THREADS 128
 #define RCSB_IK_THREADS 128
 
 namespace rcsb
@@ -49,8 +50,8 @@ struct KtArgs
   double* h;
   double* Fg;
   double* E;
-  double* scratch;     /* per-thread workspace in global memory (L2 resident) */
-  long scratchStride;  /* doubles between consecutive workspace elements = threads in flight */
+  double* rec;         /* N x recDoubles per-state records (walk -> assembly) */
+  int recDoubles;
 };
 
 struct IkArgs
@@ -74,7 +75,9 @@ struct IkArgs
 
 extern "C" {
 cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cudaStream_t stream);
-cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int blocks, cudaStream_t stream);
+/* enqueues the walk kernel and the assembly kernel (2 launches) */
+cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nLinks, int smCount,
+                           cudaStream_t stream);
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            cudaStream_t stream);
 }

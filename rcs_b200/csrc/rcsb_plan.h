@@ -55,30 +55,45 @@ typedef struct
  * every massive body is lumped into its nearest ancestor-or-self link, so that subtree
  * (composite) quantities only have to be kept per link.
  *
- * Per-thread workspace layout (doubles, element k of thread t at scratch[k * stride + t]):
- *   comp  13 * nLinks   composite m, m c (3), inertia about the world origin (9, row-major,
- *                       not symmetrised: the reference uses the tensor of the file as given)
- *   wr     6 * nLinks   composite bias wrench F (3), N about the world origin (3)
- *   ja     6 * nJ       per Jacobian column: joint axis (3), joint origin (3)
- *   pl     9 * nJ       per column: momentum of its composite under unit joint rate p (3),
- *                       L (3), and L with the transposed inertia (3)
- *   qd         nJ       joint rates in IK order
+ * The computation runs as two kernels joined by a per-state record in global memory:
+ *   ktWalkKernel      one thread per state, depth-first walk; the mass properties of the
+ *                     bodies lumped into the current link are summed in one accumulator, which
+ *                     is emitted as a "run" whenever the walk moves on to another link
+ *   ktAssembleKernel  a group of lanes per state; sums runs into links and links into their
+ *                     ancestors (composites), then builds M, h, F_gravity and E
+ * Record of one state (recDoubles doubles, offsets in the order the walk produces them):
+ *   column k   colRec[k] + {0..2 joint axis, 3..5 joint origin, 6 joint rate (IK space)}
+ *   run r      runRec[r] + {0 m, 1..3 m c, 4..12 inertia about the world origin (row-major,
+ *                           not symmetrised: the reference uses the tensor of the file as
+ *                           given), 13..15 bias force, 16..18 bias moment about the world
+ *                           origin} of the bodies of the run, belonging to link runLink[r]
+ *   potential energy at recV
  */
+#define RCSB_KT_COL_REC 7
+#define RCSB_KT_LINK_REC 19
+
 typedef struct
 {
   int nLinks;
   int nJ;
   int totalBytes;
-  int scratchDoubles;   /* 19 nLinks + 16 nJ */
+  int recDoubles;       /* doubles per state record (multiple of 4) */
+  int nRuns;
+  int recV;             /* offset of the potential energy */
+  int nPairs;           /* structurally non-zero entries of the upper triangle of M */
+  int symmetric;        /* 1: every inertia tensor of the model is symmetric (M = M^T) */
   int offBodyLink;      /* int[nb]: link the body is lumped into, -1 = none (no joint moves it) */
+  int offBodyEmit;      /* int[nb + 1]: 1 if the accumulator is emitted (and cleared) before the
+                           body is visited ([nb]: after the last body) */
   int offLinkParent;    /* int[nLinks]: nearest proper ancestor link, -1 = none */
   int offColJoint;      /* int[nJ]: jointIndex of Jacobian column */
   int offColLink;       /* int[nJ]: link of the column's joint */
   int offColIsRot;      /* int[nJ] */
-  int offRel;           /* unsigned char[nJ * nJ]: 0 unrelated, 1 col is descendant-or-equal of
-                           row, 2 col is a proper ancestor of row */
-  int scrComp, scrWr, scrJa, scrPl, scrQd;   /* offsets (in doubles) into the workspace */
-  float invNJ;
+  int offColRec;        /* int[nJ] */
+  int offRunLink;       /* int[nRuns] */
+  int offRunRec;        /* int[nRuns] */
+  int offPairs;         /* int[nPairs]: ancestor column | descendant-or-same column << 16 */
+  int pad0, pad1;
 } RcsbKtPlanHeader;
 
 /*
