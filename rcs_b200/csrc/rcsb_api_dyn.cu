@@ -82,18 +82,16 @@ int buildKtPlan(RcsbModel* m)
 
   /* walk bookkeeping: the accumulator is emitted as a run whenever the walk moves to a body of
    * another link; every record of the state gets its offset in the order of production */
-  const int* bodyFlagsArr = m->iarr(RCSB_A_BODY_FLAGS);
   std::vector<int> bodyEmit((size_t) nb + 1, 0), runLink, runRec;
   std::vector<int> colRec(nJ > 0 ? nJ : 1, 0);
   int rec = 0;
   {
     int cur = -1;
-    bool dirty = false;
     for (int b = 0; b < nb; ++b)
     {
       if (bodyLink[b] != cur)
       {
-        if (cur >= 0 && dirty)
+        if (cur >= 0)   /* every visit of a link leaves a run, so that each link has one */
         {
           bodyEmit[b] = 1;
           runLink.push_back(cur);
@@ -101,7 +99,6 @@ int buildKtPlan(RcsbModel* m)
           rec += RCSB_KT_LINK_REC;
         }
         cur = bodyLink[b];
-        dirty = false;
       }
       for (int j = bodyJntStart[b]; j < bodyJntStart[b] + bodyJntCount[b]; ++j)
       {
@@ -111,12 +108,8 @@ int buildKtPlan(RcsbModel* m)
           rec += RCSB_KT_COL_REC;
         }
       }
-      if (cur >= 0 && (bodyFlagsArr[b] & RCSB_BF_HAS_MASS))
-      {
-        dirty = true;
-      }
     }
-    if (cur >= 0 && dirty)
+    if (cur >= 0)
     {
       bodyEmit[nb] = 1;
       runLink.push_back(cur);
@@ -126,7 +119,51 @@ int buildKtPlan(RcsbModel* m)
   }
   const int nRuns = (int) runLink.size();
 
-  /* structurally non-zero entries of the upper triangle: (ancestor column, column) */
+  if (nJ > 255 || rec + 1 > 65535)
+  {
+    rcsb_set_error("rcsb_kinetic_terms: model too large (nJ %d, record %d doubles)", nJ, rec + 1);
+    return RCSB_EUNSUPPORTED;
+  }
+
+  /* shared-memory layout of the assembly kernel */
+  const int asmV = 16 * nJ;
+  const int asmRuns = 16 * nJ + 4;
+  const int runArea = RCSB_KT_LINK_REC * nRuns > nJ * nJ ? RCSB_KT_LINK_REC * nRuns : nJ * nJ;
+  const int asmDoubles = asmRuns + runArea;
+  const int recDoubles = (rec + 1 + 3) & ~3;
+  std::vector<unsigned short> recDst((size_t) recDoubles, (unsigned short) (asmV + 1));
+  for (int k = 0; k < nJ; ++k)
+  {
+    for (int t = 0; t < RCSB_KT_COL_REC; ++t)
+    {
+      recDst[(size_t) colRec[k] + t] = (unsigned short) (7 * k + t);
+    }
+  }
+  std::vector<int> linkHome((size_t) (nLinks > 0 ? nLinks : 1), -1), extraRuns;
+  for (int r = 0; r < nRuns; ++r)
+  {
+    for (int t = 0; t < RCSB_KT_LINK_REC; ++t)
+    {
+      recDst[(size_t) runRec[r] + t] = (unsigned short) (asmRuns + RCSB_KT_LINK_REC * r + t);
+    }
+    if (linkHome[runLink[r]] < 0)
+    {
+      linkHome[runLink[r]] = asmRuns + RCSB_KT_LINK_REC * r;
+    }
+    else
+    {
+      extraRuns.push_back(asmRuns + RCSB_KT_LINK_REC * r);
+      extraRuns.push_back(linkHome[runLink[r]]);
+    }
+  }
+  recDst[(size_t) rec] = (unsigned short) asmV;
+  std::vector<int> colHome((size_t) (nJ > 0 ? nJ : 1), 0);
+  for (int k = 0; k < nJ; ++k)
+  {
+    colHome[k] = linkHome[colLink[k]];
+  }
+
+  /* structurally non-zero entries of the upper triangle: (ancestor column i, column k) */
   std::vector<int> pairs;
   for (int k = 0; k < nJ; ++k)
   {
@@ -134,7 +171,10 @@ int buildKtPlan(RcsbModel* m)
     {
       if (rel[(size_t) i * nJ + k] == 1)
       {
-        pairs.push_back(i | (k << 16));
+        pairs.push_back(7 * i);
+        pairs.push_back(7 * nJ + 9 * k);
+        pairs.push_back((i * nJ + k) | ((k * nJ + i) << 16));
+        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((7 * k) << 8));
       }
     }
   }
@@ -153,10 +193,14 @@ int buildKtPlan(RcsbModel* m)
   ph.nLinks = nLinks;
   ph.nJ = nJ;
   ph.nRuns = nRuns;
-  ph.nPairs = (int) pairs.size();
+  ph.nPairs = (int) pairs.size() / 4;
   ph.symmetric = symmetric ? 1 : 0;
   ph.recV = rec;
-  ph.recDoubles = (rec + 1 + 3) & ~3;
+  ph.recDoubles = recDoubles;
+  ph.asmV = asmV;
+  ph.asmRuns = asmRuns;
+  ph.asmDoubles = asmDoubles;
+  ph.nExtraRuns = (int) extraRuns.size() / 2;
   int off = align16((int) sizeof(ph));
   auto place = [&](int& field, size_t bytes) {
     field = off;
@@ -164,6 +208,7 @@ int buildKtPlan(RcsbModel* m)
   };
   place(ph.offBodyLink, (size_t) nb * 4);
   place(ph.offBodyEmit, ((size_t) nb + 1) * 4);
+  ph.walkBytes = off;
   place(ph.offLinkParent, (size_t) nLinks * 4);
   place(ph.offColJoint, colJoint.size() * 4);
   place(ph.offColLink, colLink.size() * 4);
@@ -172,6 +217,10 @@ int buildKtPlan(RcsbModel* m)
   place(ph.offRunLink, (size_t) nRuns * 4);
   place(ph.offRunRec, (size_t) nRuns * 4);
   place(ph.offPairs, pairs.size() * 4);
+  place(ph.offRecDst, recDst.size() * 2);
+  place(ph.offLinkHome, linkHome.size() * 4);
+  place(ph.offExtraRuns, extraRuns.size() * 4);
+  place(ph.offColHome, colHome.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob((size_t) ph.totalBytes, 0);
@@ -192,13 +241,18 @@ int buildKtPlan(RcsbModel* m)
   put(ph.offRunLink, runLink.data(), (size_t) nRuns * 4);
   put(ph.offRunRec, runRec.data(), (size_t) nRuns * 4);
   put(ph.offPairs, pairs.data(), pairs.size() * 4);
+  put(ph.offRecDst, recDst.data(), recDst.size() * 2);
+  put(ph.offLinkHome, linkHome.data(), linkHome.size() * 4);
+  put(ph.offExtraRuns, extraRuns.data(), extraRuns.size() * 4);
+  put(ph.offColHome, colHome.data(), colHome.size() * 4);
 
   RCSB_CUDA(cudaSetDevice(m->device));
   RCSB_CUDA(cudaMalloc(&m->ktPlan.dev, blob.size()));
   RCSB_CUDA(cudaMemcpy(m->ktPlan.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   m->ktPlan.bytes = ph.totalBytes;
   m->ktPlan.aux0 = ph.recDoubles;
-  m->ktPlan.aux1 = ph.nLinks;
+  m->ktPlan.aux1 = ph.asmDoubles;
+  m->ktPlan.nScrRows = ph.walkBytes;
   m->ktPlanBuilt = true;
   return RCSB_OK;
 }
@@ -250,6 +304,7 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     a.plan = m->ktPlan.dev;
     a.modelBytes = m->hdr.totalBytes;
     a.planBytes = m->ktPlan.bytes;
+    a.planWalkBytes = m->ktPlan.nScrRows;
     a.N = n;
     a.qdim = qdim;
     a.q = q + s0 * qdim;

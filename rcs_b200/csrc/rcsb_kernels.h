@@ -8,7 +8,7 @@
 
 #define RCSB_FK_THREADS 128
 #define RCSB_MAX_FRAME_SLOTS 8
-#define RCSB_KT_WALK_THREADS 64
+#define RCSB_KT_WALK_THREADS 128
 #define RCSB_KT_ASM_THREADS 128
 #define RCSB_IK_THREADS 128
 
@@ -52,6 +52,7 @@ struct KtArgs
   double* E;
   double* rec;         /* N x recDoubles per-state records (walk -> assembly) */
   int recDoubles;
+  int planWalkBytes;   /* leading part of the plan staged by the walk kernel */
 };
 
 struct IkArgs
@@ -76,7 +77,7 @@ struct IkArgs
 extern "C" {
 cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cudaStream_t stream);
 /* enqueues the walk kernel and the assembly kernel (2 launches) */
-cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nLinks, int smCount,
+cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int asmDoubles, int smCount,
                            cudaStream_t stream);
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            cudaStream_t stream);

@@ -53,7 +53,11 @@ struct KtPlanView
   const int* colRec;
   const int* runLink;
   const int* runRec;
-  const int* pairs;
+  const int4* pairs;
+  const unsigned short* recDst;
+  const int* linkHome;
+  const int2* extraRuns;
+  const int* colHome;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -67,7 +71,11 @@ struct KtPlanView
     colRec = reinterpret_cast<const int*>(blob + hdr->offColRec);
     runLink = reinterpret_cast<const int*>(blob + hdr->offRunLink);
     runRec = reinterpret_cast<const int*>(blob + hdr->offRunRec);
-    pairs = reinterpret_cast<const int*>(blob + hdr->offPairs);
+    pairs = reinterpret_cast<const int4*>(blob + hdr->offPairs);
+    recDst = reinterpret_cast<const unsigned short*>(blob + hdr->offRecDst);
+    linkHome = reinterpret_cast<const int*>(blob + hdr->offLinkHome);
+    extraRuns = reinterpret_cast<const int2*>(blob + hdr->offExtraRuns);
+    colHome = reinterpret_cast<const int*>(blob + hdr->offColHome);
   }
 };
 
@@ -125,14 +133,25 @@ struct RecordWriter
   int lane;
   int p;             /* records produced so far */
 
-  __device__ __forceinline__ void flush(int base, int cnt)
+  __device__ __noinline__ void flush(int base, int cnt)
   {
     __syncwarp();
     if (lane < cnt)
     {
-      for (int t = 0; t < nv; ++t)
+      double* d = dst + base + lane;
+      const double* src = win + lane * 33;
+      int t = 0;
+      for (; t + 4 <= nv; t += 4)
       {
-        dst[(long) t * recDoubles + base + lane] = win[lane * 33 + t];
+        const double v0 = src[t], v1 = src[t + 1], v2 = src[t + 2], v3 = src[t + 3];
+        d[(long) t * recDoubles] = v0;
+        d[(long) (t + 1) * recDoubles] = v1;
+        d[(long) (t + 2) * recDoubles] = v2;
+        d[(long) (t + 3) * recDoubles] = v3;
+      }
+      for (; t < nv; ++t)
+      {
+        d[(long) t * recDoubles] = src[t];
       }
     }
     __syncwarp();
@@ -145,6 +164,53 @@ struct RecordWriter
     if ((p & 31) == 0)
     {
       flush(p - 32, 32);
+    }
+  }
+
+  /* N consecutive records; one window check when they do not straddle a flush */
+  template <int N>
+  __device__ __forceinline__ void emitN(const double (&v)[N])
+  {
+    const int pos = p & 31;
+    if (pos + N <= 32)
+    {
+      double* wp = win + pos * 33 + lane;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+      {
+        wp[i * 33] = v[i];
+      }
+      p += N;
+      if (pos + N == 32)
+      {
+        flush(p - 32, 32);
+      }
+    }
+    else
+    {
+      /* straddles the window: split at the boundary */
+      const int first = 32 - pos;
+      double* wp = win + pos * 33 + lane;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+      {
+        if (i < first)
+        {
+          wp[i * 33] = v[i];
+        }
+      }
+      p += first;
+      flush(p - 32, 32);
+      wp = win + lane - first * 33;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+      {
+        if (i >= first)
+        {
+          wp[i * 33] = v[i];
+        }
+      }
+      p += N - first;
     }
   }
 
@@ -164,17 +230,17 @@ ktWalkKernel(const KtArgs a)
   extern __shared__ __align__(16) char smem[];
   char* sModel = smem;
   char* sPlan = smem + a.modelBytes;
-  double* sWin = reinterpret_cast<double*>(sPlan + a.planBytes);
+  double* sWin = reinterpret_cast<double*>(sPlan + a.planWalkBytes);
   double* sAcc = sWin + (RCSB_KT_WALK_THREADS / 32) * 32 * 33;
 
   stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
+  stageBlob(sPlan, a.plan, a.planWalkBytes);
   __syncthreads();
 
   ModelView m;
   m.bind(sModel);
   KtPlanView p;
-  p.bind(sPlan);
+  p.bind(sPlan);   /* only hdr, bodyLink and bodyEmit are staged */
 
   constexpr int T = RCSB_KT_WALK_THREADS;
   const int tid = threadIdx.x;
@@ -215,12 +281,14 @@ ktWalkKernel(const KtArgs a)
     acc[i * T] = 0.0;
   }
   auto emitRun = [&]() {
+    double v[RCSB_KT_LINK_REC];
 #pragma unroll
     for (int i = 0; i < RCSB_KT_LINK_REC; ++i)
     {
-      w.emit(acc[i * T]);
+      v[i] = acc[i * T];
       acc[i * T] = 0.0;
     }
+    w.emitN(v);
   };
 
   Kin k, keep;
@@ -232,6 +300,15 @@ ktWalkKernel(const KtArgs a)
   }
   keep = k;
   double V = 0.0;
+  double nextQ = 0.0, nextQd = 0.0;
+  if (dof > 0)
+  {
+    nextQ = rd.fetchQ(m, 0);
+    if (VEL)
+    {
+      nextQd = rd.fetchQd(m, 0);
+    }
+  }
 
   for (int b = 0; b < nb; ++b)
   {
@@ -296,13 +373,24 @@ ktWalkKernel(const KtArgs a)
         }
       }
 
-      const double qj = rd.jointQ(m, j);
+      /* joints are visited in jointIndex order: the loads of the next joint are in flight
+       * while this one is processed */
+      const double rawQ = nextQ, rawQd = nextQd;
+      if (j + 1 < dof)
+      {
+        nextQ = rd.fetchQ(m, j + 1);
+        if (VEL)
+        {
+          nextQd = rd.fetchQd(m, j + 1);
+        }
+      }
+      const double qj = rd.finishQ(m, j, rawQ);
       const int dir = m.jntType[j] % 3;
       const int col = m.jntJacobi[j];
       double qdFull = 0.0, qdIk = 0.0;
       if (VEL)
       {
-        qdFull = rd.jointQd(m, j);
+        qdFull = rd.finishQd(m, j, rawQ, rawQd);
         qdIk = col >= 0 ? qdFull : 0.0;
       }
       double ax[3];
@@ -350,13 +438,8 @@ ktWalkKernel(const KtArgs a)
 
       if (col >= 0)
       {
-        w.emit(ax[0]);
-        w.emit(ax[1]);
-        w.emit(ax[2]);
-        w.emit(k.f.o[0]);
-        w.emit(k.f.o[1]);
-        w.emit(k.f.o[2]);
-        w.emit(qdIk);
+        const double v[RCSB_KT_COL_REC] = {ax[0], ax[1], ax[2], k.f.o[0], k.f.o[1], k.f.o[2], qdIk};
+        w.emitN(v);
       }
     }
 
@@ -517,51 +600,83 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   const int nLinks = p.hdr->nLinks;
   const int R = a.recDoubles;
   const bool sym = p.hdr->symmetric != 0;
-  double* buf = sBuf + (long) grp * groupStride;   /* the state's record */
-  double* fb = buf + R;                            /* 9 per column: p, L, L with I^T */
-  double* comp = fb + 9 * nJ;                      /* 19 per link: composite of the subtree */
-  double* Ms = comp + RCSB_KT_LINK_REC * nLinks;   /* nJ x nJ */
+  double* buf = sBuf + (long) grp * groupStride;   /* layout: RcsbKtPlanHeader, asm* fields */
+  double* fb = buf + 7 * nJ;                       /* 9 per column: p, L, L with I^T */
+  double* Ms = buf + p.hdr->asmRuns;               /* nJ x nJ, over the consumed runs */
   const double grav = 9.81;
+
+  /* The record of the group's next state is fetched into registers while the current state is
+   * assembled (PF doubles per lane; longer records fall back to a plain copy loop). */
+  constexpr int PF = 32;
+  const bool prefetch = R <= PF * LPS;
+  double nxt[PF];
+  auto fetch = [&](long state) {
+    const double* src = a.rec + (state < a.N ? state : a.N - 1) * R;
+#pragma unroll
+    for (int t = 0; t < PF; ++t)
+    {
+      const int e = gl + t * LPS;
+      if (e < R)
+      {
+        nxt[t] = src[e];
+      }
+    }
+  };
 
   /* all groups of a warp iterate together (warp-level barriers inside) */
   const long nGroupsTotal = (a.N + GPB - 1) / GPB * GPB;
-  for (long s = (long) blockIdx.x * GPB + grp; s < nGroupsTotal; s += (long) gridDim.x * GPB)
+  const long sFirst = (long) blockIdx.x * GPB + grp;
+  const long sStep = (long) gridDim.x * GPB;
+  if (prefetch && sFirst < nGroupsTotal)
+  {
+    fetch(sFirst);
+  }
+  for (long s = sFirst; s < nGroupsTotal; s += sStep)
   {
     const bool valid = s < a.N;
     const long sc = valid ? s : a.N - 1;
 
-    const double* src = a.rec + sc * R;
-    for (int e = gl; e < R; e += LPS)
+    if (prefetch)
     {
-      buf[e] = src[e];
-    }
-    for (int e = gl; e < RCSB_KT_LINK_REC * nLinks; e += LPS)
-    {
-      comp[e] = 0.0;
-    }
-    if (a.M)
-    {
-      for (int e = gl; e < nJ * nJ; e += LPS)
+#pragma unroll
+      for (int t = 0; t < PF; ++t)
       {
-        Ms[e] = 0.0;
+        const int e = gl + t * LPS;
+        if (e < R)
+        {
+          buf[p.recDst[e]] = nxt[t];
+        }
+      }
+      if (s + sStep < nGroupsTotal)
+      {
+        fetch(s + sStep);
+      }
+    }
+    else
+    {
+      const double* src = a.rec + sc * R;
+      for (int e = gl; e < R; e += LPS)
+      {
+        buf[p.recDst[e]] = src[e];
       }
     }
     __syncwarp();
 
-    /* ---- composites: runs into links, links into their ancestors (children have larger
-     * indices than their parents; element i always stays with the same lane) --------------- */
+    /* ---- composites in place: extra runs into their link, links into their ancestors
+     * (children have larger indices than their parents; element i stays with one lane) ---- */
     for (int i = gl; i < RCSB_KT_LINK_REC; i += LPS)
     {
-      for (int r = 0; r < p.hdr->nRuns; ++r)
+      for (int r = 0; r < p.hdr->nExtraRuns; ++r)
       {
-        comp[p.runLink[r] * RCSB_KT_LINK_REC + i] += buf[p.runRec[r] + i];
+        const int2 x = p.extraRuns[r];
+        buf[x.y + i] += buf[x.x + i];
       }
       for (int l = nLinks - 1; l > 0; --l)
       {
         const int pl = p.linkParent[l];
         if (pl >= 0)
         {
-          comp[pl * RCSB_KT_LINK_REC + i] += comp[l * RCSB_KT_LINK_REC + i];
+          buf[p.linkHome[pl] + i] += buf[p.linkHome[l] + i];
         }
       }
     }
@@ -570,8 +685,8 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     /* ---- per column: momentum of its composite under a unit joint rate, h, F_gravity ---- */
     for (int k = gl; k < nJ; k += LPS)
     {
-      const double* ja = buf + p.colRec[k];
-      const double* cp = comp + p.colLink[k] * RCSB_KT_LINK_REC;
+      const double* ja = buf + 7 * k;
+      const double* cp = buf + p.colHome[k];
       const bool isRot = p.colIsRot[k] != 0;
       const double ax[3] = {ja[0], ja[1], ja[2]};
       const double o[3] = {ja[3], ja[4], ja[5]};
@@ -637,38 +752,47 @@ ktAssembleKernel(const KtArgs a, int groupStride)
 
     /* ---- mass matrix: only the structurally non-zero pairs (ancestor i, column k) ----------
      * M[i][k] = <joint i, momentum of column k>; M[k][i] the same with the transposed
-     * inertia. Staged in shared memory, rows leave as coalesced stores. */
+     * inertia. Staged in shared memory (over the consumed runs), rows leave as coalesced
+     * stores. */
     double tk = 0.0;
     if (a.M || (a.E && VEL))
     {
+      if (a.M)
+      {
+        for (int e = gl; e < nJ * nJ; e += LPS)
+        {
+          Ms[e] = 0.0;
+        }
+        __syncwarp();
+      }
       const int nPairs = p.hdr->nPairs;
       for (int e = gl; e < nPairs; e += LPS)
       {
-        const int pr = p.pairs[e];
-        const int i = pr & 0xffff, k = pr >> 16;
-        const double* ji = buf + p.colRec[i];
-        const double* fk = fb + 9 * k;
-        const bool iRot = p.colIsRot[i] != 0;
+        const int4 pr = p.pairs[e];
+        const double* ji = buf + pr.x;
+        const double* fk = buf + pr.y;
+        const bool iRot = (pr.w & 1) != 0;
+        const bool diag = (pr.w & 2) != 0;
         const double ai[3] = {ji[0], ji[1], ji[2]};
         const double oi[3] = {ji[3], ji[4], ji[5]};
         const double pk[3] = {fk[0], fk[1], fk[2]};
         const double Lk[3] = {fk[3], fk[4], fk[5]};
         const double upper = pairing(iRot, ai, oi, pk, Lk);
         double lower = upper;
-        if (!sym && i != k)
+        if (!sym && !diag)
         {
           const double Lkt[3] = {fk[6], fk[7], fk[8]};
           lower = pairing(iRot, ai, oi, pk, Lkt);
         }
         if (a.M)
         {
-          Ms[i * nJ + k] = upper;
-          Ms[k * nJ + i] = lower;
+          Ms[pr.z & 0xffff] = upper;
+          Ms[pr.z >> 16] = lower;
         }
         if (VEL)
         {
-          const double qq = ji[6] * buf[p.colRec[k] + 6];
-          tk += (i == k) ? qq * upper : qq * (upper + lower);
+          const double qq = ji[6] * buf[(pr.w >> 8) + 6];
+          tk += diag ? qq * upper : qq * (upper + lower);
         }
       }
       if (a.M)
@@ -697,7 +821,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
       if (gl == 0 && valid)
       {
-        a.E[s] = buf[p.hdr->recV] + 0.5 * tk;
+        a.E[s] = buf[p.hdr->asmV] + 0.5 * tk;
       }
     }
     __syncwarp();
@@ -707,7 +831,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
 template <bool VEL>
 static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 {
-  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planWalkBytes +
                            (size_t) (RCSB_KT_WALK_THREADS / 32) * 32 * 33 * sizeof(double) +
                            (size_t) RCSB_KT_LINK_REC * RCSB_KT_WALK_THREADS * sizeof(double);
   const dim3 grid((unsigned int) ((a.N + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS));
@@ -739,13 +863,12 @@ static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 }
 
 template <bool VEL, int LPS>
-static cudaError_t launchAssemble(const KtArgs& a, int nJ, int nLinks, int smCount,
+static cudaError_t launchAssemble(const KtArgs& a, int nJ, int asmDoubles, int smCount,
                                   cudaStream_t stream)
 {
   constexpr int GPB = RCSB_KT_ASM_THREADS / LPS;
   /* group buffers 4 doubles apart modulo 16: the groups of a warp read different banks */
-  int groupStride = a.recDoubles + 9 * nJ + RCSB_KT_LINK_REC * nLinks + nJ * nJ;
-  groupStride = ((groupStride + 15) & ~15) + 4;
+  int groupStride = ((asmDoubles + 15) & ~15) + 4;
   const size_t smemBytes = (size_t) a.planBytes + (size_t) GPB * groupStride * sizeof(double);
   auto k = ktAssembleKernel<VEL, LPS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -769,7 +892,7 @@ static cudaError_t launchAssemble(const KtArgs& a, int nJ, int nLinks, int smCou
 
 }   // namespace rcsb
 
-extern "C" cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nLinks,
+extern "C" cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int asmDoubles,
                                       int smCount, cudaStream_t stream)
 {
   using namespace rcsb;
@@ -785,14 +908,14 @@ extern "C" cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ,
   }
   if (nJ <= 8)
   {
-    return vel ? launchAssemble<true, 8>(*a, nJ, nLinks, smCount, stream)
-               : launchAssemble<false, 8>(*a, nJ, nLinks, smCount, stream);
+    return vel ? launchAssemble<true, 8>(*a, nJ, asmDoubles, smCount, stream)
+               : launchAssemble<false, 8>(*a, nJ, asmDoubles, smCount, stream);
   }
   if (nJ <= 16)
   {
-    return vel ? launchAssemble<true, 16>(*a, nJ, nLinks, smCount, stream)
-               : launchAssemble<false, 16>(*a, nJ, nLinks, smCount, stream);
+    return vel ? launchAssemble<true, 16>(*a, nJ, asmDoubles, smCount, stream)
+               : launchAssemble<false, 16>(*a, nJ, asmDoubles, smCount, stream);
   }
-  return vel ? launchAssemble<true, 32>(*a, nJ, nLinks, smCount, stream)
-             : launchAssemble<false, 32>(*a, nJ, nLinks, smCount, stream);
+  return vel ? launchAssemble<true, 32>(*a, nJ, asmDoubles, smCount, stream)
+             : launchAssemble<false, 32>(*a, nJ, asmDoubles, smCount, stream);
 }

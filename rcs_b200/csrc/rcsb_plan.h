@@ -92,8 +92,23 @@ typedef struct
   int offColRec;        /* int[nJ] */
   int offRunLink;       /* int[nRuns] */
   int offRunRec;        /* int[nRuns] */
-  int offPairs;         /* int[nPairs]: ancestor column | descendant-or-same column << 16 */
-  int pad0, pad1;
+  /* assembly kernel: per-state shared-memory layout (doubles)
+   *   [0, 7 nJ)            column k at 7 k: axis, origin, rate
+   *   [7 nJ, 16 nJ)        column k at 7 nJ + 9 k: p, L, L with the transposed inertia
+   *   asmV                 potential energy
+   *   [asmRuns, ...)       run r at asmRuns + 19 r; the first run of a link becomes the link's
+   *                        composite in place; later the same area holds the nJ x nJ matrix */
+  int asmV, asmRuns, asmDoubles;
+  int nExtraRuns;       /* runs that are not the first of their link */
+  int offRecDst;        /* unsigned short[recDoubles]: where each record element goes */
+  int offLinkHome;      /* int[nLinks]: shared-memory offset of the link's composite */
+  int offExtraRuns;     /* int2[nExtraRuns]: {offset of the run, offset of the link's composite} */
+  int offColHome;       /* int[nJ]: composite of the column's link */
+  int offPairs;         /* int4[nPairs], structurally non-zero upper-triangle entries (ancestor
+                           column i, column k): {7 i, 7 nJ + 9 k, (i nJ + k) | (k nJ + i) << 16,
+                           isRot(i) | (i == k) << 1 | (7 k) << 8} */
+  int walkBytes;        /* leading part of the plan the walk kernel needs (header, bodyLink,
+                           bodyEmit); multiple of 16 */
 } RcsbKtPlanHeader;
 
 /*
