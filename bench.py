@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of rcs_b200 (contract: see the task description / DESIGN.md).
+"""bench.py — benchmark of rcs_b200 (contract: task description / DESIGN.md §6).
 
-Workload at every N (weak scaling, one process per GPU): BASELINE.json configs[1],
+Default workload (the headline line the driver records): BASELINE.json configs[1],
 "7-DoF arm batched FK + Jacobians, 1M uniformly sampled joint states, FP64":
   per state  in : q (7 doubles)
              out: A_BI of all 12 bodies (12 x 96 B) + JT, JR of BallTip (2 x 3 x 7 doubles)
-             = 1544 algorithmic bytes.
-One step = one pass of the hot path over one batch of 1,048,576 states per GPU
-(one fkKernel launch per rank) + one NCCL allgather of per-rank summary statistics (N > 1).
+             = 1544 algorithmic bytes; one fkKernel launch per step and rank.
+Other workloads (same JSON line, selected with --workload):
+  kinetic  configs[2]: humanoid (dof 65, nJ 34, 63 bodies), 262,144 states per GPU,
+           M + h + F_gravity + E; 10,840 algorithmic bytes per state; two kernels per pass.
+  ik       configs[3]: 7-DoF arm, XYZ + ABC tasks on BallTip, lambda 1e-8, alpha 0.05,
+           10 RMR iterations, 4,194,304 targets in total (strong scaling: sharded over ranks).
 
-  value  states/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e    states/s through the host-pointer C ABI (pinned host buffers; H2D of q and D2H of
-         every result inside the timed region)
-  roofline.achieved = 1544 B x states per launch / mean launch duration
-  cpu_baseline / --impl reference: the reference library (oracle/_ref, unmodified Rcs
-         sources) on the host cores, one RcsGraph_clone per thread.
+One step = one pass of the hot path over one batch + (N > 1) one NCCL all-gather of per-rank
+summary statistics, the only collective of the path.
+  value     units/s with inputs resident in HBM, CUDA-event timed on the launching stream,
+            barrier + synchronize on both sides, max over ranks
+  e2e       the same through the host-pointer C ABI (RCSB_HOST_PTRS): pinned host buffers,
+            H2D of the inputs and D2H of every result inside the timed region
+  roofline  algorithmic bytes (or FP64 flops) per launch / mean kernel time of the timed steps
+  cpu_baseline / --impl reference: the unmodified reference library (oracle/_ref) on the
+            host cores, one RcsGraph_clone (+ controller and solver) per thread.
 """
 from __future__ import annotations
 
@@ -31,12 +37,14 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-N_STATES = 1 << 20
-GRAPH = os.path.join(ROOT, "tests", "golden", "graphs", "wam_arm.xml")
-EFFECTOR = "BallTip"
-BYTES_PER_STATE = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8   # 1544
-METRIC = "FK+Jacobian states/sec FP64 (7-DoF arm, 1M states per GPU)"
-UNIT = "states/s"
+GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
+UNIT = {"fk": "states/s", "kinetic": "states/s", "ik": "solves/s"}
+METRIC = {
+    "fk": "FK+Jacobian states/sec FP64 (7-DoF arm, 1M states per GPU)",
+    "kinetic": "kinetic terms M,h,g states/sec FP64 (humanoid, 256K states per GPU)",
+    "ik": "RMR IK solves/sec FP64 (7-DoF arm, XYZ+ABC, 10 iterations, 4M targets)",
+}
+IK_ITERS, IK_LAMBDA, IK_ALPHA = 10, 1.0e-8, 0.05
 
 
 def host_threads() -> int:
@@ -46,46 +54,137 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def workload_config(n_gpus: int) -> dict:
-    return {
-        "workload": "configs[1]: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames + "
-                    "JT/JR of BallTip, uniformly sampled joint states",
-        "states_per_gpu": N_STATES,
-        "global_states": N_STATES * n_gpus,
-        "bytes_per_state": BYTES_PER_STATE,
-        "parallelism": f"dp{n_gpus} (independent state slices; allgather of summary statistics)",
-        "l2": "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)",
-    }
+class Workload:
+    """Sizes, byte counts and descriptions of one BASELINE.json configuration."""
+
+    def __init__(self, name: str, world: int):
+        self.name = name
+        self.world = world
+        if name == "fk":
+            self.graph, self.eff = "wam_arm", "BallTip"
+            self.per_gpu = 1 << 20
+            self.scaling = "weak"
+            self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8            # 1544
+            self.kernel = "rcsb::fkKernel"
+            self.launches_per_step = 1
+            self.desc = ("configs[1]: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames + "
+                         "JT/JR of BallTip, uniformly sampled joint states")
+            self.l2 = "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)"
+        elif name == "kinetic":
+            self.graph, self.eff = "humanoid", None
+            self.per_gpu = 1 << 18
+            self.scaling = "weak"
+            self.bytes_per_unit = 2 * 65 * 8 + (34 * 34 + 2 * 34 + 1) * 8     # 10840
+            self.kernel = "rcsb::ktWalkKernel + rcsb::ktAssembleKernel"
+            self.launches_per_step = None                                     # counted live
+            self.desc = ("configs[2]: GenericHumanoid (dof 65, nJ 34, 63 bodies), "
+                         "RcsGraph_computeKineticTerms M, h, F_gravity, E; q and q_dot uniformly sampled")
+            self.l2 = "per-step working set 2.8 GB per GPU >> 126 MB L2 (no flush needed)"
+        elif name == "ik":
+            self.graph, self.eff = "wam_arm", "BallTip"
+            total = 1 << 22
+            self.per_gpu = total // world
+            self.scaling = "strong"
+            self.bytes_per_unit = 56 + 48 + 56 + 8                            # q in, x_des, q out, det
+            self.kernel = "rcsb::ikChainKernel<7, 6>"
+            self.launches_per_step = 1
+            self.desc = ("configs[3]: WAM 7-DoF arm, IkSolverRMR right inverse, tasks XYZ + ABC on BallTip, "
+                         f"lambda {IK_LAMBDA}, alpha {IK_ALPHA}, {IK_ITERS} iterations per target; targets = "
+                         "poses of uniformly sampled states, start = goal state + U(-0.1, 0.1) rad")
+            self.l2 = "per-step working set 0.7 GB in total >> 126 MB L2 (no flush needed)"
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        self.graph_file = os.path.join(GRAPHS, self.graph + ".xml")
+
+    def config(self):
+        return {
+            "workload": self.desc,
+            "units_per_gpu": self.per_gpu,
+            "global_units": self.per_gpu * self.world,
+            "bytes_per_unit": self.bytes_per_unit,
+            "parallelism": f"dp{self.world} (independent state slices; all-gather of summary statistics)",
+            "l2": self.l2,
+        }
+
+
+# ---------------------------------------------------------------------------------------------
+# inputs (identical arrays for the GPU path and the CPU reference)
+# ---------------------------------------------------------------------------------------------
+
+def euler_xyz(A9: np.ndarray) -> np.ndarray:
+    """x-y-z Euler angles of row-major rotations (input preparation, Rcs_Mat3d.c:956)."""
+    A = A9.reshape(-1, 3, 3)
+    cy = np.sqrt(A[:, 0, 0] ** 2 + A[:, 1, 0] ** 2)
+    return np.stack([-np.arctan2(A[:, 2, 1], A[:, 2, 2]), -np.arctan2(-A[:, 2, 0], cy),
+                     -np.arctan2(A[:, 1, 0], A[:, 0, 0])], axis=1)
+
+
+def ik_inputs(layout, model_fk, first: int, count: int, dof: int, tip: int):
+    """(q_start, x_des) for `count` targets starting at global index `first`. model_fk maps a
+    q array to the effector frames (GPU model or reference graph)."""
+    from rcs_b200 import workload
+
+    q_goal = workload.sample_states(layout, count, first=(1 << 24) + first, margin=0.2)
+    frames = model_fk(q_goal)
+    x_des = np.ascontiguousarray(np.concatenate([frames[:, :3], euler_xyz(frames[:, 3:])], axis=1))
+    u = workload.uniform01(workload.SEED, first, count, dof, stream=7)
+    q_start = np.ascontiguousarray(q_goal + 0.1 * (2.0 * u - 1.0))
+    return q_start, x_des
 
 
 # ---------------------------------------------------------------------------------------------
 # reference arm / CPU baseline
 # ---------------------------------------------------------------------------------------------
 
-def reference_rate(sample_states: int, repeats: int, threads: int):
-    """FK + Jacobians of `sample_states` states with the reference library, `repeats` times.
-    Returns (states/s of the best repeat, seconds list)."""
-    from oracle import ref
-    from rcs_b200 import workload
+class ReferenceRunner:
+    """The reference's own functions (oracle/_ref: unmodified Rcs sources) over a sample."""
 
-    g = ref.RefGraph(GRAPH)
-    eff = [g.body_index(EFFECTOR)]
-    q = workload.sample_states(g.layout(), sample_states)
-    ref.set_threads(threads)
-    A = np.empty((sample_states, g.n_bodies, 12))
-    JT = np.empty((sample_states, 1, 3, g.nJ))
-    JR = np.empty((sample_states, 1, 3, g.nJ))
-    import ctypes
+    def __init__(self, wl: Workload, threads: int):
+        from oracle import ref
 
-    L = ref.lib()
-    effarr = (ctypes.c_int * 1)(*eff)
+        self.ref, self.wl, self.threads = ref, wl, threads
+        self.g = ref.RefGraph(wl.graph_file)
+        self.layout = self.g.layout()
+        if wl.name == "ik":
+            self.ik = ref.RefIk(wl.graph_file, [("XYZ", wl.eff), ("ABC", wl.eff)])
+        self.sample = 0
 
-    def once():
-        return L.ref_fk_jacobians(g._h, sample_states, g.dof, q.ctypes.data, 1, effarr, None,
-                                  A.ctypes.data, JT.ctypes.data, JR.ctypes.data)
+    def prepare(self, sample: int):
+        from rcs_b200 import workload
 
-    secs = [once() for _ in range(repeats)]
-    return sample_states / min(secs), secs
+        wl, g = self.wl, self.g
+        self.sample = sample
+        if wl.name == "fk":
+            self.q = workload.sample_states(self.layout, sample)
+            self.eff = [g.body_index(wl.eff)]
+        elif wl.name == "kinetic":
+            self.q, self.qd = workload.sample_states(self.layout, sample, with_velocity=True)
+        else:
+            tip = g.body_index(wl.eff)
+            self.ref.set_threads(self.threads)
+            self.q, self.x_des = ik_inputs(self.layout, lambda q: g.fk(q)["A_BI"][:, tip], 0, sample,
+                                           g.dof, tip)
+
+    def run(self) -> float:
+        """One pass over the sample on self.threads threads; returns seconds inside the library."""
+        self.ref.set_threads(self.threads)
+        wl, g = self.wl, self.g
+        if wl.name == "fk":
+            g.fk_jacobians(self.q, self.eff)
+            return g.last_seconds
+        if wl.name == "kinetic":
+            g.kinetic_terms(self.q, self.qd)
+            return g.last_seconds
+        self.ik.rmr(self.q, self.x_des, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS)
+        return self.ik.last_seconds
+
+    def calibrate(self, target_seconds: float, cap: int) -> int:
+        """Sample size (power of two) whose pass takes about target_seconds."""
+        n = {"fk": 1 << 14, "kinetic": 1 << 8, "ik": 1 << 12}[self.wl.name]
+        self.prepare(n)
+        rate = n / max(self.run(), 1e-9)
+        want = int(min(cap, max(n, rate * target_seconds)))
+        return 1 << (want.bit_length() - 1)
 
 
 def run_reference(args):
@@ -94,32 +193,31 @@ def run_reference(args):
         return
     from oracle import ref
 
+    wl = Workload(args.workload, args.gpus)
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librcsref.so missing"}))
         return
     threads = host_threads()
-    # calibrate so that one step stays around a second of wall time
-    rate, _ = reference_rate(1 << 14, 1, threads)
-    sample = int(min(N_STATES, max(1 << 14, rate * 1.0)))
-    sample = 1 << (sample.bit_length() - 1)
+    runner = ReferenceRunner(wl, threads)
+    sample = runner.calibrate(1.0, wl.per_gpu * wl.world)
+    runner.prepare(sample)
     for _ in range(args.warmup):
-        reference_rate(sample, 1, threads)
+        runner.run()
     t0 = time.perf_counter()
-    _, secs = reference_rate(sample, args.steps, threads)
+    secs = [runner.run() for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     total = sum(secs)
     value = sample * args.steps / total
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "metric": METRIC[wl.name], "value": value, "unit": UNIT[wl.name], "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": f"{sample} states per step x {args.steps} steps, one "
-                                   f"RcsGraph_clone per thread, {threads} threads "
-                                   f"(wall incl. thread start {wall:.2f} s)"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": wl.config(),
+        "cpu_baseline": {"value": value, "unit": UNIT[wl.name], "cores": threads, "kind": "reference",
+                         "sample": f"{sample} units per step x {args.steps} steps, one RcsGraph_clone per "
+                                   f"thread, {threads} threads (wall incl. thread start {wall:.2f} s)"},
+        "e2e": {"value": value, "unit": UNIT[wl.name], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -180,7 +278,7 @@ class ClockSampler:
 # our arm
 # ---------------------------------------------------------------------------------------------
 
-def measured_peak_gbs():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(p) as f:
@@ -189,13 +287,23 @@ def measured_peak_gbs():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    p = os.path.join(ROOT, "profiles", "fk_traffic.json")
+def profile_record(name: str):
+    """Per-launch DRAM traffic / FP64 instruction counts taken from the committed ncu captures."""
     try:
-        with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+            return json.load(f).get(name, {})
     except Exception:
-        return None
+        return {}
+
+
+def fp64_peak_tflops():
+    """DFMA microbenchmark (tools/fp64_peak.cu) run live; falls back to the committed figure."""
+    exe = os.path.join(ROOT, "build", "fp64_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        return float(json.loads(out)["fp64_tflops"]), "build/fp64_peak DFMA microbenchmark, this run"
+    except Exception:
+        return 34.2, "tools/fp64_peak.cu measured on B200 in round 1 (34.2 TFLOP/s)"
 
 
 def run_ours(args):
@@ -203,7 +311,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import rcs_b200
-    from rcs_b200 import workload
+    from rcs_b200 import TASK_ABC, TASK_XYZ, shard, workload
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,29 +323,101 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    g = rcs_b200.Graph(GRAPH)
+    wl = Workload(args.workload, world)
+    g = rcs_b200.Graph(wl.graph_file)
     m = rcs_b200.Model(g, local)
-    eff = [g.body_index(EFFECTOR)]
-    n = N_STATES
-    # every rank owns its own slice of the global, counter-based state sequence
-    q_host = workload.sample_states(g.layout(), n, first=rank * n)
-    q = torch.from_numpy(q_host).to(dev)
-    out = {
-        "A_BI": torch.empty((n, g.n_bodies, 12), dtype=torch.float64, device=dev),
-        "JT": torch.empty((n, 1, 3, g.nJ), dtype=torch.float64, device=dev),
-        "JR": torch.empty((n, 1, 3, g.nJ), dtype=torch.float64, device=dev),
-    }
-    stats = torch.zeros(4, dtype=torch.float64, device=dev)
-    gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
-    tip = eff[0]
+    lay = g.layout()
+    n = wl.per_gpu
+    first = rank * n                     # every rank owns its slice of the global sequence
+    f64 = torch.float64
 
-    def step():
-        m.fk_jacobians(q, eff, out=out)
+    def pinned(shape):
+        return torch.empty(shape, dtype=f64).pin_memory()
+
+    def dev_empty(shape):
+        return torch.empty(shape, dtype=f64, device=dev)
+
+    # ---- workload-specific buffers and the two call forms (device pointers / host pointers) ----
+    if wl.name == "fk":
+        eff = [g.body_index(wl.eff)]
+        q_host = workload.sample_states(lay, n, first=first)
+        q = torch.from_numpy(q_host).to(dev)
+        shapes = {"A_BI": (n, g.n_bodies, 12), "JT": (n, 1, 3, g.nJ), "JR": (n, 1, 3, g.nJ)}
+        out = {k: dev_empty(s) for k, s in shapes.items()}
+        hq = pinned((n, g.dof))
+        hq.copy_(torch.from_numpy(q_host))
+        hout = {k: pinned(s) for k, s in shapes.items()}
+        h2d, d2h = n * g.dof * 8, n * (g.n_bodies * 12 + 2 * 3 * g.nJ) * 8
+
+        def device_call():
+            m.fk_jacobians(q, eff, out=out)
+
+        def host_call():
+            m.fk_jacobians(hq, eff, out=hout)
+
+        def stat_source():
+            return out["A_BI"][:: 1024, eff[0], 2]          # effector height, strided sample
+
+        def same():
+            return bool(torch.equal(hout["JT"][:1000], out["JT"][:1000].cpu()))
+    elif wl.name == "kinetic":
+        q_host, qd_host = workload.sample_states(lay, n, first=first, with_velocity=True)
+        q, qd = torch.from_numpy(q_host).to(dev), torch.from_numpy(qd_host).to(dev)
+        shapes = {"M": (n, g.nJ, g.nJ), "h": (n, g.nJ), "Fg": (n, g.nJ), "E": (n,)}
+        out = {k: dev_empty(s) for k, s in shapes.items()}
+        hq, hqd = pinned((n, g.dof)), pinned((n, g.dof))
+        hq.copy_(torch.from_numpy(q_host))
+        hqd.copy_(torch.from_numpy(qd_host))
+        hout = {k: pinned(s) for k, s in shapes.items()}
+        h2d, d2h = 2 * n * g.dof * 8, n * (g.nJ * g.nJ + 2 * g.nJ + 1) * 8
+
+        def device_call():
+            m.kinetic_terms(q, qd, out=out)
+
+        def host_call():
+            m.kinetic_terms(hq, hqd, out=hout)
+
+        def stat_source():
+            return out["E"][:: 256]
+
+        def same():
+            return bool(torch.equal(hout["h"][:1000], out["h"][:1000].cpu()))
+    else:
+        tip = g.body_index(wl.eff)
+        tasks = [(TASK_XYZ, tip), (TASK_ABC, tip)]
+
+        def gpu_frames(qa):
+            return m.fk(torch.from_numpy(qa).to(dev), bodies=[tip])["A_BI"][:, 0].cpu().numpy()
+
+        q_start_host, x_host = ik_inputs(lay, gpu_frames, first, n, g.dof, tip)
+        q_start, x_des = torch.from_numpy(q_start_host).to(dev), torch.from_numpy(x_host).to(dev)
+        q = q_start.clone()
+        out = {"det": dev_empty((n,))}
+        hq0, hq, hx = pinned((n, g.dof)), pinned((n, g.dof)), pinned((n, 6))
+        hq0.copy_(torch.from_numpy(q_start_host))
+        hx.copy_(torch.from_numpy(x_host))
+        hout = {"det": pinned((n,))}
+        h2d, d2h = n * (g.dof + 6) * 8, n * (g.dof + 1) * 8
+
+        def device_call():
+            q.copy_(q_start)                                 # restore the start states (untimed kernel-wise)
+            m.ik_rmr(tasks, q, x_des, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS, out=out)
+
+        def host_call():
+            hq.copy_(hq0)
+            m.ik_rmr(tasks, hq, hx, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS, out=hout)
+
+        def stat_source():
+            return out["det"][:: 1024]
+
+        def same():
+            return bool(torch.equal(hq[:1000], q[:1000].cpu()))
+
+    gathered = torch.zeros(5 * world, dtype=f64, device=dev)
+
+    def exchange():
         if world > 1:
-            # summary statistics of this rank's slice: mean effector position + |JT| checksum
-            stats[:3] = out["A_BI"][:: 4096, tip, :3].mean(dim=0)
-            stats[3] = out["JT"][:: 4096].abs().sum()
-            dist.all_gather_into_tensor(gathered, stats)
+            shard.all_gather_stats(shard.local_stats(stat_source()), out=gathered)
 
     def barrier():
         if world > 1:
@@ -245,7 +425,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step()
+        device_call()
+        exchange()
     barrier()
 
     launches0 = rcs_b200.kernel_launch_count()
@@ -256,69 +437,78 @@ def run_ours(args):
         barrier()
         ev[0].record()
         for i in range(args.steps):
+            if wl.name == "ik":
+                q.copy_(q_start)
             kev[i][0].record()
-            m.fk_jacobians(q, eff, out=out)
+            if wl.name == "ik":
+                m.ik_rmr(tasks, q, x_des, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS, out=out)
+            else:
+                device_call()
             kev[i][1].record()
-            if world > 1:
-                stats[:3] = out["A_BI"][:: 4096, tip, :3].mean(dim=0)
-                stats[3] = out["JT"][:: 4096].abs().sum()
-                dist.all_gather_into_tensor(gathered, stats)
+            exchange()
             ev[i + 1].record()
         barrier()
         launches = rcs_b200.kernel_launch_count() - launches0
         # keep the GPU busy a little longer so that short runs still get clock samples under load
         t_hold = time.perf_counter()
         while time.perf_counter() - t_hold < args.hold:
-            m.fk_jacobians(q, eff, out=out)
+            device_call()
             torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = [a.elapsed_time(b) for a, b in kev]
 
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = n * world * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the host-pointer ABI (pinned buffers) ---------------------------
-    hq = torch.empty((n, g.dof), dtype=torch.float64).pin_memory()
-    hq.copy_(torch.from_numpy(q_host))
-    hout = {
-        "A_BI": torch.empty((n, g.n_bodies, 12), dtype=torch.float64).pin_memory(),
-        "JT": torch.empty((n, 1, 3, g.nJ), dtype=torch.float64).pin_memory(),
-        "JR": torch.empty((n, 1, 3, g.nJ), dtype=torch.float64).pin_memory(),
-    }
     e2e_steps = max(2, min(args.steps, 5))
-    m.fk_jacobians(hq, eff, out=hout)
+    host_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        m.fk_jacobians(hq, eff, out=hout)
+        host_call()
     t1 = time.perf_counter()
-    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    te = torch.tensor([t1 - t0], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n * world * e2e_steps / float(te.item())
-    # the pinned results must equal the device results of the same states
-    same = bool(torch.equal(hout["JT"][:1000], out["JT"][:1000].cpu()))
+    device_call()
+    torch.cuda.synchronize()
+    results_match = same()               # pinned results equal the device results of the same states
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
         k_ms = float(np.mean(kern_ms))
-        achieved = BYTES_PER_STATE * n / (k_ms * 1e-3) / 1e9
+        counters = profile_record(wl.name)
+        if wl.name == "ik":
+            peak, peak_src = fp64_peak_tflops()
+            flops = counters.get("fp64_flops_per_unit")
+            achieved = (flops * n / (k_ms * 1e-3) / 1e12) if flops else None
+            roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if achieved else None,
+                    "traffic": counters.get("dram_bytes_per_launch"),
+                    "flops_per_unit": flops,
+                    "flops_source": "ncu FP64 instruction counts of one launch (DFMA x 2 + DMUL + DADD), "
+                                    "profiles/kernel_counters.json",
+                    "hbm_frac": wl.bytes_per_unit * n / (k_ms * 1e-3) / 1e9 / measured_peaks()[0]}
+        else:
+            peak, peak_src = measured_peaks()
+            achieved = wl.bytes_per_unit * n / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": counters.get("dram_bytes_per_launch")}
+        roof.update({"kernel": wl.kernel, "kernel_ms": k_ms, "peak_source": peak_src,
+                     "algorithmic_per_launch": wl.bytes_per_unit * n})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC[wl.name], "value": value, "unit": UNIT[wl.name], "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "rcsb::fkKernel", "kernel_ms": k_ms, "peak_source": peak_src,
-                         "bytes_per_launch": BYTES_PER_STATE * n},
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": n * g.dof * 8 * world,
-                    "d2h_bytes_per_step": n * (g.n_bodies * 12 + 2 * 3 * g.nJ) * 8 * world,
-                    "steps": e2e_steps, "results_match_device_path": same},
+            "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": wl.config(),
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": UNIT[wl.name], "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                    "results_match_device_path": results_match},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
@@ -327,17 +517,23 @@ def run_ours(args):
 
             if ref.available():
                 threads = host_threads()
-                rate1, _ = reference_rate(1 << 16, 2, 1)
-                rateN, secs = reference_rate(N_STATES, 3, threads)
+                runner = ReferenceRunner(wl, threads)
+                sample = runner.calibrate(4.0, n)
+                runner.prepare(sample)
+                secs = [runner.run() for _ in range(3)]
+                one = ReferenceRunner(wl, 1)
+                s1 = one.calibrate(1.0, n)
+                one.prepare(s1)
+                t_one = one.run()
                 line["cpu_baseline"] = {
-                    "value": rateN, "unit": UNIT, "cores": threads, "kind": "reference",
-                    "single_core_value": rate1,
-                    "sample": f"reference library (unmodified Rcs sources), {N_STATES} states x 3 "
-                              f"passes on {threads} threads (best pass), one RcsGraph_clone per "
-                              f"thread; single core: 65536 states x 2"}
+                    "value": sample / min(secs), "unit": UNIT[wl.name], "cores": threads,
+                    "kind": "reference", "single_core_value": s1 / t_one,
+                    "sample": f"reference library (unmodified Rcs sources), {sample} units x 3 passes on "
+                              f"{threads} threads (best pass), one RcsGraph_clone per thread; "
+                              f"single core: {s1} units x 1"}
             else:
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                                        "sample": "oracle/_ref/librcsref.so missing"}
+                line["cpu_baseline"] = {"value": None, "unit": UNIT[wl.name], "cores": 0,
+                                        "kind": "reference", "sample": "oracle/_ref/librcsref.so missing"}
         print(json.dumps(line))
 
     if world > 1:
@@ -350,6 +546,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fk", choices=["fk", "kinetic", "ik"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hold", type=float, default=1.0,
                     help="seconds of extra (untimed) load for the clock sampler")

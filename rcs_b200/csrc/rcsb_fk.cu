@@ -97,6 +97,15 @@ fkKernel(const FkArgs a)
   double keepXd[3] = {0.0, 0.0, 0.0}, keepOm[3] = {0.0, 0.0, 0.0};
   setIdentity(f);
   setIdentity(keep);
+  double nextQ = 0.0, nextQd = 0.0;
+  if (dof > 0)
+  {
+    nextQ = rd.fetchQ(m, 0);
+    if (VEL)
+    {
+      nextQd = rd.fetchQd(m, 0);
+    }
+  }
 
   for (int b = 0; b < nb; ++b)
   {
@@ -173,7 +182,18 @@ fkKernel(const FkArgs a)
         applyRel(f, m.jntAJP + 12 * j);
       }
 
-      const double qj = rd.jointQ(m, j);
+      /* joints are visited in jointIndex order: the loads of the next joint are in flight
+       * while this one is processed */
+      const double rawQ = nextQ, rawQd = nextQd;
+      if (j + 1 < dof)
+      {
+        nextQ = rd.fetchQ(m, j + 1);
+        if (VEL)
+        {
+          nextQd = rd.fetchQd(m, j + 1);
+        }
+      }
+      const double qj = rd.finishQ(m, j, rawQ);
       const int dir = m.jntType[j] % 3;
       double ax[3];
 
@@ -197,7 +217,7 @@ fkKernel(const FkArgs a)
         /* x_dot += sum_trans a qd + sum_rot (a qd) x (r_b - o_j), omega += sum_rot a qd;
          * r_b is only known after the last joint, so the cross products are split into
          * w x r_b - sum (a qd) x o_j. */
-        const double qdj = rd.jointQd(m, j);
+        const double qdj = rd.finishQd(m, j, rawQ, rawQd);
         if (a.qdOut && active)
         {
           a.qdOut[s * dof + j] = qdj;
