@@ -128,6 +128,16 @@ int rcsb_ik_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, long 
                 const double* xDes, double lambda, double alpha, int iters, double* dx,
                 double* dq, double* det, unsigned flags, void* stream);
 
+/* ---- multi-GPU summary statistics ------------------------------------------------------- */
+
+/*
+ * out5 = {count, sum, sum of squares, min, max} of x[0], x[stride], ..., x[(n - 1) stride];
+ * x and out5 are device pointers on the current device, asynchronous on `stream`. This is the
+ * payload every rank contributes to the one all-gather of the sharded path (states are
+ * independent, so nothing else is exchanged).
+ */
+int rcsb_summary_stats(const double* x, long n, long stride, double* out5, void* stream);
+
 /* ---- utilities -------------------------------------------------------------------------- */
 
 const char* rcsb_last_error(void);

@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     kernel_launch_count,
     lib,
     library_path,
+    summary_stats,
 )
 
 __all__ = [
@@ -27,4 +28,5 @@ __all__ = [
     "kernel_launch_count",
     "lib",
     "library_path",
+    "summary_stats",
 ]

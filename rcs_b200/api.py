@@ -106,6 +106,7 @@ def lib() -> ctypes.CDLL:
         c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
     sig("RcsGraph_setState", ctypes.c_bool, c_void, c_void, c_void)
     sig("MatNd_create", c_void, ctypes.c_uint, ctypes.c_uint)
     sig("MatNd_destroy", None, c_void)
@@ -117,6 +118,26 @@ def lib() -> ctypes.CDLL:
 
 def kernel_launch_count() -> int:
     return int(lib().rcsb_kernel_launch_count())
+
+
+def summary_stats(x, out=None):
+    """[count, sum, sum of squares, min, max] of a (possibly strided) 1-D float64 CUDA tensor,
+    computed by one librcsb kernel on the current torch stream (rcsb_summary_stats)."""
+    import torch
+
+    if not (x.is_cuda and x.dtype == torch.float64 and x.dim() == 1):
+        raise RcsbError("summary_stats: need a 1-D float64 CUDA tensor")
+    if out is None:
+        out = torch.empty(5, dtype=torch.float64, device=x.device)
+    stride = x.stride(0) if x.numel() > 1 else 1
+    if stride < 1:
+        raise RcsbError("summary_stats: need a positive stride")
+    with torch.cuda.device(x.device):
+        rc = lib().rcsb_summary_stats(ctypes.c_void_p(x.data_ptr()), x.numel(), stride,
+                                      ctypes.c_void_p(out.data_ptr()),
+                                      ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _err(rc, "rcsb_summary_stats")
+    return out
 
 
 def _err(rc: int, what: str) -> None:

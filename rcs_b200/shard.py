@@ -29,6 +29,10 @@ def local_stats(values) -> "np.ndarray | object":
     if type(values).__module__.startswith("torch"):
         import torch
 
+        if values.is_cuda and values.dtype == torch.float64 and values.dim() == 1 and values.numel() > 0:
+            from .api import summary_stats
+
+            return summary_stats(values)          # one librcsb kernel instead of five torch ops
         v = values.reshape(-1).to(torch.float64)
         if v.numel() == 0:
             return torch.tensor([0.0, 0.0, 0.0, float("inf"), float("-inf")], dtype=torch.float64,
@@ -52,17 +56,23 @@ def merge_stats(gathered) -> Dict[str, float]:
             "min": float(g[:, 3].min()), "max": float(g[:, 4].max())}
 
 
-def all_gather_stats(stats, out=None):
+def all_gather_stats(stats, out=None, async_op=False):
     """One all_gather_into_tensor of the per-rank statistics over the default process group
-    (NCCL on GPU tensors, gloo on CPU tensors). Without an initialised group: a copy."""
+    (NCCL on GPU tensors, gloo on CPU tensors). Without an initialised group: a copy.
+
+    async_op=True returns (gathered, work): the collective is enqueued behind the work already
+    on the current stream and overlaps whatever the caller launches next; work.wait() before
+    reading `gathered`."""
     import torch
     import torch.distributed as dist
 
     t = stats if isinstance(stats, torch.Tensor) else torch.from_numpy(np.asarray(stats, dtype=np.float64))
     if not (dist.is_available() and dist.is_initialized()):
-        return t.reshape(1, -1).clone()
+        g = t.reshape(1, -1).clone()
+        return (g, None) if async_op else g
     world = dist.get_world_size()
     if out is None:
         out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t.contiguous())
-    return out.reshape(world, -1)
+    work = dist.all_gather_into_tensor(out, t.contiguous(), async_op=async_op)
+    g = out.reshape(world, -1)
+    return (g, work) if async_op else g
