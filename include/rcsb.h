@@ -102,6 +102,22 @@ int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q,
                       const double* effPt, double* JT, double* JR, unsigned flags,
                       void* stream);
 
+/*
+ * Task Jacobians relative to a (possibly articulated) reference body / frame:
+ * RcsGraph_3dPosJacobian (RCSB_JAC_POS) and RcsGraph_3dOmegaJacobian (RCSB_JAC_OMEGA),
+ * src/RcsCore/Rcs_kinematics.c:566, :789. effector / refBdy / refFrame are depth-first body
+ * indices, -1 = NULL (world). J [N x nJac x 3 x nJ].
+ */
+#define RCSB_JAC_POS 1
+#define RCSB_JAC_OMEGA 2
+typedef struct
+{
+  int kind;
+  int effector, refBdy, refFrame;
+} RcsbRelJac;
+int rcsb_task_jacobians(const RcsbModel* model, long N, int qdim, const double* q, int nJac,
+                        const RcsbRelJac* jac, double* J, unsigned flags, void* stream);
+
 /* ---- dynamics --------------------------------------------------------------------------- */
 
 /*
@@ -112,6 +128,15 @@ int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q,
 int rcsb_kinetic_terms(const RcsbModel* model, long N, int qdim, const double* q,
                        const double* qd, double* M, double* h, double* Fg, double* E,
                        unsigned flags, void* stream);
+
+/*
+ * Centre of gravity cog [N x 3] (RcsGraph_COG, src/RcsCore/Rcs_kinematics.c:904) and its
+ * Jacobian Jcog [N x 3 x nJ] (RcsGraph_COGJacobian, :973); either may be NULL. Same kernels as
+ * rcsb_kinetic_terms: column k of sum_b m_b JT_b is the linear momentum of column k's composite
+ * body under a unit joint rate.
+ */
+int rcsb_cog(const RcsbModel* model, long N, int qdim, const double* q, double* cog, double* Jcog,
+             unsigned flags, void* stream);
 
 /* ---- inverse kinematics ----------------------------------------------------------------- */
 
@@ -162,8 +187,19 @@ void RcsGraph_bodyPointJacobian(const RcsGraph* self, const RcsBody* body, const
                                 double A_BI[3][3], MatNd* J);
 void RcsGraph_rotationJacobian(const RcsGraph* self, const RcsBody* body, double A_BI[3][3],
                                MatNd* J);
+/* src/RcsCore/Rcs_kinematics.c:566, :789 */
+void RcsGraph_3dPosJacobian(const RcsGraph* self, const RcsBody* effector, const RcsBody* refBdy,
+                            const RcsBody* refFrame, MatNd* J);
+void RcsGraph_3dOmegaJacobian(const RcsGraph* self, const RcsBody* effector, const RcsBody* refBdy,
+                              const RcsBody* refFrame, MatNd* J);
 /* src/RcsCore/Rcs_dynamics.c:439 */
 double RcsGraph_computeKineticTerms(const RcsGraph* self, MatNd* M, MatNd* h, MatNd* F_gravity);
+/* src/RcsCore/Rcs_dynamics.c:610, :576 */
+void RcsGraph_computeMassMatrix(const RcsGraph* self, MatNd* M);
+void RcsGraph_computeGravityTorque(const RcsGraph* self, MatNd* T_gravity);
+/* src/RcsCore/Rcs_kinematics.c:904, :973; RcsGraph_COG returns the mass it averaged over */
+double RcsGraph_COG(const RcsGraph* self, double r_cog[3]);
+void RcsGraph_COGJacobian(const RcsGraph* self, MatNd* J_cog);
 
 #ifdef __cplusplus
 }

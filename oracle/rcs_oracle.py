@@ -293,6 +293,52 @@ class Oracle:
         return {"M": M, "h": h, "Fg": Fg, "E": V + T}
 
     # ------------------------------------------------------------------------------------
+    # task Jacobians relative to a reference body / frame:
+    # RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian (Rcs_kinematics.c:566-615, :789-822)
+    # ------------------------------------------------------------------------------------
+    def is_articulated(self, body: int) -> bool:
+        """RcsBody_isArticulated (src/RcsCore/Rcs_body.c:688)."""
+        return any(self.jac[j] >= 0 for j in self.chain(body))
+
+    def task_jacobians(self, q, spec):
+        """spec: [(kind "POS" | "OMEGA", effector, refBdy, refFrame)], body indices, -1 = NULL."""
+        self.fk(q)
+        org, rot, jorg, jrot = self._last
+        n = org.shape[0]
+        zero = np.zeros((n, 3, self.nJ))
+
+        def JT(b):
+            return zero.copy() if b < 0 else self._point_jacobian(b, org[:, b], jorg, jrot)
+
+        def JR(b):
+            return zero.copy() if b < 0 else self._rotation_jacobian(b, jrot, n)
+
+        out = np.zeros((n, len(spec), 3, self.nJ))
+        for t, (kind, eff, rb, rf) in enumerate(spec):
+            if kind == "POS":
+                if rb < 0:
+                    J = JT(eff)
+                    if rf >= 0:
+                        J = np.einsum("nij,njk->nik", rot[:, rf], J)
+                else:
+                    r2 = org[:, eff] if eff >= 0 else np.zeros((n, 3))
+                    r12 = r2 - org[:, rb]
+                    J = JT(eff) - JT(rb) + np.cross(r12[:, :, None], JR(rf), axis=1)
+                    A = rot[:, rf] if (rf >= 0 and rf != rb) else rot[:, rb]
+                    J = np.einsum("nij,njk->nik", A, J)
+            else:
+                if rb < 0 and rf < 0:
+                    J = JR(eff)
+                elif rb >= 0 and rf == rb and not self.is_articulated(rb):
+                    J = np.einsum("nij,njk->nik", rot[:, rb], JR(eff))
+                else:
+                    J = JR(eff) - JR(rb)
+                    if rf >= 0:
+                        J = np.einsum("nij,njk->nik", rot[:, rf], J)
+            out[:, t] = J
+        return out
+
+    # ------------------------------------------------------------------------------------
     # centre of gravity: RcsGraph_COG / RcsGraph_COGJacobian (Rcs_kinematics.c:904, :973)
     # ------------------------------------------------------------------------------------
     def cog(self, q):

@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
         L.ref_fk_jacobians.argtypes = [vp, cl, ci, vp, ci, vp, vp, vp, vp, vp]
         L.ref_cog.restype = cd
         L.ref_cog.argtypes = [vp, cl, ci, vp, vp, vp]
+        L.ref_task_jacobians.restype = cd
+        L.ref_task_jacobians.argtypes = [vp, cl, ci, vp, ci, vp, vp]
         L.ref_kinetic_terms.restype = cd
         L.ref_kinetic_terms.argtypes = [vp, cl, ci] + [vp] * 6
         L.ref_mass_matrix.restype = cd
@@ -168,6 +170,20 @@ class RefGraph:
         J = np.empty((N, 3, self.nJ))
         self.last_seconds = lib().ref_cog(self._h, N, qdim, _p(q), _p(cog), _p(J))
         return cog, J
+
+    # RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian (Rcs_kinematics.c:566, :789)
+    def task_jacobians(self, q, spec):
+        """spec: sequence of (kind "POS" | "OMEGA", effector, refBdy, refFrame) body indices,
+        -1 for NULL. Returns J: N x len(spec) x 3 x nJ."""
+        q = _c(q)
+        N, qdim = q.shape
+        flat = []
+        for kind, eff, rb, rf in spec:
+            flat += [1 if kind == "POS" else 2, int(eff), int(rb), int(rf)]
+        arr = (ctypes.c_int * max(len(flat), 1))(*flat)
+        J = np.empty((N, len(spec), 3, self.nJ))
+        self.last_seconds = lib().ref_task_jacobians(self._h, N, qdim, _p(q), len(spec), arr, _p(J))
+        return J
 
     # RcsGraph_computeKineticTerms (Rcs_dynamics.c:439)
     def kinetic_terms(self, q, qd=None, want=("M", "h", "Fg", "E")):

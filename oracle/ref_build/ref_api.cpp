@@ -438,6 +438,45 @@ double ref_cog(void* g, long N, int qdim, const double* q, double* cog, double* 
   });
 }
 
+/* Task Jacobians relative to a (possibly articulated) reference body / frame:
+ * RcsGraph_3dPosJacobian (kind 1) / RcsGraph_3dOmegaJacobian (kind 2), Rcs_kinematics.c:566, :789.
+ * spec: nJac x {kind, effector, refBdy, refFrame} (depth-first body indices, -1 = NULL).
+ * J: N x nJac x 3 x nJ. */
+double ref_task_jacobians(void* g, long N, int qdim, const double* q, int nJac, const int* spec,
+                          double* Jout)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    std::vector<RcsBody*> bodies = dfsBodies(graph);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* J = MatNd_create(3, nJ);
+    auto body = [&](int idx) -> const RcsBody* { return idx < 0 ? NULL : bodies[idx]; };
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      for (int t = 0; t < nJac; ++t)
+      {
+        const int* sp = spec + 4 * t;
+        if (sp[0] == 1)
+        {
+          RcsGraph_3dPosJacobian(graph, body(sp[1]), body(sp[2]), body(sp[3]), J);
+        }
+        else
+        {
+          RcsGraph_3dOmegaJacobian(graph, body(sp[1]), body(sp[2]), body(sp[3]), J);
+        }
+        memcpy(Jout + ((size_t) i * nJac + t) * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(J);
+    RcsGraph_destroy(graph);
+  });
+}
+
 /* Kinetic terms. M: N x nJ x nJ, h: N x nJ, Fg: N x nJ, E: N (any may be NULL). */
 double ref_kinetic_terms(void* g, long N, int qdim, const double* q, const double* qd,
                          double* M, double* h, double* Fg, double* E)

@@ -33,7 +33,8 @@ class RcsbError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "librcsb.so")
+    # RCSB_LIBRARY: an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("RCSB_LIBRARY") or os.path.join(_HERE, "librcsb.so")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -49,6 +50,11 @@ def build_library(verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("building librcsb.so failed")
     return library_path()
+
+
+class _RcsbRelJac(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("effector", ctypes.c_int), ("refBdy", ctypes.c_int),
+                ("refFrame", ctypes.c_int)]
 
 
 class _RcsbTask(ctypes.Structure):
@@ -104,6 +110,9 @@ def lib() -> ctypes.CDLL:
         c_int, c_void, c_void, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_kinetic_terms", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
         c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_task_jacobians", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
+        ctypes.c_uint, c_void)
+    sig("rcsb_cog", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
@@ -362,6 +371,22 @@ class Model:
         _err(rc, "rcsb_fk_jacobians")
         return out
 
+    def task_jacobians(self, q, spec, out=None):
+        """RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian over a batch.
+
+        spec: sequence of ("POS" | "OMEGA", effector, refBdy, refFrame), body indices, -1 = NULL.
+        Returns J [N x len(spec) x 3 x nJ]."""
+        N, qdim = self._batch(q)
+        if out is None:
+            out = self._alloc(q, (N, len(spec), 3, self.nJ))
+        arr = (_RcsbRelJac * max(len(spec), 1))(
+            *[_RcsbRelJac(1 if k == "POS" else 2, int(e), int(rb), int(rf)) for k, e, rb, rf in spec])
+        a = _Args(self)
+        rc = lib().rcsb_task_jacobians(self._h, N, qdim, a.ptr(q, "q"), len(spec), arr,
+                                       a.ptr(out, "J"), a.flags(), a.stream())
+        _err(rc, "rcsb_task_jacobians")
+        return out
+
     # -- dynamics ------------------------------------------------------------------------
     def kinetic_terms(self, q, qd=None, want=("M", "h", "Fg", "E"), out=None):
         """RcsGraph_computeKineticTerms over a batch."""
@@ -378,6 +403,20 @@ class Model:
             a.flags(), a.stream(),
         )
         _err(rc, "rcsb_kinetic_terms")
+        return out
+
+    def cog(self, q, want=("cog", "Jcog"), out=None):
+        """RcsGraph_COG / RcsGraph_COGJacobian over a batch."""
+        N, qdim = self._batch(q)
+        shapes = {"cog": (N, 3), "Jcog": (N, 3, self.nJ)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        a = _Args(self)
+        rc = lib().rcsb_cog(self._h, N, qdim, a.ptr(q, "q"), a.ptr(out.get("cog"), "cog"),
+                            a.ptr(out.get("Jcog"), "Jcog"), a.flags(), a.stream())
+        _err(rc, "rcsb_cog")
         return out
 
     # -- inverse kinematics --------------------------------------------------------------

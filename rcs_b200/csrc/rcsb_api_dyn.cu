@@ -119,19 +119,19 @@ int buildKtPlan(RcsbModel* m)
   }
   const int nRuns = (int) runLink.size();
 
-  if (nJ > 255 || rec + 1 > 65535)
+  if (nJ > 255 || rec + 5 > 65535)
   {
-    rcsb_set_error("rcsb_kinetic_terms: model too large (nJ %d, record %d doubles)", nJ, rec + 1);
+    rcsb_set_error("rcsb_kinetic_terms: model too large (nJ %d, record %d doubles)", nJ, rec + 5);
     return RCSB_EUNSUPPORTED;
   }
 
   /* shared-memory layout of the assembly kernel */
   const int asmV = 16 * nJ;
-  const int asmRuns = 16 * nJ + 4;
+  const int asmRuns = 16 * nJ + 8;
   const int runArea = RCSB_KT_LINK_REC * nRuns > nJ * nJ ? RCSB_KT_LINK_REC * nRuns : nJ * nJ;
   const int asmDoubles = asmRuns + runArea;
-  const int recDoubles = (rec + 1 + 3) & ~3;
-  std::vector<unsigned short> recDst((size_t) recDoubles, (unsigned short) (asmV + 1));
+  const int recDoubles = (rec + 5 + 3) & ~3;
+  std::vector<unsigned short> recDst((size_t) recDoubles, (unsigned short) (asmV + 7));
   for (int k = 0; k < nJ; ++k)
   {
     for (int t = 0; t < RCSB_KT_COL_REC; ++t)
@@ -156,7 +156,10 @@ int buildKtPlan(RcsbModel* m)
       extraRuns.push_back(linkHome[runLink[r]]);
     }
   }
-  recDst[(size_t) rec] = (unsigned short) asmV;
+  for (int t = 0; t < 5; ++t)
+  {
+    recDst[(size_t) rec + t] = (unsigned short) (asmV + t);
+  }
   std::vector<int> colHome((size_t) (nJ > 0 ? nJ : 1), 0);
   for (int k = 0; k < nJ; ++k)
   {
@@ -273,7 +276,7 @@ long ktChunk(const RcsbModel* m, int recDoubles)
 }
 
 int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
-             double* h, double* Fg, double* E, cudaStream_t stream, int ws)
+             double* h, double* Fg, double* E, double* cog, double* Jcog, cudaStream_t stream, int ws)
 {
   const int recDoubles = m->ktPlan.aux0;
   const long chunk = ktChunk(m, recDoubles) < N ? ktChunk(m, recDoubles) : N;
@@ -313,6 +316,8 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     a.h = h ? h + s0 * nJ : nullptr;
     a.Fg = Fg ? Fg + s0 * nJ : nullptr;
     a.E = E ? E + s0 : nullptr;
+    a.cog = cog ? cog + s0 * 3 : nullptr;
+    a.Jcog = Jcog ? Jcog + s0 * 3 * nJ : nullptr;
     a.rec = m->ktScratch[ws];
     a.recDoubles = recDoubles;
     RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, m->ktPlan.aux1, m->smCount, stream));
@@ -323,9 +328,9 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
 
 }   // namespace
 
-extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const double* q,
-                                  const double* qd, double* M, double* h, double* Fg, double* E,
-                                  unsigned flags, void* stream)
+static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
+                    double* M, double* h, double* Fg, double* E, double* cog, double* Jcog,
+                    unsigned flags, void* stream)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   int rc = checkModel(m, N, qdim, q);
@@ -341,25 +346,41 @@ extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const d
 
   if (!(flags & RCSB_HOST_PTRS))
   {
-    /* the workspace is shared: device-pointer calls on one model must use one stream at a
+    /* the record buffer is shared: device-pointer calls on one model must use one stream at a
      * time (documented in rcsb.h) */
-    return ktDevice(m, N, qdim, q, qd, M, h, Fg, E, static_cast<cudaStream_t>(stream), 0);
+    return ktDevice(m, N, qdim, q, qd, M, h, Fg, E, cog, Jcog, static_cast<cudaStream_t>(stream), 0);
   }
 
   const size_t nJ = (size_t) m->hdr.nJ;
   std::vector<StagedArray> arr;
-  enum { I_Q, I_QD, I_M, I_H, I_G, I_E };
+  enum { I_Q, I_QD, I_M, I_H, I_G, I_E, I_C, I_JC };
   arr.push_back({q, nullptr, (size_t) qdim, nullptr});
   arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
   arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
   arr.push_back({nullptr, h, h ? nJ : 0, nullptr});
   arr.push_back({nullptr, Fg, Fg ? nJ : 0, nullptr});
   arr.push_back({nullptr, E, (size_t) (E ? 1 : 0), nullptr});
+  arr.push_back({nullptr, cog, (size_t) (cog ? 3 : 0), nullptr});
+  arr.push_back({nullptr, Jcog, Jcog ? 3 * nJ : 0, nullptr});
   return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int slot) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
     return ktDevice(m, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_M, M), dv(I_H, h), dv(I_G, Fg),
-                    dv(I_E, E), st, slot);
+                    dv(I_E, E), dv(I_C, cog), dv(I_JC, Jcog), st, slot);
   });
+}
+
+extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const double* q,
+                                  const double* qd, double* M, double* h, double* Fg, double* E,
+                                  unsigned flags, void* stream)
+{
+  return ktCommon(cm, N, qdim, q, qd, M, h, Fg, E, nullptr, nullptr, flags, stream);
+}
+
+extern "C" int rcsb_cog(const RcsbModel* cm, long N, int qdim, const double* q, double* cog,
+                        double* Jcog, unsigned flags, void* stream)
+{
+  return ktCommon(cm, N, qdim, q, nullptr, nullptr, nullptr, nullptr, nullptr, cog, Jcog, flags,
+                  stream);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -501,7 +522,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
         {
           if (jntFlags[j] & RCSB_JF_HAS_AJP)
           {
-            const int step[4] = {0, m->hdr.off[RCSB_A_JNT_AJP] + 96 * j, 0, 0};
+            const int step[4] = {0, m->hdr.off[RCSB_A_JNT_AJP] + 96 * j, jntFlags[j], 0};
             prog.insert(prog.end(), step, step + 4);
           }
           if (jntJacobi[j] >= 0)
@@ -518,7 +539,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
         }
         if (bodyFlags[b] & RCSB_BF_HAS_ABP)
         {
-          const int step[4] = {0, m->hdr.off[RCSB_A_BODY_ABP] + 96 * b, 0, 0};
+          const int step[4] = {0, m->hdr.off[RCSB_A_BODY_ABP] + 96 * b, bodyFlags[b], 0};
           prog.insert(prog.end(), step, step + 4);
         }
       }

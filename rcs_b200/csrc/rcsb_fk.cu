@@ -179,7 +179,7 @@ fkKernel(const FkArgs a)
       const int jf = m.jntFlags[j];
       if (jf & RCSB_JF_HAS_AJP)
       {
-        applyRel(f, m.jntAJP + 12 * j);
+        applyRelF(f, m.jntAJP + 12 * j, jf);
       }
 
       /* joints are visited in jointIndex order: the loads of the next joint are in flight
@@ -270,7 +270,7 @@ fkKernel(const FkArgs a)
     /* ---- body frame ---------------------------------------------------------------------- */
     if (bflags & RCSB_BF_HAS_ABP)
     {
-      applyRel(f, m.bodyABP + 12 * b);
+      applyRelF(f, m.bodyABP + 12 * b, bflags);
     }
 
     if (VEL)

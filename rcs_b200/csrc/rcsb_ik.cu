@@ -322,7 +322,7 @@ ikKernel(const IkArgs a)
         const int jf = m.jntFlags[j];
         if (jf & RCSB_JF_HAS_AJP)
         {
-          applyRel(f, m.jntAJP + 12 * j);
+          applyRelF(f, m.jntAJP + 12 * j, jf);
         }
         const double qj = qv[j];
         const int dir = m.jntType[j] % 3;
@@ -354,7 +354,7 @@ ikKernel(const IkArgs a)
       }
       if (bflags & RCSB_BF_HAS_ABP)
       {
-        applyRel(f, m.bodyABP + 12 * b);
+        applyRelF(f, m.bodyABP + 12 * b, bflags);
       }
       if (NSLOTS > 0)
       {
@@ -623,7 +623,7 @@ __device__ __forceinline__ void chainStep(Frame& f, const int4 st, const char* s
 {
   if (st.x == 0)
   {
-    applyRel(f, reinterpret_cast<const double*>(sModel + st.y));
+    applyRelF(f, reinterpret_cast<const double*>(sModel + st.y), st.z);
     return;
   }
   const double qj = qRow[st.z];
@@ -658,8 +658,11 @@ __device__ __forceinline__ void chainStep(Frame& f, const int4 st, const char* s
  * effector's rotation matrix directly instead of rebuilding it from its Euler angles
  * (TaskEuler3D.cpp:110, :243): identical up to rounding away from gimbal lock.
  */
+#ifndef RCSB_IK_CHAIN_MIN_BLOCKS
+#define RCSB_IK_CHAIN_MIN_BLOCKS 2
+#endif
 template <int NC, int NX>
-__global__ void __launch_bounds__(RCSB_IK_THREADS)
+__global__ void __launch_bounds__(RCSB_IK_THREADS, RCSB_IK_CHAIN_MIN_BLOCKS)
 ikChainKernel(const IkArgs a)
 {
   extern __shared__ __align__(16) char smem[];

@@ -50,6 +50,8 @@ struct KtArgs
   double* h;
   double* Fg;
   double* E;
+  double* cog;         /* N x 3 centre of gravity (RcsGraph_COG) */
+  double* Jcog;        /* N x 3 x nJ (RcsGraph_COGJacobian) */
   double* rec;         /* N x recDoubles per-state records (walk -> assembly) */
   int recDoubles;
   int planWalkBytes;   /* leading part of the plan staged by the walk kernel */

@@ -300,6 +300,7 @@ ktWalkKernel(const KtArgs a)
   }
   keep = k;
   double V = 0.0;
+  double freeM[4] = {0.0, 0.0, 0.0, 0.0};   /* m, m c of massive bodies no joint moves */
   double nextQ = 0.0, nextQd = 0.0;
   if (dof > 0)
   {
@@ -366,7 +367,7 @@ ktWalkKernel(const KtArgs a)
       if (jf & RCSB_JF_HAS_AJP)
       {
         double d[3];
-        applyRelD(k.f, m.jntAJP + 12 * j, d);
+        applyRelD(k.f, m.jntAJP + 12 * j, jf, d);
         if (VEL)
         {
           addOffsetAccel(k, d);
@@ -446,7 +447,7 @@ ktWalkKernel(const KtArgs a)
     if (bflags & RCSB_BF_HAS_ABP)
     {
       double d[3];
-      applyRelD(k.f, m.bodyABP + 12 * b, d);
+      applyRelD(k.f, m.bodyABP + 12 * b, bflags, d);
       if (VEL)
       {
         addOffsetAccel(k, d);
@@ -497,7 +498,14 @@ ktWalkKernel(const KtArgs a)
       const double c[3] = {k.f.o[0] + r[0], k.f.o[1] + r[1], k.f.o[2] + r[2]};
       V += mass * grav * c[2];
 
-      if (p.bodyLink[b] >= 0)   /* some unconstrained joint moves the body */
+      if (p.bodyLink[b] < 0)
+      {
+        freeM[0] += mass;
+        freeM[1] += mass * c[0];
+        freeM[2] += mass * c[1];
+        freeM[3] += mass * c[2];
+      }
+      else   /* some unconstrained joint moves the body */
       {
         /* world inertia about the COM: R^T I_b R (Mat3d_similarityTransform) */
         double tmp[9], Iw[9];
@@ -571,7 +579,8 @@ ktWalkKernel(const KtArgs a)
   {
     emitRun();
   }
-  w.emit(V);
+  const double tail[5] = {V, freeM[0], freeM[1], freeM[2], freeM[3]};
+  w.emitN(tail);
   w.finish();
 }
 
@@ -749,6 +758,42 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
     }
     __syncwarp();
+
+    /* ---- centre of gravity and its Jacobian (RcsGraph_COG / RcsGraph_COGJacobian,
+     * Rcs_kinematics.c:904, :973): column k of sum_b m_b JT_b is the linear momentum p of
+     * column k's composite under a unit joint rate ---------------------------------------- */
+    if (a.cog || a.Jcog)
+    {
+      const double* tail = buf + p.hdr->asmV;
+      double mT = tail[1], mc0 = tail[2], mc1 = tail[3], mc2 = tail[4];
+      for (int l = 0; l < nLinks; ++l)
+      {
+        if (p.linkParent[l] < 0)
+        {
+          const double* cp = buf + p.linkHome[l];
+          mT += cp[0];
+          mc0 += cp[1];
+          mc1 += cp[2];
+          mc2 += cp[3];
+        }
+      }
+      const double inv = mT > 0.0 ? 1.0 / mT : 0.0;
+      if (a.cog && gl == 0 && valid)
+      {
+        a.cog[s * 3] = mc0 * inv;
+        a.cog[s * 3 + 1] = mc1 * inv;
+        a.cog[s * 3 + 2] = mc2 * inv;
+      }
+      if (a.Jcog && valid)
+      {
+        for (int e = gl; e < 3 * nJ; e += LPS)
+        {
+          const int r = e / nJ, k = e - r * nJ;
+          a.Jcog[s * 3 * nJ + e] = fb[9 * k + r] * inv;
+        }
+      }
+      __syncwarp();   /* the composites are overwritten by the matrix staging below */
+    }
 
     /* ---- mass matrix: only the structurally non-zero pairs (ancestor i, column k) ----------
      * M[i][k] = <joint i, momentum of column k>; M[k][i] the same with the transposed

@@ -20,6 +20,30 @@ static int alignUp16(int x)
   return (x + 15) & ~15;
 }
 
+/* Exactly-identity rotation / exactly-zero translation of a relative transform: the kernels
+ * skip the corresponding products (the result is bit-identical). */
+static int relFlags(const HTr* A)
+{
+  int f = 0;
+  bool ident = true;
+  for (int i = 0; i < 3; ++i)
+  {
+    for (int j = 0; j < 3; ++j)
+    {
+      ident = ident && (A->rot[i][j] == (i == j ? 1.0 : 0.0));
+    }
+  }
+  if (ident)
+  {
+    f |= RCSB_REL_ROT_IDENT;
+  }
+  if (A->org[0] == 0.0 && A->org[1] == 0.0 && A->org[2] == 0.0)
+  {
+    f |= RCSB_REL_NO_TRANS;
+  }
+  return f;
+}
+
 int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
 {
   if (!graph || !blobOut || !bytesOut)
@@ -175,7 +199,7 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
     double* abp = DARR(RCSB_A_BODY_ABP) + 12 * b;
     if (B->A_BP)
     {
-      flags |= RCSB_BF_HAS_ABP;
+      flags |= RCSB_BF_HAS_ABP | relFlags(B->A_BP);
       memcpy(abp, B->A_BP, sizeof(HTr));
     }
     else
@@ -232,7 +256,7 @@ int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut)
       double* ajp = DARR(RCSB_A_JNT_AJP) + 12 * j;
       if (J->A_JP)
       {
-        jf |= RCSB_JF_HAS_AJP;
+        jf |= RCSB_JF_HAS_AJP | relFlags(J->A_JP);
         memcpy(ajp, J->A_JP, sizeof(HTr));
       }
       else

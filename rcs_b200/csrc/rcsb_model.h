@@ -19,10 +19,17 @@ extern "C" {
 #define RCSB_BF_HAS_ABP 1      /* A_BP is not the identity */
 #define RCSB_BF_HAS_MASS 2     /* m != 0: contributes to the kinetic terms */
 #define RCSB_BF_LEAF 4         /* no children (and not a root): evaluated on a register copy */
+#define RCSB_BF_ABP_ROT_IDENT 8   /* rotation part of A_BP is exactly the identity */
+#define RCSB_BF_ABP_NO_TRANS 16   /* translation part of A_BP is exactly zero */
 /* joint flags */
 #define RCSB_JF_HAS_AJP 1
 #define RCSB_JF_CONSTRAINED 2
 #define RCSB_JF_ROT 4          /* rotational (else translational) */
+#define RCSB_JF_AJP_ROT_IDENT 8   /* rotation part of A_JP is exactly the identity */
+#define RCSB_JF_AJP_NO_TRANS 16   /* translation part of A_JP is exactly zero */
+/* the *_ROT_IDENT / *_NO_TRANS bits share their values between body and joint flags */
+#define RCSB_REL_ROT_IDENT 8
+#define RCSB_REL_NO_TRANS 16
 
 /* frame sources of a body (bodyLoad) */
 #define RCSB_LOAD_CONT (-2)    /* parent is the previously visited body: keep registers */

@@ -67,7 +67,8 @@ typedef struct
  *                           not symmetrised: the reference uses the tensor of the file as
  *                           given), 13..15 bias force, 16..18 bias moment about the world
  *                           origin} of the bodies of the run, belonging to link runLink[r]
- *   potential energy at recV
+ *   tail at recV: potential energy, then m and m c (3) of the massive bodies that no
+ *   unconstrained joint moves (they count for the centre of gravity only)
  */
 #define RCSB_KT_COL_REC 7
 #define RCSB_KT_LINK_REC 19
@@ -79,7 +80,7 @@ typedef struct
   int totalBytes;
   int recDoubles;       /* doubles per state record (multiple of 4) */
   int nRuns;
-  int recV;             /* offset of the potential energy */
+  int recV;             /* offset of the 5-double tail: V, m_free, (m c)_free */
   int nPairs;           /* structurally non-zero entries of the upper triangle of M */
   int symmetric;        /* 1: every inertia tensor of the model is symmetric (M = M^T) */
   int offBodyLink;      /* int[nb]: link the body is lumped into, -1 = none (no joint moves it) */
@@ -95,7 +96,7 @@ typedef struct
   /* assembly kernel: per-state shared-memory layout (doubles)
    *   [0, 7 nJ)            column k at 7 k: axis, origin, rate
    *   [7 nJ, 16 nJ)        column k at 7 nJ + 9 k: p, L, L with the transposed inertia
-   *   asmV                 potential energy
+   *   asmV                 the 5-double tail of the record (8 slots reserved)
    *   [asmRuns, ...)       run r at asmRuns + 19 r; the first run of a link becomes the link's
    *                        composite in place; later the same area holds the nJ x nJ matrix */
   int asmV, asmRuns, asmDoubles;
@@ -145,7 +146,7 @@ typedef struct
   int nOther;           /* unconstrained joints that are not on the chain */
   int offProgStart;     /* int[chainNc + 2] */
   int offProg;          /* int4[nSteps]: {op, a, b, 0}; op 0: relative transform at byte offset a
-                           of the flat model; op 1: joint of type a, jointIndex b, value from q */
+                           of the flat model, b = its RCSB_REL_* flags; op 1: joint of type a, jointIndex b, value from q */
   int offChainType;     /* int[chainNc]: RCSJOINT_TYPE of the column's joint */
   int offChainJoint;    /* int[chainNc]: jointIndex */
   int offChainW;        /* double[chainNc]: invWq */

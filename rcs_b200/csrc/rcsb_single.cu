@@ -5,6 +5,10 @@
  *   RcsGraph_bodyPointJacobian         src/RcsCore/Rcs_kinematics.c:200
  *   RcsGraph_rotationJacobian          src/RcsCore/Rcs_kinematics.c:416
  *   RcsGraph_computeKineticTerms       src/RcsCore/Rcs_dynamics.c:439
+ *   RcsGraph_computeMassMatrix         src/RcsCore/Rcs_dynamics.c:610
+ *   RcsGraph_computeGravityTorque      src/RcsCore/Rcs_dynamics.c:576
+ *   RcsGraph_COG / RcsGraph_COGJacobian   src/RcsCore/Rcs_kinematics.c:904, :973
+ *   RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian   src/RcsCore/Rcs_kinematics.c:566, :789
  * as N = 1 calls into the batched kernels, so that code (and tests) written against the
  * reference run unchanged on this library. Nothing is evaluated on the host: the wrappers
  * only move the state in and the results back into the RcsGraph / MatNd structures.
@@ -353,4 +357,124 @@ extern "C" double RcsGraph_computeKineticTerms(const RcsGraph* cself, MatNd* M, 
     return 0.0;
   }
   return E;
+}
+
+extern "C" void RcsGraph_computeMassMatrix(const RcsGraph* cself, MatNd* M)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  GraphCache* c = (self && M) ? cacheOf(self) : nullptr;
+  if (!c || M->size < self->nJ * self->nJ)
+  {
+    RCSB_FATAL("RcsGraph_computeMassMatrix: %s", c ? "M is too small" : rcsb_last_error());
+    return;
+  }
+  MatNd_reshapeAndSetZero(M, self->nJ, self->nJ);
+  if (rcsb_kinetic_terms(c->model, 1, (int) self->dof, c->q.data(), nullptr, M->ele, nullptr,
+                         nullptr, nullptr, RCSB_HOST_PTRS, nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("RcsGraph_computeMassMatrix: %s", rcsb_last_error());
+  }
+}
+
+extern "C" void RcsGraph_computeGravityTorque(const RcsGraph* cself, MatNd* T_gravity)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  GraphCache* c = (self && T_gravity) ? cacheOf(self) : nullptr;
+  if (!c || T_gravity->size < self->nJ)
+  {
+    RCSB_FATAL("RcsGraph_computeGravityTorque: %s", c ? "T_gravity is too small" : rcsb_last_error());
+    return;
+  }
+  MatNd_reshapeAndSetZero(T_gravity, self->nJ, 1);
+  /* J_cog^T (0, 0, -m g) = sum_b m_b JT_b^T (0, 0, -g): the F_gravity of the kinetic terms */
+  if (rcsb_kinetic_terms(c->model, 1, (int) self->dof, c->q.data(), nullptr, nullptr, nullptr,
+                         T_gravity->ele, nullptr, RCSB_HOST_PTRS, nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("RcsGraph_computeGravityTorque: %s", rcsb_last_error());
+  }
+}
+
+extern "C" double RcsGraph_COG(const RcsGraph* cself, double r_cog[3])
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  GraphCache* c = (self && r_cog) ? cacheOf(self) : nullptr;
+  if (!c)
+  {
+    RCSB_FATAL("RcsGraph_COG: %s", rcsb_last_error());
+    return 0.0;
+  }
+  r_cog[0] = r_cog[1] = r_cog[2] = 0.0;
+  if (rcsb_cog(c->model, 1, (int) self->dof, c->q.data(), r_cog, nullptr, RCSB_HOST_PTRS,
+               nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("RcsGraph_COG: %s", rcsb_last_error());
+    return 0.0;
+  }
+  double m = 0.0;
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    m += BODY->m > 0.0 ? BODY->m : 0.0;
+  }
+  return m;
+}
+
+extern "C" void RcsGraph_COGJacobian(const RcsGraph* cself, MatNd* J_cog)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  GraphCache* c = (self && J_cog) ? cacheOf(self) : nullptr;
+  if (!c || J_cog->size < 3 * self->nJ)
+  {
+    RCSB_FATAL("RcsGraph_COGJacobian: %s", c ? "J_cog is too small" : rcsb_last_error());
+    return;
+  }
+  MatNd_reshapeAndSetZero(J_cog, 3, self->nJ);
+  if (self->nJ > 0 && rcsb_cog(c->model, 1, (int) self->dof, c->q.data(), nullptr, J_cog->ele,
+                               RCSB_HOST_PTRS, nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("RcsGraph_COGJacobian: %s", rcsb_last_error());
+  }
+}
+
+namespace
+{
+
+void relJacobian(const RcsGraph* cself, int kind, const RcsBody* effector, const RcsBody* refBdy,
+                 const RcsBody* refFrame, MatNd* J, const char* who)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cself);
+  GraphCache* c = (self && J) ? cacheOf(self) : nullptr;
+  if (!c || J->size < 3 * self->nJ)
+  {
+    RCSB_FATAL("%s: %s", who, c ? "J is too small" : rcsb_last_error());
+    return;
+  }
+  MatNd_reshapeAndSetZero(J, 3, self->nJ);
+  if (self->nJ == 0)
+  {
+    return;
+  }
+  RcsbRelJac r;
+  r.kind = kind;
+  r.effector = effector ? RcsGraph_bodyIndex(self, effector) : -1;
+  r.refBdy = refBdy ? RcsGraph_bodyIndex(self, refBdy) : -1;
+  r.refFrame = refFrame ? RcsGraph_bodyIndex(self, refFrame) : -1;
+  if (rcsb_task_jacobians(c->model, 1, (int) self->dof, c->q.data(), 1, &r, J->ele, RCSB_HOST_PTRS,
+                          nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("%s: %s", who, rcsb_last_error());
+  }
+}
+
+}   // namespace
+
+extern "C" void RcsGraph_3dPosJacobian(const RcsGraph* self, const RcsBody* effector,
+                                       const RcsBody* refBdy, const RcsBody* refFrame, MatNd* J)
+{
+  relJacobian(self, RCSB_JAC_POS, effector, refBdy, refFrame, J, "RcsGraph_3dPosJacobian");
+}
+
+extern "C" void RcsGraph_3dOmegaJacobian(const RcsGraph* self, const RcsBody* effector,
+                                         const RcsBody* refBdy, const RcsBody* refFrame, MatNd* J)
+{
+  relJacobian(self, RCSB_JAC_OMEGA, effector, refBdy, refFrame, J, "RcsGraph_3dOmegaJacobian");
 }

@@ -1,0 +1,303 @@
+/*
+ * Task Jacobians relative to a (possibly articulated) reference body / frame, batched:
+ *   RcsGraph_3dPosJacobian    src/RcsCore/Rcs_kinematics.c:566-615
+ *       world:      J = JT_2, rotated by A_3I if a refFrame is given
+ *       relative:   J = A_xI (JT_2 - JT_1 + r_12 x JR_3),  x = refFrame if given and != refBdy,
+ *                   else refBdy
+ *   RcsGraph_3dOmegaJacobian  src/RcsCore/Rcs_kinematics.c:789-822
+ *       world:      J = JR_2
+ *       fixed ref:  J = A_1I JR_2          (refFrame == refBdy, not articulated)
+ *       relative:   J = A_3I (JR_2 - JR_1)
+ * (2 = effector, 1 = refBdy, 3 = refFrame.) The frames and world Jacobians of the bodies
+ * involved come from fkKernel (rcsb_fk.cu) in passes of a few ten thousand states, so that
+ * the intermediate stays in L2; combineKernel turns them into the task rows, one thread per
+ * (state, task, column), consecutive threads on consecutive columns.
+ */
+#include "rcsb_priv.h"
+
+namespace
+{
+
+struct CombineTask
+{
+  int kind;       /* RCSB_JAC_POS / RCSB_JAC_OMEGA */
+  int mode;       /* 0 world (optionally rotated), 1 relative */
+  int u2, u1, u3; /* slots of effector / refBdy / rotation-Jacobian body in the pass buffers, -1 */
+  int uA;         /* slot of the body whose rotation is applied, -1 = none */
+};
+
+struct CombineArgs
+{
+  const double* A;    /* n x nU x 12 */
+  const double* JT;   /* n x nU x 3 x nJ */
+  const double* JR;
+  double* out;        /* n x nTasks x 3 x nJ */
+  const CombineTask* tasks;
+  long n;
+  int nU, nTasks, nJ;
+};
+
+__global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
+{
+  const long total = a.n * a.nTasks * a.nJ;
+  const long perState = (long) a.nTasks * a.nJ;
+  for (long e = (long) blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long) gridDim.x * blockDim.x)
+  {
+    const long s = e / perState;
+    const int rem = (int) (e - s * perState);
+    const int t = rem / a.nJ, k = rem - t * a.nJ;
+    const CombineTask tk = a.tasks[t];
+    const long rec = 3L * a.nJ;
+    const double* JTs = a.JT + s * a.nU * rec;
+    const double* JRs = a.JR + s * a.nU * rec;
+    const double* As = a.A + s * a.nU * 12;
+
+    double v[3] = {0.0, 0.0, 0.0};
+    if (tk.kind == RCSB_JAC_POS)
+    {
+      if (tk.u2 >= 0)
+      {
+        const double* j2 = JTs + tk.u2 * rec + k;
+        v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
+      }
+      if (tk.mode == 1)
+      {
+        const double* j1 = JTs + tk.u1 * rec + k;
+        v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
+        if (tk.u3 >= 0)
+        {
+          const double* o1 = As + tk.u1 * 12;
+          double r[3] = {-o1[0], -o1[1], -o1[2]};
+          if (tk.u2 >= 0)
+          {
+            const double* o2 = As + tk.u2 * 12;
+            r[0] += o2[0]; r[1] += o2[1]; r[2] += o2[2];
+          }
+          const double* j3 = JRs + tk.u3 * rec + k;
+          const double w0 = j3[0], w1 = j3[a.nJ], w2 = j3[2 * a.nJ];
+          v[0] += r[1] * w2 - r[2] * w1;
+          v[1] += -r[0] * w2 + r[2] * w0;
+          v[2] += r[0] * w1 - r[1] * w0;
+        }
+      }
+    }
+    else
+    {
+      if (tk.u2 >= 0)
+      {
+        const double* j2 = JRs + tk.u2 * rec + k;
+        v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
+      }
+      if (tk.mode == 1 && tk.u1 >= 0)
+      {
+        const double* j1 = JRs + tk.u1 * rec + k;
+        v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
+      }
+    }
+    if (tk.uA >= 0)
+    {
+      const double* R = As + tk.uA * 12 + 3;
+      const double x = v[0], y = v[1], z = v[2];
+      v[0] = R[0] * x + R[1] * y + R[2] * z;
+      v[1] = R[3] * x + R[4] * y + R[5] * z;
+      v[2] = R[6] * x + R[7] * y + R[8] * z;
+    }
+    double* o = a.out + (s * a.nTasks + t) * rec + k;
+    o[0] = v[0];
+    o[a.nJ] = v[1];
+    o[2 * a.nJ] = v[2];
+  }
+}
+
+}   // namespace
+
+using namespace rcsbhost;
+
+extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const double* q, int nJac,
+                                   const RcsbRelJac* jac, double* J, unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  int rc = checkModel(m, N, qdim, q);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  if (nJac <= 0 || !jac || (N > 0 && !J))
+  {
+    rcsb_set_error("rcsb_task_jacobians: no tasks / no output");
+    return RCSB_EINVAL;
+  }
+  const int nb = m->hdr.nb, nJ = m->hdr.nJ;
+  const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
+  auto articulated = [&](int b) {   /* RcsBody_isArticulated, Rcs_body.c:688 */
+    for (int j = bodyLastJnt[b]; j >= 0; j = jntPrev[j])
+    {
+      if (jntJacobi[j] >= 0)
+      {
+        return true;
+      }
+    }
+    return false;
+  };
+
+  /* bodies involved -> slots of the pass buffers */
+  std::vector<int> slotOf((size_t) nb, -1), bodies;
+  auto slot = [&](int b) {
+    if (b < 0)
+    {
+      return -1;
+    }
+    if (slotOf[(size_t) b] < 0)
+    {
+      slotOf[(size_t) b] = (int) bodies.size();
+      bodies.push_back(b);
+    }
+    return slotOf[(size_t) b];
+  };
+  std::vector<CombineTask> tasks((size_t) nJac);
+  for (int t = 0; t < nJac; ++t)
+  {
+    const RcsbRelJac& r = jac[t];
+    if ((r.kind != RCSB_JAC_POS && r.kind != RCSB_JAC_OMEGA) || r.effector >= nb || r.refBdy >= nb ||
+        r.refFrame >= nb || r.effector < -1 || r.refBdy < -1 || r.refFrame < -1)
+    {
+      rcsb_set_error("rcsb_task_jacobians: task %d is invalid", t);
+      return RCSB_EINVAL;
+    }
+    CombineTask& c = tasks[(size_t) t];
+    c.kind = r.kind;
+    c.u2 = slot(r.effector);
+    c.u1 = c.u3 = c.uA = -1;
+    c.mode = 0;
+    if (r.kind == RCSB_JAC_POS)
+    {
+      if (r.refBdy < 0)
+      {
+        c.uA = slot(r.refFrame);
+      }
+      else
+      {
+        c.mode = 1;
+        c.u1 = slot(r.refBdy);
+        c.u3 = slot(r.refFrame);
+        c.uA = (r.refFrame >= 0 && r.refFrame != r.refBdy) ? slot(r.refFrame) : c.u1;
+      }
+    }
+    else
+    {
+      if (r.refBdy < 0 && r.refFrame < 0)
+      {
+        /* world */
+      }
+      else if (r.refBdy >= 0 && r.refFrame == r.refBdy && !articulated(r.refBdy))
+      {
+        c.uA = slot(r.refBdy);
+      }
+      else
+      {
+        c.mode = 1;
+        c.u1 = slot(r.refBdy);
+        c.uA = slot(r.refFrame);
+      }
+    }
+  }
+  if (N == 0)
+  {
+    return RCSB_OK;
+  }
+  if (bodies.empty())
+  {
+    bodies.push_back(0);   /* only NULL bodies: all rows are zero, keep the pass well-formed */
+  }
+  const int nU = (int) bodies.size();
+
+  const bool host = (flags & RCSB_HOST_PTRS) != 0;
+  cudaStream_t st = host ? nullptr : static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
+  RCSB_CUDA(cudaSetDevice(m->device));
+
+  const long chunk = N < 32768 ? N : 32768;
+  const size_t perState = (size_t) nU * (12 + 6 * (size_t) nJ);
+  const size_t tmpDoubles = (size_t) chunk * perState;
+  const size_t outDoubles = host ? (size_t) chunk * nJac * 3 * nJ : 0;
+  const size_t qDoubles = host ? (size_t) chunk * qdim : 0;
+  double* tmp = nullptr;
+  CombineTask* dTasks = nullptr;
+  RCSB_CUDA(cudaMalloc(&tmp, (tmpDoubles + outDoubles + qDoubles) * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dTasks, tasks.size() * sizeof(CombineTask));
+  if (e == cudaSuccess)
+  {
+    e = cudaMemcpyAsync(dTasks, tasks.data(), tasks.size() * sizeof(CombineTask),
+                        cudaMemcpyHostToDevice, st);
+  }
+  int result = RCSB_OK;
+  for (long s0 = 0; s0 < N && e == cudaSuccess && result == RCSB_OK; s0 += chunk)
+  {
+    const long n = N - s0 < chunk ? N - s0 : chunk;
+    double* A = tmp;
+    double* JT = A + (size_t) n * nU * 12;
+    double* JR = JT + (size_t) n * nU * 3 * nJ;
+    double* dOut = host ? tmp + tmpDoubles : J + (size_t) s0 * nJac * 3 * nJ;
+    const double* dQ = q + (size_t) s0 * qdim;
+    if (host)
+    {
+      double* dq = tmp + tmpDoubles + outDoubles;
+      e = cudaMemcpyAsync(dq, dQ, sizeof(double) * (size_t) n * qdim, cudaMemcpyHostToDevice, st);
+      dQ = dq;
+      if (e != cudaSuccess)
+      {
+        break;
+      }
+    }
+    result = fkCommon(m, n, qdim, dQ, nullptr, nU, bodies.data(), A, nullptr, nullptr, nullptr,
+                      nullptr, nU, bodies.data(), nullptr, JT, JR, nullptr, false, 0, st);
+    if (result != RCSB_OK)
+    {
+      break;
+    }
+    CombineArgs ca;
+    ca.A = A;
+    ca.JT = JT;
+    ca.JR = JR;
+    ca.out = dOut;
+    ca.tasks = dTasks;
+    ca.n = n;
+    ca.nU = nU;
+    ca.nTasks = nJac;
+    ca.nJ = nJ;
+    const long total = n * nJac * nJ;
+    long blocks = (total + 255) / 256;
+    const long cap = (long) m->smCount * 8;
+    blocks = blocks < cap ? blocks : cap;
+    combineKernel<<<(unsigned int) blocks, 256, 0, st>>>(ca);
+    e = cudaGetLastError();
+    g_launches.fetch_add(1);
+    if (e == cudaSuccess && host)
+    {
+      e = cudaMemcpyAsync(J + (size_t) s0 * nJac * 3 * nJ, dOut,
+                          sizeof(double) * (size_t) n * nJac * 3 * nJ, cudaMemcpyDeviceToHost, st);
+    }
+  }
+  /* the pass buffers are released once the stream has consumed them */
+  cudaError_t e2 = host ? cudaStreamSynchronize(st) : cudaSuccess;
+  if (!host)
+  {
+    cudaFreeAsync(tmp, st);
+    cudaFreeAsync(dTasks, st);
+  }
+  else
+  {
+    cudaFree(tmp);
+    cudaFree(dTasks);
+  }
+  if (result != RCSB_OK)
+  {
+    return result;
+  }
+  RCSB_CUDA(e);
+  RCSB_CUDA(e2);
+  return RCSB_OK;
+}

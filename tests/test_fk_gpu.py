@@ -120,3 +120,34 @@ def test_known_answers_wam_default_state(cuda_device):
         out["JR"][0, 0, 0],
         [0, -0.25881904510252074, 0.16773125949652062, -0.25881904510252074,
          0.95125124256419769, 0.25881904510252085, 0.95125124256419769], rtol=0, atol=1e-14)
+
+
+def _rel_spec(g, name):
+    n = g.body_names()
+    if name == "humanoid":
+        a, b, c = n.index("RightHandTip"), n.index("LeftHandTip"), n.index("UpperBody")
+        fixed = n.index("Heel")
+    else:
+        a, b, c = n.index("Hand"), n.index("Base"), n.index("PowerGrip")
+        fixed = 0
+    return [("POS", a, -1, -1), ("POS", a, -1, c), ("POS", a, b, b), ("POS", a, b, c), ("POS", a, c, -1),
+            ("POS", -1, b, c), ("OMEGA", a, -1, -1), ("OMEGA", a, b, b), ("OMEGA", a, b, c),
+            ("OMEGA", a, fixed, fixed), ("OMEGA", a, -1, c), ("OMEGA", a, b, -1)]
+
+
+@pytest.mark.parametrize("name", ["humanoid", "wam_scenario"])
+def test_relative_task_jacobians(name, refmod, cuda_device):
+    """RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian (Rcs_kinematics.c:566, :789): world,
+    rotated, relative to an articulated refBdy, with a separate refFrame, NULL effector."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    spec = _rel_spec(g, name)
+    q = workload.sample_states(g.layout(), 40000 if name == "wam_scenario" else 500, first=12)
+    ref = r.task_jacobians(q[:500], spec)
+    ours = m.task_jacobians(q, spec)
+    assert_close(ours[:500], ref, what=f"{name}: task Jacobians (host pointers)")
+    assert_structural_zeros(ours[:500], ref, what=f"{name}: task Jacobians")
+    dev = m.task_jacobians(torch.from_numpy(q).cuda(cuda_device), spec)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), ours)

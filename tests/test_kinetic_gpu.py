@@ -86,3 +86,19 @@ def test_ragged_batches(refmod, cuda_device):
         for k in ("M", "h", "Fg", "E"):
             assert_close(ours[k], ref[k], what=f"N={n}:{k}")
     assert m.kinetic_terms(np.empty((0, g.dof)))["M"].shape == (0, g.nJ, g.nJ)
+
+
+@pytest.mark.parametrize("name,n", [("wam_arm", 300), ("wam_scenario", 100), ("humanoid", 64), ("husky", 64)])
+def test_cog_and_cog_jacobian(name, n, refmod, cuda_device):
+    """RcsGraph_COG / RcsGraph_COGJacobian (Rcs_kinematics.c:904, :973) over a batch."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    q = workload.sample_states(g.layout(), n, first=77)
+    cog_ref, jcog_ref = r.cog(q)
+    ours = m.cog(q)
+    assert_close(ours["cog"], cog_ref, what=f"{name}:cog")
+    assert_close(ours["Jcog"], jcog_ref, what=f"{name}:Jcog")
+    assert_structural_zeros(ours["Jcog"], jcog_ref, what=f"{name}:Jcog")
+    dev = m.cog(torch.from_numpy(q).cuda(cuda_device), want=("Jcog",))
+    assert_close(dev["Jcog"].cpu().numpy(), jcog_ref, what=f"{name}:Jcog (device pointers)")

@@ -53,6 +53,14 @@ def _lib():
     L.RcsGraph_computeKineticTerms.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(MatNd)] * 3
     L.RcsGraph_computeKineticTerms.restype = ctypes.c_double
     L.MatNd_destroy.argtypes = [ctypes.POINTER(MatNd)]
+    L.RcsGraph_computeMassMatrix.argtypes = [ctypes.c_void_p, ctypes.POINTER(MatNd)]
+    L.RcsGraph_computeMassMatrix.restype = None
+    L.RcsGraph_computeGravityTorque.argtypes = [ctypes.c_void_p, ctypes.POINTER(MatNd)]
+    L.RcsGraph_computeGravityTorque.restype = None
+    L.RcsGraph_COG.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    L.RcsGraph_COG.restype = ctypes.c_double
+    L.RcsGraph_COGJacobian.argtypes = [ctypes.c_void_p, ctypes.POINTER(MatNd)]
+    L.RcsGraph_COGJacobian.restype = None
     return L
 
 
@@ -108,6 +116,17 @@ def test_reference_call_sequence_matches_golden(name, cuda_device):
         assert_close(_arr(h)[:, 0], z["kt_h"][s], what=f"{name}: h")
         assert_close(_arr(Fg)[:, 0], z["kt_Fg"][s], what=f"{name}: F_gravity")
         assert abs(E - z["kt_E"][s]) <= 1e-12 * max(1.0, abs(z["kt_E"][s]))
+        # reference invariants (bin/TestGraph.cpp:314-352): the separate entry points agree
+        L.RcsGraph_computeMassMatrix(g.handle, Mm)
+        assert_close(_arr(Mm), z["kt_M"][s], what=f"{name}: computeMassMatrix")
+        L.RcsGraph_computeGravityTorque(g.handle, Fg)
+        assert_close(_arr(Fg)[:, 0], z["kt_Fg"][s], tol=1e-11, what=f"{name}: computeGravityTorque")
+        r_cog = (ctypes.c_double * 3)()
+        mass = L.RcsGraph_COG(g.handle, r_cog)
+        assert abs(mass - g.mass()) < 1e-12 * max(1.0, mass)
+        assert_close(np.array(list(r_cog)), z["cog"][s], what=f"{name}: COG")
+        L.RcsGraph_COGJacobian(g.handle, J)
+        assert_close(_arr(J), z["Jcog"][s], what=f"{name}: COG Jacobian")
         L.MatNd_destroy(q)
         L.MatNd_destroy(qd)
     # NULL body = world frame: zero Jacobian (Rcs_kinematics.c:188-191)
@@ -151,3 +170,27 @@ def test_wrong_dimensions_are_reported(cuda_device):
     L.RcsGraph_setState.restype = ctypes.c_bool
     assert L.RcsGraph_setState(g.handle, bad, None) is False
     assert b"wrong dimensions" in L.rcsb_last_error()
+
+
+def test_relative_jacobian_wrappers(cuda_device, refmod):
+    """RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian with body pointers, as reference code
+    calls them (Rcs_kinematics.c:566, :789)."""
+    L = _lib()
+    for fn in (L.RcsGraph_3dPosJacobian, L.RcsGraph_3dOmegaJacobian):
+        fn.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(RcsBody)] * 3 + [ctypes.POINTER(MatNd)]
+        fn.restype = None
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    r = refmod.RefGraph(graph_file("humanoid"))
+    z = np.load(f"{ROOT}/tests/golden/humanoid.npz")
+    names = g.body_names()
+    a, b, c = names.index("RightHandTip"), names.index("LeftHandTip"), names.index("UpperBody")
+    ref = r.task_jacobians(z["q"][:1], [("POS", a, b, c), ("OMEGA", a, b, c), ("POS", a, -1, -1)])
+    L.RcsGraph_setState(g.handle, _mat(L, z["q"][0]), None)
+    body = lambda i: L.RcsGraph_getBodyByIndex(g.handle, i)   # noqa: E731
+    J = _mat(L, m=3, n=g.nJ)
+    L.RcsGraph_3dPosJacobian(g.handle, body(a), body(b), body(c), J)
+    assert_close(_arr(J), ref[0, 0], what="3dPosJacobian")
+    L.RcsGraph_3dOmegaJacobian(g.handle, body(a), body(b), body(c), J)
+    assert_close(_arr(J), ref[0, 1], what="3dOmegaJacobian")
+    L.RcsGraph_3dPosJacobian(g.handle, body(a), None, None, J)
+    assert_close(_arr(J), ref[0, 2], what="3dPosJacobian (world)")
