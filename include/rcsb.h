@@ -130,6 +130,16 @@ int rcsb_kinetic_terms(const RcsbModel* model, long N, int qdim, const double* q
                        unsigned flags, void* stream);
 
 /*
+ * Joint accelerations qdd [N x nJ] of Rcs_directDynamics (src/RcsCore/Rcs_dynamics.c:673):
+ * M qdd = F_gravity + F_ext - F_jnt + h, solved with the reference's Cholesky factorisation
+ * (src/RcsCore/Rcs_linAlg.c:66, :133) inside the assembly kernel: M never leaves the SM.
+ * Fext / Fjnt [N x nJ] may be NULL; E [N] optional. A failed factorisation gives zeros.
+ */
+int rcsb_direct_dynamics(const RcsbModel* model, long N, int qdim, const double* q,
+                         const double* qd, const double* Fext, const double* Fjnt, double* qdd,
+                         double* E, unsigned flags, void* stream);
+
+/*
  * Centre of gravity cog [N x 3] (RcsGraph_COG, src/RcsCore/Rcs_kinematics.c:904) and its
  * Jacobian Jcog [N x 3 x nJ] (RcsGraph_COGJacobian, :973); either may be NULL. Same kernels as
  * rcsb_kinetic_terms: column k of sum_b m_b JT_b is the linear momentum of column k's composite
@@ -194,6 +204,9 @@ void RcsGraph_3dOmegaJacobian(const RcsGraph* self, const RcsBody* effector, con
                               const RcsBody* refFrame, MatNd* J);
 /* src/RcsCore/Rcs_dynamics.c:439 */
 double RcsGraph_computeKineticTerms(const RcsGraph* self, MatNd* M, MatNd* h, MatNd* F_gravity);
+/* src/RcsCore/Rcs_dynamics.c:673; returns the energy like the reference */
+double Rcs_directDynamics(const RcsGraph* graph, const MatNd* F_ext, const MatNd* F_jnt,
+                          MatNd* q_ddot);
 /* src/RcsCore/Rcs_dynamics.c:610, :576 */
 void RcsGraph_computeMassMatrix(const RcsGraph* self, MatNd* M);
 void RcsGraph_computeGravityTorque(const RcsGraph* self, MatNd* T_gravity);

@@ -394,6 +394,43 @@ class Oracle:
         return dH, cost
 
     # ------------------------------------------------------------------------------------
+    # direct dynamics: Rcs_directDynamics (src/RcsCore/Rcs_dynamics.c:673-804) with
+    # MatNd_choleskySolve (src/RcsCore/Rcs_linAlg.c:133-187, factor :66-101)
+    # ------------------------------------------------------------------------------------
+    def direct_dynamics(self, q, qd, F_ext=None, F_jnt=None):
+        kt = self.kinetic_terms(q, qd)
+        b = kt["Fg"].copy()
+        if F_ext is not None:
+            b = b + F_ext
+        if F_jnt is not None:
+            b = b - F_jnt
+        b = b + kt["h"]
+        L = kt["M"].copy()
+        ns, n, _ = L.shape
+        fail = np.zeros(ns, dtype=bool)
+        for i in range(n):
+            for k in range(i + 1):
+                s = L[:, i, k] - np.einsum("nt,nt->n", L[:, i, :k], L[:, k, :k])
+                if i > k:
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        L[:, i, k] = s / L[:, k, k]
+                else:
+                    fail |= ~(s > 0.0)
+                    L[:, i, i] = np.sqrt(np.where(s > 0.0, s, 1.0))
+        x = np.zeros_like(b)
+        for i in range(n):
+            x[:, i] = b[:, i]
+            for j in range(i):
+                x[:, i] -= L[:, i, j] * x[:, j]
+            x[:, i] /= L[:, i, i]
+        for i in range(n - 1, -1, -1):
+            for j in range(i + 1, n):
+                x[:, i] -= L[:, j, i] * x[:, j]
+            x[:, i] /= L[:, i, i]
+        x[fail] = 0.0
+        return x, kt["E"]
+
+    # ------------------------------------------------------------------------------------
     # orientation helpers
     # ------------------------------------------------------------------------------------
     @staticmethod

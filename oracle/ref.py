@@ -55,6 +55,8 @@ def lib() -> ctypes.CDLL:
         L.ref_cog.argtypes = [vp, cl, ci, vp, vp, vp]
         L.ref_task_jacobians.restype = cd
         L.ref_task_jacobians.argtypes = [vp, cl, ci, vp, ci, vp, vp]
+        L.ref_direct_dynamics.restype = cd
+        L.ref_direct_dynamics.argtypes = [vp, cl, ci] + [vp] * 6
         L.ref_kinetic_terms.restype = cd
         L.ref_kinetic_terms.argtypes = [vp, cl, ci] + [vp] * 6
         L.ref_mass_matrix.restype = cd
@@ -203,6 +205,17 @@ class RefGraph:
             self._h, N, qdim, _p(q), _p(qd), _p(out.get("M")), _p(out.get("h")),
             _p(out.get("Fg")), _p(out.get("E")))
         return out
+
+    # Rcs_directDynamics (Rcs_dynamics.c:673)
+    def direct_dynamics(self, q, qd, F_ext=None, F_jnt=None):
+        q, qd = _c(q), _c(qd)
+        N, qdim = q.shape
+        fe = None if F_ext is None else _c(F_ext)
+        fj = None if F_jnt is None else _c(F_jnt)
+        qdd, E = np.empty((N, self.nJ)), np.empty((N,))
+        self.last_seconds = lib().ref_direct_dynamics(self._h, N, qdim, _p(q), _p(qd), _p(fe), _p(fj),
+                                                      _p(qdd), _p(E))
+        return qdd, E
 
     def mass_matrix(self, q):
         q = _c(q)

@@ -521,6 +521,48 @@ double ref_kinetic_terms(void* g, long N, int qdim, const double* q, const doubl
   });
 }
 
+/* Joint accelerations through Rcs_directDynamics (Rcs_dynamics.c:673): M qdd = F_g + F_ext -
+ * F_jnt + h. Fext, Fjnt: N x nJ or NULL; qdd: N x nJ; E: N or NULL. */
+double ref_direct_dynamics(void* g, long N, int qdim, const double* q, const double* qd,
+                           const double* Fext, const double* Fjnt, double* qdd, double* E)
+{
+  RcsGraph* master = (RcsGraph*) g;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    RcsGraph* graph = RcsGraph_clone(master);
+    const unsigned int dof = graph->dof, nJ = graph->nJ;
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* qdv = MatNd_create(dof, 1);
+    MatNd* fe = MatNd_create(nJ, 1);
+    MatNd* fj = MatNd_create(nJ, 1);
+    MatNd* acc = MatNd_create(nJ, 1);
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
+      if (Fext)
+      {
+        memcpy(fe->ele, Fext + (size_t) i * nJ, sizeof(double) * nJ);
+      }
+      if (Fjnt)
+      {
+        memcpy(fj->ele, Fjnt + (size_t) i * nJ, sizeof(double) * nJ);
+      }
+      double e = Rcs_directDynamics(graph, Fext ? fe : NULL, Fjnt ? fj : NULL, acc);
+      memcpy(qdd + (size_t) i * nJ, acc->ele, sizeof(double) * nJ);
+      if (E)
+      {
+        E[i] = e;
+      }
+    }
+    MatNd_destroy(qv);
+    MatNd_destroy(qdv);
+    MatNd_destroy(fe);
+    MatNd_destroy(fj);
+    MatNd_destroy(acc);
+    RcsGraph_destroy(graph);
+  });
+}
+
 /* Mass matrix through RcsGraph_computeMassMatrix. */
 double ref_mass_matrix(void* g, long N, int qdim, const double* q, double* M)
 {

@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
         c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_task_jacobians", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
         ctypes.c_uint, c_void)
+    sig("rcsb_direct_dynamics", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+        c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_cog", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
@@ -403,6 +405,22 @@ class Model:
             a.flags(), a.stream(),
         )
         _err(rc, "rcsb_kinetic_terms")
+        return out
+
+    def direct_dynamics(self, q, qd, F_ext=None, F_jnt=None, want=("qdd", "E"), out=None):
+        """Rcs_directDynamics over a batch: M qdd = F_gravity + F_ext - F_jnt + h."""
+        N, qdim = self._batch(q)
+        shapes = {"qdd": (N, self.nJ), "E": (N,)}
+        out = dict(out or {})
+        for k in set(want) | {"qdd"}:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        a = _Args(self)
+        rc = lib().rcsb_direct_dynamics(
+            self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), a.ptr(F_ext, "F_ext"),
+            a.ptr(F_jnt, "F_jnt"), a.ptr(out["qdd"], "qdd"), a.ptr(out.get("E"), "E"), a.flags(),
+            a.stream())
+        _err(rc, "rcsb_direct_dynamics")
         return out
 
     def cog(self, q, want=("cog", "Jcog"), out=None):

@@ -129,7 +129,8 @@ int buildKtPlan(RcsbModel* m)
   const int asmV = 16 * nJ;
   const int asmRuns = 16 * nJ + 8;
   const int runArea = RCSB_KT_LINK_REC * nRuns > nJ * nJ ? RCSB_KT_LINK_REC * nRuns : nJ * nJ;
-  const int asmDoubles = asmRuns + runArea;
+  const int asmRhs = asmRuns + ((runArea + 3) & ~3);
+  const int asmDoubles = asmRhs + nJ;
   const int recDoubles = (rec + 5 + 3) & ~3;
   std::vector<unsigned short> recDst((size_t) recDoubles, (unsigned short) (asmV + 7));
   for (int k = 0; k < nJ; ++k)
@@ -203,6 +204,7 @@ int buildKtPlan(RcsbModel* m)
   ph.asmV = asmV;
   ph.asmRuns = asmRuns;
   ph.asmDoubles = asmDoubles;
+  ph.asmRhs = asmRhs;
   ph.nExtraRuns = (int) extraRuns.size() / 2;
   int off = align16((int) sizeof(ph));
   auto place = [&](int& field, size_t bytes) {
@@ -275,9 +277,20 @@ long ktChunk(const RcsbModel* m, int recDoubles)
   return (chunk + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS * RCSB_KT_WALK_THREADS;
 }
 
-int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
-             double* h, double* Fg, double* E, double* cog, double* Jcog, cudaStream_t stream, int ws)
+struct KtExtra
 {
+  double* cog = nullptr;
+  double* Jcog = nullptr;
+  const double* Fext = nullptr;
+  const double* Fjnt = nullptr;
+  double* qdd = nullptr;
+};
+
+int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
+             double* h, double* Fg, double* E, const KtExtra& x, cudaStream_t stream, int ws)
+{
+  double* cog = x.cog;
+  double* Jcog = x.Jcog;
   const int recDoubles = m->ktPlan.aux0;
   const long chunk = ktChunk(m, recDoubles) < N ? ktChunk(m, recDoubles) : N;
   const size_t need = (size_t) chunk * (size_t) recDoubles;
@@ -318,6 +331,9 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     a.E = E ? E + s0 : nullptr;
     a.cog = cog ? cog + s0 * 3 : nullptr;
     a.Jcog = Jcog ? Jcog + s0 * 3 * nJ : nullptr;
+    a.Fext = x.Fext ? x.Fext + s0 * nJ : nullptr;
+    a.Fjnt = x.Fjnt ? x.Fjnt + s0 * nJ : nullptr;
+    a.qdd = x.qdd ? x.qdd + s0 * nJ : nullptr;
     a.rec = m->ktScratch[ws];
     a.recDoubles = recDoubles;
     RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, m->ktPlan.aux1, m->smCount, stream));
@@ -329,8 +345,8 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
 }   // namespace
 
 static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
-                    double* M, double* h, double* Fg, double* E, double* cog, double* Jcog,
-                    unsigned flags, void* stream)
+                    double* M, double* h, double* Fg, double* E, const KtExtra& x, unsigned flags,
+                    void* stream)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   int rc = checkModel(m, N, qdim, q);
@@ -348,24 +364,33 @@ static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
   {
     /* the record buffer is shared: device-pointer calls on one model must use one stream at a
      * time (documented in rcsb.h) */
-    return ktDevice(m, N, qdim, q, qd, M, h, Fg, E, cog, Jcog, static_cast<cudaStream_t>(stream), 0);
+    return ktDevice(m, N, qdim, q, qd, M, h, Fg, E, x, static_cast<cudaStream_t>(stream), 0);
   }
 
   const size_t nJ = (size_t) m->hdr.nJ;
   std::vector<StagedArray> arr;
-  enum { I_Q, I_QD, I_M, I_H, I_G, I_E, I_C, I_JC };
+  enum { I_Q, I_QD, I_M, I_H, I_G, I_E, I_C, I_JC, I_FE, I_FJ, I_QDD };
   arr.push_back({q, nullptr, (size_t) qdim, nullptr});
   arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
   arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
   arr.push_back({nullptr, h, h ? nJ : 0, nullptr});
   arr.push_back({nullptr, Fg, Fg ? nJ : 0, nullptr});
   arr.push_back({nullptr, E, (size_t) (E ? 1 : 0), nullptr});
-  arr.push_back({nullptr, cog, (size_t) (cog ? 3 : 0), nullptr});
-  arr.push_back({nullptr, Jcog, Jcog ? 3 * nJ : 0, nullptr});
+  arr.push_back({nullptr, x.cog, (size_t) (x.cog ? 3 : 0), nullptr});
+  arr.push_back({nullptr, x.Jcog, x.Jcog ? 3 * nJ : 0, nullptr});
+  arr.push_back({x.Fext, nullptr, x.Fext ? nJ : 0, nullptr});
+  arr.push_back({x.Fjnt, nullptr, x.Fjnt ? nJ : 0, nullptr});
+  arr.push_back({nullptr, x.qdd, x.qdd ? nJ : 0, nullptr});
   return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int slot) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    KtExtra d;
+    d.cog = dv(I_C, x.cog);
+    d.Jcog = dv(I_JC, x.Jcog);
+    d.Fext = dv(I_FE, x.Fext);
+    d.Fjnt = dv(I_FJ, x.Fjnt);
+    d.qdd = dv(I_QDD, x.qdd);
     return ktDevice(m, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_M, M), dv(I_H, h), dv(I_G, Fg),
-                    dv(I_E, E), dv(I_C, cog), dv(I_JC, Jcog), st, slot);
+                    dv(I_E, E), d, st, slot);
   });
 }
 
@@ -373,14 +398,32 @@ extern "C" int rcsb_kinetic_terms(const RcsbModel* cm, long N, int qdim, const d
                                   const double* qd, double* M, double* h, double* Fg, double* E,
                                   unsigned flags, void* stream)
 {
-  return ktCommon(cm, N, qdim, q, qd, M, h, Fg, E, nullptr, nullptr, flags, stream);
+  return ktCommon(cm, N, qdim, q, qd, M, h, Fg, E, KtExtra(), flags, stream);
 }
 
 extern "C" int rcsb_cog(const RcsbModel* cm, long N, int qdim, const double* q, double* cog,
                         double* Jcog, unsigned flags, void* stream)
 {
-  return ktCommon(cm, N, qdim, q, nullptr, nullptr, nullptr, nullptr, nullptr, cog, Jcog, flags,
-                  stream);
+  KtExtra x;
+  x.cog = cog;
+  x.Jcog = Jcog;
+  return ktCommon(cm, N, qdim, q, nullptr, nullptr, nullptr, nullptr, nullptr, x, flags, stream);
+}
+
+extern "C" int rcsb_direct_dynamics(const RcsbModel* cm, long N, int qdim, const double* q,
+                                    const double* qd, const double* Fext, const double* Fjnt,
+                                    double* qdd, double* E, unsigned flags, void* stream)
+{
+  if (N > 0 && !qdd)
+  {
+    rcsb_set_error("rcsb_direct_dynamics: qdd is NULL");
+    return RCSB_EINVAL;
+  }
+  KtExtra x;
+  x.Fext = Fext;
+  x.Fjnt = Fjnt;
+  x.qdd = qdd;
+  return ktCommon(cm, N, qdim, q, qd, nullptr, nullptr, nullptr, E, x, flags, stream);
 }
 
 /* ------------------------------------------------------------------------------------------ */

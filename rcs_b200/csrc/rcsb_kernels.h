@@ -50,6 +50,9 @@ struct KtArgs
   double* h;
   double* Fg;
   double* E;
+  const double* Fext;  /* N x nJ external / joint forces of the direct dynamics, or NULL */
+  const double* Fjnt;
+  double* qdd;         /* N x nJ joint accelerations (Rcs_directDynamics), or NULL */
   double* cog;         /* N x 3 centre of gravity (RcsGraph_COG) */
   double* Jcog;        /* N x 3 x nJ (RcsGraph_COGJacobian) */
   double* rec;         /* N x recDoubles per-state records (walk -> assembly) */

@@ -612,6 +612,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   double* buf = sBuf + (long) grp * groupStride;   /* layout: RcsbKtPlanHeader, asm* fields */
   double* fb = buf + 7 * nJ;                       /* 9 per column: p, L, L with I^T */
   double* Ms = buf + p.hdr->asmRuns;               /* nJ x nJ, over the consumed runs */
+  double* rhs = buf + p.hdr->asmRhs;               /* nJ: right-hand side of the direct dynamics */
   const double grav = 9.81;
 
   /* The record of the group's next state is fetched into registers while the current state is
@@ -731,30 +732,46 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       f[3] = Lv[0]; f[4] = Lv[1]; f[5] = Lv[2];
       f[6] = Lt[0]; f[7] = Lt[1]; f[8] = Lt[2];
 
-      if (a.h && valid)
+      double hval = 0.0, gval = 0.0;
+      if ((a.h || a.qdd) && VEL)
       {
-        double hval = 0.0;
-        if (VEL)
-        {
-          hval = -pairing(isRot, ax, o, cp + 13, cp + 16);
-        }
-        a.h[s * nJ + k] = hval;
+        hval = -pairing(isRot, ax, o, cp + 13, cp + 16);
       }
-      if (a.Fg && valid)
+      if (a.Fg || a.qdd)
       {
-        double g;
         if (isRot)
         {
           /* a . ((h - m o) x (0, 0, -g)) */
           const double hr0 = hC[0] - mC * o[0];
           const double hr1 = hC[1] - mC * o[1];
-          g = ax[0] * (hr1 * -grav) + ax[1] * (hr0 * grav);
+          gval = ax[0] * (hr1 * -grav) + ax[1] * (hr0 * grav);
         }
         else
         {
-          g = ax[2] * (mC * -grav);
+          gval = ax[2] * (mC * -grav);
         }
-        a.Fg[s * nJ + k] = g;
+      }
+      if (a.h && valid)
+      {
+        a.h[s * nJ + k] = hval;
+      }
+      if (a.Fg && valid)
+      {
+        a.Fg[s * nJ + k] = gval;
+      }
+      if (a.qdd)
+      {
+        /* b = F_gravity + F_ext - F_jnt + h, in this order (Rcs_dynamics.c:718-731) */
+        double b = gval;
+        if (a.Fext)
+        {
+          b += a.Fext[sc * nJ + k];
+        }
+        if (a.Fjnt)
+        {
+          b -= a.Fjnt[sc * nJ + k];
+        }
+        rhs[k] = b + hval;
       }
     }
     __syncwarp();
@@ -800,9 +817,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
      * inertia. Staged in shared memory (over the consumed runs), rows leave as coalesced
      * stores. */
     double tk = 0.0;
-    if (a.M || (a.E && VEL))
+    const bool wantM = a.M || a.qdd;
+    if (wantM || (a.E && VEL))
     {
-      if (a.M)
+      if (wantM)
       {
         for (int e = gl; e < nJ * nJ; e += LPS)
         {
@@ -829,7 +847,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
           const double Lkt[3] = {fk[6], fk[7], fk[8]};
           lower = pairing(iRot, ai, oi, pk, Lkt);
         }
-        if (a.M)
+        if (wantM)
         {
           Ms[pr.z & 0xffff] = upper;
           Ms[pr.z >> 16] = lower;
@@ -840,16 +858,94 @@ ktAssembleKernel(const KtArgs a, int groupStride)
           tk += diag ? qq * upper : qq * (upper + lower);
         }
       }
-      if (a.M)
+      if (wantM)
       {
         __syncwarp();
-        if (valid)
+      }
+      if (a.M && valid)
+      {
+        double* dst = a.M + s * nJ * nJ;
+        for (int e = gl; e < nJ * nJ; e += LPS)
         {
-          double* dst = a.M + s * nJ * nJ;
-          for (int e = gl; e < nJ * nJ; e += LPS)
+          dst[e] = Ms[e];
+        }
+      }
+    }
+
+    /* ---- direct dynamics: M qdd = b by the reference's Cholesky solve, in shared memory ----
+     * (Rcs_directDynamics, Rcs_dynamics.c:673; MatNd_choleskySolve, Rcs_linAlg.c:133; factor
+     * :66-101). Column-oriented evaluation of the same sums: for column k every lane owns a
+     * row i > k and forms A[i][k] - sum_{t<k} L[i][t] L[k][t] in the reference's order. */
+    if (a.qdd)
+    {
+      __syncwarp();
+      bool ok = true;
+      for (int k = 0; k < nJ && ok; ++k)
+      {
+        /* diagonal (every lane computes it: no broadcast needed) */
+        double d = 0.0;
+        for (int t = 0; t < k; ++t)
+        {
+          const double l = Ms[k * nJ + t];
+          d += l * l;
+        }
+        const double piv = Ms[k * nJ + k] - d;
+        ok = piv > 0.0;
+        const double lkk = sqrt(ok ? piv : 1.0);
+        __syncwarp();
+        if (gl == 0)
+        {
+          Ms[k * nJ + k] = lkk;
+        }
+        for (int i = k + 1 + gl; i < nJ; i += LPS)
+        {
+          double dot = 0.0;
+          for (int t = 0; t < k; ++t)
           {
-            dst[e] = Ms[e];
+            dot += Ms[i * nJ + t] * Ms[k * nJ + t];
           }
+          Ms[i * nJ + k] = (Ms[i * nJ + k] - dot) / lkk;
+        }
+        __syncwarp();
+      }
+      if (ok)
+      {
+        /* forward solve L z = b, backward solve L^T x = z (lane 0 holds the running
+         * element; the other lanes update the rows below / above) */
+        for (int i = 0; i < nJ; ++i)
+        {
+          const double xi = rhs[i] / Ms[i * nJ + i];
+          __syncwarp();
+          if (gl == 0)
+          {
+            rhs[i] = xi;
+          }
+          for (int r = i + 1 + gl; r < nJ; r += LPS)
+          {
+            rhs[r] -= Ms[r * nJ + i] * xi;
+          }
+          __syncwarp();
+        }
+        for (int i = nJ - 1; i >= 0; --i)
+        {
+          const double xi = rhs[i] / Ms[i * nJ + i];
+          __syncwarp();
+          if (gl == 0)
+          {
+            rhs[i] = xi;
+          }
+          for (int r = gl; r < i; r += LPS)
+          {
+            rhs[r] -= Ms[i * nJ + r] * xi;
+          }
+          __syncwarp();
+        }
+      }
+      if (valid)
+      {
+        for (int k = gl; k < nJ; k += LPS)
+        {
+          a.qdd[s * nJ + k] = ok ? rhs[k] : 0.0;   /* failed factorisation: zeros, as the reference */
         }
       }
     }

@@ -100,6 +100,7 @@ typedef struct
    *   [asmRuns, ...)       run r at asmRuns + 19 r; the first run of a link becomes the link's
    *                        composite in place; later the same area holds the nJ x nJ matrix */
   int asmV, asmRuns, asmDoubles;
+  int asmRhs;           /* nJ doubles: right-hand side / solution of the direct dynamics */
   int nExtraRuns;       /* runs that are not the first of their link */
   int offRecDst;        /* unsigned short[recDoubles]: where each record element goes */
   int offLinkHome;      /* int[nLinks]: shared-memory offset of the link's composite */

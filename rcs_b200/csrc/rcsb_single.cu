@@ -5,6 +5,7 @@
  *   RcsGraph_bodyPointJacobian         src/RcsCore/Rcs_kinematics.c:200
  *   RcsGraph_rotationJacobian          src/RcsCore/Rcs_kinematics.c:416
  *   RcsGraph_computeKineticTerms       src/RcsCore/Rcs_dynamics.c:439
+ *   Rcs_directDynamics                 src/RcsCore/Rcs_dynamics.c:673
  *   RcsGraph_computeMassMatrix         src/RcsCore/Rcs_dynamics.c:610
  *   RcsGraph_computeGravityTorque      src/RcsCore/Rcs_dynamics.c:576
  *   RcsGraph_COG / RcsGraph_COGJacobian   src/RcsCore/Rcs_kinematics.c:904, :973
@@ -477,4 +478,29 @@ extern "C" void RcsGraph_3dOmegaJacobian(const RcsGraph* self, const RcsBody* ef
                                          const RcsBody* refBdy, const RcsBody* refFrame, MatNd* J)
 {
   relJacobian(self, RCSB_JAC_OMEGA, effector, refBdy, refFrame, J, "RcsGraph_3dOmegaJacobian");
+}
+
+extern "C" double Rcs_directDynamics(const RcsGraph* cgraph, const MatNd* F_ext, const MatNd* F_jnt,
+                                     MatNd* q_ddot)
+{
+  RcsGraph* self = const_cast<RcsGraph*>(cgraph);
+  GraphCache* c = (self && q_ddot) ? cacheOf(self) : nullptr;
+  const unsigned int n = self ? self->nJ : 0;
+  if (!c || q_ddot->size < n || (F_ext && (F_ext->m != n || F_ext->n != 1)) ||
+      (F_jnt && (F_jnt->m != n || F_jnt->n != 1)))
+  {
+    RCSB_FATAL("Rcs_directDynamics: %s", c ? "F_ext / F_jnt / q_ddot must be nJ x 1" : rcsb_last_error());
+    return 0.0;
+  }
+  MatNd_reshapeAndSetZero(q_ddot, n, 1);
+  double E = 0.0;
+  if (rcsb_direct_dynamics(c->model, 1, (int) self->dof, c->q.data(),
+                           c->haveVel ? c->qd.data() : self->q_dot->ele, F_ext ? F_ext->ele : nullptr,
+                           F_jnt ? F_jnt->ele : nullptr, q_ddot->ele, &E, RCSB_HOST_PTRS,
+                           nullptr) != RCSB_OK)
+  {
+    RCSB_FATAL("Rcs_directDynamics: %s", rcsb_last_error());
+    return 0.0;
+  }
+  return E;
 }

@@ -102,3 +102,35 @@ def test_cog_and_cog_jacobian(name, n, refmod, cuda_device):
     assert_structural_zeros(ours["Jcog"], jcog_ref, what=f"{name}:Jcog")
     dev = m.cog(torch.from_numpy(q).cuda(cuda_device), want=("Jcog",))
     assert_close(dev["Jcog"].cpu().numpy(), jcog_ref, what=f"{name}:Jcog (device pointers)")
+
+
+@pytest.mark.parametrize("name,n", [("wam_arm", 2000), ("wam_scenario", 300), ("humanoid", 200), ("husky", 100)])
+def test_direct_dynamics(name, n, refmod, cuda_device):
+    """Rcs_directDynamics (Rcs_dynamics.c:673): M qdd = F_gravity + F_ext - F_jnt + h. The solve
+    goes through M^-1, so the bar is scaled by the condition number of M per state:
+    |ours - ref|_inf <= 1e-12 max(1, cond(M) / 100) max(1, |ref|_inf)."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    q, qd = workload.sample_states(g.layout(), n, first=31, with_velocity=True)
+    rng = np.random.default_rng(8)
+    fe, fj = rng.normal(size=(n, g.nJ)), rng.normal(size=(n, g.nJ))
+    ref_qdd, ref_E = r.direct_dynamics(q, qd, fe, fj)
+    ours = m.direct_dynamics(q, qd, fe, fj)
+    cond = np.linalg.cond(r.kinetic_terms(q, qd, want=("M",))["M"])
+    err = np.abs(ours["qdd"] - ref_qdd).max(axis=1)
+    tol = 1e-12 * np.maximum(1.0, cond / 100.0) * np.maximum(1.0, np.abs(ref_qdd).max(axis=1))
+    assert np.all(np.isfinite(ours["qdd"]))
+    assert np.all(err <= tol), f"{name}: worst err/tol {float((err / tol).max()):.2f}"
+    assert_close(ours["E"], ref_E, what=f"{name}: E")
+    # residual check that needs no oracle: M qdd = b
+    kt = m.kinetic_terms(q, qd)
+    b = kt["Fg"] + fe - fj + kt["h"]
+    res = np.einsum("nij,nj->ni", np.tril(kt["M"]) + np.tril(kt["M"], -1).transpose(0, 2, 1), ours["qdd"]) - b
+    assert np.all(np.abs(res).max(axis=1) <= 1e-9 * np.maximum(1.0, np.abs(b).max(axis=1)))
+    # device pointers, no external forces
+    dev = m.direct_dynamics(torch.from_numpy(q).cuda(cuda_device), torch.from_numpy(qd).cuda(cuda_device))
+    ref0, _ = r.direct_dynamics(q, qd)
+    err0 = np.abs(dev["qdd"].cpu().numpy() - ref0).max(axis=1)
+    tol0 = 1e-12 * np.maximum(1.0, cond / 100.0) * np.maximum(1.0, np.abs(ref0).max(axis=1))
+    assert np.all(err0 <= tol0)

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--states", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--dynamics", action="store_true",
+                    help="time rcsb_direct_dynamics (qdd, E; M stays on the SM) instead")
     args = ap.parse_args()
 
     g = rcs_b200.Graph(os.path.join(ROOT, "tests", "golden", "graphs", args.graph + ".xml"))
@@ -37,19 +39,29 @@ def main():
         "Fg": torch.empty((n, g.nJ), dtype=torch.float64, device="cuda"),
         "E": torch.empty((n,), dtype=torch.float64, device="cuda"),
     }
+    if args.dynamics:
+        out = {"qdd": torch.empty((n, g.nJ), dtype=torch.float64, device="cuda"), "E": out["E"]}
+
+        def call():
+            m.direct_dynamics(dq, dqd, out=out)
+    else:
+        def call():
+            m.kinetic_terms(dq, dqd, out=out)
     for _ in range(args.warmup):
-        m.kinetic_terms(dq, dqd, out=out)
+        call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        m.kinetic_terms(dq, dqd, out=out)
+        call()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     bytes_per_state = 2 * g.dof * 8 + (g.nJ * g.nJ + 2 * g.nJ + 1) * 8
+    if args.dynamics:
+        bytes_per_state = 2 * g.dof * 8 + (g.nJ + 1) * 8
     print(json.dumps({
-        "workload": f"{args.graph} kinetic terms M,h,Fg,E", "states": n, "ms": ms,
+        "workload": f"{args.graph} " + ("direct dynamics qdd,E" if args.dynamics else "kinetic terms M,h,Fg,E"), "states": n, "ms": ms,
         "states_per_s": n / (ms * 1e-3), "bytes_per_state": bytes_per_state,
         "GBps": bytes_per_state * n / (ms * 1e-3) / 1e9,
         "blocks_per_sm": os.environ.get("RCSB_KT_BLOCKS_PER_SM", "auto")}))
