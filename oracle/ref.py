@@ -242,9 +242,10 @@ class RefIk:
     """ControllerBase + IkSolverRMR of the reference with XYZ / ABC tasks, all active."""
 
     def __init__(self, graph_file: str, tasks: Sequence):
-        """tasks: sequence of ("XYZ" | "ABC", effector body name)."""
+        """tasks: sequence of (controlVariable, effector body name[, refBdy name[, refFrame name]]);
+        any controlVariable of the reference's TaskFactory (XYZ, ABC, XYZABC, COGX, ...)."""
         L = lib()
-        spec = ";".join(f"{k}:{e}" for k, e in tasks)
+        spec = ";".join(":".join(str(x) for x in t) for t in tasks)
         self._h = L.ref_ik_create(graph_file.encode(), spec.encode())
         if not self._h:
             raise RuntimeError("reference controller creation failed")

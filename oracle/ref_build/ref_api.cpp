@@ -639,11 +639,32 @@ void* ref_ik_create(const char* graphFile, const char* taskSpec)
       end = spec.size();
     }
     std::string item = spec.substr(pos, end - pos);
-    size_t c = item.find(':');
-    if (c != std::string::npos)
+    /* kind:effector[:refBdy[:refFrame]] */
+    std::vector<std::string> f;
+    size_t a = 0;
+    while (a <= item.size())
     {
-      x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << item.substr(0, c)
-        << "\" effector=\"" << item.substr(c + 1) << "\" active=\"true\"/>";
+      size_t b = item.find(':', a);
+      if (b == std::string::npos)
+      {
+        b = item.size();
+      }
+      f.push_back(item.substr(a, b - a));
+      a = b + 1;
+    }
+    if (f.size() >= 2)
+    {
+      x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << f[0] << "\" effector=\"" << f[1]
+        << "\"";
+      if (f.size() >= 3 && !f[2].empty())
+      {
+        x << " refBdy=\"" << f[2] << "\"";
+      }
+      if (f.size() >= 4 && !f[3].empty())
+      {
+        x << " refFrame=\"" << f[3] << "\"";
+      }
+      x << " active=\"true\"/>";
     }
     pos = end + 1;
   }

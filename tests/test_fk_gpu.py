@@ -151,3 +151,26 @@ def test_relative_task_jacobians(name, refmod, cuda_device):
     dev = m.task_jacobians(torch.from_numpy(q).cuda(cuda_device), spec)
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy(), ours)
+
+
+def test_whole_body_task_stack_matches_controller(refmod, cuda_device):
+    """BASELINE.json configs[4] shape: the active task set of the reference's
+    GenericHumanoid/cAction.xml (hand positions, COG x/y, both feet as 6-D poses relative to the
+    Heel: nx = 20) stacked from rcsb_task_jacobians + rcsb_cog, against the reference's own
+    ControllerBase::computeJ (ControllerBase.cpp:776) with its task classes."""
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    m = rcs_b200.Model(g, cuda_device)
+    tasks = [("XYZ", "RightHandTip"), ("XYZ", "LeftHandTip"), ("COGX", "Heel"), ("COGY", "Heel"),
+             ("XYZABC", "FootL", "Heel"), ("XYZABC", "FootR", "Heel")]
+    ctrl = refmod.RefIk(graph_file("humanoid"), tasks)
+    assert ctrl.nx == 20
+    q = workload.sample_states(g.layout(), 700, first=5)
+    _, J_ref = ctrl.task_kinematics(q)
+    rh, lh, heel, fl, fr = [g.body_index(n) for n in ("RightHandTip", "LeftHandTip", "Heel", "FootL", "FootR")]
+    Jt = m.task_jacobians(q, [("POS", rh, -1, -1), ("POS", lh, -1, -1), ("POS", fl, heel, heel),
+                              ("OMEGA", fl, heel, heel), ("POS", fr, heel, heel), ("OMEGA", fr, heel, heel)])
+    Jc = m.cog(q, want=("Jcog",))["Jcog"]
+    J = np.concatenate([Jt[:, 0], Jt[:, 1], Jc[:, 0:1], Jc[:, 1:2], Jt[:, 2], Jt[:, 3], Jt[:, 4], Jt[:, 5]],
+                       axis=1)
+    assert_close(J, J_ref, what="stacked task Jacobian (20 x 34)")
+    assert_structural_zeros(J, J_ref, what="stacked task Jacobian")
