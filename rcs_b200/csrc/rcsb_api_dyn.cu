@@ -461,14 +461,49 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   const int* jntCpl = m->iarr(RCSB_A_JNT_CPL);
   const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
 
-  /* RcsGraph_countCoupledJoints (Rcs_graph.c:2804): slaves that are not constrained */
-  for (int j = 0; j < dof; ++j)
+  /* RcsGraph_countCoupledJoints (Rcs_graph.c:2804): slaves that are not constrained. They put
+   * the solver into the reduced joint space of RcsGraph_coupledJointMatrix (Rcs_graph.c:2823). */
+  const RcsbCoupling* cpl = reinterpret_cast<const RcsbCoupling*>(m->host.data() + m->hdr.off[RCSB_A_CPL]);
+  std::vector<int> colRed((size_t) (nJ > 0 ? nJ : 1), 0), colCpl((size_t) (nJ > 0 ? nJ : 1), -1);
+  int nqr = 0;
   {
-    if (jntCpl[j] >= 0 && jntJacobi[j] >= 0)
+    std::vector<int> redOfCol((size_t) (nJ > 0 ? nJ : 1), -1);
+    for (int j = 0; j < dof; ++j)
     {
-      rcsb_set_error("rcsb_ik_rmr: graphs with kinematically coupled joints are not supported "
-                     "(coupled-joint projection of IkSolverRMR.cpp:424-443)");
-      return RCSB_EUNSUPPORTED;
+      if (jntJacobi[j] >= 0 && jntCpl[j] < 0)
+      {
+        redOfCol[jntJacobi[j]] = 0;   /* free or master column */
+      }
+    }
+    for (int c = 0; c < nJ; ++c)
+    {
+      if (redOfCol[c] == 0)
+      {
+        redOfCol[c] = nqr++;
+      }
+    }
+    for (int j = 0; j < dof; ++j)
+    {
+      const int c = jntJacobi[j];
+      if (c < 0)
+      {
+        continue;
+      }
+      if (jntCpl[j] < 0)
+      {
+        colRed[c] = redOfCol[c];
+      }
+      else
+      {
+        const int mc = jntJacobi[cpl[jntCpl[j]].master];
+        if (mc < 0 || redOfCol[mc] < 0)
+        {
+          rcsb_set_error("rcsb_ik_rmr: slave joint %d is coupled to a constrained or slave joint", j);
+          return RCSB_EUNSUPPORTED;
+        }
+        colRed[c] = redOfCol[mc];
+        colCpl[c] = jntCpl[j];
+      }
     }
   }
 
@@ -588,9 +623,9 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
       }
       progStart.push_back((int) prog.size() / 4);
       chainNc = (int) chainJoint.size();
-      if (chainNc < 1 || chainNc > 8)
+      if (chainNc < 1 || chainNc > 8 || m->hdr.nCpl > 0)
       {
-        chainNc = 0;
+        chainNc = 0;   /* long chains and graphs with coupled joints take the general kernel */
       }
     }
     if (chainNc > 0)
@@ -634,6 +669,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   ph.nTasks = nTasks;
   ph.nx = 3 * nTasks;
   ph.nJ = nJ;
+  ph.nqr = nqr;
   ph.chainNc = chainNc;
   ph.nOther = (int) otherJoint.size();
   int off = align16((int) sizeof(ph));
@@ -653,6 +689,8 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   place(ph.offJlGain, jlGain.size() * 8);
   place(ph.offQ0, q0c.size() * 8);
   auto atLeast1 = [](size_t n) { return n > 0 ? n : (size_t) 1; };
+  place(ph.offColRed, colRed.size() * 4);
+  place(ph.offColCpl, colCpl.size() * 4);
   place(ph.offProgStart, progStart.size() * 4);
   place(ph.offProg, prog.size() * 4);
   place(ph.offChainType, atLeast1(chainType.size()) * 4);
@@ -688,6 +726,8 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
       memcpy(blob.data() + offset, src, bytes);
     }
   };
+  put(ph.offColRed, colRed.data(), colRed.size() * 4);
+  put(ph.offColCpl, colCpl.data(), colCpl.size() * 4);
   put(ph.offProgStart, progStart.data(), progStart.size() * 4);
   put(ph.offProg, prog.data(), prog.size() * 4);
   put(ph.offChainType, chainType.data(), chainType.size() * 4);

@@ -19,9 +19,9 @@
  *                                              Rcs_linAlg.c:66-101, :210-227, :270-307
  *     dq     = J# dx + (1 - J# J) invWq (-dH); singular (a pivot <= 0): det = 0, dq = 0
  *   q += dq; RcsGraph_setState
- * All tasks are active (activation 1). Graphs with kinematically coupled joints take the
- * reference's coupled-joint projection, which is not implemented here: the host rejects
- * them (RCSB_EUNSUPPORTED).
+ * All tasks are active (activation 1). Graphs with kinematically coupled joints are solved in
+ * the reduced joint space of RcsGraph_coupledJointMatrix (Rcs_graph.c:2823, IkSolverRMR.cpp:
+ * 424-443) by the general kernel.
  *
  * The small dense algebra (6 x 7 for the arm) stays in per-thread local arrays (L1), the
  * tree walk is the one of rcsb_fk.cu. Bound: FP64 pipe / L1, not HBM (176 B per solve).
@@ -51,6 +51,8 @@ struct IkPlanView
   const double* invWq;
   const double* jlGain;
   const double* q0;
+  const int* colRed;
+  const int* colCpl;
   const int* progStart;
   const int4* prog;
   const int* chainType;
@@ -66,6 +68,8 @@ struct IkPlanView
   __device__ __forceinline__ void bind(const char* blob)
   {
     hdr = reinterpret_cast<const RcsbIkPlanHeader*>(blob);
+    colRed = reinterpret_cast<const int*>(blob + hdr->offColRed);
+    colCpl = reinterpret_cast<const int*>(blob + hdr->offColCpl);
     progStart = reinterpret_cast<const int*>(blob + hdr->offProgStart);
     prog = reinterpret_cast<const int4*>(blob + hdr->offProg);
     chainType = reinterpret_cast<const int*>(blob + hdr->offChainType);
@@ -282,8 +286,21 @@ ikKernel(const IkArgs a)
     dx[i] = 0.0;
   }
 
+  const int nCpl = m.hdr->nCpl;
+  const bool hasCpl = p.hdr->nqr < nJ;   /* unconstrained slave joints: reduced joint space */
+  /* RcsGraph_updateSlaveJoints (Rcs_graph.c:2756): part of every RcsGraph_setState */
+  auto updateSlaves = [&]() {
+    for (int c = 0; c < nCpl; ++c)
+    {
+      qv[m.cpl[c].slave] = slaveAngle(m.cpl[c], qv[m.cpl[c].master]);
+    }
+  };
+  const int nq = p.hdr->nqr;         /* columns of the (reduced) problem */
+  double wv[MAXNJ], av[MAXNJ];       /* reduced joint metric; weights of the coupling matrix A */
+
   for (int it = 0; it < a.iters; ++it)
   {
+    updateSlaves();
     /* ---- forward kinematics (RcsGraph_setState) ------------------------------------------ */
     Frame f, keep;
     setIdentity(f);
@@ -452,10 +469,89 @@ ikKernel(const IkArgs a)
       }
     }
 
-    /* ---- J# = invWq J^T (J invWq J^T + lambda 1)^-1 ------------------------------------------ */
+    /* ---- joint-limit gradient, (-alpha dH), in IK order --------------------------------------- */
     for (int i = 0; i < nJ; ++i)
     {
-      const double w = p.invWq[i];
+      const double delta = qv[p.colJoint[i]] - p.q0[i];
+      g[i] = -(a.alpha * (p.jlGain[i] * delta));
+    }
+
+    /* ---- kinematically coupled joints: reduced joint space (IkSolverRMR.cpp:424-443,
+     * RcsGraph_coupledJointMatrix, Rcs_graph.c:2823). Column r of A holds 1 at its master / free
+     * joint and the coupling sensitivities at its slaves, divided by |column sum|; every joint
+     * has exactly one entry av[c] in column colRed[c].  J <- J A, invWq <- A+ invWq,
+     * dH <- A+ dH with A+ = (A^T A)^-1 A^T. ------------------------------------------------- */
+    if (hasCpl)
+    {
+      double colSum[MAXNJ], den[MAXNJ];
+      for (int r = 0; r < nq; ++r)
+      {
+        colSum[r] = 0.0;
+        den[r] = 0.0;
+      }
+      for (int c = 0; c < nJ; ++c)
+      {
+        const int ci = p.colCpl[c];
+        av[c] = ci < 0 ? 1.0 : slaveVelocity(m.cpl[ci], qv[m.cpl[ci].master], 1.0);
+        colSum[p.colRed[c]] += av[c];
+      }
+      for (int c = 0; c < nJ; ++c)
+      {
+        av[c] = av[c] / fabs(colSum[p.colRed[c]]);
+        den[p.colRed[c]] += av[c] * av[c];
+      }
+      for (int r = 0; r < nq; ++r)
+      {
+        den[r] = 1.0 / den[r];
+        wv[r] = 0.0;
+        dq[r] = 0.0;    /* used as scratch for the reduced gradient */
+      }
+      for (int c = 0; c < nJ; ++c)
+      {
+        const int r = p.colRed[c];
+        const double ia = den[r] * av[c];
+        wv[r] += ia * p.invWq[c];
+        dq[r] += ia * g[c];
+      }
+      for (int r = 0; r < nq; ++r)
+      {
+        g[r] = dq[r];
+      }
+      for (int k = 0; k < nx; ++k)
+      {
+        /* row k of J A; den is free again and serves as the accumulator */
+        double* Jk = J + k * nJ;
+        for (int r = 0; r < nq; ++r)
+        {
+          den[r] = 0.0;
+        }
+        for (int c = 0; c < nJ; ++c)
+        {
+          den[p.colRed[c]] += Jk[c] * av[c];
+        }
+        for (int r = 0; r < nq; ++r)
+        {
+          Jk[r] = den[r];
+        }
+      }
+    }
+    else
+    {
+      for (int i = 0; i < nJ; ++i)
+      {
+        wv[i] = p.invWq[i];
+      }
+    }
+    /* null-space gradient with the joint metric applied: invWq (-alpha dH) */
+    for (int i = 0; i < nq; ++i)
+    {
+      g[i] = wv[i] * g[i];
+    }
+
+    /* ---- J# = invWq J^T (J invWq J^T + lambda 1)^-1 ------------------------------------------ */
+    for (int i = 0; i < nq; ++i)
+    {
+      const double w = wv[i];
       for (int k = 0; k < nx; ++k)
       {
         P[i * nx + k] = w * J[k * nJ + i];
@@ -466,7 +562,7 @@ ikKernel(const IkArgs a)
       for (int c = 0; c < nx; ++c)
       {
         double sum = 0.0;
-        for (int i = 0; i < nJ; ++i)
+        for (int i = 0; i < nq; ++i)
         {
           sum += J[r * nJ + i] * P[i * nx + c];
         }
@@ -541,7 +637,7 @@ ikKernel(const IkArgs a)
       }
     }
     /* J# = (invWq J^T) inverse, row by row in place */
-    for (int i = 0; i < nJ; ++i)
+    for (int i = 0; i < nq; ++i)
     {
       for (int k = 0; k < nx; ++k)
       {
@@ -559,32 +655,55 @@ ikKernel(const IkArgs a)
     }
 
     /* ---- dq = J# dx + (1 - J# J) invWq (-alpha dH) ------------------------------------------- */
-    for (int i = 0; i < nJ; ++i)
-    {
-      const double delta = qv[p.colJoint[i]] - p.q0[i];
-      g[i] = p.invWq[i] * (-(a.alpha * (p.jlGain[i] * delta)));
-    }
     for (int r = 0; r < nx; ++r)
     {
       double sum = 0.0;
-      for (int i = 0; i < nJ; ++i)
+      for (int i = 0; i < nq; ++i)
       {
         sum += J[r * nJ + i] * g[i];
       }
       Jg[r] = sum;
     }
+    if (!hasCpl)
+    {
+      for (int i = 0; i < nJ; ++i)
+      {
+        double ts = 0.0, ns = 0.0;
+        for (int c = 0; c < nx; ++c)
+        {
+          ts += P[i * nx + c] * dx[c];
+          ns += P[i * nx + c] * Jg[c];
+        }
+        dq[i] = ts + (g[i] - ns);
+      }
+    }
+    else
+    {
+      /* task-space and null-space steps of the reduced problem, expanded with A separately as
+       * the reference does (dq_ts = A dqr, dq_ns = A dqr; IkSolverRMR.cpp:541-590) */
+      double tsr[MAXNJ], nsr[MAXNJ];
+      for (int i = 0; i < nq; ++i)
+      {
+        double ts = 0.0, ns = 0.0;
+        for (int c = 0; c < nx; ++c)
+        {
+          ts += P[i * nx + c] * dx[c];
+          ns += P[i * nx + c] * Jg[c];
+        }
+        tsr[i] = ts;
+        nsr[i] = g[i] - ns;
+      }
+      for (int c = 0; c < nJ; ++c)
+      {
+        dq[c] = av[c] * tsr[p.colRed[c]] + av[c] * nsr[p.colRed[c]];
+      }
+    }
     for (int i = 0; i < nJ; ++i)
     {
-      double ts = 0.0, ns = 0.0;
-      for (int c = 0; c < nx; ++c)
-      {
-        ts += P[i * nx + c] * dx[c];
-        ns += P[i * nx + c] * Jg[c];
-      }
-      dq[i] = ts + (g[i] - ns);
       qv[p.colJoint[i]] += dq[i];
     }
   }
+  updateSlaves();   /* the state the last RcsGraph_setState leaves in the graph */
 
   /* ---- results ---------------------------------------------------------------------------------- */
   for (int j = 0; j < dof; ++j)

@@ -143,6 +143,11 @@ typedef struct
    * joint motion; the steps progStart[chainNc] .. progStart[chainNc + 1] lead on to the
    * effector body. chainNc == 0: not eligible, the general kernel runs.
    */
+  int nqr;              /* columns of the reduced problem: nJ minus the unconstrained slave joints */
+  int offColRed;        /* int[nJ]: column of the coupling matrix A the joint belongs to (its own
+                           reduced index, or its master's) */
+  int offColCpl;        /* int[nJ]: coupling record of a slave column, -1 otherwise */
+  int padc;
   int chainNc;
   int nOther;           /* unconstrained joints that are not on the chain */
   int offProgStart;     /* int[chainNc + 2] */

@@ -155,11 +155,52 @@ def test_null_space_does_not_increase_joint_limit_cost(cuda_device, refmod):
     assert np.all(cost1 <= cost0 + 1e-5)
 
 
-def test_coupled_joints_are_rejected(cuda_device):
-    g = rcs_b200.Graph(graph_file("wam_scenario"))
-    m = rcs_b200.Model(g, cuda_device)
-    with pytest.raises(rcs_b200.RcsbError, match="coupled"):
-        m.ik_rmr([(TASK_XYZ, g.body_index("Hand"))], np.zeros((1, g.dof)), np.zeros((1, 3)))
+def step_condition_coupled(rik, q, lay):
+    """Condition number of the reduced matrix J A W_r (J A)^T + lambda 1 (linear couplings)."""
+    _, J = rik.task_kinematics(q)
+    joints = [j for j in lay["joints"] if j["jacobiIndex"] >= 0]
+    nJ = len(joints)
+    H = np.zeros((nJ, nJ))
+    for j in joints:
+        if j["coupledTo"] < 0:
+            H[j["jacobiIndex"], j["jacobiIndex"]] = 1.0
+        else:
+            H[j["jacobiIndex"], lay["joints"][j["coupledTo"]]["jacobiIndex"]] = j["couplingFactors"][0]
+    cols = [c for c in range(nJ) if abs(H[:, c].sum()) > 0]
+    A = H[:, cols] / np.abs(H[:, cols].sum(axis=0))
+    invA = np.linalg.pinv(A)
+    w = invA @ rik.graph.inv_wq()
+    JA = J @ A
+    M = np.einsum("nij,j,nkj->nik", JA, w, JA) + 1.0e-8 * np.eye(J.shape[1])
+    return np.linalg.cond(M)
+
+
+@pytest.mark.parametrize("name,eff,kinds", [("wam_scenario", "Hand", ("XYZ", "ABC")),
+                                            ("wam_scenario", "FingerTipTip1", ("XYZ",)),
+                                            ("wam_scenario", "FingerTipTip2", ("XYZ", "ABC")),
+                                            ("schunk_sdh", "DistalTouch3", ("XYZ",))])
+def test_coupled_joints_reduced_space(name, eff, kinds, refmod, cuda_device):
+    """Kinematically coupled (slave) joints: the reference solves in the reduced joint space of
+    RcsGraph_coupledJointMatrix (Rcs_graph.c:2823, IkSolverRMR.cpp:424-443) and every
+    RcsGraph_setState moves the slaves with their masters."""
+    g, m, rik, tasks = _setup(name, eff, refmod, cuda_device, kinds)
+    lay = g.layout()
+    assert any(j["coupledTo"] >= 0 and not j["constrained"] for j in lay["joints"])
+    q0, x_des = _targets(g, rik, 600, seed_first=41, perturb=0.05)
+    cond = step_condition_coupled(rik, q0, lay)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx")
+    ok = det_ref > 0.0
+    assert ok.mean() > 0.9
+    assert_step_close(out["dq"][ok], dq_ref[ok], cond[ok], "dq")
+    assert_step_close((q - q0)[ok], (q_ref - q0)[ok], cond[ok], "q")
+    q3_ref, _, _, _ = rik.rmr(q0, x_des, iters=3)
+    q3 = q0.copy()
+    m.ik_rmr(tasks, q3, x_des, iters=3)
+    good = ok & (cond < 1.0e4)
+    assert_step_close((q3 - q0)[good], (q3_ref - q0)[good], 3.0 * cond[good], "q after 3 iterations")
 
 
 def test_chain_and_general_kernels_agree_over_ten_iterations(refmod, cuda_device, monkeypatch):
