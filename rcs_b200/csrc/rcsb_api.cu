@@ -392,6 +392,13 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.qdOut = qdOut;
   a.noCoupling = noCoupling ? 1 : 0;
   RCSB_CUDA(cudaSetDevice(m->device));
+  if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
+  {
+    rcsb_set_error("forward kinematics: the effectors' joint chains need %zu bytes of shared memory "
+                   "(limit %d); ask for fewer effectors per call",
+                   rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows), RCSB_SMEM_LIMIT);
+    return RCSB_EUNSUPPORTED;
+  }
   RCSB_CUDA(rcsb_launch_fk(&a, m->hdr.nSlots, plan->nScrRows, stream));
   if (N > 0)
   {

@@ -107,11 +107,26 @@ fkKernel(const FkArgs a)
     }
   }
 
+  /* the model lives in shared memory next to the Jacobian scratch the kernel writes, so the
+   * compiler cannot hoist its loads: the per-body and per-joint descriptors are fetched one
+   * step ahead by hand */
+  int nLd = m.bodyLoad[0], nFlags = m.bodyFlags[0], nJ0 = m.bodyJntStart[0], nCnt = m.bodyJntCount[0];
+  int nJf = dof > 0 ? m.jntFlags[0] : 0, nType = dof > 0 ? m.jntType[0] : 0;
+
   for (int b = 0; b < nb; ++b)
   {
     /* ---- parent frame ---------------------------------------------------------------- */
-    const int ld = m.bodyLoad[b];
-    const int bflags = m.bodyFlags[b];
+    const int ld = nLd;
+    const int bflags = nFlags;
+    const int j0 = nJ0;
+    const int j1 = j0 + nCnt;
+    if (b + 1 < nb)
+    {
+      nLd = m.bodyLoad[b + 1];
+      nFlags = m.bodyFlags[b + 1];
+      nJ0 = m.bodyJntStart[b + 1];
+      nCnt = m.bodyJntCount[b + 1];
+    }
     if (ld == RCSB_LOAD_IDENT)
     {
       setIdentity(f);
@@ -172,11 +187,15 @@ fkKernel(const FkArgs a)
     }
 
     /* ---- joints of the body ------------------------------------------------------------ */
-    const int j0 = m.bodyJntStart[b];
-    const int j1 = j0 + m.bodyJntCount[b];
     for (int j = j0; j < j1; ++j)
     {
-      const int jf = m.jntFlags[j];
+      const int jf = nJf;
+      const int jtype = nType;
+      if (j + 1 < dof)
+      {
+        nJf = m.jntFlags[j + 1];
+        nType = m.jntType[j + 1];
+      }
       if (jf & RCSB_JF_HAS_AJP)
       {
         applyRelF(f, m.jntAJP + 12 * j, jf);
@@ -194,7 +213,7 @@ fkKernel(const FkArgs a)
         }
       }
       const double qj = rd.finishQ(m, j, rawQ);
-      const int dir = m.jntType[j] % 3;
+      const int dir = jtype % 3;
       double ax[3];
 
       if (jf & RCSB_JF_ROT)

@@ -103,6 +103,14 @@ inline int align16(int x)
 
 int checkModel(const RcsbModel* m, long N, int qdim, const double* q);
 
+/* dynamic shared memory of one fkKernel block: model + plan + Jacobian scratch */
+#define RCSB_SMEM_LIMIT (227 * 1024)
+inline size_t fkSharedBytes(const RcsbModel* m, int planBytes, int nScrRows)
+{
+  return (size_t) m->hdr.totalBytes + (size_t) planBytes +
+         (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double);
+}
+
 /* One array of a staged (host-pointer) call: `perState` doubles per state; exactly one of
  * hostIn / hostOut is set; dev receives the device address of the current chunk. */
 struct StagedArray

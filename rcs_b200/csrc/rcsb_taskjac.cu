@@ -26,15 +26,23 @@ struct CombineTask
   int uA;         /* slot of the body whose rotation is applied, -1 = none */
 };
 
+/* where the pass buffers hold body u: fkKernel runs once per group of bodies (as many as its
+ * shared-memory scratch takes), each group state-major */
+struct SlotInfo
+{
+  long offA, strideA;   /* doubles: frame of state s at tmp[offA + s strideA] */
+  long offJ, strideJ;   /* JT at tmp[offJ + s strideJ], JR at tmp[offJ + jrShift + s strideJ] */
+  long jrShift;
+};
+
 struct CombineArgs
 {
-  const double* A;    /* n x nU x 12 */
-  const double* JT;   /* n x nU x 3 x nJ */
-  const double* JR;
+  const double* tmp;
+  const SlotInfo* slots;
   double* out;        /* n x nTasks x 3 x nJ */
   const CombineTask* tasks;
   long n;
-  int nU, nTasks, nJ;
+  int nTasks, nJ;
 };
 
 __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
@@ -49,32 +57,32 @@ __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
     const int t = rem / a.nJ, k = rem - t * a.nJ;
     const CombineTask tk = a.tasks[t];
     const long rec = 3L * a.nJ;
-    const double* JTs = a.JT + s * a.nU * rec;
-    const double* JRs = a.JR + s * a.nU * rec;
-    const double* As = a.A + s * a.nU * 12;
+    auto frame = [&](int u) { return a.tmp + a.slots[u].offA + s * a.slots[u].strideA; };
+    auto jt = [&](int u) { return a.tmp + a.slots[u].offJ + s * a.slots[u].strideJ; };
+    auto jr = [&](int u) { return a.tmp + a.slots[u].offJ + a.slots[u].jrShift + s * a.slots[u].strideJ; };
 
     double v[3] = {0.0, 0.0, 0.0};
     if (tk.kind == RCSB_JAC_POS)
     {
       if (tk.u2 >= 0)
       {
-        const double* j2 = JTs + tk.u2 * rec + k;
+        const double* j2 = jt(tk.u2) + k;
         v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
       }
       if (tk.mode == 1)
       {
-        const double* j1 = JTs + tk.u1 * rec + k;
+        const double* j1 = jt(tk.u1) + k;
         v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
         if (tk.u3 >= 0)
         {
-          const double* o1 = As + tk.u1 * 12;
+          const double* o1 = frame(tk.u1);
           double r[3] = {-o1[0], -o1[1], -o1[2]};
           if (tk.u2 >= 0)
           {
-            const double* o2 = As + tk.u2 * 12;
+            const double* o2 = frame(tk.u2);
             r[0] += o2[0]; r[1] += o2[1]; r[2] += o2[2];
           }
-          const double* j3 = JRs + tk.u3 * rec + k;
+          const double* j3 = jr(tk.u3) + k;
           const double w0 = j3[0], w1 = j3[a.nJ], w2 = j3[2 * a.nJ];
           v[0] += r[1] * w2 - r[2] * w1;
           v[1] += -r[0] * w2 + r[2] * w0;
@@ -86,18 +94,18 @@ __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
     {
       if (tk.u2 >= 0)
       {
-        const double* j2 = JRs + tk.u2 * rec + k;
+        const double* j2 = jr(tk.u2) + k;
         v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
       }
       if (tk.mode == 1 && tk.u1 >= 0)
       {
-        const double* j1 = JRs + tk.u1 * rec + k;
+        const double* j1 = jr(tk.u1) + k;
         v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
       }
     }
     if (tk.uA >= 0)
     {
-      const double* R = As + tk.uA * 12 + 3;
+      const double* R = frame(tk.uA) + 3;
       const double x = v[0], y = v[1], z = v[2];
       v[0] = R[0] * x + R[1] * y + R[2] * z;
       v[1] = R[3] * x + R[4] * y + R[5] * z;
@@ -214,6 +222,39 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
   }
   const int nU = (int) bodies.size();
 
+  /* groups of bodies whose joint chains fit the FK kernel's shared-memory scratch together */
+  std::vector<std::vector<int>> groups;
+  {
+    std::vector<char> onChain((size_t) m->hdr.dof, 0);
+    int nChain = 0;
+    for (int u = 0; u < nU; ++u)
+    {
+      int add = 0;
+      for (int j = bodyLastJnt[bodies[(size_t) u]]; j >= 0; j = jntPrev[j])
+      {
+        add += (jntJacobi[j] >= 0 && !onChain[(size_t) j]) ? 1 : 0;
+      }
+      const int g = groups.empty() ? 0 : (int) groups.back().size();
+      const int rows = 6 * (nChain + add) + 3 * (g + 1);
+      /* plan blobs are small next to the scratch; 8 KB covers them */
+      if (groups.empty() || fkSharedBytes(m, 8192 + 8 * 3 * nJ * (g + 1), rows) > RCSB_SMEM_LIMIT)
+      {
+        groups.emplace_back();
+        std::fill(onChain.begin(), onChain.end(), 0);
+        nChain = 0;
+      }
+      for (int j = bodyLastJnt[bodies[(size_t) u]]; j >= 0; j = jntPrev[j])
+      {
+        if (jntJacobi[j] >= 0 && !onChain[(size_t) j])
+        {
+          onChain[(size_t) j] = 1;
+          ++nChain;
+        }
+      }
+      groups.back().push_back(u);
+    }
+  }
+
   const bool host = (flags & RCSB_HOST_PTRS) != 0;
   cudaStream_t st = host ? nullptr : static_cast<cudaStream_t>(stream);
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
@@ -226,20 +267,21 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
   const size_t qDoubles = host ? (size_t) chunk * qdim : 0;
   double* tmp = nullptr;
   CombineTask* dTasks = nullptr;
+  SlotInfo* dSlots = nullptr;
   RCSB_CUDA(cudaMalloc(&tmp, (tmpDoubles + outDoubles + qDoubles) * sizeof(double)));
-  cudaError_t e = cudaMalloc(&dTasks, tasks.size() * sizeof(CombineTask));
+  cudaError_t e = cudaMalloc(&dTasks, tasks.size() * sizeof(CombineTask) + (size_t) nU * sizeof(SlotInfo));
   if (e == cudaSuccess)
   {
+    dSlots = reinterpret_cast<SlotInfo*>(dTasks + tasks.size());
     e = cudaMemcpyAsync(dTasks, tasks.data(), tasks.size() * sizeof(CombineTask),
                         cudaMemcpyHostToDevice, st);
   }
   int result = RCSB_OK;
+  std::vector<SlotInfo> slots((size_t) nU);
+  long lastN = -1;
   for (long s0 = 0; s0 < N && e == cudaSuccess && result == RCSB_OK; s0 += chunk)
   {
     const long n = N - s0 < chunk ? N - s0 : chunk;
-    double* A = tmp;
-    double* JT = A + (size_t) n * nU * 12;
-    double* JR = JT + (size_t) n * nU * 3 * nJ;
     double* dOut = host ? tmp + tmpDoubles : J + (size_t) s0 * nJac * 3 * nJ;
     const double* dQ = q + (size_t) s0 * qdim;
     if (host)
@@ -252,20 +294,55 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
         break;
       }
     }
-    result = fkCommon(m, n, qdim, dQ, nullptr, nU, bodies.data(), A, nullptr, nullptr, nullptr,
-                      nullptr, nU, bodies.data(), nullptr, JT, JR, nullptr, false, 0, st);
+    long base = 0;
+    for (const std::vector<int>& grp : groups)
+    {
+      const int G = (int) grp.size();
+      std::vector<int> gb((size_t) G);
+      for (int i = 0; i < G; ++i)
+      {
+        gb[(size_t) i] = bodies[(size_t) grp[(size_t) i]];
+      }
+      double* A = tmp + base;
+      double* JT = A + (size_t) n * G * 12;
+      double* JR = JT + (size_t) n * G * 3 * nJ;
+      for (int i = 0; i < G; ++i)
+      {
+        SlotInfo& si = slots[(size_t) grp[(size_t) i]];
+        si.offA = base + 12L * i;
+        si.strideA = 12L * G;
+        si.offJ = (JT - tmp) + 3L * nJ * i;
+        si.strideJ = 3L * nJ * G;
+        si.jrShift = JR - JT;
+      }
+      result = fkCommon(m, n, qdim, dQ, nullptr, G, gb.data(), A, nullptr, nullptr, nullptr,
+                        nullptr, G, gb.data(), nullptr, JT, JR, nullptr, false, 0, st);
+      if (result != RCSB_OK)
+      {
+        break;
+      }
+      base += (long) n * G * (12 + 6L * nJ);
+    }
     if (result != RCSB_OK)
     {
       break;
     }
+    if (n != lastN)
+    {
+      /* pageable source: the copy has left the host buffer when the call returns */
+      e = cudaMemcpyAsync(dSlots, slots.data(), slots.size() * sizeof(SlotInfo), cudaMemcpyHostToDevice, st);
+      lastN = n;
+      if (e != cudaSuccess)
+      {
+        break;
+      }
+    }
     CombineArgs ca;
-    ca.A = A;
-    ca.JT = JT;
-    ca.JR = JR;
+    ca.tmp = tmp;
+    ca.slots = dSlots;
     ca.out = dOut;
     ca.tasks = dTasks;
     ca.n = n;
-    ca.nU = nU;
     ca.nTasks = nJac;
     ca.nJ = nJ;
     const long total = n * nJac * nJ;

@@ -174,3 +174,13 @@ def test_whole_body_task_stack_matches_controller(refmod, cuda_device):
                        axis=1)
     assert_close(J, J_ref, what="stacked task Jacobian (20 x 34)")
     assert_structural_zeros(J, J_ref, what="stacked task Jacobian")
+
+
+def test_too_many_effector_chains_is_a_clear_error(cuda_device):
+    """The Jacobian scratch of fkKernel lives in shared memory: effectors whose chains need more
+    than 227 KB are refused with a message (rcsb_task_jacobians splits them into groups itself)."""
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    m = rcs_b200.Model(g, cuda_device)
+    effs = [g.body_index(n) for n in ("RightHandTip", "LeftHandTip", "FootL", "FootR", "Helmet")]
+    with pytest.raises(rcs_b200.RcsbError, match="shared memory"):
+        m.fk_jacobians(np.zeros((4, g.dof)), effs)
