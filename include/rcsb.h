@@ -103,6 +103,18 @@ int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const double* q,
                       void* stream);
 
 /*
+ * rcsb_fk_jacobians plus the joint-space mass matrix M [N x nJ x nJ]
+ * (RcsGraph_computeMassMatrix, src/RcsCore/Rcs_dynamics.c:610) from the same tree walk: one
+ * kernel launch for "FK + Jacobians + M(q)". Fused for models with nJ <= 8 and symmetric
+ * inertia tensors (the 7-DoF arm); other models run rcsb_fk_jacobians and rcsb_kinetic_terms
+ * one after the other. M == NULL is rcsb_fk_jacobians.
+ */
+int rcsb_fk_jacobians_mass(const RcsbModel* model, long N, int qdim, const double* q, int nSel,
+                           const int* bodySel, double* A_BI, int nEff, const int* effBody,
+                           const double* effPt, double* JT, double* JR, double* M, unsigned flags,
+                           void* stream);
+
+/*
  * Task Jacobians relative to a (possibly articulated) reference body / frame:
  * RcsGraph_3dPosJacobian (RCSB_JAC_POS) and RcsGraph_3dOmegaJacobian (RCSB_JAC_OMEGA),
  * src/RcsCore/Rcs_kinematics.c:566, :789. effector / refBdy / refFrame are depth-first body

@@ -108,6 +108,8 @@ def lib() -> ctypes.CDLL:
         c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_fk_jacobians", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
         c_int, c_void, c_void, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_fk_jacobians_mass", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
+        c_int, c_void, c_void, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_kinetic_terms", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
         c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_task_jacobians", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p,
@@ -349,11 +351,13 @@ class Model:
 
     def fk_jacobians(self, q, effectors: Sequence[int], points=None,
                      bodies: Optional[Sequence[int]] = None, want=("A_BI", "JT", "JR"), out=None):
-        """FK + RcsGraph_bodyPointJacobian / RcsGraph_rotationJacobian per effector."""
+        """FK + RcsGraph_bodyPointJacobian / RcsGraph_rotationJacobian per effector; with "M" in
+        `want` also the mass matrix from the same launch (rcsb_fk_jacobians_mass)."""
         N, qdim = self._batch(q)
         nsel = self.n_bodies if bodies is None else len(bodies)
         neff = len(effectors)
-        shapes = {"A_BI": (N, nsel, 12), "JT": (N, neff, 3, self.nJ), "JR": (N, neff, 3, self.nJ)}
+        shapes = {"A_BI": (N, nsel, 12), "JT": (N, neff, 3, self.nJ), "JR": (N, neff, 3, self.nJ),
+                  "M": (N, self.nJ, self.nJ)}
         out = dict(out or {})
         for k in want:
             if k not in out:
@@ -366,11 +370,12 @@ class Model:
             pa = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(neff, 3))
             a.keep.append(pa)
             pts = ctypes.c_void_p(pa.ctypes.data)
-        rc = lib().rcsb_fk_jacobians(
+        rc = lib().rcsb_fk_jacobians_mass(
             self._h, N, qdim, a.ptr(q, "q"), ns, sel, a.ptr(out.get("A_BI"), "A_BI"), ne, eff, pts,
-            a.ptr(out.get("JT"), "JT"), a.ptr(out.get("JR"), "JR"), a.flags(), a.stream(),
+            a.ptr(out.get("JT"), "JT"), a.ptr(out.get("JR"), "JR"), a.ptr(out.get("M"), "M"),
+            a.flags(), a.stream(),
         )
-        _err(rc, "rcsb_fk_jacobians")
+        _err(rc, "rcsb_fk_jacobians_mass")
         return out
 
     def task_jacobians(self, q, spec, out=None):

@@ -149,9 +149,26 @@ namespace
 /* ---- FK plan ---------------------------------------------------------------------------- */
 
 int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int* effBody,
-                const double* effPt, const DevicePlan** out)
+                const double* effPt, bool withMass, const DevicePlan** out)
 {
   const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
+
+  if (withMass)
+  {
+    /* the fused path keeps 6 doubles per Jacobian column in registers */
+    bool symmetric = true;
+    const double* I = m->darr(RCSB_A_BODY_INERTIA);
+    for (int b = 0; b < nb; ++b)
+    {
+      symmetric = symmetric && I[9 * b + 1] == I[9 * b + 3] && I[9 * b + 2] == I[9 * b + 6] &&
+                  I[9 * b + 5] == I[9 * b + 7];
+    }
+    if (nJ < 1 || nJ > 8 || !symmetric)
+    {
+      rcsb_set_error("fused mass matrix: needs 1 <= nJ <= 8 (is %d) and symmetric inertia tensors", nJ);
+      return RCSB_EUNSUPPORTED;
+    }
+  }
 
   if (nSel < 0 || nEff < 0 || (nSel > 0 && !bodySel) || (nEff > 0 && !effBody))
   {
@@ -176,6 +193,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   }
 
   std::string key;
+  key.push_back(withMass ? 'M' : 'k');
   key.append(reinterpret_cast<const char*>(&nSel), sizeof(int));
   key.append(reinterpret_cast<const char*>(&nEff), sizeof(int));
   if (nSel > 0)
@@ -244,10 +262,10 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   bool inPlace = true;
   for (int j = 0; j < dof; ++j)
   {
-    if (useCount[j] > 0)
+    if (useCount[j] > 0 || (withMass && jntJacobi[j] >= 0))
     {
-      jntScr[j] = nChain++;
-      inPlace = inPlace && (useCount[j] == 1);
+      jntScr[j] = nChain++;   /* with the mass matrix: every column, slot == column */
+      inPlace = inPlace && (useCount[j] <= 1);
     }
   }
   if (nChain > 0xffff || nEff > 2047)
@@ -313,7 +331,46 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   ph.nSel = nOut;
   ph.nEff = nEff;
   ph.nChain = nChain;
-  ph.nScrRows = (nEff > 0) ? 6 * nChain + 3 * nEff : 0;
+  ph.nScrRows = (nEff > 0 || withMass) ? 6 * nChain + 3 * nEff : 0;
+  std::vector<int> pathMask((size_t) nb, 0);
+  if (withMass)
+  {
+    ph.mass = 1;
+    ph.nJ = nJ;
+    /* the matrices are staged over the Jacobian scratch once the Jacobians are out */
+    ph.mStageRow = 0;
+    ph.nScrRows = ph.nScrRows > nJ * nJ ? ph.nScrRows : nJ * nJ;
+    ph.invNJ2 = 1.0f / (float) (nJ * nJ);
+    for (int j = 0; j < dof; ++j)
+    {
+      const int c = jntJacobi[j];
+      if (c < 0)
+      {
+        continue;
+      }
+      if (jntFlags[j] & RCSB_JF_ROT)
+      {
+        ph.rotMask |= 1 << c;
+      }
+      for (int a = jntPrev[j]; a >= 0; a = jntPrev[a])
+      {
+        if (jntJacobi[a] >= 0)
+        {
+          ph.relMask[c] |= 1 << jntJacobi[a];
+        }
+      }
+    }
+    for (int b = 0; b < nb; ++b)
+    {
+      for (int j = bodyLastJnt[b]; j >= 0; j = jntPrev[j])
+      {
+        if (jntJacobi[j] >= 0)
+        {
+          pathMask[(size_t) b] |= 1 << jntJacobi[j];
+        }
+      }
+    }
+  }
   ph.jacRecord = rec;
   ph.inPlace = inPlace ? 1 : 0;
   ph.invJacRecord = rec > 0 ? 1.0f / (float) rec : 0.0f;
@@ -336,6 +393,8 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   off = align16(off + (nEff + 1) * 4);
   ph.offEffChain = off;
   off = align16(off + (int) effChain.size() * 4);
+  ph.offBodyPathMask = off;
+  off = align16(off + nb * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob(ph.totalBytes, 0);
@@ -352,6 +411,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   memcpy(blob.data() + ph.offJTabR, jtabR.data(), jtabR.size() * 4);
   memcpy(blob.data() + ph.offEffChainStart, effChainStart.data(), (nEff + 1) * 4);
   memcpy(blob.data() + ph.offEffChain, effChain.data(), effChain.size() * 4);
+  memcpy(blob.data() + ph.offBodyPathMask, pathMask.data(), (size_t) nb * 4);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -370,7 +430,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
 /* FK (+ Jacobians) on device pointers */
 int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const double* q,
              const double* qd, double* A_BI, double* A_JI, double* xdot, double* omega,
-             double* qOut, double* JT, double* JR, double* qdOut, bool noCoupling,
+             double* qOut, double* JT, double* JR, double* qdOut, bool noCoupling, double* M,
              cudaStream_t stream)
 {
   rcsb::FkArgs a;
@@ -390,6 +450,7 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.JT = JT;
   a.JR = JR;
   a.qdOut = qdOut;
+  a.M = M;
   a.noCoupling = noCoupling ? 1 : 0;
   RCSB_CUDA(cudaSetDevice(m->device));
   if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
@@ -587,7 +648,7 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
                        int nSel, const int* bodySel, double* A_BI, double* A_JI, double* xdot,
                        double* omega, double* qOut, int nEff, const int* effBody,
                        const double* effPt, double* JT, double* JR, double* qdOut,
-                       bool noCoupling, unsigned flags, void* stream)
+                       bool noCoupling, unsigned flags, void* stream, double* M)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   int rc = checkModel(m, N, qdim, q);
@@ -607,7 +668,12 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
   }
 
   const DevicePlan* plan = nullptr;
-  rc = buildFkPlan(m, nSel, bodySel, (JT || JR) ? nEff : 0, effBody, effPt, &plan);
+  if (M && qd)
+  {
+    rcsb_set_error("the fused mass matrix is computed without velocities");
+    return RCSB_EINVAL;
+  }
+  rc = buildFkPlan(m, nSel, bodySel, (JT || JR) ? nEff : 0, effBody, effPt, M != nullptr, &plan);
   if (rc != RCSB_OK)
   {
     return rc;
@@ -620,13 +686,13 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
   if (!(flags & RCSB_HOST_PTRS))
   {
     return fkDevice(m, plan, N, qdim, q, qd, A_BI, A_JI, xdot, omega, qOut, JT, JR, qdOut,
-                    noCoupling, static_cast<cudaStream_t>(stream));
+                    noCoupling, M, static_cast<cudaStream_t>(stream));
   }
 
   const size_t dof = (size_t) m->hdr.dof, nOut = (size_t) plan->nSel;
   const size_t recJ = (size_t) plan->nEff * 3 * m->hdr.nJ;
   std::vector<StagedArray> arr;
-  enum { I_Q, I_QD, I_A, I_AJ, I_XD, I_OM, I_QO, I_JT, I_JR, I_QDO };
+  enum { I_Q, I_QD, I_A, I_AJ, I_XD, I_OM, I_QO, I_JT, I_JR, I_QDO, I_M };
   arr.push_back({q, nullptr, (size_t) qdim, nullptr});
   arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
   arr.push_back({nullptr, A_BI, A_BI ? nOut * 12 : 0, nullptr});
@@ -637,12 +703,13 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
   arr.push_back({nullptr, JT, JT ? recJ : 0, nullptr});
   arr.push_back({nullptr, JR, JR ? recJ : 0, nullptr});
   arr.push_back({nullptr, qdOut, qdOut ? dof : 0, nullptr});
+  arr.push_back({nullptr, M, M ? (size_t) m->hdr.nJ * m->hdr.nJ : 0, nullptr});
 
   return runStaged(m, N, arr, {}, [&](long n, cudaStream_t st, int) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
     return fkDevice(m, plan, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_A, A_BI), dv(I_AJ, A_JI),
                     dv(I_XD, xdot), dv(I_OM, omega), dv(I_QO, qOut), dv(I_JT, JT), dv(I_JR, JR),
-                    dv(I_QDO, qdOut), noCoupling, st);
+                    dv(I_QDO, qdOut), noCoupling, dv(I_M, M), st);
   });
 }
 
@@ -662,4 +729,31 @@ extern "C" int rcsb_fk_jacobians(const RcsbModel* model, long N, int qdim, const
 {
   return fkCommon(model, N, qdim, q, nullptr, nSel, bodySel, A_BI, nullptr, nullptr, nullptr,
                   nullptr, nEff, effBody, effPt, JT, JR, nullptr, false, flags, stream);
+}
+
+/* FK + Jacobians + mass matrix in one launch (models with nJ <= 8 and symmetric inertia
+ * tensors); other models take rcsb_fk_jacobians + rcsb_kinetic_terms. */
+extern "C" int rcsb_fk_jacobians_mass(const RcsbModel* model, long N, int qdim, const double* q,
+                                      int nSel, const int* bodySel, double* A_BI, int nEff,
+                                      const int* effBody, const double* effPt, double* JT,
+                                      double* JR, double* M, unsigned flags, void* stream)
+{
+  if (!M)
+  {
+    return rcsb_fk_jacobians(model, N, qdim, q, nSel, bodySel, A_BI, nEff, effBody, effPt, JT, JR,
+                             flags, stream);
+  }
+  int rc = fkCommon(model, N, qdim, q, nullptr, nSel, bodySel, A_BI, nullptr, nullptr, nullptr,
+                    nullptr, nEff, effBody, effPt, JT, JR, nullptr, false, flags, stream, M);
+  if (rc != RCSB_EUNSUPPORTED)
+  {
+    return rc;
+  }
+  rc = rcsb_fk_jacobians(model, N, qdim, q, nSel, bodySel, A_BI, nEff, effBody, effPt, JT, JR, flags,
+                         stream);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  return rcsb_kinetic_terms(model, N, qdim, q, nullptr, M, nullptr, nullptr, nullptr, flags, stream);
 }

@@ -38,6 +38,7 @@ struct PlanView
   const int* jtabR;
   const int* effChainStart;
   const int* effChain;
+  const int* bodyPathMask;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -51,11 +52,21 @@ struct PlanView
     jtabR = reinterpret_cast<const int*>(blob + hdr->offJTabR);
     effChainStart = reinterpret_cast<const int*>(blob + hdr->offEffChainStart);
     effChain = reinterpret_cast<const int*>(blob + hdr->offEffChain);
+    bodyPathMask = reinterpret_cast<const int*>(blob + hdr->offBodyPathMask);
   }
 };
 
-template <bool VEL, bool ALIGNED32, int NSLOTS>
-__global__ void __launch_bounds__(RCSB_FK_THREADS)
+/* MASS: additionally the joint-space mass matrix (RcsGraph_computeMassMatrix, Rcs_dynamics.c:
+ * 610) for models with at most 8 Jacobian columns: for every massive body and every column k
+ * that moves it, the body's momentum under a unit rate of joint k, (p, L) about the world
+ * origin, is added to the column's accumulator F[k] (registers); after the walk
+ * M[i][k] = <joint i, F[k]> for i an ancestor-or-self of k. Same result as the composite-body
+ * route of rcsb_kinetic.cu, without the per-link storage. */
+#ifndef RCSB_FKM_MIN_BLOCKS
+#define RCSB_FKM_MIN_BLOCKS 1
+#endif
+template <bool VEL, bool ALIGNED32, int NSLOTS, bool MASS>
+__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : 1)
 fkKernel(const FkArgs a)
 {
   extern __shared__ __align__(16) char smem[];
@@ -91,6 +102,19 @@ fkKernel(const FkArgs a)
 
   constexpr int SLOT_DOUBLES = VEL ? 18 : 12;
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * SLOT_DOUBLES];
+  double F[MASS ? 8 : 1][6];
+  if (MASS)
+  {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+      {
+        F[k][i] = 0.0;
+      }
+    }
+  }
 
   Frame f, keep;
   double xd[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
@@ -343,6 +367,76 @@ fkKernel(const FkArgs a)
       }
     }
 
+    /* ---- mass properties: momentum of the body under unit joint rates ---------------------- */
+    if (MASS && (bflags & RCSB_BF_HAS_MASS))
+    {
+      const double mass = m.bodyMass[b];
+      const double* cl = m.bodyCom + 3 * b;
+      const double* Ib = m.bodyInertia + 9 * b;
+      const double* R = f.R;
+      const double c[3] = {f.o[0] + (R[0] * cl[0] + R[3] * cl[1] + R[6] * cl[2]),
+                           f.o[1] + (R[1] * cl[0] + R[4] * cl[1] + R[7] * cl[2]),
+                           f.o[2] + (R[2] * cl[0] + R[5] * cl[1] + R[8] * cl[2])};
+      /* world inertia about the COM: R^T I_b R (Mat3d_similarityTransform) */
+      double tmp[9], Iw[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+        {
+          tmp[3 * i + jj] = Ib[3 * i] * R[jj] + Ib[3 * i + 1] * R[3 + jj] + Ib[3 * i + 2] * R[6 + jj];
+        }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+        {
+          Iw[3 * i + jj] = R[i] * tmp[jj] + R[3 + i] * tmp[3 + jj] + R[6 + i] * tmp[6 + jj];
+        }
+      const int mask = p.bodyPathMask[b];
+      const int rotMask = p.hdr->rotMask;
+      const int rs = nChain * scrStride;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        if ((mask >> k) & 1)
+        {
+          const double* col = scr + k * scrStride + tid;
+          const double ak[3] = {col[0], col[rs], col[2 * rs]};
+          double pk[3], Lk[3];
+          if ((rotMask >> k) & 1)
+          {
+            const double d[3] = {c[0] - col[3 * rs], c[1] - col[4 * rs], c[2] - col[5 * rs]};
+            double jt[3];
+            cross3(jt, ak, d);                 /* velocity of the COM: a x (c - o) */
+            pk[0] = mass * jt[0];
+            pk[1] = mass * jt[1];
+            pk[2] = mass * jt[2];
+            double cp[3];
+            cross3(cp, c, pk);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+              Lk[i] = Iw[3 * i] * ak[0] + Iw[3 * i + 1] * ak[1] + Iw[3 * i + 2] * ak[2] + cp[i];
+            }
+          }
+          else
+          {
+            pk[0] = mass * ak[0];
+            pk[1] = mass * ak[1];
+            pk[2] = mass * ak[2];
+            cross3(Lk, c, pk);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            F[k][i] += pk[i];
+            F[k][3 + i] += Lk[i];
+          }
+        }
+      }
+    }
+
     const int out = p.bodyOut[b];
     if (out >= 0 && active)
     {
@@ -387,6 +481,45 @@ fkKernel(const FkArgs a)
           xd[i] = keepXd[i];
           om[i] = keepOm[i];
         }
+      }
+    }
+  }
+
+  /* ---- mass matrix entries (upper triangle, registers): computed before the Jacobian pass
+   * overwrites the joint origins, staged after it over the same scratch rows ------------------ */
+  double Mv[MASS ? 36 : 1];
+  if (MASS && a.M)
+  {
+    const int nJ = p.hdr->nJ;
+    const int rs = nChain * scrStride;
+    const int rotMask = p.hdr->rotMask;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const int rel = k < nJ ? (p.hdr->relMask[k] | (1 << k)) : 0;
+#pragma unroll
+      for (int i = 0; i <= k; ++i)
+      {
+        double val = 0.0;
+        if ((rel >> i) & 1)
+        {
+          const double* col = scr + i * scrStride + tid;
+          const double ai[3] = {col[0], col[rs], col[2 * rs]};
+          if ((rotMask >> i) & 1)
+          {
+            /* a . (L - o x p) */
+            const double oi[3] = {col[3 * rs], col[4 * rs], col[5 * rs]};
+            const double pk[3] = {F[k][0], F[k][1], F[k][2]};
+            double t[3];
+            cross3(t, oi, pk);
+            val = ai[0] * (F[k][3] - t[0]) + ai[1] * (F[k][4] - t[1]) + ai[2] * (F[k][5] - t[2]);
+          }
+          else
+          {
+            val = ai[0] * F[k][0] + ai[1] * F[k][1] + ai[2] * F[k][2];
+          }
+        }
+        Mv[k * (k + 1) / 2 + i] = val;
       }
     }
   }
@@ -497,15 +630,55 @@ fkKernel(const FkArgs a)
       }
     }
   }
+
+  if (MASS && a.M)
+  {
+    /* stage the matrices over the scratch rows the Jacobians have left, then copy out: the
+     * warp's 32 matrices are contiguous in global memory */
+    __syncwarp();
+    {
+      const int nJ = p.hdr->nJ;
+      double* st = scr + p.hdr->mStageRow * scrStride + tid;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+#pragma unroll
+        for (int i = 0; i <= k; ++i)
+        {
+          if (k < nJ)
+          {
+            st[(i * nJ + k) * scrStride] = Mv[k * (k + 1) / 2 + i];
+            st[(k * nJ + i) * scrStride] = Mv[k * (k + 1) / 2 + i];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int lane = tid & 31;
+    const long w0 = s - lane;
+    long nv = a.N - w0;
+    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+    const int nJ2 = p.hdr->nJ * p.hdr->nJ;
+    const int total = (int) nv * nJ2;
+    const float inv = p.hdr->invNJ2;
+    const double* stw = scr + p.hdr->mStageRow * scrStride + (tid - lane);
+    double* Mw = a.M + w0 * nJ2;
+    for (int e = lane; e < total; e += 32)
+    {
+      const int sl = __float2int_rd(((float) e + 0.5f) * inv);
+      const int rem = e - sl * nJ2;
+      Mw[e] = stw[rem * scrStride + sl];
+    }
+  }
 }
 
-template <bool VEL, bool ALIGNED32>
+template <bool VEL, bool ALIGNED32, bool MASS>
 static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t smemBytes,
                                cudaStream_t stream)
 {
 #define RCSB_LAUNCH(NS)                                                                        \
   {                                                                                            \
-    auto k = fkKernel<VEL, ALIGNED32, NS>;                                                     \
+    auto k = fkKernel<VEL, ALIGNED32, NS, MASS>;                                               \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int) smemBytes);                                     \
     if (e != cudaSuccess)                                                                      \
@@ -547,11 +720,16 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
   const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &
                    31u) == 0;
 
+  if (a->M)
+  {
+    return al ? launchSlots<false, true, true>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<false, false, true>(*a, nSlots, grid, smemBytes, stream);
+  }
   if (vel)
   {
-    return al ? launchSlots<true, true>(*a, nSlots, grid, smemBytes, stream)
-              : launchSlots<true, false>(*a, nSlots, grid, smemBytes, stream);
+    return al ? launchSlots<true, true, false>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<true, false, false>(*a, nSlots, grid, smemBytes, stream);
   }
-  return al ? launchSlots<false, true>(*a, nSlots, grid, smemBytes, stream)
-            : launchSlots<false, false>(*a, nSlots, grid, smemBytes, stream);
+  return al ? launchSlots<false, true, false>(*a, nSlots, grid, smemBytes, stream)
+            : launchSlots<false, false, false>(*a, nSlots, grid, smemBytes, stream);
 }

@@ -47,6 +47,16 @@ typedef struct
   int offEffChainStart; /* int[nEff + 1]: CSR over (slot | isRot << 16) per effector */
   int offEffChain;      /* int[sum of chain lengths] */
   float invJacRecord;
+  /* fused mass matrix (fkKernel<..., MASS>: models with nJ <= 8 and symmetric inertia tensors):
+   * every Jacobian column has a scratch slot (slot == column), the bodies' path masks say
+   * which columns move them, M is staged in nJ x nJ extra scratch rows from mStageRow on */
+  int mass;            /* 1: plan carries the tables below */
+  int nJ;
+  int rotMask;         /* bit k: column k is a rotational joint */
+  int mStageRow;       /* first scratch row of the M staging area */
+  int offBodyPathMask; /* int[nb]: bit k set if column k moves the body */
+  int relMask[8];      /* bit i of relMask[k]: column i is a proper ancestor of column k */
+  float invNJ2;
   int pad;
 } RcsbFkPlanHeader;
 

@@ -137,7 +137,8 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
 int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd, int nSel,
              const int* bodySel, double* A_BI, double* A_JI, double* xdot, double* omega,
              double* qOut, int nEff, const int* effBody, const double* effPt, double* JT,
-             double* JR, double* qdOut, bool noCoupling, unsigned flags, void* stream);
+             double* JR, double* qdOut, bool noCoupling, unsigned flags, void* stream,
+             double* M = nullptr);
 
 }   // namespace rcsbhost
 

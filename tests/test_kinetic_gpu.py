@@ -134,3 +134,31 @@ def test_direct_dynamics(name, n, refmod, cuda_device):
     err0 = np.abs(dev["qdd"].cpu().numpy() - ref0).max(axis=1)
     tol0 = 1e-12 * np.maximum(1.0, cond / 100.0) * np.maximum(1.0, np.abs(ref0).max(axis=1))
     assert np.all(err0 <= tol0)
+
+
+@pytest.mark.parametrize("name,effs,n", [("wam_arm", ["BallTip"], 5000), ("wam_arm", ["BallTip", "Link4"], 333),
+                                         ("schunk_sdh", ["DistalTouch3"], 500), ("humanoid", ["RightHandTip"], 64),
+                                         ("husky", None, 64)])
+def test_fused_fk_jacobians_mass_matrix(name, effs, n, refmod, cuda_device):
+    """rcsb_fk_jacobians_mass: FK + Jacobians + M(q) from one launch (nJ <= 8, symmetric inertia:
+    wam_arm, schunk_sdh) or from the two general paths (humanoid: nJ 34; husky: asymmetric
+    tensors) — same outputs either way, against the reference."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    eff = [g.body_index(e) for e in effs] if effs else [g.n_bodies - 1]
+    q = workload.sample_states(g.layout(), n, first=17)
+    launches0 = rcs_b200.kernel_launch_count()
+    ours = m.fk_jacobians(torch.from_numpy(q).cuda(cuda_device), eff, want=("A_BI", "JT", "JR", "M"))
+    torch.cuda.synchronize()
+    launches = rcs_b200.kernel_launch_count() - launches0
+    fused = name in ("wam_arm", "schunk_sdh")
+    assert launches == (1 if fused else 3)
+    ref = r.fk_jacobians(q, eff)
+    for k in ("A_BI", "JT", "JR"):
+        assert_close(ours[k].cpu().numpy(), ref[k], what=f"{name}:{k}")
+    M_ref = r.mass_matrix(q)
+    assert_close(ours["M"].cpu().numpy(), M_ref, what=f"{name}:M")
+    assert_structural_zeros(ours["M"].cpu().numpy(), M_ref, what=f"{name}:M")
+    host = m.fk_jacobians(q, eff, want=("JT", "M"))
+    assert np.array_equal(host["M"], ours["M"].cpu().numpy())

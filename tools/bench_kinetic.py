@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--states", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--m-only", action="store_true", help="mass matrix only, no velocities")
     ap.add_argument("--dynamics", action="store_true",
                     help="time rcsb_direct_dynamics (qdd, E; M stays on the SM) instead")
     args = ap.parse_args()
@@ -39,7 +40,12 @@ def main():
         "Fg": torch.empty((n, g.nJ), dtype=torch.float64, device="cuda"),
         "E": torch.empty((n,), dtype=torch.float64, device="cuda"),
     }
-    if args.dynamics:
+    if args.m_only:
+        out = {"M": out["M"]}
+
+        def call():
+            m.kinetic_terms(dq, out=out)
+    elif args.dynamics:
         out = {"qdd": torch.empty((n, g.nJ), dtype=torch.float64, device="cuda"), "E": out["E"]}
 
         def call():
@@ -58,10 +64,12 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     bytes_per_state = 2 * g.dof * 8 + (g.nJ * g.nJ + 2 * g.nJ + 1) * 8
+    if args.m_only:
+        bytes_per_state = g.dof * 8 + g.nJ * g.nJ * 8
     if args.dynamics:
         bytes_per_state = 2 * g.dof * 8 + (g.nJ + 1) * 8
     print(json.dumps({
-        "workload": f"{args.graph} " + ("direct dynamics qdd,E" if args.dynamics else "kinetic terms M,h,Fg,E"), "states": n, "ms": ms,
+        "workload": f"{args.graph} " + ("direct dynamics qdd,E" if args.dynamics else "mass matrix only" if args.m_only else "kinetic terms M,h,Fg,E"), "states": n, "ms": ms,
         "states_per_s": n / (ms * 1e-3), "bytes_per_state": bytes_per_state,
         "GBps": bytes_per_state * n / (ms * 1e-3) / 1e9,
         "blocks_per_sm": os.environ.get("RCSB_KT_BLOCKS_PER_SM", "auto")}))
