@@ -38,9 +38,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
-UNIT = {"fk": "states/s", "kinetic": "states/s", "ik": "solves/s"}
+UNIT = {"fk": "states/s", "fkm": "states/s", "kinetic": "states/s", "ik": "solves/s"}
 METRIC = {
     "fk": "FK+Jacobian states/sec FP64 (7-DoF arm, 1M states per GPU)",
+    "fkm": "FK+Jacobian+M(q) states/sec FP64 (7-DoF arm, 1M states per GPU, one launch)",
     "kinetic": "kinetic terms M,h,g states/sec FP64 (humanoid, 256K states per GPU)",
     "ik": "RMR IK solves/sec FP64 (7-DoF arm, XYZ+ABC, 10 iterations, 4M targets)",
 }
@@ -70,6 +71,16 @@ class Workload:
             self.desc = ("configs[1]: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames + "
                          "JT/JR of BallTip, uniformly sampled joint states")
             self.l2 = "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)"
+        elif name == "fkm":
+            self.graph, self.eff = "wam_arm", "BallTip"
+            self.per_gpu = 1 << 20
+            self.scaling = "weak"
+            self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8 + 7 * 7 * 8  # 1936
+            self.kernel = "rcsb::fkKernel<MASS>"
+            self.launches_per_step = 1
+            self.desc = ("north_star target: WAM 7-DoF arm, FK all 12 body frames + JT/JR of BallTip + "
+                         "mass matrix M(q) from one launch (rcsb_fk_jacobians_mass)")
+            self.l2 = "per-step working set 2.0 GB per GPU >> 126 MB L2 (no flush needed)"
         elif name == "kinetic":
             self.graph, self.eff = "humanoid", None
             self.per_gpu = 1 << 18
@@ -154,7 +165,7 @@ class ReferenceRunner:
 
         wl, g = self.wl, self.g
         self.sample = sample
-        if wl.name == "fk":
+        if wl.name in ("fk", "fkm"):
             self.q = workload.sample_states(self.layout, sample)
             self.eff = [g.body_index(wl.eff)]
         elif wl.name == "kinetic":
@@ -172,6 +183,11 @@ class ReferenceRunner:
         if wl.name == "fk":
             g.fk_jacobians(self.q, self.eff)
             return g.last_seconds
+        if wl.name == "fkm":
+            g.fk_jacobians(self.q, self.eff)
+            t = g.last_seconds
+            g.mass_matrix(self.q)
+            return t + g.last_seconds
         if wl.name == "kinetic":
             g.kinetic_terms(self.q, self.qd)
             return g.last_seconds
@@ -180,7 +196,7 @@ class ReferenceRunner:
 
     def calibrate(self, target_seconds: float, cap: int) -> int:
         """Sample size (power of two) whose pass takes about target_seconds."""
-        n = {"fk": 1 << 14, "kinetic": 1 << 8, "ik": 1 << 12}[self.wl.name]
+        n = {"fk": 1 << 14, "fkm": 1 << 13, "kinetic": 1 << 8, "ik": 1 << 12}[self.wl.name]
         self.prepare(n)
         rate = n / max(self.run(), 1e-9)
         want = int(min(cap, max(n, rate * target_seconds)))
@@ -338,16 +354,18 @@ def run_ours(args):
         return torch.empty(shape, dtype=f64, device=dev)
 
     # ---- workload-specific buffers and the two call forms (device pointers / host pointers) ----
-    if wl.name == "fk":
+    if wl.name in ("fk", "fkm"):
         eff = [g.body_index(wl.eff)]
         q_host = workload.sample_states(lay, n, first=first)
         q = torch.from_numpy(q_host).to(dev)
         shapes = {"A_BI": (n, g.n_bodies, 12), "JT": (n, 1, 3, g.nJ), "JR": (n, 1, 3, g.nJ)}
+        if wl.name == "fkm":
+            shapes["M"] = (n, g.nJ, g.nJ)
         out = {k: dev_empty(s) for k, s in shapes.items()}
         hq = pinned((n, g.dof))
         hq.copy_(torch.from_numpy(q_host))
         hout = {k: pinned(s) for k, s in shapes.items()}
-        h2d, d2h = n * g.dof * 8, n * (g.n_bodies * 12 + 2 * 3 * g.nJ) * 8
+        h2d, d2h = n * g.dof * 8, sum(int(np.prod(sh[1:])) for sh in shapes.values()) * n * 8
 
         def device_call():
             m.fk_jacobians(q, eff, out=out)
@@ -562,7 +580,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fk", choices=["fk", "kinetic", "ik"])
+    ap.add_argument("--workload", default="fk", choices=["fk", "fkm", "kinetic", "ik"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hold", type=float, default=1.0,
                     help="seconds of extra (untimed) load for the clock sampler")

@@ -623,7 +623,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
       }
       progStart.push_back((int) prog.size() / 4);
       chainNc = (int) chainJoint.size();
-      if (chainNc < 1 || chainNc > 8 || m->hdr.nCpl > 0)
+      if (chainNc < 1 || chainNc > 32 || m->hdr.nCpl > 0)
       {
         chainNc = 0;   /* long chains and graphs with coupled joints take the general kernel */
       }

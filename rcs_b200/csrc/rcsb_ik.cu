@@ -1134,6 +1134,383 @@ ikChainKernel(const IkArgs a)
   }
 }
 
+/* In-place Cholesky factor of the packed lower triangle A (row i at i (i + 1) / 2), as the
+ * reference's MatNd_choleskyDecompositionSelf (Rcs_linAlg.c:66-101), followed by the solution of
+ * (L L^T) y = r by substitution. Returns false on a non-positive pivot (det = 0). */
+template <int NX>
+__device__ __forceinline__ bool choleskySolve(double (&A)[NX * (NX + 1) / 2], const double (&r)[NX],
+                                              double (&y)[NX], double& det)
+{
+  double invd[NX];
+  bool ok = true;
+  det = 1.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+#pragma unroll
+    for (int k = 0; k <= i; ++k)
+    {
+      double sum = A[i * (i + 1) / 2 + k];
+#pragma unroll
+      for (int t = 0; t < k; ++t)
+      {
+        sum -= A[i * (i + 1) / 2 + t] * A[k * (k + 1) / 2 + t];
+      }
+      if (k < i)
+      {
+        A[i * (i + 1) / 2 + k] = sum * invd[k];
+      }
+      else
+      {
+        ok = ok && (sum > 0.0);
+        const double d = sqrt(ok ? sum : 1.0);
+        A[i * (i + 1) / 2 + i] = d;
+        invd[i] = 1.0 / d;
+        det *= d * d;
+      }
+    }
+  }
+  if (!ok)
+  {
+    det = 0.0;
+    return false;
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+    double sum = r[i];
+#pragma unroll
+    for (int t = 0; t < i; ++t)
+    {
+      sum -= A[i * (i + 1) / 2 + t] * y[t];
+    }
+    y[i] = sum * invd[i];
+  }
+#pragma unroll
+  for (int i = NX - 1; i >= 0; --i)
+  {
+    double sum = y[i];
+#pragma unroll
+    for (int t = i + 1; t < NX; ++t)
+    {
+      sum -= A[t * (t + 1) / 2 + i] * y[t];
+    }
+    y[i] = sum * invd[i];
+  }
+  return true;
+}
+
+/*
+ * Single chain with more columns than the register file takes (9 .. RCSB_IK_LOOP_MAX_NC, e.g.
+ * a humanoid's hand: 13 columns): the same step as ikChainKernel with the per-column data
+ * (axis / origin, then the Jacobian column; joint value; step) in shared memory
+ * [column][element][thread] and ordinary loops over the columns; the NX x NX system stays in
+ * registers.
+ */
+#define RCSB_IK_LOOP_MAX_NC 32
+#define RCSB_IK_LOOP_THREADS 64
+template <int NX>
+__global__ void __launch_bounds__(RCSB_IK_LOOP_THREADS)
+ikChainLoopKernel(const IkArgs a, int nc)
+{
+  extern __shared__ __align__(16) char smem[];
+  constexpr int T = RCSB_IK_LOOP_THREADS;
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [9][T] */
+  double* sCol = sAd + 9 * T;                                     /* [nc][8][T]: 0..5 column, 6 q, 7 dq */
+  stageBlob(sModel, a.model, a.modelBytes);
+  stageBlob(sPlan, a.plan, a.planBytes);
+  __syncthreads();
+
+  ModelView m;
+  m.bind(sModel);
+  IkPlanView p;
+  p.bind(sPlan);
+
+  const int tid = threadIdx.x;
+  const long s = (long) blockIdx.x * T + tid;
+  if (s >= a.N)
+  {
+    return;
+  }
+
+  constexpr int NT = NX / 3;
+  constexpr int NA = NX * (NX + 1) / 2;
+  const int dof = m.hdr->dof;
+  const bool xyzFirst = p.taskKind[0] == RCSB_TASK_XYZ;
+  const bool hasAbc = (NT == 2) || !xyzFirst;
+  const bool hasXyz = (NT == 2) || xyzFirst;
+  double* qRow = a.q + s * dof;
+  const double* xd = a.xDes + s * NX;
+  double* col = sCol + tid;
+  auto at = [&](int c, int i) -> double& { return col[(c * 8 + i) * T]; };
+
+  for (int c = 0; c < nc; ++c)
+  {
+    at(c, 6) = qRow[p.chainJoint[c]];
+    at(c, 7) = 0.0;
+  }
+  double xPos[3] = {0.0, 0.0, 0.0};
+  if (hasXyz)
+  {
+    const int o = (NT == 2 && !xyzFirst) ? 3 : 0;
+    xPos[0] = xd[o];
+    xPos[1] = xd[o + 1];
+    xPos[2] = xd[o + 2];
+  }
+  if (hasAbc)
+  {
+    const int o = (NT == 2 && xyzFirst) ? 3 : 0;
+    const double ea[3] = {xd[o], xd[o + 1], xd[o + 2]};
+    double Ad[9];
+    fromEuler(Ad, ea);
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+    {
+      sAd[i * T + tid] = Ad[i];
+    }
+  }
+
+  double dx[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+    dx[i] = 0.0;
+  }
+  double det = 0.0;
+  unsigned long long singular = 0ull;
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    /* ---- forward kinematics along the chain ------------------------------------------------ */
+    Frame f;
+    setIdentity(f);
+    for (int c = 0; c < nc; ++c)
+    {
+      for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
+      {
+        chainStep(f, p.prog[k], sModel, qRow);
+      }
+      const int type = p.chainType[c];
+      const int dir = type % 3;
+      const double qc = at(c, 6);
+      double axc[3];
+      if (type < 3)
+      {
+        double sn, cs;
+        sincos(qc, &sn, &cs);
+        rotateAboutAxis(f, dir, sn, cs);
+        axisOf(f, dir, axc);
+      }
+      else
+      {
+        axisOf(f, dir, axc);
+        f.o[0] += qc * axc[0];
+        f.o[1] += qc * axc[1];
+        f.o[2] += qc * axc[2];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        at(c, i) = axc[i];
+        at(c, 3 + i) = f.o[i];
+      }
+    }
+    for (int k = p.progStart[nc]; k < p.progStart[nc + 1]; ++k)
+    {
+      chainStep(f, p.prog[k], sModel, qRow);
+    }
+
+    /* ---- task error (ControllerBase::computeDX) ---------------------------------------------- */
+    double ePos[3] = {0.0, 0.0, 0.0}, eRot[3] = {0.0, 0.0, 0.0};
+    if (hasXyz)
+    {
+      ePos[0] = xPos[0] - f.o[0];
+      ePos[1] = xPos[1] - f.o[1];
+      ePos[2] = xPos[2] - f.o[2];
+    }
+    if (hasAbc)
+    {
+      double Ad[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        Ad[i] = sAd[i * T + tid];
+      }
+      rotationTaskError(eRot, Ad, f.R);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+      dx[i] = xyzFirst ? ePos[i] : eRot[i];
+      if (NT == 2)
+      {
+        dx[3 + i] = xyzFirst ? eRot[i] : ePos[i];
+      }
+    }
+
+    /* ---- Jacobian columns in row order; A = J invWq J^T + lambda 1; r = dx - J g ------------- */
+    double A[NA], r[NX];
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+    {
+      A[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      r[i] = 0.0;
+    }
+    for (int c = 0; c < nc; ++c)
+    {
+      double ja[3] = {at(c, 0), at(c, 1), at(c, 2)};
+      double jt[3];
+      if (p.chainType[c] < 3)
+      {
+        const double d0 = f.o[0] - at(c, 3), d1 = f.o[1] - at(c, 4), d2 = f.o[2] - at(c, 5);
+        jt[0] = ja[1] * d2 - ja[2] * d1;
+        jt[1] = ja[2] * d0 - ja[0] * d2;
+        jt[2] = ja[0] * d1 - ja[1] * d0;
+      }
+      else
+      {
+        jt[0] = ja[0];
+        jt[1] = ja[1];
+        jt[2] = ja[2];
+        ja[0] = ja[1] = ja[2] = 0.0;
+      }
+      double u[NX];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        u[i] = xyzFirst ? jt[i] : ja[i];
+        if (NT == 2)
+        {
+          u[3 + i] = xyzFirst ? ja[i] : jt[i];
+        }
+      }
+      const double w = p.chainW[c];
+      const double g = w * (-(a.alpha * (p.chainGain[c] * (at(c, 6) - p.chainQ0[c]))));
+      at(c, 7) = g;
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        at(c, i) = u[i];
+        const double wu = w * u[i];
+#pragma unroll
+        for (int k = 0; k <= i; ++k)
+        {
+          A[i * (i + 1) / 2 + k] += u[k] * wu;
+        }
+        r[i] += u[i] * g;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      A[i * (i + 1) / 2 + i] += a.lambda;
+      r[i] = dx[i] - r[i];
+    }
+
+    double y[NX];
+    if (!choleskySolve<NX>(A, r, y, det))
+    {
+      /* singular: zero displacement, q untouched */
+      singular |= 1ull << it;
+      for (int c = 0; c < nc; ++c)
+      {
+        at(c, 7) = 0.0;
+      }
+      continue;
+    }
+
+    /* ---- dq = g + invWq J^T y; q += dq ----------------------------------------------------------- */
+    for (int c = 0; c < nc; ++c)
+    {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        sum += at(c, i) * y[i];
+      }
+      const double dqc = at(c, 7) + p.chainW[c] * sum;
+      at(c, 7) = dqc;
+      at(c, 6) += dqc;
+    }
+  }
+
+  /* ---- results ---------------------------------------------------------------------------------- */
+  const bool lastSingular = a.iters > 0 && ((singular >> (a.iters - 1)) & 1ull);
+  if (a.dq)
+  {
+    for (int j = 0; j < dof; ++j)
+    {
+      a.dq[s * dof + j] = 0.0;
+    }
+  }
+  for (int k = 0; k < p.hdr->nOther; ++k)
+  {
+    const int j = p.otherJoint[k];
+    double qj = qRow[j], step = 0.0;
+    for (int it = 0; it < a.iters; ++it)
+    {
+      step = 0.0;
+      if (!((singular >> it) & 1ull))
+      {
+        step = p.otherW[k] * (-(a.alpha * (p.otherGain[k] * (qj - p.otherQ0[k]))));
+        qj += step;
+      }
+    }
+    qRow[j] = qj;
+    if (a.dq)
+    {
+      a.dq[s * dof + j] = step;
+    }
+  }
+  for (int c = 0; c < nc; ++c)
+  {
+    qRow[p.chainJoint[c]] = at(c, 6);
+    if (a.dq)
+    {
+      a.dq[s * dof + p.chainJoint[c]] = (lastSingular || a.iters == 0) ? 0.0 : at(c, 7);
+    }
+  }
+  if (a.dx)
+  {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      a.dx[s * NX + i] = dx[i];
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = det;
+  }
+}
+
+template <int NX>
+static cudaError_t launchChainLoop(const IkArgs& a, int nc, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
+                           (size_t) (9 + 8 * nc) * RCSB_IK_LOOP_THREADS * sizeof(double);
+  if (smemBytes > 227 * 1024)
+  {
+    return cudaErrorInvalidValue;
+  }
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_LOOP_THREADS - 1) / RCSB_IK_LOOP_THREADS));
+  auto k = ikChainLoopKernel<NX>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smemBytes);
+  if (e != cudaSuccess)
+  {
+    return e;
+  }
+  k<<<grid, RCSB_IK_LOOP_THREADS, smemBytes, stream>>>(a, nc);
+  return cudaGetLastError();
+}
+
 template <int NC, int NX>
 static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
 {
@@ -1209,6 +1586,16 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
   if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
   {
     return nx == 3 ? launchChainNc<3>(*a, chainNc, stream) : launchChainNc<6>(*a, chainNc, stream);
+  }
+  if (chainNc > 8 && chainNc <= RCSB_IK_LOOP_MAX_NC && (nx == 3 || nx == 6))
+  {
+    const cudaError_t e = nx == 3 ? launchChainLoop<3>(*a, chainNc, stream)
+                                  : launchChainLoop<6>(*a, chainNc, stream);
+    if (e != cudaErrorInvalidValue)
+    {
+      return e;
+    }
+    cudaGetLastError();   /* does not fit in shared memory: general kernel */
   }
   if (nx <= 6 && nJ <= 8 && dof <= 8)
   {

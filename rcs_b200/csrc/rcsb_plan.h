@@ -147,7 +147,8 @@ typedef struct
   int offQ0;            /* double[nJ] */
   /*
    * Single-chain fast path (rcsb_ik.cu, ikChainKernel): all tasks sit on one effector whose
-   * backward joint chain has chainNc <= 8 unconstrained joints. The walk from the root to the
+   * backward joint chain has chainNc <= 32 unconstrained joints (<= 8: ikChainKernel, registers;
+   * 9..32: ikChainLoopKernel, shared memory). The walk from the root to the
    * effector is a straight-line program: per chain column c the steps progStart[c] ..
    * progStart[c + 1] (constant transforms and constrained joints) precede the column's own
    * joint motion; the steps progStart[chainNc] .. progStart[chainNc + 1] lead on to the

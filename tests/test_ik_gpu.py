@@ -234,3 +234,44 @@ def test_short_chains_on_the_humanoid(eff, kinds, refmod, cuda_device):
     m.ik_rmr(tasks, q3, x_des, iters=3)
     ok = cond < 1.0e4
     assert_step_close(q3[ok] - q0[ok], q3_ref[ok] - q0[ok], 3.0 * cond[ok], "q after 3 iterations")
+
+
+@pytest.mark.parametrize("general", [False, True], ids=["loop-kernel", "general-kernel"])
+def test_long_chain_on_the_humanoid(general, refmod, cuda_device, monkeypatch):
+    """RightHandTip: 13 Jacobian columns on the chain — more than ikChainKernel keeps in
+    registers; ikChainLoopKernel keeps the columns in shared memory."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
+    g, m, rik, tasks = _setup("humanoid", "RightHandTip", refmod, cuda_device)
+    q0, x_des = _targets(g, rik, 500, seed_first=3, perturb=0.05)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx")
+    cond = step_condition(rik, q0)
+    assert_step_close(out["dq"], dq_ref, cond, "dq")
+    assert_step_close(q - q0, q_ref - q0, cond, "q")
+    q5_ref, _, _, _ = rik.rmr(q0, x_des, iters=5)
+    q5 = q0.copy()
+    m.ik_rmr(tasks, q5, x_des, iters=5)
+    ok = cond < 1.0e4
+    assert_step_close((q5 - q0)[ok], (q5_ref - q0)[ok], 5.0 * cond[ok], "q after 5 iterations")
+
+
+def test_two_effectors_general_kernel(refmod, cuda_device):
+    """Both hands at once (nx = 12): task sets on several effectors take the general kernel."""
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    m = rcs_b200.Model(g, cuda_device)
+    names = [("XYZ", "RightHandTip"), ("ABC", "RightHandTip"), ("XYZ", "LeftHandTip"), ("ABC", "LeftHandTip")]
+    rik = refmod.RefIk(graph_file("humanoid"), names)
+    code = {"XYZ": TASK_XYZ, "ABC": TASK_ABC}
+    tasks = [(code[k], g.body_index(e)) for k, e in names]
+    q0, x_des = _targets(g, rik, 300, seed_first=8, perturb=0.05)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx")
+    _, J = rik.task_kinematics(q0)
+    A = np.einsum("nij,j,nkj->nik", J, rik.graph.inv_wq(), J) + 1.0e-8 * np.eye(J.shape[1])
+    cond = np.linalg.cond(A)
+    assert_step_close(out["dq"], dq_ref, cond, "dq")

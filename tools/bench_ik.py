@@ -33,11 +33,13 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", default="wam_arm")
+    ap.add_argument("--effector", default="BallTip")
     args = ap.parse_args()
 
-    g = rcs_b200.Graph(os.path.join(ROOT, "tests", "golden", "graphs", "wam_arm.xml"))
+    g = rcs_b200.Graph(os.path.join(ROOT, "tests", "golden", "graphs", args.graph + ".xml"))
     m = rcs_b200.Model(g, 0)
-    tip = g.body_index("BallTip")
+    tip = g.body_index(args.effector)
     tasks = [(TASK_XYZ, tip), (TASK_ABC, tip)]
     n = args.states
     lay = g.layout()
@@ -62,7 +64,7 @@ def main():
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     t = float(np.mean(ms))
-    print(json.dumps({"workload": f"wam_arm RMR IK XYZ+ABC, {args.iters} iterations", "targets": n,
+    print(json.dumps({"workload": f"{args.graph}/{args.effector} RMR IK XYZ+ABC, {args.iters} iterations", "targets": n,
                       "ms": t, "solves_per_s": n / (t * 1e-3),
                       "iterations_per_s": n * args.iters / (t * 1e-3),
                       "bytes_per_solve": 56 + 48 + 56 + 8,
