@@ -45,6 +45,16 @@ def test_fk_jacobians_kinetic_terms_match_golden(name, cuda_device):
     kt = m.kinetic_terms(q, qd)
     for k in ("M", "h", "Fg", "E"):
         assert_close(kt[k], z["kt_" + k], what=f"{name}:{k}")
+    cg = m.cog(q)
+    assert_close(cg["cog"], z["cog"], what=f"{name}:cog")
+    assert_close(cg["Jcog"], z["Jcog"], what=f"{name}:Jcog")
+    spec = [("POS" if k == 1 else "OMEGA", int(e), int(rb), int(rf)) for k, e, rb, rf in z["rel_spec"]]
+    assert_close(m.task_jacobians(q, spec), z["rel_J"], what=f"{name}: relative task Jacobians")
+    dd = m.direct_dynamics(q, qd, np.ascontiguousarray(z["dd_Fext"]), np.ascontiguousarray(z["dd_Fjnt"]))
+    cond = np.linalg.cond(z["kt_M"])
+    err = np.abs(dd["qdd"] - z["dd_qdd"]).max(axis=1)
+    tol = 1e-12 * np.maximum(1.0, cond / 100.0) * np.maximum(1.0, np.abs(z["dd_qdd"]).max(axis=1))
+    assert np.all(err <= tol), f"{name}: direct dynamics, worst err/tol {float((err / tol).max()):.2f}"
 
 
 @pytest.mark.parametrize("name", ["wam_arm", "humanoid"])

@@ -60,6 +60,24 @@ def test_cog_matches_golden(name):
     assert_close(jcog, z["Jcog"], what=f"{name}:Jcog")
 
 
+@pytest.mark.parametrize("name", GOLDEN)
+def test_relative_task_jacobians_match_golden(name):
+    z, o = golden(name), rcs_oracle.Oracle(layout(name))
+    spec = [("POS" if k == 1 else "OMEGA", int(e), int(rb), int(rf)) for k, e, rb, rf in z["rel_spec"]]
+    assert_close(o.task_jacobians(z["q"], spec), z["rel_J"], what=f"{name}: 3dPos / 3dOmega Jacobians")
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_direct_dynamics_matches_golden(name):
+    """The solve goes through M^-1: bar scaled by cond(M) per state (see tests/test_kinetic_gpu.py)."""
+    z, o = golden(name), rcs_oracle.Oracle(layout(name))
+    qdd, _ = o.direct_dynamics(z["q"], z["qd"], z["dd_Fext"], z["dd_Fjnt"])
+    cond = np.linalg.cond(z["kt_M"])
+    err = np.abs(qdd - z["dd_qdd"]).max(axis=1)
+    tol = 1e-12 * np.maximum(1.0, cond / 100.0) * np.maximum(1.0, np.abs(z["dd_qdd"]).max(axis=1))
+    assert np.all(err <= tol), float((err / tol).max())
+
+
 @pytest.mark.parametrize("name", ["wam_arm", "humanoid"])
 def test_ik_matches_golden(name):
     z, o = golden(name), rcs_oracle.Oracle(layout(name))

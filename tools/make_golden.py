@@ -44,7 +44,18 @@ def main():
         jac = g.fk_jacobians(q, eff, points=pts, want=("JT", "JR"))
         kt = g.kinetic_terms(q, qd)
         cog, jcog = g.cog(q)
+        # relative task Jacobians (RcsGraph_3dPosJacobian / 3dOmegaJacobian) and direct dynamics
+        a, b, c = eff[0], eff[-1], len(names) // 3
+        rel_spec = [("POS", a, -1, -1), ("POS", a, -1, c), ("POS", a, b, b), ("POS", a, b, c),
+                    ("POS", -1, b, c), ("OMEGA", a, -1, -1), ("OMEGA", a, b, b), ("OMEGA", a, b, c),
+                    ("OMEGA", a, -1, c), ("OMEGA", a, b, -1)]
+        rel = g.task_jacobians(q, rel_spec)
+        rng = np.random.default_rng(9)
+        f_ext, f_jnt = rng.normal(size=(n, g.nJ)), rng.normal(size=(n, g.nJ))
+        qdd, _ = g.direct_dynamics(q, qd, f_ext, f_jnt)
         out = dict(q=q, qd=qd, eff=np.array(eff), pts=pts, cog=cog, Jcog=jcog,
+                   rel_spec=np.array([[1 if k == "POS" else 2, e, rb, rf] for k, e, rb, rf in rel_spec]),
+                   rel_J=rel, dd_Fext=f_ext, dd_Fjnt=f_jnt, dd_qdd=qdd,
                    **{"fk_" + k: v for k, v in fk.items()},
                    **{"jac_" + k: v for k, v in jac.items()},
                    **{"kt_" + k: v for k, v in kt.items()})
