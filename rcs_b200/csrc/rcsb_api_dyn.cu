@@ -126,40 +126,25 @@ int buildKtPlan(RcsbModel* m)
   }
 
   /* shared-memory layout of the assembly kernel */
-  const int asmV = 16 * nJ;
-  const int asmRuns = 16 * nJ + 8;
-  const int runArea = RCSB_KT_LINK_REC * nRuns > nJ * nJ ? RCSB_KT_LINK_REC * nRuns : nJ * nJ;
-  const int asmRhs = asmRuns + ((runArea + 3) & ~3);
-  const int asmDoubles = asmRhs + nJ;
   const int recDoubles = (rec + 5 + 3) & ~3;
-  std::vector<unsigned short> recDst((size_t) recDoubles, (unsigned short) (asmV + 7));
-  for (int k = 0; k < nJ; ++k)
-  {
-    for (int t = 0; t < RCSB_KT_COL_REC; ++t)
-    {
-      recDst[(size_t) colRec[k] + t] = (unsigned short) (7 * k + t);
-    }
-  }
+  const int region0 = ((recDoubles > nJ * nJ ? recDoubles : nJ * nJ) + 3) & ~3;
+  const int asmS = region0;
+  const int asmF = asmS + ((7 * nJ + 3) & ~3);
+  const int asmTail = asmF + ((9 * nJ + 3) & ~3);
+  const int asmRhs = asmTail + 8;
+  const int asmDoubles = asmRhs + nJ;
   std::vector<int> linkHome((size_t) (nLinks > 0 ? nLinks : 1), -1), extraRuns;
   for (int r = 0; r < nRuns; ++r)
   {
-    for (int t = 0; t < RCSB_KT_LINK_REC; ++t)
-    {
-      recDst[(size_t) runRec[r] + t] = (unsigned short) (asmRuns + RCSB_KT_LINK_REC * r + t);
-    }
     if (linkHome[runLink[r]] < 0)
     {
-      linkHome[runLink[r]] = asmRuns + RCSB_KT_LINK_REC * r;
+      linkHome[runLink[r]] = runRec[r];
     }
     else
     {
-      extraRuns.push_back(asmRuns + RCSB_KT_LINK_REC * r);
+      extraRuns.push_back(runRec[r]);
       extraRuns.push_back(linkHome[runLink[r]]);
     }
-  }
-  for (int t = 0; t < 5; ++t)
-  {
-    recDst[(size_t) rec + t] = (unsigned short) (asmV + t);
   }
   std::vector<int> colHome((size_t) (nJ > 0 ? nJ : 1), 0);
   for (int k = 0; k < nJ; ++k)
@@ -175,10 +160,10 @@ int buildKtPlan(RcsbModel* m)
     {
       if (rel[(size_t) i * nJ + k] == 1)
       {
-        pairs.push_back(7 * i);
-        pairs.push_back(7 * nJ + 9 * k);
+        pairs.push_back(asmS + 7 * i);
+        pairs.push_back(asmF + 9 * k);
         pairs.push_back((i * nJ + k) | ((k * nJ + i) << 16));
-        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((7 * k) << 8));
+        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((asmS + 7 * k) << 8));
       }
     }
   }
@@ -201,10 +186,11 @@ int buildKtPlan(RcsbModel* m)
   ph.symmetric = symmetric ? 1 : 0;
   ph.recV = rec;
   ph.recDoubles = recDoubles;
-  ph.asmV = asmV;
-  ph.asmRuns = asmRuns;
-  ph.asmDoubles = asmDoubles;
+  ph.asmS = asmS;
+  ph.asmF = asmF;
+  ph.asmTail = asmTail;
   ph.asmRhs = asmRhs;
+  ph.asmDoubles = asmDoubles;
   ph.nExtraRuns = (int) extraRuns.size() / 2;
   int off = align16((int) sizeof(ph));
   auto place = [&](int& field, size_t bytes) {
@@ -222,7 +208,6 @@ int buildKtPlan(RcsbModel* m)
   place(ph.offRunLink, (size_t) nRuns * 4);
   place(ph.offRunRec, (size_t) nRuns * 4);
   place(ph.offPairs, pairs.size() * 4);
-  place(ph.offRecDst, recDst.size() * 2);
   place(ph.offLinkHome, linkHome.size() * 4);
   place(ph.offExtraRuns, extraRuns.size() * 4);
   place(ph.offColHome, colHome.size() * 4);
@@ -246,7 +231,6 @@ int buildKtPlan(RcsbModel* m)
   put(ph.offRunLink, runLink.data(), (size_t) nRuns * 4);
   put(ph.offRunRec, runRec.data(), (size_t) nRuns * 4);
   put(ph.offPairs, pairs.data(), pairs.size() * 4);
-  put(ph.offRecDst, recDst.data(), recDst.size() * 2);
   put(ph.offLinkHome, linkHome.data(), linkHome.size() * 4);
   put(ph.offExtraRuns, extraRuns.data(), extraRuns.size() * 4);
   put(ph.offColHome, colHome.data(), colHome.size() * 4);

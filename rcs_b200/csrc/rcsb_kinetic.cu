@@ -54,7 +54,6 @@ struct KtPlanView
   const int* runLink;
   const int* runRec;
   const int4* pairs;
-  const unsigned short* recDst;
   const int* linkHome;
   const int2* extraRuns;
   const int* colHome;
@@ -72,7 +71,6 @@ struct KtPlanView
     runLink = reinterpret_cast<const int*>(blob + hdr->offRunLink);
     runRec = reinterpret_cast<const int*>(blob + hdr->offRunRec);
     pairs = reinterpret_cast<const int4*>(blob + hdr->offPairs);
-    recDst = reinterpret_cast<const unsigned short*>(blob + hdr->offRecDst);
     linkHome = reinterpret_cast<const int*>(blob + hdr->offLinkHome);
     extraRuns = reinterpret_cast<const int2*>(blob + hdr->offExtraRuns);
     colHome = reinterpret_cast<const int*>(blob + hdr->offColHome);
@@ -121,6 +119,48 @@ __device__ __forceinline__ double pairing(bool isRot, const double a[3], const d
 /* kernel 1: depth-first walk, one thread per state                                            */
 /* ------------------------------------------------------------------------------------------ */
 
+/* One window of a warp to global memory: record r of state t sits at win[r * 33 + t] and goes
+ * to dst[t * recDoubles + r]. Kept out of line (it is called from many places of the walk) with
+ * explicit shared / global accesses: through a generic pointer the compiler would emit generic
+ * loads and 64-bit address arithmetic per element. */
+__device__ __noinline__ void flushWindow(const double* win, double* dst, int recDoubles, int nv,
+                                         int lane, int cnt)
+{
+  __syncwarp();
+  if (lane < cnt)
+  {
+    unsigned int src = (unsigned int) __cvta_generic_to_shared(win + lane * 33);
+    double* d = dst + lane;
+    const long step = recDoubles;
+    int t = 0;
+    for (; t + 4 <= nv; t += 4)
+    {
+      double v0, v1, v2, v3;
+      asm volatile("ld.shared.f64 %0, [%4];\n\t"
+                   "ld.shared.f64 %1, [%4+8];\n\t"
+                   "ld.shared.f64 %2, [%4+16];\n\t"
+                   "ld.shared.f64 %3, [%4+24];"
+                   : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3)
+                   : "r"(src));
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(d), "d"(v0) : "memory");
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + step), "d"(v1) : "memory");
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + 2 * step), "d"(v2) : "memory");
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + 3 * step), "d"(v3) : "memory");
+      src += 32;
+      d += 4 * step;
+    }
+    for (; t < nv; ++t)
+    {
+      double v;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(src));
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(d), "d"(v) : "memory");
+      src += 8;
+      d += step;
+    }
+  }
+  __syncwarp();
+}
+
 /* Streams the records of a warp's 32 states to global memory through a 32-record window in
  * shared memory (win[r * 33 + lane]): a full window leaves as one 256-byte row per state.
  * All calls are warp-uniform (the walk is the same for every state). */
@@ -133,28 +173,9 @@ struct RecordWriter
   int lane;
   int p;             /* records produced so far */
 
-  __device__ __noinline__ void flush(int base, int cnt)
+  __device__ __forceinline__ void flush(int base, int cnt)
   {
-    __syncwarp();
-    if (lane < cnt)
-    {
-      double* d = dst + base + lane;
-      const double* src = win + lane * 33;
-      int t = 0;
-      for (; t + 4 <= nv; t += 4)
-      {
-        const double v0 = src[t], v1 = src[t + 1], v2 = src[t + 2], v3 = src[t + 3];
-        d[(long) t * recDoubles] = v0;
-        d[(long) (t + 1) * recDoubles] = v1;
-        d[(long) (t + 2) * recDoubles] = v2;
-        d[(long) (t + 3) * recDoubles] = v3;
-      }
-      for (; t < nv; ++t)
-      {
-        d[(long) t * recDoubles] = src[t];
-      }
-    }
-    __syncwarp();
+    flushWindow(win, dst + base, recDoubles, nv, lane, cnt);
   }
 
   __device__ __forceinline__ void emit(double v)
@@ -610,8 +631,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   const int R = a.recDoubles;
   const bool sym = p.hdr->symmetric != 0;
   double* buf = sBuf + (long) grp * groupStride;   /* layout: RcsbKtPlanHeader, asm* fields */
-  double* fb = buf + 7 * nJ;                       /* 9 per column: p, L, L with I^T */
-  double* Ms = buf + p.hdr->asmRuns;               /* nJ x nJ, over the consumed runs */
+  double* scol = buf + p.hdr->asmS;                /* 7 per column: axis, origin, rate */
+  double* fb = buf + p.hdr->asmF;                  /* 9 per column: p, L, L with I^T */
+  double* tail = buf + p.hdr->asmTail;             /* V, m and m c of the bodies no joint moves */
+  double* Ms = buf;                                /* nJ x nJ, over the consumed record */
   double* rhs = buf + p.hdr->asmRhs;               /* nJ: right-hand side of the direct dynamics */
   const double grav = 9.81;
 
@@ -654,7 +677,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         const int e = gl + t * LPS;
         if (e < R)
         {
-          buf[p.recDst[e]] = nxt[t];
+          buf[e] = nxt[t];
         }
       }
       if (s + sStep < nGroupsTotal)
@@ -667,20 +690,32 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       const double* src = a.rec + sc * R;
       for (int e = gl; e < R; e += LPS)
       {
-        buf[p.recDst[e]] = src[e];
+        buf[e] = src[e];
       }
     }
     __syncwarp();
 
-    /* ---- composites in place: extra runs into their link, links into their ancestors
-     * (children have larger indices than their parents; element i stays with one lane) ---- */
+    /* ---- composites in place: extra runs into their link, links into their ancestors ------ */
+    if (gl < 5)
+    {
+      tail[gl] = buf[p.hdr->recV + gl];
+    }
+    if (p.hdr->nExtraRuns > 0)
+    {
+      for (int i = gl; i < RCSB_KT_LINK_REC; i += LPS)
+      {
+        for (int r = 0; r < p.hdr->nExtraRuns; ++r)
+        {
+          const int2 x = p.extraRuns[r];
+          buf[x.y + i] += buf[x.x + i];
+        }
+      }
+      __syncwarp();
+    }
+    /* links into their ancestors: children have larger indices than their parents, element i
+     * stays with one lane (measured: a level-parallel gather costs twice the instructions) */
     for (int i = gl; i < RCSB_KT_LINK_REC; i += LPS)
     {
-      for (int r = 0; r < p.hdr->nExtraRuns; ++r)
-      {
-        const int2 x = p.extraRuns[r];
-        buf[x.y + i] += buf[x.x + i];
-      }
       for (int l = nLinks - 1; l > 0; --l)
       {
         const int pl = p.linkParent[l];
@@ -695,7 +730,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     /* ---- per column: momentum of its composite under a unit joint rate, h, F_gravity ---- */
     for (int k = gl; k < nJ; k += LPS)
     {
-      const double* ja = buf + 7 * k;
+      const double* ja = buf + p.colRec[k];
       const double* cp = buf + p.colHome[k];
       const bool isRot = p.colIsRot[k] != 0;
       const double ax[3] = {ja[0], ja[1], ja[2]};
@@ -727,6 +762,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         Lt[1] = Lv[1];
         Lt[2] = Lv[2];
       }
+      double* sk = scol + 7 * k;
+      sk[0] = ax[0]; sk[1] = ax[1]; sk[2] = ax[2];
+      sk[3] = o[0]; sk[4] = o[1]; sk[5] = o[2];
+      sk[6] = ja[6];
       double* f = fb + 9 * k;
       f[0] = pv[0]; f[1] = pv[1]; f[2] = pv[2];
       f[3] = Lv[0]; f[4] = Lv[1]; f[5] = Lv[2];
@@ -781,7 +820,6 @@ ktAssembleKernel(const KtArgs a, int groupStride)
      * column k's composite under a unit joint rate ---------------------------------------- */
     if (a.cog || a.Jcog)
     {
-      const double* tail = buf + p.hdr->asmV;
       double mT = tail[1], mc0 = tail[2], mc1 = tail[3], mc2 = tail[4];
       for (int l = 0; l < nLinks; ++l)
       {
@@ -962,7 +1000,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
       if (gl == 0 && valid)
       {
-        a.E[s] = buf[p.hdr->asmV] + 0.5 * tk;
+        a.E[s] = tail[0] + 0.5 * tk;
       }
     }
     __syncwarp();

@@ -104,21 +104,22 @@ typedef struct
   int offRunLink;       /* int[nRuns] */
   int offRunRec;        /* int[nRuns] */
   /* assembly kernel: per-state shared-memory layout (doubles)
-   *   [0, 7 nJ)            column k at 7 k: axis, origin, rate
-   *   [7 nJ, 16 nJ)        column k at 7 nJ + 9 k: p, L, L with the transposed inertia
-   *   asmV                 the 5-double tail of the record (8 slots reserved)
-   *   [asmRuns, ...)       run r at asmRuns + 19 r; the first run of a link becomes the link's
-   *                        composite in place; later the same area holds the nJ x nJ matrix */
-  int asmV, asmRuns, asmDoubles;
-  int asmRhs;           /* nJ doubles: right-hand side / solution of the direct dynamics */
+   *   [0, max(recDoubles, nJ^2))  the record as the walk wrote it; the first run of a link
+   *                               becomes the link's composite in place; later the same area
+   *                               holds the nJ x nJ matrix
+   *   asmS + 7 k                  column k: axis, origin, rate (copied out of the record)
+   *   asmF + 9 k                  column k: p, L, L with the transposed inertia
+   *   asmTail                     copy of the record's 5-double tail (8 slots)
+   *   asmRhs                      nJ doubles: right-hand side / solution of the direct dynamics */
+  int asmS, asmF, asmTail, asmRhs, asmDoubles;
   int nExtraRuns;       /* runs that are not the first of their link */
-  int offRecDst;        /* unsigned short[recDoubles]: where each record element goes */
-  int offLinkHome;      /* int[nLinks]: shared-memory offset of the link's composite */
+  int offLinkHome;      /* int[nLinks]: offset of the link's composite (= its first run) */
   int offExtraRuns;     /* int2[nExtraRuns]: {offset of the run, offset of the link's composite} */
   int offColHome;       /* int[nJ]: composite of the column's link */
   int offPairs;         /* int4[nPairs], structurally non-zero upper-triangle entries (ancestor
-                           column i, column k): {7 i, 7 nJ + 9 k, (i nJ + k) | (k nJ + i) << 16,
-                           isRot(i) | (i == k) << 1 | (7 k) << 8} */
+                           column i, column k): {asmS + 7 i, asmF + 9 k,
+                           (i nJ + k) | (k nJ + i) << 16, isRot(i) | (i == k) << 1 | (asmS + 7 k) << 8} */
+  int pad0;
   int walkBytes;        /* leading part of the plan the walk kernel needs (header, bodyLink,
                            bodyEmit); multiple of 16 */
 } RcsbKtPlanHeader;
