@@ -648,12 +648,177 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
     }
   }
 
+  /* ---- several effectors, no couplings (ikMultiKernel) ------------------------------------ */
+  std::vector<int> jntSlot((size_t) dof, -1), slotTaskMask, taskEff((size_t) nTasks, 0),
+    bodyEffIdx((size_t) nb, -1);
+  int multiNu = 0, nEffs = 0;
+  if (chainNc == 0 && m->hdr.nCpl == 0 && nTasks <= 4)
+  {
+    for (int t = 0; t < nTasks; ++t)
+    {
+      if (bodyEffIdx[(size_t) body[t]] < 0)
+      {
+        bodyEffIdx[(size_t) body[t]] = nEffs++;
+      }
+      taskEff[(size_t) t] = bodyEffIdx[(size_t) body[t]];
+    }
+    for (int j = 0; j < dof; ++j)
+    {
+      if (needed[j])
+      {
+        jntSlot[(size_t) j] = multiNu++;
+      }
+    }
+    if (multiNu >= 1 && multiNu <= 48)
+    {
+      slotTaskMask.assign((size_t) multiNu, 0);
+      for (int t = 0; t < nTasks; ++t)
+      {
+        for (int j = bodyLastJnt[body[t]]; j >= 0; j = jntPrev[j])
+        {
+          if (jntJacobi[j] >= 0)
+          {
+            slotTaskMask[(size_t) jntSlot[(size_t) j]] |= 1 << t;
+          }
+        }
+      }
+      chainType.clear();
+      chainJoint.clear();
+      chainW.clear();
+      chainGain.clear();
+      chainQ0.clear();
+      otherJoint.clear();
+      otherW.clear();
+      otherGain.clear();
+      otherQ0.clear();
+      for (int j = 0; j < dof; ++j)
+      {
+        const int col = jntJacobi[j];
+        if (col < 0)
+        {
+          continue;
+        }
+        if (jntSlot[(size_t) j] >= 0)
+        {
+          chainType.push_back(jntType[j]);
+          chainJoint.push_back(j);
+          chainW.push_back(invWq[col]);
+          chainGain.push_back(jlGain[col]);
+          chainQ0.push_back(q0c[col]);
+        }
+        else
+        {
+          otherJoint.push_back(j);
+          otherW.push_back(invWq[col]);
+          otherGain.push_back(jlGain[col]);
+          otherQ0.push_back(q0c[col]);
+        }
+      }
+    }
+    else
+    {
+      multiNu = 0;
+    }
+  }
+  if (slotTaskMask.empty())
+  {
+    slotTaskMask.assign(1, 0);
+  }
+  /* pruned walk: ancestors-or-self of the effectors in depth-first order, with a frame-stack
+   * program of their own (a body whose parent is not the previously visited one reloads it) */
+  std::vector<int> walk;
+  int walkSlots = 0;
+  if (multiNu > 0)
+  {
+    std::vector<char> wanted((size_t) nb, 0);
+    for (int t = 0; t < nTasks; ++t)
+    {
+      for (int b = body[t]; b >= 0; b = bodyParent[b])
+      {
+        wanted[(size_t) b] = 1;
+      }
+    }
+    std::vector<int> list;
+    for (int b = 0; b < nb; ++b)
+    {
+      if (wanted[(size_t) b])
+      {
+        list.push_back(b);
+      }
+    }
+    std::vector<int> saved;   /* bodies whose frame is parked, innermost last */
+    auto isAncestor = [&](int anc, int b) {
+      for (b = bodyParent[b]; b >= 0; b = bodyParent[b])
+      {
+        if (b == anc)
+        {
+          return true;
+        }
+      }
+      return false;
+    };
+    for (size_t i = 0; i < list.size(); ++i)
+    {
+      const int b = list[i];
+      while (!saved.empty() && !isAncestor(saved.back(), b))
+      {
+        saved.pop_back();
+      }
+      int load = RCSB_LOAD_IDENT;
+      if (bodyParent[b] >= 0)
+      {
+        if (i > 0 && list[i - 1] == bodyParent[b])
+        {
+          load = RCSB_LOAD_CONT;
+        }
+        else
+        {
+          load = -3;
+          for (size_t k = 0; k < saved.size(); ++k)
+          {
+            if (saved[k] == bodyParent[b])
+            {
+              load = (int) k;
+            }
+          }
+        }
+      }
+      /* park the frame if a later body (not the next one) hangs under this one */
+      bool later = false;
+      for (size_t k = i + 2; k < list.size(); ++k)
+      {
+        later = later || bodyParent[list[k]] == b;
+      }
+      int save = -1;
+      if (later)
+      {
+        saved.push_back(b);
+        save = (int) saved.size() - 1;
+        walkSlots = (int) saved.size() > walkSlots ? (int) saved.size() : walkSlots;
+      }
+      const int w4[4] = {b, load, save, 0};
+      walk.insert(walk.end(), w4, w4 + 4);
+      if (load == -3 || walkSlots > RCSB_MAX_FRAME_SLOTS)
+      {
+        multiNu = 0;   /* should not happen; the general kernel takes over */
+      }
+    }
+  }
+  if (walk.empty())
+  {
+    walk.assign(4, 0);
+  }
+
   RcsbIkPlanHeader ph;
   memset(&ph, 0, sizeof(ph));
   ph.nTasks = nTasks;
   ph.nx = 3 * nTasks;
   ph.nJ = nJ;
   ph.nqr = nqr;
+  ph.multiNu = multiNu;
+  ph.nEffs = nEffs;
+  ph.nWalk = multiNu > 0 ? (int) walk.size() / 4 : 0;
+  ph.walkSlots = walkSlots;
   ph.chainNc = chainNc;
   ph.nOther = (int) otherJoint.size();
   int off = align16((int) sizeof(ph));
@@ -686,6 +851,11 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   place(ph.offOtherW, atLeast1(otherW.size()) * 8);
   place(ph.offOtherGain, atLeast1(otherGain.size()) * 8);
   place(ph.offOtherQ0, atLeast1(otherQ0.size()) * 8);
+  place(ph.offJntSlot, jntSlot.size() * 4);
+  place(ph.offSlotTaskMask, slotTaskMask.size() * 4);
+  place(ph.offTaskEff, taskEff.size() * 4);
+  place(ph.offBodyEffIdx, bodyEffIdx.size() * 4);
+  place(ph.offWalk, walk.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob((size_t) ph.totalBytes, 0);
@@ -723,6 +893,11 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   put(ph.offOtherW, otherW.data(), otherW.size() * 8);
   put(ph.offOtherGain, otherGain.data(), otherGain.size() * 8);
   put(ph.offOtherQ0, otherQ0.data(), otherQ0.size() * 8);
+  put(ph.offJntSlot, jntSlot.data(), jntSlot.size() * 4);
+  put(ph.offSlotTaskMask, slotTaskMask.data(), slotTaskMask.size() * 4);
+  put(ph.offTaskEff, taskEff.data(), taskEff.size() * 4);
+  put(ph.offBodyEffIdx, bodyEffIdx.data(), bodyEffIdx.size() * 4);
+  put(ph.offWalk, walk.data(), walk.size() * 4);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -731,6 +906,9 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
   dp.bytes = ph.totalBytes;
   dp.aux0 = ph.nx;
   dp.aux1 = ph.chainNc;
+  dp.nEff = ph.multiNu;
+  dp.nSel = ph.nEffs;
+  dp.nScrRows = nTasks | (walkSlots << 8);
   auto ins = m->ikPlans.emplace(key, dp);
   *out = &ins.first->second;
   return RCSB_OK;
@@ -756,9 +934,11 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
   a.det = det;
   RCSB_CUDA(cudaSetDevice(m->device));
   const char* noFast = getenv("RCSB_IK_GENERAL");   /* force the general kernel (tests) */
-  const int chainNc = (noFast && noFast[0] == '1') || iters > 64 ? 0 : plan->aux1;
+  const bool general = (noFast && noFast[0] == '1') || iters > 64;
+  const int chainNc = general ? 0 : plan->aux1;
+  const int multiNu = general ? 0 : plan->nEff;
   cudaError_t e = rcsb_launch_ik(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, chainNc,
-                                 stream);
+                                 multiNu, plan->nSel | ((plan->nScrRows >> 8) << 16), plan->nScrRows & 0xff, stream);
   if (e == cudaErrorInvalidValue)
   {
     cudaGetLastError();

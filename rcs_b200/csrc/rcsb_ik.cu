@@ -53,6 +53,11 @@ struct IkPlanView
   const double* q0;
   const int* colRed;
   const int* colCpl;
+  const int* jntSlot;
+  const int* slotTaskMask;
+  const int* taskEff;
+  const int* bodyEffIdx;
+  const int4* walk;
   const int* progStart;
   const int4* prog;
   const int* chainType;
@@ -68,6 +73,11 @@ struct IkPlanView
   __device__ __forceinline__ void bind(const char* blob)
   {
     hdr = reinterpret_cast<const RcsbIkPlanHeader*>(blob);
+    jntSlot = reinterpret_cast<const int*>(blob + hdr->offJntSlot);
+    slotTaskMask = reinterpret_cast<const int*>(blob + hdr->offSlotTaskMask);
+    taskEff = reinterpret_cast<const int*>(blob + hdr->offTaskEff);
+    bodyEffIdx = reinterpret_cast<const int*>(blob + hdr->offBodyEffIdx);
+    walk = reinterpret_cast<const int4*>(blob + hdr->offWalk);
     colRed = reinterpret_cast<const int*>(blob + hdr->offColRed);
     colCpl = reinterpret_cast<const int*>(blob + hdr->offColCpl);
     progStart = reinterpret_cast<const int*>(blob + hdr->offProgStart);
@@ -1511,6 +1521,403 @@ static cudaError_t launchChainLoop(const IkArgs& a, int nc, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+/*
+ * Tasks on several effectors (no coupled joints), e.g. both hands of a humanoid: the step of
+ * the chain kernels over the union of the tasks' chain joints. Only the bodies above some
+ * effector are walked (pruned depth-first list with its own frame-stack program); per union slot the joint axis / origin / value / step live in shared
+ * memory [slot][element][thread], the effector frames and desired rotations likewise; the
+ * NX x NX system stays in registers. A slot contributes to the rows of the tasks whose chain
+ * it lies on (slotTaskMask).
+ */
+#define RCSB_IK_MULTI_THREADS 64
+template <int NX, int NSLOTS>
+__global__ void __launch_bounds__(RCSB_IK_MULTI_THREADS)
+ikMultiKernel(const IkArgs a, int nU, int nEffs)
+{
+  extern __shared__ __align__(16) char smem[];
+  constexpr int T = RCSB_IK_MULTI_THREADS;
+  constexpr int NT = NX / 3;
+  constexpr int NA = NX * (NX + 1) / 2;
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [NT][9][T] desired rotations */
+  double* sEff = sAd + NT * 9 * T;                                /* [nEffs][12][T] effector frames */
+  double* sCol = sEff + nEffs * 12 * T;                           /* [nU][8][T] */
+  stageBlob(sModel, a.model, a.modelBytes);
+  stageBlob(sPlan, a.plan, a.planBytes);
+  __syncthreads();
+
+  ModelView m;
+  m.bind(sModel);
+  IkPlanView p;
+  p.bind(sPlan);
+
+  const int tid = threadIdx.x;
+  const long s = (long) blockIdx.x * T + tid;
+  if (s >= a.N)
+  {
+    return;
+  }
+  const int dof = m.hdr->dof;
+  double* qRow = a.q + s * dof;
+  const double* xd = a.xDes + s * NX;
+  double* col = sCol + tid;
+  double* eff = sEff + tid;
+  auto at = [&](int c, int i) -> double& { return col[(c * 8 + i) * T]; };
+
+  for (int c = 0; c < nU; ++c)
+  {
+    at(c, 6) = qRow[p.chainJoint[c]];
+    at(c, 7) = 0.0;
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+  {
+    if (p.taskKind[t] == RCSB_TASK_ABC)
+    {
+      const double ea[3] = {xd[3 * t], xd[3 * t + 1], xd[3 * t + 2]};
+      double Ad[9];
+      fromEuler(Ad, ea);
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        sAd[(t * 9 + i) * T + tid] = Ad[i];
+      }
+    }
+  }
+
+  double dx[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+    dx[i] = 0.0;
+  }
+  double det = 0.0;
+  unsigned long long singular = 0ull;
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
+
+  /* column of the stacked task Jacobian for union slot c (rows of tasks off its chain are 0) */
+  auto column = [&](int c, double (&u)[NX]) {
+    const int mask = p.slotTaskMask[c];
+    const bool isRot = p.chainType[c] < 3;
+    const double ax[3] = {at(c, 0), at(c, 1), at(c, 2)};
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+    {
+      double v[3] = {0.0, 0.0, 0.0};
+      if ((mask >> t) & 1)
+      {
+        if (p.taskKind[t] == RCSB_TASK_XYZ)
+        {
+          if (isRot)
+          {
+            const double* e = eff + p.taskEff[t] * 12 * T;
+            const double d0 = e[0] - at(c, 3), d1 = e[T] - at(c, 4), d2 = e[2 * T] - at(c, 5);
+            v[0] = ax[1] * d2 - ax[2] * d1;
+            v[1] = ax[2] * d0 - ax[0] * d2;
+            v[2] = ax[0] * d1 - ax[1] * d0;
+          }
+          else
+          {
+            v[0] = ax[0];
+            v[1] = ax[1];
+            v[2] = ax[2];
+          }
+        }
+        else if (isRot)
+        {
+          v[0] = ax[0];
+          v[1] = ax[1];
+          v[2] = ax[2];
+        }
+      }
+      u[3 * t] = v[0];
+      u[3 * t + 1] = v[1];
+      u[3 * t + 2] = v[2];
+    }
+  };
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    /* ---- forward kinematics (RcsGraph_setState) ------------------------------------------ */
+    Frame f;
+    setIdentity(f);
+    for (int wi = 0; wi < p.hdr->nWalk; ++wi)
+    {
+      const int4 wd = p.walk[wi];
+      const int b = wd.x;
+      const int ld = wd.y;
+      const int bflags = m.bodyFlags[b];
+      if (ld == RCSB_LOAD_IDENT)
+      {
+        setIdentity(f);
+      }
+      else if (NSLOTS > 0 && ld >= 0)
+      {
+        const double* sp = stk + ld * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          f.o[i] = sp[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          f.R[i] = sp[3 + i];
+        }
+      }
+      const int j0 = m.bodyJntStart[b];
+      const int j1 = j0 + m.bodyJntCount[b];
+      for (int j = j0; j < j1; ++j)
+      {
+        const int jf = m.jntFlags[j];
+        if (jf & RCSB_JF_HAS_AJP)
+        {
+          applyRelF(f, m.jntAJP + 12 * j, jf);
+        }
+        const int slot = p.jntSlot[j];
+        const double qj = slot >= 0 ? at(slot, 6) : qRow[j];
+        const int dir = m.jntType[j] % 3;
+        double ax[3];
+        if (jf & RCSB_JF_ROT)
+        {
+          double sn, cs;
+          sincos(qj, &sn, &cs);
+          rotateAboutAxis(f, dir, sn, cs);
+          axisOf(f, dir, ax);
+        }
+        else
+        {
+          axisOf(f, dir, ax);
+          f.o[0] += qj * ax[0];
+          f.o[1] += qj * ax[1];
+          f.o[2] += qj * ax[2];
+        }
+        if (slot >= 0)
+        {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            at(slot, i) = ax[i];
+            at(slot, 3 + i) = f.o[i];
+          }
+        }
+      }
+      if (bflags & RCSB_BF_HAS_ABP)
+      {
+        applyRelF(f, m.bodyABP + 12 * b, bflags);
+      }
+      if (NSLOTS > 0)
+      {
+        const int sv = wd.z;
+        if (sv >= 0)
+        {
+          double* sp = stk + sv * 12;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            sp[i] = f.o[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+          {
+            sp[3 + i] = f.R[i];
+          }
+        }
+      }
+      const int ei = p.bodyEffIdx[b];
+      if (ei >= 0)
+      {
+        double* e = eff + ei * 12 * T;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          e[i * T] = f.o[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          e[(3 + i) * T] = f.R[i];
+        }
+      }
+    }
+
+    /* ---- task errors (ControllerBase::computeDX) -------------------------------------------- */
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+    {
+      const double* e = eff + p.taskEff[t] * 12 * T;
+      if (p.taskKind[t] == RCSB_TASK_XYZ)
+      {
+        dx[3 * t] = xd[3 * t] - e[0];
+        dx[3 * t + 1] = xd[3 * t + 1] - e[T];
+        dx[3 * t + 2] = xd[3 * t + 2] - e[2 * T];
+      }
+      else
+      {
+        double Ad[9], Ac[9], er[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          Ad[i] = sAd[(t * 9 + i) * T + tid];
+          Ac[i] = e[(3 + i) * T];
+        }
+        rotationTaskError(er, Ad, Ac);
+        dx[3 * t] = er[0];
+        dx[3 * t + 1] = er[1];
+        dx[3 * t + 2] = er[2];
+      }
+    }
+
+    /* ---- A = J invWq J^T + lambda 1, r = dx - J g ---------------------------------------------- */
+    double A[NA], r[NX];
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+    {
+      A[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      r[i] = 0.0;
+    }
+    for (int c = 0; c < nU; ++c)
+    {
+      double u[NX];
+      column(c, u);
+      const double w = p.chainW[c];
+      const double g = w * (-(a.alpha * (p.chainGain[c] * (at(c, 6) - p.chainQ0[c]))));
+      at(c, 7) = g;
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        const double wu = w * u[i];
+#pragma unroll
+        for (int k = 0; k <= i; ++k)
+        {
+          A[i * (i + 1) / 2 + k] += u[k] * wu;
+        }
+        r[i] += u[i] * g;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      A[i * (i + 1) / 2 + i] += a.lambda;
+      r[i] = dx[i] - r[i];
+    }
+
+    double y[NX];
+    if (!choleskySolve<NX>(A, r, y, det))
+    {
+      singular |= 1ull << it;
+      for (int c = 0; c < nU; ++c)
+      {
+        at(c, 7) = 0.0;
+      }
+      continue;
+    }
+
+    for (int c = 0; c < nU; ++c)
+    {
+      double u[NX];
+      column(c, u);
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        sum += u[i] * y[i];
+      }
+      const double dqc = at(c, 7) + p.chainW[c] * sum;
+      at(c, 7) = dqc;
+      at(c, 6) += dqc;
+    }
+  }
+
+  /* ---- results ---------------------------------------------------------------------------------- */
+  const bool lastSingular = a.iters > 0 && ((singular >> (a.iters - 1)) & 1ull);
+  if (a.dq)
+  {
+    for (int j = 0; j < dof; ++j)
+    {
+      a.dq[s * dof + j] = 0.0;
+    }
+  }
+  for (int k = 0; k < p.hdr->nOther; ++k)
+  {
+    const int j = p.otherJoint[k];
+    double qj = qRow[j], step = 0.0;
+    for (int it = 0; it < a.iters; ++it)
+    {
+      step = 0.0;
+      if (!((singular >> it) & 1ull))
+      {
+        step = p.otherW[k] * (-(a.alpha * (p.otherGain[k] * (qj - p.otherQ0[k]))));
+        qj += step;
+      }
+    }
+    qRow[j] = qj;
+    if (a.dq)
+    {
+      a.dq[s * dof + j] = step;
+    }
+  }
+  for (int c = 0; c < nU; ++c)
+  {
+    qRow[p.chainJoint[c]] = at(c, 6);
+    if (a.dq)
+    {
+      a.dq[s * dof + p.chainJoint[c]] = (lastSingular || a.iters == 0) ? 0.0 : at(c, 7);
+    }
+  }
+  if (a.dx)
+  {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+    {
+      a.dx[s * NX + i] = dx[i];
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = det;
+  }
+}
+
+template <int NX>
+static cudaError_t launchMulti(const IkArgs& a, int nSlots, int nU, int nEffs, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
+                           (size_t) ((NX / 3) * 9 + nEffs * 12 + nU * 8) * RCSB_IK_MULTI_THREADS *
+                             sizeof(double);
+  if (smemBytes > 227 * 1024)
+  {
+    return cudaErrorInvalidValue;
+  }
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_MULTI_THREADS - 1) / RCSB_IK_MULTI_THREADS));
+#define RCSB_LAUNCH(NS)                                                                        \
+  {                                                                                            \
+    auto k = ikMultiKernel<NX, NS>;                                                            \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, RCSB_IK_MULTI_THREADS, smemBytes, stream>>>(a, nU, nEffs);                       \
+    return cudaGetLastError();                                                                 \
+  }
+  if (nSlots <= 0)
+  {
+    RCSB_LAUNCH(0)
+  }
+  else
+  {
+    RCSB_LAUNCH(RCSB_MAX_FRAME_SLOTS)
+  }
+#undef RCSB_LAUNCH
+}
+
 template <int NC, int NX>
 static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
 {
@@ -1576,7 +1983,8 @@ static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
 }   // namespace rcsb
 
 extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
-                                      int chainNc, cudaStream_t stream)
+                                      int chainNc, int multiNu, int nEffs, int nTasks,
+                                      cudaStream_t stream)
 {
   using namespace rcsb;
   if (a->N <= 0)
@@ -1596,6 +2004,23 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
       return e;
     }
     cudaGetLastError();   /* does not fit in shared memory: general kernel */
+  }
+  if (multiNu > 0 && nx == 3 * nTasks && nTasks >= 1 && nTasks <= 4)
+  {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (nTasks)
+    {
+      /* nEffs carries the frame-stack depth of the pruned walk in its upper half */
+      case 1: e = launchMulti<3>(*a, nEffs >> 16, multiNu, nEffs & 0xffff, stream); break;
+      case 2: e = launchMulti<6>(*a, nEffs >> 16, multiNu, nEffs & 0xffff, stream); break;
+      case 3: e = launchMulti<9>(*a, nEffs >> 16, multiNu, nEffs & 0xffff, stream); break;
+      default: e = launchMulti<12>(*a, nEffs >> 16, multiNu, nEffs & 0xffff, stream); break;
+    }
+    if (e != cudaErrorInvalidValue)
+    {
+      return e;
+    }
+    cudaGetLastError();
   }
   if (nx <= 6 && nJ <= 8 && dof <= 8)
   {

@@ -86,7 +86,7 @@ cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cuda
 cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int asmDoubles, int smCount,
                            cudaStream_t stream);
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
-                           cudaStream_t stream);
+                           int multiNu, int nEffs, int nTasks, cudaStream_t stream);
 }
 
 #endif

@@ -174,6 +174,22 @@ typedef struct
   int offOtherW;        /* double[nOther] */
   int offOtherGain;     /* double[nOther] */
   int offOtherQ0;       /* double[nOther] */
+  /*
+   * Several effectors without coupled joints (ikMultiKernel): the union of the tasks' chain
+   * joints gets multiNu slots (ascending Jacobian column) described by the chain* arrays above
+   * (type, jointIndex, invWq, joint-limit gain, q0); the other* arrays list the remaining
+   * unconstrained joints. multiNu == 0: not eligible.
+   */
+  int multiNu;
+  int nEffs;            /* distinct effector bodies */
+  int offJntSlot;       /* int[dof]: slot of the joint, -1 = not on any task's chain */
+  int offSlotTaskMask;  /* int[multiNu]: bit t set if the slot lies on the chain of task t */
+  int offTaskEff;       /* int[nTasks]: effector index of the task */
+  int offBodyEffIdx;    /* int[nb]: effector index of the body, -1 = none */
+  /* pruned walk of ikMultiKernel: only the bodies above some effector, depth first */
+  int nWalk;
+  int walkSlots;        /* frame-stack slots the pruned walk needs */
+  int offWalk;          /* int4[nWalk]: {body, load (RCSB_LOAD_* or slot), save slot or -1, 0} */
   int pad;
 } RcsbIkPlanHeader;
 

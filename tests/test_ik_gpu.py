@@ -258,11 +258,19 @@ def test_long_chain_on_the_humanoid(general, refmod, cuda_device, monkeypatch):
     assert_step_close((q5 - q0)[ok], (q5_ref - q0)[ok], 5.0 * cond[ok], "q after 5 iterations")
 
 
-def test_two_effectors_general_kernel(refmod, cuda_device):
-    """Both hands at once (nx = 12): task sets on several effectors take the general kernel."""
+@pytest.mark.parametrize("general", [False, True], ids=["multi-kernel", "general-kernel"])
+@pytest.mark.parametrize("names", [
+    [("XYZ", "RightHandTip"), ("ABC", "RightHandTip"), ("XYZ", "LeftHandTip"), ("ABC", "LeftHandTip")],
+    [("XYZ", "RightHandTip"), ("XYZ", "LeftHandTip"), ("ABC", "Helmet")],
+    [("ABC", "FootL"), ("XYZ", "FootR")],
+], ids=["both-hands-12", "hands-head-9", "feet-6"])
+def test_several_effectors(names, general, refmod, cuda_device, monkeypatch):
+    """Task sets on several effectors (nx = 6 .. 12): ikMultiKernel over the union of the chains,
+    or the general kernel (RCSB_IK_GENERAL=1); both against the reference."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
     g = rcs_b200.Graph(graph_file("humanoid"))
     m = rcs_b200.Model(g, cuda_device)
-    names = [("XYZ", "RightHandTip"), ("ABC", "RightHandTip"), ("XYZ", "LeftHandTip"), ("ABC", "LeftHandTip")]
     rik = refmod.RefIk(graph_file("humanoid"), names)
     code = {"XYZ": TASK_XYZ, "ABC": TASK_ABC}
     tasks = [(code[k], g.body_index(e)) for k, e in names]
@@ -275,3 +283,9 @@ def test_two_effectors_general_kernel(refmod, cuda_device):
     A = np.einsum("nij,j,nkj->nik", J, rik.graph.inv_wq(), J) + 1.0e-8 * np.eye(J.shape[1])
     cond = np.linalg.cond(A)
     assert_step_close(out["dq"], dq_ref, cond, "dq")
+    assert_step_close(q - q0, q_ref - q0, cond, "q")
+    q4_ref, _, _, _ = rik.rmr(q0, x_des, iters=4)
+    q4 = q0.copy()
+    m.ik_rmr(tasks, q4, x_des, iters=4)
+    ok = cond < 1.0e4
+    assert_step_close((q4 - q0)[ok], (q4_ref - q0)[ok], 4.0 * cond[ok], "q after 4 iterations")

@@ -35,17 +35,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--graph", default="wam_arm")
     ap.add_argument("--effector", default="BallTip")
+    ap.add_argument("--effector2", default=None, help="second effector (XYZ+ABC as well): nx = 12")
     args = ap.parse_args()
 
     g = rcs_b200.Graph(os.path.join(ROOT, "tests", "golden", "graphs", args.graph + ".xml"))
     m = rcs_b200.Model(g, 0)
     tip = g.body_index(args.effector)
     tasks = [(TASK_XYZ, tip), (TASK_ABC, tip)]
+    effs = [tip]
+    if args.effector2:
+        tip2 = g.body_index(args.effector2)
+        tasks += [(TASK_XYZ, tip2), (TASK_ABC, tip2)]
+        effs.append(tip2)
     n = args.states
     lay = g.layout()
     q_goal = torch.from_numpy(workload.sample_states(lay, n, first=1 << 24, margin=0.2)).cuda()
-    fk = m.fk(q_goal, bodies=[tip])["A_BI"][:, 0]
-    x_des = torch.cat([fk[:, :3], euler_xyz(fk[:, 3:])], dim=1).contiguous()
+    frames = m.fk(q_goal, bodies=effs)["A_BI"]
+    x_des = torch.cat([torch.cat([frames[:, i, :3], euler_xyz(frames[:, i, 3:])], dim=1)
+                       for i in range(len(effs))], dim=1).contiguous()
     u = torch.from_numpy(workload.uniform01(workload.SEED, 0, n, g.dof, stream=7)).cuda()
     q_start = (q_goal + 0.1 * (2.0 * u - 1.0)).contiguous()
     q = q_start.clone()
@@ -64,7 +71,7 @@ def main():
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     t = float(np.mean(ms))
-    print(json.dumps({"workload": f"{args.graph}/{args.effector} RMR IK XYZ+ABC, {args.iters} iterations", "targets": n,
+    print(json.dumps({"workload": f"{args.graph}/{args.effector}{'+' + args.effector2 if args.effector2 else ''} RMR IK XYZ+ABC, {args.iters} iterations", "targets": n,
                       "ms": t, "solves_per_s": n / (t * 1e-3),
                       "iterations_per_s": n * args.iters / (t * 1e-3),
                       "bytes_per_solve": 56 + 48 + 56 + 8,
