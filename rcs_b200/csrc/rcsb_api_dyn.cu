@@ -127,12 +127,6 @@ int buildKtPlan(RcsbModel* m)
 
   /* shared-memory layout of the assembly kernel */
   const int recDoubles = (rec + 5 + 3) & ~3;
-  const int region0 = ((recDoubles > nJ * nJ ? recDoubles : nJ * nJ) + 3) & ~3;
-  const int asmS = region0;
-  const int asmF = asmS + ((7 * nJ + 3) & ~3);
-  const int asmTail = asmF + ((9 * nJ + 3) & ~3);
-  const int asmRhs = asmTail + 8;
-  const int asmDoubles = asmRhs + nJ;
   std::vector<int> linkHome((size_t) (nLinks > 0 ? nLinks : 1), -1), extraRuns;
   for (int r = 0; r < nRuns; ++r)
   {
@@ -160,10 +154,10 @@ int buildKtPlan(RcsbModel* m)
     {
       if (rel[(size_t) i * nJ + k] == 1)
       {
-        pairs.push_back(asmS + 7 * i);
-        pairs.push_back(asmF + 9 * k);
+        pairs.push_back(7 * i);
+        pairs.push_back(9 * k);
         pairs.push_back((i * nJ + k) | ((k * nJ + i) << 16));
-        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((asmS + 7 * k) << 8));
+        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((7 * k) << 8));
       }
     }
   }
@@ -186,11 +180,6 @@ int buildKtPlan(RcsbModel* m)
   ph.symmetric = symmetric ? 1 : 0;
   ph.recV = rec;
   ph.recDoubles = recDoubles;
-  ph.asmS = asmS;
-  ph.asmF = asmF;
-  ph.asmTail = asmTail;
-  ph.asmRhs = asmRhs;
-  ph.asmDoubles = asmDoubles;
   ph.nExtraRuns = (int) extraRuns.size() / 2;
   int off = align16((int) sizeof(ph));
   auto place = [&](int& field, size_t bytes) {
@@ -240,7 +229,7 @@ int buildKtPlan(RcsbModel* m)
   RCSB_CUDA(cudaMemcpy(m->ktPlan.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   m->ktPlan.bytes = ph.totalBytes;
   m->ktPlan.aux0 = ph.recDoubles;
-  m->ktPlan.aux1 = ph.asmDoubles;
+  m->ktPlan.aux1 = nJ;
   m->ktPlan.nScrRows = ph.walkBytes;
   m->ktPlanBuilt = true;
   return RCSB_OK;
@@ -318,6 +307,7 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     a.Fext = x.Fext ? x.Fext + s0 * nJ : nullptr;
     a.Fjnt = x.Fjnt ? x.Fjnt + s0 * nJ : nullptr;
     a.qdd = x.qdd ? x.qdd + s0 * nJ : nullptr;
+    a.stageM = x.qdd ? 1 : 0;   /* the Cholesky solve of the direct dynamics works on the staged M */
     a.rec = m->ktScratch[ws];
     a.recDoubles = recDoubles;
     RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, m->ktPlan.aux1, m->smCount, stream));

@@ -59,6 +59,7 @@ struct KtArgs
   double* rec;         /* N x recDoubles per-state records (walk -> assembly) */
   int recDoubles;
   int planWalkBytes;   /* leading part of the plan staged by the walk kernel */
+  int stageM;          /* assembly: stage M in shared memory (needed by the direct dynamics) */
 };
 
 struct IkArgs
@@ -83,7 +84,7 @@ struct IkArgs
 extern "C" {
 cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cudaStream_t stream);
 /* enqueues the walk kernel and the assembly kernel (2 launches) */
-cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int asmDoubles, int smCount,
+cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nJ2, int smCount,
                            cudaStream_t stream);
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            int multiNu, int nEffs, int nTasks, cudaStream_t stream);

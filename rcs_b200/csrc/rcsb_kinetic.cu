@@ -631,11 +631,13 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   const int R = a.recDoubles;
   const bool sym = p.hdr->symmetric != 0;
   double* buf = sBuf + (long) grp * groupStride;   /* layout: RcsbKtPlanHeader, asm* fields */
-  double* scol = buf + p.hdr->asmS;                /* 7 per column: axis, origin, rate */
-  double* fb = buf + p.hdr->asmF;                  /* 9 per column: p, L, L with I^T */
-  double* tail = buf + p.hdr->asmTail;             /* V, m and m c of the bodies no joint moves */
-  double* Ms = buf;                                /* nJ x nJ, over the consumed record */
-  double* rhs = buf + p.hdr->asmRhs;               /* nJ: right-hand side of the direct dynamics */
+  const RcsbKtAsmLayout lay = rcsbKtAsmLayout(R, nJ, a.stageM);
+  double* scol = buf + lay.S;                      /* 7 per column: axis, origin, rate */
+  double* fb = buf + lay.F;                        /* 9 per column: p, L, L with I^T */
+  double* tail = buf + lay.tail;                   /* V, m and m c of the bodies no joint moves */
+  double* Ms = buf;                                /* nJ x nJ, over the consumed record (stageM) */
+  double* rhs = buf + lay.rhs;                     /* nJ: right-hand side of the direct dynamics */
+  const bool stage = a.stageM != 0;
   const double grav = 9.81;
 
   /* The record of the group's next state is fetched into registers while the current state is
@@ -858,7 +860,8 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     const bool wantM = a.M || a.qdd;
     if (wantM || (a.E && VEL))
     {
-      if (wantM)
+      double* Mg = (a.M && valid) ? a.M + s * nJ * nJ : nullptr;
+      if (stage)
       {
         for (int e = gl; e < nJ * nJ; e += LPS)
         {
@@ -866,12 +869,26 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         }
         __syncwarp();
       }
+      else
+      {
+        /* no staging: zeros straight to global memory (coalesced), the non-zero pairs follow
+         * after the barrier, which orders the two stores to the same address; L2 merges them.
+         * The barrier is taken by every group of the warp, valid state or not. */
+        if (Mg)
+        {
+          for (int e = gl; e < nJ * nJ; e += LPS)
+          {
+            Mg[e] = 0.0;
+          }
+        }
+        __syncwarp();
+      }
       const int nPairs = p.hdr->nPairs;
       for (int e = gl; e < nPairs; e += LPS)
       {
         const int4 pr = p.pairs[e];
-        const double* ji = buf + pr.x;
-        const double* fk = buf + pr.y;
+        const double* ji = scol + pr.x;
+        const double* fk = fb + pr.y;
         const bool iRot = (pr.w & 1) != 0;
         const bool diag = (pr.w & 2) != 0;
         const double ai[3] = {ji[0], ji[1], ji[2]};
@@ -885,27 +902,31 @@ ktAssembleKernel(const KtArgs a, int groupStride)
           const double Lkt[3] = {fk[6], fk[7], fk[8]};
           lower = pairing(iRot, ai, oi, pk, Lkt);
         }
-        if (wantM)
+        if (stage)
         {
           Ms[pr.z & 0xffff] = upper;
           Ms[pr.z >> 16] = lower;
         }
+        else if (Mg)
+        {
+          Mg[pr.z & 0xffff] = upper;
+          Mg[pr.z >> 16] = lower;
+        }
         if (VEL)
         {
-          const double qq = ji[6] * buf[(pr.w >> 8) + 6];
+          const double qq = ji[6] * scol[(pr.w >> 8) + 6];
           tk += diag ? qq * upper : qq * (upper + lower);
         }
       }
-      if (wantM)
+      if (stage)
       {
         __syncwarp();
-      }
-      if (a.M && valid)
-      {
-        double* dst = a.M + s * nJ * nJ;
-        for (int e = gl; e < nJ * nJ; e += LPS)
+        if (Mg)
         {
-          dst[e] = Ms[e];
+          for (int e = gl; e < nJ * nJ; e += LPS)
+          {
+            Mg[e] = Ms[e];
+          }
         }
       }
     }
@@ -917,8 +938,9 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     if (a.qdd)
     {
       __syncwarp();
+      /* no early exit: several groups share a warp and its barriers */
       bool ok = true;
-      for (int k = 0; k < nJ && ok; ++k)
+      for (int k = 0; k < nJ; ++k)
       {
         /* diagonal (every lane computes it: no broadcast needed) */
         double d = 0.0;
@@ -928,8 +950,9 @@ ktAssembleKernel(const KtArgs a, int groupStride)
           d += l * l;
         }
         const double piv = Ms[k * nJ + k] - d;
-        ok = piv > 0.0;
-        const double lkk = sqrt(ok ? piv : 1.0);
+        const bool good = piv > 0.0;
+        ok = ok && good;
+        const double lkk = sqrt(good ? piv : 1.0);
         __syncwarp();
         if (gl == 0)
         {
@@ -946,10 +969,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         }
         __syncwarp();
       }
-      if (ok)
       {
         /* forward solve L z = b, backward solve L^T x = z (lane 0 holds the running
-         * element; the other lanes update the rows below / above) */
+         * element; the other lanes update the rows below / above); run unconditionally, the
+         * result of a failed factorisation is discarded below */
         for (int i = 0; i < nJ; ++i)
         {
           const double xi = rhs[i] / Ms[i * nJ + i];
@@ -1042,11 +1065,11 @@ static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 }
 
 template <bool VEL, int LPS>
-static cudaError_t launchAssemble(const KtArgs& a, int nJ, int asmDoubles, int smCount,
-                                  cudaStream_t stream)
+static cudaError_t launchAssemble(const KtArgs& a, int nJ, int, int smCount, cudaStream_t stream)
 {
   constexpr int GPB = RCSB_KT_ASM_THREADS / LPS;
   /* group buffers 4 doubles apart modulo 16: the groups of a warp read different banks */
+  const int asmDoubles = rcsbKtAsmLayout(a.recDoubles, nJ, a.stageM).doubles;
   int groupStride = ((asmDoubles + 15) & ~15) + 4;
   const size_t smemBytes = (size_t) a.planBytes + (size_t) GPB * groupStride * sizeof(double);
   auto k = ktAssembleKernel<VEL, LPS>;

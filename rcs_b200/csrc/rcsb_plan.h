@@ -103,26 +103,49 @@ typedef struct
   int offColRec;        /* int[nJ] */
   int offRunLink;       /* int[nRuns] */
   int offRunRec;        /* int[nRuns] */
-  /* assembly kernel: per-state shared-memory layout (doubles)
-   *   [0, max(recDoubles, nJ^2))  the record as the walk wrote it; the first run of a link
-   *                               becomes the link's composite in place; later the same area
-   *                               holds the nJ x nJ matrix
-   *   asmS + 7 k                  column k: axis, origin, rate (copied out of the record)
-   *   asmF + 9 k                  column k: p, L, L with the transposed inertia
-   *   asmTail                     copy of the record's 5-double tail (8 slots)
-   *   asmRhs                      nJ doubles: right-hand side / solution of the direct dynamics */
-  int asmS, asmF, asmTail, asmRhs, asmDoubles;
+  /* assembly kernel: per-state shared-memory layout (doubles), see rcsbKtAsmLayout():
+   *   [0, region0)   the record as the walk wrote it; the first run of a link becomes the
+   *                  link's composite in place. With matrix staging (direct dynamics: the
+   *                  Cholesky solve works on it) region0 also takes the nJ x nJ matrix once the
+   *                  record is consumed; without staging M goes straight to global memory.
+   *   S + 7 k        column k: axis, origin, rate (copied out of the record)
+   *   F + 9 k        column k: p, L, L with the transposed inertia
+   *   tail           copy of the record's 5-double tail (8 slots)
+   *   rhs            nJ doubles: right-hand side / solution of the direct dynamics */
   int nExtraRuns;       /* runs that are not the first of their link */
   int offLinkHome;      /* int[nLinks]: offset of the link's composite (= its first run) */
   int offExtraRuns;     /* int2[nExtraRuns]: {offset of the run, offset of the link's composite} */
   int offColHome;       /* int[nJ]: composite of the column's link */
   int offPairs;         /* int4[nPairs], structurally non-zero upper-triangle entries (ancestor
-                           column i, column k): {asmS + 7 i, asmF + 9 k,
-                           (i nJ + k) | (k nJ + i) << 16, isRot(i) | (i == k) << 1 | (asmS + 7 k) << 8} */
+                           column i, column k): {7 i, 9 k, (i nJ + k) | (k nJ + i) << 16,
+                           isRot(i) | (i == k) << 1 | (7 k) << 8} */
   int pad0;
   int walkBytes;        /* leading part of the plan the walk kernel needs (header, bodyLink,
                            bodyEmit); multiple of 16 */
 } RcsbKtPlanHeader;
+
+typedef struct
+{
+  int S, F, tail, rhs, doubles;
+} RcsbKtAsmLayout;
+
+#ifdef __CUDACC__
+#define RCSB_HD __host__ __device__
+#else
+#define RCSB_HD
+#endif
+static inline RCSB_HD RcsbKtAsmLayout rcsbKtAsmLayout(int recDoubles, int nJ, int stageM)
+{
+  RcsbKtAsmLayout l;
+  int region0 = (stageM && nJ * nJ > recDoubles) ? nJ * nJ : recDoubles;
+  region0 = (region0 + 3) & ~3;
+  l.S = region0;
+  l.F = l.S + ((7 * nJ + 3) & ~3);
+  l.tail = l.F + ((9 * nJ + 3) & ~3);
+  l.rhs = l.tail + 8;
+  l.doubles = l.rhs + nJ;
+  return l;
+}
 
 /*
  * IK plan: tasks (all active), their effectors' joint chains and the per-column constants
