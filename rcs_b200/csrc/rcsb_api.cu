@@ -373,6 +373,20 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   }
   ph.jacRecord = rec;
   ph.inPlace = inPlace ? 1 : 0;
+  {
+    /* output slots ascending along the walk? */
+    int last = -1;
+    bool mono = true;
+    for (int b = 0; b < nb; ++b)
+    {
+      if (bodyOut[b] >= 0)
+      {
+        mono = mono && bodyOut[b] == last + 1;
+        last = bodyOut[b];
+      }
+    }
+    ph.velStream = mono ? 1 : 0;
+  }
   ph.invJacRecord = rec > 0 ? 1.0f / (float) rec : 0.0f;
   int off = align16((int) sizeof(ph));
   ph.offBodyOut = off;
@@ -452,6 +466,7 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.qdOut = qdOut;
   a.M = M;
   a.noCoupling = noCoupling ? 1 : 0;
+  a.scrDoubles = plan->nScrRows * (RCSB_FK_THREADS + 1);
   RCSB_CUDA(cudaSetDevice(m->device));
   if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
   {

@@ -65,14 +65,18 @@ struct PlanView
 #ifndef RCSB_FKM_MIN_BLOCKS
 #define RCSB_FKM_MIN_BLOCKS 1
 #endif
+/* with velocities: 3 resident blocks per SM pay off for shallow frame stacks (arm: 0.58 ->
+ * 0.45 ms per 1M states), not for deep ones (humanoid: spills) */
 template <bool VEL, bool ALIGNED32, int NSLOTS, bool MASS>
-__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : ((VEL && NSLOTS <= 2) ? 3 : 1))
 fkKernel(const FkArgs a)
 {
   extern __shared__ __align__(16) char smem[];
   char* sModel = smem;
   char* sPlan = smem + a.modelBytes;
   double* scr = reinterpret_cast<double*>(sPlan + a.planBytes);
+  /* VEL: two 32-record windows per warp behind the scratch (x_dot, omega) */
+  double* velWin = scr + a.scrDoubles;
 
   stageBlob(sModel, a.model, a.modelBytes);
   stageBlob(sPlan, a.plan, a.planBytes);
@@ -114,6 +118,27 @@ fkKernel(const FkArgs a)
         F[k][i] = 0.0;
       }
     }
+  }
+
+  /* x_dot / omega of the selected bodies stream out through shared-memory windows as full
+   * 256-byte rows per state (scalar 24-byte stores per body cost 3x the kernel time); only
+   * when the selection follows the walk order */
+  const bool velStream = VEL && p.hdr->velStream != 0 && (a.xdot || a.omega);
+  RecordWriter wx, wo;
+  if (VEL)
+  {
+    const int lane = tid & 31;
+    const long w0 = s - lane;
+    long nvl = a.N - w0;
+    nvl = nvl < 0 ? 0 : (nvl > 32 ? 32 : nvl);
+    wx.win = velWin + (tid >> 5) * 2 * 32 * 33;
+    wo.win = wx.win + 32 * 33;
+    wx.dst = a.xdot ? a.xdot + w0 * nSel * 3 : nullptr;
+    wo.dst = a.omega ? a.omega + w0 * nSel * 3 : nullptr;
+    wx.recDoubles = wo.recDoubles = nSel * 3;
+    wx.nv = wo.nv = (int) nvl;
+    wx.lane = wo.lane = lane;
+    wx.p = wo.p = 0;
   }
 
   Frame f, keep;
@@ -444,7 +469,7 @@ fkKernel(const FkArgs a)
       {
         storeFrame<ALIGNED32>(a.A_BI + (s * nSel + out) * 12, f);
       }
-      if (VEL)
+      if (VEL && !velStream)
       {
         if (a.xdot)
         {
@@ -456,6 +481,18 @@ fkKernel(const FkArgs a)
           double* d = a.omega + (s * nSel + out) * 3;
           d[0] = om[0]; d[1] = om[1]; d[2] = om[2];
         }
+      }
+    }
+    if (VEL && velStream && out >= 0)
+    {
+      /* warp-uniform: every lane (shadow lanes too) feeds its window column */
+      if (a.xdot)
+      {
+        wx.emitN(xd);
+      }
+      if (a.omega)
+      {
+        wo.emitN(om);
       }
     }
 
@@ -482,6 +519,18 @@ fkKernel(const FkArgs a)
           om[i] = keepOm[i];
         }
       }
+    }
+  }
+
+  if (VEL && velStream)
+  {
+    if (a.xdot)
+    {
+      wx.finish();
+    }
+    if (a.omega)
+    {
+      wo.finish();
     }
   }
 
@@ -713,8 +762,10 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
   {
     return cudaSuccess;
   }
+  const bool velOut = a->qd != nullptr;
   const size_t smemBytes = (size_t) a->modelBytes + (size_t) a->planBytes +
-                           (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double);
+                           (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double) +
+                           (velOut ? (size_t) (RCSB_FK_THREADS / 32) * 2 * 32 * 33 * sizeof(double) : 0);
   const dim3 grid((unsigned int) ((a->N + RCSB_FK_THREADS - 1) / RCSB_FK_THREADS));
   const bool vel = (a->qd != nullptr);
   const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &

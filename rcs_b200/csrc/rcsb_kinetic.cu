@@ -119,131 +119,6 @@ __device__ __forceinline__ double pairing(bool isRot, const double a[3], const d
 /* kernel 1: depth-first walk, one thread per state                                            */
 /* ------------------------------------------------------------------------------------------ */
 
-/* One window of a warp to global memory: record r of state t sits at win[r * 33 + t] and goes
- * to dst[t * recDoubles + r]. Kept out of line (it is called from many places of the walk) with
- * explicit shared / global accesses: through a generic pointer the compiler would emit generic
- * loads and 64-bit address arithmetic per element. */
-__device__ __noinline__ void flushWindow(const double* win, double* dst, int recDoubles, int nv,
-                                         int lane, int cnt)
-{
-  __syncwarp();
-  if (lane < cnt)
-  {
-    unsigned int src = (unsigned int) __cvta_generic_to_shared(win + lane * 33);
-    double* d = dst + lane;
-    const long step = recDoubles;
-    int t = 0;
-    for (; t + 4 <= nv; t += 4)
-    {
-      double v0, v1, v2, v3;
-      asm volatile("ld.shared.f64 %0, [%4];\n\t"
-                   "ld.shared.f64 %1, [%4+8];\n\t"
-                   "ld.shared.f64 %2, [%4+16];\n\t"
-                   "ld.shared.f64 %3, [%4+24];"
-                   : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3)
-                   : "r"(src));
-      asm volatile("st.global.f64 [%0], %1;" ::"l"(d), "d"(v0) : "memory");
-      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + step), "d"(v1) : "memory");
-      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + 2 * step), "d"(v2) : "memory");
-      asm volatile("st.global.f64 [%0], %1;" ::"l"(d + 3 * step), "d"(v3) : "memory");
-      src += 32;
-      d += 4 * step;
-    }
-    for (; t < nv; ++t)
-    {
-      double v;
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(src));
-      asm volatile("st.global.f64 [%0], %1;" ::"l"(d), "d"(v) : "memory");
-      src += 8;
-      d += step;
-    }
-  }
-  __syncwarp();
-}
-
-/* Streams the records of a warp's 32 states to global memory through a 32-record window in
- * shared memory (win[r * 33 + lane]): a full window leaves as one 256-byte row per state.
- * All calls are warp-uniform (the walk is the same for every state). */
-struct RecordWriter
-{
-  double* win;
-  double* dst;       /* record of the warp's first state */
-  int recDoubles;
-  int nv;            /* valid states in this warp */
-  int lane;
-  int p;             /* records produced so far */
-
-  __device__ __forceinline__ void flush(int base, int cnt)
-  {
-    flushWindow(win, dst + base, recDoubles, nv, lane, cnt);
-  }
-
-  __device__ __forceinline__ void emit(double v)
-  {
-    win[(p & 31) * 33 + lane] = v;
-    ++p;
-    if ((p & 31) == 0)
-    {
-      flush(p - 32, 32);
-    }
-  }
-
-  /* N consecutive records; one window check when they do not straddle a flush */
-  template <int N>
-  __device__ __forceinline__ void emitN(const double (&v)[N])
-  {
-    const int pos = p & 31;
-    if (pos + N <= 32)
-    {
-      double* wp = win + pos * 33 + lane;
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-      {
-        wp[i * 33] = v[i];
-      }
-      p += N;
-      if (pos + N == 32)
-      {
-        flush(p - 32, 32);
-      }
-    }
-    else
-    {
-      /* straddles the window: split at the boundary */
-      const int first = 32 - pos;
-      double* wp = win + pos * 33 + lane;
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-      {
-        if (i < first)
-        {
-          wp[i * 33] = v[i];
-        }
-      }
-      p += first;
-      flush(p - 32, 32);
-      wp = win + lane - first * 33;
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-      {
-        if (i >= first)
-        {
-          wp[i * 33] = v[i];
-        }
-      }
-      p += N - first;
-    }
-  }
-
-  __device__ __forceinline__ void finish()
-  {
-    if (p & 31)
-    {
-      flush(p & ~31, p & 31);
-    }
-  }
-};
-
 template <bool VEL, int NSLOTS>
 __global__ void __launch_bounds__(RCSB_KT_WALK_THREADS)
 ktWalkKernel(const KtArgs a)

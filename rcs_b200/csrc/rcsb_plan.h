@@ -50,6 +50,8 @@ typedef struct
   /* fused mass matrix (fkKernel<..., MASS>: models with nJ <= 8 and symmetric inertia tensors):
    * every Jacobian column has a scratch slot (slot == column), the bodies' path masks say
    * which columns move them, M is staged in nJ x nJ extra scratch rows from mStageRow on */
+  int velStream;       /* 1: the selected bodies come out in depth-first order, so x_dot / omega
+                          can stream through 32-record windows (fkKernel<VEL>) */
   int mass;            /* 1: plan carries the tables below */
   int nJ;
   int rotMask;         /* bit k: column k is a rotational joint */
