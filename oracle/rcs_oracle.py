@@ -545,30 +545,74 @@ class Oracle:
         inv[fail] = 0.0
         return inv, det
 
+    def coupled_joint_matrix(self, qf):
+        """RcsGraph_coupledJointMatrix (src/RcsCore/Rcs_graph.c:2823): A [n x nJ x nqr] and
+        A+ = (A^T A)^-1 A^T [n x nqr x nJ] at the full states qf."""
+        n = qf.shape[0]
+        nJ = self.nJ
+        H = np.zeros((n, nJ, nJ))
+        col_sum = np.zeros((n, nJ))
+        for j, jn in enumerate(self.joints):
+            c = self.jac[j]
+            if c < 0:
+                continue
+            mj = jn["coupledTo"]
+            if mj < 0:
+                H[:, c, c] = 1.0
+                col_sum[:, c] += 1.0
+            else:
+                ms = self.joints[mj]
+                coef = jn["couplingFactors"]
+                if len(coef) == 1:
+                    sens = np.full(n, coef[0])
+                else:                                    # RcsJoint_computeSlaveJointVelocity, qd = 1
+                    sens = self._poly_d(coef, np.clip(qf[:, mj], ms["q_min"], ms["q_max"])) * 1.0
+                H[:, c, self.jac[mj]] = sens
+                col_sum[:, self.jac[mj]] += sens
+        keep = [c for c in range(nJ) if np.all(np.abs(col_sum[:, c]) > 0.0)]
+        A = H[:, :, keep] / np.abs(col_sum[:, None, keep])
+        inv_diag = 1.0 / np.einsum("nij,nij->nj", A, A)
+        invA = inv_diag[:, :, None] * np.transpose(A, (0, 2, 1))
+        return A, invA
+
     def ik_rmr(self, q, tasks, x_des, lam=1.0e-8, alpha=0.05, iters=1):
         """examples/ExampleIK.cpp:154-177 with IkSolverRMR::solveRightInverse
-        (src/RcsCore/IkSolverRMR.cpp:415-596, no joint couplings) and MatNd_rwPinv
-        (src/RcsCore/Rcs_MatNd.c:1833). Returns (q, dx_last, dq_last, det_last)."""
-        q = np.asarray(q, dtype=np.float64).copy()
+        (src/RcsCore/IkSolverRMR.cpp:415-596, kinematically coupled joints in the reduced space
+        of RcsGraph_coupledJointMatrix) and MatNd_rwPinv (src/RcsCore/Rcs_MatNd.c:1833).
+        Returns (q, dx_last, dq_last, det_last)."""
+        q = self.expand(np.asarray(q, dtype=np.float64))[0]
         x_des = np.asarray(x_des, dtype=np.float64)
         nJ = self.nJ
         cols = self.ik_columns()
         inv_wq = self.inv_wq()
+        coupled = any(jn["coupledTo"] >= 0 and self.jac[j] >= 0 for j, jn in enumerate(self.joints))
         dx = dq_full = det = None
         for _ in range(iters):
             dx = self.ik_task_error(q, tasks, x_des)
             _, J = self.task_kinematics(q, tasks)
             # RcsGraph_jointLimitGradient (Rcs_kinematics.c:1496), then dH *= alpha
-            dH = self.joint_limit_gradient(q)[0] * alpha
-            WJt = inv_wq[None, :, None] * np.transpose(J, (0, 2, 1))
-            A = np.einsum("nij,njk->nik", J, WJt) + lam * np.eye(J.shape[1])
-            inv, det = self._cholesky_inverse(A)
+            dHr = -(self.joint_limit_gradient(q)[0] * alpha)
+            w = np.tile(inv_wq, (q.shape[0], 1))
+            if coupled:
+                A, invA = self.coupled_joint_matrix(q)
+                J = np.einsum("nij,njk->nik", J, A)
+                w = np.einsum("nij,j->ni", invA, inv_wq)
+                dHr = np.einsum("nij,nj->ni", invA, dHr)
+            nq = J.shape[2]
+            WJt = w[:, :, None] * np.transpose(J, (0, 2, 1))
+            M = np.einsum("nij,njk->nik", J, WJt) + lam * np.eye(J.shape[1])
+            inv, det = self._cholesky_inverse(M)
             pinv = np.einsum("nij,njk->nik", WJt, inv)
-            N = np.eye(nJ) - np.einsum("nij,njk->nik", pinv, J)           # MatNd_nullspace :3758
-            NinvW = N * inv_wq[None, None, :]
-            dq = np.einsum("nij,nj->ni", pinv, dx) + np.einsum("nij,nj->ni", NinvW, -dH)
+            N = np.eye(nq) - np.einsum("nij,njk->nik", pinv, J)           # MatNd_nullspace :3758
+            NinvW = N * w[:, None, :]
+            ts = np.einsum("nij,nj->ni", pinv, dx)
+            ns = np.einsum("nij,nj->ni", NinvW, dHr)
+            if coupled:
+                ts = np.einsum("nij,nj->ni", A, ts)
+                ns = np.einsum("nij,nj->ni", A, ns)
+            dq = ts + ns
             dq[det == 0.0] = 0.0
             dq_full = np.zeros_like(q)
             dq_full[:, cols] = dq
-            q = q + dq_full
+            q = self.expand(q + dq_full)[0]                               # RcsGraph_setState
         return q, dx, dq_full, det

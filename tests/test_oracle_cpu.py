@@ -282,3 +282,26 @@ def test_oracle_ik_vs_reference_library(refmod):
     q_near = q0 + 1e-3
     _, dx_ref, _, _ = rik.rmr(q_near, x_here, iters=1)
     assert_close(o.ik_task_error(q_near, tasks, x_here), dx_ref, what="dx (Euler-error branch)")
+
+
+def test_oracle_ik_with_coupled_joints_vs_reference_library(refmod):
+    """Reduced joint space of RcsGraph_coupledJointMatrix (Rcs_graph.c:2823, IkSolverRMR.cpp:
+    424-443) on the WAM scenario (coupled finger joints)."""
+    lay = layout("wam_scenario")
+    o = rcs_oracle.Oracle(lay)
+    names = [b["name"] for b in lay["bodies"]]
+    tip = names.index("FingerTipTip2")
+    rik = refmod.RefIk(graph_file("wam_scenario"), [("XYZ", "FingerTipTip2"), ("ABC", "FingerTipTip2")])
+    tasks = [("XYZ", tip), ("ABC", tip)]
+    q_goal = workload.sample_states(lay, 60, first=41, margin=0.2)
+    x_des, _ = rik.task_kinematics(q_goal)
+    q0 = q_goal + 0.05 * np.random.default_rng(3).uniform(-1, 1, size=q_goal.shape)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q1, dx1, dq1, det1 = o.ik_rmr(q0, tasks, x_des, iters=1)
+    assert_close(dx1, dx_ref, what="dx")
+    ok = det_ref > 1e-12
+    assert ok.mean() > 0.8
+    scale = np.maximum(1.0, np.abs(dq_ref).max(axis=1))
+    assert np.all(np.abs(dq1 - dq_ref).max(axis=1)[ok] <= 1e-7 * scale[ok])   # ill-conditioned fingers
+    well = ok & (det_ref > np.median(det_ref))
+    assert_close(q1[well], q_ref[well], tol=1e-9, what="q after one step (coupled)")
