@@ -68,7 +68,7 @@ struct PlanView
 /* with velocities: 3 resident blocks per SM pay off for shallow frame stacks (arm: 0.58 ->
  * 0.45 ms per 1M states), not for deep ones (humanoid: spills) */
 template <bool VEL, bool ALIGNED32, int NSLOTS, bool MASS>
-__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : ((VEL && NSLOTS <= 2) ? 3 : 1))
+__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : (VEL ? (NSLOTS <= 2 ? 3 : 1) : 4))
 fkKernel(const FkArgs a)
 {
   extern __shared__ __align__(16) char smem[];
@@ -141,11 +141,9 @@ fkKernel(const FkArgs a)
     wx.p = wo.p = 0;
   }
 
-  Frame f, keep;
+  Frame f;
   double xd[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
-  double keepXd[3] = {0.0, 0.0, 0.0}, keepOm[3] = {0.0, 0.0, 0.0};
   setIdentity(f);
-  setIdentity(keep);
   double nextQ = 0.0, nextQd = 0.0;
   if (dof > 0)
   {
@@ -209,21 +207,11 @@ fkKernel(const FkArgs a)
       }
     }
 
-    /* a leaf does not advance the walk: remember the parent frame in registers */
-    if (bflags & RCSB_BF_LEAF)
+    /* The body is evaluated in place when the walk continues below it, and on a copy of the
+     * parent frame when it is a leaf (the walk then carries on from the parent): two inlined
+     * instances behind a warp-uniform branch instead of predicated register copies. */
+    auto evalBody = [&](Frame& f, double (&xd)[3], double (&om)[3])
     {
-      keep = f;
-      if (VEL)
-      {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-          keepXd[i] = xd[i];
-          keepOm[i] = om[i];
-        }
-      }
-    }
-
     double op[3], w[3], c[3], vt[3];
     if (VEL)
     {
@@ -507,18 +495,16 @@ fkKernel(const FkArgs a)
       col[2 * scrStride] = f.o[2] + (f.R[2] * pt[0] + f.R[5] * pt[1] + f.R[8] * pt[2]);
     }
 
+    };
     if (bflags & RCSB_BF_LEAF)
     {
-      f = keep;
-      if (VEL)
-      {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-          xd[i] = keepXd[i];
-          om[i] = keepOm[i];
-        }
-      }
+      Frame g = f;
+      double gx[3] = {xd[0], xd[1], xd[2]}, go[3] = {om[0], om[1], om[2]};
+      evalBody(g, gx, go);
+    }
+    else
+    {
+      evalBody(f, xd, om);
     }
   }
 
