@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py — benchmark of rcs_b200 (contract: task description / DESIGN.md §6).
 
-Default workload (the headline line the driver records): BASELINE.json configs[1],
-"7-DoF arm batched FK + Jacobians, 1M uniformly sampled joint states, FP64":
+Default workload (the headline line the driver records): BASELINE.json's metric,
+"FK+Jacobian+M(q) states/sec FP64", on the arm and batch of configs[1] ("7-DoF arm batched
+FK + Jacobians, 1M uniformly sampled joint states") -- the configuration north_star's target is
+quoted on ("batched FK+Jacobian+M(q) on a 7-DoF arm at N=1M states on one B200"):
   per state  in : q (7 doubles)
              out: A_BI of all 12 bodies (12 x 96 B) + JT, JR of BallTip (2 x 3 x 7 doubles)
-             = 1544 algorithmic bytes; one fkKernel launch per step and rank.
+                  + M(q) (7 x 7 doubles)
+             = 1936 algorithmic bytes; one fkKernel<MASS> launch per step and rank.
 Other workloads (same JSON line, selected with --workload):
+  fk       configs[1] literally, without M(q): 1544 algorithmic bytes per state, fkKernel.
   kinetic  configs[2]: humanoid (dof 65, nJ 34, 63 bodies), 262,144 states per GPU,
            M + h + F_gravity + E; 10,840 algorithmic bytes per state; two kernels per pass.
   ik       configs[3]: 7-DoF arm, XYZ + ABC tasks on BallTip, lambda 1e-8, alpha 0.05,
@@ -41,7 +45,7 @@ GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
 UNIT = {"fk": "states/s", "fkm": "states/s", "kinetic": "states/s", "ik": "solves/s"}
 METRIC = {
     "fk": "FK+Jacobian states/sec FP64 (7-DoF arm, 1M states per GPU)",
-    "fkm": "FK+Jacobian+M(q) states/sec FP64 (7-DoF arm, 1M states per GPU, one launch)",
+    "fkm": "FK+Jacobian+M(q) states/sec FP64 (7-DoF arm, 1M states per GPU)",
     "kinetic": "kinetic terms M,h,g states/sec FP64 (humanoid, 256K states per GPU)",
     "ik": "RMR IK solves/sec FP64 (7-DoF arm, XYZ+ABC, 10 iterations, 4M targets)",
 }
@@ -68,8 +72,8 @@ class Workload:
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8            # 1544
             self.kernel = "rcsb::fkKernel"
             self.launches_per_step = 1
-            self.desc = ("configs[1]: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames + "
-                         "JT/JR of BallTip, uniformly sampled joint states")
+            self.desc = ("configs[1] without M(q): WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames "
+                         "+ JT/JR of BallTip, uniformly sampled joint states")
             self.l2 = "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)"
         elif name == "fkm":
             self.graph, self.eff = "wam_arm", "BallTip"
@@ -78,8 +82,10 @@ class Workload:
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8 + 7 * 7 * 8  # 1936
             self.kernel = "rcsb::fkKernel<MASS>"
             self.launches_per_step = 1
-            self.desc = ("north_star target: WAM 7-DoF arm, FK all 12 body frames + JT/JR of BallTip + "
-                         "mass matrix M(q) from one launch (rcsb_fk_jacobians_mass)")
+            self.desc = ("configs[1] + M(q), the configuration the metric and north_star's target are quoted "
+                         "on: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all 12 body frames + JT/JR of "
+                         "BallTip + mass matrix M(q) from one launch (rcsb_fk_jacobians_mass), uniformly "
+                         "sampled joint states")
             self.l2 = "per-step working set 2.0 GB per GPU >> 126 MB L2 (no flush needed)"
         elif name == "kinetic":
             self.graph, self.eff = "humanoid", None
@@ -580,7 +586,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fk", choices=["fk", "fkm", "kinetic", "ik"])
+    ap.add_argument("--workload", default="fkm", choices=["fkm", "fk", "kinetic", "ik"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hold", type=float, default=1.0,
                     help="seconds of extra (untimed) load for the clock sampler")

@@ -371,6 +371,37 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
       }
     }
   }
+  std::vector<int> massList;
+  if (withMass)
+  {
+    const double* mass = m->darr(RCSB_A_BODY_MASS);
+    bool chain = true;
+    for (int k = 0; k < nJ; ++k)
+    {
+      chain = chain && ph.relMask[k] == (1 << k) - 1;
+    }
+    for (int cols = nJ; cols >= 1 && chain; --cols)
+    {
+      for (int b = 0; b < nb; ++b)
+      {
+        if (mass[b] > 0.0 && pathMask[(size_t) b] == (1 << cols) - 1)
+        {
+          chain = chain && bodyOut[b] >= 0;
+          massList.insert(massList.end(), {b, bodyOut[b], cols, 0});
+        }
+      }
+    }
+    ph.massChain = chain ? 1 : 0;
+    ph.nMass = chain ? (int) massList.size() / 4 : 0;
+  }
+  if (massList.empty())
+  {
+    massList.assign(4, 0);
+  }
+  if (rec > 0)
+  {
+    ph.zeroRow = ph.nScrRows++;
+  }
   ph.jacRecord = rec;
   ph.inPlace = inPlace ? 1 : 0;
   {
@@ -409,6 +440,8 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   off = align16(off + (int) effChain.size() * 4);
   ph.offBodyPathMask = off;
   off = align16(off + nb * 4);
+  ph.offMassList = off;
+  off = align16(off + (int) massList.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob(ph.totalBytes, 0);
@@ -426,6 +459,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   memcpy(blob.data() + ph.offEffChainStart, effChainStart.data(), (nEff + 1) * 4);
   memcpy(blob.data() + ph.offEffChain, effChain.data(), effChain.size() * 4);
   memcpy(blob.data() + ph.offBodyPathMask, pathMask.data(), (size_t) nb * 4);
+  memcpy(blob.data() + ph.offMassList, massList.data(), massList.size() * 4);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -435,6 +469,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   dp.nScrRows = ph.nScrRows;
   dp.nSel = nOut;
   dp.nEff = nEff;
+  dp.aux0 = ph.massChain;
 
   auto ins = m->fkPlans.emplace(key, dp);
   *out = &ins.first->second;
@@ -466,7 +501,9 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.qdOut = qdOut;
   a.M = M;
   a.noCoupling = noCoupling ? 1 : 0;
-  a.scrDoubles = plan->nScrRows * (RCSB_FK_THREADS + 1);
+  /* composite (tip-to-root) mass matrix when the plan allows it and the frames are written */
+  a.massMode = M ? ((plan->aux0 && A_BI) ? 2 : 1) : 0;
+  a.scrDoubles = plan->nScrRows * (RCSB_FK_BLOCK(M != nullptr) + 1);
   RCSB_CUDA(cudaSetDevice(m->device));
   if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
   {

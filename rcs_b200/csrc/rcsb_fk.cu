@@ -19,6 +19,7 @@
  *
  * Bound: HBM (output stream); see DESIGN.md for the byte counts.
  */
+#include <cstdlib>
 #include "rcsb_device.cuh"
 #include "rcsb_kernels.h"
 #include "rcsb_plan.h"
@@ -39,6 +40,7 @@ struct PlanView
   const int* effChainStart;
   const int* effChain;
   const int* bodyPathMask;
+  const int4* massList;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -53,22 +55,34 @@ struct PlanView
     effChainStart = reinterpret_cast<const int*>(blob + hdr->offEffChainStart);
     effChain = reinterpret_cast<const int*>(blob + hdr->offEffChain);
     bodyPathMask = reinterpret_cast<const int*>(blob + hdr->offBodyPathMask);
+    massList = reinterpret_cast<const int4*>(blob + hdr->offMassList);
   }
 };
 
 /* MASS: additionally the joint-space mass matrix (RcsGraph_computeMassMatrix, Rcs_dynamics.c:
- * 610) for models with at most 8 Jacobian columns: for every massive body and every column k
- * that moves it, the body's momentum under a unit rate of joint k, (p, L) about the world
- * origin, is added to the column's accumulator F[k] (registers); after the walk
- * M[i][k] = <joint i, F[k]> for i an ancestor-or-self of k. Same result as the composite-body
- * route of rcsb_kinetic.cu, without the per-link storage. */
+ * 610) for models with at most 8 Jacobian columns.
+ * MASS = 1 (any tree): for every massive body and every column k that moves it, the body's
+ * momentum under a unit rate of joint k, (p, L) about the world origin, is added to the
+ * column's accumulator F[k] (registers); after the walk M[i][k] = <joint i, F[k]> for i an
+ * ancestor-or-self of k.
+ * MASS = 2 (serial chains whose body frames are all written, e.g. an arm): the walk stays the
+ * plain FK walk. Afterwards the thread reads the frames of the massive bodies back (its own
+ * stores, still in L2), tip to root, sums their inertia about the world origin into one
+ * composite (10 doubles), and at every column k takes F[k] = composite x joint k and
+ * M[i][k] = <joint i, F[k]>, i <= k. Joints are kept in shared memory as (w, v): angular part
+ * and velocity of the point at the world origin under a unit rate (rotation: a, o x a;
+ * translation: 0, a), so that M[i][k] = w_i . L + v_i . p and a Jacobian column is w x p + v.
+ * 48 accumulator doubles less than MASS = 1: 3 blocks per SM instead of 2. */
+#ifndef RCSB_FKM_CHAIN_BLOCKS
+#define RCSB_FKM_CHAIN_BLOCKS 3
+#endif
 #ifndef RCSB_FKM_MIN_BLOCKS
 #define RCSB_FKM_MIN_BLOCKS 1
 #endif
 /* with velocities: 3 resident blocks per SM pay off for shallow frame stacks (arm: 0.58 ->
  * 0.45 ms per 1M states), not for deep ones (humanoid: spills) */
-template <bool VEL, bool ALIGNED32, int NSLOTS, bool MASS>
-__global__ void __launch_bounds__(RCSB_FK_THREADS, MASS ? RCSB_FKM_MIN_BLOCKS : (VEL ? (NSLOTS <= 2 ? 3 : 1) : 4))
+template <bool VEL, bool ALIGNED32, int NSLOTS, int MASS>
+__global__ void __launch_bounds__(RCSB_FK_BLOCK(MASS), MASS == 2 ? RCSB_FKM_CHAIN_BLOCKS : (MASS ? RCSB_FKM_MIN_BLOCKS : (VEL ? (NSLOTS <= 2 ? 3 : 1) : 4)))
 fkKernel(const FkArgs a)
 {
   extern __shared__ __align__(16) char smem[];
@@ -87,9 +101,14 @@ fkKernel(const FkArgs a)
   PlanView p;
   p.bind(sPlan);
 
+  constexpr int THREADS = RCSB_FK_BLOCK(MASS);
   const int tid = threadIdx.x;
-  const int scrStride = RCSB_FK_THREADS + 1;   /* odd stride: conflict-free transposed reads */
-  const long s = (long) blockIdx.x * RCSB_FK_THREADS + tid;
+  const int scrStride = THREADS + 1;           /* odd stride: conflict-free transposed reads */
+  if (p.hdr->jacRecord > 0)
+  {
+    scr[p.hdr->zeroRow * scrStride + tid] = 0.0;   /* source of the Jacobians' structural zeros */
+  }
+  const long s = (long) blockIdx.x * THREADS + tid;
   const bool active = s < a.N;
   const long sc = active ? s : a.N - 1;        /* idle lanes shadow the last state, no stores */
 
@@ -106,8 +125,8 @@ fkKernel(const FkArgs a)
 
   constexpr int SLOT_DOUBLES = VEL ? 18 : 12;
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * SLOT_DOUBLES];
-  double F[MASS ? 8 : 1][6];
-  if (MASS)
+  double F[MASS == 1 ? 8 : 1][6];
+  if (MASS == 1)
   {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -314,12 +333,25 @@ fkKernel(const FkArgs a)
       {
         double* col = scr + slot * scrStride + tid;
         const int rs = nChain * scrStride;
-        col[0] = ax[0];
-        col[rs] = ax[1];
-        col[2 * rs] = ax[2];
-        col[3 * rs] = f.o[0];
-        col[4 * rs] = f.o[1];
-        col[5 * rs] = f.o[2];
+        if (MASS == 2)
+        {
+          const bool rot = (jf & RCSB_JF_ROT) != 0;
+          col[0] = rot ? ax[0] : 0.0;
+          col[rs] = rot ? ax[1] : 0.0;
+          col[2 * rs] = rot ? ax[2] : 0.0;
+          col[3 * rs] = rot ? f.o[1] * ax[2] - f.o[2] * ax[1] : ax[0];
+          col[4 * rs] = rot ? f.o[2] * ax[0] - f.o[0] * ax[2] : ax[1];
+          col[5 * rs] = rot ? f.o[0] * ax[1] - f.o[1] * ax[0] : ax[2];
+        }
+        else
+        {
+          col[0] = ax[0];
+          col[rs] = ax[1];
+          col[2 * rs] = ax[2];
+          col[3 * rs] = f.o[0];
+          col[4 * rs] = f.o[1];
+          col[5 * rs] = f.o[2];
+        }
       }
     }
 
@@ -381,7 +413,7 @@ fkKernel(const FkArgs a)
     }
 
     /* ---- mass properties: momentum of the body under unit joint rates ---------------------- */
-    if (MASS && (bflags & RCSB_BF_HAS_MASS))
+    if (MASS == 1 && (bflags & RCSB_BF_HAS_MASS))
     {
       const double mass = m.bodyMass[b];
       const double* cl = m.bodyCom + 3 * b;
@@ -523,7 +555,102 @@ fkKernel(const FkArgs a)
   /* ---- mass matrix entries (upper triangle, registers): computed before the Jacobian pass
    * overwrites the joint origins, staged after it over the same scratch rows ------------------ */
   double Mv[MASS ? 36 : 1];
-  if (MASS && a.M)
+  if (MASS == 2 && a.M)
+  {
+    const int nJ = p.hdr->nJ;
+    const int rs = nChain * scrStride;
+    const int nMass = p.hdr->nMass;
+    const double* frames = a.A_BI + sc * nSel * 12;
+    /* composite about the world origin: mass, first moment, inertia (xx, xy, xz, yy, yz, zz) */
+    double cm = 0.0, ch[3] = {0.0, 0.0, 0.0}, cI[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int li = 0;
+    int4 ent = p.massList[0];
+#pragma unroll
+    for (int k = 7; k >= 0; --k)
+    {
+      if (k < nJ)
+      {
+        while (li < nMass && ent.z == k + 1)
+        {
+          /* own stores of the walk, read back from L2 */
+          const double* fp = frames + ent.y * 12;
+          double o[3], R[9];
+          if (ALIGNED32)
+          {
+            load4cg(fp, o[0], o[1], o[2], R[0]);
+            load4cg(fp + 4, R[1], R[2], R[3], R[4]);
+            load4cg(fp + 8, R[5], R[6], R[7], R[8]);
+          }
+          else
+          {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+              o[i] = __ldcg(fp + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+            {
+              R[i] = __ldcg(fp + 3 + i);
+            }
+          }
+          const int b = ent.x;
+          const double mass = m.bodyMass[b];
+          const double* cl = m.bodyCom + 3 * b;
+          const double* Ib = m.bodyInertia + 9 * b;
+          ++li;
+          if (li < nMass)
+          {
+            ent = p.massList[li];
+          }
+          const double c[3] = {o[0] + (R[0] * cl[0] + R[3] * cl[1] + R[6] * cl[2]),
+                               o[1] + (R[1] * cl[0] + R[4] * cl[1] + R[7] * cl[2]),
+                               o[2] + (R[2] * cl[0] + R[5] * cl[1] + R[8] * cl[2])};
+          /* R^T I_b R (Mat3d_similarityTransform), symmetric: upper triangle only */
+          double t[9];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+            {
+              t[3 * i + jj] = Ib[3 * i] * R[jj] + Ib[3 * i + 1] * R[3 + jj] + Ib[3 * i + 2] * R[6 + jj];
+            }
+          const double mc[3] = {mass * c[0], mass * c[1], mass * c[2]};
+          cm += mass;
+          ch[0] += mc[0];
+          ch[1] += mc[1];
+          ch[2] += mc[2];
+          cI[0] += (R[0] * t[0] + R[3] * t[3] + R[6] * t[6]) + (mc[1] * c[1] + mc[2] * c[2]);
+          cI[1] += (R[0] * t[1] + R[3] * t[4] + R[6] * t[7]) - mc[0] * c[1];
+          cI[2] += (R[0] * t[2] + R[3] * t[5] + R[6] * t[8]) - mc[0] * c[2];
+          cI[3] += (R[1] * t[1] + R[4] * t[4] + R[7] * t[7]) + (mc[0] * c[0] + mc[2] * c[2]);
+          cI[4] += (R[1] * t[2] + R[4] * t[5] + R[7] * t[8]) - mc[1] * c[2];
+          cI[5] += (R[2] * t[2] + R[5] * t[5] + R[8] * t[8]) + (mc[0] * c[0] + mc[1] * c[1]);
+        }
+        /* momentum of the composite under a unit rate of column k: p = m v + w x h,
+         * L = I w + h x v */
+        const double* col = scr + k * scrStride + tid;
+        const double w[3] = {col[0], col[rs], col[2 * rs]};
+        const double v[3] = {col[3 * rs], col[4 * rs], col[5 * rs]};
+        const double pk[3] = {cm * v[0] + (w[1] * ch[2] - w[2] * ch[1]),
+                              cm * v[1] + (w[2] * ch[0] - w[0] * ch[2]),
+                              cm * v[2] + (w[0] * ch[1] - w[1] * ch[0])};
+        const double Lk[3] = {cI[0] * w[0] + cI[1] * w[1] + cI[2] * w[2] + (ch[1] * v[2] - ch[2] * v[1]),
+                              cI[1] * w[0] + cI[3] * w[1] + cI[4] * w[2] + (ch[2] * v[0] - ch[0] * v[2]),
+                              cI[2] * w[0] + cI[4] * w[1] + cI[5] * w[2] + (ch[0] * v[1] - ch[1] * v[0])};
+        Mv[k * (k + 1) / 2 + k] = (w[0] * Lk[0] + w[1] * Lk[1] + w[2] * Lk[2]) +
+                                  (v[0] * pk[0] + v[1] * pk[1] + v[2] * pk[2]);
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+        {
+          const double* ci = scr + i * scrStride + tid;
+          Mv[k * (k + 1) / 2 + i] = (ci[0] * Lk[0] + ci[rs] * Lk[1] + ci[2 * rs] * Lk[2]) +
+                                    (ci[3 * rs] * pk[0] + ci[4 * rs] * pk[1] + ci[5 * rs] * pk[2]);
+        }
+      }
+    }
+  }
+  if (MASS == 1 && a.M)
   {
     const int nJ = p.hdr->nJ;
     const int rs = nChain * scrStride;
@@ -578,7 +705,14 @@ fkKernel(const FkArgs a)
           const int ent = p.effChain[k];
           double* col = scr + (ent & 0xffff) * scrStride + tid;
           const double a0 = col[0], a1 = col[rs], a2 = col[2 * rs];
-          if (ent >> 16)
+          if (MASS == 2)
+          {
+            /* (w, v) storage: column = w x I_p + v for both joint types */
+            col[3 * rs] += a1 * pz - a2 * py;
+            col[4 * rs] += a2 * px - a0 * pz;
+            col[5 * rs] += a0 * py - a1 * px;
+          }
+          else if (ent >> 16)
           {
             const double d0 = px - col[3 * rs], d1 = py - col[4 * rs], d2 = pz - col[5 * rs];
             col[3 * rs] = a1 * d2 - a2 * d1;
@@ -608,20 +742,40 @@ fkKernel(const FkArgs a)
 
     if (inPlace)
     {
-      /* plain gather: one shared-memory read per element, coalesced global writes */
-      for (int e = lane; e < total; e += 32)
+      /* one record row per warp instruction: lane r owns element r of the record, so its
+       * scratch row is fixed (structural zeros read the zero row) and the loop over the
+       * warp's states is a shared-memory read and a global store with constant strides, no
+       * index arithmetic; the 32 records of the warp are contiguous in global memory */
+      const double* zero = scrWarp + p.hdr->zeroRow * scrStride;
+      for (int r0 = 0; r0 < rec; r0 += 32)
       {
-        const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
-        const int rem = e - sl * rec;
-        if (JTw)
+        const int rem = r0 + lane;
+        if (rem < rec)
         {
-          const int t = p.jtab[rem];
-          JTw[e] = t >= 0 ? scrWarp[t * scrStride + sl] : 0.0;
-        }
-        if (JRw)
-        {
-          const int t = p.jtabR[rem];
-          JRw[e] = t >= 0 ? scrWarp[t * scrStride + sl] : 0.0;
+          const int tT = p.jtab[rem], tR = p.jtabR[rem];
+          const double* srcT = tT >= 0 ? scrWarp + tT * scrStride : zero;
+          const double* srcR = tR >= 0 ? scrWarp + tR * scrStride : zero;
+          if (JTw && JRw)
+          {
+            double* dT = JTw + rem;
+            double* dR = JRw + rem;
+#pragma unroll 4
+            for (int sl = 0; sl < (int) nv; ++sl)
+            {
+              dT[(long) sl * rec] = srcT[sl];
+              dR[(long) sl * rec] = srcR[sl];
+            }
+          }
+          else
+          {
+            double* d = JTw ? JTw + rem : JRw + rem;
+            const double* src = JTw ? srcT : srcR;
+#pragma unroll 4
+            for (int sl = 0; sl < (int) nv; ++sl)
+            {
+              d[(long) sl * rec] = src[sl];
+            }
+          }
         }
       }
     }
@@ -637,7 +791,15 @@ fkKernel(const FkArgs a)
         {
           const int r = RCSB_JTAB_ROW(t);
           const double* ja = scrWarp + RCSB_JTAB_SLOT(t) * scrStride + sl;
-          if (RCSB_JTAB_ISROT(t))
+          if (MASS == 2)
+          {
+            const int r1 = r == 2 ? 0 : r + 1;
+            const int r2 = r == 0 ? 2 : r - 1;
+            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
+            vT = ja[(3 + r) * rs] + (ja[r1 * rs] * pe[r2 * scrStride] - ja[r2 * rs] * pe[r1 * scrStride]);
+            vR = ja[r * rs];
+          }
+          else if (RCSB_JTAB_ISROT(t))
           {
             /* column = axis x (I_p - joint origin), component r */
             const int r1 = r == 2 ? 0 : r + 1;
@@ -694,20 +856,26 @@ fkKernel(const FkArgs a)
     long nv = a.N - w0;
     nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
     const int nJ2 = p.hdr->nJ * p.hdr->nJ;
-    const int total = (int) nv * nJ2;
-    const float inv = p.hdr->invNJ2;
     const double* stw = scr + p.hdr->mStageRow * scrStride + (tid - lane);
     double* Mw = a.M + w0 * nJ2;
-    for (int e = lane; e < total; e += 32)
+    for (int r0 = 0; r0 < nJ2; r0 += 32)
     {
-      const int sl = __float2int_rd(((float) e + 0.5f) * inv);
-      const int rem = e - sl * nJ2;
-      Mw[e] = stw[rem * scrStride + sl];
+      const int rem = r0 + lane;
+      if (rem < nJ2)
+      {
+        const double* src = stw + rem * scrStride;
+        double* d = Mw + rem;
+#pragma unroll 4
+        for (int sl = 0; sl < (int) nv; ++sl)
+        {
+          d[(long) sl * nJ2] = src[sl];
+        }
+      }
     }
   }
 }
 
-template <bool VEL, bool ALIGNED32, bool MASS>
+template <bool VEL, bool ALIGNED32, int MASS>
 static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t smemBytes,
                                cudaStream_t stream)
 {
@@ -720,7 +888,7 @@ static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t sm
     {                                                                                          \
       return e;                                                                                \
     }                                                                                          \
-    k<<<grid, RCSB_FK_THREADS, smemBytes, stream>>>(a);                                        \
+    k<<<grid, RCSB_FK_BLOCK(MASS), smemBytes, stream>>>(a);                                        \
     return cudaGetLastError();                                                                 \
   }
   if (nSlots <= 0)
@@ -749,24 +917,35 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
     return cudaSuccess;
   }
   const bool velOut = a->qd != nullptr;
+  const int threads = RCSB_FK_BLOCK(a->M != nullptr);
   const size_t smemBytes = (size_t) a->modelBytes + (size_t) a->planBytes +
-                           (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double) +
-                           (velOut ? (size_t) (RCSB_FK_THREADS / 32) * 2 * 32 * 33 * sizeof(double) : 0);
-  const dim3 grid((unsigned int) ((a->N + RCSB_FK_THREADS - 1) / RCSB_FK_THREADS));
+                           (size_t) nScrRows * (threads + 1) * sizeof(double) +
+                           (velOut ? (size_t) (threads / 32) * 2 * 32 * 33 * sizeof(double) : 0);
+  const dim3 grid((unsigned int) ((a->N + threads - 1) / threads));
+#ifdef RCSB_TUNING_KNOBS
+  /* occupancy experiments: unused shared memory lowers the resident blocks per SM */
+  static const size_t padBytes = getenv("RCSB_FK_PAD_SMEM") ? (size_t) atol(getenv("RCSB_FK_PAD_SMEM")) : 0;
+  const_cast<size_t&>(smemBytes) += padBytes;
+#endif
   const bool vel = (a->qd != nullptr);
   const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &
                    31u) == 0;
 
+  if (a->M && a->massMode == 2)
+  {
+    return al ? launchSlots<false, true, 2>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<false, false, 2>(*a, nSlots, grid, smemBytes, stream);
+  }
   if (a->M)
   {
-    return al ? launchSlots<false, true, true>(*a, nSlots, grid, smemBytes, stream)
-              : launchSlots<false, false, true>(*a, nSlots, grid, smemBytes, stream);
+    return al ? launchSlots<false, true, 1>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<false, false, 1>(*a, nSlots, grid, smemBytes, stream);
   }
   if (vel)
   {
-    return al ? launchSlots<true, true, false>(*a, nSlots, grid, smemBytes, stream)
-              : launchSlots<true, false, false>(*a, nSlots, grid, smemBytes, stream);
+    return al ? launchSlots<true, true, 0>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<true, false, 0>(*a, nSlots, grid, smemBytes, stream);
   }
-  return al ? launchSlots<false, true, false>(*a, nSlots, grid, smemBytes, stream)
-            : launchSlots<false, false, false>(*a, nSlots, grid, smemBytes, stream);
+  return al ? launchSlots<false, true, 0>(*a, nSlots, grid, smemBytes, stream)
+            : launchSlots<false, false, 0>(*a, nSlots, grid, smemBytes, stream);
 }

@@ -7,6 +7,12 @@
 #include <cuda_runtime.h>
 
 #define RCSB_FK_THREADS 128
+/* block size of the fused FK + Jacobians + mass-matrix variant (register-bound: smaller
+ * blocks fill the register file more evenly) */
+#ifndef RCSB_FKM_THREADS
+#define RCSB_FKM_THREADS 128
+#endif
+#define RCSB_FK_BLOCK(mass) ((mass) ? RCSB_FKM_THREADS : RCSB_FK_THREADS)
 #define RCSB_MAX_FRAME_SLOTS 8
 #define RCSB_KT_WALK_THREADS 128
 #define RCSB_KT_ASM_THREADS 128
@@ -34,6 +40,7 @@ struct FkArgs
   double* JR;
   double* M;           /* N x nJ x nJ mass matrix (fused path, plans built with mass = 1) */
   double* qdOut;       /* N x dof joint rates after expansion and coupling (needs qd) */
+  int massMode;        /* 0: no M; 1: per-column momentum accumulators; 2: serial chain, composites */
   int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
   int scrDoubles;      /* doubles of the Jacobian scratch: nScrRows x (RCSB_FK_THREADS + 1) */
 };

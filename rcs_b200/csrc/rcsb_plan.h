@@ -59,7 +59,14 @@ typedef struct
   int offBodyPathMask; /* int[nb]: bit k set if column k moves the body */
   int relMask[8];      /* bit i of relMask[k]: column i is a proper ancestor of column k */
   float invNJ2;
-  int pad;
+  /* serial-chain variant of the fused mass matrix (fkKernel<..., MASS = 2>): every column is an
+   * ancestor of the next one (relMask[k] == (1 << k) - 1) and the frame of every massive body
+   * is among the outputs. The massive bodies are then listed by descending number of columns
+   * that move them, and M is built after the walk from composite inertias, tip to root. */
+  int massChain;
+  int nMass;           /* entries of the list */
+  int offMassList;     /* int4[nMass]: {body, output slot, number of columns moving it, 0} */
+  int zeroRow;         /* scratch row kept at zero (last row): structural zeros of JT / JR */
 } RcsbFkPlanHeader;
 
 /*
