@@ -138,10 +138,12 @@ def test_direct_dynamics(name, n, refmod, cuda_device):
 
 @pytest.mark.parametrize("name,effs,n", [("wam_arm", ["BallTip"], 5000), ("wam_arm", ["BallTip", "Link4"], 333),
                                          ("schunk_sdh", ["DistalTouch3"], 500), ("humanoid", ["RightHandTip"], 64),
-                                         ("husky", None, 64)])
+                                         ("husky", None, 64), ("gantry", ["Tool"], 2000),
+                                         ("gantry", ["Tool", "Camera", "Trolley"], 333)])
 def test_fused_fk_jacobians_mass_matrix(name, effs, n, refmod, cuda_device):
     """rcsb_fk_jacobians_mass: FK + Jacobians + M(q) from one launch (nJ <= 8, symmetric inertia:
-    wam_arm, schunk_sdh) or from the two general paths (humanoid: nJ 34; husky: asymmetric
+    wam_arm and gantry = serial chains, composite variant, the latter with translational joints;
+    schunk_sdh = branching hand, accumulator variant) or from the two general paths (humanoid: nJ 34; husky: asymmetric
     tensors) — same outputs either way, against the reference."""
     import torch
 
@@ -152,7 +154,7 @@ def test_fused_fk_jacobians_mass_matrix(name, effs, n, refmod, cuda_device):
     ours = m.fk_jacobians(torch.from_numpy(q).cuda(cuda_device), eff, want=("A_BI", "JT", "JR", "M"))
     torch.cuda.synchronize()
     launches = rcs_b200.kernel_launch_count() - launches0
-    fused = name in ("wam_arm", "schunk_sdh")
+    fused = name in ("wam_arm", "schunk_sdh", "gantry")
     assert launches == (1 if fused else 3)
     ref = r.fk_jacobians(q, eff)
     for k in ("A_BI", "JT", "JR"):
@@ -160,5 +162,12 @@ def test_fused_fk_jacobians_mass_matrix(name, effs, n, refmod, cuda_device):
     M_ref = r.mass_matrix(q)
     assert_close(ours["M"].cpu().numpy(), M_ref, what=f"{name}:M")
     assert_structural_zeros(ours["M"].cpu().numpy(), M_ref, what=f"{name}:M")
+    # without the frames among the outputs a serial chain cannot read them back: the
+    # per-column accumulator variant runs instead (same result up to rounding)
     host = m.fk_jacobians(q, eff, want=("JT", "M"))
-    assert np.array_equal(host["M"], ours["M"].cpu().numpy())
+    assert_close(host["M"], M_ref, what=f"{name}:M (frames not requested)")
+    assert_close(host["JT"], ref["JT"], what=f"{name}:JT (frames not requested)")
+    # a body selection that leaves out massive bodies: same fallback
+    sel = m.fk_jacobians(q, eff, bodies=[eff[0]], want=("A_BI", "JR", "M"))
+    assert_close(sel["M"], M_ref, what=f"{name}:M (one frame requested)")
+    assert_close(sel["JR"], ref["JR"], what=f"{name}:JR (one frame requested)")

@@ -30,6 +30,9 @@ GRAPHS = {
     "husky": "Husky/husky.xml",
     "schunk_sdh": "Schunk/sdh.xml",
 }
+# fixtures written by hand for this repository (not re-serialised): only their layout is recorded,
+# by the reference loader
+LOCAL = ["gantry"]
 # layout keys that legitimately differ after export (shapes are dropped)
 IGNORE = {"nShapes"}
 
@@ -65,6 +68,16 @@ def main():
             raise SystemExit(1)
         with open(os.path.join(out_dir, name + ".layout.json"), "w") as f:
             json.dump(orig, f, indent=0, sort_keys=True)
+    for name in LOCAL:
+        src = os.path.join(out_dir, name + ".xml")
+        lay_ref = strip(ref.RefGraph(src).layout())
+        ok = lay_ref == strip(rcs_b200.Graph(src).layout())
+        print(f"{name:14s} dof={lay_ref['dof']:3d} nJ={lay_ref['nJ']:3d} nb={lay_ref['nBodies']:3d} "
+              f"own fixture, both loaders agree: {ok}")
+        if not ok:
+            raise SystemExit(1)
+        with open(os.path.join(out_dir, name + ".layout.json"), "w") as f:
+            json.dump(lay_ref, f, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":
