@@ -80,7 +80,7 @@ class Workload:
             self.per_gpu = 1 << 20
             self.scaling = "weak"
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8 + 7 * 7 * 8  # 1936
-            self.kernel = "rcsb::fkKernel<MASS>"
+            self.kernel = "rcsb::fkKernel<MASS = 2> (serial chain: composite inertias after the walk)"
             self.launches_per_step = 1
             self.desc = ("configs[1] + M(q), the configuration the metric and north_star's target are quoted "
                          "on: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all 12 body frames + JT/JR of "
