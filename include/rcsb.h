@@ -204,7 +204,14 @@ unsigned long long rcsb_kernel_launch_count(void);
 bool RcsGraph_setState(RcsGraph* self, const MatNd* q, const MatNd* q_dot);
 /* src/RcsCore/Rcs_graph.c:301 */
 void RcsGraph_computeForwardKinematics(RcsGraph* self, const MatNd* q, const MatNd* q_dot);
-/* src/RcsCore/Rcs_kinematics.c:200, :416 — world frame only (A_BI must be NULL). */
+/* src/RcsCore/Rcs_graph.c:327: forward kinematics of one body (or its subtree) from explicit
+ * q / q_dot; the other bodies keep their frames. */
+void RcsGraph_computeBodyKinematics(RcsGraph* self, RcsBody* bdy, const MatNd* q, const MatNd* q_dot,
+                                    bool subTree);
+/* src/RcsCore/Rcs_kinematics.c:178, :200, :416. A_BI = NULL: columns in world coordinates,
+ * otherwise rotated into the frame with rotation matrix A_BI (J <- A_BI J). */
+void RcsGraph_worldPointJacobian(const RcsGraph* self, const RcsBody* body, const double I_pt[3],
+                                 double A_BI[3][3], MatNd* J);
 void RcsGraph_bodyPointJacobian(const RcsGraph* self, const RcsBody* body, const double B_pt[3],
                                 double A_BI[3][3], MatNd* J);
 void RcsGraph_rotationJacobian(const RcsGraph* self, const RcsBody* body, double A_BI[3][3],

@@ -216,6 +216,12 @@ void RcsGraph_stateVectorToIK(const RcsGraph* self, const MatNd* q_full, MatNd* 
 /* src/RcsCore/Rcs_graph.c:1087, :2804 */
 void RcsGraph_getInvWq(const RcsGraph* self, MatNd* invWq, RcsStateType type);
 int RcsGraph_countCoupledJoints(const RcsGraph* self);
+/* src/RcsCore/Rcs_graph.c:2756, :2823; Rcs_kinematics.c:1496, :47 (host-side helpers of the
+ * single-state API: O(dof) loops over the joint list, nothing to batch) */
+bool RcsGraph_updateSlaveJoints(const RcsGraph* self, MatNd* q, MatNd* q_dot);
+int RcsGraph_coupledJointMatrix(const RcsGraph* self, MatNd* A, MatNd* invA);
+double RcsGraph_jointLimitGradient(const RcsGraph* self, MatNd* dH, RcsStateType type);
+void RcsGraph_bodyPoint(const RcsBody* body, const double B_pt[3], double I_pt[3]);
 void RcsGraph_getDefaultState(const RcsGraph* self, MatNd* q0);
 
 /* Canonical JSON description of everything the hot path reads from the graph (tree

@@ -622,6 +622,186 @@ int RcsGraph_countCoupledJoints(const RcsGraph* self)
   return n;
 }
 
+/* Applies the coupling rules to an explicit state (src/RcsCore/Rcs_graph.c:2756): slave angle
+ * and rate from the master's; reports whether an angle moved by more than 1e-8. */
+bool RcsGraph_updateSlaveJoints(const RcsGraph* self, MatNd* q, MatNd* q_dot)
+{
+  if (!self || !q || q->m != self->dof || q->n != 1 ||
+      (q_dot && (q_dot->m != self->dof || q_dot->n != 1)))
+  {
+    RCSB_FATAL("RcsGraph_updateSlaveJoints: q / q_dot must be %u x 1", self ? self->dof : 0);
+    return false;
+  }
+  bool moved = false;
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      const RcsJoint* master = JNT->coupledTo;
+      if (!master)
+      {
+        continue;
+      }
+      const double qm = q->ele[master->jointIndex];
+      const double qs = RcsJoint_computeSlaveJointAngle(JNT, qm);
+      moved = moved || fabs(qs - q->ele[JNT->jointIndex]) > 1.0e-8;
+      q->ele[JNT->jointIndex] = qs;
+      if (q_dot)
+      {
+        q_dot->ele[JNT->jointIndex] =
+          RcsJoint_computeSlaveJointVelocity(JNT, qm, q_dot->ele[master->jointIndex]);
+      }
+    }
+  }
+  return moved;
+}
+
+/* Coupling matrices of the reduced joint space (src/RcsCore/Rcs_graph.c:2823): column c of A
+ * (nJ x nqr) belongs to an uncoupled joint and holds 1 in its own row and the sensitivity
+ * d q_slave / d q_master in the rows of its slaves, the column scaled by 1 / |column sum|;
+ * invA = (A^T A)^-1 A^T (A^T A is diagonal). Returns the number of coupled joints. */
+int RcsGraph_coupledJointMatrix(const RcsGraph* self, MatNd* A, MatNd* invA)
+{
+  const unsigned int nq = self->nJ;
+  const int nCoupled = RcsGraph_countCoupledJoints(self);
+  const unsigned int nqr = nq - (unsigned int) nCoupled;
+  if (!A || !invA || A->size < nq * nqr || invA->size < nq * nqr)
+  {
+    RCSB_FATAL("RcsGraph_coupledJointMatrix: A and invA need room for %u x %u doubles", nq, nqr);
+    return nCoupled;
+  }
+  MatNd_reshapeAndSetZero(A, nq, nqr);
+  MatNd_reshapeAndSetZero(invA, nqr, nq);
+  /* reduced column of every master (unconstrained, uncoupled joint), in jacobiIndex order */
+  int* redCol = (int*) malloc(sizeof(int) * (nq + 1));
+  double* sum = (double*) calloc(nq + 1, sizeof(double));
+  double* sq = (double*) calloc(nq + 1, sizeof(double));
+  for (unsigned int i = 0; i < nq; ++i)
+  {
+    redCol[i] = -1;
+  }
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      if (!JNT->constrained && !JNT->coupledTo)
+      {
+        redCol[JNT->jacobiIndex] = 0;   /* marks a master; numbered below */
+      }
+    }
+  }
+  int next = 0;
+  for (unsigned int i = 0; i < nq; ++i)
+  {
+    if (redCol[i] == 0)
+    {
+      redCol[i] = next++;
+    }
+  }
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      if (JNT->constrained)
+      {
+        continue;
+      }
+      const RcsJoint* master = JNT->coupledTo;
+      double entry = 1.0;
+      int col = redCol[JNT->jacobiIndex];
+      if (master)
+      {
+        if (master->coupledTo || master->jacobiIndex < 0)
+        {
+          RCSB_FATAL("joint \"%s\" is coupled to \"%s\", which is itself coupled or constrained",
+                     JNT->name, master->name);
+          continue;
+        }
+        entry = RcsJoint_computeSlaveJointVelocity(JNT, self->q->ele[master->jointIndex], 1.0);
+        col = redCol[master->jacobiIndex];
+      }
+      A->ele[(unsigned int) JNT->jacobiIndex * nqr + (unsigned int) col] = entry;
+      sum[col] += entry;
+    }
+  }
+  for (unsigned int c = 0; c < nqr; ++c)
+  {
+    const double scale = fabs(sum[c]);
+    for (unsigned int r = 0; r < nq && scale > 0.0; ++r)
+    {
+      const double a = A->ele[r * nqr + c] / scale;
+      A->ele[r * nqr + c] = a;
+      invA->ele[c * nq + r] = a;
+      sq[c] += a * a;
+    }
+  }
+  for (unsigned int c = 0; c < nqr; ++c)
+  {
+    const double inv = 1.0 / sq[c];
+    for (unsigned int r = 0; r < nq; ++r)
+    {
+      invA->ele[c * nq + r] *= inv;
+    }
+  }
+  free(redCol);
+  free(sum);
+  free(sq);
+  return nCoupled;
+}
+
+/* Gradient of the joint-limit cost 1/2 sum w ((q - q0) / range)^2 over the unconstrained joints
+ * with a non-empty range, at the graph's state (src/RcsCore/Rcs_kinematics.c:1496); dH is
+ * 1 x dof or 1 x nJ. Returns the cost. */
+double RcsGraph_jointLimitGradient(const RcsGraph* self, MatNd* dH, RcsStateType type)
+{
+  const unsigned int n = (type == RcsStateFull) ? self->dof : self->nJ;
+  if (!dH || dH->size < n)
+  {
+    RCSB_FATAL("RcsGraph_jointLimitGradient: dH needs room for %u doubles", n);
+    return 0.0;
+  }
+  MatNd_reshapeAndSetZero(dH, 1, n);
+  double cost = 0.0;
+  RCSGRAPH_TRAVERSE_BODIES(self)
+  {
+    RCSBODY_TRAVERSE_JOINTS(BODY)
+    {
+      const double range = JNT->q_max - JNT->q_min;
+      if (JNT->jacobiIndex < 0 || !(range > 0.0))
+      {
+        continue;
+      }
+      const double d = self->q->ele[JNT->jointIndex] - JNT->q0;
+      dH->ele[type == RcsStateIK ? JNT->jacobiIndex : JNT->jointIndex] = JNT->weightJL * d / (range * range);
+      cost += JNT->weightJL * (d / range) * (d / range);
+    }
+  }
+  return 0.5 * cost;
+}
+
+/* World coordinates of a body-fixed point from the frames of the last forward kinematics
+ * (src/RcsCore/Rcs_kinematics.c:47); NULL body = world frame, NULL point = body origin. */
+void RcsGraph_bodyPoint(const RcsBody* body, const double B_pt[3], double I_pt[3])
+{
+  if (!body)
+  {
+    for (int i = 0; i < 3; ++i)
+    {
+      I_pt[i] = B_pt ? B_pt[i] : 0.0;
+    }
+    return;
+  }
+  const HTr* A = body->A_BI;
+  for (int i = 0; i < 3; ++i)
+  {
+    I_pt[i] = A->org[i];
+    if (B_pt)
+    {
+      I_pt[i] += A->rot[0][i] * B_pt[0] + A->rot[1][i] * B_pt[1] + A->rot[2][i] * B_pt[2];
+    }
+  }
+}
+
 void RcsGraph_getDefaultState(const RcsGraph* self, MatNd* q0)
 {
   MatNd_reshape(q0, self->dof, 1);

@@ -67,7 +67,7 @@ GraphCache* cacheOf(RcsGraph* self)
 
 /* One forward-kinematics pass at (q, qd) [dof each], results into the graph. */
 bool runFk(RcsGraph* self, GraphCache* c, const double* q, const double* qd, bool noCoupling,
-           bool writeBack)
+           bool writeBack, const RcsBody* only = nullptr, bool subTree = false)
 {
   const unsigned int dof = self->dof, nb = RcsGraph_numBodies(self);
   c->frames.resize((size_t) nb * 12);
@@ -88,6 +88,37 @@ bool runFk(RcsGraph* self, GraphCache* c, const double* q, const double* qd, boo
   {
     RCSB_FATAL("forward kinematics failed: %s", rcsb_last_error());
     return false;
+  }
+
+  if (only)
+  {
+    /* RcsGraph_computeBodyKinematics: only this body (or its subtree) takes the new frames;
+     * Jacobian columns are not renumbered (Rcs_graph.c:327-352 passes nJ = NULL) and the
+     * state the Jacobian / dynamics wrappers evaluate at stays that of the last full pass */
+    unsigned int idx = 0;
+    RCSGRAPH_TRAVERSE_BODIES(self)
+    {
+      bool take = (BODY == only);
+      for (const RcsBody* a = BODY->parent; a && subTree && !take; a = a->parent)
+      {
+        take = (a == only);
+      }
+      if (take)
+      {
+        memcpy(BODY->A_BI, &c->frames[(size_t) idx * 12], sizeof(HTr));
+        if (qd)
+        {
+          memcpy(BODY->x_dot, &c->xdot[(size_t) idx * 3], 3 * sizeof(double));
+          memcpy(BODY->omega, &c->omega[(size_t) idx * 3], 3 * sizeof(double));
+        }
+        RCSBODY_TRAVERSE_JOINTS(BODY)
+        {
+          memcpy(&JNT->A_JI, &c->jframes[(size_t) JNT->jointIndex * 12], sizeof(HTr));
+        }
+      }
+      ++idx;
+    }
+    return true;
   }
 
   unsigned int b = 0, nJ = 0;
@@ -247,6 +278,29 @@ extern "C" void RcsGraph_computeForwardKinematics(RcsGraph* self, const MatNd* q
   runFk(self, c, q ? q->ele : self->q->ele, q_dot ? q_dot->ele : self->q_dot->ele, true, false);
 }
 
+extern "C" void RcsGraph_computeBodyKinematics(RcsGraph* self, RcsBody* bdy, const MatNd* q,
+                                               const MatNd* q_dot, bool subTree)
+{
+  if (!self || !bdy)
+  {
+    RCSB_FATAL("RcsGraph_computeBodyKinematics: NULL argument");
+    return;
+  }
+  if ((q && q->m != self->dof) || (q_dot && q_dot->m != self->dof))
+  {
+    RCSB_FATAL("RcsGraph_computeBodyKinematics: q / q_dot must have dof = %d rows", self->dof);
+    return;
+  }
+  GraphCache* c = cacheOf(self);
+  if (!c)
+  {
+    RCSB_FATAL("RcsGraph_computeBodyKinematics: %s", rcsb_last_error());
+    return;
+  }
+  runFk(self, c, q ? q->ele : self->q->ele, q_dot ? q_dot->ele : self->q_dot->ele, true, false, bdy,
+        subTree);
+}
+
 namespace
 {
 
@@ -269,11 +323,6 @@ void jacobianCommon(const RcsGraph* cself, const RcsBody* body, const double* B_
   {
     return;   /* NULL body = world frame: zero Jacobian (Rcs_kinematics.c:188-191, :424-427) */
   }
-  if (A_BI)
-  {
-    RCSB_FATAL("%s: rotation into a frame A_BI is not supported, pass NULL (world frame)", who);
-    return;
-  }
   GraphCache* c = cacheOf(self);
   if (!c)
   {
@@ -294,10 +343,44 @@ void jacobianCommon(const RcsGraph* cself, const RcsBody* body, const double* B_
   if (rc != RCSB_OK)
   {
     RCSB_FATAL("%s: %s", who, rcsb_last_error());
+    return;
+  }
+  if (A_BI)
+  {
+    /* J <- A_BI J: the columns expressed in the frame with rotation matrix A_BI
+     * (MatNd_rotateSelf, Rcs_kinematics.c:160-163, :453-456) */
+    const unsigned int n = self->nJ;
+    for (unsigned int k = 0; k < n; ++k)
+    {
+      const double v[3] = {J->ele[k], J->ele[n + k], J->ele[2 * n + k]};
+      for (int r = 0; r < 3; ++r)
+      {
+        J->ele[r * n + k] = A_BI[r][0] * v[0] + A_BI[r][1] * v[1] + A_BI[r][2] * v[2];
+      }
+    }
   }
 }
 
 }   // namespace
+
+/* Jacobian of a point given in world coordinates that moves with the body
+ * (Rcs_kinematics.c:178): the point is taken into the body frame of the last forward
+ * kinematics; NULL point = body origin. */
+extern "C" void RcsGraph_worldPointJacobian(const RcsGraph* self, const RcsBody* body,
+                                            const double I_pt[3], double A_BI[3][3], MatNd* J)
+{
+  if (!body || !I_pt)
+  {
+    jacobianCommon(self, body, nullptr, A_BI, J, false, "RcsGraph_worldPointJacobian");
+    return;
+  }
+  const HTr* A = body->A_BI;
+  const double d[3] = {I_pt[0] - A->org[0], I_pt[1] - A->org[1], I_pt[2] - A->org[2]};
+  const double B_pt[3] = {A->rot[0][0] * d[0] + A->rot[0][1] * d[1] + A->rot[0][2] * d[2],
+                          A->rot[1][0] * d[0] + A->rot[1][1] * d[1] + A->rot[1][2] * d[2],
+                          A->rot[2][0] * d[0] + A->rot[2][1] * d[1] + A->rot[2][2] * d[2]};
+  jacobianCommon(self, body, B_pt, A_BI, J, false, "RcsGraph_worldPointJacobian");
+}
 
 extern "C" void RcsGraph_bodyPointJacobian(const RcsGraph* self, const RcsBody* body,
                                            const double B_pt[3], double A_BI[3][3], MatNd* J)

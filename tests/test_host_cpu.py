@@ -199,3 +199,98 @@ def test_product_package_never_imports_the_oracle():
             assert "oracle" not in text.replace("oracle/", "oracle/").lower() or \
                 all("import" not in ln and "#include" not in ln and "dlopen" not in ln
                     for ln in text.splitlines() if "oracle" in ln.lower()), path
+
+
+# ---------------------------------------------------------------------------------------------
+# host helpers of the single-state API (O(dof) loops over the joint list; no device needed)
+# ---------------------------------------------------------------------------------------------
+
+class _MatNd(ctypes.Structure):
+    _fields_ = [("ele", ctypes.POINTER(ctypes.c_double)), ("m", ctypes.c_uint), ("n", ctypes.c_uint),
+                ("size", ctypes.c_uint), ("stackMem", ctypes.c_bool)]
+
+
+class _RcsGraph(ctypes.Structure):
+    _fields_ = [("root", ctypes.c_void_p), ("dof", ctypes.c_uint), ("nJ", ctypes.c_uint),
+                ("q", ctypes.POINTER(_MatNd)), ("q_dot", ctypes.POINTER(_MatNd))]
+
+
+def _host_lib():
+    L = rcs_b200.lib()
+    L.MatNd_create.restype = ctypes.POINTER(_MatNd)
+    L.MatNd_create.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    L.RcsGraph_updateSlaveJoints.restype = ctypes.c_bool
+    L.RcsGraph_updateSlaveJoints.argtypes = [ctypes.c_void_p, ctypes.POINTER(_MatNd), ctypes.POINTER(_MatNd)]
+    L.RcsGraph_coupledJointMatrix.restype = ctypes.c_int
+    L.RcsGraph_coupledJointMatrix.argtypes = [ctypes.c_void_p, ctypes.POINTER(_MatNd), ctypes.POINTER(_MatNd)]
+    L.RcsGraph_jointLimitGradient.restype = ctypes.c_double
+    L.RcsGraph_jointLimitGradient.argtypes = [ctypes.c_void_p, ctypes.POINTER(_MatNd), ctypes.c_int]
+    return L
+
+
+def _mat(L, values=None, m=1, n=1):
+    if values is not None:
+        values = np.asarray(values, dtype=np.float64).reshape(-1)
+        m, n = len(values), 1
+    M = L.MatNd_create(m, n)
+    if values is not None:
+        for i, v in enumerate(values):
+            M.contents.ele[i] = v
+    return M
+
+
+def _arr(M):
+    c = M.contents
+    return np.array([c.ele[i] for i in range(c.m * c.n)]).reshape(c.m, c.n)
+
+
+@pytest.mark.parametrize("name", ["wam_scenario", "dexbot", "humanoid", "gantry"])
+def test_slave_joint_update_coupling_matrix_and_limit_gradient_match_the_oracle(name):
+    """RcsGraph_updateSlaveJoints (Rcs_graph.c:2756), RcsGraph_coupledJointMatrix (:2823) and
+    RcsGraph_jointLimitGradient (Rcs_kinematics.c:1496) against the numpy restatement, which
+    tests/test_oracle_cpu.py pins to the reference library."""
+    from oracle import rcs_oracle
+    from rcs_b200 import workload
+
+    L = _host_lib()
+    g = rcs_b200.Graph(graph_file(name))
+    lay = g.layout()
+    o = rcs_oracle.Oracle(lay)
+    q, qd = workload.sample_states(lay, 3, first=99, with_velocity=True)
+    rng = np.random.default_rng(5)
+    for s in range(3):
+        # perturb the slaves so that the update has something to do
+        qs, qds = q[s].copy(), qd[s].copy()
+        slaves = [j["jointIndex"] for j in lay["joints"] if j["coupledTo"] >= 0]
+        qs[slaves] += 0.05 * rng.uniform(-1, 1, len(slaves))
+        Q, QD = _mat(L, qs), _mat(L, qds)
+        moved = L.RcsGraph_updateSlaveJoints(g.handle, Q, QD)
+        want_q, want_qd = o.expand(qs[None, :], qds[None, :])
+        assert moved == (len(slaves) > 0 and bool(np.any(np.abs(want_q[0] - qs) > 1e-8)))
+        np.testing.assert_allclose(_arr(Q)[:, 0], want_q[0], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(_arr(QD)[:, 0], want_qd[0], rtol=0, atol=1e-15)
+
+        # the remaining two read the state held by the graph
+        G = ctypes.cast(g.handle, ctypes.POINTER(_RcsGraph)).contents
+        for i in range(g.dof):
+            G.q.contents.ele[i] = want_q[0, i]
+        nJ = g.nJ
+        nqr = nJ - sum(1 for j in lay["joints"] if j["coupledTo"] >= 0 and not j["constrained"])
+        A, invA = _mat(L, m=nJ, n=max(nqr, 1)), _mat(L, m=max(nqr, 1), n=nJ)
+        assert L.RcsGraph_coupledJointMatrix(g.handle, A, invA) == nJ - nqr
+        A_ref, invA_ref = o.coupled_joint_matrix(want_q)
+        assert _arr(A).shape == (nJ, nqr) and _arr(invA).shape == (nqr, nJ)
+        np.testing.assert_allclose(_arr(A), A_ref[0], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(_arr(invA), invA_ref[0], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(_arr(invA) @ _arr(A), np.eye(nqr), rtol=0, atol=1e-14)
+
+        dH = _mat(L, m=1, n=g.dof)
+        cost = L.RcsGraph_jointLimitGradient(g.handle, dH, 1)            # RcsStateIK
+        dH_ref, cost_ref = o.joint_limit_gradient(want_q)
+        assert _arr(dH).shape == (1, nJ)
+        np.testing.assert_allclose(_arr(dH)[0], dH_ref[0], rtol=0, atol=1e-15)
+        assert abs(cost - cost_ref[0]) <= 1e-14 * max(1.0, abs(cost_ref[0]))
+        cost_full = L.RcsGraph_jointLimitGradient(g.handle, dH, 0)        # RcsStateFull
+        cols = [j["jointIndex"] for j in lay["joints"] if j["jacobiIndex"] >= 0]
+        assert _arr(dH).shape == (1, g.dof) and cost_full == cost
+        np.testing.assert_allclose(_arr(dH)[0, cols], dH_ref[0], rtol=0, atol=1e-15)

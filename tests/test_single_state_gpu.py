@@ -194,3 +194,88 @@ def test_relative_jacobian_wrappers(cuda_device, refmod):
     assert_close(_arr(J), ref[0, 1], what="3dOmegaJacobian")
     L.RcsGraph_3dPosJacobian(g.handle, body(a), None, None, J)
     assert_close(_arr(J), ref[0, 2], what="3dPosJacobian (world)")
+
+
+def test_jacobians_in_a_rotated_frame_world_point_and_body_point(cuda_device):
+    """A_BI != NULL rotates the columns into that frame (MatNd_rotateSelf, Rcs_kinematics.c:160);
+    RcsGraph_worldPointJacobian (:178) takes the point in world coordinates;
+    RcsGraph_bodyPoint (:47) maps a body-fixed point with the frames of the last FK."""
+    L = _lib()
+    Rot = (ctypes.c_double * 3) * 3
+    L.RcsGraph_bodyPointJacobian.argtypes = [ctypes.c_void_p, ctypes.POINTER(RcsBody),
+                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Rot),
+                                             ctypes.POINTER(MatNd)]
+    L.RcsGraph_rotationJacobian.argtypes = [ctypes.c_void_p, ctypes.POINTER(RcsBody), ctypes.POINTER(Rot),
+                                            ctypes.POINTER(MatNd)]
+    L.RcsGraph_worldPointJacobian.argtypes = L.RcsGraph_bodyPointJacobian.argtypes
+    L.RcsGraph_worldPointJacobian.restype = None
+    L.RcsGraph_bodyPoint.argtypes = [ctypes.POINTER(RcsBody), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_double)]
+    L.RcsGraph_bodyPoint.restype = None
+    z = np.load(f"{ROOT}/tests/golden/humanoid.npz")
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    J = _mat(L, m=3, n=g.nJ)
+    L.RcsGraph_setState(g.handle, _mat(L, z["q"][1]), None)
+    e = 0
+    b = int(z["eff"][e])
+    body = L.RcsGraph_getBodyByIndex(g.handle, b)
+    frame = z["fk_A_BI"][1, b]
+    A = frame[3:].reshape(3, 3)
+    rot = Rot(*[(ctypes.c_double * 3)(*row) for row in A])
+    pt = (ctypes.c_double * 3)(*z["pts"][e])
+    L.RcsGraph_bodyPointJacobian(g.handle, body, pt, ctypes.byref(rot), J)
+    assert_close(_arr(J), A @ z["jac_JT"][1, e], what="JT in the body frame")
+    L.RcsGraph_rotationJacobian(g.handle, body, ctypes.byref(rot), J)
+    assert_close(_arr(J), A @ z["jac_JR"][1, e], what="JR in the body frame")
+    I_pt = (ctypes.c_double * 3)()
+    L.RcsGraph_bodyPoint(body, pt, I_pt)
+    want = frame[:3] + A.T @ z["pts"][e]
+    assert_close(np.array(list(I_pt)), want, what="RcsGraph_bodyPoint")
+    L.RcsGraph_worldPointJacobian(g.handle, body, I_pt, None, J)
+    assert_close(_arr(J), z["jac_JT"][1, e], what="worldPointJacobian of the same point")
+    L.RcsGraph_worldPointJacobian(g.handle, body, None, None, J)
+    L.RcsGraph_bodyPointJacobian(g.handle, body, None, None, _mat(L, m=3, n=g.nJ))
+    origin = (ctypes.c_double * 3)()
+    L.RcsGraph_bodyPoint(body, None, origin)
+    assert_close(np.array(list(origin)), frame[:3], what="body origin")
+    L.RcsGraph_bodyPoint(None, pt, origin)
+    assert list(origin) == list(pt)
+
+
+def test_compute_body_kinematics_updates_only_the_subtree(cuda_device):
+    """RcsGraph_computeBodyKinematics (Rcs_graph.c:327): the body (or its subtree) takes the
+    frames of the explicit state, every other body keeps those of the last full pass."""
+    L = _lib()
+    L.RcsGraph_computeBodyKinematics.argtypes = [ctypes.c_void_p, ctypes.POINTER(RcsBody),
+                                                 ctypes.POINTER(MatNd), ctypes.POINTER(MatNd), ctypes.c_bool]
+    L.RcsGraph_computeBodyKinematics.restype = None
+    z = np.load(f"{ROOT}/tests/golden/humanoid.npz")
+    g = rcs_b200.Graph(graph_file("humanoid"))
+    lay = g.layout()
+    names = g.body_names()
+    L.RcsGraph_computeForwardKinematics(g.handle, _mat(L, z["fk_q"][0]), _mat(L, z["qd"][0]))
+    old = _frames(L, g)
+    assert_close(old, z["fk_A_BI"][0], what="state 0")
+    root = names.index("RightSh0")
+    parents = [b["parent"] for b in lay["bodies"]]
+
+    def in_subtree(i):
+        while i >= 0:
+            if i == root:
+                return True
+            i = parents[i]
+        return False
+
+    sub = np.array([in_subtree(i) for i in range(len(names))])
+    assert sub.sum() > 1 and (~sub).sum() > 1
+    L.RcsGraph_computeBodyKinematics(g.handle, L.RcsGraph_getBodyByIndex(g.handle, root),
+                                     _mat(L, z["fk_q"][2]), _mat(L, z["qd"][2]), True)
+    new = _frames(L, g)
+    assert_close(new[sub], z["fk_A_BI"][2][sub], what="subtree at state 2")
+    assert np.array_equal(new[~sub], old[~sub])
+    L.RcsGraph_computeBodyKinematics(g.handle, L.RcsGraph_getBodyByIndex(g.handle, root),
+                                     _mat(L, z["fk_q"][3]), None, False)
+    one = _frames(L, g)
+    assert_close(one[root], z["fk_A_BI"][3][root], what="single body at state 3")
+    keep = np.arange(len(names)) != root
+    assert np.array_equal(one[keep], new[keep])
