@@ -15,6 +15,9 @@ Other workloads (same JSON line, selected with --workload):
            M + h + F_gravity + E; 10,840 algorithmic bytes per state; two kernels per pass.
   ik       configs[3]: 7-DoF arm, XYZ + ABC tasks on BallTip, lambda 1e-8, alpha 0.05,
            10 RMR iterations, 4,194,304 targets in total (strong scaling: sharded over ranks).
+  wholebody configs[4]: humanoid, FK of all 63 bodies + the 20 task-Jacobian rows of the
+           reference's cAction.xml + M(q), 1,048,576 states per GPU; N > 1 adds the all-gather
+           of both hand-tip frames of every state (192 B per state) to the summary statistics.
 
 One step = one pass of the hot path over one batch + (N > 1) one NCCL all-gather of per-rank
 summary statistics, the only collective of the path.
@@ -42,12 +45,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
-UNIT = {"fk": "states/s", "fkm": "states/s", "kinetic": "states/s", "ik": "solves/s"}
+UNIT = {"fk": "states/s", "fkm": "states/s", "kinetic": "states/s", "ik": "solves/s", "wholebody": "states/s"}
+# active task set of the reference's GenericHumanoid/cAction.xml (nx = 20): hand positions, COG x / y,
+# both feet as 6-D poses relative to the Heel
+WB_TASKS = [("XYZ", "RightHandTip"), ("XYZ", "LeftHandTip"), ("COGX", "Heel"), ("COGY", "Heel"),
+            ("XYZABC", "FootL", "Heel"), ("XYZABC", "FootR", "Heel")]
 METRIC = {
     "fk": "FK+Jacobian states/sec FP64 (7-DoF arm, 1M states per GPU)",
     "fkm": "FK+Jacobian+M(q) states/sec FP64 (7-DoF arm, 1M states per GPU)",
     "kinetic": "kinetic terms M,h,g states/sec FP64 (humanoid, 256K states per GPU)",
     "ik": "RMR IK solves/sec FP64 (7-DoF arm, XYZ+ABC, 10 iterations, 4M targets)",
+    "wholebody": "whole-body FK + all-task Jacobians + M(q) states/sec FP64 (humanoid, 1M states per GPU)",
 }
 IK_ITERS, IK_LAMBDA, IK_ALPHA = 10, 1.0e-8, 0.05
 
@@ -109,6 +117,18 @@ class Workload:
                          f"lambda {IK_LAMBDA}, alpha {IK_ALPHA}, {IK_ITERS} iterations per target; targets = "
                          "poses of uniformly sampled states, start = goal state + U(-0.1, 0.1) rad")
             self.l2 = "per-step working set 0.7 GB in total >> 126 MB L2 (no flush needed)"
+        elif name == "wholebody":
+            self.graph, self.eff = "humanoid", None
+            self.per_gpu = 1 << 20
+            self.scaling = "weak"
+            # q + 63 frames + 20 task rows x 34 + M
+            self.bytes_per_unit = 65 * 8 + 63 * 96 + 20 * 34 * 8 + 34 * 34 * 8   # 21256
+            self.kernel = "rcsb::fkKernel (frames; effector chains) + combineKernel + ktWalkKernel + ktAssembleKernel"
+            self.launches_per_step = None
+            self.desc = ("configs[4]: GenericHumanoid (dof 65, nJ 34, 63 bodies), FK of all 63 bodies + the task "
+                         "Jacobians of cAction.xml's active set (hands XYZ, COG x/y, both feet XYZABC relative to "
+                         "the Heel: nx 20) + mass matrix; N > 1: all-gather of both hand-tip frames (192 B per state)")
+            self.l2 = "per-step working set 22 GB per GPU >> 126 MB L2 (no flush needed)"
         else:
             raise SystemExit(f"unknown workload {name}")
         self.graph_file = os.path.join(GRAPHS, self.graph + ".xml")
@@ -164,6 +184,8 @@ class ReferenceRunner:
         self.layout = self.g.layout()
         if wl.name == "ik":
             self.ik = ref.RefIk(wl.graph_file, [("XYZ", wl.eff), ("ABC", wl.eff)])
+        if wl.name == "wholebody":
+            self.ik = ref.RefIk(wl.graph_file, WB_TASKS)
         self.sample = 0
 
     def prepare(self, sample: int):
@@ -174,6 +196,8 @@ class ReferenceRunner:
         if wl.name in ("fk", "fkm"):
             self.q = workload.sample_states(self.layout, sample)
             self.eff = [g.body_index(wl.eff)]
+        elif wl.name == "wholebody":
+            self.q = workload.sample_states(self.layout, sample)
         elif wl.name == "kinetic":
             self.q, self.qd = workload.sample_states(self.layout, sample, with_velocity=True)
         else:
@@ -197,12 +221,20 @@ class ReferenceRunner:
         if wl.name == "kinetic":
             g.kinetic_terms(self.q, self.qd)
             return g.last_seconds
+        if wl.name == "wholebody":
+            # RcsGraph_setState (frames of every body), ControllerBase::computeJ, RcsGraph_computeMassMatrix
+            g.fk(self.q)
+            t = g.last_seconds
+            self.ik.task_kinematics(self.q, want_x=False)
+            t += self.ik.last_seconds
+            g.mass_matrix(self.q)
+            return t + g.last_seconds
         self.ik.rmr(self.q, self.x_des, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS)
         return self.ik.last_seconds
 
     def calibrate(self, target_seconds: float, cap: int) -> int:
         """Sample size (power of two) whose pass takes about target_seconds."""
-        n = {"fk": 1 << 14, "fkm": 1 << 13, "kinetic": 1 << 8, "ik": 1 << 12}[self.wl.name]
+        n = {"fk": 1 << 14, "fkm": 1 << 13, "kinetic": 1 << 8, "ik": 1 << 12, "wholebody": 1 << 8}[self.wl.name]
         self.prepare(n)
         rate = n / max(self.run(), 1e-9)
         want = int(min(cap, max(n, rate * target_seconds)))
@@ -384,6 +416,42 @@ def run_ours(args):
 
         def same():
             return bool(torch.equal(hout["JT"][:1000], out["JT"][:1000].cpu()))
+    elif wl.name == "wholebody":
+        rh, lh, heel, fl, fr = [g.body_index(x) for x in ("RightHandTip", "LeftHandTip", "Heel", "FootL", "FootR")]
+        spec = [("POS", rh, -1, -1), ("POS", lh, -1, -1), ("POS", fl, heel, heel), ("OMEGA", fl, heel, heel),
+                ("POS", fr, heel, heel), ("OMEGA", fr, heel, heel)]
+        q_host = workload.sample_states(lay, n, first=first)
+        q = torch.from_numpy(q_host).to(dev)
+        shapes = {"A_BI": (n, g.n_bodies, 12), "Jt": (n, len(spec), 3, g.nJ), "M": (n, g.nJ, g.nJ),
+                  "Jcog": (n, 3, g.nJ)}
+        out = {k: dev_empty(sh) for k, sh in shapes.items()}
+        # end to end on a bounded slice (pinning 22 GB of host memory is not part of the path)
+        ne = min(n, 1 << 17)
+        hq = pinned((ne, g.dof))
+        hq.copy_(torch.from_numpy(q_host[:ne]))
+        hout = {k: pinned((ne,) + sh[1:]) for k, sh in shapes.items()}
+        h2d, d2h = ne * g.dof * 8, sum(int(np.prod(sh[1:])) for sh in shapes.values()) * ne * 8
+        e2e_units = ne
+        hands = torch.tensor([rh, lh], device=dev)
+        compact = dev_empty((n, 2, 12))
+        gathered_frames = dev_empty((world * n, 2, 12)) if world > 1 else None
+
+        def device_call():
+            m.fk(q, out={"A_BI": out["A_BI"]})
+            m.task_jacobians(q, spec, out=out["Jt"])
+            m.kinetic_terms(q, want=("M", "Jcog"), out={"M": out["M"], "Jcog": out["Jcog"]})
+
+        def host_call():
+            m.fk(hq, out={"A_BI": hout["A_BI"]})
+            m.task_jacobians(hq, spec, out=hout["Jt"])
+            m.kinetic_terms(hq, want=("M", "Jcog"), out={"M": hout["M"], "Jcog": hout["Jcog"]})
+
+        def stat_source():
+            return out["A_BI"][:: 1024, rh, 2]
+
+        def same():
+            return bool(torch.equal(hout["Jt"][:500], out["Jt"][:500].cpu()) and
+                        torch.equal(hout["M"][:500], out["M"][:500].cpu()))
     elif wl.name == "kinetic":
         q_host, qd_host = workload.sample_states(lay, n, first=first, with_velocity=True)
         q, qd = torch.from_numpy(q_host).to(dev), torch.from_numpy(qd_host).to(dev)
@@ -450,6 +518,10 @@ def run_ours(args):
             rcs_b200.summary_stats(stat_source(), out=stats[slot])
             _, work = shard.all_gather_stats(stats[slot], out=gathered[slot], async_op=True)
             pending.append(work)
+            if wl.name == "wholebody":
+                # configs[4]: all-gather of per-state results, the two hand-tip frames of every state
+                torch.index_select(out["A_BI"], 1, hands, out=compact)
+                pending.append(dist.all_gather_into_tensor(gathered_frames, compact, async_op=True))
 
     def drain():
         while pending:
@@ -514,7 +586,8 @@ def run_ours(args):
     te = torch.tensor([t1 - t0], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / float(te.item())
+    e2e_n = e2e_units if wl.name == "wholebody" else n
+    e2e_value = e2e_n * world * e2e_steps / float(te.item())
     device_call()
     torch.cuda.synchronize()
     results_match = same()               # pinned results equal the device results of the same states
@@ -547,7 +620,7 @@ def run_ours(args):
             "data": "synthetic", "config": wl.config(),
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT[wl.name], "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "units_per_step": e2e_n * world,
                     "results_match_device_path": results_match},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -586,7 +659,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fkm", choices=["fkm", "fk", "kinetic", "ik"])
+    ap.add_argument("--workload", default="fkm", choices=["fkm", "fk", "kinetic", "ik", "wholebody"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hold", type=float, default=1.0,
                     help="seconds of extra (untimed) load for the clock sampler")

@@ -160,6 +160,15 @@ int rcsb_direct_dynamics(const RcsbModel* model, long N, int qdim, const double*
 int rcsb_cog(const RcsbModel* model, long N, int qdim, const double* q, double* cog, double* Jcog,
              unsigned flags, void* stream);
 
+/*
+ * rcsb_kinetic_terms and rcsb_cog from ONE pass of the kinetic-terms kernels (the whole-body
+ * evaluation of BASELINE.json configs[4] wants M together with the COG Jacobian rows of its
+ * COGX / COGY tasks). Every output may be NULL.
+ */
+int rcsb_kinetic_terms_cog(const RcsbModel* model, long N, int qdim, const double* q,
+                           const double* qd, double* M, double* h, double* Fg, double* E,
+                           double* cog, double* Jcog, unsigned flags, void* stream);
+
 /* ---- inverse kinematics ----------------------------------------------------------------- */
 
 /*

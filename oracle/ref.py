@@ -253,12 +253,13 @@ class RefIk:
         self.graph = RefGraph("", _handle=L.ref_ik_graph(self._h), _owner=self)
         self.last_seconds = 0.0
 
-    def task_kinematics(self, q):
+    def task_kinematics(self, q, want_x=True):
         q = _c(q)
         N, qdim = q.shape
-        x = np.empty((N, self.nx))
+        x = np.empty((N, self.nx)) if want_x else None
         J = np.empty((N, self.nx, self.graph.nJ))
-        lib().ref_ik_task_kinematics(self._h, N, qdim, _p(q), _p(x), _p(J))
+        self.last_seconds = lib().ref_ik_task_kinematics(self._h, N, qdim, _p(q), _p(x) if want_x else None,
+                                                         _p(J))
         return x, J
 
     def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1):

@@ -117,6 +117,8 @@ def lib() -> ctypes.CDLL:
     sig("rcsb_direct_dynamics", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
         c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_cog", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_kinetic_terms_cog", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+        c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
@@ -396,14 +398,24 @@ class Model:
 
     # -- dynamics ------------------------------------------------------------------------
     def kinetic_terms(self, q, qd=None, want=("M", "h", "Fg", "E"), out=None):
-        """RcsGraph_computeKineticTerms over a batch."""
+        """RcsGraph_computeKineticTerms over a batch; with "cog" / "Jcog" in `want` also
+        RcsGraph_COG / RcsGraph_COGJacobian from the same pass (rcsb_kinetic_terms_cog)."""
         N, qdim = self._batch(q)
-        shapes = {"M": (N, self.nJ, self.nJ), "h": (N, self.nJ), "Fg": (N, self.nJ), "E": (N,)}
+        shapes = {"M": (N, self.nJ, self.nJ), "h": (N, self.nJ), "Fg": (N, self.nJ), "E": (N,),
+                  "cog": (N, 3), "Jcog": (N, 3, self.nJ)}
         out = dict(out or {})
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
         a = _Args(self)
+        if "cog" in out or "Jcog" in out:
+            rc = lib().rcsb_kinetic_terms_cog(
+                self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), a.ptr(out.get("M"), "M"),
+                a.ptr(out.get("h"), "h"), a.ptr(out.get("Fg"), "Fg"), a.ptr(out.get("E"), "E"),
+                a.ptr(out.get("cog"), "cog"), a.ptr(out.get("Jcog"), "Jcog"), a.flags(), a.stream(),
+            )
+            _err(rc, "rcsb_kinetic_terms_cog")
+            return out
         rc = lib().rcsb_kinetic_terms(
             self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), a.ptr(out.get("M"), "M"),
             a.ptr(out.get("h"), "h"), a.ptr(out.get("Fg"), "Fg"), a.ptr(out.get("E"), "E"),

@@ -402,6 +402,113 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   {
     ph.zeroRow = ph.nScrRows++;
   }
+
+  /* pruned walk: selected bodies, effector bodies and their ancestors */
+  std::vector<int> visit, jntNext((size_t) (dof > 0 ? dof : 1), -1);
+  ph.firstJnt = -1;
+  if (nSel > 0 && !withMass)
+  {
+    const int* parent = m->iarr(RCSB_A_BODY_PARENT);
+    const int* jStart = m->iarr(RCSB_A_BODY_JNT_START);
+    const int* jCount = m->iarr(RCSB_A_BODY_JNT_COUNT);
+    std::vector<char> need((size_t) nb, 0);
+    auto mark = [&](int b) {
+      for (; b >= 0 && !need[(size_t) b]; b = parent[b])
+      {
+        need[(size_t) b] = 1;
+      }
+    };
+    for (int i = 0; i < nSel; ++i)
+    {
+      mark(bodySel[i]);
+    }
+    for (int e = 0; e < nEff; ++e)
+    {
+      mark(effBody[e]);
+    }
+    int nNeed = 0;
+    for (int b = 0; b < nb; ++b)
+    {
+      nNeed += need[(size_t) b];
+    }
+    if (nNeed < nb)
+    {
+      /* the same simulation of the depth-first walk as in the flattener (rcsb_model.c),
+       * restricted to the sub-tree */
+      std::vector<int> kids((size_t) nb, 0), needSlot((size_t) nb, 0), loadKind((size_t) nb, 0),
+        slotOf((size_t) nb, -1), depth((size_t) nb, 0);
+      for (int b = 0; b < nb; ++b)
+      {
+        if (need[(size_t) b] && parent[b] >= 0)
+        {
+          kids[(size_t) parent[b]]++;
+        }
+      }
+      int cur = -1;
+      for (int b = 0; b < nb; ++b)
+      {
+        if (!need[(size_t) b])
+        {
+          continue;
+        }
+        const int pb = parent[b];
+        if (pb < 0)
+        {
+          loadKind[(size_t) b] = RCSB_LOAD_IDENT;
+        }
+        else if (cur == pb)
+        {
+          loadKind[(size_t) b] = RCSB_LOAD_CONT;
+        }
+        else
+        {
+          loadKind[(size_t) b] = 0;
+          needSlot[(size_t) pb] = 1;
+        }
+        cur = (kids[(size_t) b] == 0 && pb >= 0) ? pb : b;
+      }
+      int slots = 0, lastJ = -1;
+      for (int b = 0; b < nb; ++b)
+      {
+        if (!need[(size_t) b])
+        {
+          continue;
+        }
+        const int pb = parent[b];
+        const int inherited = pb >= 0 ? depth[(size_t) pb] : 0;
+        depth[(size_t) b] = inherited;
+        if (needSlot[(size_t) b])
+        {
+          slotOf[(size_t) b] = inherited;
+          depth[(size_t) b] = inherited + 1;
+          slots = depth[(size_t) b] > slots ? depth[(size_t) b] : slots;
+        }
+        visit.insert(visit.end(), {b, loadKind[(size_t) b] == 0 ? slotOf[(size_t) pb] : loadKind[(size_t) b],
+                                   slotOf[(size_t) b], (kids[(size_t) b] == 0 && pb >= 0) ? 1 : 0});
+        for (int j = jStart[b]; j < jStart[b] + jCount[b]; ++j)
+        {
+          if (lastJ >= 0)
+          {
+            jntNext[(size_t) lastJ] = j;
+          }
+          else
+          {
+            ph.firstJnt = j;
+          }
+          lastJ = j;
+        }
+      }
+      if (slots <= RCSB_MAX_FRAME_SLOTS)
+      {
+        ph.nVisit = (int) visit.size() / 4;
+        ph.prunedSlots = slots;
+      }
+    }
+  }
+  if (visit.empty())
+  {
+    visit.assign(4, 0);
+  }
   ph.jacRecord = rec;
   ph.inPlace = inPlace ? 1 : 0;
   {
@@ -442,6 +549,10 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   off = align16(off + nb * 4);
   ph.offMassList = off;
   off = align16(off + (int) massList.size() * 4);
+  ph.offVisit = off;
+  off = align16(off + (int) visit.size() * 4);
+  ph.offJntNext = off;
+  off = align16(off + (int) jntNext.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob(ph.totalBytes, 0);
@@ -460,6 +571,8 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   memcpy(blob.data() + ph.offEffChain, effChain.data(), effChain.size() * 4);
   memcpy(blob.data() + ph.offBodyPathMask, pathMask.data(), (size_t) nb * 4);
   memcpy(blob.data() + ph.offMassList, massList.data(), massList.size() * 4);
+  memcpy(blob.data() + ph.offVisit, visit.data(), visit.size() * 4);
+  memcpy(blob.data() + ph.offJntNext, jntNext.data(), jntNext.size() * 4);
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -470,6 +583,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   dp.nSel = nOut;
   dp.nEff = nEff;
   dp.aux0 = ph.massChain;
+  dp.aux1 = ph.nVisit > 0 ? ph.prunedSlots + 1 : 0;   /* 0: no pruned walk */
 
   auto ins = m->fkPlans.emplace(key, dp);
   *out = &ins.first->second;
@@ -503,6 +617,9 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.noCoupling = noCoupling ? 1 : 0;
   /* composite (tip-to-root) mass matrix when the plan allows it and the frames are written */
   a.massMode = M ? ((plan->aux0 && A_BI) ? 2 : 1) : 0;
+  /* per-joint outputs and velocities need every body: the pruned walk serves frames and
+   * Jacobians of a body selection only */
+  a.pruned = (plan->aux1 > 0 && !A_JI && !qOut && !qd && !qdOut && !M) ? 1 : 0;
   a.scrDoubles = plan->nScrRows * (RCSB_FK_BLOCK(M != nullptr) + 1);
   RCSB_CUDA(cudaSetDevice(m->device));
   if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
@@ -512,7 +629,7 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
                    rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows), RCSB_SMEM_LIMIT);
     return RCSB_EUNSUPPORTED;
   }
-  RCSB_CUDA(rcsb_launch_fk(&a, m->hdr.nSlots, plan->nScrRows, stream));
+  RCSB_CUDA(rcsb_launch_fk(&a, a.pruned ? plan->aux1 - 1 : m->hdr.nSlots, plan->nScrRows, stream));
   if (N > 0)
   {
     g_launches.fetch_add(1);

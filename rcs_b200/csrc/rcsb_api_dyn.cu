@@ -387,6 +387,17 @@ extern "C" int rcsb_cog(const RcsbModel* cm, long N, int qdim, const double* q, 
   return ktCommon(cm, N, qdim, q, nullptr, nullptr, nullptr, nullptr, nullptr, x, flags, stream);
 }
 
+extern "C" int rcsb_kinetic_terms_cog(const RcsbModel* cm, long N, int qdim, const double* q,
+                                      const double* qd, double* M, double* h, double* Fg,
+                                      double* E, double* cog, double* Jcog, unsigned flags,
+                                      void* stream)
+{
+  KtExtra x;
+  x.cog = cog;
+  x.Jcog = Jcog;
+  return ktCommon(cm, N, qdim, q, qd, M, h, Fg, E, x, flags, stream);
+}
+
 extern "C" int rcsb_direct_dynamics(const RcsbModel* cm, long N, int qdim, const double* q,
                                     const double* qd, const double* Fext, const double* Fjnt,
                                     double* qdd, double* E, unsigned flags, void* stream)

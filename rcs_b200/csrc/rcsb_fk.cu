@@ -41,6 +41,8 @@ struct PlanView
   const int* effChain;
   const int* bodyPathMask;
   const int4* massList;
+  const int4* visit;
+  const int* jntNext;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -56,6 +58,8 @@ struct PlanView
     effChain = reinterpret_cast<const int*>(blob + hdr->offEffChain);
     bodyPathMask = reinterpret_cast<const int*>(blob + hdr->offBodyPathMask);
     massList = reinterpret_cast<const int4*>(blob + hdr->offMassList);
+    visit = reinterpret_cast<const int4*>(blob + hdr->offVisit);
+    jntNext = reinterpret_cast<const int*>(blob + hdr->offJntNext);
   }
 };
 
@@ -81,7 +85,9 @@ struct PlanView
 #endif
 /* with velocities: 3 resident blocks per SM pay off for shallow frame stacks (arm: 0.58 ->
  * 0.45 ms per 1M states), not for deep ones (humanoid: spills) */
-template <bool VEL, bool ALIGNED32, int NSLOTS, int MASS>
+/* PRUNED: the caller selected some bodies only; the walk visits them, the effector bodies and
+ * their ancestors (plan tables visit / jntNext) instead of the whole tree. */
+template <bool VEL, bool ALIGNED32, int NSLOTS, int MASS, bool PRUNED = false>
 __global__ void __launch_bounds__(RCSB_FK_BLOCK(MASS), MASS == 2 ? RCSB_FKM_CHAIN_BLOCKS : (MASS ? RCSB_FKM_MIN_BLOCKS : (VEL ? (NSLOTS <= 2 ? 3 : 1) : 4)))
 fkKernel(const FkArgs a)
 {
@@ -164,34 +170,65 @@ fkKernel(const FkArgs a)
   double xd[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
   setIdentity(f);
   double nextQ = 0.0, nextQd = 0.0;
-  if (dof > 0)
+  const int jFirst = PRUNED ? p.hdr->firstJnt : (dof > 0 ? 0 : -1);
+  if (jFirst >= 0)
   {
-    nextQ = rd.fetchQ(m, 0);
+    nextQ = rd.fetchQ(m, jFirst);
     if (VEL)
     {
-      nextQd = rd.fetchQd(m, 0);
+      nextQd = rd.fetchQd(m, jFirst);
     }
   }
 
   /* the model lives in shared memory next to the Jacobian scratch the kernel writes, so the
    * compiler cannot hoist its loads: the per-body and per-joint descriptors are fetched one
    * step ahead by hand */
-  int nLd = m.bodyLoad[0], nFlags = m.bodyFlags[0], nJ0 = m.bodyJntStart[0], nCnt = m.bodyJntCount[0];
-  int nJf = dof > 0 ? m.jntFlags[0] : 0, nType = dof > 0 ? m.jntType[0] : 0;
+  const int nWalk = PRUNED ? p.hdr->nVisit : nb;
+  int nBody = 0, nLd, nFlags, nSave = -1, nJ0, nCnt;
+  if (PRUNED)
+  {
+    const int4 v = p.visit[0];
+    nBody = v.x;
+    nLd = v.y;
+    nSave = v.z;
+    nFlags = (m.bodyFlags[nBody] & ~RCSB_BF_LEAF) | (v.w ? RCSB_BF_LEAF : 0);
+  }
+  else
+  {
+    nLd = m.bodyLoad[0];
+    nFlags = m.bodyFlags[0];
+  }
+  nJ0 = m.bodyJntStart[nBody];
+  nCnt = m.bodyJntCount[nBody];
+  int nJf = jFirst >= 0 ? m.jntFlags[jFirst] : 0, nType = jFirst >= 0 ? m.jntType[jFirst] : 0;
 
-  for (int b = 0; b < nb; ++b)
+  for (int vi = 0; vi < nWalk; ++vi)
   {
     /* ---- parent frame ---------------------------------------------------------------- */
+    const int b = PRUNED ? nBody : vi;
     const int ld = nLd;
     const int bflags = nFlags;
+    const int svp = nSave;
     const int j0 = nJ0;
     const int j1 = j0 + nCnt;
-    if (b + 1 < nb)
+    if (vi + 1 < nWalk)
     {
-      nLd = m.bodyLoad[b + 1];
-      nFlags = m.bodyFlags[b + 1];
-      nJ0 = m.bodyJntStart[b + 1];
-      nCnt = m.bodyJntCount[b + 1];
+      if (PRUNED)
+      {
+        const int4 v = p.visit[vi + 1];
+        nBody = v.x;
+        nLd = v.y;
+        nSave = v.z;
+        nFlags = (m.bodyFlags[nBody] & ~RCSB_BF_LEAF) | (v.w ? RCSB_BF_LEAF : 0);
+      }
+      else
+      {
+        nBody = vi + 1;
+        nLd = m.bodyLoad[vi + 1];
+        nFlags = m.bodyFlags[vi + 1];
+      }
+      nJ0 = m.bodyJntStart[nBody];
+      nCnt = m.bodyJntCount[nBody];
     }
     if (ld == RCSB_LOAD_IDENT)
     {
@@ -247,10 +284,11 @@ fkKernel(const FkArgs a)
     {
       const int jf = nJf;
       const int jtype = nType;
-      if (j + 1 < dof)
+      const int jn = PRUNED ? p.jntNext[j] : (j + 1 < dof ? j + 1 : -1);
+      if (jn >= 0)
       {
-        nJf = m.jntFlags[j + 1];
-        nType = m.jntType[j + 1];
+        nJf = m.jntFlags[jn];
+        nType = m.jntType[jn];
       }
       if (jf & RCSB_JF_HAS_AJP)
       {
@@ -260,12 +298,12 @@ fkKernel(const FkArgs a)
       /* joints are visited in jointIndex order: the loads of the next joint are in flight
        * while this one is processed */
       const double rawQ = nextQ, rawQd = nextQd;
-      if (j + 1 < dof)
+      if (jn >= 0)
       {
-        nextQ = rd.fetchQ(m, j + 1);
+        nextQ = rd.fetchQ(m, jn);
         if (VEL)
         {
-          nextQd = rd.fetchQd(m, j + 1);
+          nextQd = rd.fetchQd(m, jn);
         }
       }
       const double qj = rd.finishQ(m, j, rawQ);
@@ -386,7 +424,7 @@ fkKernel(const FkArgs a)
 
     if (NSLOTS > 0)
     {
-      const int sv = m.bodySave[b];
+      const int sv = PRUNED ? svp : m.bodySave[b];
       if (sv >= 0)
       {
         double* sp = stk + sv * SLOT_DOUBLES;
@@ -875,13 +913,13 @@ fkKernel(const FkArgs a)
   }
 }
 
-template <bool VEL, bool ALIGNED32, int MASS>
+template <bool VEL, bool ALIGNED32, int MASS, bool PRUNED = false>
 static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t smemBytes,
                                cudaStream_t stream)
 {
 #define RCSB_LAUNCH(NS)                                                                        \
   {                                                                                            \
-    auto k = fkKernel<VEL, ALIGNED32, NS, MASS>;                                               \
+    auto k = fkKernel<VEL, ALIGNED32, NS, MASS, PRUNED>;                                       \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int) smemBytes);                                     \
     if (e != cudaSuccess)                                                                      \
@@ -945,6 +983,11 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
   {
     return al ? launchSlots<true, true, 0>(*a, nSlots, grid, smemBytes, stream)
               : launchSlots<true, false, 0>(*a, nSlots, grid, smemBytes, stream);
+  }
+  if (a->pruned)
+  {
+    return al ? launchSlots<false, true, 0, true>(*a, nSlots, grid, smemBytes, stream)
+              : launchSlots<false, false, 0, true>(*a, nSlots, grid, smemBytes, stream);
   }
   return al ? launchSlots<false, true, 0>(*a, nSlots, grid, smemBytes, stream)
             : launchSlots<false, false, 0>(*a, nSlots, grid, smemBytes, stream);

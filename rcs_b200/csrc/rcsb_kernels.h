@@ -41,6 +41,7 @@ struct FkArgs
   double* M;           /* N x nJ x nJ mass matrix (fused path, plans built with mass = 1) */
   double* qdOut;       /* N x dof joint rates after expansion and coupling (needs qd) */
   int massMode;        /* 0: no M; 1: per-column momentum accumulators; 2: serial chain, composites */
+  int pruned;          /* 1: walk the plan's sub-tree only (body selections without velocities) */
   int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
   int scrDoubles;      /* doubles of the Jacobian scratch: nScrRows x (RCSB_FK_THREADS + 1) */
 };

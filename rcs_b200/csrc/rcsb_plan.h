@@ -67,6 +67,16 @@ typedef struct
   int nMass;           /* entries of the list */
   int offMassList;     /* int4[nMass]: {body, output slot, number of columns moving it, 0} */
   int zeroRow;         /* scratch row kept at zero (last row): structural zeros of JT / JR */
+  /* pruned walk (fkKernel<..., PRUNED>): when only some bodies are asked for, the walk visits
+   * them, the effector bodies and their ancestors only; the frame-stack program is rebuilt for
+   * that sub-tree */
+  int nVisit;          /* 0: the plan has no pruned walk (every body is needed) */
+  int offVisit;        /* int4[nVisit]: {body, parent-frame source (RCSB_LOAD_*, or slot), slot to
+                          save the frame in or -1, 1 if the body is a leaf of the sub-tree} */
+  int offJntNext;      /* int[dof]: joint visited after joint j, -1 = none */
+  int firstJnt;        /* first joint of the pruned walk, -1 = none */
+  int prunedSlots;     /* frame-stack depth of the pruned walk */
+  int pad[3];
 } RcsbFkPlanHeader;
 
 /*

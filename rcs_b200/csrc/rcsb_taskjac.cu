@@ -13,6 +13,7 @@
  * the intermediate stays in L2; combineKernel turns them into the task rows, one thread per
  * (state, task, column), consecutive threads on consecutive columns.
  */
+#include <cstdlib>
 #include "rcsb_priv.h"
 
 namespace
@@ -237,7 +238,12 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
       const int g = groups.empty() ? 0 : (int) groups.back().size();
       const int rows = 6 * (nChain + add) + 3 * (g + 1);
       /* plan blobs are small next to the scratch; 8 KB covers them */
-      if (groups.empty() || fkSharedBytes(m, 8192 + 8 * 3 * nJ * (g + 1), rows) > RCSB_SMEM_LIMIT)
+      /* one body per launch by default: with the pruned walk a launch visits that body's
+       * ancestors only and its scratch leaves room for two blocks per SM (measured on the
+       * humanoid's cAction task set: 10.2 ms per 1M states with full groups, 8.0 ms with 1) */
+      static const int maxGroup = getenv("RCSB_TASKJAC_GROUP") ? atoi(getenv("RCSB_TASKJAC_GROUP")) : 1;
+      if (groups.empty() || g >= maxGroup ||
+          fkSharedBytes(m, 8192 + 8 * 3 * nJ * (g + 1), rows) > RCSB_SMEM_LIMIT)
       {
         groups.emplace_back();
         std::fill(onChain.begin(), onChain.end(), 0);
@@ -260,7 +266,8 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
   RCSB_CUDA(cudaSetDevice(m->device));
 
-  const long chunk = N < 32768 ? N : 32768;
+  static const long passStates = getenv("RCSB_TASKJAC_PASS") ? atol(getenv("RCSB_TASKJAC_PASS")) : 32768;
+  const long chunk = N < passStates ? N : passStates;
   const size_t perState = (size_t) nU * (12 + 6 * (size_t) nJ);
   const size_t tmpDoubles = (size_t) chunk * perState;
   const size_t outDoubles = host ? (size_t) chunk * nJac * 3 * nJ : 0;

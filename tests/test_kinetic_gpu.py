@@ -102,6 +102,12 @@ def test_cog_and_cog_jacobian(name, n, refmod, cuda_device):
     assert_structural_zeros(ours["Jcog"], jcog_ref, what=f"{name}:Jcog")
     dev = m.cog(torch.from_numpy(q).cuda(cuda_device), want=("Jcog",))
     assert_close(dev["Jcog"].cpu().numpy(), jcog_ref, what=f"{name}:Jcog (device pointers)")
+    # rcsb_kinetic_terms_cog: the same from the pass that also builds M
+    launches0 = rcs_b200.kernel_launch_count()
+    both = m.kinetic_terms(q, want=("M", "Jcog", "cog"))
+    assert rcs_b200.kernel_launch_count() - launches0 == 2
+    assert np.array_equal(both["Jcog"], ours["Jcog"]) and np.array_equal(both["cog"], ours["cog"])
+    assert np.array_equal(both["M"], m.kinetic_terms(q, want=("M",))["M"])
 
 
 @pytest.mark.parametrize("name,n", [("wam_arm", 2000), ("wam_scenario", 300), ("humanoid", 200), ("husky", 100)])
