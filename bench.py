@@ -521,7 +521,7 @@ def run_ours(args):
             if wl.name == "wholebody":
                 # configs[4]: all-gather of per-state results, the two hand-tip frames of every state
                 torch.index_select(out["A_BI"], 1, hands, out=compact)
-                pending.append(dist.all_gather_into_tensor(gathered_frames, compact, async_op=True))
+                pending.append(shard.all_gather_results(compact, out=gathered_frames, async_op=True)[1])
 
     def drain():
         while pending:

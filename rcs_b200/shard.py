@@ -2,8 +2,9 @@
 
 States are independent and the model is tiny and replicated, so the batch is cut into
 contiguous slices and there is no data-path collective; the only exchange is one all-gather
-of compact per-rank summary statistics — NCCL over NVLink on the GPU box,
-gloo in the CPU tests.
+of compact per-rank summary statistics, or of compact per-state results of equal
+slices (configs[4]: the hand-tip frames of every state) — NCCL over NVLink on the GPU box, gloo
+in the CPU tests.
 """
 from __future__ import annotations
 
@@ -76,3 +77,22 @@ def all_gather_stats(stats, out=None, async_op=False):
     work = dist.all_gather_into_tensor(out, t.contiguous(), async_op=async_op)
     g = out.reshape(world, -1)
     return (g, work) if async_op else g
+
+
+def all_gather_results(local, out=None, async_op=False):
+    """All-gather of compact per-state results [n_local x ...] of equally sized slices into
+    [world * n_local x ...], rank r's rows at [r * n_local, (r + 1) * n_local): with
+    slice_of() that is the order of the global state sequence. Same calling convention as
+    all_gather_stats."""
+    import torch
+    import torch.distributed as dist
+
+    t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
+    if not (dist.is_available() and dist.is_initialized()):
+        g = t.clone()
+        return (g, None) if async_op else g
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    work = dist.all_gather_into_tensor(out, t.contiguous(), async_op=async_op)
+    return (out, work) if async_op else out

@@ -73,14 +73,21 @@ def _worker(rank, world, port, n_global, ret):
         # timing reduction used by bench.py: max over ranks
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ret[rank] = (merged, float(t.item()), gathered.numpy().copy())
+        # configs[4]: all-gather of compact per-state results (here the effector frame)
+        frames = heights = None
+        if n_global % world == 0:                            # the collective needs equal slices
+            frames = shard.all_gather_results(
+                torch.from_numpy(np.ascontiguousarray(o.fk(q)["A_BI"][:, tip]))).numpy().copy()
+            work_out, work = shard.all_gather_results(torch.from_numpy(height.copy()), async_op=True)
+            work.wait()
+            heights = work_out.numpy().copy()
+        ret[rank] = (merged, float(t.item()), gathered.numpy().copy(), frames, heights)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_all_gather_of_summary_statistics(world):
-    n_global = 1001
+@pytest.mark.parametrize("world,n_global", [(2, 1000), (3, 1001), (2, 1001)])
+def test_all_gather_of_summary_statistics(world, n_global):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n_global, ret), nprocs=world, join=True)
@@ -90,8 +97,11 @@ def test_all_gather_of_summary_statistics(world):
     lay = _layout("wam_arm")
     tip = [b["name"] for b in lay["bodies"]].index("BallTip")
     height = rcs_oracle.Oracle(lay).fk(workload.sample_states(lay, n_global))["A_BI"][:, tip, 2]
+    frames_all = rcs_oracle.Oracle(lay).fk(workload.sample_states(lay, n_global))["A_BI"][:, tip]
     for r in range(world):
-        merged, tmax, gathered = ret[r]
+        merged, tmax, gathered, frames, heights = ret[r]
+        if n_global % world == 0:                            # equal slices: rows in global order
+            assert np.array_equal(frames, frames_all) and np.array_equal(heights, height)
         assert tmax == float(world)
         assert np.array_equal(gathered, ret[0][2])          # every rank holds the same table
         assert merged["count"] == n_global
