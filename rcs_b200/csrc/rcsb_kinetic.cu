@@ -515,29 +515,44 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   const bool stage = a.stageM != 0;
   const double grav = 9.81;
 
-  /* The record of the group's next state is fetched into registers while the current state is
-   * assembled (PF doubles per lane; longer records fall back to a plain copy loop). */
-  constexpr int PF = 32;
-  const bool prefetch = R <= PF * LPS;
-  double nxt[PF];
+  /* The record of a state (R doubles, a multiple of 32 bytes, contiguous in global memory) comes
+   * in as ONE bulk asynchronous copy (TMA, cp.async.bulk) straight into the group's region,
+   * completion on the group's mbarrier: no per-lane loads, no staging registers. The copy of
+   * the group's next state is issued as soon as the record region is dead: after the column
+   * phase when M goes straight to global memory, at the end of the iteration when the region
+   * is reused (matrix staging of the direct dynamics, COG sums). */
+  __shared__ __align__(8) unsigned long long recBar[GPB];
+  const unsigned int barAddr = (unsigned int) __cvta_generic_to_shared(&recBar[grp]);
+  const unsigned int bufAddr = (unsigned int) __cvta_generic_to_shared(buf);
+  const unsigned int recBytes = (unsigned int) R * 8u;
+  if (gl == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   auto fetch = [&](long state) {
-    const double* src = a.rec + (state < a.N ? state : a.N - 1) * R;
-#pragma unroll
-    for (int t = 0; t < PF; ++t)
+    /* every lane of the group has finished with the region (warp barrier before the call);
+     * order those generic-proxy accesses before the asynchronous write */
+    if (gl == 0)
     {
-      const int e = gl + t * LPS;
-      if (e < R)
-      {
-        nxt[t] = src[e];
-      }
+      const double* src = a.rec + (state < a.N ? state : a.N - 1) * R;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(recBytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(bufAddr), "l"(src), "r"(recBytes), "r"(barAddr)
+                   : "memory");
     }
   };
+  const bool earlyFetch = !stage && !a.cog && !a.Jcog;
+  unsigned int phase = 0;
 
   /* all groups of a warp iterate together (warp-level barriers inside) */
   const long nGroupsTotal = (a.N + GPB - 1) / GPB * GPB;
   const long sFirst = (long) blockIdx.x * GPB + grp;
   const long sStep = (long) gridDim.x * GPB;
-  if (prefetch && sFirst < nGroupsTotal)
+  if (sFirst < nGroupsTotal)
   {
     fetch(sFirst);
   }
@@ -546,29 +561,18 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     const bool valid = s < a.N;
     const long sc = valid ? s : a.N - 1;
 
-    if (prefetch)
     {
-#pragma unroll
-      for (int t = 0; t < PF; ++t)
+      unsigned int done;
+      do
       {
-        const int e = gl + t * LPS;
-        if (e < R)
-        {
-          buf[e] = nxt[t];
-        }
-      }
-      if (s + sStep < nGroupsTotal)
-      {
-        fetch(s + sStep);
-      }
-    }
-    else
-    {
-      const double* src = a.rec + sc * R;
-      for (int e = gl; e < R; e += LPS)
-      {
-        buf[e] = src[e];
-      }
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(barAddr), "r"(phase)
+                     : "memory");
+      } while (!done);
+      phase ^= 1u;
     }
     __syncwarp();
 
@@ -691,6 +695,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
     }
     __syncwarp();
+    if (earlyFetch && s + sStep < nGroupsTotal)
+    {
+      fetch(s + sStep);   /* the record region is dead from here on */
+    }
 
     /* ---- centre of gravity and its Jacobian (RcsGraph_COG / RcsGraph_COGJacobian,
      * Rcs_kinematics.c:904, :973): column k of sum_b m_b JT_b is the linear momentum p of
@@ -902,6 +910,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
     }
     __syncwarp();
+    if (!earlyFetch && s + sStep < nGroupsTotal)
+    {
+      fetch(s + sStep);
+    }
   }
 }
 
