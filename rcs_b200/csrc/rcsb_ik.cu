@@ -189,12 +189,13 @@ __device__ __forceinline__ void rotationTaskError(double dx[3], const double Ad[
     ax[0] = R[5] - R[7];
     ax[1] = R[6] - R[2];
     ax[2] = R[1] - R[3];
-    const double len = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
-    if (len > 0.0)
+    const double len2 = ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2];
+    if (len2 > 0.0)
     {
-      ax[0] /= len;
-      ax[1] /= len;
-      ax[2] /= len;
+      const double inv = rsqrt(len2);
+      ax[0] *= inv;
+      ax[1] *= inv;
+      ax[2] *= inv;
     }
   }
   else
@@ -1022,11 +1023,13 @@ ikChainKernel(const IkArgs a)
         }
         else
         {
+          /* L_ii = sqrt(pivot) and 1 / L_ii from one reciprocal square root (the sqrt + divide
+           * pair sits on the critical path of the factorisation); det = prod L_ii^2 = prod pivot */
           ok = ok && (sum > 0.0);
-          const double d = sqrt(ok ? sum : 1.0);
-          A[i * (i + 1) / 2 + i] = d;
-          invd[i] = 1.0 / d;
-          det *= d * d;
+          const double piv = ok ? sum : 1.0;
+          invd[i] = rsqrt(piv);
+          A[i * (i + 1) / 2 + i] = piv * invd[i];
+          det *= piv;
         }
       }
     }
@@ -1173,10 +1176,10 @@ __device__ __forceinline__ bool choleskySolve(double (&A)[NX * (NX + 1) / 2], co
       else
       {
         ok = ok && (sum > 0.0);
-        const double d = sqrt(ok ? sum : 1.0);
-        A[i * (i + 1) / 2 + i] = d;
-        invd[i] = 1.0 / d;
-        det *= d * d;
+        const double piv = ok ? sum : 1.0;
+        invd[i] = rsqrt(piv);
+        A[i * (i + 1) / 2 + i] = piv * invd[i];
+        det *= piv;
       }
     }
   }
