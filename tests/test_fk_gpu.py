@@ -184,3 +184,45 @@ def test_too_many_effector_chains_is_a_clear_error(cuda_device):
     effs = [g.body_index(n) for n in ("RightHandTip", "LeftHandTip", "FootL", "FootR", "Helmet")]
     with pytest.raises(rcs_b200.RcsbError, match="shared memory"):
         m.fk_jacobians(np.zeros((4, g.dof)), effs)
+
+
+@pytest.mark.parametrize("name,n", [("wam_arm", 1), ("wam_arm", 33), ("wam_arm", 1000), ("gantry", 257),
+                                    ("humanoid", 95)])
+def test_unaligned_outputs_ragged_batches_and_body_selections(name, n, refmod, cuda_device):
+    """Output arrays that are only 8-byte aligned take the scalar store / load paths (frames
+    written and, for the fused mass matrix of a serial chain, read back); batch sizes that are
+    not a multiple of the warp or block size leave idle lanes; a body selection walks the
+    pruned sub-tree. Same results in every combination."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    q = workload.sample_states(g.layout(), n, first=3)
+    dq = torch.from_numpy(q).cuda(cuda_device)
+    eff = [g.n_bodies - 1]
+    ref = r.fk_jacobians(q, eff)
+    want = ("A_BI", "JT", "JR", "M") if g.nJ <= 8 else ("A_BI", "JT", "JR")
+
+    def odd(shape):
+        """torch tensor whose data pointer is 8 bytes past a 32-byte boundary"""
+        flat = torch.zeros(int(np.prod(shape)) + 4, dtype=torch.float64, device=dq.device)
+        assert flat.data_ptr() % 32 == 0
+        return flat[1:1 + int(np.prod(shape))].view(shape)
+
+    shapes = {"A_BI": (n, g.n_bodies, 12), "JT": (n, 1, 3, g.nJ), "JR": (n, 1, 3, g.nJ), "M": (n, g.nJ, g.nJ)}
+    out = {k: odd(shapes[k]) for k in want}
+    assert all(v.data_ptr() % 32 == 8 for v in out.values())
+    m.fk_jacobians(dq, eff, want=want, out=out)
+    torch.cuda.synchronize()
+    for k in ("A_BI", "JT", "JR"):
+        assert_close(out[k].cpu().numpy(), ref[k], what=f"{name}:{k} (unaligned)")
+    if "M" in want:
+        assert_close(out["M"].cpu().numpy(), r.mass_matrix(q), what=f"{name}:M (unaligned)")
+    # pruned walk: the effector and one more body, unaligned as well
+    sel = [eff[0], g.n_bodies // 2]
+    frames = odd((n, 2, 12))
+    pr = m.fk_jacobians(dq, eff, bodies=sel, want=("A_BI", "JT"), out={"A_BI": frames})
+    torch.cuda.synchronize()
+    assert_close(pr["A_BI"].cpu().numpy(), ref["A_BI"][:, sel], what=f"{name}: selected frames")
+    assert_close(pr["JT"].cpu().numpy(), ref["JT"], what=f"{name}: JT from the pruned walk")
+    only = m.fk(dq, bodies=[g.n_bodies // 3])["A_BI"]
+    assert_close(only.cpu().numpy(), ref["A_BI"][:, [g.n_bodies // 3]], what=f"{name}: one frame")
