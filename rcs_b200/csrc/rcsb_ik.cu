@@ -61,6 +61,7 @@ struct IkPlanView
   const int* progStart;
   const int4* prog;
   const int* chainType;
+  const double* chainXf;
   const int* chainJoint;
   const double* chainW;
   const double* chainGain;
@@ -83,6 +84,7 @@ struct IkPlanView
     progStart = reinterpret_cast<const int*>(blob + hdr->offProgStart);
     prog = reinterpret_cast<const int4*>(blob + hdr->offProg);
     chainType = reinterpret_cast<const int*>(blob + hdr->offChainType);
+    chainXf = reinterpret_cast<const double*>(blob + hdr->offChainXf);
     chainJoint = reinterpret_cast<const int*>(blob + hdr->offChainJoint);
     chainW = reinterpret_cast<const double*>(blob + hdr->offChainW);
     chainGain = reinterpret_cast<const double*>(blob + hdr->offChainGain);
@@ -746,28 +748,77 @@ ikKernel(const IkArgs a)
 /* Single-chain fast path                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 
+/* The chain kernels keep the rows of the running rotation matrix cyclically shifted so that the
+ * axis of the joint that comes next is row 2 and the two rows it mixes are rows 0 and 1 (the
+ * shifts are folded into the plan's transforms, RcsbIkPlanHeader::offProg): every joint runs
+ * the same code, u' = c u + s v, v' = -s u + c v as in rotateAboutAxis. */
+__device__ __forceinline__ void rotateRows01(Frame& f, double s, double c)
+{
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const double ru = f.R[k], rv = f.R[3 + k];
+    f.R[k] = c * ru + s * rv;
+    f.R[3 + k] = c * rv - s * ru;
+  }
+}
+
 /* One step of the root-to-effector program: a constant relative transform, or the motion of a
  * joint that is not a Jacobian column (constrained: its value never changes during the solve). */
-__device__ __forceinline__ void chainStep(Frame& f, const int4 st, const char* sModel,
+template <bool PERM>
+__device__ __forceinline__ void chainStep(Frame& f, const int4 st, const double* __restrict__ xf,
                                           const double* __restrict__ qRow)
 {
   if (st.x == 0)
   {
-    applyRelF(f, reinterpret_cast<const double*>(sModel + st.y), st.z);
+    applyRelF(f, xf + 12 * st.y, st.z);
+    return;
+  }
+  if (PERM && st.x == 2)
+  {
+    /* rows shifted by st.y (1 or 2): new row i = old row (i + st.y) mod 3 */
+    double t[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+    {
+      t[i] = f.R[i];
+    }
+    if (st.y == 1)
+    {
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        f.R[i] = t[(i + 3) % 9];
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        f.R[i] = t[(i + 6) % 9];
+      }
+    }
     return;
   }
   const double qj = qRow[st.z];
-  const int dir = st.y % 3;
   if (st.y < 3)
   {
     double sn, cs;
     sincos(qj, &sn, &cs);
-    rotateAboutAxis(f, dir, sn, cs);
+    if (PERM)
+    {
+      rotateRows01(f, sn, cs);
+    }
+    else
+    {
+      rotateAboutAxis(f, st.w, sn, cs);
+    }
   }
   else
   {
     double ax[3];
-    axisOf(f, dir, ax);
+    axisOf(f, st.w, ax);
     f.o[0] += qj * ax[0];
     f.o[1] += qj * ax[1];
     f.o[2] += qj * ax[2];
@@ -879,21 +930,22 @@ ikChainKernel(const IkArgs a)
     {
       for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
       {
-        chainStep(f, p.prog[k], sModel, qRow);
+        chainStep<true>(f, p.prog[k], p.chainXf, qRow);
       }
-      const int type = p.chainType[c];
-      const int dir = type % 3;
-      isRot[c] = type < 3;
+      const int ctype = p.chainType[c];
+      isRot[c] = (ctype & 15) < 3;
       if (isRot[c])
       {
         double sn, cs;
         sincos(qc[c], &sn, &cs);
-        rotateAboutAxis(f, dir, sn, cs);
-        axisOf(f, dir, ax[c]);
+        rotateRows01(f, sn, cs);
+        ax[c][0] = f.R[6];         /* the axis of a rotation is row 2 of the shifted frame */
+        ax[c][1] = f.R[7];
+        ax[c][2] = f.R[8];
       }
       else
       {
-        axisOf(f, dir, ax[c]);
+        axisOf(f, ctype >> 4, ax[c]);
         f.o[0] += qc[c] * ax[c][0];
         f.o[1] += qc[c] * ax[c][1];
         f.o[2] += qc[c] * ax[c][2];
@@ -904,7 +956,7 @@ ikChainKernel(const IkArgs a)
     }
     for (int k = p.progStart[NC]; k < p.progStart[NC + 1]; ++k)
     {
-      chainStep(f, p.prog[k], sModel, qRow);
+      chainStep<true>(f, p.prog[k], p.chainXf, qRow);
     }
 
     /* ---- task error (ControllerBase::computeDX) ---------------------------------------------- */
@@ -1303,22 +1355,21 @@ ikChainLoopKernel(const IkArgs a, int nc)
     {
       for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
       {
-        chainStep(f, p.prog[k], sModel, qRow);
+        chainStep<false>(f, p.prog[k], p.chainXf, qRow);
       }
-      const int type = p.chainType[c];
-      const int dir = type % 3;
+      const int ctype = p.chainType[c];
       const double qc = at(c, 6);
       double axc[3];
-      if (type < 3)
+      if ((ctype & 15) < 3)
       {
         double sn, cs;
         sincos(qc, &sn, &cs);
-        rotateAboutAxis(f, dir, sn, cs);
-        axisOf(f, dir, axc);
+        rotateAboutAxis(f, ctype >> 4, sn, cs);   /* long chains keep the rows in place */
+        axisOf(f, ctype >> 4, axc);
       }
       else
       {
-        axisOf(f, dir, axc);
+        axisOf(f, ctype >> 4, axc);
         f.o[0] += qc * axc[0];
         f.o[1] += qc * axc[1];
         f.o[2] += qc * axc[2];
@@ -1332,7 +1383,7 @@ ikChainLoopKernel(const IkArgs a, int nc)
     }
     for (int k = p.progStart[nc]; k < p.progStart[nc + 1]; ++k)
     {
-      chainStep(f, p.prog[k], sModel, qRow);
+      chainStep<false>(f, p.prog[k], p.chainXf, qRow);
     }
 
     /* ---- task error (ControllerBase::computeDX) ---------------------------------------------- */
@@ -1379,7 +1430,7 @@ ikChainLoopKernel(const IkArgs a, int nc)
     {
       double ja[3] = {at(c, 0), at(c, 1), at(c, 2)};
       double jt[3];
-      if (p.chainType[c] < 3)
+      if ((p.chainType[c] & 15) < 3)
       {
         const double d0 = f.o[0] - at(c, 3), d1 = f.o[1] - at(c, 4), d2 = f.o[2] - at(c, 5);
         jt[0] = ja[1] * d2 - ja[2] * d1;

@@ -201,13 +201,23 @@ typedef struct
   int offColRed;        /* int[nJ]: column of the coupling matrix A the joint belongs to (its own
                            reduced index, or its master's) */
   int offColCpl;        /* int[nJ]: coupling record of a slave column, -1 otherwise */
-  int padc;
+  int offChainXf;       /* double[nXf][12]: the chain's relative transforms, rows / columns
+                           permuted for the frame representation of the chain kernels (below) */
   int chainNc;
   int nOther;           /* unconstrained joints that are not on the chain */
   int offProgStart;     /* int[chainNc + 2] */
-  int offProg;          /* int4[nSteps]: {op, a, b, 0}; op 0: relative transform at byte offset a
-                           of the flat model, b = its RCSB_REL_* flags; op 1: joint of type a, jointIndex b, value from q */
-  int offChainType;     /* int[chainNc]: RCSJOINT_TYPE of the column's joint */
+  int offProg;          /* int4[nSteps]: {op, a, b, 0}; op 0: relative transform a of chainXf, b =
+                           its RCSB_REL_* flags; op 1: joint of type a, jointIndex b, value from q.
+                           The chain kernels keep the rows of the running rotation matrix cyclically
+                           shifted so that the axis of the NEXT joint is row 2 and the rows it
+                           mixes are rows 0 and 1: every joint then runs the same code (no
+                           three-way selection by axis). The shifts are static, so they are folded
+                           into the transforms on the host: rot' = P_out rot P_in^T, org' = P_in org
+                           (exact permutations); a shift change with no transform to carry it
+                           is op 2 (rows shifted by a, registers only); the last step restores
+                           shift 0. A translational joint only reads its axis: the row that holds it
+                           is op 1's fourth entry / chainType >> 4. */
+  int offChainType;     /* int[chainNc]: RCSJOINT_TYPE of the column's joint | axis row << 4 */
   int offChainJoint;    /* int[chainNc]: jointIndex */
   int offChainW;        /* double[chainNc]: invWq */
   int offChainGain;     /* double[chainNc]: joint-limit gain */
