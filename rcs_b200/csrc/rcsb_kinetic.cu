@@ -38,6 +38,10 @@
 #include "rcsb_kernels.h"
 #include "rcsb_plan.h"
 
+#ifndef RCSB_KT_PREFETCH
+#define RCSB_KT_PREFETCH 3
+#endif
+
 namespace rcsb
 {
 
@@ -197,13 +201,22 @@ ktWalkKernel(const KtArgs a)
   keep = k;
   double V = 0.0;
   double freeM[4] = {0.0, 0.0, 0.0, 0.0};   /* m, m c of massive bodies no joint moves */
-  double nextQ = 0.0, nextQd = 0.0;
-  if (dof > 0)
+  /* q / q_dot of the next RCSB_KT_PREFETCH joints are in flight while a joint is processed: the
+   * rows of a warp's 32 states (2 x 520 B each for the humanoid) do not stay in L1 next to
+   * those of the other warps, so a load is an L2 round trip (with distance 1 the joint loop
+   * waited on it for 17 % of the kernel's stall samples) */
+  double nextQ[RCSB_KT_PREFETCH], nextQd[RCSB_KT_PREFETCH];
+#pragma unroll
+  for (int i = 0; i < RCSB_KT_PREFETCH; ++i)
   {
-    nextQ = rd.fetchQ(m, 0);
-    if (VEL)
+    nextQ[i] = nextQd[i] = 0.0;
+    if (i < dof)
     {
-      nextQd = rd.fetchQd(m, 0);
+      nextQ[i] = rd.fetchQ(m, i);
+      if (VEL)
+      {
+        nextQd[i] = rd.fetchQd(m, i);
+      }
     }
   }
 
@@ -272,13 +285,19 @@ ktWalkKernel(const KtArgs a)
 
       /* joints are visited in jointIndex order: the loads of the next joint are in flight
        * while this one is processed */
-      const double rawQ = nextQ, rawQd = nextQd;
-      if (j + 1 < dof)
+      const double rawQ = nextQ[0], rawQd = nextQd[0];
+#pragma unroll
+      for (int i = 0; i + 1 < RCSB_KT_PREFETCH; ++i)
       {
-        nextQ = rd.fetchQ(m, j + 1);
+        nextQ[i] = nextQ[i + 1];
+        nextQd[i] = nextQd[i + 1];
+      }
+      if (j + RCSB_KT_PREFETCH < dof)
+      {
+        nextQ[RCSB_KT_PREFETCH - 1] = rd.fetchQ(m, j + RCSB_KT_PREFETCH);
         if (VEL)
         {
-          nextQd = rd.fetchQd(m, j + 1);
+          nextQd[RCSB_KT_PREFETCH - 1] = rd.fetchQd(m, j + RCSB_KT_PREFETCH);
         }
       }
       const double qj = rd.finishQ(m, j, rawQ);
