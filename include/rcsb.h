@@ -52,6 +52,8 @@ extern "C" {
 #define RCSB_EUNSUPPORTED (-5)
 
 #define RCSB_HOST_PTRS 1u    /* array arguments are host pointers */
+#define RCSB_IK_LEFT_INVERSE 2u   /* rcsb_ik_rmr: IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205),
+                                     the nq x nq left pseudo-inverse, instead of solveRightInverse */
 
 /* task kinds of rcsb_ik_rmr, named after the reference's controlVariable strings
  * (src/RcsCore/TaskPosition3D.cpp:49, TaskEuler3D.cpp:52) */

@@ -575,11 +575,13 @@ class Oracle:
         invA = inv_diag[:, :, None] * np.transpose(A, (0, 2, 1))
         return A, invA
 
-    def ik_rmr(self, q, tasks, x_des, lam=1.0e-8, alpha=0.05, iters=1):
+    def ik_rmr(self, q, tasks, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
         """examples/ExampleIK.cpp:154-177 with IkSolverRMR::solveRightInverse
         (src/RcsCore/IkSolverRMR.cpp:415-596, kinematically coupled joints in the reduced space
-        of RcsGraph_coupledJointMatrix) and MatNd_rwPinv (src/RcsCore/Rcs_MatNd.c:1833).
-        Returns (q, dx_last, dq_last, det_last)."""
+        of RcsGraph_coupledJointMatrix) and MatNd_rwPinv (src/RcsCore/Rcs_MatNd.c:1833); with
+        `left` IkSolverRMR::solveLeftInverse (:205-272; computeKinematics :176-200 scales the
+        Jacobian by the joint metric, binary task blending = unit task weights) and MatNd_rwPinv2
+        (Rcs_MatNd.c:1920). Returns (q, dx_last, dq_last, det_last)."""
         q = self.expand(np.asarray(q, dtype=np.float64))[0]
         x_des = np.asarray(x_des, dtype=np.float64)
         nJ = self.nJ
@@ -599,6 +601,20 @@ class Oracle:
                 w = np.einsum("nij,j->ni", invA, inv_wq)
                 dHr = np.einsum("nij,nj->ni", invA, dHr)
             nq = J.shape[2]
+            if left:
+                Jr = J * w[:, None, :]                                    # J A invWq_r
+                B = np.einsum("nki,nkj->nij", Jr, Jr) + lam * np.eye(nq)
+                inv, det = self._cholesky_inverse(B)
+                pinv = np.einsum("nij,nkj->nik", inv, Jr)                 # (J^T J + lam)^-1 J^T
+                N = np.eye(nq) - np.einsum("nij,njk->nik", pinv, Jr)
+                dqr = np.einsum("nij,nj->ni", pinv, dx) + np.einsum("nij,nj->ni", N * w[:, None, :], dHr)
+                dqr = dqr * w                                             # back to the unweighted space
+                dq = np.einsum("nij,nj->ni", A, dqr) if coupled else dqr
+                dq[det == 0.0] = 0.0
+                dq_full = np.zeros_like(q)
+                dq_full[:, cols] = dq
+                q = self.expand(q + dq_full)[0]
+                continue
             WJt = w[:, :, None] * np.transpose(J, (0, 2, 1))
             M = np.einsum("nij,njk->nik", J, WJt) + lam * np.eye(J.shape[1])
             inv, det = self._cholesky_inverse(M)

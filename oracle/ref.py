@@ -75,6 +75,8 @@ def lib() -> ctypes.CDLL:
         L.ref_ik_task_kinematics.argtypes = [vp, cl, ci, vp, vp, vp]
         L.ref_ik_rmr.restype = cd
         L.ref_ik_rmr.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
+        L.ref_ik_rmr_left.restype = cd
+        L.ref_ik_rmr_left.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
         L.ref_set_threads.argtypes = [ci]
         L.ref_set_log_level.argtypes = [ci]
         _LIB = L
@@ -262,15 +264,17 @@ class RefIk:
                                                          _p(J))
         return x, J
 
-    def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1):
-        """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp."""
+    def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
+        """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp with
+        solveRightInverse, or solveLeftInverse (IkSolverRMR.cpp:205) if `left`."""
         q = _c(q).copy()
         x_des = _c(x_des)
         N = q.shape[0]
         dx = np.empty((N, self.nx))
         dq = np.empty((N, self.graph.dof))
         det = np.empty((N,))
-        self.last_seconds = lib().ref_ik_rmr(
+        fn = lib().ref_ik_rmr_left if left else lib().ref_ik_rmr
+        self.last_seconds = fn(
             self._h, N, _p(q), _p(x_des), float(lam), float(alpha), int(iters), _p(dx), _p(dq),
             _p(det))
         return q, dx, dq, det

@@ -732,8 +732,26 @@ double ref_ik_task_kinematics(void* ik, long N, int qdim, const double* q, doubl
  *   dqOut : N x dof  joint displacement of the LAST iteration, or NULL
  *   det   : N determinant of (J W J^T + lambda I) in the LAST iteration, or NULL
  */
+static double ikRmrImpl(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
+                        int iters, double* dxOut, double* dqOut, double* det, bool leftInverse);
+
 double ref_ik_rmr(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
                   int iters, double* dxOut, double* dqOut, double* det)
+{
+  return ikRmrImpl(ik, N, q, xDes, lambda, alpha, iters, dxOut, dqOut, det, false);
+}
+
+/* the same loop with IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205) */
+double ref_ik_rmr_left(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
+                       int iters, double* dxOut, double* dqOut, double* det)
+{
+  return ikRmrImpl(ik, N, q, xDes, lambda, alpha, iters, dxOut, dqOut, det, true);
+}
+
+}   // extern "C"
+
+static double ikRmrImpl(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
+                        int iters, double* dxOut, double* dqOut, double* det, bool leftInverse)
 {
   IkHandle* h = (IkHandle*) ik;
   return parallelSlices(N, [=](int, long lo, long hi)
@@ -758,7 +776,14 @@ double ref_ik_rmr(void* ik, long N, double* q, const double* xDes, double lambda
         c.computeDX(dx, xd);
         c.computeJointlimitGradient(dH);
         MatNd_constMulSelf(dH, alpha);
-        solver.solveRightInverse(dq, dx, dH, a, lambda);
+        if (leftInverse)
+        {
+          solver.solveLeftInverse(dq, dx, dH, a, lambda);
+        }
+        else
+        {
+          solver.solveRightInverse(dq, dx, dH, a, lambda);
+        }
         MatNd_addSelf(graph->q, dq);
         RcsGraph_setState(graph, NULL, NULL);
       }
@@ -784,5 +809,3 @@ double ref_ik_rmr(void* ik, long N, double* q, const double* xDes, double lambda
     MatNd_destroy(dH);
   });
 }
-
-}   // extern "C"

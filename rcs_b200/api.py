@@ -26,6 +26,7 @@ _LIB = None
 TASK_XYZ = 1
 TASK_ABC = 2
 _HOST_PTRS = 1
+_IK_LEFT_INVERSE = 2
 
 
 class RcsbError(RuntimeError):
@@ -456,8 +457,9 @@ class Model:
 
     # -- inverse kinematics --------------------------------------------------------------
     def ik_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1,
-               want=("det",), out=None):
-        """`iters` IkSolverRMR::solveRightInverse steps per state; q is updated in place.
+               want=("det",), out=None, left_inverse=False):
+        """`iters` IkSolverRMR::solveRightInverse steps per state (solveLeftInverse with
+        `left_inverse`); q is updated in place.
 
         tasks: sequence of (TASK_XYZ | TASK_ABC, effector body index).
         """
@@ -475,7 +477,7 @@ class Model:
         rc = lib().rcsb_ik_rmr(
             self._h, len(tasks), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam),
             float(alpha), int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"),
-            a.ptr(out.get("det"), "det"), a.flags(), a.stream(),
+            a.ptr(out.get("det"), "det"), a.flags() | (_IK_LEFT_INVERSE if left_inverse else 0), a.stream(),
         )
         _err(rc, "rcsb_ik_rmr")
         return out

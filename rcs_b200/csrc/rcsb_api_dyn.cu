@@ -1033,7 +1033,7 @@ int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePla
 
 int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const double* xDes,
              double lambda, double alpha, int iters, double* dx, double* dq, double* det,
-             cudaStream_t stream)
+             bool leftInverse, cudaStream_t stream)
 {
   rcsb::IkArgs a;
   a.model = m->dev;
@@ -1046,6 +1046,7 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
   a.lambda = lambda;
   a.alpha = alpha;
   a.iters = iters;
+  a.leftInverse = leftInverse ? 1 : 0;
   a.dx = dx;
   a.dq = dq;
   a.det = det;
@@ -1092,10 +1093,11 @@ extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* task
   {
     return rc;
   }
+  const bool left = (flags & RCSB_IK_LEFT_INVERSE) != 0;
 
   if (!(flags & RCSB_HOST_PTRS))
   {
-    return ikDevice(m, plan, N, q, xDes, lambda, alpha, iters, dx, dq, det,
+    return ikDevice(m, plan, N, q, xDes, lambda, alpha, iters, dx, dq, det, left,
                     static_cast<cudaStream_t>(stream));
   }
 
@@ -1111,6 +1113,6 @@ extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* task
   return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
     return ikDevice(m, plan, n, arr[I_QIN].dev, arr[I_X].dev, lambda, alpha, iters,
-                    dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), st);
+                    dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), left, st);
   });
 }

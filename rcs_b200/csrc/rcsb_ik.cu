@@ -246,7 +246,11 @@ __device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3
   rotationTaskError(dx, Ad, Ac);
 }
 
-template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS>
+/* LEFT: IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) instead of solveRightInverse:
+ * J_r = J A invWq_r (computeKinematics, :176-200; binary task blending = unit task weights),
+ * J# = (J_r^T J_r + lambda 1)^-1 J_r^T (MatNd_rwPinv2, Rcs_MatNd.c:1920: explicit Cholesky inverse
+ * of the nq x nq matrix), dq_r = invWq_r o (J# dx + (1 - J# J_r) invWq_r (-alpha A+ dH)), dq = A dq_r. */
+template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS, bool LEFT = false>
 __global__ void __launch_bounds__(RCSB_IK_THREADS)
 ikKernel(const IkArgs a)
 {
@@ -280,8 +284,9 @@ ikKernel(const IkArgs a)
   double ef[12 * MAXT];       /* effector frame per task */
   double J[MAXNX * MAXNJ];    /* nx x nJ */
   double P[MAXNJ * MAXNX];    /* nJ x nx: invWq J^T, then J# */
-  double A[MAXNX * MAXNX];    /* J invWq J^T + lambda 1 -> L -> L^-1 */
-  double Ai[MAXNX * MAXNX];   /* inverse */
+  constexpr int MAXS = LEFT ? MAXNJ : MAXNX;   /* size of the symmetric system */
+  double A[MAXS * MAXS];      /* J invWq J^T + lambda 1 (LEFT: J_r^T J_r + lambda 1) -> L -> L^-1 */
+  double Ai[MAXS * MAXS];     /* inverse */
   double dx[MAXNX], g[MAXNJ], Jg[MAXNX], dq[MAXNJ], row[MAXNX];
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
   double det = 0.0;
@@ -562,46 +567,72 @@ ikKernel(const IkArgs a)
     }
 
     /* ---- J# = invWq J^T (J invWq J^T + lambda 1)^-1 ------------------------------------------ */
-    for (int i = 0; i < nq; ++i)
+    const int n = LEFT ? nq : nx;
+    if (LEFT)
     {
-      const double w = wv[i];
       for (int k = 0; k < nx; ++k)
       {
-        P[i * nx + k] = w * J[k * nJ + i];
-      }
-    }
-    for (int r = 0; r < nx; ++r)
-    {
-      for (int c = 0; c < nx; ++c)
-      {
-        double sum = 0.0;
         for (int i = 0; i < nq; ++i)
         {
-          sum += J[r * nJ + i] * P[i * nx + c];
+          J[k * nJ + i] *= wv[i];
         }
-        A[r * nx + c] = sum + (r == c ? a.lambda : 0.0);
+      }
+      for (int r = 0; r < nq; ++r)
+      {
+        for (int c = 0; c < nq; ++c)
+        {
+          double sum = 0.0;
+          for (int k = 0; k < nx; ++k)
+          {
+            sum += J[k * nJ + r] * J[k * nJ + c];
+          }
+          A[r * n + c] = sum + (r == c ? a.lambda : 0.0);
+        }
+      }
+    }
+    else
+    {
+      for (int i = 0; i < nq; ++i)
+      {
+        const double w = wv[i];
+        for (int k = 0; k < nx; ++k)
+        {
+          P[i * nx + k] = w * J[k * nJ + i];
+        }
+      }
+      for (int r = 0; r < nx; ++r)
+      {
+        for (int c = 0; c < nx; ++c)
+        {
+          double sum = 0.0;
+          for (int i = 0; i < nq; ++i)
+          {
+            sum += J[r * nJ + i] * P[i * nx + c];
+          }
+          A[r * nx + c] = sum + (r == c ? a.lambda : 0.0);
+        }
       }
     }
 
     /* Banachiewicz Cholesky, lower triangle in place; det = prod L_ii^2 */
     det = 1.0;
-    for (int i = 0; i < nx && det != 0.0; ++i)
+    for (int i = 0; i < n && det != 0.0; ++i)
     {
       for (int k = 0; k <= i; ++k)
       {
-        double sum = A[i * nx + k];
+        double sum = A[i * n + k];
         for (int t = 0; t < k; ++t)
         {
-          sum -= A[i * nx + t] * A[k * nx + t];
+          sum -= A[i * n + t] * A[k * n + t];
         }
         if (i > k)
         {
-          A[i * nx + k] = sum / A[k * nx + k];
+          A[i * n + k] = sum / A[k * n + k];
         }
         else if (sum > 0.0)
         {
-          A[i * nx + i] = sqrt(sum);
-          det *= A[i * nx + i] * A[i * nx + i];
+          A[i * n + i] = sqrt(sum);
+          det *= A[i * n + i] * A[i * n + i];
         }
         else
         {
@@ -622,48 +653,67 @@ ikKernel(const IkArgs a)
     }
 
     /* L <- L^-1 in place */
-    for (int k = 0; k < nx; ++k)
+    for (int k = 0; k < n; ++k)
     {
-      A[k * nx + k] = 1.0 / A[k * nx + k];
-      for (int i = k + 1; i < nx; ++i)
+      A[k * n + k] = 1.0 / A[k * n + k];
+      for (int i = k + 1; i < n; ++i)
       {
         double sum = 0.0;
         for (int t = k; t < i; ++t)
         {
-          sum += A[i * nx + t] * A[t * nx + k];
+          sum += A[i * n + t] * A[t * n + k];
         }
-        A[i * nx + k] = -sum / A[i * nx + i];
+        A[i * n + k] = -sum / A[i * n + i];
       }
     }
     /* inverse = L^-T L^-1 */
-    for (int r = 0; r < nx; ++r)
+    for (int r = 0; r < n; ++r)
     {
-      for (int c = r; c < nx; ++c)
+      for (int c = r; c < n; ++c)
       {
         double sum = 0.0;
-        for (int t = c; t < nx; ++t)
+        for (int t = c; t < n; ++t)
         {
-          sum += A[t * nx + r] * A[t * nx + c];
+          sum += A[t * n + r] * A[t * n + c];
         }
-        Ai[r * nx + c] = sum;
-        Ai[c * nx + r] = sum;
+        Ai[r * n + c] = sum;
+        Ai[c * n + r] = sum;
       }
     }
-    /* J# = (invWq J^T) inverse, row by row in place */
-    for (int i = 0; i < nq; ++i)
+    if (LEFT)
     {
-      for (int k = 0; k < nx; ++k)
+      /* J# = inverse J_r^T */
+      for (int i = 0; i < nq; ++i)
       {
-        row[k] = P[i * nx + k];
+        for (int c = 0; c < nx; ++c)
+        {
+          double sum = 0.0;
+          for (int t = 0; t < nq; ++t)
+          {
+            sum += Ai[i * n + t] * J[c * nJ + t];
+          }
+          P[i * nx + c] = sum;
+        }
       }
-      for (int c = 0; c < nx; ++c)
+    }
+    else
+    {
+      /* J# = (invWq J^T) inverse, row by row in place */
+      for (int i = 0; i < nq; ++i)
       {
-        double sum = 0.0;
         for (int k = 0; k < nx; ++k)
         {
-          sum += row[k] * Ai[k * nx + c];
+          row[k] = P[i * nx + k];
         }
-        P[i * nx + c] = sum;
+        for (int c = 0; c < nx; ++c)
+        {
+          double sum = 0.0;
+          for (int k = 0; k < nx; ++k)
+          {
+            sum += row[k] * Ai[k * nx + c];
+          }
+          P[i * nx + c] = sum;
+        }
       }
     }
 
@@ -687,7 +737,7 @@ ikKernel(const IkArgs a)
           ts += P[i * nx + c] * dx[c];
           ns += P[i * nx + c] * Jg[c];
         }
-        dq[i] = ts + (g[i] - ns);
+        dq[i] = LEFT ? (ts + (g[i] - ns)) * wv[i] : ts + (g[i] - ns);
       }
     }
     else
@@ -705,10 +755,15 @@ ikKernel(const IkArgs a)
         }
         tsr[i] = ts;
         nsr[i] = g[i] - ns;
+        if (LEFT)
+        {
+          tsr[i] = (ts + nsr[i]) * wv[i];   /* one reduced step, back in the unweighted space */
+          nsr[i] = 0.0;
+        }
       }
       for (int c = 0; c < nJ; ++c)
       {
-        dq[c] = av[c] * tsr[p.colRed[c]] + av[c] * nsr[p.colRed[c]];
+        dq[c] = LEFT ? av[c] * tsr[p.colRed[c]] : av[c] * tsr[p.colRed[c]] + av[c] * nsr[p.colRed[c]];
       }
     }
     for (int i = 0; i < nJ; ++i)
@@ -2006,14 +2061,14 @@ static cudaError_t launchChainNc(const IkArgs& a, int nc, cudaStream_t stream)
   }
 }
 
-template <int MAXNX, int MAXNJ, int MAXDOF>
+template <int MAXNX, int MAXNJ, int MAXDOF, bool LEFT = false>
 static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes;
   const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
 #define RCSB_LAUNCH(NS)                                                                        \
   {                                                                                            \
-    auto k = ikKernel<MAXNX, MAXNJ, MAXDOF, NS>;                                               \
+    auto k = ikKernel<MAXNX, MAXNJ, MAXDOF, NS, LEFT>;                                         \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int) smemBytes);                                     \
     if (e != cudaSuccess)                                                                      \
@@ -2044,6 +2099,19 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
   if (a->N <= 0)
   {
     return cudaSuccess;
+  }
+  if (a->leftInverse)
+  {
+    /* solveLeftInverse: general kernel only */
+    if (nx <= 6 && nJ <= 8 && dof <= 8)
+    {
+      return launchIk<6, 8, 8, true>(*a, nSlots, stream);
+    }
+    if (nx <= 12 && nJ <= 40 && dof <= 72)
+    {
+      return launchIk<12, 40, 72, true>(*a, nSlots, stream);
+    }
+    return cudaErrorInvalidValue;
   }
   if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
   {

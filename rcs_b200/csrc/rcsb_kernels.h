@@ -83,6 +83,7 @@ struct IkArgs
   double lambda;
   double alpha;
   int iters;
+  int leftInverse;     /* 1: IkSolverRMR::solveLeftInverse instead of solveRightInverse */
   double* dx;
   double* dq;
   double* det;

@@ -289,3 +289,67 @@ def test_several_effectors(names, general, refmod, cuda_device, monkeypatch):
     m.ik_rmr(tasks, q4, x_des, iters=4)
     ok = cond < 1.0e4
     assert_step_close((q4 - q0)[ok], (q4_ref - q0)[ok], 4.0 * cond[ok], "q after 4 iterations")
+
+
+def _left_condition(rik, q, lam=1.0e-8):
+    """2-norm condition number of J_r^T J_r + lambda 1, J_r = J invWq (no coupled joints)."""
+    _, J = rik.task_kinematics(q)
+    Jr = J * rik.graph.inv_wq()[None, None, :]
+    B = np.einsum("nki,nkj->nij", Jr, Jr) + lam * np.eye(J.shape[2])
+    return np.linalg.cond(B)
+
+
+@pytest.mark.parametrize("name,eff,kinds,lam", [("gantry", "Tool", ("XYZ", "ABC"), 1.0e-8),
+                                                ("gantry", "Tool", ("XYZ",), 1.0e-4),
+                                                ("wam_arm", "BallTip", ("XYZ", "ABC"), 1.0e-3),
+                                                ("wam_arm", "BallTip", ("ABC", "XYZ"), 1.0e-8)])
+def test_left_inverse_matches_reference(name, eff, kinds, lam, refmod, cuda_device):
+    """RCSB_IK_LEFT_INVERSE: IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272), the nq x nq
+    left pseudo-inverse (J_r^T J_r + lambda 1)^-1 J_r^T with J_r = J A invWq_r and the null-space
+    term through the same inverse. The step goes through the inverse of that nq x nq matrix: the
+    bar is scaled by its condition number per state like the right inverse's (a redundant arm
+    with lambda = 1e-8 is regularised by lambda alone)."""
+    g, m, rik, tasks = _setup(name, eff, refmod, cuda_device, kinds)
+    q0, x_des = _targets(g, rik, 1500, seed_first=77, perturb=0.08)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, lam=lam, iters=1, left=True)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, lam=lam, iters=1, want=("dx", "dq", "det"), left_inverse=True)
+    assert_close(out["dx"], dx_ref, what="dx")
+    cond = _left_condition(rik, q0, lam)
+    ok = det_ref > 0.0
+    assert ok.mean() > 0.95
+    assert_step_close(out["dq"][ok], dq_ref[ok], cond[ok], "dq (left inverse)")
+    assert_step_close((q - q0)[ok], (q_ref - q0)[ok], cond[ok], "q (left inverse)")
+    assert np.all(out["det"][~ok] == 0.0) and np.all(out["dq"][~ok] == 0.0)
+    rel = np.abs(out["det"][ok] / det_ref[ok] - 1.0)
+    assert np.all(rel <= 1e-11 * np.maximum(1.0, cond[ok] / 100.0)), "det (relative, conditioned)"
+    # device pointers, several iterations: the task error shrinks like the reference's
+    import torch
+
+    q5_ref, dx5_ref, _, _ = rik.rmr(q0, x_des, lam=lam, iters=5, left=True)
+    dq5 = torch.from_numpy(q0.copy()).cuda(cuda_device)
+    out5 = m.ik_rmr(tasks, dq5, torch.from_numpy(x_des).cuda(cuda_device), lam=lam, iters=5, want=("dx",),
+                    left_inverse=True)
+    e0 = np.abs(dx_ref).max(axis=1)
+    e5 = np.abs(out5["dx"].cpu().numpy()).max(axis=1)
+    assert np.mean(e5 < 0.5 * e0 + 1e-9) > 0.95
+    good = ok & (cond < 1.0e6)
+    if good.any():
+        assert_step_close((dq5.cpu().numpy() - q0)[good], (q5_ref - q0)[good], 5.0 * cond[good],
+                          "q after 5 left-inverse iterations")
+
+
+def test_left_inverse_with_coupled_joints(refmod, cuda_device):
+    """Reduced joint space of RcsGraph_coupledJointMatrix in the left inverse as well."""
+    g, m, rik, tasks = _setup("wam_scenario", "FingerTipTip2", refmod, cuda_device, ("XYZ", "ABC"))
+    q0, x_des = _targets(g, rik, 400, seed_first=5, perturb=0.05)
+    lam = 1.0e-3
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, lam=lam, iters=1, left=True)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, lam=lam, iters=1, want=("dx", "dq", "det"), left_inverse=True)
+    assert_close(out["dx"], dx_ref, what="dx")
+    ok = det_ref > 0.0
+    # lambda = 1e-3 bounds the condition number of the regularised matrix by (s_max^2 + lam) / lam
+    scale = np.maximum(1.0, np.abs(dq_ref).max(axis=1))
+    assert np.all(np.abs(out["dq"] - dq_ref)[ok].max(axis=1) <= 1e-8 * scale[ok])
+    assert np.all(np.abs(q - q_ref)[ok].max(axis=1) <= 1e-8 * scale[ok])

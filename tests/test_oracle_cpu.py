@@ -305,3 +305,24 @@ def test_oracle_ik_with_coupled_joints_vs_reference_library(refmod):
     assert np.all(np.abs(dq1 - dq_ref).max(axis=1)[ok] <= 1e-7 * scale[ok])   # ill-conditioned fingers
     well = ok & (det_ref > np.median(det_ref))
     assert_close(q1[well], q_ref[well], tol=1e-9, what="q after one step (coupled)")
+
+
+@pytest.mark.parametrize("name,eff", [("gantry", "Tool"), ("wam_arm", "BallTip"), ("wam_scenario", "FingerTipTip2")])
+def test_oracle_left_inverse_vs_reference_library(name, eff, refmod):
+    """The numpy restatement of IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) against the
+    reference library. lambda = 1e-3 keeps the nq x nq matrix of a redundant arm well conditioned."""
+    lay = layout(name)
+    o = rcs_oracle.Oracle(lay)
+    tip = [b["name"] for b in lay["bodies"]].index(eff)
+    rik = refmod.RefIk(graph_file(name), [("XYZ", eff), ("ABC", eff)])
+    q_goal = workload.sample_states(lay, 40, first=9, margin=0.2)
+    x_des, _ = rik.task_kinematics(q_goal)
+    q0 = q_goal + 0.05
+    for iters in (1, 4):
+        qa, dxa, dqa, deta = rik.rmr(q0, x_des, lam=1.0e-3, iters=iters, left=True)
+        qb, dxb, dqb, detb = o.ik_rmr(q0, [("XYZ", tip), ("ABC", tip)], x_des, lam=1.0e-3, iters=iters, left=True)
+        ok = deta > 0.0
+        assert ok.mean() > 0.9
+        assert np.abs(dqa - dqb)[ok].max() < 1e-9 and np.abs(qa - qb)[ok].max() < 1e-9
+        assert np.abs(deta[ok] / detb[ok] - 1.0).max() < 1e-9
+        assert np.abs(dxa - dxb)[ok].max() < 1e-9
