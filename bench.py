@@ -532,6 +532,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # bring the SM clocks up before the warm-up steps: a step is 0.5 ms, so a short --warmup alone
+    # would be timed on a GPU that is still ramping from idle (measured: 1.87 instead of 2.05 G
+    # states/s with --warmup 3 --steps 5)
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < args.settle:
+        device_call()
+        torch.cuda.synchronize()
     for i in range(args.warmup):
         device_call()
         exchange(args.steps + i)
@@ -661,6 +668,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fkm", choices=["fkm", "fk", "kinetic", "ik", "wholebody"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--settle", type=float, default=1.0,
+                    help="seconds of untimed work before the warm-up steps (clock ramp from idle)")
     ap.add_argument("--hold", type=float, default=1.0,
                     help="seconds of extra (untimed) load for the clock sampler")
     args = ap.parse_args()
