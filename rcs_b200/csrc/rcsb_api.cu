@@ -148,8 +148,12 @@ namespace
 
 /* ---- FK plan ---------------------------------------------------------------------------- */
 
+/* compact: the Jacobian records hold the columns of the effectors' own chains only,
+ * [nEff][3][recCols] with recCols = the longest chain of the group, column ci = the chain's
+ * ci-th Jacobian column in ascending order (rcsb_task_jacobians: its intermediates are read
+ * back by combineKernel, structural zeros would be two thirds of the traffic) */
 int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int* effBody,
-                const double* effPt, bool withMass, const DevicePlan** out)
+                const double* effPt, bool withMass, const DevicePlan** out, bool compact = false)
 {
   const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
 
@@ -193,7 +197,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   }
 
   std::string key;
-  key.push_back(withMass ? 'M' : 'k');
+  key.push_back(withMass ? 'M' : (compact ? 'c' : 'k'));
   key.append(reinterpret_cast<const char*>(&nSel), sizeof(int));
   key.append(reinterpret_cast<const char*>(&nEff), sizeof(int));
   if (nSel > 0)
@@ -274,23 +278,47 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
     return RCSB_EUNSUPPORTED;
   }
 
-  const int rec = nEff * 3 * nJ;
+  int recCols = nJ;
+  if (compact)
+  {
+    recCols = 1;
+    for (int e = 0; e < nEff; ++e)
+    {
+      int nc = 0;
+      for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
+      {
+        nc += jntJacobi[j] >= 0 ? 1 : 0;
+      }
+      recCols = nc > recCols ? nc : recCols;
+    }
+  }
+  const int rec = nEff * 3 * recCols;
   std::vector<int> jtab(rec > 0 ? rec : 1, -1), jtabR(rec > 0 ? rec : 1, -1);
   std::vector<int> effChainStart(nEff + 1, 0), effChain;
   for (int e = 0; e < nEff; ++e)
   {
+    int below = 0;   /* chain columns still to come on the way to the root */
     for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
     {
-      const int col = jntJacobi[j];
+      below += jntJacobi[j] >= 0 ? 1 : 0;
+    }
+    for (int j = bodyLastJnt[effBody[e]]; j >= 0; j = jntPrev[j])
+    {
+      int col = jntJacobi[j];
       if (col < 0)
       {
         continue;
+      }
+      --below;
+      if (compact)
+      {
+        col = below;   /* rank of the column among the chain's columns, ascending */
       }
       const bool isRot = (jntFlags[j] & RCSB_JF_ROT) != 0;
       effChain.push_back(jntScr[j] | (isRot ? (1 << 16) : 0));
       for (int r = 0; r < 3; ++r)
       {
-        const int idx = (e * 3 + r) * nJ + col;
+        const int idx = (e * 3 + r) * recCols + col;
         if (inPlace)
         {
           jtab[idx] = (3 + r) * nChain + jntScr[j];        /* JT column (was: joint origin) */
@@ -582,7 +610,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   dp.nScrRows = ph.nScrRows;
   dp.nSel = nOut;
   dp.nEff = nEff;
-  dp.aux0 = ph.massChain;
+  dp.aux0 = compact ? recCols : ph.massChain;   /* compact plans never carry the mass tables */
   dp.aux1 = ph.nVisit > 0 ? ph.prunedSlots + 1 : 0;   /* 0: no pruned walk */
 
   auto ins = m->fkPlans.emplace(key, dp);
@@ -616,7 +644,7 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.M = M;
   a.noCoupling = noCoupling ? 1 : 0;
   /* composite (tip-to-root) mass matrix when the plan allows it and the frames are written */
-  a.massMode = M ? ((plan->aux0 && A_BI) ? 2 : 1) : 0;
+  a.massMode = M ? ((plan->aux0 && A_BI) ? 2 : 1) : 0;   /* (plans with M are never compact) */
   /* per-joint outputs and velocities need every body: the pruned walk serves frames and
    * Jacobians of a body selection only */
   a.pruned = (plan->aux1 > 0 && !A_JI && !qOut && !qd && !qdOut && !M) ? 1 : 0;
@@ -880,6 +908,25 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
                     dv(I_XD, xdot), dv(I_OM, omega), dv(I_QO, qOut), dv(I_JT, JT), dv(I_JR, JR),
                     dv(I_QDO, qdOut), noCoupling, dv(I_M, M), st);
   });
+}
+
+/* Frames + compact world Jacobians of a few bodies, device pointers (rcsb_task_jacobians). */
+int rcsbhost::fkCompactDevice(RcsbModel* m, long n, int qdim, const double* q, int G, const int* bodies,
+                              double* A, double* JT, double* JR, cudaStream_t stream, int* recCols)
+{
+  const DevicePlan* plan = nullptr;
+  const int rc = buildFkPlan(m, G, bodies, G, bodies, nullptr, false, &plan, true);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  *recCols = plan->aux0;
+  if (n == 0)
+  {
+    return RCSB_OK;
+  }
+  return fkDevice(m, plan, n, qdim, q, nullptr, A, nullptr, nullptr, nullptr, nullptr, JT, JR, nullptr,
+                  false, nullptr, stream);
 }
 
 extern "C" int rcsb_fk(const RcsbModel* model, long N, int qdim, const double* q,

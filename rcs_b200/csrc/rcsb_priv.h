@@ -140,6 +140,9 @@ int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const doubl
              double* JR, double* qdOut, bool noCoupling, unsigned flags, void* stream,
              double* M = nullptr);
 
+int fkCompactDevice(RcsbModel* m, long n, int qdim, const double* q, int G, const int* bodies,
+                    double* A, double* JT, double* JR, cudaStream_t stream, int* recCols);
+
 }   // namespace rcsbhost
 
 #endif

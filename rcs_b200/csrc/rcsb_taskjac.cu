@@ -34,6 +34,9 @@ struct SlotInfo
   long offA, strideA;   /* doubles: frame of state s at tmp[offA + s strideA] */
   long offJ, strideJ;   /* JT at tmp[offJ + s strideJ], JR at tmp[offJ + jrShift + s strideJ] */
   long jrShift;
+  int rowStride;        /* doubles between the rows of a 3 x rowStride Jacobian record: the records
+                           are compact, they hold the columns of the body's own chain only */
+  int pad;
 };
 
 struct CombineArgs
@@ -42,6 +45,7 @@ struct CombineArgs
   const SlotInfo* slots;
   double* out;        /* n x nTasks x 3 x nJ */
   const CombineTask* tasks;
+  const int* colMap;  /* [bodies][nJ]: index of Jacobian column k in the body's compact record, -1 = zero */
   long n;
   int nTasks, nJ;
 };
@@ -62,18 +66,32 @@ __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
     auto jt = [&](int u) { return a.tmp + a.slots[u].offJ + s * a.slots[u].strideJ; };
     auto jr = [&](int u) { return a.tmp + a.slots[u].offJ + a.slots[u].jrShift + s * a.slots[u].strideJ; };
 
+    /* column k of body u's translation (rot = false) / rotation Jacobian; zero off its chain */
+    auto column = [&](int u, bool rot, double (&c)[3]) {
+      const int ci = a.colMap[u * a.nJ + k];
+      c[0] = c[1] = c[2] = 0.0;
+      if (ci >= 0)
+      {
+        const int rs = a.slots[u].rowStride;
+        const double* j = (rot ? jr(u) : jt(u)) + ci;
+        c[0] = j[0];
+        c[1] = j[rs];
+        c[2] = j[2 * rs];
+      }
+    };
+
     double v[3] = {0.0, 0.0, 0.0};
     if (tk.kind == RCSB_JAC_POS)
     {
       if (tk.u2 >= 0)
       {
-        const double* j2 = jt(tk.u2) + k;
-        v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
+        column(tk.u2, false, v);
       }
       if (tk.mode == 1)
       {
-        const double* j1 = jt(tk.u1) + k;
-        v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
+        double j1[3];
+        column(tk.u1, false, j1);
+        v[0] -= j1[0]; v[1] -= j1[1]; v[2] -= j1[2];
         if (tk.u3 >= 0)
         {
           const double* o1 = frame(tk.u1);
@@ -83,8 +101,9 @@ __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
             const double* o2 = frame(tk.u2);
             r[0] += o2[0]; r[1] += o2[1]; r[2] += o2[2];
           }
-          const double* j3 = jr(tk.u3) + k;
-          const double w0 = j3[0], w1 = j3[a.nJ], w2 = j3[2 * a.nJ];
+          double j3[3];
+          column(tk.u3, true, j3);
+          const double w0 = j3[0], w1 = j3[1], w2 = j3[2];
           v[0] += r[1] * w2 - r[2] * w1;
           v[1] += -r[0] * w2 + r[2] * w0;
           v[2] += r[0] * w1 - r[1] * w0;
@@ -95,13 +114,13 @@ __global__ void __launch_bounds__(256) combineKernel(const CombineArgs a)
     {
       if (tk.u2 >= 0)
       {
-        const double* j2 = jr(tk.u2) + k;
-        v[0] = j2[0]; v[1] = j2[a.nJ]; v[2] = j2[2 * a.nJ];
+        column(tk.u2, true, v);
       }
       if (tk.mode == 1 && tk.u1 >= 0)
       {
-        const double* j1 = jr(tk.u1) + k;
-        v[0] -= j1[0]; v[1] -= j1[a.nJ]; v[2] -= j1[2 * a.nJ];
+        double j1[3];
+        column(tk.u1, true, j1);
+        v[0] -= j1[0]; v[1] -= j1[1]; v[2] -= j1[2];
       }
     }
     if (tk.uA >= 0)
@@ -268,7 +287,29 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
 
   static const long passStates = getenv("RCSB_TASKJAC_PASS") ? atol(getenv("RCSB_TASKJAC_PASS")) : 32768;
   const long chunk = N < passStates ? N : passStates;
-  const size_t perState = (size_t) nU * (12 + 6 * (size_t) nJ);
+  /* compact record width of every group and the column maps of the bodies */
+  std::vector<int> colMap((size_t) nU * nJ, -1), groupCols(groups.size(), 1);
+  size_t perState = 0;
+  for (size_t gi = 0; gi < groups.size(); ++gi)
+  {
+    for (int u : groups[gi])
+    {
+      std::vector<int> cols;
+      for (int j = bodyLastJnt[bodies[(size_t) u]]; j >= 0; j = jntPrev[j])
+      {
+        if (jntJacobi[j] >= 0)
+        {
+          cols.push_back(jntJacobi[j]);
+        }
+      }
+      for (size_t i = 0; i < cols.size(); ++i)
+      {
+        colMap[(size_t) u * nJ + cols[i]] = (int) (cols.size() - 1 - i);   /* ascending rank */
+      }
+      groupCols[gi] = (int) cols.size() > groupCols[gi] ? (int) cols.size() : groupCols[gi];
+    }
+    perState += groups[gi].size() * (12 + 6 * (size_t) groupCols[gi]);
+  }
   const size_t tmpDoubles = (size_t) chunk * perState;
   const size_t outDoubles = host ? (size_t) chunk * nJac * 3 * nJ : 0;
   const size_t qDoubles = host ? (size_t) chunk * qdim : 0;
@@ -276,12 +317,19 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
   CombineTask* dTasks = nullptr;
   SlotInfo* dSlots = nullptr;
   RCSB_CUDA(cudaMalloc(&tmp, (tmpDoubles + outDoubles + qDoubles) * sizeof(double)));
-  cudaError_t e = cudaMalloc(&dTasks, tasks.size() * sizeof(CombineTask) + (size_t) nU * sizeof(SlotInfo));
+  int* dColMap = nullptr;
+  cudaError_t e = cudaMalloc(&dTasks, tasks.size() * sizeof(CombineTask) + (size_t) nU * sizeof(SlotInfo) +
+                                      colMap.size() * sizeof(int));
   if (e == cudaSuccess)
   {
     dSlots = reinterpret_cast<SlotInfo*>(dTasks + tasks.size());
+    dColMap = reinterpret_cast<int*>(dSlots + nU);
     e = cudaMemcpyAsync(dTasks, tasks.data(), tasks.size() * sizeof(CombineTask),
                         cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess)
+  {
+    e = cudaMemcpyAsync(dColMap, colMap.data(), colMap.size() * sizeof(int), cudaMemcpyHostToDevice, st);
   }
   int result = RCSB_OK;
   std::vector<SlotInfo> slots((size_t) nU);
@@ -302,9 +350,11 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
       }
     }
     long base = 0;
-    for (const std::vector<int>& grp : groups)
+    for (size_t gi = 0; gi < groups.size(); ++gi)
     {
+      const std::vector<int>& grp = groups[gi];
       const int G = (int) grp.size();
+      const long nc = groupCols[gi];
       std::vector<int> gb((size_t) G);
       for (int i = 0; i < G; ++i)
       {
@@ -312,23 +362,31 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
       }
       double* A = tmp + base;
       double* JT = A + (size_t) n * G * 12;
-      double* JR = JT + (size_t) n * G * 3 * nJ;
+      double* JR = JT + (size_t) n * G * 3 * nc;
       for (int i = 0; i < G; ++i)
       {
         SlotInfo& si = slots[(size_t) grp[(size_t) i]];
         si.offA = base + 12L * i;
         si.strideA = 12L * G;
-        si.offJ = (JT - tmp) + 3L * nJ * i;
-        si.strideJ = 3L * nJ * G;
+        si.offJ = (JT - tmp) + 3L * nc * i;
+        si.strideJ = 3L * nc * G;
         si.jrShift = JR - JT;
+        si.rowStride = (int) nc;
+        si.pad = 0;
       }
-      result = fkCommon(m, n, qdim, dQ, nullptr, G, gb.data(), A, nullptr, nullptr, nullptr,
-                        nullptr, G, gb.data(), nullptr, JT, JR, nullptr, false, 0, st);
+      int recCols = 0;
+      result = fkCompactDevice(m, n, qdim, dQ, G, gb.data(), A, JT, JR, st, &recCols);
       if (result != RCSB_OK)
       {
         break;
       }
-      base += (long) n * G * (12 + 6L * nJ);
+      if (recCols != nc)
+      {
+        rcsb_set_error("rcsb_task_jacobians: internal record width mismatch (%d, %ld)", recCols, nc);
+        result = RCSB_EINVAL;
+        break;
+      }
+      base += (long) n * G * (12 + 6L * nc);
     }
     if (result != RCSB_OK)
     {
@@ -349,6 +407,7 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
     ca.slots = dSlots;
     ca.out = dOut;
     ca.tasks = dTasks;
+    ca.colMap = dColMap;
     ca.n = n;
     ca.nTasks = nJac;
     ca.nJ = nJ;
