@@ -241,6 +241,33 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
     bodies.push_back(0);   /* only NULL bodies: all rows are zero, keep the pass well-formed */
   }
   const int nU = (int) bodies.size();
+  std::vector<char> needT((size_t) nU, 0), needR((size_t) nU, 0);
+  for (const CombineTask& c : tasks)
+  {
+    auto mark = [&](std::vector<char>& v, int u) {
+      if (u >= 0)
+      {
+        v[(size_t) u] = 1;
+      }
+    };
+    if (c.kind == RCSB_JAC_POS)
+    {
+      mark(needT, c.u2);
+      if (c.mode == 1)
+      {
+        mark(needT, c.u1);
+        mark(needR, c.u3);
+      }
+    }
+    else
+    {
+      mark(needR, c.u2);
+      if (c.mode == 1)
+      {
+        mark(needR, c.u1);
+      }
+    }
+  }
 
   /* groups of bodies whose joint chains fit the FK kernel's shared-memory scratch together */
   std::vector<std::vector<int>> groups;
@@ -374,8 +401,16 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
         si.rowStride = (int) nc;
         si.pad = 0;
       }
+      /* only the Jacobians some task reads (a world position task needs no rotation Jacobian) */
+      bool wantT = false, wantR = false;
+      for (int i = 0; i < G; ++i)
+      {
+        wantT = wantT || needT[(size_t) grp[(size_t) i]];
+        wantR = wantR || needR[(size_t) grp[(size_t) i]];
+      }
       int recCols = 0;
-      result = fkCompactDevice(m, n, qdim, dQ, G, gb.data(), A, JT, JR, st, &recCols);
+      result = fkCompactDevice(m, n, qdim, dQ, G, gb.data(), A, wantT ? JT : nullptr,
+                               wantR ? JR : nullptr, st, &recCols);
       if (result != RCSB_OK)
       {
         break;
