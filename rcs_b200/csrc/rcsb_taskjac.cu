@@ -9,8 +9,8 @@
  *       fixed ref:  J = A_1I JR_2          (refFrame == refBdy, not articulated)
  *       relative:   J = A_3I (JR_2 - JR_1)
  * (2 = effector, 1 = refBdy, 3 = refFrame.) The frames and world Jacobians of the bodies
- * involved come from fkKernel (rcsb_fk.cu) in passes of a few ten thousand states, so that
- * the intermediate stays in L2; combineKernel turns them into the task rows, one thread per
+ * involved come from fkKernel (rcsb_fk.cu) in passes of 131,072 states (compact records of
+ * the bodies' own chain columns); combineKernel turns them into the task rows, one thread per
  * (state, task, column), consecutive threads on consecutive columns.
  */
 #include <cstdlib>
@@ -312,7 +312,10 @@ extern "C" int rcsb_task_jacobians(const RcsbModel* cm, long N, int qdim, const 
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
   RCSB_CUDA(cudaSetDevice(m->device));
 
-  static const long passStates = getenv("RCSB_TASKJAC_PASS") ? atol(getenv("RCSB_TASKJAC_PASS")) : 32768;
+  /* states per pass: large enough to fill the GPU with the per-body launches (measured on the
+   * humanoid's cAction task set, ms per 1M states: 8192: 12.9, 32768: 5.8, 131072: 5.5,
+   * 262144: 5.2), bounded for the size of the intermediate buffer */
+  static const long passStates = getenv("RCSB_TASKJAC_PASS") ? atol(getenv("RCSB_TASKJAC_PASS")) : 131072;
   const long chunk = N < passStates ? N : passStates;
   /* compact record width of every group and the column maps of the bodies */
   std::vector<int> colMap((size_t) nU * nJ, -1), groupCols(groups.size(), 1);
