@@ -59,6 +59,8 @@ extern "C" {
  * (src/RcsCore/TaskPosition3D.cpp:49, TaskEuler3D.cpp:52) */
 #define RCSB_TASK_XYZ 1
 #define RCSB_TASK_ABC 2
+#define RCSB_TASK_XYZABC 3   /* TaskPose6D (src/RcsCore/TaskPose6D.cpp): XYZ followed by ABC of the same
+                                effector, six entries of x_des */
 
 typedef struct RcsbModel RcsbModel;
 

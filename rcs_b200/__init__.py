@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     RcsbError,
     TASK_ABC,
     TASK_XYZ,
+    TASK_XYZABC,
     build_library,
     kernel_launch_count,
     lib,
@@ -24,6 +25,7 @@ __all__ = [
     "RcsbError",
     "TASK_ABC",
     "TASK_XYZ",
+    "TASK_XYZABC",
     "build_library",
     "kernel_launch_count",
     "lib",

@@ -25,6 +25,7 @@ _LIB = None
 
 TASK_XYZ = 1
 TASK_ABC = 2
+TASK_XYZABC = 3
 _HOST_PTRS = 1
 _IK_LEFT_INVERSE = 2
 
@@ -461,12 +462,12 @@ class Model:
         """`iters` IkSolverRMR::solveRightInverse steps per state (solveLeftInverse with
         `left_inverse`); q is updated in place.
 
-        tasks: sequence of (TASK_XYZ | TASK_ABC, effector body index).
+        tasks: sequence of (TASK_XYZ | TASK_ABC | TASK_XYZABC, effector body index).
         """
         N, qdim = self._batch(q)
         if qdim != self.dof:
             raise RcsbError("ik_rmr: q must be N x dof")
-        nx = 3 * len(tasks)
+        nx = sum(6 if int(k) == TASK_XYZABC else 3 for k, _ in tasks)
         shapes = {"dx": (N, nx), "dq": (N, self.dof), "det": (N,)}
         out = dict(out or {})
         for k in want:

@@ -421,14 +421,30 @@ extern "C" int rcsb_direct_dynamics(const RcsbModel* cm, long N, int qdim, const
 namespace
 {
 
-int buildIkPlan(RcsbModel* m, int nTasks, const RcsbTask* tasks, const DevicePlan** out)
+int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const DevicePlan** out)
 {
   const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
-  if (nTasks <= 0 || !tasks)
+  if (nTasksIn <= 0 || !tasksIn)
   {
     rcsb_set_error("rcsb_ik_rmr: no tasks");
     return RCSB_EINVAL;
   }
+  /* a 6-D pose task is a position task followed by an orientation task of the same effector */
+  std::vector<RcsbTask> expanded;
+  for (int t = 0; t < nTasksIn; ++t)
+  {
+    if (tasksIn[t].kind == RCSB_TASK_XYZABC)
+    {
+      expanded.push_back({RCSB_TASK_XYZ, tasksIn[t].effector});
+      expanded.push_back({RCSB_TASK_ABC, tasksIn[t].effector});
+    }
+    else
+    {
+      expanded.push_back(tasksIn[t]);
+    }
+  }
+  const int nTasks = (int) expanded.size();
+  const RcsbTask* tasks = expanded.data();
   for (int t = 0; t < nTasks; ++t)
   {
     if (tasks[t].kind != RCSB_TASK_XYZ && tasks[t].kind != RCSB_TASK_ABC)

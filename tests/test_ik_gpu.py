@@ -353,3 +353,25 @@ def test_left_inverse_with_coupled_joints(refmod, cuda_device):
     scale = np.maximum(1.0, np.abs(dq_ref).max(axis=1))
     assert np.all(np.abs(out["dq"] - dq_ref)[ok].max(axis=1) <= 1e-8 * scale[ok])
     assert np.all(np.abs(q - q_ref)[ok].max(axis=1) <= 1e-8 * scale[ok])
+
+
+def test_pose6d_task_is_position_plus_euler_angles(refmod, cuda_device):
+    """RCSB_TASK_XYZABC = the reference's TaskPose6D (controlVariable "XYZABC",
+    src/RcsCore/TaskPose6D.cpp): one 6-D task instead of an XYZ and an ABC task."""
+    from rcs_b200 import TASK_XYZABC
+
+    g = rcs_b200.Graph(graph_file("wam_arm"))
+    m = rcs_b200.Model(g, cuda_device)
+    rik = refmod.RefIk(graph_file("wam_arm"), [("XYZABC", "BallTip")])
+    assert rik.nx == 6
+    q0, x_des = _targets(g, rik, 1000, seed_first=3)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr([(TASK_XYZABC, g.body_index("BallTip"))], q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert out["dx"].shape == (1000, 6)
+    assert_close(out["dx"], dx_ref, what="dx")
+    cond = step_condition(rik, q0)
+    assert_step_close(out["dq"], dq_ref, cond, "dq")
+    two = q0.copy()
+    m.ik_rmr([(TASK_XYZ, g.body_index("BallTip")), (TASK_ABC, g.body_index("BallTip"))], two, x_des, iters=1)
+    assert np.array_equal(two, q)
