@@ -66,6 +66,45 @@ __global__ void __launch_bounds__(128, 4) tripleKernel(double* out, long n, int 
   }
 }
 
+/* "bulk": every thread stages its frame in its own 96-byte shared-memory slot and hands it to the
+ * TMA engine as one asynchronous bulk store (cp.async.bulk.global.shared::cta): no exchange
+ * between lanes, no warp barrier, the store does not occupy the thread */
+template <int FRAMES>
+__global__ void __launch_bounds__(128, 4) bulkKernel(double* out, long n, int recDoubles, int spin)
+{
+  __shared__ __align__(16) double slot[128 * 12];
+  const long s = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+  {
+    return;
+  }
+  double* mine = slot + 12 * threadIdx.x;
+  const unsigned int src = (unsigned int) __cvta_generic_to_shared(mine);
+  double* rec = out + s * recDoubles;
+  double x = (double) s;
+  for (int f = 0; f < FRAMES; ++f)
+  {
+    for (int k = 0; k < spin; ++k)
+    {
+      x = fma(x, 1.0000001, 1e-9);
+    }
+    /* the previous bulk store must have read the slot before it is overwritten */
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    double2* m2 = reinterpret_cast<double2*>(mine);
+    m2[0] = make_double2(x, x + 1);
+    m2[1] = make_double2(x + 2, x + 3);
+    m2[2] = make_double2(x + 4, x + 5);
+    m2[3] = make_double2(x + 6, x + 7);
+    m2[4] = make_double2(x + 8, x + 9);
+    m2[5] = make_double2(x + 10, x + 11);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;" ::"l"(rec + 12 * f), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(128, 4) rowKernel(double* out, long n, int recDoubles)
 {
   const long w0 = ((long) blockIdx.x * blockDim.x + threadIdx.x) / 32 * 32;
@@ -113,6 +152,10 @@ static void launchTriple12(double* out, long n, int rd)
 {
   tripleKernel<12><<<(unsigned) ((n + 127) / 128), 128>>>(out, n, rd);
 }
+static void launchBulk12(double* out, long n, int rd)
+{
+  bulkKernel<12><<<(unsigned) ((n + 127) / 128), 128>>>(out, n, rd, g_spin);
+}
 static void launchRow(double* out, long n, int rd)
 {
   rowKernel<<<(unsigned) ((n + 127) / 128), 128>>>(out, n, rd);
@@ -139,6 +182,13 @@ int main()
   const float mst = timeIt(launchTriple12, out, n, recDoubles);
   printf("{\"pattern\": \"triple: the 3 sectors of a frame from 3 neighbouring lanes of one store\", \"ms\": %.4f, "
          "\"GBps\": %.1f}\n", mst, bytes / (mst * 1e-3) / 1e9);
+  for (int spin = 0; spin <= 64; spin += 64)
+  {
+    g_spin = spin;
+    const float msb = timeIt(launchBulk12, out, n, recDoubles);
+    printf("{\"pattern\": \"bulk: one 96-byte TMA bulk store per thread and frame\", \"spin\": %d, \"ms\": %.4f, "
+           "\"GBps\": %.1f}\n", spin, msb, bytes / (msb * 1e-3) / 1e9);
+  }
   const float msr = timeIt(launchRow, out, n, recDoubles);
   printf("{\"pattern\": \"row: coalesced 8-byte stores, 32 records per warp\", \"ms\": %.4f, \"GBps\": %.1f}\n", msr,
          bytes / (msr * 1e-3) / 1e9);
