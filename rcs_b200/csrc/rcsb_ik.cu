@@ -257,9 +257,7 @@ ikKernel(const IkArgs a)
   extern __shared__ __align__(16) char smem[];
   char* sModel = smem;
   char* sPlan = smem + a.modelBytes;
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
 
   ModelView m;
   m.bind(sModel);
@@ -905,9 +903,7 @@ ikChainKernel(const IkArgs a)
   char* sModel = smem;
   char* sPlan = smem + a.modelBytes;
   double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [9][RCSB_IK_THREADS] */
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
 
   ModelView m;
   m.bind(sModel);
@@ -1339,9 +1335,7 @@ ikChainLoopKernel(const IkArgs a, int nc)
   char* sPlan = smem + a.modelBytes;
   double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [9][T] */
   double* sCol = sAd + 9 * T;                                     /* [nc][8][T]: 0..5 column, 6 q, 7 dq */
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
 
   ModelView m;
   m.bind(sModel);
@@ -1652,9 +1646,7 @@ ikMultiKernel(const IkArgs a, int nU, int nEffs)
   double* sAd = reinterpret_cast<double*>(sPlan + a.planBytes);   /* [NT][9][T] desired rotations */
   double* sEff = sAd + NT * 9 * T;                                /* [nEffs][12][T] effector frames */
   double* sCol = sEff + nEffs * 12 * T;                           /* [nU][8][T] */
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
 
   ModelView m;
   m.bind(sModel);

@@ -133,9 +133,7 @@ ktWalkKernel(const KtArgs a)
   double* sWin = reinterpret_cast<double*>(sPlan + a.planWalkBytes);
   double* sAcc = sWin + (RCSB_KT_WALK_THREADS / 32) * 32 * 33;
 
-  stageBlob(sModel, a.model, a.modelBytes);
-  stageBlob(sPlan, a.plan, a.planWalkBytes);
-  __syncthreads();
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planWalkBytes);
 
   ModelView m;
   m.bind(sModel);
@@ -511,8 +509,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   char* sPlan = smem;
   double* sBuf = reinterpret_cast<double*>(sPlan + a.planBytes);
 
-  stageBlob(sPlan, a.plan, a.planBytes);
-  __syncthreads();
+  stageBlobsTma(sPlan, a.plan, a.planBytes, nullptr, nullptr, 0);
   KtPlanView p;
   p.bind(sPlan);
 
