@@ -12,7 +12,12 @@
  *                        src/RcsCore/Rcs_graph.c:231, :301 (kernel: :61-226)
  *   rcsb_fk_jacobians    + RcsGraph_bodyPointJacobian  src/RcsCore/Rcs_kinematics.c:200
  *                        + RcsGraph_rotationJacobian   src/RcsCore/Rcs_kinematics.c:416
+ *   rcsb_fk_jacobians_mass   the same + M(q) (RcsGraph_computeMassMatrix, Rcs_dynamics.c:610) in
+ *                        one launch: BASELINE.json's metric "FK+Jacobian+M(q) states/sec"
+ *   rcsb_task_jacobians  RcsGraph_3dPosJacobian / 3dOmegaJacobian  Rcs_kinematics.c:566, :789
  *   rcsb_kinetic_terms   RcsGraph_computeKineticTerms  src/RcsCore/Rcs_dynamics.c:439
+ *   rcsb_cog, rcsb_kinetic_terms_cog   RcsGraph_COG / COGJacobian  Rcs_kinematics.c:904, :973
+ *   rcsb_direct_dynamics Rcs_directDynamics            src/RcsCore/Rcs_dynamics.c:673
  *   rcsb_ik_rmr          ControllerBase::computeDX / computeJ / computeJointlimitGradient
  *                        (src/RcsCore/ControllerBase.cpp:776, :896, :1332) +
  *                        IkSolverRMR::solveRightInverse (src/RcsCore/IkSolverRMR.cpp:403)
