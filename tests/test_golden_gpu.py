@@ -17,7 +17,7 @@ from conftest import GRAPH_DIR, ROOT, assert_close, assert_structural_zeros, gra
 from oracle import rcs_oracle
 
 pytestmark = pytest.mark.gpu
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry"]
 
 
 def _golden(name):
@@ -57,7 +57,38 @@ def test_fk_jacobians_kinetic_terms_match_golden(name, cuda_device):
     assert np.all(err <= tol), f"{name}: direct dynamics, worst err/tol {float((err / tol).max()):.2f}"
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "humanoid"])
+@pytest.mark.parametrize("name", ["wam_arm", "gantry"])
+def test_fused_mass_matrix_and_left_inverse_match_golden(name, cuda_device):
+    """The fused FK + Jacobians + M(q) launch (serial-chain variant on both graphs, the gantry with
+    translational joints) and RCSB_IK_LEFT_INVERSE steps against vectors recorded from the
+    reference (RcsGraph_computeMassMatrix; IkSolverRMR::solveLeftInverse, lambda 1e-3)."""
+    z = _golden(name)
+    g = rcs_b200.Graph(graph_file(name))
+    m = rcs_b200.Model(g, cuda_device)
+    q = np.ascontiguousarray(z["q"])
+    out = m.fk_jacobians(q, [int(e) for e in z["eff"]], points=z["pts"], want=("A_BI", "JT", "JR", "M"))
+    assert_close(out["M"], z["mass_M"], what=f"{name}:M (fused)")
+    assert_structural_zeros(out["M"], z["mass_M"], what=f"{name}:M (fused)")
+    assert_close(out["JT"], z["jac_JT"], what=f"{name}:JT (fused)")
+    assert_close(out["JR"], z["jac_JR"], what=f"{name}:JR (fused)")
+    assert_close(out["A_BI"], z["fk_A_BI"], what=f"{name}:A_BI (fused)")
+    tip = int(z["ik_tip"])
+    qs = np.ascontiguousarray(z["ik_q_start"]).copy()
+    ik = m.ik_rmr([(TASK_XYZ, tip), (TASK_ABC, tip)], qs, np.ascontiguousarray(z["ik_x_des"]), lam=1.0e-3,
+                  iters=1, want=("dx", "dq", "det"), left_inverse=True)
+    assert_close(ik["dx"], z["ikl_dx1"], what="dx")
+    # lambda = 1e-3 bounds the condition number of J_r^T J_r + lambda 1 by (s_max^2 + lambda) / lambda
+    scale = np.maximum(1.0, np.abs(z["ikl_dq1"]).max(axis=1))
+    assert np.all(np.abs(ik["dq"] - z["ikl_dq1"]).max(axis=1) <= 1e-9 * scale)
+    assert np.all(np.abs(qs - z["ikl_q1"]).max(axis=1) <= 1e-9 * scale)
+    assert np.all(np.abs(ik["det"] / z["ikl_det1"] - 1.0) <= 1e-9)
+    q5 = np.ascontiguousarray(z["ik_q_start"]).copy()
+    m.ik_rmr([(TASK_XYZ, tip), (TASK_ABC, tip)], q5, np.ascontiguousarray(z["ik_x_des"]), lam=1.0e-3, iters=5,
+             left_inverse=True)
+    assert np.abs(q5 - z["ikl_q5"]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry"])
 def test_ik_matches_golden(name, cuda_device):
     z = _golden(name)
     g = rcs_b200.Graph(graph_file(name))

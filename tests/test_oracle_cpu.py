@@ -15,7 +15,7 @@ from conftest import GRAPH_DIR, GRAPHS, ROOT, assert_close, assert_structural_ze
 from oracle import rcs_oracle
 from rcs_b200 import workload
 
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry"]
 
 
 def layout(name):
@@ -78,7 +78,25 @@ def test_direct_dynamics_matches_golden(name):
     assert np.all(err <= tol), float((err / tol).max())
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "humanoid"])
+@pytest.mark.parametrize("name", ["wam_arm", "gantry"])
+def test_left_inverse_and_mass_matrix_match_golden(name):
+    """Recorded from the reference: IkSolverRMR::solveLeftInverse steps (lambda 1e-3) and
+    RcsGraph_computeMassMatrix."""
+    z, o = golden(name), rcs_oracle.Oracle(layout(name))
+    tip = int(z["ik_tip"])
+    tasks = [("XYZ", tip), ("ABC", tip)]
+    q1, dx1, dq1, det1 = o.ik_rmr(z["ik_q_start"], tasks, z["ik_x_des"], lam=1.0e-3, iters=1, left=True)
+    assert_close(dx1, z["ikl_dx1"], what="dx")
+    ok = z["ikl_det1"] > 0.0
+    assert ok.all()
+    assert np.abs(dq1 - z["ikl_dq1"]).max() <= 1e-9 and np.abs(q1 - z["ikl_q1"]).max() <= 1e-9
+    assert np.abs(det1 / z["ikl_det1"] - 1.0).max() <= 1e-9
+    q5 = o.ik_rmr(z["ik_q_start"], tasks, z["ik_x_des"], lam=1.0e-3, iters=5, left=True)[0]
+    assert np.abs(q5 - z["ikl_q5"]).max() <= 1e-8
+    assert_close(o.kinetic_terms(z["q"])["M"], z["mass_M"], what="M")
+
+
+@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry"])
 def test_ik_matches_golden(name):
     z, o = golden(name), rcs_oracle.Oracle(layout(name))
     tip = int(z["ik_tip"])

@@ -25,6 +25,7 @@ CASES = {
     "wam_scenario": dict(n=16, effectors=["Hand", "PowerGrip"]),
     "humanoid": dict(n=12, effectors=["RightHandTip", "LeftHandTip", "FootL"]),
     "husky": dict(n=8, effectors=None),
+    "gantry": dict(n=16, effectors=["Tool", "Camera"]),
 }
 
 
@@ -59,14 +60,22 @@ def main():
                    **{"fk_" + k: v for k, v in fk.items()},
                    **{"jac_" + k: v for k, v in jac.items()},
                    **{"kt_" + k: v for k, v in kt.items()})
-        if name in ("wam_arm", "humanoid"):
-            tip = "BallTip" if name == "wam_arm" else "RightHandTip"
+        if g.nJ <= 8:
+            out["mass_M"] = g.mass_matrix(q)          # RcsGraph_computeMassMatrix (fused FK + J + M launch)
+        if name in ("wam_arm", "humanoid", "gantry"):
+            tip = {"wam_arm": "BallTip", "humanoid": "RightHandTip", "gantry": "Tool"}[name]
             ik = ref.RefIk(f, [("XYZ", tip), ("ABC", tip)])
             q_goal = workload.sample_states(lay, n, first=2000, margin=0.2)
             x_des, J = ik.task_kinematics(q_goal)
             q_start = q_goal + 0.1 * np.random.default_rng(5).uniform(-1, 1, size=q_goal.shape)
             q1, dx1, dq1, det1 = ik.rmr(q_start, x_des, iters=1)
             q10, dx10, dq10, det10 = ik.rmr(q_start, x_des, iters=10)
+            if name != "humanoid":
+                # IkSolverRMR::solveLeftInverse, lambda 1e-3 (keeps the nq x nq matrix of the redundant
+                # arm well conditioned)
+                ql, dxl, dql, detl = ik.rmr(q_start, x_des, lam=1.0e-3, iters=1, left=True)
+                ql5, _, _, _ = ik.rmr(q_start, x_des, lam=1.0e-3, iters=5, left=True)
+                out.update(ikl_q1=ql, ikl_dx1=dxl, ikl_dq1=dql, ikl_det1=detl, ikl_q5=ql5)
             out.update(ik_tip=np.array(names.index(tip)), ik_q_start=q_start, ik_x_des=x_des,
                        ik_J_goal=J, ik_q1=q1, ik_dx1=dx1, ik_dq1=dq1, ik_det1=det1, ik_q10=q10,
                        ik_dx10=dx10, ik_det10=det10)
