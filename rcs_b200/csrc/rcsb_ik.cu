@@ -895,7 +895,10 @@ __device__ __forceinline__ void chainStep(Frame& f, const int4 st, const double*
 #ifndef RCSB_IK_CHAIN_MIN_BLOCKS
 #define RCSB_IK_CHAIN_MIN_BLOCKS 2
 #endif
-template <int NC, int NX>
+/* LEFT: the step of IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) instead: with
+ * J_r = J invWq, dq = invWq o (g + (J_r^T J_r + lambda 1)^-1 J_r^T (dx - J_r g)), the NC x NC
+ * system factored like the NX x NX one of the right inverse. */
+template <int NC, int NX, bool LEFT = false>
 __global__ void __launch_bounds__(RCSB_IK_THREADS, RCSB_IK_CHAIN_MIN_BLOCKS)
 ikChainKernel(const IkArgs a)
 {
@@ -1056,6 +1059,149 @@ ikChainKernel(const IkArgs a)
         jo[c][2] = ax[c][2];
         ax[c][0] = ax[c][1] = ax[c][2] = 0.0;
       }
+    }
+
+    if (LEFT)
+    {
+      constexpr int NB = NC * (NC + 1) / 2;
+      double B[NB], rl[NX], gl[NC], bl[NC], invl[NC];
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        rl[i] = 0.0;
+      }
+      /* columns of J_r = J invWq in place; r = dx - J_r g */
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+      {
+        const double w = p.chainW[c];
+        gl[c] = w * (-(a.alpha * (p.chainGain[c] * (qc[c] - p.chainQ0[c]))));
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          jo[c][i] *= w;
+          ax[c][i] *= w;
+          rl[i] += (xyzFirst ? jo[c][i] : ax[c][i]) * gl[c];
+          if (NT == 2)
+          {
+            rl[3 + i] += (xyzFirst ? ax[c][i] : jo[c][i]) * gl[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+      {
+        rl[i] = dx[i] - rl[i];
+      }
+      /* B = J_r^T J_r + lambda 1 (lower triangle), b = J_r^T r */
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+      {
+#pragma unroll
+        for (int d = 0; d <= c; ++d)
+        {
+          double sum = 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+          {
+            sum += jo[c][i] * jo[d][i];
+          }
+          if (NT == 2)
+          {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+              sum += ax[c][i] * ax[d][i];
+            }
+          }
+          else if (!xyzFirst)
+          {
+            /* a single orientation task: its rows are the rotation rows */
+            sum = ax[c][0] * ax[d][0] + ax[c][1] * ax[d][1] + ax[c][2] * ax[d][2];
+          }
+          B[c * (c + 1) / 2 + d] = sum + (c == d ? a.lambda : 0.0);
+        }
+        double sb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          sb += (xyzFirst ? jo[c][i] : ax[c][i]) * rl[i];
+          if (NT == 2)
+          {
+            sb += (xyzFirst ? ax[c][i] : jo[c][i]) * rl[3 + i];
+          }
+        }
+        bl[c] = sb;
+      }
+      /* Banachiewicz Cholesky of the NC x NC matrix, det = prod of the pivots */
+      bool okl = true;
+      det = 1.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+      {
+#pragma unroll
+        for (int k = 0; k <= i; ++k)
+        {
+          double sum = B[i * (i + 1) / 2 + k];
+#pragma unroll
+          for (int t = 0; t < k; ++t)
+          {
+            sum -= B[i * (i + 1) / 2 + t] * B[k * (k + 1) / 2 + t];
+          }
+          if (k < i)
+          {
+            B[i * (i + 1) / 2 + k] = sum * invl[k];
+          }
+          else
+          {
+            okl = okl && (sum > 0.0);
+            const double piv = okl ? sum : 1.0;
+            invl[i] = rsqrt(piv);
+            B[i * (i + 1) / 2 + i] = piv * invl[i];
+            det *= piv;
+          }
+        }
+      }
+      if (!okl)
+      {
+        det = 0.0;
+        singular |= 1ull << it;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+        {
+          dq[c] = 0.0;
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+      {
+        double sum = bl[i];
+#pragma unroll
+        for (int t = 0; t < i; ++t)
+        {
+          sum -= B[i * (i + 1) / 2 + t] * bl[t];
+        }
+        bl[i] = sum * invl[i];
+      }
+#pragma unroll
+      for (int i = NC - 1; i >= 0; --i)
+      {
+        double sum = bl[i];
+#pragma unroll
+        for (int t = i + 1; t < NC; ++t)
+        {
+          sum -= B[t * (t + 1) / 2 + i] * bl[t];
+        }
+        bl[i] = sum * invl[i];
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+      {
+        dq[c] = (gl[c] + bl[c]) * p.chainW[c];
+        qc[c] += dq[c];
+      }
+      continue;
     }
 
     /* ---- A = J invWq J^T + lambda 1 (lower triangle), r = dx - J g ---------------------------- */
@@ -2019,13 +2165,13 @@ static cudaError_t launchMulti(const IkArgs& a, int nSlots, int nU, int nEffs, c
 #undef RCSB_LAUNCH
 }
 
-template <int NC, int NX>
+template <int NC, int NX, bool LEFT = false>
 static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
                            9 * RCSB_IK_THREADS * sizeof(double);
   const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
-  auto k = ikChainKernel<NC, NX>;
+  auto k = ikChainKernel<NC, NX, LEFT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int) smemBytes);
   if (e != cudaSuccess)
@@ -2036,19 +2182,19 @@ static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
   return cudaGetLastError();
 }
 
-template <int NX>
+template <int NX, bool LEFT = false>
 static cudaError_t launchChainNc(const IkArgs& a, int nc, cudaStream_t stream)
 {
   switch (nc)
   {
-    case 1: return launchChain<1, NX>(a, stream);
-    case 2: return launchChain<2, NX>(a, stream);
-    case 3: return launchChain<3, NX>(a, stream);
-    case 4: return launchChain<4, NX>(a, stream);
-    case 5: return launchChain<5, NX>(a, stream);
-    case 6: return launchChain<6, NX>(a, stream);
-    case 7: return launchChain<7, NX>(a, stream);
-    case 8: return launchChain<8, NX>(a, stream);
+    case 1: return launchChain<1, NX, LEFT>(a, stream);
+    case 2: return launchChain<2, NX, LEFT>(a, stream);
+    case 3: return launchChain<3, NX, LEFT>(a, stream);
+    case 4: return launchChain<4, NX, LEFT>(a, stream);
+    case 5: return launchChain<5, NX, LEFT>(a, stream);
+    case 6: return launchChain<6, NX, LEFT>(a, stream);
+    case 7: return launchChain<7, NX, LEFT>(a, stream);
+    case 8: return launchChain<8, NX, LEFT>(a, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -2094,7 +2240,11 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
   }
   if (a->leftInverse)
   {
-    /* solveLeftInverse: general kernel only */
+    /* solveLeftInverse: the register kernel for short single chains, else the general kernel */
+    if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
+    {
+      return nx == 3 ? launchChainNc<3, true>(*a, chainNc, stream) : launchChainNc<6, true>(*a, chainNc, stream);
+    }
     if (nx <= 6 && nJ <= 8 && dof <= 8)
     {
       return launchIk<6, 8, 8, true>(*a, nSlots, stream);

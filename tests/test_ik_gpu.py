@@ -299,16 +299,21 @@ def _left_condition(rik, q, lam=1.0e-8):
     return np.linalg.cond(B)
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["chain-kernel", "general-kernel"])
 @pytest.mark.parametrize("name,eff,kinds,lam", [("gantry", "Tool", ("XYZ", "ABC"), 1.0e-8),
                                                 ("gantry", "Tool", ("XYZ",), 1.0e-4),
+                                                ("gantry", "Tool", ("ABC",), 1.0e-4),
                                                 ("wam_arm", "BallTip", ("XYZ", "ABC"), 1.0e-3),
                                                 ("wam_arm", "BallTip", ("ABC", "XYZ"), 1.0e-8)])
-def test_left_inverse_matches_reference(name, eff, kinds, lam, refmod, cuda_device):
+def test_left_inverse_matches_reference(name, eff, kinds, lam, general, refmod, cuda_device, monkeypatch):
     """RCSB_IK_LEFT_INVERSE: IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272), the nq x nq
     left pseudo-inverse (J_r^T J_r + lambda 1)^-1 J_r^T with J_r = J A invWq_r and the null-space
     term through the same inverse. The step goes through the inverse of that nq x nq matrix: the
     bar is scaled by its condition number per state like the right inverse's (a redundant arm
-    with lambda = 1e-8 is regularised by lambda alone)."""
+    with lambda = 1e-8 is regularised by lambda alone). Short single chains take the register
+    kernel (ikChainKernel<..., LEFT>), RCSB_IK_GENERAL=1 forces the general one."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
     g, m, rik, tasks = _setup(name, eff, refmod, cuda_device, kinds)
     q0, x_des = _targets(g, rik, 1500, seed_first=77, perturb=0.08)
     q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, lam=lam, iters=1, left=True)

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--graph", default="wam_arm")
     ap.add_argument("--effector", default="BallTip")
     ap.add_argument("--effector2", default=None, help="second effector (XYZ+ABC as well): nx = 12")
+    ap.add_argument("--left", action="store_true", help="IkSolverRMR::solveLeftInverse, lambda 1e-3")
     args = ap.parse_args()
 
     g = rcs_b200.Graph(os.path.join(ROOT, "tests", "golden", "graphs", args.graph + ".xml"))
@@ -59,14 +60,16 @@ def main():
     det = torch.empty(n, dtype=torch.float64, device="cuda")
     for _ in range(args.warmup):
         q.copy_(q_start)
-        m.ik_rmr(tasks, q, x_des, iters=args.iters, out={"det": det})
+        m.ik_rmr(tasks, q, x_des, iters=args.iters, out={"det": det}, left_inverse=args.left,
+                 lam=1.0e-3 if args.left else 1.0e-8)
     torch.cuda.synchronize()
     ms = []
     for _ in range(args.steps):
         q.copy_(q_start)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m.ik_rmr(tasks, q, x_des, iters=args.iters, out={"det": det})
+        m.ik_rmr(tasks, q, x_des, iters=args.iters, out={"det": det}, left_inverse=args.left,
+                 lam=1.0e-3 if args.left else 1.0e-8)
         e1.record()
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
