@@ -294,3 +294,22 @@ def test_slave_joint_update_coupling_matrix_and_limit_gradient_match_the_oracle(
         cols = [j["jointIndex"] for j in lay["joints"] if j["jacobiIndex"] >= 0]
         assert _arr(dH).shape == (1, g.dof) and cost_full == cost
         np.testing.assert_allclose(_arr(dH)[0, cols], dH_ref[0], rtol=0, atol=1e-15)
+
+
+def test_bench_reference_arm_prints_the_contract_line(refmod):
+    """`bench.py --impl reference` (the CPU reference arm the driver runs next to ours): one JSON
+    line with the contract's keys, on the default workload, without touching a GPU."""
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["higher_is_better"] is True
+    assert line["metric"].startswith("FK+Jacobian+M(q) states/sec") and line["unit"] == "states/s"
+    assert line["value"] > 0 and line["dtype"] == "f64" and line["data"] == "synthetic"
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "states/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["vs_baseline"] is None
