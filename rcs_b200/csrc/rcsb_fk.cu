@@ -169,14 +169,25 @@ fkKernel(const FkArgs a)
   Frame f;
   double xd[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
   setIdentity(f);
-  double nextQ = 0.0, nextQd = 0.0;
+  /* joint values are fetched two joints ahead of their use */
+  double nextQ = 0.0, nextQd = 0.0, next2Q = 0.0, next2Qd = 0.0;
   const int jFirst = PRUNED ? p.hdr->firstJnt : (dof > 0 ? 0 : -1);
+  auto jointAfter = [&](int j) { return PRUNED ? p.jntNext[j] : (j + 1 < dof ? j + 1 : -1); };
   if (jFirst >= 0)
   {
     nextQ = rd.fetchQ(m, jFirst);
     if (VEL)
     {
       nextQd = rd.fetchQd(m, jFirst);
+    }
+    const int jSecond = jointAfter(jFirst);
+    if (jSecond >= 0)
+    {
+      next2Q = rd.fetchQ(m, jSecond);
+      if (VEL)
+      {
+        next2Qd = rd.fetchQd(m, jSecond);
+      }
     }
   }
 
@@ -284,7 +295,7 @@ fkKernel(const FkArgs a)
     {
       const int jf = nJf;
       const int jtype = nType;
-      const int jn = PRUNED ? p.jntNext[j] : (j + 1 < dof ? j + 1 : -1);
+      const int jn = jointAfter(j);
       if (jn >= 0)
       {
         nJf = m.jntFlags[jn];
@@ -298,12 +309,15 @@ fkKernel(const FkArgs a)
       /* joints are visited in jointIndex order: the loads of the next joint are in flight
        * while this one is processed */
       const double rawQ = nextQ, rawQd = nextQd;
-      if (jn >= 0)
+      nextQ = next2Q;
+      nextQd = next2Qd;
+      const int jn2 = jn >= 0 ? jointAfter(jn) : -1;
+      if (jn2 >= 0)
       {
-        nextQ = rd.fetchQ(m, jn);
+        next2Q = rd.fetchQ(m, jn2);
         if (VEL)
         {
-          nextQd = rd.fetchQd(m, jn);
+          next2Qd = rd.fetchQd(m, jn2);
         }
       }
       const double qj = rd.finishQ(m, j, rawQ);
