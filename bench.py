@@ -1,23 +1,26 @@
 #!/usr/bin/env python
 """bench.py — benchmark of rcs_b200 (contract: task description / DESIGN.md §6).
 
-Default workload (the headline line the driver records): BASELINE.json's metric,
-"FK+Jacobian+M(q) states/sec FP64", on the arm and batch of configs[1] ("7-DoF arm batched
-FK + Jacobians, 1M uniformly sampled joint states") -- the configuration north_star's target is
-quoted on ("batched FK+Jacobian+M(q) on a 7-DoF arm at N=1M states on one B200"):
+The default run prints ONE JSON line. Its top-level keys are the headline workload `fkm`:
+BASELINE.json's metric "FK+Jacobian+M(q) states/sec FP64" on the arm and batch of configs[1]
+("7-DoF arm batched FK + Jacobians, 1M uniformly sampled joint states"), the configuration
+north_star's target is quoted on:
   per state  in : q (7 doubles)
              out: A_BI of all 12 bodies (12 x 96 B) + JT, JR of BallTip (2 x 3 x 7 doubles)
                   + M(q) (7 x 7 doubles)
              = 1936 algorithmic bytes; one fkKernel<MASS> launch per step and rank.
-Other workloads (same JSON line, selected with --workload):
-  fk       configs[1] literally, without M(q): 1544 algorithmic bytes per state, fkKernel.
+Under "secondary" the same line carries one complete record (value, roofline, e2e, cpu_baseline,
+clocks, launches) for each other configuration of BASELINE.json, measured in the same process
+right after the headline:
+  ik       configs[3], the second half of the metric ("RMR IK solves/sec"): 7-DoF arm, XYZ + ABC
+           tasks on BallTip, lambda 1e-8, alpha 0.05, 10 RMR iterations, 4,194,304 targets in
+           total (strong scaling: sharded over the ranks).
   kinetic  configs[2]: humanoid (dof 65, nJ 34, 63 bodies), 262,144 states per GPU,
-           M + h + F_gravity + E; 10,840 algorithmic bytes per state; two kernels per pass.
-  ik       configs[3]: 7-DoF arm, XYZ + ABC tasks on BallTip, lambda 1e-8, alpha 0.05,
-           10 RMR iterations, 4,194,304 targets in total (strong scaling: sharded over ranks).
+           M + h + F_gravity + E; 10,840 algorithmic bytes per state.
   wholebody configs[4]: humanoid, FK of all 63 bodies + the 20 task-Jacobian rows of the
            reference's cAction.xml + M(q), 1,048,576 states per GPU; N > 1 adds the all-gather
            of both hand-tip frames of every state (192 B per state) to the summary statistics.
+`--workload X` measures X alone (fk = configs[1] literally, without M(q)).
 
 One step = one pass of the hot path over one batch + (N > 1) one NCCL all-gather of per-rank
 summary statistics, the only collective of the path.
@@ -27,7 +30,8 @@ summary statistics, the only collective of the path.
             H2D of the inputs and D2H of every result inside the timed region
   roofline  algorithmic bytes (or FP64 flops) per launch / mean kernel time of the timed steps
   cpu_baseline / --impl reference: the unmodified reference library (oracle/_ref) on the
-            host cores, one RcsGraph_clone (+ controller and solver) per thread.
+            host cores, one RcsGraph_clone (+ controller and solver) per thread, cloned before
+            the clock starts, one RcsGraph_setState per state.
 """
 from __future__ import annotations
 
@@ -46,6 +50,7 @@ import numpy as np  # noqa: E402
 
 GRAPHS = os.path.join(ROOT, "tests", "golden", "graphs")
 UNIT = {"fk": "states/s", "fkm": "states/s", "kinetic": "states/s", "ik": "solves/s", "wholebody": "states/s"}
+SECONDARY = ("ik", "kinetic", "wholebody")
 # active task set of the reference's GenericHumanoid/cAction.xml (nx = 20): hand positions, COG x / y,
 # both feet as 6-D poses relative to the Heel
 WB_TASKS = [("XYZ", "RightHandTip"), ("XYZ", "LeftHandTip"), ("COGX", "Heel"), ("COGY", "Heel"),
@@ -79,7 +84,6 @@ class Workload:
             self.scaling = "weak"
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8            # 1544
             self.kernel = "rcsb::fkKernel"
-            self.launches_per_step = 1
             self.desc = ("configs[1] without M(q): WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames "
                          "+ JT/JR of BallTip, uniformly sampled joint states")
             self.l2 = "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)"
@@ -89,7 +93,6 @@ class Workload:
             self.scaling = "weak"
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8 + 7 * 7 * 8  # 1936
             self.kernel = "rcsb::fkKernel<MASS = 2> (serial chain: composite inertias after the walk)"
-            self.launches_per_step = 1
             self.desc = ("configs[1] + M(q), the configuration the metric and north_star's target are quoted "
                          "on: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all 12 body frames + JT/JR of "
                          "BallTip + mass matrix M(q) from one launch (rcsb_fk_jacobians_mass), uniformly "
@@ -100,8 +103,7 @@ class Workload:
             self.per_gpu = 1 << 18
             self.scaling = "weak"
             self.bytes_per_unit = 2 * 65 * 8 + (34 * 34 + 2 * 34 + 1) * 8     # 10840
-            self.kernel = "rcsb::ktWalkKernel + rcsb::ktAssembleKernel"
-            self.launches_per_step = None                                     # counted live
+            self.kernel = "rcsb kinetic-terms kernels (see DESIGN.md)"
             self.desc = ("configs[2]: GenericHumanoid (dof 65, nJ 34, 63 bodies), "
                          "RcsGraph_computeKineticTerms M, h, F_gravity, E; q and q_dot uniformly sampled")
             self.l2 = "per-step working set 2.8 GB per GPU >> 126 MB L2 (no flush needed)"
@@ -112,7 +114,6 @@ class Workload:
             self.scaling = "strong"
             self.bytes_per_unit = 56 + 48 + 56 + 8                            # q in, x_des, q out, det
             self.kernel = "rcsb::ikChainKernel<7, 6>"
-            self.launches_per_step = 1
             self.desc = ("configs[3]: WAM 7-DoF arm, IkSolverRMR right inverse, tasks XYZ + ABC on BallTip, "
                          f"lambda {IK_LAMBDA}, alpha {IK_ALPHA}, {IK_ITERS} iterations per target; targets = "
                          "poses of uniformly sampled states, start = goal state + U(-0.1, 0.1) rad")
@@ -123,8 +124,7 @@ class Workload:
             self.scaling = "weak"
             # q + 63 frames + 20 task rows x 34 + M
             self.bytes_per_unit = 65 * 8 + 63 * 96 + 20 * 34 * 8 + 34 * 34 * 8   # 21256
-            self.kernel = "rcsb::fkKernel (frames; effector chains) + combineKernel + ktWalkKernel + ktAssembleKernel"
-            self.launches_per_step = None
+            self.kernel = "rcsb whole-body kernels (see DESIGN.md)"
             self.desc = ("configs[4]: GenericHumanoid (dof 65, nJ 34, 63 bodies), FK of all 63 bodies + the task "
                          "Jacobians of cAction.xml's active set (hands XYZ, COG x/y, both feet XYZABC relative to "
                          "the Heel: nx 20) + mass matrix; N > 1: all-gather of both hand-tip frames (192 B per state)")
@@ -174,7 +174,9 @@ def ik_inputs(layout, model_fk, first: int, count: int, dof: int, tip: int):
 # ---------------------------------------------------------------------------------------------
 
 class ReferenceRunner:
-    """The reference's own functions (oracle/_ref: unmodified Rcs sources) over a sample."""
+    """The reference's own functions (oracle/_ref: unmodified Rcs sources) over a sample: per
+    state ONE RcsGraph_setState followed by the reference functions of the workload; every thread
+    clones its graph / controller before the clock starts (oracle/ref_build/ref_api.cpp)."""
 
     def __init__(self, wl: Workload, threads: int):
         from oracle import ref
@@ -214,21 +216,16 @@ class ReferenceRunner:
             g.fk_jacobians(self.q, self.eff)
             return g.last_seconds
         if wl.name == "fkm":
-            g.fk_jacobians(self.q, self.eff)
-            t = g.last_seconds
-            g.mass_matrix(self.q)
-            return t + g.last_seconds
+            # RcsGraph_setState -> bodyPointJacobian / rotationJacobian -> RcsGraph_computeMassMatrix
+            g.fk_jacobians(self.q, self.eff, want=("A_BI", "JT", "JR", "M"))
+            return g.last_seconds
         if wl.name == "kinetic":
             g.kinetic_terms(self.q, self.qd)
             return g.last_seconds
         if wl.name == "wholebody":
             # RcsGraph_setState (frames of every body), ControllerBase::computeJ, RcsGraph_computeMassMatrix
-            g.fk(self.q)
-            t = g.last_seconds
-            self.ik.task_kinematics(self.q, want_x=False)
-            t += self.ik.last_seconds
-            g.mass_matrix(self.q)
-            return t + g.last_seconds
+            self.ik.wholebody(self.q)
+            return self.ik.last_seconds
         self.ik.rmr(self.q, self.x_des, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS)
         return self.ik.last_seconds
 
@@ -241,19 +238,12 @@ class ReferenceRunner:
         return 1 << (want.bit_length() - 1)
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import ref
-
-    wl = Workload(args.workload, args.gpus)
-    if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librcsref.so missing"}))
-        return
+def reference_record(name: str, args, step_seconds: float):
+    """`steps` timed passes of the reference over a bounded sample of workload `name`."""
+    wl = Workload(name, args.gpus)
     threads = host_threads()
     runner = ReferenceRunner(wl, threads)
-    sample = runner.calibrate(1.0, wl.per_gpu * wl.world)
+    sample = runner.calibrate(step_seconds, wl.per_gpu * wl.world)
     runner.prepare(sample)
     for _ in range(args.warmup):
         runner.run()
@@ -262,7 +252,7 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     total = sum(secs)
     value = sample * args.steps / total
-    line = {
+    return {
         "impl": "reference",
         "metric": METRIC[wl.name], "value": value, "unit": UNIT[wl.name], "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -270,10 +260,25 @@ def run_reference(args):
         "data": "synthetic", "config": wl.config(),
         "cpu_baseline": {"value": value, "unit": UNIT[wl.name], "cores": threads, "kind": "reference",
                          "sample": f"{sample} units per step x {args.steps} steps, one RcsGraph_clone per "
-                                   f"thread, {threads} threads (wall incl. thread start {wall:.2f} s)"},
+                                   f"thread made before the clock starts, one RcsGraph_setState per state, "
+                                   f"{threads} threads (wall incl. thread start and cloning {wall:.2f} s)"},
         "e2e": {"value": value, "unit": UNIT[wl.name], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librcsref.so missing"}))
+        return
+    line = reference_record(args.workload, args, 1.0)
+    if args.workload == "fkm" and not args.no_secondary:
+        line["secondary"] = {name: reference_record(name, args, 0.4) for name in SECONDARY}
     print(json.dumps(line))
 
 
@@ -282,16 +287,61 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled on a thread while the GPU works: through
+    NVML every 2 ms where pynvml is importable (several samples even inside a 10 ms timed region),
+    else by polling nvidia-smi (one sample per ~60 ms)."""
+
     def __init__(self, device_index: int):
-        self.samples = []
+        self.samples = []          # (perf_counter, sm MHz, max MHz, [reasons])
         self.stop = threading.Event()
         self.idx = device_index
+        self.source = "nvidia-smi"
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.marks = {}
+
+    def mark(self, name: str):
+        self.marks[name] = time.perf_counter()
+
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.idx
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip() != ""]
+                if idx < len(ids) and ids[idx].strip().isdigit():
+                    idx = int(ids[idx])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {
+                "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self.stop.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((time.perf_counter(), sm, smax, [n for n, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self.stop.wait(0.002)
+        return True
 
     def _run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
                 out = subprocess.run(
@@ -299,7 +349,9 @@ class ClockSampler:
                      "--format=csv,noheader,nounits"],
                     capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                    s = [x.strip() for x in out.split(",")]
+                    self.samples.append((time.perf_counter(), float(s[0]), float(s[1]),
+                                         [n for n, v in zip(names, s[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 pass
             self.stop.wait(0.05)
@@ -313,19 +365,24 @@ class ClockSampler:
         self.thread.join(timeout=10)
 
     def summary(self):
-        sm, smax, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                smax = max(smax, float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        """Median SM clock and the union of the throttle reasons over ALL samples (settle loop,
+        warm-up, timed steps and the hold loop: identical launches back to back), plus the same
+        for the samples that fell between the two barriers of the timed region."""
+        def agg(rows):
+            sm = [r[1] for r in rows]
+            reasons = sorted({n for r in rows for n in r[3]})
+            return (float(np.median(sm)) if sm else None), reasons
+
+        sm, reasons = agg(self.samples)
+        smax = max([r[2] for r in self.samples], default=0.0)
+        t0, t1 = self.marks.get("timed_begin"), self.marks.get("timed_end")
+        timed = [r for r in self.samples if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        sm_t, reasons_t = agg(timed)
+        return {"sm_mhz": sm, "sm_max_mhz": smax or None, "reasons": reasons, "samples": len(self.samples),
+                "source": self.source,
+                "covers": "settle loop + warm-up + timed steps + hold loop (the same launches back to back)",
+                "timed_region": {"samples": len(timed), "sm_mhz": sm_t, "reasons": reasons_t,
+                                 "seconds": (t1 - t0) if timed or (t0 and t1) else None}}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -350,34 +407,65 @@ def profile_record(name: str):
         return {}
 
 
+_FP64_PEAK = None
+
+
 def fp64_peak_tflops():
     """DFMA microbenchmark (tools/fp64_peak.cu) run live; falls back to the committed figure."""
-    exe = os.path.join(ROOT, "build", "fp64_peak")
-    try:
-        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
-        return float(json.loads(out)["fp64_tflops"]), "build/fp64_peak DFMA microbenchmark, this run"
-    except Exception:
-        return 34.2, "tools/fp64_peak.cu measured on B200 in round 1 (34.2 TFLOP/s)"
+    global _FP64_PEAK
+    if _FP64_PEAK is None:
+        exe = os.path.join(ROOT, "build", "fp64_peak")
+        try:
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            _FP64_PEAK = (float(json.loads(out)["fp64_tflops"]), "build/fp64_peak DFMA microbenchmark, this run")
+        except Exception:
+            _FP64_PEAK = (34.2, "tools/fp64_peak.cu measured on B200 in round 1 (34.2 TFLOP/s)")
+    return _FP64_PEAK
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of our arm: rank, device, process group."""
 
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: rcs_b200 has no CPU fallback")
+        # host side of the end-to-end path: run this rank's threads and place its pinned buffers
+        # next to its GPU where the container allows it (rcsb_bind_host_to_device)
+        import rcs_b200
+
+        self.numa = rcs_b200.bind_host_to_device(self.local)
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure_ours(name: str, args, ctx: Ctx, cpu_seconds: float = 4.0):
+    """One workload on this rank's GPU; returns the record on rank 0, None elsewhere."""
     import rcs_b200
     from rcs_b200 import TASK_ABC, TASK_XYZ, shard, workload
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: rcs_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    wl = Workload(args.workload, world)
+    torch = ctx.torch
+    rank, world, local, dev = ctx.rank, ctx.world, ctx.local, ctx.dev
+    wl = Workload(name, world)
     g = rcs_b200.Graph(wl.graph_file)
     m = rcs_b200.Model(g, local)
     lay = g.layout()
@@ -386,11 +474,12 @@ def run_ours(args):
     f64 = torch.float64
 
     def pinned(shape):
-        return torch.empty(shape, dtype=f64).pin_memory()
+        return rcs_b200.pinned_empty(shape)
 
     def dev_empty(shape):
         return torch.empty(shape, dtype=f64, device=dev)
 
+    e2e_units = n
     # ---- workload-specific buffers and the two call forms (device pointers / host pointers) ----
     if wl.name in ("fk", "fkm"):
         eff = [g.body_index(wl.eff)]
@@ -437,14 +526,10 @@ def run_ours(args):
         gathered_frames = dev_empty((world * n, 2, 12)) if world > 1 else None
 
         def device_call():
-            m.fk(q, out={"A_BI": out["A_BI"]})
-            m.task_jacobians(q, spec, out=out["Jt"])
-            m.kinetic_terms(q, want=("M", "Jcog"), out={"M": out["M"], "Jcog": out["Jcog"]})
+            m.wholebody(q, spec, out=out)
 
         def host_call():
-            m.fk(hq, out={"A_BI": hout["A_BI"]})
-            m.task_jacobians(hq, spec, out=hout["Jt"])
-            m.kinetic_terms(hq, want=("M", "Jcog"), out={"M": hout["M"], "Jcog": hout["Jcog"]})
+            m.wholebody(hq, spec, out=hout)
 
         def stat_source():
             return out["A_BI"][:: 1024, rh, 2]
@@ -527,30 +612,27 @@ def run_ours(args):
         while pending:
             pending.pop().wait()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # bring the SM clocks up before the warm-up steps: a step is 0.5 ms, so a short --warmup alone
-    # would be timed on a GPU that is still ramping from idle (measured: 1.87 instead of 2.05 G
-    # states/s with --warmup 3 --steps 5)
-    t_settle = time.perf_counter()
-    while time.perf_counter() - t_settle < args.settle:
-        device_call()
-        torch.cuda.synchronize()
-    for i in range(args.warmup):
-        device_call()
-        exchange(args.steps + i)
-    drain()
-    barrier()
-
-    launches0 = rcs_b200.kernel_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+    barrier = ctx.barrier
     with ClockSampler(local) as clocks:
+        # bring the SM clocks up before the warm-up steps: a step is 0.5 ms, so a short --warmup
+        # alone would be timed on a GPU that is still ramping from idle (measured: 1.87 instead of
+        # 2.05 G states/s with --warmup 3 --steps 5)
+        t_settle = time.perf_counter()
+        while time.perf_counter() - t_settle < args.settle:
+            device_call()
+            torch.cuda.synchronize()
+        for i in range(args.warmup):
+            device_call()
+            exchange(args.steps + i)
+        drain()
         barrier()
+
+        launches0 = rcs_b200.kernel_launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        barrier()
+        clocks.mark("timed_begin")
         ev[0].record()
         for i in range(args.steps):
             if wl.name == "ik":
@@ -567,6 +649,7 @@ def run_ours(args):
         end = torch.cuda.Event(enable_timing=True)
         end.record()
         barrier()
+        clocks.mark("timed_end")
         launches = rcs_b200.kernel_launch_count() - launches0
         # keep the GPU busy a little longer so that short runs still get clock samples under load
         t_hold = time.perf_counter()
@@ -575,11 +658,7 @@ def run_ours(args):
             torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(end)
     kern_ms = [a.elapsed_time(b) for a, b in kev]
-
-    t = torch.tensor([total_ms], dtype=f64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = ctx.max_over_ranks(total_ms)
     value = n * world * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the host-pointer ABI (pinned buffers) ---------------------------
@@ -590,18 +669,18 @@ def run_ours(args):
     for _ in range(e2e_steps):
         host_call()
     t1 = time.perf_counter()
-    te = torch.tensor([t1 - t0], dtype=f64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_n = e2e_units if wl.name == "wholebody" else n
-    e2e_value = e2e_n * world * e2e_steps / float(te.item())
+    e2e_seconds = ctx.max_over_ranks(t1 - t0)
+    e2e_value = e2e_units * world * e2e_steps / e2e_seconds
     device_call()
     torch.cuda.synchronize()
     results_match = same()               # pinned results equal the device results of the same states
 
+    line = None
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         counters = profile_record(wl.name)
+        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` "
+                        "capture (profiles/kernel_counters.json), not measured in this run")
         if wl.name == "ik":
             peak, peak_src = fp64_peak_tflops()
             flops = counters.get("fp64_flops_per_unit")
@@ -618,8 +697,8 @@ def run_ours(args):
             achieved = wl.bytes_per_unit * n / (k_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": counters.get("dram_bytes_per_launch")}
-        roof.update({"kernel": wl.kernel, "kernel_ms": k_ms, "peak_source": peak_src,
-                     "algorithmic_per_launch": wl.bytes_per_unit * n})
+        roof.update({"kernel": counters.get("kernel_names", wl.kernel), "kernel_ms": k_ms, "peak_source": peak_src,
+                     "algorithmic_per_launch": wl.bytes_per_unit * n, "traffic_source": traffic_note})
         line = {
             "metric": METRIC[wl.name], "value": value, "unit": UNIT[wl.name], "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -627,8 +706,10 @@ def run_ours(args):
             "data": "synthetic", "config": wl.config(),
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT[wl.name], "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "units_per_step": e2e_n * world,
-                    "results_match_device_path": results_match},
+                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "units_per_step": e2e_units * world,
+                    "results_match_device_path": results_match,
+                    "host_gbs_per_gpu": (h2d + d2h) * e2e_steps / e2e_seconds / 1e9,
+                    "host_binding": ctx.numa},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
@@ -638,7 +719,7 @@ def run_ours(args):
             if ref.available():
                 threads = host_threads()
                 runner = ReferenceRunner(wl, threads)
-                sample = runner.calibrate(4.0, n)
+                sample = runner.calibrate(cpu_seconds, n)
                 runner.prepare(sample)
                 secs = [runner.run() for _ in range(3)]
                 one = ReferenceRunner(wl, 1)
@@ -649,15 +730,30 @@ def run_ours(args):
                     "value": sample / min(secs), "unit": UNIT[wl.name], "cores": threads,
                     "kind": "reference", "single_core_value": s1 / t_one,
                     "sample": f"reference library (unmodified Rcs sources), {sample} units x 3 passes on "
-                              f"{threads} threads (best pass), one RcsGraph_clone per thread; "
-                              f"single core: {s1} units x 1"}
+                              f"{threads} threads (best pass), one RcsGraph_clone per thread made before the "
+                              f"clock starts, one RcsGraph_setState per state; single core: {s1} units x 1"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT[wl.name], "cores": 0,
                                         "kind": "reference", "sample": "oracle/_ref/librcsref.so missing"}
-        print(json.dumps(line))
+    # free this workload's buffers before the next one is set up
+    del out, hout
+    torch.cuda.empty_cache()
+    return line
 
-    if world > 1:
-        dist.destroy_process_group()
+
+def run_ours(args):
+    ctx = Ctx()
+    line = measure_ours(args.workload, args, ctx)
+    secondary = {}
+    if args.workload == "fkm" and not args.no_secondary:
+        for name in SECONDARY:
+            secondary[name] = measure_ours(name, args, ctx, cpu_seconds=2.0)
+    if ctx.rank == 0:
+        if secondary:
+            line["secondary"] = secondary
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -668,6 +764,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fkm", choices=["fkm", "fk", "kinetic", "ik", "wholebody"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="default workload only: skip the ik / kinetic / wholebody records")
     ap.add_argument("--settle", type=float, default=1.0,
                     help="seconds of untimed work before the warm-up steps (clock ramp from idle)")
     ap.add_argument("--hold", type=float, default=1.0,

@@ -18,6 +18,7 @@
  *   rcsb_kinetic_terms   RcsGraph_computeKineticTerms  src/RcsCore/Rcs_dynamics.c:439
  *   rcsb_cog, rcsb_kinetic_terms_cog   RcsGraph_COG / COGJacobian  Rcs_kinematics.c:904, :973
  *   rcsb_direct_dynamics Rcs_directDynamics            src/RcsCore/Rcs_dynamics.c:673
+ *   rcsb_wholebody       RcsGraph_setState + ControllerBase::computeJ + RcsGraph_computeMassMatrix
  *   rcsb_ik_rmr          ControllerBase::computeDX / computeJ / computeJointlimitGradient
  *                        (src/RcsCore/ControllerBase.cpp:776, :896, :1332) +
  *                        IkSolverRMR::solveRightInverse (src/RcsCore/IkSolverRMR.cpp:403)
@@ -178,6 +179,18 @@ int rcsb_kinetic_terms_cog(const RcsbModel* model, long N, int qdim, const doubl
                            const double* qd, double* M, double* h, double* Fg, double* E,
                            double* cog, double* Jcog, unsigned flags, void* stream);
 
+/*
+ * Whole-body evaluation of BASELINE.json configs[4] in one call: frames of the selected bodies
+ * (A_BI as in rcsb_fk), the task Jacobians `jac` (J as in rcsb_task_jacobians), the mass matrix
+ * M [N x nJ x nJ] and the COG Jacobian Jcog [N x 3 x nJ] of the same states. Every output may
+ * be NULL. Reference per state: RcsGraph_setState (Rcs_graph.c:231), ControllerBase::computeJ
+ * (ControllerBase.cpp:776) over XYZ / XYZABC / COG tasks, RcsGraph_computeMassMatrix
+ * (Rcs_dynamics.c:610).
+ */
+int rcsb_wholebody(const RcsbModel* model, long N, int qdim, const double* q, int nSel,
+                   const int* bodySel, double* A_BI, int nJac, const RcsbRelJac* jac, double* J,
+                   double* M, double* Jcog, unsigned flags, void* stream);
+
 /* ---- inverse kinematics ----------------------------------------------------------------- */
 
 /*
@@ -210,6 +223,15 @@ int rcsb_device_count(void);
 /* pinned host memory for RCSB_HOST_PTRS calls */
 void* rcsb_host_alloc(size_t bytes);
 void rcsb_host_free(void* p);
+/*
+ * Host side of the RCSB_HOST_PTRS path on multi-socket boxes: restricts the calling thread (and
+ * the threads it creates later) to the allowed CPUs of the NUMA node `device` is attached to, and
+ * makes that node the preferred one for the memory it allocates from now on (pinned buffers
+ * included), as far as the process's cpuset allows. Call it once per rank before allocating the
+ * host buffers. `info` (may be NULL) receives a one-line description of what was done.
+ * Returns 0, or RCSB_EINVAL for an unknown device; an unavailable topology is not an error.
+ */
+int rcsb_bind_host_to_device(int device, char* info, size_t infoBytes);
 /* number of kernels launched by this library in this process (all threads) */
 unsigned long long rcsb_kernel_launch_count(void);
 

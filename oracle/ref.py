@@ -51,6 +51,10 @@ def lib() -> ctypes.CDLL:
         L.ref_fk.argtypes = [vp, cl, ci] + [vp] * 7
         L.ref_fk_jacobians.restype = cd
         L.ref_fk_jacobians.argtypes = [vp, cl, ci, vp, ci, vp, vp, vp, vp, vp]
+        L.ref_fk_jacobians_mass.restype = cd
+        L.ref_fk_jacobians_mass.argtypes = [vp, cl, ci, vp, ci, vp, vp, vp, vp, vp, vp]
+        L.ref_ik_wholebody.restype = cd
+        L.ref_ik_wholebody.argtypes = [vp, cl, ci, vp, vp, vp, vp]
         L.ref_cog.restype = cd
         L.ref_cog.argtypes = [vp, cl, ci, vp, vp, vp]
         L.ref_task_jacobians.restype = cd
@@ -162,6 +166,13 @@ class RefGraph:
             out["JT"] = np.empty((N, ne, 3, self.nJ))
         if "JR" in want:
             out["JR"] = np.empty((N, ne, 3, self.nJ))
+        if "M" in want:
+            # + RcsGraph_computeMassMatrix on the same graph state: one RcsGraph_setState per state
+            out["M"] = np.empty((N, self.nJ, self.nJ))
+            self.last_seconds = lib().ref_fk_jacobians_mass(
+                self._h, N, qdim, _p(q), ne, eff, _p(pts), _p(out.get("A_BI")), _p(out.get("JT")),
+                _p(out.get("JR")), _p(out["M"]))
+            return out
         self.last_seconds = lib().ref_fk_jacobians(
             self._h, N, qdim, _p(q), ne, eff, _p(pts), _p(out.get("A_BI")), _p(out.get("JT")),
             _p(out.get("JR")))
@@ -263,6 +274,23 @@ class RefIk:
         self.last_seconds = lib().ref_ik_task_kinematics(self._h, N, qdim, _p(q), _p(x) if want_x else None,
                                                          _p(J))
         return x, J
+
+    def wholebody(self, q, want=("A_BI", "J", "M")):
+        """RcsGraph_setState + ControllerBase::computeJ + RcsGraph_computeMassMatrix, one pass per
+        state on the controller's graph."""
+        q = _c(q)
+        N, qdim = q.shape
+        g = self.graph
+        out = {}
+        if "A_BI" in want:
+            out["A_BI"] = np.empty((N, g.n_bodies, 12))
+        if "J" in want:
+            out["J"] = np.empty((N, self.nx, g.nJ))
+        if "M" in want:
+            out["M"] = np.empty((N, g.nJ, g.nJ))
+        self.last_seconds = lib().ref_ik_wholebody(self._h, N, qdim, _p(q), _p(out.get("A_BI")),
+                                                   _p(out.get("J")), _p(out.get("M")))
+        return out
 
     def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
         """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp with

@@ -35,6 +35,8 @@
 #include <IkSolverRMR.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,6 +50,53 @@ namespace
 
 int g_threads = 1;
 
+/*
+ * Timing of a batch call. Every slice runs on its own thread with its own RcsGraph_clone (or
+ * controller copy). A slice calls sliceReady() once its clone and work matrices exist: the
+ * call returns when every slice has got there, and the clock of the batch starts at that
+ * moment (the reference's apps clone once per thread, outside their loops). sliceDone() stops
+ * the slice's clock before it frees its clone. The batch time is first start -> last stop.
+ * Slices that never call sliceReady() are timed over their whole lifetime, clone included.
+ */
+struct SliceClock
+{
+  std::mutex mtx;
+  std::condition_variable cv;
+  int expected = 0;
+  int arrived = 0;
+  bool started = false;
+  std::chrono::steady_clock::time_point t0, t1;
+};
+
+SliceClock* g_clock = NULL;   /* one batch call at a time (the Python wrapper is serial) */
+
+void sliceReady()
+{
+  SliceClock* c = g_clock;
+  std::unique_lock<std::mutex> lk(c->mtx);
+  if (++c->arrived == c->expected)
+  {
+    c->t0 = std::chrono::steady_clock::now();
+    c->started = true;
+    c->cv.notify_all();
+  }
+  else
+  {
+    c->cv.wait(lk, [c]() { return c->started; });
+  }
+}
+
+void sliceDone()
+{
+  SliceClock* c = g_clock;
+  auto now = std::chrono::steady_clock::now();
+  std::lock_guard<std::mutex> lk(c->mtx);
+  if (now > c->t1)
+  {
+    c->t1 = now;
+  }
+}
+
 template <class F>
 double parallelSlices(long N, F body)
 {
@@ -56,7 +105,11 @@ double parallelSlices(long N, F body)
   {
     nt = N > 0 ? (int) N : 1;
   }
+  SliceClock clock;
+  clock.expected = nt;
+  g_clock = &clock;
   auto t0 = std::chrono::steady_clock::now();
+  clock.t1 = t0;
   if (nt == 1)
   {
     body(0, 0L, N);
@@ -75,6 +128,11 @@ double parallelSlices(long N, F body)
     }
   }
   auto t1 = std::chrono::steady_clock::now();
+  g_clock = NULL;
+  if (clock.started)
+  {
+    return std::chrono::duration<double>(clock.t1 - clock.t0).count();
+  }
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
@@ -322,6 +380,7 @@ double ref_fk(void* g, long N, int qdim, const double* q, const double* qd, doub
     const unsigned int dof = graph->dof;
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* qdv = MatNd_create(dof, 1);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
@@ -358,6 +417,7 @@ double ref_fk(void* g, long N, int qdim, const double* q, const double* qd, doub
         memcpy(qOut + i * dof, graph->q->ele, dof * sizeof(double));
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(qdv);
     RcsGraph_destroy(graph);
@@ -366,8 +426,25 @@ double ref_fk(void* g, long N, int qdim, const double* q, const double* qd, doub
 
 /* FK + per-effector translation / rotation Jacobians. effPt: nEff x 3 body-fixed points
  * or NULL (body origin). JT, JR: N x nEff x 3 x nJ (either may be NULL). A_BI as ref_fk. */
+static double fkJacobiansImpl(void* g, long N, int qdim, const double* q, int nEff, const int* effBody,
+                              const double* effPt, double* A_BI, double* JT, double* JR, double* M);
+
 double ref_fk_jacobians(void* g, long N, int qdim, const double* q, int nEff, const int* effBody,
                         const double* effPt, double* A_BI, double* JT, double* JR)
+{
+  return fkJacobiansImpl(g, N, qdim, q, nEff, effBody, effPt, A_BI, JT, JR, NULL);
+}
+
+/* The same pass plus RcsGraph_computeMassMatrix (Rcs_dynamics.c:610) on the same graph state:
+ * ONE RcsGraph_setState per state for "FK + Jacobians + M(q)". M: N x nJ x nJ. */
+double ref_fk_jacobians_mass(void* g, long N, int qdim, const double* q, int nEff, const int* effBody,
+                             const double* effPt, double* A_BI, double* JT, double* JR, double* M)
+{
+  return fkJacobiansImpl(g, N, qdim, q, nEff, effBody, effPt, A_BI, JT, JR, M);
+}
+
+static double fkJacobiansImpl(void* g, long N, int qdim, const double* q, int nEff, const int* effBody,
+                              const double* effPt, double* A_BI, double* JT, double* JR, double* M)
 {
   RcsGraph* master = (RcsGraph*) g;
   return parallelSlices(N, [=](int, long lo, long hi)
@@ -378,6 +455,8 @@ double ref_fk_jacobians(void* g, long N, int qdim, const double* q, int nEff, co
     const unsigned int dof = graph->dof, nJ = graph->nJ;
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* J = MatNd_create(3, nJ);
+    MatNd* Mm = MatNd_create(nJ, nJ);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
@@ -402,9 +481,16 @@ double ref_fk_jacobians(void* g, long N, int qdim, const double* q, int nEff, co
           memcpy(JR + ((size_t) i * nEff + e) * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
         }
       }
+      if (M)
+      {
+        RcsGraph_computeMassMatrix(graph, Mm);
+        memcpy(M + (size_t) i * nJ * nJ, Mm->ele, sizeof(double) * nJ * nJ);
+      }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(J);
+    MatNd_destroy(Mm);
     RcsGraph_destroy(graph);
   });
 }
@@ -419,6 +505,7 @@ double ref_cog(void* g, long N, int qdim, const double* q, double* cog, double* 
     const unsigned int dof = graph->dof, nJ = graph->nJ;
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* J = MatNd_create(3, nJ);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
@@ -432,6 +519,7 @@ double ref_cog(void* g, long N, int qdim, const double* q, double* cog, double* 
         memcpy(Jcog + (size_t) i * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(J);
     RcsGraph_destroy(graph);
@@ -454,6 +542,7 @@ double ref_task_jacobians(void* g, long N, int qdim, const double* q, int nJac, 
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* J = MatNd_create(3, nJ);
     auto body = [&](int idx) -> const RcsBody* { return idx < 0 ? NULL : bodies[idx]; };
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
@@ -471,6 +560,7 @@ double ref_task_jacobians(void* g, long N, int qdim, const double* q, int nJac, 
         memcpy(Jout + ((size_t) i * nJac + t) * 3 * nJ, J->ele, 3 * nJ * sizeof(double));
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(J);
     RcsGraph_destroy(graph);
@@ -491,6 +581,7 @@ double ref_kinetic_terms(void* g, long N, int qdim, const double* q, const doubl
     MatNd* Mm = MatNd_create(nJ, nJ);
     MatNd* hm = MatNd_create(nJ, 1);
     MatNd* gm = MatNd_create(nJ, 1);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
@@ -512,6 +603,7 @@ double ref_kinetic_terms(void* g, long N, int qdim, const double* q, const doubl
         E[i] = e;
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(qdv);
     MatNd_destroy(Mm);
@@ -536,6 +628,7 @@ double ref_direct_dynamics(void* g, long N, int qdim, const double* q, const dou
     MatNd* fe = MatNd_create(nJ, 1);
     MatNd* fj = MatNd_create(nJ, 1);
     MatNd* acc = MatNd_create(nJ, 1);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, qdv, qdim, q + i * qdim, qd ? qd + i * qdim : NULL);
@@ -554,6 +647,7 @@ double ref_direct_dynamics(void* g, long N, int qdim, const double* q, const dou
         E[i] = e;
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(qdv);
     MatNd_destroy(fe);
@@ -573,12 +667,14 @@ double ref_mass_matrix(void* g, long N, int qdim, const double* q, double* M)
     const unsigned int dof = graph->dof, nJ = graph->nJ;
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* Mm = MatNd_create(nJ, nJ);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
       RcsGraph_computeMassMatrix(graph, Mm);
       memcpy(M + (size_t) i * nJ * nJ, Mm->ele, sizeof(double) * nJ * nJ);
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(Mm);
     RcsGraph_destroy(graph);
@@ -605,6 +701,7 @@ double ref_joint_limit_gradient(void* g, long N, int qdim, const double* q, doub
     const unsigned int dof = graph->dof, nJ = graph->nJ;
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* d = MatNd_create(1, nJ);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
@@ -615,6 +712,7 @@ double ref_joint_limit_gradient(void* g, long N, int qdim, const double* q, doub
         cost[i] = c;
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(d);
     RcsGraph_destroy(graph);
@@ -704,6 +802,7 @@ double ref_ik_task_kinematics(void* ik, long N, int qdim, const double* q, doubl
     MatNd* qv = MatNd_create(dof, 1);
     MatNd* xm = MatNd_create(nx, 1);
     MatNd* Jm = MatNd_create(nx, nJ);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
@@ -718,9 +817,55 @@ double ref_ik_task_kinematics(void* ik, long N, int qdim, const double* q, doubl
         memcpy(J + (size_t) i * nx * nJ, Jm->ele, sizeof(double) * nx * nJ);
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(xm);
     MatNd_destroy(Jm);
+  });
+}
+
+/* Whole-body evaluation of one state in ONE pass on the controller's graph: RcsGraph_setState
+ * (frames of every body, A_BI: N x nb x 12), ControllerBase::computeJ (stacked task Jacobian,
+ * J: N x nx x nJ) and RcsGraph_computeMassMatrix (M: N x nJ x nJ). Any output may be NULL. */
+double ref_ik_wholebody(void* ik, long N, int qdim, const double* q, double* A_BI, double* J, double* M)
+{
+  IkHandle* h = (IkHandle*) ik;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*h->controller);
+    RcsGraph* graph = c.getGraph();
+    std::vector<RcsBody*> bodies = dfsBodies(graph);
+    const size_t nb = bodies.size();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* Jm = MatNd_create(nx, nJ);
+    MatNd* Mm = MatNd_create(nJ, nJ);
+    sliceReady();
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, qdim, q + i * qdim, NULL);
+      if (A_BI)
+      {
+        for (size_t b = 0; b < nb; ++b)
+        {
+          memcpy(A_BI + (i * nb + b) * 12, bodies[b]->A_BI, 12 * sizeof(double));
+        }
+      }
+      if (J)
+      {
+        c.computeJ(Jm);
+        memcpy(J + (size_t) i * nx * nJ, Jm->ele, sizeof(double) * nx * nJ);
+      }
+      if (M)
+      {
+        RcsGraph_computeMassMatrix(graph, Mm);
+        memcpy(M + (size_t) i * nJ * nJ, Mm->ele, sizeof(double) * nJ * nJ);
+      }
+    }
+    sliceDone();
+    MatNd_destroy(qv);
+    MatNd_destroy(Jm);
+    MatNd_destroy(Mm);
   });
 }
 
@@ -767,6 +912,7 @@ static double ikRmrImpl(void* ik, long N, double* q, const double* xDes, double 
     MatNd* dx = MatNd_create(nx, 1);
     MatNd* dH = MatNd_create(1, nJ);
     MatNd_setElementsTo(a, 1.0);
+    sliceReady();
     for (long i = lo; i < hi; ++i)
     {
       setQ(graph, qv, NULL, dof, q + i * dof, NULL);
@@ -801,6 +947,7 @@ static double ikRmrImpl(void* ik, long N, double* q, const double* xDes, double 
         det[i] = solver.getDeterminant();
       }
     }
+    sliceDone();
     MatNd_destroy(qv);
     MatNd_destroy(dq);
     MatNd_destroy(a);

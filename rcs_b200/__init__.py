@@ -12,10 +12,12 @@ from .api import (  # noqa: F401
     TASK_ABC,
     TASK_XYZ,
     TASK_XYZABC,
+    bind_host_to_device,
     build_library,
     kernel_launch_count,
     lib,
     library_path,
+    pinned_empty,
     summary_stats,
 )
 
@@ -26,9 +28,11 @@ __all__ = [
     "TASK_ABC",
     "TASK_XYZ",
     "TASK_XYZABC",
+    "bind_host_to_device",
     "build_library",
     "kernel_launch_count",
     "lib",
     "library_path",
+    "pinned_empty",
     "summary_stats",
 ]

@@ -124,6 +124,9 @@ def lib() -> ctypes.CDLL:
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
+    sig("rcsb_wholebody", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p, c_int, c_void,
+        c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_bind_host_to_device", c_int, c_int, ctypes.c_char_p, ctypes.c_size_t)
     sig("RcsGraph_setState", ctypes.c_bool, c_void, c_void, c_void)
     sig("MatNd_create", c_void, ctypes.c_uint, ctypes.c_uint)
     sig("MatNd_destroy", None, c_void)
@@ -135,6 +138,21 @@ def lib() -> ctypes.CDLL:
 
 def kernel_launch_count() -> int:
     return int(lib().rcsb_kernel_launch_count())
+
+
+def bind_host_to_device(device: int) -> str:
+    """rcsb_bind_host_to_device: run this process's host threads and place its pinned buffers on
+    the NUMA node of GPU `device` (as far as the cpuset allows). Returns what was done."""
+    buf = ctypes.create_string_buffer(512)
+    _err(lib().rcsb_bind_host_to_device(int(device), buf, len(buf)), "rcsb_bind_host_to_device")
+    return buf.value.decode()
+
+
+def pinned_empty(shape):
+    """Page-locked float64 host tensor for RCSB_HOST_PTRS calls (torch owns the memory)."""
+    import torch
+
+    return torch.empty(shape, dtype=torch.float64, pin_memory=True)
 
 
 def summary_stats(x, out=None):
@@ -396,6 +414,33 @@ class Model:
         rc = lib().rcsb_task_jacobians(self._h, N, qdim, a.ptr(q, "q"), len(spec), arr,
                                        a.ptr(out, "J"), a.flags(), a.stream())
         _err(rc, "rcsb_task_jacobians")
+        return out
+
+    def wholebody(self, q, spec, bodies: Optional[Sequence[int]] = None,
+                  want=("A_BI", "Jt", "M", "Jcog"), out=None):
+        """rcsb_wholebody: frames, task Jacobians (spec as in task_jacobians), M and the COG
+        Jacobian of the same states from one call."""
+        N, qdim = self._batch(q)
+        nsel = self.n_bodies if bodies is None else len(bodies)
+        shapes = {"A_BI": (N, nsel, 12), "Jt": (N, len(spec), 3, self.nJ), "M": (N, self.nJ, self.nJ),
+                  "Jcog": (N, 3, self.nJ)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        for k, v in out.items():
+            if tuple(v.shape) != shapes[k]:
+                raise RcsbError(f"wholebody: {k} has shape {tuple(v.shape)}, expected {shapes[k]}")
+        arr = (_RcsbRelJac * max(len(spec), 1))(
+            *[_RcsbRelJac(1 if k == "POS" else 2, int(e), int(rb), int(rf)) for k, e, rb, rf in spec])
+        sel, ns = _int_array(bodies)
+        a = _Args(self)
+        has_j = out.get("Jt") is not None
+        rc = lib().rcsb_wholebody(self._h, N, qdim, a.ptr(q, "q"), ns, sel, a.ptr(out.get("A_BI"), "A_BI"),
+                                  len(spec) if has_j else 0, arr if has_j else None, a.ptr(out.get("Jt"), "Jt"),
+                                  a.ptr(out.get("M"), "M"), a.ptr(out.get("Jcog"), "Jcog"), a.flags(),
+                                  a.stream())
+        _err(rc, "rcsb_wholebody")
         return out
 
     # -- dynamics ------------------------------------------------------------------------

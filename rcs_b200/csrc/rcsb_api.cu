@@ -9,6 +9,8 @@
  */
 #include "rcsb_priv.h"
 
+#include <cctype>
+
 extern "C" int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut);
 
 namespace rcsbhost
@@ -685,6 +687,23 @@ extern "C" int rcsb_device_count(void)
     return 0;
   }
   return n;
+}
+
+/* PCI address of a device as sysfs spells it (rcsb_hostbind.c) */
+extern "C" int rcsb_device_pci_bus_id(int device, char* busId, int len)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n ||
+      cudaDeviceGetPCIBusId(busId, len, device) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char* c = busId; *c; ++c)
+  {
+    *c = (char) tolower(*c);
+  }
+  return 0;
 }
 
 extern "C" void* rcsb_host_alloc(size_t bytes)
