@@ -237,6 +237,11 @@ unsigned long long rcsb_kernel_launch_count(void);
 
 /* ---- single-state reference API (N = 1 through the kernels above) ---------------------- */
 
+/* The wrappers below keep a device model per graph (rebuilt when the graph's parameters are
+ * edited). RcsGraph_destroy() of this library releases it; for a graph owned by another library
+ * (libRcsCore: same struct layout) call this before destroying the graph. */
+void rcsb_graph_release_device_cache(RcsGraph* self);
+
 /* src/RcsCore/Rcs_graph.c:231. q / q_dot: dof x 1, nJ x 1 or NULL (use graph->q). Fills
  * A_BI / A_JI / x_dot / omega of every body and joint. Returns true if a slave joint's
  * value had to be changed by more than 1e-8. Wrong dimensions are fatal (see

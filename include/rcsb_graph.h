@@ -8,9 +8,14 @@
  *   HTr       src/RcsCore/Rcs_HTr.h:62-66      {org[3], rot[3][3]}, rows of rot = frame axes
  *   MatNd     src/RcsCore/Rcs_MatNd.h:92-99    row-major, caller-allocated, callee reshapes
  *   RcsJoint  src/RcsCore/Rcs_typedef.h:66-94
- *   RcsShape  src/RcsCore/Rcs_typedef.h:133-149 (only what the default inertia needs)
+ *   RcsShape  src/RcsCore/Rcs_typedef.h:133-149
  *   RcsBody   src/RcsCore/Rcs_typedef.h:187-214
  *   RcsGraph  src/RcsCore/Rcs_typedef.h:247-259
+ * The structs are binary compatible with the reference's (same fields, same order, same types;
+ * tests/test_abi_cpu.py compares sizes and offsets with the reference's own headers, and
+ * tests/test_abi_gpu.py hands a graph created by libRcsCore's RcsGraph_create to
+ * rcsb_model_create): a graph built by either library can be read by the other. A graph is
+ * destroyed by the library that created it.
  *
  * Only the loader and bookkeeping run on the host. Everything that evaluates a state
  * (forward kinematics, Jacobians, kinetic terms, the IK step) runs in the CUDA kernels
@@ -135,7 +140,13 @@ struct _RcsShape
   HTr A_CB;
   double extents[3];
   double scale;
+  bool resizeable;
   char computeType;
+  char* meshFile;     /* the four strings are carried (clone, destroy), never interpreted here */
+  char* textureFile;
+  char* color;
+  char* material;
+  void* userData;
 };
 
 struct _RcsBody
@@ -145,6 +156,7 @@ struct _RcsBody
   int physicsSim;
   double x_dot[3];
   double omega[3];
+  double confidence;
   char* name;
   char* xmlName;
   char* suffix;
@@ -158,17 +170,24 @@ struct _RcsBody
   RcsBody* prev;
   RcsShape** shape;   /* NULL-terminated */
   RcsJoint* jnt;      /* first joint of the body */
+  void* extraInfo;    /* generic bodies: the body they are linked to */
 };
+
+typedef struct _RcsSensor RcsSensor;   /* src/RcsCore/Rcs_typedef.h:233-243; not on the hot path */
 
 struct _RcsGraph
 {
   RcsBody* root;
+  RcsBody gBody[10];  /* generic bodies (placeholders the reference's tasks can be re-linked to);
+                         kept for layout compatibility, this loader leaves them unlinked */
   unsigned int dof;
   unsigned int nJ;
   MatNd* q;
   MatNd* q_dot;
   char* xmlFile;
-  void* userData;     /* device model cache of the single-state wrappers (rcsb.h) */
+  RcsSensor* sensor;  /* sensors are not loaded here (always NULL in graphs of this loader) */
+  void* userData;     /* the reference leaves it to extensions; the single-state wrappers of rcsb.h
+                         keep their device model cache in a side table keyed by the graph instead */
 };
 
 /* ---- MatNd (src/RcsCore/Rcs_MatNd.h): the few calls the path needs ------------------- */

@@ -839,6 +839,10 @@ static void destroyBody(RcsBody* b)
   {
     for (RcsShape** s = b->shape; *s; ++s)
     {
+      free((*s)->meshFile);
+      free((*s)->textureFile);
+      free((*s)->color);
+      free((*s)->material);
       free(*s);
     }
     free(b->shape);
@@ -922,6 +926,7 @@ RcsGraph* RcsGraph_clone(const RcsGraph* src)
     d->physicsSim = s->physicsSim;
     memcpy(d->x_dot, s->x_dot, sizeof(d->x_dot));
     memcpy(d->omega, s->omega, sizeof(d->omega));
+    d->confidence = s->confidence;
     d->name = cloneString(s->name);
     d->xmlName = cloneString(s->xmlName);
     d->suffix = cloneString(s->suffix);
@@ -942,6 +947,11 @@ RcsGraph* RcsGraph_clone(const RcsGraph* src)
     {
       d->shape[k] = (RcsShape*) malloc(sizeof(RcsShape));
       memcpy(d->shape[k], s->shape[k], sizeof(RcsShape));
+      d->shape[k]->meshFile = cloneString(s->shape[k]->meshFile);
+      d->shape[k]->textureFile = cloneString(s->shape[k]->textureFile);
+      d->shape[k]->color = cloneString(s->shape[k]->color);
+      d->shape[k]->material = cloneString(s->shape[k]->material);
+      d->shape[k]->userData = NULL;
     }
 
     /* DFS order guarantees that the parent has been cloned already */

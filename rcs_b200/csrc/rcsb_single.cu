@@ -19,12 +19,17 @@
  * remembers the joint state of the last forward-kinematics call instead, and the Jacobian /
  * dynamics wrappers evaluate at that state.
  *
- * The flattened device model is created on first use (current CUDA device) from the graph's
- * parameters at that moment and released by RcsGraph_destroy().
+ * The flattened device model is created on first use (current CUDA device). Every call
+ * re-flattens the graph on the host and rebuilds the device model if the mechanism (transforms,
+ * mass properties, limits, constraints, couplings) has been edited since, so the wrappers read
+ * the graph on every call like the reference does. The cache is released by RcsGraph_destroy()
+ * or rcsb_graph_release_device_cache() (graphs created by another library).
  */
 #include "rcsb_priv.h"
 
 using namespace rcsbhost;
+
+extern "C" int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut);
 
 namespace
 {
@@ -38,13 +43,55 @@ struct GraphCache
   std::vector<double> frames, jframes, xdot, omega, qOut, qdOut;
 };
 
+/* graph -> device cache. A side table, not RcsGraph::userData: graphs created by the reference
+ * library (same struct layout) may carry their own user data. */
+std::mutex g_cacheMutex;
+std::map<const RcsGraph*, GraphCache*> g_caches;
+
+/* true if two flat models describe the same mechanism: everything but the reference state
+ * (RCSB_A_JNT_QREF, the joint values the graph held when it was flattened; the single-state
+ * wrappers always pass full state vectors and never read it) */
+bool sameMechanism(const std::vector<char>& a, const char* b, size_t bytes)
+{
+  if (a.size() != bytes)
+  {
+    return false;
+  }
+  const RcsbFlatHeader* h = reinterpret_cast<const RcsbFlatHeader*>(a.data());
+  const size_t q0 = (size_t) h->off[RCSB_A_JNT_QREF], q1 = q0 + sizeof(double) * (size_t) h->dof;
+  return memcmp(a.data(), b, q0) == 0 && memcmp(a.data() + q1, b + q1, bytes - q1) == 0;
+}
+
 GraphCache* cacheOf(RcsGraph* self)
 {
-  GraphCache* c = static_cast<GraphCache*>(self->userData);
-  if (!c)
+  GraphCache* c = nullptr;
   {
-    c = new GraphCache;
-    self->userData = c;
+    std::lock_guard<std::mutex> lock(g_cacheMutex);
+    GraphCache*& slot = g_caches[self];
+    if (!slot)
+    {
+      slot = new GraphCache;
+    }
+    c = slot;
+  }
+  if (c->model)
+  {
+    /* the reference reads the graph on every call: a caller may have edited A_BP, masses, joint
+     * limits, constraints ... since the device model was made. Re-flatten (a few microseconds
+     * of host work) and rebuild the device model when the mechanism has changed. */
+    void* blob = nullptr;
+    size_t bytes = 0;
+    if (rcsb_flatten(self, &blob, &bytes) != 0)
+    {
+      return nullptr;
+    }
+    const bool same = sameMechanism(c->model->host, static_cast<const char*>(blob), bytes);
+    free(blob);
+    if (!same)
+    {
+      rcsb_model_destroy(c->model);
+      c->model = nullptr;
+    }
   }
   if (!c->model)
   {
@@ -59,8 +106,11 @@ GraphCache* cacheOf(RcsGraph* self)
       c->model = nullptr;
       return nullptr;
     }
-    c->q.assign(self->q->ele, self->q->ele + self->dof);
-    c->qd.assign(self->dof, 0.0);
+    if (c->q.size() != self->dof)
+    {
+      c->q.assign(self->q->ele, self->q->ele + self->dof);
+      c->qd.assign(self->dof, 0.0);
+    }
   }
   return c;
 }
@@ -166,12 +216,20 @@ bool runFk(RcsGraph* self, GraphCache* c, const double* q, const double* qd, boo
 
 extern "C" void rcsb_graph_release_device_cache(RcsGraph* self)
 {
-  GraphCache* c = self ? static_cast<GraphCache*>(self->userData) : nullptr;
+  GraphCache* c = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_cacheMutex);
+    auto it = g_caches.find(self);
+    if (it != g_caches.end())
+    {
+      c = it->second;
+      g_caches.erase(it);
+    }
+  }
   if (c)
   {
     rcsb_model_destroy(c->model);
     delete c;
-    self->userData = nullptr;
   }
 }
 

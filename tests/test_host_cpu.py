@@ -211,8 +211,9 @@ class _MatNd(ctypes.Structure):
 
 
 class _RcsGraph(ctypes.Structure):
-    _fields_ = [("root", ctypes.c_void_p), ("dof", ctypes.c_uint), ("nJ", ctypes.c_uint),
-                ("q", ctypes.POINTER(_MatNd)), ("q_dot", ctypes.POINTER(_MatNd))]
+    # root, gBody[10] (10 x 184 bytes, tests/golden/abi_layout.json), dof, nJ, q, q_dot
+    _fields_ = [("root", ctypes.c_void_p), ("gBody", ctypes.c_char * 1840), ("dof", ctypes.c_uint),
+                ("nJ", ctypes.c_uint), ("q", ctypes.POINTER(_MatNd)), ("q_dot", ctypes.POINTER(_MatNd))]
 
 
 def _host_lib():

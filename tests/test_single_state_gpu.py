@@ -29,7 +29,7 @@ class MatNd(ctypes.Structure):
 class RcsBody(ctypes.Structure):
     _fields_ = [("m", ctypes.c_double), ("rigid_body_joints", ctypes.c_bool),
                 ("physicsSim", ctypes.c_int), ("x_dot", ctypes.c_double * 3),
-                ("omega", ctypes.c_double * 3), ("name", ctypes.c_char_p),
+                ("omega", ctypes.c_double * 3), ("confidence", ctypes.c_double), ("name", ctypes.c_char_p),
                 ("xmlName", ctypes.c_char_p), ("suffix", ctypes.c_char_p),
                 ("A_BP", ctypes.POINTER(HTr)), ("A_BI", ctypes.POINTER(HTr))]
 
