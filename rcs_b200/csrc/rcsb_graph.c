@@ -1127,6 +1127,14 @@ bool RcsGraph_check(const RcsGraph* self, int* nErrorsOut, int* nWarningsOut)
       {
         nErrors++;
       }
+      /* the reference's check counts polynomial couplings (5 / 9 coefficients) as errors although
+       * its loader and RcsGraph_setState accept them (src/RcsCore/Rcs_graph.c:2047-2063) */
+      if (JNT->couplingFactors && JNT->couplingFactors->size != 1)
+      {
+        nErrors++;
+        RCSB_LOG(1, "Incorrect number of coupling factors in joint \"%s\": %u", JNT->name,
+                 JNT->couplingFactors->size);
+      }
       if ((JNT->coupledJointName != NULL) != (JNT->coupledTo != NULL))
       {
         nErrors++;

@@ -147,12 +147,12 @@ __device__ __forceinline__ void fromEuler(double A[9], const double ea[3])
 __device__ __forceinline__ void rotationTaskError(double dx[3], const double Ad[9],
                                                   const double Ac[9])
 {
-  double tr = 0.0;
-#pragma unroll
-  for (int i = 0; i < 9; ++i)
-  {
-    tr += Ad[i] * Ac[i];   /* trace(A_des A_curr^T) */
-  }
+  /* trace(A_des A_curr^T), summed as the reference does (diagonal entries of the product first,
+   * Rcs_Mat3d.c:1613-1632): the branches below switch on the result */
+  const double d0 = Ad[0] * Ac[0] + Ad[1] * Ac[1] + Ad[2] * Ac[2];
+  const double d1 = Ad[3] * Ac[3] + Ad[4] * Ac[4] + Ad[5] * Ac[5];
+  const double d2 = Ad[6] * Ac[6] + Ad[7] * Ac[7] + Ad[8] * Ac[8];
+  const double tr = d0 + d1 + d2;
   double cs = 0.5 * (tr - 1.0);
   cs = cs > 1.0 ? 1.0 : (cs < -1.0 ? -1.0 : cs);
   const double angle = acos(cs);
@@ -233,6 +233,44 @@ __device__ __forceinline__ void rotationTaskError(double dx[3], const double Ad[
   {
     dx[i] = (Ac[i] * ax[0] + Ac[3 + i] * ax[1] + Ac[6 + i] * ax[2]) * angle;
   }
+}
+
+/* Out of line on purpose: taken for effector orientations in Euler gimbal lock only, it must not
+ * cost the kernels around it registers. */
+static __device__ __noinline__ void eulerRoundTrip(double A[9])
+{
+  double ea[3];
+  toEuler(ea, A);
+  fromEuler(A, ea);
+}
+
+/* Orientation error from the effector's rotation matrix itself. The reference rebuilds the
+ * current rotation from its Euler angles (x = Mat3d_toEulerAngles(A_curr) in computeX, then
+ * Mat3d_fromEulerAngles(x) in computeDX, TaskEuler3D.cpp:110, :243). Away from gimbal lock that
+ * round trip is the identity up to rounding; in the gimbal branch of Mat3d_toEulerAngles
+ * (cy <= 16 FLT_EPSILON, Rcs_Mat3d.c:956) the third angle is set to 0 and the rebuilt matrix
+ * differs from A_curr by O(cy): there the round trip is made here too. */
+__device__ __forceinline__ void rotationTaskErrorOfFrame(double dx[3], const double Ad[9],
+                                                         const double Ac[9])
+{
+  const double cy2 = Ac[0] * Ac[0] + Ac[3] * Ac[3];
+  const double lim = 16.0 * (double) FLT_EPSILON;
+  if (cy2 <= lim * lim * 1.0000001)   /* warp-divergent and rare; exact test inside toEuler */
+  {
+    double Ar[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+    {
+      Ar[i] = Ac[i];
+    }
+    if (sqrt(cy2) <= lim)
+    {
+      eulerRoundTrip(Ar);
+    }
+    rotationTaskError(dx, Ad, Ar);
+    return;
+  }
+  rotationTaskError(dx, Ad, Ac);
 }
 
 /* The reference goes through the Euler angles of both frames (x = Mat3d_toEulerAngles(A_curr),
@@ -1029,7 +1067,7 @@ ikChainKernel(const IkArgs a)
       {
         Ad[i] = sAd[i * RCSB_IK_THREADS + tid];
       }
-      rotationTaskError(eRot, Ad, f.R);
+      rotationTaskErrorOfFrame(eRot, Ad, f.R);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -1597,7 +1635,7 @@ ikChainLoopKernel(const IkArgs a, int nc)
       {
         Ad[i] = sAd[i * T + tid];
       }
-      rotationTaskError(eRot, Ad, f.R);
+      rotationTaskErrorOfFrame(eRot, Ad, f.R);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -2009,7 +2047,7 @@ ikMultiKernel(const IkArgs a, int nU, int nEffs)
           Ad[i] = sAd[(t * 9 + i) * T + tid];
           Ac[i] = e[(3 + i) * T];
         }
-        rotationTaskError(er, Ad, Ac);
+        rotationTaskErrorOfFrame(er, Ad, Ac);
         dx[3 * t] = er[0];
         dx[3 * t + 1] = er[1];
         dx[3 * t + 2] = er[2];

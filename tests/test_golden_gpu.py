@@ -17,7 +17,7 @@ from conftest import GRAPH_DIR, ROOT, assert_close, assert_structural_zeros, gra
 from oracle import rcs_oracle
 
 pytestmark = pytest.mark.gpu
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled"]
 
 
 def _golden(name):

@@ -380,3 +380,100 @@ def test_pose6d_task_is_position_plus_euler_angles(refmod, cuda_device):
     two = q0.copy()
     m.ik_rmr([(TASK_XYZ, g.body_index("BallTip")), (TASK_ABC, g.body_index("BallTip"))], two, x_des, iters=1)
     assert np.array_equal(two, q)
+
+
+# BallTip orientations in Euler gimbal lock (A_BI[0][0] = A_BI[1][0] = 0: the body's z axis along
+# +-world x), found with scipy.optimize.least_squares on the reference's forward kinematics
+GIMBAL_Q = np.array([
+    [-7.1190738352776806e-01, 1.4755194061861028e+00, -1.6833390958112393e+00, 2.4223650408364081e+00,
+     -2.4298145887218032e+00, -2.7491382779975156e-03, 4.9202740586879057e-01],
+    [1.2320546385281472e+00, -6.0693448234085534e-01, 9.1935666370087543e-01, 1.4327587768815675e+00,
+     -1.4356246522855529e+00, -9.2097734367572637e-01, 1.0561844816455193e+00],
+    [-1.3562394255813479e+00, -3.5396771043214315e-01, -1.7720685886737224e+00, 1.1130013367792444e+00,
+     -3.1425298303927574e+00, -3.8392707132874870e-01, 3.1822920163696600e-01],
+    [-1.4476816245535711e+00, -6.3523096704291238e-01, -8.4736230089356779e-01, 1.5230382027416323e+00,
+     -1.6259983240365072e+00, 8.2148542412183390e-01, -2.3667168596103072e+00],
+    [1.5672988870559459e+00, 1.1196964082085539e+00, 8.6558087905293279e-01, 1.4325950808294861e+00,
+     -1.7354304737087207e+00, -7.1849924701470036e-01, -2.7366948575469702e-01],
+    [7.7396381831464398e-02, -1.2480815245291657e+00, 1.8722791169211497e+00, 7.6464927716839826e-01,
+     -3.6233622971051758e+00, 6.4610448347188398e-01, 1.2703103350823217e+00],
+    [-1.9863875114840446e-02, 3.5695898590589678e-02, 5.2791787899981424e-01, 1.4424742104794526e+00,
+     -1.4150239939121507e+00, 5.1451841168281864e-01, -2.1749648595872979e+00],
+    [1.9739603175822400e+00, -8.6986863073481879e-01, 5.3824773987390973e-01, 1.5941785305090341e+00,
+     -1.9766704042891521e+00, -8.0153808901275925e-01, -6.2589533226996341e-02],
+])
+
+
+@pytest.mark.parametrize("general", [False, True], ids=["chain-kernel", "general-kernel"])
+def test_euler_gimbal_lock_of_the_effector(general, refmod, cuda_device, monkeypatch):
+    """Mat3d_toEulerAngles' gimbal branch (cy <= 16 FLT_EPSILON, Rcs_Mat3d.c:956): the reference
+    rebuilds the effector rotation from Euler angles whose third entry was set to 0, so the task
+    error differs from that of the true rotation by O(cy). States exactly in gimbal lock, inside
+    the branch (cy ~ 1e-6) and just outside it (cy ~ 3e-6); targets near (Euler error) and far
+    (axis-angle error)."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
+    g, m, rik, tasks = _setup("wam_arm", "BallTip", refmod, cuda_device)
+    tip = g.body_index("BallTip")
+    inside, outside = GIMBAL_Q.copy(), GIMBAL_Q.copy()
+    inside[:, 5] += 1.0e-6
+    outside[:, 5] += 3.0e-6
+    q0 = np.ascontiguousarray(np.concatenate([GIMBAL_Q, inside, outside, GIMBAL_Q, inside]))
+    A = rik.graph.fk(q0)["A_BI"][:, tip, 3:]
+    cy = np.hypot(A[:, 0], A[:, 3])
+    lim = 16.0 * float(np.finfo(np.float32).eps)
+    n = len(GIMBAL_Q)
+    assert np.all(cy[:n] < 1e-12) and np.all((cy[n:2 * n] > 1e-7) & (cy[n:2 * n] < lim))
+    assert np.all(cy[2 * n:3 * n] > lim)
+    x_cur, _ = rik.task_kinematics(q0)
+    x_des = x_cur.copy()
+    rng = np.random.default_rng(4)
+    x_des[:3 * n, :3] += 0.05 * rng.uniform(-1, 1, size=(3 * n, 3))
+    x_des[:3 * n, 3:] = rng.uniform(-1.2, 1.2, size=(3 * n, 3))            # far: axis-angle branch
+    x_des[3 * n:, 3:] += 2.0e-3 * rng.uniform(-1, 1, size=(2 * n, 3))      # near: Euler-error branch
+    x_des = np.ascontiguousarray(x_des)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx in gimbal lock")
+    # ignoring the round trip would miss by O(cy) ~ 1e-6 on the states inside the branch
+    assert np.max(np.abs(dx_ref[n:2 * n, 3:])) > 1e-3
+    cond = step_condition(rik, q0)
+    ok = det_ref > 0.0
+    assert_step_close(out["dq"][ok], dq_ref[ok], cond[ok], "dq in gimbal lock")
+
+
+@pytest.mark.parametrize("general", [False, True], ids=["chain-kernel", "general-kernel"])
+@pytest.mark.parametrize("kinds", [("ABC",), ("XYZ", "ABC")])
+def test_relative_rotation_of_exactly_pi(kinds, general, refmod, cuda_device, monkeypatch):
+    """Mat3d_getAxisAngleSelf's angle == pi branch (external/Rcs_thirdPartyMath.c:90-163): axis
+    from the largest diagonal entry. The gantry's Bridge keeps the identity orientation in every
+    state (translational joints only), so targets with Euler angles (pi, 0, 0), (0, pi, 0) and
+    (0, 0, pi) are rotations of exactly pi about x, y and z in both implementations (the trace of
+    A_des A_curr^T is exactly -1): one case per diagonal branch."""
+    if general:
+        monkeypatch.setenv("RCSB_IK_GENERAL", "1")
+    g, m, rik, tasks = _setup("gantry", "Bridge", refmod, cuda_device, kinds)
+    lay = g.layout()
+    q0 = np.ascontiguousarray(np.repeat(workload.sample_states(lay, 4, first=31, margin=0.2), 3, axis=0))
+    x_cur, _ = rik.task_kinematics(q0)
+    x_des = x_cur.copy()
+    o = 3 if kinds == ("XYZ", "ABC") else 0
+    assert np.all(x_cur[:, o:o + 3] == 0.0), "Bridge must have exactly the identity orientation"
+    for i in range(len(q0)):
+        x_des[i, o + (i % 3)] = np.pi
+    if o:
+        x_des[:, :3] += 0.02
+    x_des = np.ascontiguousarray(x_des)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    # the reference took the pi branch: |dx_rot| = pi, along the axis of the non-zero Euler angle
+    rot = dx_ref[:, o:o + 3]
+    assert np.allclose(np.linalg.norm(rot, axis=1), np.pi, atol=1e-12)
+    assert np.all(np.argmax(np.abs(rot), axis=1) == np.arange(len(q0)) % 3)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx at angle pi")
+    # Bridge is moved by one joint only: J W J^T + lambda 1 has five eigenvalues equal to lambda
+    cond = step_condition(rik, q0)
+    assert_step_close(out["dq"], dq_ref, cond, "dq at angle pi")
+    assert_step_close(q - q0, q_ref - q0, cond, "q at angle pi")

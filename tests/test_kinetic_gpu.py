@@ -14,7 +14,7 @@ from conftest import assert_close, assert_structural_zeros, graph_file
 pytestmark = pytest.mark.gpu
 
 CASES = [("wam_arm", 500), ("wam_scenario", 200), ("schunk_sdh", 200), ("dexbot", 64),
-         ("husky", 64), ("humanoid", 48)]
+         ("husky", 64), ("humanoid", 48), ("polycoupled", 300)]
 
 
 def _models(name, refmod, dev):

@@ -15,7 +15,7 @@ from conftest import GRAPH_DIR, GRAPHS, ROOT, assert_close, assert_structural_ze
 from oracle import rcs_oracle
 from rcs_b200 import workload
 
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled"]
 
 
 def layout(name):

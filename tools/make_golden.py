@@ -26,7 +26,22 @@ CASES = {
     "humanoid": dict(n=12, effectors=["RightHandTip", "LeftHandTip", "FootL"]),
     "husky": dict(n=8, effectors=None),
     "gantry": dict(n=16, effectors=["Tool", "Camera"]),
+    # 5- and 9-coefficient polynomial couplings (Rcs_joint.c:318-462); a third of the states have
+    # the master joints below, a third above their limits (tangent extension of the polynomial)
+    "polycoupled": dict(n=24, effectors=["Tip", "Probe"], beyond=True),
 }
+
+
+def push_masters_beyond_limits(lay, q):
+    """States 1, 4, 7, ... get every master joint below q_min, states 2, 5, 8, ... above q_max."""
+    masters = sorted({j["coupledTo"] for j in lay["joints"] if j["coupledTo"] >= 0})
+    q = q.copy()
+    for mj in masters:
+        lo, hi = lay["joints"][mj]["q_min"], lay["joints"][mj]["q_max"]
+        span = hi - lo
+        q[1::3, mj] = lo - 0.05 * span - 0.3 * span * np.linspace(0.0, 1.0, len(q[1::3]))
+        q[2::3, mj] = hi + 0.05 * span + 0.3 * span * np.linspace(0.0, 1.0, len(q[2::3]))
+    return np.ascontiguousarray(q)
 
 
 def main():
@@ -37,6 +52,8 @@ def main():
         lay = g.layout()
         n = case["n"]
         q, qd = workload.sample_states(lay, n, first=1000, with_velocity=True)
+        if case.get("beyond"):
+            q = push_masters_beyond_limits(lay, q)
         names = [b["name"] for b in lay["bodies"]]
         effs = case["effectors"] or [names[-1], names[len(names) // 2]]
         eff = [names.index(e) for e in effs]
