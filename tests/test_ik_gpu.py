@@ -123,7 +123,12 @@ def test_ten_iterations_device_pointers(refmod, cuda_device):
     # ten steps compound: allow ten times the single-step bar on the states whose whole
     # trajectory stays reasonably conditioned
     ok = cond_max < 1.0e4
-    assert ok.mean() > 0.5
+    # measured on B200 (profiles/r02_ik_error_report.md): 80 % of the bench's target distribution
+    # stays below 1e4 along its whole trajectory, and every such state meets the FLAT bar
+    assert ok.mean() > 0.75
+    flat = np.abs(q - q_ref).max(axis=1) <= 1e-12 * np.maximum(1.0, np.abs(q_ref - q0).max(axis=1))
+    assert flat[ok].all(), f"{int((~flat[ok]).sum())} well-conditioned states miss the flat 1e-12 bar"
+    assert flat.mean() > 0.93            # measured 0.961 .. 0.965 over all states, cond up to 2e9
     assert_step_close(q[ok] - q0[ok], q_ref[ok] - q0[ok], 10.0 * cond_max[ok], "q after 10 iterations")
     # the iteration converges: the remaining task error is small
     assert np.median(np.abs(out["dx"].cpu().numpy()[ok])) < 1e-3
@@ -435,11 +440,22 @@ def test_euler_gimbal_lock_of_the_effector(general, refmod, cuda_device, monkeyp
     q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
     q = q0.copy()
     out = m.ik_rmr(tasks, q, x_des, iters=1, want=("dx", "dq", "det"))
-    assert_close(out["dx"], dx_ref, what="dx in gimbal lock")
-    # ignoring the round trip would miss by O(cy) ~ 1e-6 on the states inside the branch
+    # In the gimbal branch the rebuilt rotation is well conditioned (first angle from entries of
+    # size 1, third angle 0): flat 1e-12 bar. Ignoring the round trip would miss by O(cy) ~ 1e-6 on
+    # the states inside the branch.
+    in_branch = np.r_[0:2 * n, 3 * n:5 * n]
+    assert_close(out["dx"][in_branch], dx_ref[in_branch], what="dx in gimbal lock")
     assert np.max(np.abs(dx_ref[n:2 * n, 3:])) > 1e-3
+    # Just outside the branch the reference's own Euler angles are ill conditioned: alpha and gamma
+    # come from atan2 of entries of size cy that carry absolute rounding noise eps, i.e. an angle
+    # noise of eps / cy (3e-6 -> 7e-11) that differs between any two forward-kinematics
+    # implementations. Stated bar there: 8 eps / cy.
+    near = np.r_[2 * n:3 * n]
+    err = np.abs(out["dx"][near] - dx_ref[near]).max(axis=1)
+    assert np.all(err <= 8.0 * np.finfo(float).eps / cy[near]), err.max()
     cond = step_condition(rik, q0)
-    ok = det_ref > 0.0
+    ok = (det_ref > 0.0)
+    ok[near] = False
     assert_step_close(out["dq"][ok], dq_ref[ok], cond[ok], "dq in gimbal lock")
 
 
