@@ -206,6 +206,47 @@ int rcsb_ik_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, long 
                 const double* xDes, double lambda, double alpha, int iters, double* dx,
                 double* dq, double* det, unsigned flags, void* stream);
 
+/*
+ * The same solver with the remaining inputs and outputs of the reference's interface
+ * (IkSolverRMR::solveRightInverse(dq_ts, dq_ns, dx, dH, activation, lambda),
+ * src/RcsCore/IkSolverRMR.cpp:385-415, :415-596; solveLeftInverse :205-360):
+ *   activation  one value per task, shared by all states of the call (the reference passes it per
+ *               call). Tasks with activation <= 0 are dropped from J and dx
+ *               (ControllerBase::computeJ / compressToActive, ControllerBase.cpp:776, :1204);
+ *               xDes keeps its full layout [N x nx], nx over ALL tasks. NULL = all active.
+ *   scaleDx     != 0: the rows of dx are multiplied by their task's activation
+ *               (ControllerBase::computeDX(dx, x_des, a_des), ControllerBase.cpp:896-935);
+ *               0: dx as computeDX(dx, x_des) leaves it (examples/ExampleIK.cpp:162).
+ *   lambdaRows  right inverse: one regularisation value per ACTIVE row of J (the m x 1 lambda of
+ *               MatNd_rwPinv, Rcs_MatNd.c:1833); NULL = the scalar `lambda` on every row.
+ *   blending    left inverse: task-space weights Wx of TaskSpaceBlender (TaskSpaceBlender.cpp:
+ *               1193 Binary, :1228 Linear, :1109 Approximate) as selected by
+ *               IkSolverRMR::setActivationBlending (IkSolverRMR.cpp:800). The iterative modes
+ *               (IndependentTasks / DependentTasks) are not implemented: RCSB_EUNSUPPORTED.
+ *   dqTs, dqNs  [N x dof] task-space and null-space part of the LAST step (dq = dqTs + dqNs for
+ *               the right inverse); either may be NULL.
+ * dx (if given) holds the ACTIVE rows only, [N x nxActive]. Host arrays: activation, lambdaRows.
+ * Calls that use scaleDx with activations != 1, lambdaRows, blending != Binary, dqTs or dqNs run
+ * the general kernel (literal algebra of the reference); plain activation masks keep the fast
+ * kernels.
+ */
+#define RCSB_BLEND_BINARY 0
+#define RCSB_BLEND_LINEAR 1
+#define RCSB_BLEND_APPROXIMATE 2
+typedef struct
+{
+  const double* activation;   /* [nTasks] or NULL */
+  int scaleDx;
+  int blending;               /* RCSB_BLEND_*, left inverse only */
+  const double* lambdaRows;   /* [active rows] or NULL */
+  double* dqTs;
+  double* dqNs;
+} RcsbIkOptions;
+int rcsb_ik_rmr_ex(const RcsbModel* model, int nTasks, const RcsbTask* tasks, long N, double* q,
+                   const double* xDes, double lambda, double alpha, int iters, double* dx,
+                   double* dq, double* det, const RcsbIkOptions* options, unsigned flags,
+                   void* stream);
+
 /* ---- multi-GPU summary statistics ------------------------------------------------------- */
 
 /*

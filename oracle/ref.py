@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
         L.ref_ik_rmr.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
         L.ref_ik_rmr_left.restype = cd
         L.ref_ik_rmr_left.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
+        L.ref_ik_rmr_ex.restype = cd
+        L.ref_ik_rmr_ex.argtypes = [vp, cl, vp, vp, vp, ci, vp, ci, cd, cd, ci, ci, ci, vp, vp, vp, vp]
         L.ref_set_threads.argtypes = [ci]
         L.ref_set_log_level.argtypes = [ci]
         _LIB = L
@@ -291,6 +293,24 @@ class RefIk:
         self.last_seconds = lib().ref_ik_wholebody(self._h, N, qdim, _p(q), _p(out.get("A_BI")),
                                                    _p(out.get("J")), _p(out.get("M")))
         return out
+
+    def rmr_ex(self, q, x_des, activation=None, scale_dx=False, lambda_rows=None, lam=1.0e-8, alpha=0.05,
+               iters=1, left=False, blending=0):
+        """The reference's full solver interface: IkSolverRMR::solveRightInverse / solveLeftInverse
+        (dq_ts, dq_ns, dx, dH, activation, lambda | lambda vector) with ControllerBase::computeDX
+        (dx, x_des[, activation]). Returns dict(q, dx [active rows], dq_ts, dq_ns, det)."""
+        q = _c(q).copy()
+        x_des = _c(x_des)
+        N = q.shape[0]
+        act = None if activation is None else _c(np.asarray(activation, dtype=np.float64))
+        lr = None if lambda_rows is None else _c(np.asarray(lambda_rows, dtype=np.float64))
+        dx = np.zeros((N, self.nx))
+        ts, ns = np.empty((N, self.graph.dof)), np.empty((N, self.graph.dof))
+        det = np.empty((N,))
+        self.last_seconds = lib().ref_ik_rmr_ex(
+            self._h, N, _p(q), _p(x_des), _p(act), int(bool(scale_dx)), _p(lr), 0 if lr is None else len(lr),
+            float(lam), float(alpha), int(iters), int(bool(left)), int(blending), _p(dx), _p(ts), _p(ns), _p(det))
+        return dict(q=q, dx=dx, dq_ts=ts, dq_ns=ns, det=det)
 
     def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
         """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp with

@@ -893,6 +893,120 @@ double ref_ik_rmr_left(void* ik, long N, double* q, const double* xDes, double l
   return ikRmrImpl(ik, N, q, xDes, lambda, alpha, iters, dxOut, dqOut, det, true);
 }
 
+/*
+ * The same loop with the remaining arguments of the reference's solver interface:
+ *   activation [nTasks]      passed to computeDX (if scaleDx) and to the solver
+ *   lambdaRows [active rows] or NULL: the m x 1 lambda of solveRightInverse(..., const MatNd* lambda)
+ *   blending                 IkSolverRMR::setActivationBlending: 0 Binary, 1 Linear, 2 Approximate,
+ *                            3 IndependentTasks, 4 DependentTasks (left inverse)
+ *   dxOut  N x nx: dx of the last iteration, ACTIVE rows first (compressToActive), rest untouched
+ *   dqTs, dqNs N x dof: solveRightInverse / solveLeftInverse (dq_ts, dq_ns, ...) of the last iteration
+ */
+double ref_ik_rmr_ex(void* ik, long N, double* q, const double* xDes, const double* activation,
+                     int scaleDx, const double* lambdaRows, int nLambdaRows, double lambda, double alpha,
+                     int iters, int leftInverse, int blending, double* dxOut, double* dqTs, double* dqNs,
+                     double* det)
+{
+  IkHandle* h = (IkHandle*) ik;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*h->controller);
+    Rcs::IkSolverRMR solver(&c);
+    static const char* modes[] = {"Binary", "Linear", "Approximate", "IndependentTasks", "DependentTasks"};
+    solver.setActivationBlending(modes[blending]);
+    RcsGraph* graph = c.getGraph();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    const unsigned int nTasks = c.getNumberOfTasks();
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* ts = MatNd_create(dof, 1);
+    MatNd* ns = MatNd_create(dof, 1);
+    MatNd* a = MatNd_create(nTasks, 1);
+    MatNd* xd = MatNd_create(nx, 1);
+    MatNd* dx = MatNd_create(nx, 1);
+    MatNd* dxc = MatNd_create(nx, 1);
+    MatNd* dH = MatNd_create(1, nJ);
+    MatNd* lam = MatNd_create(nLambdaRows > 0 ? nLambdaRows : 1, 1);
+    for (unsigned int t = 0; t < nTasks; ++t)
+    {
+      a->ele[t] = activation ? activation[t] : 1.0;
+    }
+    for (int r = 0; r < nLambdaRows; ++r)
+    {
+      lam->ele[r] = lambdaRows[r];
+    }
+    sliceReady();
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, dof, q + i * dof, NULL);
+      memcpy(xd->ele, xDes + (size_t) i * nx, sizeof(double) * nx);
+      for (int it = 0; it < iters; ++it)
+      {
+        MatNd_reshape(dx, nx, 1);
+        if (scaleDx)
+        {
+          c.computeDX(dx, xd, a);      /* active rows only, scaled by the activations */
+        }
+        else
+        {
+          c.computeDX(dx, xd);         /* all rows; the solver compresses them */
+        }
+        c.computeJointlimitGradient(dH);
+        MatNd_constMulSelf(dH, alpha);
+        if (leftInverse)
+        {
+          solver.solveLeftInverse(ts, ns, dx, dH, a, lambda);
+        }
+        else if (nLambdaRows > 0)
+        {
+          solver.solveRightInverse(ts, ns, dx, dH, a, lam);
+        }
+        else
+        {
+          solver.solveRightInverse(ts, ns, dx, dH, a, lambda);
+        }
+        MatNd_addSelf(graph->q, ts);
+        MatNd_addSelf(graph->q, ns);
+        RcsGraph_setState(graph, NULL, NULL);
+      }
+      memcpy(q + i * dof, graph->q->ele, sizeof(double) * dof);
+      if (dxOut)
+      {
+        if (dx->m == nx && !scaleDx)
+        {
+          c.compressToActive(dxc, dx, a);
+          memcpy(dxOut + (size_t) i * nx, dxc->ele, sizeof(double) * dxc->m);
+        }
+        else
+        {
+          memcpy(dxOut + (size_t) i * nx, dx->ele, sizeof(double) * dx->m);
+        }
+      }
+      if (dqTs)
+      {
+        memcpy(dqTs + (size_t) i * dof, ts->ele, sizeof(double) * dof);
+      }
+      if (dqNs)
+      {
+        memcpy(dqNs + (size_t) i * dof, ns->ele, sizeof(double) * dof);
+      }
+      if (det)
+      {
+        det[i] = solver.getDeterminant();
+      }
+    }
+    sliceDone();
+    MatNd_destroy(qv);
+    MatNd_destroy(ts);
+    MatNd_destroy(ns);
+    MatNd_destroy(a);
+    MatNd_destroy(xd);
+    MatNd_destroy(dx);
+    MatNd_destroy(dxc);
+    MatNd_destroy(dH);
+    MatNd_destroy(lam);
+  });
+}
+
 }   // extern "C"
 
 static double ikRmrImpl(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,

@@ -6,6 +6,9 @@ used by the tests and ``bench.py``; it adds no computation of its own and raises
 library is missing — there is no Python or CPU fallback for the compute path.
 """
 from .api import (  # noqa: F401
+    BLEND_APPROXIMATE,
+    BLEND_BINARY,
+    BLEND_LINEAR,
     Graph,
     Model,
     RcsbError,
@@ -22,6 +25,9 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
+    "BLEND_APPROXIMATE",
+    "BLEND_BINARY",
+    "BLEND_LINEAR",
     "Graph",
     "Model",
     "RcsbError",

@@ -63,6 +63,14 @@ class _RcsbTask(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("effector", ctypes.c_int)]
 
 
+class _RcsbIkOptions(ctypes.Structure):
+    _fields_ = [("activation", ctypes.c_void_p), ("scaleDx", ctypes.c_int), ("blending", ctypes.c_int),
+                ("lambdaRows", ctypes.c_void_p), ("dqTs", ctypes.c_void_p), ("dqNs", ctypes.c_void_p)]
+
+
+BLEND_BINARY, BLEND_LINEAR, BLEND_APPROXIMATE = 0, 1, 2
+
+
 def lib() -> ctypes.CDLL:
     """Loads librcsb.so once. Fails loudly if it has not been built."""
     global _LIB
@@ -123,6 +131,8 @@ def lib() -> ctypes.CDLL:
         c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_ik_rmr_ex", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
+        ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_void, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
     sig("rcsb_wholebody", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p, c_int, c_void,
         c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
@@ -502,6 +512,47 @@ class Model:
         return out
 
     # -- inverse kinematics --------------------------------------------------------------
+    def ik_rmr_ex(self, tasks: Sequence, q, x_des, activation=None, scale_dx=False, lambda_rows=None,
+                  blending=BLEND_BINARY, lam=1.0e-8, alpha=0.05, iters=1,
+                  want=("det", "dq_ts", "dq_ns"), out=None, left_inverse=False):
+        """rcsb_ik_rmr_ex: the solver with task activations, per-row regularisation, task-space
+        blending (left inverse) and the task-space / null-space parts of the step. x_des keeps the
+        full layout over ALL tasks; "dx" holds the active rows only."""
+        N, qdim = self._batch(q)
+        if qdim != self.dof:
+            raise RcsbError("ik_rmr_ex: q must be N x dof")
+        dims = [6 if int(k) == TASK_XYZABC else 3 for k, _ in tasks]
+        act = np.ones(len(tasks)) if activation is None else np.ascontiguousarray(activation, dtype=np.float64)
+        if act.shape != (len(tasks),):
+            raise RcsbError("ik_rmr_ex: one activation per task")
+        nx_all = sum(dims)
+        nx_act = sum(d for d, a_ in zip(dims, act) if a_ > 0.0)
+        if tuple(x_des.shape) != (N, nx_all):
+            raise RcsbError(f"ik_rmr_ex: x_des must be {N} x {nx_all}")
+        lr = None
+        if lambda_rows is not None:
+            lr = np.ascontiguousarray(lambda_rows, dtype=np.float64)
+            if lr.shape != (nx_act,):
+                raise RcsbError(f"ik_rmr_ex: lambda_rows needs {nx_act} entries (active rows)")
+        shapes = {"dx": (N, nx_act), "dq": (N, self.dof), "det": (N,), "dq_ts": (N, self.dof),
+                  "dq_ns": (N, self.dof)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        tarr = (_RcsbTask * max(len(tasks), 1))(*[_RcsbTask(int(k), int(e)) for k, e in tasks])
+        a = _Args(self)
+        opt = _RcsbIkOptions(act.ctypes.data, int(bool(scale_dx)), int(blending),
+                             None if lr is None else lr.ctypes.data,
+                             a.ptr(out.get("dq_ts"), "dq_ts"), a.ptr(out.get("dq_ns"), "dq_ns"))
+        rc = lib().rcsb_ik_rmr_ex(
+            self._h, len(tasks), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam),
+            float(alpha), int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"),
+            a.ptr(out.get("det"), "det"), ctypes.byref(opt),
+            a.flags() | (_IK_LEFT_INVERSE if left_inverse else 0), a.stream())
+        _err(rc, "rcsb_ik_rmr_ex")
+        return out
+
     def ik_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1,
                want=("det",), out=None, left_inverse=False):
         """`iters` IkSolverRMR::solveRightInverse steps per state (solveLeftInverse with

@@ -821,6 +821,8 @@ extern "C" void rcsb_model_destroy(RcsbModel* m)
   cudaFree(m->ktPlan.dev);
   cudaFree(m->ktScratch[0]);
   cudaFree(m->ktScratch[1]);
+  cudaFree(m->ikScratch[0]);
+  cudaFree(m->ikScratch[1]);
   for (int i = 0; i < 2; ++i)
   {
     if (m->pipe.buf[i])

@@ -1047,11 +1047,85 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   return RCSB_OK;
 }
 
+/* extended inputs of rcsb_ik_rmr_ex, resolved on the host */
+struct IkEx
+{
+  bool general = false;       /* needs the general kernel */
+  int lambdaPerRow = 0;
+  int blending = 0;
+  double lambdaRow[12] = {0.0};
+  double taskScale[4] = {1.0, 1.0, 1.0, 1.0};
+  double taskAct[4] = {1.0, 1.0, 1.0, 1.0};
+  double* dqTs = nullptr;
+  double* dqNs = nullptr;
+  /* activation mask: xDes rows have nxAll entries, the plan's tasks read the columns xMap[0..nx) */
+  int nxAll = 0;
+  std::vector<int> xMap;
+};
+
+/* x_des rows of the active tasks, gathered from the full rows */
+__global__ void __launch_bounds__(256)
+ikGatherKernel(const double* __restrict__ src, double* __restrict__ dst, long N, int nxAll, int nxAct,
+               const int* __restrict__ map)
+{
+  const long total = N * nxAct;
+  for (long e = (long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long) gridDim.x * blockDim.x)
+  {
+    const long s = e / nxAct;
+    const int k = (int) (e - s * nxAct);
+    dst[e] = src[s * nxAll + map[k]];
+  }
+}
+
 int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const double* xDes,
              double lambda, double alpha, int iters, double* dx, double* dq, double* det,
-             bool leftInverse, cudaStream_t stream)
+             bool leftInverse, cudaStream_t stream, const IkEx* ex = nullptr, int ws = 0)
 {
   rcsb::IkArgs a;
+  memset(&a, 0, sizeof(a));
+  RCSB_CUDA(cudaSetDevice(m->device));
+  if (ex && !ex->xMap.empty())
+  {
+    /* compressToActive on x_des: one small gather kernel into a per-stream scratch buffer */
+    const int nxAct = (int) ex->xMap.size();
+    const size_t need = (size_t) N * nxAct * sizeof(double) + 256;
+    {
+      std::lock_guard<std::recursive_mutex> lock(m->mtx);
+      if (m->ikScratchBytes[ws] < need)
+      {
+        if (m->ikScratch[ws])
+        {
+          RCSB_CUDA(cudaFree(m->ikScratch[ws]));
+          m->ikScratch[ws] = nullptr;
+          m->ikScratchBytes[ws] = 0;
+        }
+        RCSB_CUDA(cudaMalloc(&m->ikScratch[ws], need));
+        m->ikScratchBytes[ws] = need;
+      }
+    }
+    int* dMap = reinterpret_cast<int*>(m->ikScratch[ws]);
+    double* dX = reinterpret_cast<double*>(m->ikScratch[ws] + 256);
+    RCSB_CUDA(cudaMemcpyAsync(dMap, ex->xMap.data(), sizeof(int) * (size_t) nxAct, cudaMemcpyHostToDevice, stream));
+    const long total = N * nxAct;
+    long blocks = (total + 255) / 256;
+    const long cap = (long) m->smCount * 8;
+    blocks = blocks < cap ? blocks : cap;
+    ikGatherKernel<<<(unsigned int) (blocks > 0 ? blocks : 1), 256, 0, stream>>>(xDes, dX, N, ex->nxAll, nxAct, dMap);
+    RCSB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    xDes = dX;
+  }
+  if (ex)
+  {
+    a.extended = 1;
+    a.lambdaPerRow = ex->lambdaPerRow;
+    a.blending = ex->blending;
+    memcpy(a.lambdaRow, ex->lambdaRow, sizeof(a.lambdaRow));
+    memcpy(a.taskScale, ex->taskScale, sizeof(a.taskScale));
+    memcpy(a.taskAct, ex->taskAct, sizeof(a.taskAct));
+    a.dqTs = ex->dqTs;
+    a.dqNs = ex->dqNs;
+  }
   a.model = m->dev;
   a.plan = plan->dev;
   a.modelBytes = m->hdr.totalBytes;
@@ -1066,9 +1140,8 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
   a.dx = dx;
   a.dq = dq;
   a.det = det;
-  RCSB_CUDA(cudaSetDevice(m->device));
   const char* noFast = getenv("RCSB_IK_GENERAL");   /* force the general kernel (tests) */
-  const bool general = (noFast && noFast[0] == '1') || iters > 64;
+  const bool general = (noFast && noFast[0] == '1') || iters > 64 || (ex && ex->general);
   const int chainNc = general ? 0 : plan->aux1;
   const int multiNu = general ? 0 : plan->nEff;
   cudaError_t e = rcsb_launch_ik(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, chainNc,
@@ -1087,9 +1160,15 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
 
 }   // namespace
 
-extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, long N,
-                           double* q, const double* xDes, double lambda, double alpha, int iters,
-                           double* dx, double* dq, double* det, unsigned flags, void* stream)
+static int taskDim(int kind)
+{
+  return kind == RCSB_TASK_XYZABC ? 6 : 3;
+}
+
+extern "C" int rcsb_ik_rmr_ex(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, long N, double* q,
+                              const double* xDes, double lambda, double alpha, int iters, double* dx,
+                              double* dq, double* det, const RcsbIkOptions* opt, unsigned flags,
+                              void* stream)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   if (!m)
@@ -1097,38 +1176,142 @@ extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* task
     rcsb_set_error("model is NULL");
     return RCSB_EINVAL;
   }
-  if (N < 0 || (N > 0 && (!q || !xDes)) || iters < 0)
+  if (N < 0 || (N > 0 && (!q || !xDes)) || iters < 0 || nTasks <= 0 || !tasks)
   {
-    rcsb_set_error("rcsb_ik_rmr: invalid batch (N = %ld, q = %p, xDes = %p, iters = %d)", N,
-                   (void*) q, (const void*) xDes, iters);
+    rcsb_set_error("rcsb_ik_rmr: invalid batch (N = %ld, q = %p, xDes = %p, iters = %d, nTasks = %d)", N,
+                   (void*) q, (const void*) xDes, iters, nTasks);
     return RCSB_EINVAL;
   }
+  const bool left = (flags & RCSB_IK_LEFT_INVERSE) != 0;
+
+  /* ---- activation mask and the extended inputs ------------------------------------------- */
+  std::vector<RcsbTask> active;
+  IkEx ex;
+  bool useEx = false;
+  if (opt)
+  {
+    if (opt->blending != RCSB_BLEND_BINARY && opt->blending != RCSB_BLEND_LINEAR &&
+        opt->blending != RCSB_BLEND_APPROXIMATE)
+    {
+      rcsb_set_error("rcsb_ik_rmr_ex: blending mode %d is not implemented (Binary, Linear, Approximate are)",
+                     opt->blending);
+      return RCSB_EUNSUPPORTED;
+    }
+    int planTask = 0, col = 0;
+    bool allActive = true;
+    for (int t = 0; t < nTasks; ++t)
+    {
+      const int dim = taskDim(tasks[t].kind);
+      const double act = opt->activation ? opt->activation[t] : 1.0;
+      if (act > 0.0)
+      {
+        active.push_back(tasks[t]);
+        for (int k = 0; k < dim; ++k)
+        {
+          ex.xMap.push_back(col + k);
+        }
+        for (int k = 0; k < dim / 3; ++k, ++planTask)
+        {
+          if (planTask < 4)
+          {
+            ex.taskScale[planTask] = opt->scaleDx ? act : 1.0;
+            ex.taskAct[planTask] = act;
+          }
+          ex.general = ex.general || (opt->scaleDx && act != 1.0);
+        }
+      }
+      else
+      {
+        allActive = false;
+      }
+      col += dim;
+    }
+    ex.nxAll = col;
+    if (allActive)
+    {
+      ex.xMap.clear();   /* nothing to gather */
+    }
+    if (active.empty())
+    {
+      rcsb_set_error("rcsb_ik_rmr_ex: no task is active");
+      return RCSB_EINVAL;
+    }
+    const int nxAct = allActive ? col : (int) ex.xMap.size();
+    if (opt->lambdaRows)
+    {
+      if (left)
+      {
+        rcsb_set_error("rcsb_ik_rmr_ex: the left inverse takes a scalar lambda (IkSolverRMR.cpp:205)");
+        return RCSB_EINVAL;
+      }
+      if (nxAct > 12)
+      {
+        rcsb_set_error("rcsb_ik_rmr_ex: per-row lambda supports at most 12 active rows (%d)", nxAct);
+        return RCSB_EUNSUPPORTED;
+      }
+      ex.lambdaPerRow = 1;
+      memcpy(ex.lambdaRow, opt->lambdaRows, sizeof(double) * (size_t) nxAct);
+      ex.general = true;
+    }
+    if (left && opt->blending != RCSB_BLEND_BINARY)
+    {
+      ex.blending = opt->blending;
+      ex.general = true;
+    }
+    ex.dqTs = opt->dqTs;
+    ex.dqNs = opt->dqNs;
+    ex.general = ex.general || opt->dqTs || opt->dqNs;
+    if (ex.general && planTask > 4)
+    {
+      rcsb_set_error("rcsb_ik_rmr_ex: the extended solver takes at most 4 three-dimensional tasks (%d)",
+                     planTask);
+      return RCSB_EUNSUPPORTED;
+    }
+    useEx = ex.general || !ex.xMap.empty();
+    tasks = active.data();
+    nTasks = (int) active.size();
+  }
+
   const DevicePlan* plan = nullptr;
   int rc = buildIkPlan(m, nTasks, tasks, &plan);
   if (rc != RCSB_OK || N == 0)
   {
     return rc;
   }
-  const bool left = (flags & RCSB_IK_LEFT_INVERSE) != 0;
+  const IkEx* exp = useEx ? &ex : nullptr;
 
   if (!(flags & RCSB_HOST_PTRS))
   {
     return ikDevice(m, plan, N, q, xDes, lambda, alpha, iters, dx, dq, det, left,
-                    static_cast<cudaStream_t>(stream));
+                    static_cast<cudaStream_t>(stream), exp, 0);
   }
 
   const size_t dof = (size_t) m->hdr.dof, nx = (size_t) plan->aux0;
+  const size_t nxIn = (exp && !ex.xMap.empty()) ? (size_t) ex.nxAll : nx;
   std::vector<StagedArray> arr;
-  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET };
+  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET, I_TS, I_NS };
   arr.push_back({q, nullptr, dof, nullptr});
-  arr.push_back({xDes, nullptr, nx, nullptr});
+  arr.push_back({xDes, nullptr, nxIn, nullptr});
   arr.push_back({nullptr, q, dof, nullptr});          /* in-out: shares the input buffer */
   arr.push_back({nullptr, dx, dx ? nx : 0, nullptr});
   arr.push_back({nullptr, dq, dq ? dof : 0, nullptr});
   arr.push_back({nullptr, det, (size_t) (det ? 1 : 0), nullptr});
-  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
+  arr.push_back({nullptr, ex.dqTs, ex.dqTs ? dof : 0, nullptr});
+  arr.push_back({nullptr, ex.dqNs, ex.dqNs ? dof : 0, nullptr});
+  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1, -1, -1}, [&](long n, cudaStream_t st, int slot) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    IkEx local = ex;
+    local.dqTs = dv(I_TS, ex.dqTs);
+    local.dqNs = dv(I_NS, ex.dqNs);
     return ikDevice(m, plan, n, arr[I_QIN].dev, arr[I_X].dev, lambda, alpha, iters,
-                    dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), left, st);
+                    dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), left, st, useEx ? &local : nullptr, slot);
   });
+}
+
+extern "C" int rcsb_ik_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, long N,
+                           double* q, const double* xDes, double lambda, double alpha, int iters,
+                           double* dx, double* dq, double* det, unsigned flags, void* stream)
+{
+  return rcsb_ik_rmr_ex(cm, nTasks, tasks, N, q, xDes, lambda, alpha, iters, dx, dq, det, nullptr, flags,
+                        stream);
 }

@@ -324,6 +324,7 @@ ikKernel(const IkArgs a)
   double A[MAXS * MAXS];      /* J invWq J^T + lambda 1 (LEFT: J_r^T J_r + lambda 1) -> L -> L^-1 */
   double Ai[MAXS * MAXS];     /* inverse */
   double dx[MAXNX], g[MAXNJ], Jg[MAXNX], dq[MAXNJ], row[MAXNX];
+  double dqT[MAXNJ], dqN[MAXNJ];   /* task-space / null-space parts of dq (dq_ts, dq_ns) */
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
   double det = 0.0;
 
@@ -334,6 +335,8 @@ ikKernel(const IkArgs a)
   for (int i = 0; i < nJ; ++i)
   {
     dq[i] = 0.0;
+    dqT[i] = 0.0;
+    dqN[i] = 0.0;
   }
   for (int i = 0; i < nx; ++i)
   {
@@ -488,6 +491,13 @@ ikKernel(const IkArgs a)
         toEuler(xc, e + 3);
         eulerTaskError(dx + 3 * t, xdl, xc);
       }
+      if (a.extended && t < 4)
+      {
+        /* ControllerBase::computeDX with activations: dx_i *= a_i (ControllerBase.cpp:925) */
+        dx[3 * t] *= a.taskScale[t];
+        dx[3 * t + 1] *= a.taskScale[t];
+        dx[3 * t + 2] *= a.taskScale[t];
+      }
       for (int k = p.chainStart[t]; k < p.chainStart[t + 1]; ++k)
       {
         const int ent = p.chain[k];
@@ -604,6 +614,7 @@ ikKernel(const IkArgs a)
 
     /* ---- J# = invWq J^T (J invWq J^T + lambda 1)^-1 ------------------------------------------ */
     const int n = LEFT ? nq : nx;
+    double wx[MAXNX];    /* LEFT: task-space blending weights Wx, one per row of J */
     if (LEFT)
     {
       for (int k = 0; k < nx; ++k)
@@ -613,6 +624,34 @@ ikKernel(const IkArgs a)
           J[k * nJ + i] *= wv[i];
         }
       }
+      for (int k = 0; k < nx; ++k)
+      {
+        wx[k] = 1.0;     /* TaskSpaceBlender::computeBinary (TaskSpaceBlender.cpp:1193) */
+        const int t = k / 3;
+        if (a.extended && a.blending == 1 && t < 4)
+        {
+          wx[k] = a.taskAct[t];   /* computeLinear (:1228) */
+        }
+        else if (a.extended && a.blending == 2 && t < 4)
+        {
+          /* computeApproximate (:1109) on the weighted Jacobian J_r = J A invWq_r */
+          const double act = a.taskAct[t];
+          const double ci = fmin(fmax(act, 0.0), 1.0);
+          double aBuf = 0.0;
+          for (int i = 0; i < nq; ++i)
+          {
+            aBuf += J[k * nJ + i] * J[k * nJ + i];
+          }
+          double wi1 = 1.0;
+          if (ci < 1.0)
+          {
+            wi1 = aBuf == 0.0 ? 0.0 : a.lambda * ci / (aBuf * (1.0 - ci));
+          }
+          const double wi2 = pow(0.01 * a.lambda, 1.0 - ci);
+          wx[k] = act * wi2 + (1.0 - act) * wi1;
+        }
+      }
+      /* J_r^T Wx J_r + lambda 1 (MatNd_rwPinv2, Rcs_MatNd.c:1920) */
       for (int r = 0; r < nq; ++r)
       {
         for (int c = 0; c < nq; ++c)
@@ -620,7 +659,7 @@ ikKernel(const IkArgs a)
           double sum = 0.0;
           for (int k = 0; k < nx; ++k)
           {
-            sum += J[k * nJ + r] * J[k * nJ + c];
+            sum += a.extended ? J[k * nJ + r] * wx[k] * J[k * nJ + c] : J[k * nJ + r] * J[k * nJ + c];
           }
           A[r * n + c] = sum + (r == c ? a.lambda : 0.0);
         }
@@ -645,7 +684,7 @@ ikKernel(const IkArgs a)
           {
             sum += J[r * nJ + i] * P[i * nx + c];
           }
-          A[r * nx + c] = sum + (r == c ? a.lambda : 0.0);
+          A[r * nx + c] = sum + (r == c ? ((a.extended && a.lambdaPerRow) ? a.lambdaRow[r] : a.lambda) : 0.0);
         }
       }
     }
@@ -684,6 +723,8 @@ ikKernel(const IkArgs a)
       for (int i = 0; i < nJ; ++i)
       {
         dq[i] = 0.0;
+        dqT[i] = 0.0;
+        dqN[i] = 0.0;
       }
       continue;
     }
@@ -728,7 +769,7 @@ ikKernel(const IkArgs a)
           {
             sum += Ai[i * n + t] * J[c * nJ + t];
           }
-          P[i * nx + c] = sum;
+          P[i * nx + c] = a.extended ? sum * wx[c] : sum;   /* (...)^-1 J_r^T Wx */
         }
       }
     }
@@ -774,6 +815,8 @@ ikKernel(const IkArgs a)
           ns += P[i * nx + c] * Jg[c];
         }
         dq[i] = LEFT ? (ts + (g[i] - ns)) * wv[i] : ts + (g[i] - ns);
+        dqT[i] = LEFT ? ts * wv[i] : ts;
+        dqN[i] = LEFT ? (g[i] - ns) * wv[i] : g[i] - ns;
       }
     }
     else
@@ -793,13 +836,25 @@ ikKernel(const IkArgs a)
         nsr[i] = g[i] - ns;
         if (LEFT)
         {
+          /* split form (IkSolverRMR.cpp:278-360): each part goes back to the unweighted space and
+           * through A on its own */
+          dqT[i] = ts * wv[i];
+          dqN[i] = nsr[i] * wv[i];
           tsr[i] = (ts + nsr[i]) * wv[i];   /* one reduced step, back in the unweighted space */
           nsr[i] = 0.0;
         }
       }
+      double rT[MAXNJ], rN[MAXNJ];
+      for (int i = 0; i < nq; ++i)
+      {
+        rT[i] = LEFT ? dqT[i] : tsr[i];
+        rN[i] = LEFT ? dqN[i] : nsr[i];
+      }
       for (int c = 0; c < nJ; ++c)
       {
         dq[c] = LEFT ? av[c] * tsr[p.colRed[c]] : av[c] * tsr[p.colRed[c]] + av[c] * nsr[p.colRed[c]];
+        dqT[c] = av[c] * rT[p.colRed[c]];
+        dqN[c] = av[c] * rN[p.colRed[c]];
       }
     }
     for (int i = 0; i < nJ; ++i)
@@ -832,6 +887,21 @@ ikKernel(const IkArgs a)
   if (a.det)
   {
     a.det[s] = det;
+  }
+  if (a.extended && (a.dqTs || a.dqNs))
+  {
+    for (int j = 0; j < dof; ++j)
+    {
+      const int c = m.jntJacobi[j];
+      if (a.dqTs)
+      {
+        a.dqTs[s * dof + j] = c >= 0 ? dqT[c] : 0.0;
+      }
+      if (a.dqNs)
+      {
+        a.dqNs[s * dof + j] = c >= 0 ? dqN[c] : 0.0;
+      }
+    }
   }
 }
 

@@ -87,6 +87,16 @@ struct IkArgs
   double* dx;
   double* dq;
   double* det;
+  /* extended solver inputs / outputs (rcsb_ik_rmr_ex; general kernel only) */
+  int extended;        /* 1: any of the fields below is in use */
+  int lambdaPerRow;    /* 1: lambdaRow[r] regularises row r of J W J^T (MatNd_addDiag, Rcs_MatNd.c:1872) */
+  int blending;        /* left inverse: RCSB_BLEND_* task-space weights Wx (TaskSpaceBlender.cpp) */
+  int pad;
+  double lambdaRow[12];
+  double taskScale[4]; /* dx rows of task t are multiplied by it (ControllerBase::computeDX with a_des) */
+  double taskAct[4];   /* activation of task t (blending weights) */
+  double* dqTs;        /* N x dof: task-space part of the last step */
+  double* dqNs;        /* N x dof: null-space part of the last step */
 };
 
 }   // namespace rcsb

@@ -60,6 +60,8 @@ struct RcsbModel
   bool ktPlanBuilt = false;
   double* ktScratch[2] = {nullptr, nullptr};
   size_t ktScratchDoubles[2] = {0, 0};
+  char* ikScratch[2] = {nullptr, nullptr};      /* gathered x_des of masked IK calls, per staging slot */
+  size_t ikScratchBytes[2] = {0, 0};
   rcsbhost::StagePipe pipe;
 
   const int* iarr(int a) const
