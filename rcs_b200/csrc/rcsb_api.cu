@@ -819,6 +819,10 @@ extern "C" void rcsb_model_destroy(RcsbModel* m)
     cudaFree(kv.second.dev);
   }
   cudaFree(m->ktPlan.dev);
+  for (auto& kv : m->wbPlans)
+  {
+    cudaFree(kv.second.dev);
+  }
   cudaFree(m->ktScratch[0]);
   cudaFree(m->ktScratch[1]);
   cudaFree(m->ikScratch[0]);

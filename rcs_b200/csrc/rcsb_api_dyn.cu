@@ -6,17 +6,24 @@
 
 using namespace rcsbhost;
 
-namespace
-{
-
 /* ---- kinetic-terms plan ------------------------------------------------------------------- */
 
-int buildKtPlan(RcsbModel* m)
+int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
 {
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
-  if (m->ktPlanBuilt)
+  if (!wb && m->ktPlanBuilt)
   {
+    *out = &m->ktPlan;
     return RCSB_OK;
+  }
+  if (wb)
+  {
+    auto it = m->wbPlans.find(wb->key);
+    if (it != m->wbPlans.end())
+    {
+      *out = &it->second;
+      return RCSB_OK;
+    }
   }
 
   const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
@@ -80,6 +87,52 @@ int buildKtPlan(RcsbModel* m)
     }
   }
 
+  /* whole-body plans: output slots of the selected frames, task bodies whose frames go into the
+   * record, and which columns move them */
+  std::vector<int> bodyOut((size_t) nb, -1), bodyFrameRec((size_t) nb, 0), taskBodyRec;
+  std::vector<unsigned char> taskColOn;
+  int nSelOut = 0;
+  if (wb)
+  {
+    const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
+    if (wb->nSel == 0)
+    {
+      for (int b = 0; b < nb; ++b)
+      {
+        bodyOut[(size_t) b] = b;
+      }
+      nSelOut = nb;
+    }
+    else
+    {
+      for (int i = 0; i < wb->nSel; ++i)
+      {
+        const int b = wb->bodySel[i];
+        if (b < 0 || b >= nb || bodyOut[(size_t) b] >= 0)
+        {
+          rcsb_set_error("rcsb_wholebody: bodySel[%d] = %d is out of range or selected twice", i, b);
+          return RCSB_EINVAL;
+        }
+        bodyOut[(size_t) b] = i;
+      }
+      nSelOut = wb->nSel;
+    }
+    taskBodyRec.assign(wb->taskBodies.size(), 0);
+    taskColOn.assign(wb->taskBodies.size() * (size_t) (nJ > 0 ? nJ : 1), 0);
+    for (size_t u = 0; u < wb->taskBodies.size(); ++u)
+    {
+      const int b = wb->taskBodies[u];
+      bodyFrameRec[(size_t) b] = 1;
+      for (int j = bodyLastJnt[b]; j >= 0; j = jntPrev[j])
+      {
+        if (jntJacobi[j] >= 0)
+        {
+          taskColOn[u * (size_t) nJ + (size_t) jntJacobi[j]] = 1;
+        }
+      }
+    }
+  }
+
   /* walk bookkeeping: the accumulator is emitted as a run whenever the walk moves to a body of
    * another link; every record of the state gets its offset in the order of production */
   std::vector<int> bodyEmit((size_t) nb + 1, 0), runLink, runRec;
@@ -107,6 +160,17 @@ int buildKtPlan(RcsbModel* m)
           colRec[jntJacobi[j]] = rec;
           rec += RCSB_KT_COL_REC;
         }
+      }
+      if (bodyFrameRec[(size_t) b])
+      {
+        for (size_t u = 0; u < taskBodyRec.size(); ++u)
+        {
+          if (wb->taskBodies[u] == b)
+          {
+            taskBodyRec[u] = rec;
+          }
+        }
+        rec += 12;   /* the body's frame, after its joints and A_BP */
       }
     }
     if (cur >= 0)
@@ -188,7 +252,22 @@ int buildKtPlan(RcsbModel* m)
   };
   place(ph.offBodyLink, (size_t) nb * 4);
   place(ph.offBodyEmit, ((size_t) nb + 1) * 4);
+  if (wb)
+  {
+    ph.wholeBody = 1;
+    ph.nSel = nSelOut;
+    ph.nTaskBodies = (int) wb->taskBodies.size();
+    ph.nJac = (int) wb->jacTasks.size() / 8;
+    place(ph.offBodyOut, (size_t) nb * 4);
+    place(ph.offBodyFrameRec, (size_t) nb * 4);
+  }
   ph.walkBytes = off;
+  if (wb)
+  {
+    place(ph.offTaskBodyRec, taskBodyRec.size() * 4);
+    place(ph.offJacTasks, wb->jacTasks.size() * 4);
+    place(ph.offTaskColOn, taskColOn.size());
+  }
   place(ph.offLinkParent, (size_t) nLinks * 4);
   place(ph.offColJoint, colJoint.size() * 4);
   place(ph.offColLink, colLink.size() * 4);
@@ -223,17 +302,43 @@ int buildKtPlan(RcsbModel* m)
   put(ph.offLinkHome, linkHome.data(), linkHome.size() * 4);
   put(ph.offExtraRuns, extraRuns.data(), extraRuns.size() * 4);
   put(ph.offColHome, colHome.data(), colHome.size() * 4);
+  if (wb)
+  {
+    put(ph.offBodyOut, bodyOut.data(), (size_t) nb * 4);
+    put(ph.offBodyFrameRec, bodyFrameRec.data(), (size_t) nb * 4);
+    put(ph.offTaskBodyRec, taskBodyRec.data(), taskBodyRec.size() * 4);
+    put(ph.offJacTasks, wb->jacTasks.data(), wb->jacTasks.size() * 4);
+    put(ph.offTaskColOn, taskColOn.data(), taskColOn.size());
+  }
 
+  DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
-  RCSB_CUDA(cudaMalloc(&m->ktPlan.dev, blob.size()));
-  RCSB_CUDA(cudaMemcpy(m->ktPlan.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-  m->ktPlan.bytes = ph.totalBytes;
-  m->ktPlan.aux0 = ph.recDoubles;
-  m->ktPlan.aux1 = nJ;
-  m->ktPlan.nScrRows = ph.walkBytes;
-  m->ktPlanBuilt = true;
+  RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
+  /* the first launch may follow on a non-blocking stream: make sure the plan has landed */
+  RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  RCSB_CUDA(cudaDeviceSynchronize());
+  dp.bytes = ph.totalBytes;
+  dp.aux0 = ph.recDoubles;
+  dp.aux1 = nJ;
+  dp.nScrRows = ph.walkBytes;
+  dp.nSel = nSelOut;
+  dp.nEff = ph.nJac;
+  if (wb)
+  {
+    auto ins = m->wbPlans.emplace(wb->key, dp);
+    *out = &ins.first->second;
+  }
+  else
+  {
+    m->ktPlan = dp;
+    m->ktPlanBuilt = true;
+    *out = &m->ktPlan;
+  }
   return RCSB_OK;
 }
+
+namespace
+{
 
 /* States per pass: the records of one pass (recDoubles x 8 B per state) are written by the walk
  * kernel and read back by the assembly kernel right after. Larger passes are faster (measured
@@ -253,21 +358,15 @@ long ktChunk(const RcsbModel* m, int recDoubles)
   return (chunk + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS * RCSB_KT_WALK_THREADS;
 }
 
-struct KtExtra
-{
-  double* cog = nullptr;
-  double* Jcog = nullptr;
-  const double* Fext = nullptr;
-  const double* Fjnt = nullptr;
-  double* qdd = nullptr;
-};
+}   // namespace
 
-int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
-             double* h, double* Fg, double* E, const KtExtra& x, cudaStream_t stream, int ws)
+int rcsbhost::ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
+                       double* h, double* Fg, double* E, const KtExtra& x, cudaStream_t stream, int ws)
 {
   double* cog = x.cog;
   double* Jcog = x.Jcog;
-  const int recDoubles = m->ktPlan.aux0;
+  const DevicePlan& plan = x.plan ? *x.plan : m->ktPlan;
+  const int recDoubles = plan.aux0;
   const long chunk = ktChunk(m, recDoubles) < N ? ktChunk(m, recDoubles) : N;
   const size_t need = (size_t) chunk * (size_t) recDoubles;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -292,11 +391,15 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
   {
     const long n = (N - s0 < chunk) ? (N - s0) : chunk;
     rcsb::KtArgs a;
+    memset(&a, 0, sizeof(a));
     a.model = m->dev;
-    a.plan = m->ktPlan.dev;
+    a.plan = plan.dev;
     a.modelBytes = m->hdr.totalBytes;
-    a.planBytes = m->ktPlan.bytes;
-    a.planWalkBytes = m->ktPlan.nScrRows;
+    a.planBytes = plan.bytes;
+    a.planWalkBytes = plan.nScrRows;
+    a.wholeBody = x.plan ? 1 : 0;
+    a.A_BI = x.A_BI ? x.A_BI + s0 * (long) plan.nSel * 12 : nullptr;
+    a.Jt = x.Jt ? x.Jt + s0 * (long) plan.nEff * 3 * nJ : nullptr;
     a.N = n;
     a.qdim = qdim;
     a.q = q + s0 * qdim;
@@ -313,13 +416,11 @@ int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, 
     a.stageM = x.qdd ? 1 : 0;   /* the Cholesky solve of the direct dynamics works on the staged M */
     a.rec = m->ktScratch[ws];
     a.recDoubles = recDoubles;
-    RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, m->ktPlan.aux1, m->smCount, stream));
+    RCSB_CUDA(rcsb_launch_kt(&a, m->hdr.nSlots, m->hdr.nJ, plan.aux1, m->smCount, stream));
     g_launches.fetch_add(2);
   }
   return RCSB_OK;
 }
-
-}   // namespace
 
 static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, const double* qd,
                     double* M, double* h, double* Fg, double* E, const KtExtra& x, unsigned flags,
@@ -331,7 +432,8 @@ static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
   {
     return rc;
   }
-  rc = buildKtPlan(m);
+  DevicePlan* basePlan = nullptr;
+  rc = buildKtPlan(m, nullptr, &basePlan);
   if (rc != RCSB_OK || N == 0)
   {
     return rc;

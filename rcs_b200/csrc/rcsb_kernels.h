@@ -69,6 +69,10 @@ struct KtArgs
   int recDoubles;
   int planWalkBytes;   /* leading part of the plan staged by the walk kernel */
   int stageM;          /* assembly: stage M in shared memory (needed by the direct dynamics) */
+  /* whole-body plans */
+  double* A_BI;        /* N x nSel x 12 frames of the selected bodies (written by the walk) */
+  double* Jt;          /* N x nJac x 3 x nJ task Jacobians (written by the assembly) */
+  int wholeBody;       /* 1: the plan is a whole-body plan */
 };
 
 struct IkArgs
@@ -106,6 +110,7 @@ cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows, cuda
 /* enqueues the walk kernel and the assembly kernel (2 launches) */
 cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nJ2, int smCount,
                            cudaStream_t stream);
+/* maximum dynamic shared memory of the assembly kernel for a record of recDoubles (plan checks) */
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            int multiNu, int nEffs, int nTasks, cudaStream_t stream);
 }

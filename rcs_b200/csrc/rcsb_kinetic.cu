@@ -61,6 +61,12 @@ struct KtPlanView
   const int* linkHome;
   const int2* extraRuns;
   const int* colHome;
+  /* whole-body plans */
+  const int* bodyOut;
+  const int* bodyFrameRec;
+  const int* taskBodyRec;
+  const int* jacTasks;
+  const unsigned char* taskColOn;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -78,6 +84,11 @@ struct KtPlanView
     linkHome = reinterpret_cast<const int*>(blob + hdr->offLinkHome);
     extraRuns = reinterpret_cast<const int2*>(blob + hdr->offExtraRuns);
     colHome = reinterpret_cast<const int*>(blob + hdr->offColHome);
+    bodyOut = reinterpret_cast<const int*>(blob + hdr->offBodyOut);
+    bodyFrameRec = reinterpret_cast<const int*>(blob + hdr->offBodyFrameRec);
+    taskBodyRec = reinterpret_cast<const int*>(blob + hdr->offTaskBodyRec);
+    jacTasks = reinterpret_cast<const int*>(blob + hdr->offJacTasks);
+    taskColOn = reinterpret_cast<const unsigned char*>(blob + hdr->offTaskColOn);
   }
 };
 
@@ -123,7 +134,10 @@ __device__ __forceinline__ double pairing(bool isRot, const double a[3], const d
 /* kernel 1: depth-first walk, one thread per state                                            */
 /* ------------------------------------------------------------------------------------------ */
 
-template <bool VEL, int NSLOTS>
+/* WB (whole-body plans, rcsb_wholebody): the walk also stores the frames of the selected bodies
+ * (A_BI: three 32-byte stores per frame like fkKernel) and emits the frames of the bodies the task
+ * Jacobians refer to into the record. */
+template <bool VEL, int NSLOTS, bool WB>
 __global__ void __launch_bounds__(RCSB_KT_WALK_THREADS)
 ktWalkKernel(const KtArgs a)
 {
@@ -138,7 +152,7 @@ ktWalkKernel(const KtArgs a)
   ModelView m;
   m.bind(sModel);
   KtPlanView p;
-  p.bind(sPlan);   /* only hdr, bodyLink and bodyEmit are staged */
+  p.bind(sPlan);   /* only hdr, bodyLink, bodyEmit (and bodyOut, bodyFrameRec) are staged */
 
   constexpr int T = RCSB_KT_WALK_THREADS;
   const int tid = threadIdx.x;
@@ -394,6 +408,29 @@ ktWalkKernel(const KtArgs a)
             sp[21 + i] = k.ao[i];
           }
         }
+      }
+    }
+
+    if (WB)
+    {
+      const int out = p.bodyOut[b];
+      if (out >= 0 && a.A_BI && s < a.N)
+      {
+        double* dst = a.A_BI + (s * p.hdr->nSel + out) * 12;
+        if ((reinterpret_cast<uintptr_t>(a.A_BI) & 31u) == 0)
+        {
+          storeFrame<true>(dst, k.f);
+        }
+        else
+        {
+          storeFrame<false>(dst, k.f);
+        }
+      }
+      if (p.bodyFrameRec[b])
+      {
+        const double v[12] = {k.f.o[0], k.f.o[1], k.f.o[2], k.f.R[0], k.f.R[1], k.f.R[2],
+                              k.f.R[3], k.f.R[4], k.f.R[5], k.f.R[6], k.f.R[7], k.f.R[8]};
+        w.emitN(v);
       }
     }
 
@@ -711,6 +748,113 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
     }
     __syncwarp();
+
+    /* ---- task Jacobians (whole-body plans): RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian
+     * (Rcs_kinematics.c:566, :789) from the column records (axis, origin) and the frames of the
+     * task bodies in the record; one (task, column) pair per lane and pass, the three rows of a
+     * pair leave as coalesced stores. Formulas and modes as in combineKernel (rcsb_taskjac.cu). */
+    if (a.wholeBody && a.Jt)
+    {
+      const int nJac = p.hdr->nJac;
+      double* Jg = a.Jt + s * (long) nJac * 3 * nJ;
+      for (int e = gl; e < nJac * nJ; e += LPS)
+      {
+        const int t = e / nJ, kc = e - t * nJ;
+        const int* tk = p.jacTasks + 8 * t;
+        const int kind = tk[0], mode = tk[1], u2 = tk[2], u1 = tk[3], u3 = tk[4], uA = tk[5];
+        const double* jc = scol + 7 * kc;
+        const bool isRot = p.colIsRot[kc] != 0;
+        /* column kc of body u's translation / rotation Jacobian; zero off its chain */
+        auto colT = [&](int u, double (&c)[3]) {
+          c[0] = c[1] = c[2] = 0.0;
+          if (u >= 0 && p.taskColOn[u * nJ + kc])
+          {
+            if (isRot)
+            {
+              const double* fo = buf + p.taskBodyRec[u];
+              const double d0 = fo[0] - jc[3], d1 = fo[1] - jc[4], d2 = fo[2] - jc[5];
+              c[0] = jc[1] * d2 - jc[2] * d1;
+              c[1] = jc[2] * d0 - jc[0] * d2;
+              c[2] = jc[0] * d1 - jc[1] * d0;
+            }
+            else
+            {
+              c[0] = jc[0];
+              c[1] = jc[1];
+              c[2] = jc[2];
+            }
+          }
+        };
+        auto colR = [&](int u, double (&c)[3]) {
+          c[0] = c[1] = c[2] = 0.0;
+          if (u >= 0 && isRot && p.taskColOn[u * nJ + kc])
+          {
+            c[0] = jc[0];
+            c[1] = jc[1];
+            c[2] = jc[2];
+          }
+        };
+        double v[3];
+        if (kind == 1)   /* RCSB_JAC_POS */
+        {
+          colT(u2, v);
+          if (mode == 1)
+          {
+            double j1[3];
+            colT(u1, j1);
+            v[0] -= j1[0];
+            v[1] -= j1[1];
+            v[2] -= j1[2];
+            if (u3 >= 0)
+            {
+              const double* o1 = buf + p.taskBodyRec[u1];
+              double r[3] = {-o1[0], -o1[1], -o1[2]};
+              if (u2 >= 0)
+              {
+                const double* o2 = buf + p.taskBodyRec[u2];
+                r[0] += o2[0];
+                r[1] += o2[1];
+                r[2] += o2[2];
+              }
+              double j3[3];
+              colR(u3, j3);
+              v[0] += r[1] * j3[2] - r[2] * j3[1];
+              v[1] += -r[0] * j3[2] + r[2] * j3[0];
+              v[2] += r[0] * j3[1] - r[1] * j3[0];
+            }
+          }
+        }
+        else
+        {
+          colR(u2, v);
+          if (mode == 1 && u1 >= 0)
+          {
+            double j1[3];
+            colR(u1, j1);
+            v[0] -= j1[0];
+            v[1] -= j1[1];
+            v[2] -= j1[2];
+          }
+        }
+        if (uA >= 0)
+        {
+          const double* Rm = buf + p.taskBodyRec[uA] + 3;
+          const double x = v[0], y = v[1], z = v[2];
+          v[0] = Rm[0] * x + Rm[1] * y + Rm[2] * z;
+          v[1] = Rm[3] * x + Rm[4] * y + Rm[5] * z;
+          v[2] = Rm[6] * x + Rm[7] * y + Rm[8] * z;
+        }
+        if (valid)
+        {
+          double* o = Jg + (long) t * 3 * nJ + kc;
+          o[0] = v[0];
+          o[nJ] = v[1];
+          o[2 * nJ] = v[2];
+        }
+      }
+      __syncwarp();   /* the frames are read from the record region */
+    }
+
     if (earlyFetch && s + sStep < nGroupsTotal)
     {
       fetch(s + sStep);   /* the record region is dead from here on */
@@ -933,7 +1077,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   }
 }
 
-template <bool VEL>
+template <bool VEL, bool WB>
 static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planWalkBytes +
@@ -942,7 +1086,7 @@ static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
   const dim3 grid((unsigned int) ((a.N + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS));
 #define RCSB_LAUNCH(NS)                                                                        \
   {                                                                                            \
-    auto k = ktWalkKernel<VEL, NS>;                                                            \
+    auto k = ktWalkKernel<VEL, NS, WB>;                                                            \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int) smemBytes);                                     \
     if (e != cudaSuccess)                                                                      \
@@ -1006,7 +1150,15 @@ extern "C" cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ,
     return cudaSuccess;
   }
   const bool vel = a->qd != nullptr;
-  cudaError_t e = vel ? launchWalk<true>(*a, nSlots, stream) : launchWalk<false>(*a, nSlots, stream);
+  cudaError_t e;
+  if (a->wholeBody)
+  {
+    e = vel ? launchWalk<true, true>(*a, nSlots, stream) : launchWalk<false, true>(*a, nSlots, stream);
+  }
+  else
+  {
+    e = vel ? launchWalk<true, false>(*a, nSlots, stream) : launchWalk<false, false>(*a, nSlots, stream);
+  }
   if (e != cudaSuccess)
   {
     return e;

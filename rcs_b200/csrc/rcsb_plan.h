@@ -140,7 +140,20 @@ typedef struct
                            isRot(i) | (i == k) << 1 | (7 k) << 8} */
   int pad0;
   int walkBytes;        /* leading part of the plan the walk kernel needs (header, bodyLink,
-                           bodyEmit); multiple of 16 */
+                           bodyEmit, bodyOut, bodyFrameRec); multiple of 16 */
+  /* whole-body plans (rcsb_wholebody): the walk also writes the frames of the selected bodies
+   * (A_BI, like fkKernel) and puts the frames of the bodies the task Jacobians refer to into the
+   * record; the assembly kernel builds the task rows from them and the column records. */
+  int wholeBody;        /* 1: the tables below are present */
+  int nSel;             /* frames written per state */
+  int nTaskBodies;      /* bodies referred to by the tasks (slots u) */
+  int nJac;             /* task Jacobians (3 rows each) */
+  int offBodyOut;       /* int[nb]: A_BI output slot of the body, -1 = not selected        (walk part) */
+  int offBodyFrameRec;  /* int[nb]: 1 if the walk emits the body's frame into the record  (walk part) */
+  int offTaskBodyRec;   /* int[nTaskBodies]: record offset of the frame of task body u */
+  int offJacTasks;      /* int[nJac][8]: {kind, mode, u2, u1, u3, uA, 0, 0}, see rcsb_taskjac.cu */
+  int offTaskColOn;     /* unsigned char[nTaskBodies * nJ]: 1 if column k moves task body u */
+  int pad1[3];
 } RcsbKtPlanHeader;
 
 typedef struct

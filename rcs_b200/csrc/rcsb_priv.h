@@ -57,6 +57,7 @@ struct RcsbModel
   std::map<std::string, rcsbhost::DevicePlan> fkPlans;
   std::map<std::string, rcsbhost::DevicePlan> ikPlans;
   rcsbhost::DevicePlan ktPlan;
+  std::map<std::string, rcsbhost::DevicePlan> wbPlans;   /* whole-body variants of the kinetic-terms plan */
   bool ktPlanBuilt = false;
   double* ktScratch[2] = {nullptr, nullptr};
   size_t ktScratchDoubles[2] = {0, 0};
@@ -144,6 +145,34 @@ int fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, const doubl
 
 int fkCompactDevice(RcsbModel* m, long n, int qdim, const double* q, int G, const int* bodies,
                     double* A, double* JT, double* JR, cudaStream_t stream, int* recCols);
+
+/* body selection and task list of a whole-body variant of the kinetic-terms plan */
+struct WbSpec
+{
+  int nSel = 0;                    /* 0: all bodies */
+  const int* bodySel = nullptr;
+  std::vector<int> taskBodies;     /* body of slot u */
+  std::vector<int> jacTasks;       /* 8 ints per task Jacobian: kind, mode, u2, u1, u3, uA, 0, 0 */
+  std::string key;
+};
+
+/* optional inputs / outputs of one pass of the kinetic-terms kernels */
+struct KtExtra
+{
+  double* cog = nullptr;
+  double* Jcog = nullptr;
+  const double* Fext = nullptr;
+  const double* Fjnt = nullptr;
+  double* qdd = nullptr;
+  /* whole-body plans */
+  const DevicePlan* plan = nullptr;   /* nullptr: the model's kinetic-terms plan */
+  double* A_BI = nullptr;
+  double* Jt = nullptr;
+};
+
+int buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out);
+int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
+             double* h, double* Fg, double* E, const KtExtra& x, cudaStream_t stream, int ws);
 
 }   // namespace rcsbhost
 
