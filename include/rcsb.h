@@ -257,6 +257,42 @@ int rcsb_ik_rmr_ex(const RcsbModel* model, int nTasks, const RcsbTask* tasks, lo
  */
 int rcsb_summary_stats(const double* x, long n, long stride, double* out5, void* stream);
 
+/* ---- device groups: the GPUs of one node behind one handle ------------------------------ */
+
+/*
+ * States are independent and the model is replicated, so a batch is cut into contiguous slices,
+ * one per device (slice r = [first, first + count) of rcsb_group_slice: sizes differ by at most one
+ * state), each evaluated by the kernels of the single-device entry points on its own stream and
+ * host thread. All array arguments of the group calls are HOST pointers of the WHOLE batch (pinned
+ * memory from rcsb_host_alloc is fastest); the library moves every slice to its device and the
+ * results back. The path has no data-path collective; its one exchange is an NCCL all-gather,
+ * between the devices, of per-rank summary statistics {count, sum, sum of squares, min, max} of a
+ * per-state result (named with each call). `stats` (may be NULL) receives the gathered
+ * [nDevices x 5] table. `devices` = NULL means devices 0 .. nDevices-1. NCCL is loaded at run
+ * time (libnccl.so.2); a group of one device does not need it.
+ */
+typedef struct RcsbGroup RcsbGroup;
+int rcsb_group_create(const RcsGraph* graph, int nDevices, const int* devices, RcsbGroup** group);
+void rcsb_group_destroy(RcsbGroup* group);
+int rcsb_group_size(const RcsbGroup* group);
+void rcsb_group_slice(const RcsbGroup* group, long N, int rank, long* first, long* count);
+/* rcsb_fk_jacobians_mass over the group; statistics: world z of the first selected frame */
+int rcsb_group_fk_jacobians_mass(RcsbGroup* group, long N, int qdim, const double* q, int nSel,
+                                 const int* bodySel, double* A_BI, int nEff, const int* effBody,
+                                 const double* effPt, double* JT, double* JR, double* M, double* stats);
+/* rcsb_kinetic_terms over the group; statistics: total energy E (needs E) */
+int rcsb_group_kinetic_terms(RcsbGroup* group, long N, int qdim, const double* q, const double* qd,
+                             double* M, double* h, double* Fg, double* E, double* stats);
+/* rcsb_ik_rmr over the group (the 4M-target strong-scaling case of BASELINE.json configs[3]);
+ * statistics: determinant of the last step */
+int rcsb_group_ik_rmr(RcsbGroup* group, int nTasks, const RcsbTask* tasks, long N, double* q,
+                      const double* xDes, double lambda, double alpha, int iters, double* dx, double* dq,
+                      double* det, double* stats);
+/* rcsb_wholebody over the group (configs[4]); statistics: M[0][0] (needs M) */
+int rcsb_group_wholebody(RcsbGroup* group, long N, int qdim, const double* q, int nSel,
+                         const int* bodySel, double* A_BI, int nJac, const RcsbRelJac* jac, double* J,
+                         double* M, double* Jcog, double* stats);
+
 /* ---- utilities -------------------------------------------------------------------------- */
 
 const char* rcsb_last_error(void);

@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     BLEND_BINARY,
     BLEND_LINEAR,
     Graph,
+    Group,
     Model,
     RcsbError,
     TASK_ABC,
@@ -29,6 +30,7 @@ __all__ = [
     "BLEND_BINARY",
     "BLEND_LINEAR",
     "Graph",
+    "Group",
     "Model",
     "RcsbError",
     "TASK_ABC",

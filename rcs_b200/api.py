@@ -134,6 +134,18 @@ def lib() -> ctypes.CDLL:
     sig("rcsb_ik_rmr_ex", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_void, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
+    sig("rcsb_group_create", c_int, c_void, c_int, c_void, ctypes.POINTER(c_void))
+    sig("rcsb_group_destroy", None, c_void)
+    sig("rcsb_group_size", c_int, c_void)
+    sig("rcsb_group_slice", None, c_void, c_long, c_int, ctypes.POINTER(c_long), ctypes.POINTER(c_long))
+    sig("rcsb_group_fk_jacobians_mass", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p, c_int,
+        c_void, c_void, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p)
+    sig("rcsb_group_kinetic_terms", c_int, c_void, c_long, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+        c_dbl_p, c_dbl_p)
+    sig("rcsb_group_ik_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
+        ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p)
+    sig("rcsb_group_wholebody", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p, c_int, c_void,
+        c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p)
     sig("rcsb_wholebody", c_int, c_void, c_long, c_int, c_dbl_p, c_int, c_void, c_dbl_p, c_int, c_void,
         c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_bind_host_to_device", c_int, c_int, ctypes.c_char_p, ctypes.c_size_t)
@@ -578,3 +590,92 @@ class Model:
         )
         _err(rc, "rcsb_ik_rmr")
         return out
+
+
+def _host_ptr(x, name):
+    """Pointer of a host array of a group call: C-contiguous float64 numpy array or CPU tensor."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+
+        if x.is_cuda or x.dtype != torch.float64 or not x.is_contiguous():
+            raise RcsbError(f"{name}: need a contiguous float64 host tensor")
+        return ctypes.c_void_p(x.data_ptr())
+    if not isinstance(x, np.ndarray) or x.dtype != np.float64 or not x.flags["C_CONTIGUOUS"]:
+        raise RcsbError(f"{name}: need a C-contiguous float64 numpy array")
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+class Group:
+    """rcsb_group_*: the GPUs of one node behind one handle (single process). Host arrays of the
+    whole batch in, results and the gathered per-rank statistics [n_devices x 5] out."""
+
+    def __init__(self, graph: Graph, devices: Sequence[int]):
+        devs = list(devices)
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = ctypes.c_void_p()
+        _err(lib().rcsb_group_create(graph.handle, len(devs), arr, ctypes.byref(h)), "rcsb_group_create")
+        self._h = h
+        self.devices = devs
+        self.dof, self.nJ, self.n_bodies = graph.dof, graph.nJ, graph.n_bodies
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.rcsb_group_destroy(h)
+            self._h = None
+
+    def slice_of(self, rank: int, n: int):
+        first, count = ctypes.c_long(), ctypes.c_long()
+        lib().rcsb_group_slice(self._h, n, rank, ctypes.byref(first), ctypes.byref(count))
+        return first.value, count.value
+
+    def _stats(self):
+        return np.empty((len(self.devices), 5))
+
+    def fk_jacobians(self, q, effectors: Sequence[int], out: Dict):
+        """out: dict of host arrays among A_BI, JT, JR, M (whole batch)."""
+        N, qdim = int(q.shape[0]), int(q.shape[1])
+        eff, ne = _int_array(effectors)
+        st = self._stats()
+        rc = lib().rcsb_group_fk_jacobians_mass(
+            self._h, N, qdim, _host_ptr(q, "q"), 0, None, _host_ptr(out.get("A_BI"), "A_BI"), ne, eff, None,
+            _host_ptr(out.get("JT"), "JT"), _host_ptr(out.get("JR"), "JR"), _host_ptr(out.get("M"), "M"),
+            _host_ptr(st, "stats"))
+        _err(rc, "rcsb_group_fk_jacobians_mass")
+        return st
+
+    def kinetic_terms(self, q, qd, out: Dict):
+        N, qdim = int(q.shape[0]), int(q.shape[1])
+        st = self._stats()
+        rc = lib().rcsb_group_kinetic_terms(
+            self._h, N, qdim, _host_ptr(q, "q"), _host_ptr(qd, "qd"), _host_ptr(out.get("M"), "M"),
+            _host_ptr(out.get("h"), "h"), _host_ptr(out.get("Fg"), "Fg"), _host_ptr(out.get("E"), "E"),
+            _host_ptr(st, "stats"))
+        _err(rc, "rcsb_group_kinetic_terms")
+        return st
+
+    def ik_rmr(self, tasks: Sequence, q, x_des, out: Dict, lam=1.0e-8, alpha=0.05, iters=1):
+        N = int(q.shape[0])
+        tarr = (_RcsbTask * max(len(tasks), 1))(*[_RcsbTask(int(k), int(e)) for k, e in tasks])
+        st = self._stats()
+        rc = lib().rcsb_group_ik_rmr(
+            self._h, len(tasks), tarr, N, _host_ptr(q, "q"), _host_ptr(x_des, "x_des"), float(lam), float(alpha),
+            int(iters), _host_ptr(out.get("dx"), "dx"), _host_ptr(out.get("dq"), "dq"),
+            _host_ptr(out.get("det"), "det"), _host_ptr(st, "stats"))
+        _err(rc, "rcsb_group_ik_rmr")
+        return st
+
+    def wholebody(self, q, spec, out: Dict):
+        N, qdim = int(q.shape[0]), int(q.shape[1])
+        arr = (_RcsbRelJac * max(len(spec), 1))(
+            *[_RcsbRelJac(1 if k == "POS" else 2, int(e), int(rb), int(rf)) for k, e, rb, rf in spec])
+        st = self._stats()
+        has_j = out.get("Jt") is not None
+        rc = lib().rcsb_group_wholebody(
+            self._h, N, qdim, _host_ptr(q, "q"), 0, None, _host_ptr(out.get("A_BI"), "A_BI"),
+            len(spec) if has_j else 0, arr if has_j else None, _host_ptr(out.get("Jt"), "Jt"),
+            _host_ptr(out.get("M"), "M"), _host_ptr(out.get("Jcog"), "Jcog"), _host_ptr(st, "stats"))
+        _err(rc, "rcsb_group_wholebody")
+        return st
