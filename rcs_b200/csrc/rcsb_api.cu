@@ -209,7 +209,9 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   if (nEff > 0)
   {
     key.append(reinterpret_cast<const char*>(effBody), sizeof(int) * nEff);
-    if (effPt)
+    /* up to RCSB_FK_INLINE_PTS effector points are kernel arguments (FkArgs::effPtArg): the plan
+     * depends on the topology of the query only. Larger point sets are part of the plan. */
+    if (effPt && nEff > RCSB_FK_INLINE_PTS)
     {
       key.append(reinterpret_cast<const char*>(effPt), sizeof(double) * 3 * nEff);
     }
@@ -221,6 +223,27 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   {
     *out = &it->second;
     return RCSB_OK;
+  }
+  /* plans that carry their points (more than RCSB_FK_INLINE_PTS effectors with explicit points)
+   * are bounded: beyond 64 of them the oldest ones are released once the device is idle */
+  if (effPt && nEff > RCSB_FK_INLINE_PTS)
+  {
+    m->fkPointPlanKeys.push_back(key);
+    if (m->fkPointPlanKeys.size() > 64)
+    {
+      RCSB_CUDA(cudaSetDevice(m->device));
+      RCSB_CUDA(cudaDeviceSynchronize());
+      while (m->fkPointPlanKeys.size() > 32)
+      {
+        auto old = m->fkPlans.find(m->fkPointPlanKeys.front());
+        if (old != m->fkPlans.end())
+        {
+          cudaFree(old->second.dev);
+          m->fkPlans.erase(old);
+        }
+        m->fkPointPlanKeys.erase(m->fkPointPlanKeys.begin());
+      }
+    }
   }
 
   const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
@@ -591,7 +614,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   memcpy(blob.data() + ph.offJntScr, jntScr.data(), dof * 4);
   memcpy(blob.data() + ph.offBodyEffStart, effStart.data(), (nb + 1) * 4);
   memcpy(blob.data() + ph.offBodyEffList, effList.data(), effList.size() * 4);
-  if (nEff > 0 && effPt)
+  if (nEff > RCSB_FK_INLINE_PTS && effPt)
   {
     memcpy(blob.data() + ph.offEffPt, effPt, sizeof(double) * 3 * nEff);
   }
@@ -624,9 +647,19 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
 int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const double* q,
              const double* qd, double* A_BI, double* A_JI, double* xdot, double* omega,
              double* qOut, double* JT, double* JR, double* qdOut, bool noCoupling, double* M,
-             cudaStream_t stream)
+             cudaStream_t stream, const double* effPt = nullptr)
 {
   rcsb::FkArgs a;
+  a.effPtInline = 0;
+  if (plan->nEff > 0 && plan->nEff <= RCSB_FK_INLINE_PTS)
+  {
+    a.effPtInline = 1;
+    memset(a.effPtArg, 0, sizeof(a.effPtArg));
+    if (effPt)
+    {
+      memcpy(a.effPtArg, effPt, sizeof(double) * 3 * (size_t) plan->nEff);
+    }
+  }
   a.model = m->dev;
   a.plan = plan->dev;
   a.modelBytes = m->hdr.totalBytes;
@@ -652,11 +685,12 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   a.pruned = (plan->aux1 > 0 && !A_JI && !qOut && !qd && !qdOut && !M) ? 1 : 0;
   a.scrDoubles = plan->nScrRows * (RCSB_FK_BLOCK(M != nullptr) + 1);
   RCSB_CUDA(cudaSetDevice(m->device));
-  if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows) > RCSB_SMEM_LIMIT)
+  if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows, M != nullptr, qd != nullptr) > RCSB_SMEM_LIMIT)
   {
     rcsb_set_error("forward kinematics: the effectors' joint chains need %zu bytes of shared memory "
                    "(limit %d); ask for fewer effectors per call",
-                   rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows), RCSB_SMEM_LIMIT);
+                   rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows, M != nullptr, qd != nullptr),
+                   RCSB_SMEM_LIMIT);
     return RCSB_EUNSUPPORTED;
   }
   RCSB_CUDA(rcsb_launch_fk(&a, a.pruned ? plan->aux1 - 1 : m->hdr.nSlots, plan->nScrRows, stream));
@@ -908,7 +942,7 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
   if (!(flags & RCSB_HOST_PTRS))
   {
     return fkDevice(m, plan, N, qdim, q, qd, A_BI, A_JI, xdot, omega, qOut, JT, JR, qdOut,
-                    noCoupling, M, static_cast<cudaStream_t>(stream));
+                    noCoupling, M, static_cast<cudaStream_t>(stream), effPt);
   }
 
   const size_t dof = (size_t) m->hdr.dof, nOut = (size_t) plan->nSel;
@@ -931,7 +965,7 @@ int rcsbhost::fkCommon(const RcsbModel* cm, long N, int qdim, const double* q, c
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
     return fkDevice(m, plan, n, qdim, dv(I_Q, q), dv(I_QD, qd), dv(I_A, A_BI), dv(I_AJ, A_JI),
                     dv(I_XD, xdot), dv(I_OM, omega), dv(I_QO, qOut), dv(I_JT, JT), dv(I_JR, JR),
-                    dv(I_QDO, qdOut), noCoupling, dv(I_M, M), st);
+                    dv(I_QDO, qdOut), noCoupling, dv(I_M, M), st, effPt);
   });
 }
 

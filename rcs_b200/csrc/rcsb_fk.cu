@@ -572,7 +572,7 @@ fkKernel(const FkArgs a)
     for (int k = p.bodyEffStart[b]; k < p.bodyEffStart[b + 1]; ++k)
     {
       const int e = p.bodyEffList[k];
-      const double* pt = p.effPt + 3 * e;
+      const double* pt = a.effPtInline ? a.effPtArg + 3 * e : p.effPt + 3 * e;
       double* col = scr + (6 * nChain + 3 * e) * scrStride + tid;
       col[0] = f.o[0] + (f.R[0] * pt[0] + f.R[3] * pt[1] + f.R[6] * pt[2]);
       col[scrStride] = f.o[1] + (f.R[1] * pt[0] + f.R[4] * pt[1] + f.R[7] * pt[2]);

@@ -44,7 +44,13 @@ struct FkArgs
   int pruned;          /* 1: walk the plan's sub-tree only (body selections without velocities) */
   int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
   int scrDoubles;      /* doubles of the Jacobian scratch: nScrRows x (RCSB_FK_THREADS + 1) */
+  /* body-fixed points of up to RCSB_FK_INLINE_PTS effectors travel with the launch, not with the
+   * cached plan: a control loop that moves its points (RcsGraph_worldPointJacobian) neither
+   * rebuilds nor accumulates plans */
+  int effPtInline;     /* 1: take the points from effPtArg */
+  double effPtArg[3 * 8];
 };
+#define RCSB_FK_INLINE_PTS 8
 
 struct KtArgs
 {

@@ -55,6 +55,7 @@ struct RcsbModel
   RcsbFlatHeader hdr;
   std::recursive_mutex mtx;               /* guards the plan caches, workspaces and the staging pipe */
   std::map<std::string, rcsbhost::DevicePlan> fkPlans;
+  std::vector<std::string> fkPointPlanKeys;   /* FK plans that carry effector points, oldest first (bounded) */
   std::map<std::string, rcsbhost::DevicePlan> ikPlans;
   rcsbhost::DevicePlan ktPlan;
   std::map<std::string, rcsbhost::DevicePlan> wbPlans;   /* whole-body variants of the kinetic-terms plan */
@@ -108,10 +109,12 @@ int checkModel(const RcsbModel* m, long N, int qdim, const double* q);
 
 /* dynamic shared memory of one fkKernel block: model + plan + Jacobian scratch */
 #define RCSB_SMEM_LIMIT (227 * 1024)
-inline size_t fkSharedBytes(const RcsbModel* m, int planBytes, int nScrRows)
+inline size_t fkSharedBytes(const RcsbModel* m, int planBytes, int nScrRows, bool withMass = false,
+                            bool withVelocity = false)
 {
-  return (size_t) m->hdr.totalBytes + (size_t) planBytes +
-         (size_t) nScrRows * (RCSB_FK_THREADS + 1) * sizeof(double);
+  const size_t threads = (size_t) RCSB_FK_BLOCK(withMass);
+  return (size_t) m->hdr.totalBytes + (size_t) planBytes + (size_t) nScrRows * (threads + 1) * sizeof(double) +
+         (withVelocity ? (threads / 32) * 2 * 32 * 33 * sizeof(double) : 0) + 16 /* staging mbarrier */;
 }
 
 /* One array of a staged (host-pointer) call: `perState` doubles per state; exactly one of
