@@ -741,6 +741,67 @@ def measure_ours(name: str, args, ctx: Ctx, cpu_seconds: float = 4.0):
     return line
 
 
+def measure_group_abi(args, ctx: Ctx):
+    """The same workloads through the device-group entry points of the C ABI (rcsb_group_*): ONE
+    process (rank 0) drives all N GPUs with host arrays of the whole batch; the library slices,
+    runs one host thread + stream + model per device and all-gathers the per-rank statistics over
+    NCCL itself. End to end by construction (host buffers in, results back). The other ranks wait
+    on the CPU meanwhile."""
+    import rcs_b200
+    from rcs_b200 import TASK_ABC, TASK_XYZ, workload
+
+    torch = ctx.torch
+    world = ctx.world
+    out = {"devices": world, "api": "rcsb_group_fk_jacobians_mass / rcsb_group_ik_rmr (include/rcsb.h)"}
+    steps = max(2, min(args.steps, 4))
+
+    # fkm: 1M states per device
+    g = rcs_b200.Graph(Workload("fkm", world).graph_file)
+    grp = rcs_b200.Group(g, list(range(world)))
+    n = (1 << 20) * world
+    tip = g.body_index("BallTip")
+    q = rcs_b200.pinned_empty((n, g.dof))
+    q.copy_(torch.from_numpy(workload.sample_states(g.layout(), n)))
+    res = {"A_BI": rcs_b200.pinned_empty((n, g.n_bodies, 12)), "JT": rcs_b200.pinned_empty((n, 1, 3, g.nJ)),
+           "JR": rcs_b200.pinned_empty((n, 1, 3, g.nJ)), "M": rcs_b200.pinned_empty((n, g.nJ, g.nJ))}
+    grp.fk_jacobians(q, [tip], res)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st = grp.fk_jacobians(q, [tip], res)
+    dt = time.perf_counter() - t0
+    bytes_per_state = 8 * (g.dof + g.n_bodies * 12 + 6 * g.nJ + g.nJ * g.nJ)
+    out["fkm"] = {"value": n * steps / dt, "unit": "states/s", "units_per_step": n, "steps": steps,
+                  "host_gbs_total": n * steps * bytes_per_state / dt / 1e9,
+                  "gathered_stats_counts": [float(x) for x in st[:, 0]]}
+    del res, q
+
+    # ik: 4M targets in total (strong scaling)
+    n = 1 << 22
+    m0 = rcs_b200.Model(g, ctx.local)
+    lay = g.layout()
+
+    def gpu_frames(qa):
+        return m0.fk(torch.from_numpy(qa).to(ctx.dev), bodies=[tip])["A_BI"][:, 0].cpu().numpy()
+
+    q_start, x_des = ik_inputs(lay, gpu_frames, 0, n, g.dof, tip)
+    hq0, hq, hx = rcs_b200.pinned_empty((n, g.dof)), rcs_b200.pinned_empty((n, g.dof)), rcs_b200.pinned_empty((n, 6))
+    hq0.copy_(torch.from_numpy(q_start))
+    hx.copy_(torch.from_numpy(x_des))
+    o = {"det": rcs_b200.pinned_empty((n,))}
+    tasks = [(TASK_XYZ, tip), (TASK_ABC, tip)]
+    hq.copy_(hq0)
+    grp.ik_rmr(tasks, hq, hx, o, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS)
+    secs = 0.0
+    for _ in range(steps):
+        hq.copy_(hq0)
+        t0 = time.perf_counter()
+        st = grp.ik_rmr(tasks, hq, hx, o, lam=IK_LAMBDA, alpha=IK_ALPHA, iters=IK_ITERS)
+        secs += time.perf_counter() - t0
+    out["ik"] = {"value": n * steps / secs, "unit": "solves/s", "units_per_step": n, "steps": steps,
+                 "gathered_stats_counts": [float(x) for x in st[:, 0]]}
+    return out
+
+
 def run_ours(args):
     ctx = Ctx()
     line = measure_ours(args.workload, args, ctx)
@@ -748,6 +809,20 @@ def run_ours(args):
     if args.workload == "fkm" and not args.no_secondary:
         for name in SECONDARY:
             secondary[name] = measure_ours(name, args, ctx, cpu_seconds=2.0)
+        # device groups of the C ABI: rank 0 alone drives every GPU; the other ranks wait on the
+        # CPU (a gloo barrier: no kernel of theirs spins on the GPUs rank 0 is using)
+        cpu_group = ctx.dist.new_group(backend="gloo") if ctx.world > 1 else None
+        ctx.torch.cuda.synchronize()
+        group_rec = None
+        if ctx.rank == 0:
+            try:
+                group_rec = measure_group_abi(args, ctx)
+            except Exception as e:      # the headline must not depend on this record
+                group_rec = {"error": f"{type(e).__name__}: {e}"}
+        if cpu_group is not None:
+            ctx.dist.barrier(group=cpu_group)
+        if group_rec is not None:
+            secondary["group_abi"] = group_rec
     if ctx.rank == 0:
         if secondary:
             line["secondary"] = secondary

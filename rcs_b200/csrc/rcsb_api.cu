@@ -852,7 +852,8 @@ extern "C" void rcsb_model_destroy(RcsbModel* m)
   {
     cudaFree(kv.second.dev);
   }
-  cudaFree(m->ktPlan.dev);
+  cudaFree(m->ktPlan[0].dev);
+  cudaFree(m->ktPlan[1].dev);
   for (auto& kv : m->wbPlans)
   {
     cudaFree(kv.second.dev);

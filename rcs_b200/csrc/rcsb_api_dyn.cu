@@ -8,12 +8,13 @@ using namespace rcsbhost;
 
 /* ---- kinetic-terms plan ------------------------------------------------------------------- */
 
-int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
+int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, bool vel, DevicePlan** out)
 {
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
-  if (!wb && m->ktPlanBuilt)
+  const int LREC = RCSB_KT_LINK_REC_N(vel), CREC = RCSB_KT_COL_REC_N(vel);
+  if (!wb && m->ktPlanBuilt[vel ? 1 : 0])
   {
-    *out = &m->ktPlan;
+    *out = &m->ktPlan[vel ? 1 : 0];
     return RCSB_OK;
   }
   if (wb)
@@ -149,7 +150,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
           bodyEmit[b] = 1;
           runLink.push_back(cur);
           runRec.push_back(rec);
-          rec += RCSB_KT_LINK_REC;
+          rec += LREC;
         }
         cur = bodyLink[b];
       }
@@ -158,7 +159,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
         if (jntJacobi[j] >= 0)
         {
           colRec[jntJacobi[j]] = rec;
-          rec += RCSB_KT_COL_REC;
+          rec += CREC;
         }
       }
       if (bodyFrameRec[(size_t) b])
@@ -178,7 +179,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
       bodyEmit[nb] = 1;
       runLink.push_back(cur);
       runRec.push_back(rec);
-      rec += RCSB_KT_LINK_REC;
+      rec += LREC;
     }
   }
   const int nRuns = (int) runLink.size();
@@ -210,21 +211,6 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
     colHome[k] = linkHome[colLink[k]];
   }
 
-  /* structurally non-zero entries of the upper triangle: (ancestor column i, column k) */
-  std::vector<int> pairs;
-  for (int k = 0; k < nJ; ++k)
-  {
-    for (int i = 0; i <= k; ++i)
-    {
-      if (rel[(size_t) i * nJ + k] == 1)
-      {
-        pairs.push_back(7 * i);
-        pairs.push_back(9 * k);
-        pairs.push_back((i * nJ + k) | ((k * nJ + i) << 16));
-        pairs.push_back((colIsRot[i] ? 1 : 0) | (i == k ? 2 : 0) | ((7 * k) << 8));
-      }
-    }
-  }
   bool symmetric = true;
   {
     const double* I = m->darr(RCSB_A_BODY_INERTIA);
@@ -232,6 +218,68 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
     {
       symmetric = symmetric && I[9 * b + 1] == I[9 * b + 3] && I[9 * b + 2] == I[9 * b + 6] &&
                   I[9 * b + 5] == I[9 * b + 7];
+    }
+  }
+  /* structurally non-zero entries of the upper triangle: (ancestor column i, column k) */
+  std::vector<int> pairs;
+  const int fStride = RCSB_KT_F_STRIDE(symmetric ? 1 : 0);
+  for (int k = 0; k < nJ; ++k)
+  {
+    for (int i = 0; i <= k; ++i)
+    {
+      if (rel[(size_t) i * nJ + k] == 1)
+      {
+        pairs.push_back(RCSB_KT_S_STRIDE * i);
+        pairs.push_back(fStride * k);
+        pairs.push_back((i * nJ + k) | ((k * nJ + i) << 16));
+        pairs.push_back((i == k ? 2 : 0) | ((RCSB_KT_S_STRIDE * k) << 8));
+      }
+    }
+  }
+  /* links without a parent link: their composites add up to the whole mechanism (centre of gravity) */
+  std::vector<int> rootLinks;
+  for (int l = 0; l < nLinks; ++l)
+  {
+    if (linkParent[(size_t) l] < 0)
+    {
+      rootLinks.push_back(linkHome[(size_t) l]);
+    }
+  }
+  /* whole-body plans: the (task Jacobian, column) pairs that are not structurally zero */
+  std::vector<int> jacEntries;
+  if (wb)
+  {
+    const int nJacT = (int) wb->jacTasks.size() / 8;
+    for (int t = 0; t < nJacT; ++t)
+    {
+      const int* tk = wb->jacTasks.data() + 8 * t;
+      const int kind = tk[0], mode = tk[1], u2 = tk[2], u1 = tk[3], u3 = tk[4];
+      for (int k = 0; k < nJ; ++k)
+      {
+        auto on = [&](int u) { return u >= 0 && taskColOn[(size_t) u * nJ + (size_t) k] != 0; };
+        const bool rot = colIsRot[k] != 0;
+        int o2 = 0, o1 = 0, o3 = 0;
+        if (kind == RCSB_JAC_POS)
+        {
+          o2 = on(u2) ? 1 : 0;
+          o1 = (mode == 1 && on(u1)) ? 1 : 0;
+          o3 = (mode == 1 && u3 >= 0 && rot && on(u3)) ? 1 : 0;
+        }
+        else
+        {
+          o2 = (rot && on(u2)) ? 1 : 0;
+          o1 = (mode == 1 && u1 >= 0 && rot && on(u1)) ? 1 : 0;
+        }
+        if (o2 || o1 || o3)
+        {
+          jacEntries.push_back(k | (t << 8) | (o2 << 16) | (o1 << 17) | (o3 << 18));
+        }
+      }
+    }
+    if (nJ > 255 || nJacT > 255)
+    {
+      rcsb_set_error("rcsb_wholebody: too many columns / task Jacobians (%d, %d; limit 255)", nJ, nJacT);
+      return RCSB_EUNSUPPORTED;
     }
   }
 
@@ -242,6 +290,9 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
   ph.nRuns = nRuns;
   ph.nPairs = (int) pairs.size() / 4;
   ph.symmetric = symmetric ? 1 : 0;
+  ph.vel = vel ? 1 : 0;
+  ph.nRoots = (int) rootLinks.size();
+  ph.nJacEntries = (int) jacEntries.size();
   ph.recV = rec;
   ph.recDoubles = recDoubles;
   ph.nExtraRuns = (int) extraRuns.size() / 2;
@@ -279,6 +330,8 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
   place(ph.offLinkHome, linkHome.size() * 4);
   place(ph.offExtraRuns, extraRuns.size() * 4);
   place(ph.offColHome, colHome.size() * 4);
+  place(ph.offRootLinks, rootLinks.size() * 4);
+  place(ph.offJacEntries, jacEntries.size() * 4);
   ph.totalBytes = off;
 
   std::vector<char> blob((size_t) ph.totalBytes, 0);
@@ -302,6 +355,8 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
   put(ph.offLinkHome, linkHome.data(), linkHome.size() * 4);
   put(ph.offExtraRuns, extraRuns.data(), extraRuns.size() * 4);
   put(ph.offColHome, colHome.data(), colHome.size() * 4);
+  put(ph.offRootLinks, rootLinks.data(), rootLinks.size() * 4);
+  put(ph.offJacEntries, jacEntries.data(), jacEntries.size() * 4);
   if (wb)
   {
     put(ph.offBodyOut, bodyOut.data(), (size_t) nb * 4);
@@ -323,6 +378,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
   dp.nScrRows = ph.walkBytes;
   dp.nSel = nSelOut;
   dp.nEff = ph.nJac;
+  dp.aux2 = ph.symmetric;
   if (wb)
   {
     auto ins = m->wbPlans.emplace(wb->key, dp);
@@ -330,9 +386,9 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out)
   }
   else
   {
-    m->ktPlan = dp;
-    m->ktPlanBuilt = true;
-    *out = &m->ktPlan;
+    m->ktPlan[vel ? 1 : 0] = dp;
+    m->ktPlanBuilt[vel ? 1 : 0] = true;
+    *out = &m->ktPlan[vel ? 1 : 0];
   }
   return RCSB_OK;
 }
@@ -365,7 +421,7 @@ int rcsbhost::ktDevice(RcsbModel* m, long N, int qdim, const double* q, const do
 {
   double* cog = x.cog;
   double* Jcog = x.Jcog;
-  const DevicePlan& plan = x.plan ? *x.plan : m->ktPlan;
+  const DevicePlan& plan = x.plan ? *x.plan : m->ktPlan[qd ? 1 : 0];
   const int recDoubles = plan.aux0;
   const long chunk = ktChunk(m, recDoubles) < N ? ktChunk(m, recDoubles) : N;
   const size_t need = (size_t) chunk * (size_t) recDoubles;
@@ -398,6 +454,7 @@ int rcsbhost::ktDevice(RcsbModel* m, long N, int qdim, const double* q, const do
     a.planBytes = plan.bytes;
     a.planWalkBytes = plan.nScrRows;
     a.wholeBody = x.plan ? 1 : 0;
+    a.symmetric = plan.aux2;
     a.A_BI = x.A_BI ? x.A_BI + s0 * (long) plan.nSel * 12 : nullptr;
     a.Jt = x.Jt ? x.Jt + s0 * (long) plan.nEff * 3 * nJ : nullptr;
     a.N = n;
@@ -433,7 +490,7 @@ static int ktCommon(const RcsbModel* cm, long N, int qdim, const double* q, cons
     return rc;
   }
   DevicePlan* basePlan = nullptr;
-  rc = buildKtPlan(m, nullptr, &basePlan);
+  rc = buildKtPlan(m, nullptr, qd != nullptr, &basePlan);
   if (rc != RCSB_OK || N == 0)
   {
     return rc;

@@ -79,6 +79,7 @@ struct KtArgs
   double* A_BI;        /* N x nSel x 12 frames of the selected bodies (written by the walk) */
   double* Jt;          /* N x nJac x 3 x nJ task Jacobians (written by the assembly) */
   int wholeBody;       /* 1: the plan is a whole-body plan */
+  int symmetric;       /* plan header's `symmetric` (shared-memory layout of the assembly kernel) */
 };
 
 struct IkArgs

@@ -67,6 +67,8 @@ struct KtPlanView
   const int* taskBodyRec;
   const int* jacTasks;
   const unsigned char* taskColOn;
+  const int* rootLinks;
+  const int* jacEntries;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -89,6 +91,8 @@ struct KtPlanView
     taskBodyRec = reinterpret_cast<const int*>(blob + hdr->offTaskBodyRec);
     jacTasks = reinterpret_cast<const int*>(blob + hdr->offJacTasks);
     taskColOn = reinterpret_cast<const unsigned char*>(blob + hdr->offTaskColOn);
+    rootLinks = reinterpret_cast<const int*>(blob + hdr->offRootLinks);
+    jacEntries = reinterpret_cast<const int*>(blob + hdr->offJacEntries);
   }
 };
 
@@ -116,17 +120,12 @@ __device__ __forceinline__ void addOffsetAccel(Kin& k, const double d[3])
   }
 }
 
-/* <motion axis of a joint, momentum (p, L)>: rot: a . (L - o x p), trans: a . p */
-__device__ __forceinline__ double pairing(bool isRot, const double a[3], const double o[3],
-                                          const double p[3], const double L[3])
+/* <spatial axis of a joint (w, v), momentum (p, L) about the world origin> = w . L + v . p
+ * (rotation about a through o: w = a, v = o x a, i.e. a . (L - o x p); translation along a: w = 0,
+ * v = a, i.e. a . p) */
+__device__ __forceinline__ double pairing(const double* __restrict__ sj, const double p[3], const double L[3])
 {
-  if (isRot)
-  {
-    double t[3];
-    cross3(t, o, p);
-    return a[0] * (L[0] - t[0]) + a[1] * (L[1] - t[1]) + a[2] * (L[2] - t[2]);
-  }
-  return a[0] * p[0] + a[1] * p[1] + a[2] * p[2];
+  return (sj[0] * L[0] + sj[1] * L[1] + sj[2] * L[2]) + (sj[3] * p[0] + sj[4] * p[1] + sj[5] * p[2]);
 }
 
 
@@ -155,6 +154,7 @@ ktWalkKernel(const KtArgs a)
   p.bind(sPlan);   /* only hdr, bodyLink, bodyEmit (and bodyOut, bodyFrameRec) are staged */
 
   constexpr int T = RCSB_KT_WALK_THREADS;
+  constexpr int LREC = RCSB_KT_LINK_REC_N(VEL), CREC = RCSB_KT_COL_REC_N(VEL);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int nb = m.hdr->nb;
@@ -188,14 +188,14 @@ ktWalkKernel(const KtArgs a)
   /* mass properties of the bodies visited since the last emit (all of one link) */
   double* acc = sAcc + tid;
 #pragma unroll
-  for (int i = 0; i < RCSB_KT_LINK_REC; ++i)
+  for (int i = 0; i < LREC; ++i)
   {
     acc[i * T] = 0.0;
   }
   auto emitRun = [&]() {
-    double v[RCSB_KT_LINK_REC];
+    double v[LREC];
 #pragma unroll
-    for (int i = 0; i < RCSB_KT_LINK_REC; ++i)
+    for (int i = 0; i < LREC; ++i)
     {
       v[i] = acc[i * T];
       acc[i * T] = 0.0;
@@ -366,8 +366,17 @@ ktWalkKernel(const KtArgs a)
 
       if (col >= 0)
       {
-        const double v[RCSB_KT_COL_REC] = {ax[0], ax[1], ax[2], k.f.o[0], k.f.o[1], k.f.o[2], qdIk};
-        w.emitN(v);
+        if (VEL)
+        {
+          const double v[7] = {ax[0], ax[1], ax[2], k.f.o[0], k.f.o[1], k.f.o[2], qdIk};
+          w.emitN(v);
+        }
+        else
+        {
+          const double v[6] = {ax[0], ax[1], ax[2], k.f.o[0], k.f.o[1], k.f.o[2]};
+          w.emitN(v);
+        }
+        (void) CREC;
       }
     }
 
@@ -559,9 +568,12 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   const int R = a.recDoubles;
   const bool sym = p.hdr->symmetric != 0;
   double* buf = sBuf + (long) grp * groupStride;   /* layout: RcsbKtPlanHeader, asm* fields */
-  const RcsbKtAsmLayout lay = rcsbKtAsmLayout(R, nJ, a.stageM);
-  double* scol = buf + lay.S;                      /* 7 per column: axis, origin, rate */
-  double* fb = buf + lay.F;                        /* 9 per column: p, L, L with I^T */
+  const RcsbKtAsmLayout lay = rcsbKtAsmLayout(R, nJ, a.stageM, sym ? 1 : 0);
+  constexpr int LREC = RCSB_KT_LINK_REC_N(VEL);
+  constexpr int SS = RCSB_KT_S_STRIDE;
+  const int FS = RCSB_KT_F_STRIDE(sym ? 1 : 0);
+  double* scol = buf + lay.S;                      /* SS per column: spatial axis (w, v), rate */
+  double* fb = buf + lay.F;                        /* FS per column: p, L (, L with I^T) */
   double* tail = buf + lay.tail;                   /* V, m and m c of the bodies no joint moves */
   double* Ms = buf;                                /* nJ x nJ, over the consumed record (stageM) */
   double* rhs = buf + lay.rhs;                     /* nJ: right-hand side of the direct dynamics */
@@ -636,7 +648,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     }
     if (p.hdr->nExtraRuns > 0)
     {
-      for (int i = gl; i < RCSB_KT_LINK_REC; i += LPS)
+      for (int i = gl; i < LREC; i += LPS)
       {
         for (int r = 0; r < p.hdr->nExtraRuns; ++r)
         {
@@ -648,7 +660,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     }
     /* links into their ancestors: children have larger indices than their parents, element i
      * stays with one lane (measured: a level-parallel gather costs twice the instructions) */
-    for (int i = gl; i < RCSB_KT_LINK_REC; i += LPS)
+    for (int i = gl; i < LREC; i += LPS)
     {
       for (int l = nLinks - 1; l > 0; --l)
       {
@@ -696,19 +708,39 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         Lt[1] = Lv[1];
         Lt[2] = Lv[2];
       }
-      double* sk = scol + 7 * k;
-      sk[0] = ax[0]; sk[1] = ax[1]; sk[2] = ax[2];
-      sk[3] = o[0]; sk[4] = o[1]; sk[5] = o[2];
-      sk[6] = ja[6];
-      double* f = fb + 9 * k;
+      /* spatial axis of the joint about the world origin */
+      double* sk = scol + SS * k;
+      if (isRot)
+      {
+        sk[0] = ax[0]; sk[1] = ax[1]; sk[2] = ax[2];
+        sk[3] = o[1] * ax[2] - o[2] * ax[1];
+        sk[4] = o[2] * ax[0] - o[0] * ax[2];
+        sk[5] = o[0] * ax[1] - o[1] * ax[0];
+      }
+      else
+      {
+        sk[0] = 0.0; sk[1] = 0.0; sk[2] = 0.0;
+        sk[3] = ax[0]; sk[4] = ax[1]; sk[5] = ax[2];
+      }
+      if (VEL)
+      {
+        sk[6] = ja[6];
+      }
+      double* f = fb + FS * k;
       f[0] = pv[0]; f[1] = pv[1]; f[2] = pv[2];
       f[3] = Lv[0]; f[4] = Lv[1]; f[5] = Lv[2];
-      f[6] = Lt[0]; f[7] = Lt[1]; f[8] = Lt[2];
+      if (!sym)
+      {
+        f[6] = Lt[0]; f[7] = Lt[1]; f[8] = Lt[2];
+      }
 
       double hval = 0.0, gval = 0.0;
       if ((a.h || a.qdd) && VEL)
       {
-        hval = -pairing(isRot, ax, o, cp + 13, cp + 16);
+        /* a . (N - o x F) for a rotation, a . F for a translation */
+        const double* Fb = cp + 13;
+        const double* Nb = cp + 16;
+        hval = -((sk[0] * Nb[0] + sk[1] * Nb[1] + sk[2] * Nb[2]) + (sk[3] * Fb[0] + sk[4] * Fb[1] + sk[5] * Fb[2]));
       }
       if (a.Fg || a.qdd)
       {
@@ -750,91 +782,71 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     __syncwarp();
 
     /* ---- task Jacobians (whole-body plans): RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian
-     * (Rcs_kinematics.c:566, :789) from the column records (axis, origin) and the frames of the
-     * task bodies in the record; one (task, column) pair per lane and pass, the three rows of a
-     * pair leave as coalesced stores. Formulas and modes as in combineKernel (rcsb_taskjac.cu). */
+     * (Rcs_kinematics.c:566, :789) from the spatial joint axes and the frames of the task bodies in
+     * the record. Column k of a body-point Jacobian is w_k x p + v_k, of a rotation Jacobian w_k
+     * (both joint types). The rows are zero-filled with coalesced stores; the plan lists the
+     * (task, column) pairs that are not structurally zero, one per lane and pass. Modes as in
+     * combineKernel (rcsb_taskjac.cu). */
     if (a.wholeBody && a.Jt)
     {
       const int nJac = p.hdr->nJac;
       double* Jg = a.Jt + s * (long) nJac * 3 * nJ;
-      for (int e = gl; e < nJac * nJ; e += LPS)
+      if (valid)
       {
-        const int t = e / nJ, kc = e - t * nJ;
-        const int* tk = p.jacTasks + 8 * t;
-        const int kind = tk[0], mode = tk[1], u2 = tk[2], u1 = tk[3], u3 = tk[4], uA = tk[5];
-        const double* jc = scol + 7 * kc;
-        const bool isRot = p.colIsRot[kc] != 0;
-        /* column kc of body u's translation / rotation Jacobian; zero off its chain */
-        auto colT = [&](int u, double (&c)[3]) {
-          c[0] = c[1] = c[2] = 0.0;
-          if (u >= 0 && p.taskColOn[u * nJ + kc])
-          {
-            if (isRot)
-            {
-              const double* fo = buf + p.taskBodyRec[u];
-              const double d0 = fo[0] - jc[3], d1 = fo[1] - jc[4], d2 = fo[2] - jc[5];
-              c[0] = jc[1] * d2 - jc[2] * d1;
-              c[1] = jc[2] * d0 - jc[0] * d2;
-              c[2] = jc[0] * d1 - jc[1] * d0;
-            }
-            else
-            {
-              c[0] = jc[0];
-              c[1] = jc[1];
-              c[2] = jc[2];
-            }
-          }
-        };
-        auto colR = [&](int u, double (&c)[3]) {
-          c[0] = c[1] = c[2] = 0.0;
-          if (u >= 0 && isRot && p.taskColOn[u * nJ + kc])
-          {
-            c[0] = jc[0];
-            c[1] = jc[1];
-            c[2] = jc[2];
-          }
-        };
-        double v[3];
-        if (kind == 1)   /* RCSB_JAC_POS */
+        for (int e = gl; e < nJac * 3 * nJ; e += LPS)
         {
-          colT(u2, v);
-          if (mode == 1)
+          Jg[e] = 0.0;
+        }
+      }
+      __syncwarp();   /* orders the zeros before the entries below (same addresses, other lanes) */
+      const int nEnt = p.hdr->nJacEntries;
+      for (int e = gl; e < nEnt; e += LPS)
+      {
+        const int ent = p.jacEntries[e];
+        const int kc = ent & 0xff, t = (ent >> 8) & 0xff;
+        const int* tk = p.jacTasks + 8 * t;
+        const int kind = tk[0], u2 = tk[2], u1 = tk[3], uA = tk[5];
+        const double* sj = scol + SS * kc;
+        const double w0 = sj[0], w1 = sj[1], w2 = sj[2];
+        double v[3] = {0.0, 0.0, 0.0};
+        if (kind == 1)   /* RCSB_JAC_POS: JT_2 - JT_1 + r_12 x JR_3 */
+        {
+          if (ent & (1 << 16))
           {
-            double j1[3];
-            colT(u1, j1);
-            v[0] -= j1[0];
-            v[1] -= j1[1];
-            v[2] -= j1[2];
-            if (u3 >= 0)
+            const double* o2 = buf + p.taskBodyRec[u2];
+            v[0] = (w1 * o2[2] - w2 * o2[1]) + sj[3];
+            v[1] = (w2 * o2[0] - w0 * o2[2]) + sj[4];
+            v[2] = (w0 * o2[1] - w1 * o2[0]) + sj[5];
+          }
+          if (ent & (1 << 17))
+          {
+            const double* o1 = buf + p.taskBodyRec[u1];
+            v[0] -= (w1 * o1[2] - w2 * o1[1]) + sj[3];
+            v[1] -= (w2 * o1[0] - w0 * o1[2]) + sj[4];
+            v[2] -= (w0 * o1[1] - w1 * o1[0]) + sj[5];
+          }
+          if (ent & (1 << 18))
+          {
+            const double* o1 = buf + p.taskBodyRec[u1];
+            double r[3] = {-o1[0], -o1[1], -o1[2]};
+            if (u2 >= 0)
             {
-              const double* o1 = buf + p.taskBodyRec[u1];
-              double r[3] = {-o1[0], -o1[1], -o1[2]};
-              if (u2 >= 0)
-              {
-                const double* o2 = buf + p.taskBodyRec[u2];
-                r[0] += o2[0];
-                r[1] += o2[1];
-                r[2] += o2[2];
-              }
-              double j3[3];
-              colR(u3, j3);
-              v[0] += r[1] * j3[2] - r[2] * j3[1];
-              v[1] += -r[0] * j3[2] + r[2] * j3[0];
-              v[2] += r[0] * j3[1] - r[1] * j3[0];
+              const double* o2 = buf + p.taskBodyRec[u2];
+              r[0] += o2[0];
+              r[1] += o2[1];
+              r[2] += o2[2];
             }
+            v[0] += r[1] * w2 - r[2] * w1;
+            v[1] += -r[0] * w2 + r[2] * w0;
+            v[2] += r[0] * w1 - r[1] * w0;
           }
         }
-        else
+        else             /* RCSB_JAC_OMEGA: JR_2 - JR_1 */
         {
-          colR(u2, v);
-          if (mode == 1 && u1 >= 0)
-          {
-            double j1[3];
-            colR(u1, j1);
-            v[0] -= j1[0];
-            v[1] -= j1[1];
-            v[2] -= j1[2];
-          }
+          const double sgn = ((ent & (1 << 16)) ? 1.0 : 0.0) - ((ent & (1 << 17)) ? 1.0 : 0.0);
+          v[0] = sgn * w0;
+          v[1] = sgn * w1;
+          v[2] = sgn * w2;
         }
         if (uA >= 0)
         {
@@ -866,16 +878,13 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     if (a.cog || a.Jcog)
     {
       double mT = tail[1], mc0 = tail[2], mc1 = tail[3], mc2 = tail[4];
-      for (int l = 0; l < nLinks; ++l)
+      for (int l = 0; l < p.hdr->nRoots; ++l)
       {
-        if (p.linkParent[l] < 0)
-        {
-          const double* cp = buf + p.linkHome[l];
-          mT += cp[0];
-          mc0 += cp[1];
-          mc1 += cp[2];
-          mc2 += cp[3];
-        }
+        const double* cp = buf + p.rootLinks[l];
+        mT += cp[0];
+        mc0 += cp[1];
+        mc1 += cp[2];
+        mc2 += cp[3];
       }
       const double inv = mT > 0.0 ? 1.0 / mT : 0.0;
       if (a.cog && gl == 0 && valid)
@@ -889,7 +898,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         for (int e = gl; e < 3 * nJ; e += LPS)
         {
           const int r = e / nJ, k = e - r * nJ;
-          a.Jcog[s * 3 * nJ + e] = fb[9 * k + r] * inv;
+          a.Jcog[s * 3 * nJ + e] = fb[FS * k + r] * inv;
         }
       }
       __syncwarp();   /* the composites are overwritten by the matrix staging below */
@@ -932,18 +941,15 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         const int4 pr = p.pairs[e];
         const double* ji = scol + pr.x;
         const double* fk = fb + pr.y;
-        const bool iRot = (pr.w & 1) != 0;
         const bool diag = (pr.w & 2) != 0;
-        const double ai[3] = {ji[0], ji[1], ji[2]};
-        const double oi[3] = {ji[3], ji[4], ji[5]};
         const double pk[3] = {fk[0], fk[1], fk[2]};
         const double Lk[3] = {fk[3], fk[4], fk[5]};
-        const double upper = pairing(iRot, ai, oi, pk, Lk);
+        const double upper = pairing(ji, pk, Lk);
         double lower = upper;
         if (!sym && !diag)
         {
           const double Lkt[3] = {fk[6], fk[7], fk[8]};
-          lower = pairing(iRot, ai, oi, pk, Lkt);
+          lower = pairing(ji, pk, Lkt);
         }
         if (stage)
         {
@@ -1082,7 +1088,7 @@ static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planWalkBytes +
                            (size_t) (RCSB_KT_WALK_THREADS / 32) * 32 * 33 * sizeof(double) +
-                           (size_t) RCSB_KT_LINK_REC * RCSB_KT_WALK_THREADS * sizeof(double);
+                           (size_t) RCSB_KT_LINK_REC_N(VEL) * RCSB_KT_WALK_THREADS * sizeof(double);
   const dim3 grid((unsigned int) ((a.N + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS));
 #define RCSB_LAUNCH(NS)                                                                        \
   {                                                                                            \
@@ -1116,7 +1122,7 @@ static cudaError_t launchAssemble(const KtArgs& a, int nJ, int, int smCount, cud
 {
   constexpr int GPB = RCSB_KT_ASM_THREADS / LPS;
   /* group buffers 4 doubles apart modulo 16: the groups of a warp read different banks */
-  const int asmDoubles = rcsbKtAsmLayout(a.recDoubles, nJ, a.stageM).doubles;
+  const int asmDoubles = rcsbKtAsmLayout(a.recDoubles, nJ, a.stageM, a.symmetric).doubles;
   int groupStride = ((asmDoubles + 15) & ~15) + 4;
   const size_t smemBytes = (size_t) a.planBytes + (size_t) GPB * groupStride * sizeof(double);
   auto k = ktAssembleKernel<VEL, LPS>;

@@ -91,16 +91,24 @@ typedef struct
  *   ktAssembleKernel  a group of lanes per state; sums runs into links and links into their
  *                     ancestors (composites), then builds M, h, F_gravity and E
  * Record of one state (recDoubles doubles, offsets in the order the walk produces them):
- *   column k   colRec[k] + {0..2 joint axis, 3..5 joint origin, 6 joint rate (IK space)}
+ *   column k   colRec[k] + {0..2 joint axis, 3..5 joint origin, 6 joint rate (IK space; plans with
+ *                           velocities only)}
  *   run r      runRec[r] + {0 m, 1..3 m c, 4..12 inertia about the world origin (row-major,
  *                           not symmetrised: the reference uses the tensor of the file as
  *                           given), 13..15 bias force, 16..18 bias moment about the world
- *                           origin} of the bodies of the run, belonging to link runLink[r]
+ *                           origin (plans with velocities only)} of the bodies of the run,
+ *                           belonging to link runLink[r]
  *   tail at recV: potential energy, then m and m c (3) of the massive bodies that no
  *   unconstrained joint moves (they count for the centre of gravity only)
  */
-#define RCSB_KT_COL_REC 7
-#define RCSB_KT_LINK_REC 19
+/* doubles per column / run record: with velocities the joint rate and the bias wrench ride along */
+#define RCSB_KT_COL_REC_N(vel) ((vel) ? 7 : 6)
+#define RCSB_KT_LINK_REC_N(vel) ((vel) ? 19 : 13)
+/* assembly kernel, per column in shared memory: S = {w[3], v[3], rate} (spatial axis of the joint
+ * about the world origin: rotation w = a, v = o x a; translation w = 0, v = a), stride 7;
+ * F = {p[3], L[3]} (+ L with the transposed inertia for unsymmetric models), stride 7 / 9 */
+#define RCSB_KT_S_STRIDE 7
+#define RCSB_KT_F_STRIDE(sym) ((sym) ? 7 : 9)
 
 typedef struct
 {
@@ -136,8 +144,8 @@ typedef struct
   int offExtraRuns;     /* int2[nExtraRuns]: {offset of the run, offset of the link's composite} */
   int offColHome;       /* int[nJ]: composite of the column's link */
   int offPairs;         /* int4[nPairs], structurally non-zero upper-triangle entries (ancestor
-                           column i, column k): {7 i, 9 k, (i nJ + k) | (k nJ + i) << 16,
-                           isRot(i) | (i == k) << 1 | (7 k) << 8} */
+                           column i, column k): {S offset of i, F offset of k,
+                           (i nJ + k) | (k nJ + i) << 16, (i == k) << 1 | (S offset of k) << 8} */
   int pad0;
   int walkBytes;        /* leading part of the plan the walk kernel needs (header, bodyLink,
                            bodyEmit, bodyOut, bodyFrameRec); multiple of 16 */
@@ -153,7 +161,13 @@ typedef struct
   int offTaskBodyRec;   /* int[nTaskBodies]: record offset of the frame of task body u */
   int offJacTasks;      /* int[nJac][8]: {kind, mode, u2, u1, u3, uA, 0, 0}, see rcsb_taskjac.cu */
   int offTaskColOn;     /* unsigned char[nTaskBodies * nJ]: 1 if column k moves task body u */
-  int pad1[3];
+  int vel;              /* 1: records carry joint rates and bias wrenches (RCSB_KT_*_REC_N) */
+  int nRoots;           /* links without a parent link */
+  int offRootLinks;     /* int[nRoots]: record offset of their composites */
+  int nJacEntries;      /* structurally non-zero (task Jacobian, column) pairs */
+  int offJacEntries;    /* int[nJacEntries]: column | task << 8 | on2 << 16 | on1 << 17 | on3 << 18
+                           (onX: the column moves the task's effector / refBdy / refFrame body) */
+  int pad1[2];
 } RcsbKtPlanHeader;
 
 typedef struct
@@ -166,14 +180,14 @@ typedef struct
 #else
 #define RCSB_HD
 #endif
-static inline RCSB_HD RcsbKtAsmLayout rcsbKtAsmLayout(int recDoubles, int nJ, int stageM)
+static inline RCSB_HD RcsbKtAsmLayout rcsbKtAsmLayout(int recDoubles, int nJ, int stageM, int symmetric)
 {
   RcsbKtAsmLayout l;
   int region0 = (stageM && nJ * nJ > recDoubles) ? nJ * nJ : recDoubles;
   region0 = (region0 + 3) & ~3;
   l.S = region0;
-  l.F = l.S + ((7 * nJ + 3) & ~3);
-  l.tail = l.F + ((9 * nJ + 3) & ~3);
+  l.F = l.S + ((RCSB_KT_S_STRIDE * nJ + 3) & ~3);
+  l.tail = l.F + ((RCSB_KT_F_STRIDE(symmetric) * nJ + 3) & ~3);
   l.rhs = l.tail + 8;
   l.doubles = l.rhs + nJ;
   return l;

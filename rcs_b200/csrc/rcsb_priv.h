@@ -34,6 +34,7 @@ struct DevicePlan
   int nEff = 0;
   int aux0 = 0;
   int aux1 = 0;
+  int aux2 = 0;
 };
 
 /* double-buffered device workspace of the RCSB_HOST_PTRS path */
@@ -57,9 +58,9 @@ struct RcsbModel
   std::map<std::string, rcsbhost::DevicePlan> fkPlans;
   std::vector<std::string> fkPointPlanKeys;   /* FK plans that carry effector points, oldest first (bounded) */
   std::map<std::string, rcsbhost::DevicePlan> ikPlans;
-  rcsbhost::DevicePlan ktPlan;
+  rcsbhost::DevicePlan ktPlan[2];              /* kinetic-terms plans without / with velocities */
   std::map<std::string, rcsbhost::DevicePlan> wbPlans;   /* whole-body variants of the kinetic-terms plan */
-  bool ktPlanBuilt = false;
+  bool ktPlanBuilt[2] = {false, false};
   double* ktScratch[2] = {nullptr, nullptr};
   size_t ktScratchDoubles[2] = {0, 0};
   char* ikScratch[2] = {nullptr, nullptr};      /* gathered x_des of masked IK calls, per staging slot */
@@ -173,7 +174,7 @@ struct KtExtra
   double* Jt = nullptr;
 };
 
-int buildKtPlan(RcsbModel* m, const WbSpec* wb, DevicePlan** out);
+int buildKtPlan(RcsbModel* m, const WbSpec* wb, bool vel, DevicePlan** out);
 int ktDevice(RcsbModel* m, long N, int qdim, const double* q, const double* qd, double* M,
              double* h, double* Fg, double* E, const KtExtra& x, cudaStream_t stream, int ws);
 

@@ -137,7 +137,7 @@ extern "C" int rcsb_wholebody(const RcsbModel* cm, long N, int qdim, const doubl
   }
 
   DevicePlan* plan = nullptr;
-  rc = buildKtPlan(m, &spec, &plan);
+  rc = buildKtPlan(m, &spec, false, &plan);
   if (rc != RCSB_OK || N == 0)
   {
     return rc;
