@@ -236,6 +236,14 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, bool vel, DevicePlan**
       }
     }
   }
+  /* composites: links in reverse depth-first order, each added to its parent (see offLinkSteps) */
+  std::vector<int> linkSteps;
+  for (int l = nLinks - 1; l >= 0; --l)
+  {
+    const int pl = linkParent[(size_t) l];
+    linkSteps.push_back(linkHome[(size_t) l]);
+    linkSteps.push_back(pl < 0 ? -2 : (pl == l - 1 ? -1 : linkHome[(size_t) pl]));
+  }
   /* links without a parent link: their composites add up to the whole mechanism (centre of gravity) */
   std::vector<int> rootLinks;
   for (int l = 0; l < nLinks; ++l)
@@ -330,6 +338,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, bool vel, DevicePlan**
   place(ph.offLinkHome, linkHome.size() * 4);
   place(ph.offExtraRuns, extraRuns.size() * 4);
   place(ph.offColHome, colHome.size() * 4);
+  place(ph.offLinkSteps, linkSteps.size() * 4);
   place(ph.offRootLinks, rootLinks.size() * 4);
   place(ph.offJacEntries, jacEntries.size() * 4);
   ph.totalBytes = off;
@@ -355,6 +364,7 @@ int rcsbhost::buildKtPlan(RcsbModel* m, const WbSpec* wb, bool vel, DevicePlan**
   put(ph.offLinkHome, linkHome.data(), linkHome.size() * 4);
   put(ph.offExtraRuns, extraRuns.data(), extraRuns.size() * 4);
   put(ph.offColHome, colHome.data(), colHome.size() * 4);
+  put(ph.offLinkSteps, linkSteps.data(), linkSteps.size() * 4);
   put(ph.offRootLinks, rootLinks.data(), rootLinks.size() * 4);
   put(ph.offJacEntries, jacEntries.data(), jacEntries.size() * 4);
   if (wb)

@@ -69,6 +69,7 @@ struct KtPlanView
   const unsigned char* taskColOn;
   const int* rootLinks;
   const int* jacEntries;
+  const int2* linkSteps;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -93,6 +94,7 @@ struct KtPlanView
     taskColOn = reinterpret_cast<const unsigned char*>(blob + hdr->offTaskColOn);
     rootLinks = reinterpret_cast<const int*>(blob + hdr->offRootLinks);
     jacEntries = reinterpret_cast<const int*>(blob + hdr->offJacEntries);
+    linkSteps = reinterpret_cast<const int2*>(blob + hdr->offLinkSteps);
   }
 };
 
@@ -658,16 +660,27 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
       __syncwarp();
     }
-    /* links into their ancestors: children have larger indices than their parents, element i
-     * stays with one lane (measured: a level-parallel gather costs twice the instructions) */
+    /* links into their ancestors, element i of every composite with one lane: the links come in
+     * reverse depth-first order (children before parents). Along a chain (the parent is the link
+     * before) the running sum stays in a register; only at a branching point it is added to the
+     * parent's composite in shared memory. (Round 1 did a shared-memory read-modify-write per link:
+     * a third of the kernel's stall samples sat on that dependency chain.) */
     for (int i = gl; i < LREC; i += LPS)
     {
-      for (int l = nLinks - 1; l > 0; --l)
+      double carry = 0.0;
+      for (int l = 0; l < nLinks; ++l)
       {
-        const int pl = p.linkParent[l];
-        if (pl >= 0)
+        const int2 st = p.linkSteps[l];
+        const double v = buf[st.x + i] + carry;
+        buf[st.x + i] = v;
+        carry = 0.0;
+        if (st.y == -1)
         {
-          buf[p.linkHome[pl] + i] += buf[p.linkHome[l] + i];
+          carry = v;
+        }
+        else if (st.y >= 0)
+        {
+          buf[st.y + i] += v;
         }
       }
     }

@@ -167,7 +167,11 @@ typedef struct
   int nJacEntries;      /* structurally non-zero (task Jacobian, column) pairs */
   int offJacEntries;    /* int[nJacEntries]: column | task << 8 | on2 << 16 | on1 << 17 | on3 << 18
                            (onX: the column moves the task's effector / refBdy / refFrame body) */
-  int pad1[2];
+  int offLinkSteps;     /* int2[nLinks], links in descending (reverse depth-first) order: {offset of
+                           the link's composite, where it goes next: -1 = into the next entry (its parent
+                           is the preceding link: the sum stays in a register), -2 = nowhere (no parent
+                           link), else the offset of the parent's composite} */
+  int pad1[1];
 } RcsbKtPlanHeader;
 
 typedef struct
