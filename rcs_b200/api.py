@@ -613,6 +613,13 @@ class Group:
 
     def __init__(self, graph: Graph, devices: Sequence[int]):
         devs = list(devices)
+        if len(devs) > 1:
+            # librcsb picks up the NCCL copy that is already in the process: let it be PyTorch's (a
+            # different libnccl.so.2 loaded first would break a later `import torch`)
+            try:
+                import torch  # noqa: F401
+            except ImportError:
+                pass
         arr = (ctypes.c_int * len(devs))(*devs)
         h = ctypes.c_void_p()
         _err(lib().rcsb_group_create(graph.handle, len(devs), arr, ctypes.byref(h)), "rcsb_group_create")

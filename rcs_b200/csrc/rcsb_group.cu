@@ -9,9 +9,9 @@
  * between the devices of the group (single process, one communicator per device) before the
  * results go back to the host.
  *
- * NCCL is looked up at run time (dlopen of libnccl.so.2, the copy PyTorch has already loaded
- * when the caller is a Python process): librcsb.so itself does not link against it. A group of
- * more than one device cannot be created without it.
+ * NCCL is looked up at run time: the copy already in the process if there is one (PyTorch loads its
+ * own libnccl.so.2), else $RCSB_NCCL_LIBRARY, else the system's libnccl.so.2. librcsb.so itself
+ * does not link against it. A group of more than one device cannot be created without it.
  */
 #include "rcsb_priv.h"
 
@@ -39,13 +39,21 @@ NcclApi& nccl()
   static NcclApi api;
   static std::once_flag once;
   std::call_once(once, []() {
+    /* 1. a copy that is already in the process (PyTorch brings its own libnccl.so.2: loading another
+     *    one under the same soname first would make a later `import torch` bind to the wrong version),
+     * 2. RCSB_NCCL_LIBRARY, 3. the system library */
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    const char* env = getenv("RCSB_NCCL_LIBRARY");
+    if (!api.handle && env && *env)
+    {
+      api.handle = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+    }
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names)
     {
-      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-      if (api.handle)
+      if (!api.handle)
       {
-        break;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
       }
     }
     if (!api.handle)

@@ -284,6 +284,202 @@ __device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3
   rotationTaskError(dx, Ad, Ac);
 }
 
+/* One state of the general kernels, everything the solvers need from the graph: forward
+ * kinematics (RcsGraph_setState), the task errors dx (ControllerBase::computeDX), the stacked task
+ * Jacobian J [nx x nJ] (ControllerBase::computeJ) and the joint-limit gradient term g = -alpha dH
+ * in IK order (ControllerBase::computeJointlimitGradient). */
+template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS>
+__device__ __forceinline__ void ikStateKinematics(const ModelView& m, const IkPlanView& p, const IkArgs& a,
+                                                  long s, const double* qv, double* stk, double* ja,
+                                                  double* ef, double* J, double* dx, double* g)
+{
+  const int nb = m.hdr->nb;
+  const int nJ = p.hdr->nJ;
+  const int nx = p.hdr->nx;
+  const int nTasks = p.hdr->nTasks;
+  /* ---- forward kinematics (RcsGraph_setState) ------------------------------------------ */
+  Frame f, keep;
+  setIdentity(f);
+  keep = f;
+  for (int b = 0; b < nb; ++b)
+  {
+    const int ld = m.bodyLoad[b];
+    const int bflags = m.bodyFlags[b];
+    if (ld == RCSB_LOAD_IDENT)
+    {
+      setIdentity(f);
+    }
+    else if (NSLOTS > 0 && ld >= 0)
+    {
+      const double* sp = stk + ld * 12;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        f.o[i] = sp[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        f.R[i] = sp[3 + i];
+      }
+    }
+    if (bflags & RCSB_BF_LEAF)
+    {
+      keep = f;
+    }
+
+    const int j0 = m.bodyJntStart[b];
+    const int j1 = j0 + m.bodyJntCount[b];
+    for (int j = j0; j < j1; ++j)
+    {
+      const int jf = m.jntFlags[j];
+      if (jf & RCSB_JF_HAS_AJP)
+      {
+        applyRelF(f, m.jntAJP + 12 * j, jf);
+      }
+      const double qj = qv[j];
+      const int dir = m.jntType[j] % 3;
+      double ax[3];
+      if (jf & RCSB_JF_ROT)
+      {
+        double sn, cs;
+        sincos(qj, &sn, &cs);
+        rotateAboutAxis(f, dir, sn, cs);
+        axisOf(f, dir, ax);
+      }
+      else
+      {
+        axisOf(f, dir, ax);
+        f.o[0] += qj * ax[0];
+        f.o[1] += qj * ax[1];
+        f.o[2] += qj * ax[2];
+      }
+      if (p.jntNeeded[j])
+      {
+        double* d = ja + 6 * m.jntJacobi[j];
+        d[0] = ax[0];
+        d[1] = ax[1];
+        d[2] = ax[2];
+        d[3] = f.o[0];
+        d[4] = f.o[1];
+        d[5] = f.o[2];
+      }
+    }
+    if (bflags & RCSB_BF_HAS_ABP)
+    {
+      applyRelF(f, m.bodyABP + 12 * b, bflags);
+    }
+    if (NSLOTS > 0)
+    {
+      const int sv = m.bodySave[b];
+      if (sv >= 0)
+      {
+        double* sp = stk + sv * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          sp[i] = f.o[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          sp[3 + i] = f.R[i];
+        }
+      }
+    }
+    for (int k = p.bodyTaskStart[b]; k < p.bodyTaskStart[b + 1]; ++k)
+    {
+      double* d = ef + 12 * p.bodyTaskList[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        d[i] = f.o[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        d[3 + i] = f.R[i];
+      }
+    }
+    if (bflags & RCSB_BF_LEAF)
+    {
+      f = keep;
+    }
+  }
+
+  /* ---- task error and stacked Jacobian ---------------------------------------------------- */
+  for (int i = 0; i < nx * nJ; ++i)
+  {
+    J[i] = 0.0;
+  }
+  for (int t = 0; t < nTasks; ++t)
+  {
+    const double* e = ef + 12 * t;
+    const double* xd = a.xDes + s * nx + 3 * t;
+    const bool pos = p.taskKind[t] == RCSB_TASK_XYZ;
+    if (pos)
+    {
+      dx[3 * t] = xd[0] - e[0];
+      dx[3 * t + 1] = xd[1] - e[1];
+      dx[3 * t + 2] = xd[2] - e[2];
+    }
+    else
+    {
+      double xc[3];
+      const double xdl[3] = {xd[0], xd[1], xd[2]};
+      toEuler(xc, e + 3);
+      eulerTaskError(dx + 3 * t, xdl, xc);
+    }
+    if (a.extended && t < 4)
+    {
+      /* ControllerBase::computeDX with activations: dx_i *= a_i (ControllerBase.cpp:925) */
+      dx[3 * t] *= a.taskScale[t];
+      dx[3 * t + 1] *= a.taskScale[t];
+      dx[3 * t + 2] *= a.taskScale[t];
+    }
+    for (int k = p.chainStart[t]; k < p.chainStart[t + 1]; ++k)
+    {
+      const int ent = p.chain[k];
+      const int col = ent & 0xffff;
+      const bool isRot = (ent >> 16) != 0;
+      const double* jc = ja + 6 * col;
+      double c0, c1, c2;
+      if (pos)
+      {
+        if (isRot)
+        {
+          const double d0 = e[0] - jc[3], d1 = e[1] - jc[4], d2 = e[2] - jc[5];
+          c0 = jc[1] * d2 - jc[2] * d1;
+          c1 = jc[2] * d0 - jc[0] * d2;
+          c2 = jc[0] * d1 - jc[1] * d0;
+        }
+        else
+        {
+          c0 = jc[0];
+          c1 = jc[1];
+          c2 = jc[2];
+        }
+      }
+      else
+      {
+        c0 = isRot ? jc[0] : 0.0;
+        c1 = isRot ? jc[1] : 0.0;
+        c2 = isRot ? jc[2] : 0.0;
+      }
+      J[(3 * t) * nJ + col] = c0;
+      J[(3 * t + 1) * nJ + col] = c1;
+      J[(3 * t + 2) * nJ + col] = c2;
+    }
+  }
+
+  /* ---- joint-limit gradient, (-alpha dH), in IK order --------------------------------------- */
+  for (int i = 0; i < nJ; ++i)
+  {
+    const double delta = qv[p.colJoint[i]] - p.q0[i];
+    g[i] = -(a.alpha * (p.jlGain[i] * delta));
+  }
+}
+
 /* LEFT: IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) instead of solveRightInverse:
  * J_r = J A invWq_r (computeKinematics, :176-200; binary task blending = unit task weights),
  * J# = (J_r^T J_r + lambda 1)^-1 J_r^T (MatNd_rwPinv2, Rcs_MatNd.c:1920: explicit Cholesky inverse
@@ -358,187 +554,7 @@ ikKernel(const IkArgs a)
   for (int it = 0; it < a.iters; ++it)
   {
     updateSlaves();
-    /* ---- forward kinematics (RcsGraph_setState) ------------------------------------------ */
-    Frame f, keep;
-    setIdentity(f);
-    keep = f;
-    for (int b = 0; b < nb; ++b)
-    {
-      const int ld = m.bodyLoad[b];
-      const int bflags = m.bodyFlags[b];
-      if (ld == RCSB_LOAD_IDENT)
-      {
-        setIdentity(f);
-      }
-      else if (NSLOTS > 0 && ld >= 0)
-      {
-        const double* sp = stk + ld * 12;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-          f.o[i] = sp[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-        {
-          f.R[i] = sp[3 + i];
-        }
-      }
-      if (bflags & RCSB_BF_LEAF)
-      {
-        keep = f;
-      }
-
-      const int j0 = m.bodyJntStart[b];
-      const int j1 = j0 + m.bodyJntCount[b];
-      for (int j = j0; j < j1; ++j)
-      {
-        const int jf = m.jntFlags[j];
-        if (jf & RCSB_JF_HAS_AJP)
-        {
-          applyRelF(f, m.jntAJP + 12 * j, jf);
-        }
-        const double qj = qv[j];
-        const int dir = m.jntType[j] % 3;
-        double ax[3];
-        if (jf & RCSB_JF_ROT)
-        {
-          double sn, cs;
-          sincos(qj, &sn, &cs);
-          rotateAboutAxis(f, dir, sn, cs);
-          axisOf(f, dir, ax);
-        }
-        else
-        {
-          axisOf(f, dir, ax);
-          f.o[0] += qj * ax[0];
-          f.o[1] += qj * ax[1];
-          f.o[2] += qj * ax[2];
-        }
-        if (p.jntNeeded[j])
-        {
-          double* d = ja + 6 * m.jntJacobi[j];
-          d[0] = ax[0];
-          d[1] = ax[1];
-          d[2] = ax[2];
-          d[3] = f.o[0];
-          d[4] = f.o[1];
-          d[5] = f.o[2];
-        }
-      }
-      if (bflags & RCSB_BF_HAS_ABP)
-      {
-        applyRelF(f, m.bodyABP + 12 * b, bflags);
-      }
-      if (NSLOTS > 0)
-      {
-        const int sv = m.bodySave[b];
-        if (sv >= 0)
-        {
-          double* sp = stk + sv * 12;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-          {
-            sp[i] = f.o[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 9; ++i)
-          {
-            sp[3 + i] = f.R[i];
-          }
-        }
-      }
-      for (int k = p.bodyTaskStart[b]; k < p.bodyTaskStart[b + 1]; ++k)
-      {
-        double* d = ef + 12 * p.bodyTaskList[k];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-          d[i] = f.o[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-        {
-          d[3 + i] = f.R[i];
-        }
-      }
-      if (bflags & RCSB_BF_LEAF)
-      {
-        f = keep;
-      }
-    }
-
-    /* ---- task error and stacked Jacobian ---------------------------------------------------- */
-    for (int i = 0; i < nx * nJ; ++i)
-    {
-      J[i] = 0.0;
-    }
-    for (int t = 0; t < nTasks; ++t)
-    {
-      const double* e = ef + 12 * t;
-      const double* xd = a.xDes + s * nx + 3 * t;
-      const bool pos = p.taskKind[t] == RCSB_TASK_XYZ;
-      if (pos)
-      {
-        dx[3 * t] = xd[0] - e[0];
-        dx[3 * t + 1] = xd[1] - e[1];
-        dx[3 * t + 2] = xd[2] - e[2];
-      }
-      else
-      {
-        double xc[3];
-        const double xdl[3] = {xd[0], xd[1], xd[2]};
-        toEuler(xc, e + 3);
-        eulerTaskError(dx + 3 * t, xdl, xc);
-      }
-      if (a.extended && t < 4)
-      {
-        /* ControllerBase::computeDX with activations: dx_i *= a_i (ControllerBase.cpp:925) */
-        dx[3 * t] *= a.taskScale[t];
-        dx[3 * t + 1] *= a.taskScale[t];
-        dx[3 * t + 2] *= a.taskScale[t];
-      }
-      for (int k = p.chainStart[t]; k < p.chainStart[t + 1]; ++k)
-      {
-        const int ent = p.chain[k];
-        const int col = ent & 0xffff;
-        const bool isRot = (ent >> 16) != 0;
-        const double* jc = ja + 6 * col;
-        double c0, c1, c2;
-        if (pos)
-        {
-          if (isRot)
-          {
-            const double d0 = e[0] - jc[3], d1 = e[1] - jc[4], d2 = e[2] - jc[5];
-            c0 = jc[1] * d2 - jc[2] * d1;
-            c1 = jc[2] * d0 - jc[0] * d2;
-            c2 = jc[0] * d1 - jc[1] * d0;
-          }
-          else
-          {
-            c0 = jc[0];
-            c1 = jc[1];
-            c2 = jc[2];
-          }
-        }
-        else
-        {
-          c0 = isRot ? jc[0] : 0.0;
-          c1 = isRot ? jc[1] : 0.0;
-          c2 = isRot ? jc[2] : 0.0;
-        }
-        J[(3 * t) * nJ + col] = c0;
-        J[(3 * t + 1) * nJ + col] = c1;
-        J[(3 * t + 2) * nJ + col] = c2;
-      }
-    }
-
-    /* ---- joint-limit gradient, (-alpha dH), in IK order --------------------------------------- */
-    for (int i = 0; i < nJ; ++i)
-    {
-      const double delta = qv[p.colJoint[i]] - p.q0[i];
-      g[i] = -(a.alpha * (p.jlGain[i] * delta));
-    }
+    ikStateKinematics<MAXNX, MAXNJ, MAXDOF, NSLOTS>(m, p, a, s, qv, stk, ja, ef, J, dx, g);
 
     /* ---- kinematically coupled joints: reduced joint space (IkSolverRMR.cpp:424-443,
      * RcsGraph_coupledJointMatrix, Rcs_graph.c:2823). Column r of A holds 1 at its master / free
