@@ -247,6 +247,23 @@ int rcsb_ik_rmr_ex(const RcsbModel* model, int nTasks, const RcsbTask* tasks, lo
                    double* dq, double* det, const RcsbIkOptions* options, unsigned flags,
                    void* stream);
 
+/*
+ * Prioritised resolved-motion-rate steps: IkSolverPrioRMR::solve (src/RcsCore/IkSolverPrioRMR.cpp:
+ * 178-420) iterated like examples/ExampleIK.cpp. priority[t] = 0: first level, 1: second level
+ * (solved in the null space of the first), other values: the task is ignored, as are tasks with
+ * activation[t] <= 0 (activation may be NULL). Per iteration
+ *   dq1 = J1# dx1,  dq2 = (J2 N1)# (dx2 - J2 J1# dx1),  dq_ns = -N1 N2 invWq (alpha dH),
+ *   q += dq1 + dq2 + dq_ns,
+ * and all three are zero if one of the two projections is singular. Outputs of the LAST iteration
+ * (each may be NULL): dq1, dq2, dqNs [N x dof], ok [N] (1.0 = both projections regular). xDes keeps
+ * its full layout over all tasks. Models whose unconstrained joints are kinematically coupled are
+ * not supported by this entry point (RCSB_EUNSUPPORTED); at most 4 three-dimensional tasks.
+ */
+int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, const int* priority,
+                     const double* activation, long N, double* q, const double* xDes, double lambda,
+                     double alpha, int iters, double* dq1, double* dq2, double* dqNs, double* ok,
+                     unsigned flags, void* stream);
+
 /* ---- multi-GPU summary statistics ------------------------------------------------------- */
 
 /*

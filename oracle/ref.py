@@ -83,6 +83,8 @@ def lib() -> ctypes.CDLL:
         L.ref_ik_rmr_left.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
         L.ref_ik_rmr_ex.restype = cd
         L.ref_ik_rmr_ex.argtypes = [vp, cl, vp, vp, vp, ci, vp, ci, cd, cd, ci, ci, ci, vp, vp, vp, vp]
+        L.ref_ik_prio_rmr.restype = cd
+        L.ref_ik_prio_rmr.argtypes = [vp, cl, vp, vp, vp, vp, cd, cd, ci, vp, vp, vp, vp]
         L.ref_set_threads.argtypes = [ci]
         L.ref_set_log_level.argtypes = [ci]
         _LIB = L
@@ -311,6 +313,19 @@ class RefIk:
             self._h, N, _p(q), _p(x_des), _p(act), int(bool(scale_dx)), _p(lr), 0 if lr is None else len(lr),
             float(lam), float(alpha), int(iters), int(bool(left)), int(blending), _p(dx), _p(ts), _p(ns), _p(det))
         return dict(q=q, dx=dx, dq_ts=ts, dq_ns=ns, det=det)
+
+    def prio_rmr(self, q, x_des, priority, activation=None, lam=1.0e-8, alpha=0.05, iters=1):
+        """IkSolverPrioRMR::solve (IkSolverPrioRMR.cpp:178) looped; returns dict(q, dq1, dq2, dq_ns, ok)."""
+        q = _c(q).copy()
+        x_des = _c(x_des)
+        N = q.shape[0]
+        prio = (ctypes.c_int * len(priority))(*[int(p) for p in priority])
+        act = None if activation is None else _c(np.asarray(activation, dtype=np.float64))
+        d1, d2, dn = (np.empty((N, self.graph.dof)) for _ in range(3))
+        ok = np.empty((N,))
+        self.last_seconds = lib().ref_ik_prio_rmr(self._h, N, _p(q), _p(x_des), prio, _p(act), float(lam),
+                                                  float(alpha), int(iters), _p(d1), _p(d2), _p(dn), _p(ok))
+        return dict(q=q, dq1=d1, dq2=d2, dq_ns=dn, ok=ok)
 
     def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
         """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp with

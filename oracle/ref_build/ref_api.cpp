@@ -33,7 +33,9 @@
 #include <Rcs_resourcePath.h>
 #include <ControllerBase.h>
 #include <IkSolverRMR.h>
+#include <IkSolverPrioRMR.h>
 
+#include <unistd.h>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -1005,6 +1007,105 @@ double ref_ik_rmr_ex(void* ik, long N, double* q, const double* xDes, const doub
     MatNd_destroy(dH);
     MatNd_destroy(lam);
   });
+}
+
+/*
+ * Prioritised steps: IkSolverPrioRMR::solve(dq1, dq2, dq_ns, dx, dH, activation, lambda)
+ * (src/RcsCore/IkSolverPrioRMR.cpp:178), looped like examples/ExampleIK.cpp. priority [nTasks]:
+ * level of every task (IkSolverPrioRMR::setTaskPriority). Outputs of the last iteration.
+ */
+double ref_ik_prio_rmr(void* ik, long N, double* q, const double* xDes, const int* priority,
+                       const double* activation, double lambda, double alpha, int iters, double* dq1Out,
+                       double* dq2Out, double* dqNsOut, double* okOut)
+{
+  IkHandle* h = (IkHandle*) ik;
+  /* IkSolverPrioRMR's constructor re-reads the controller's xml FILE for "prio" attributes
+   * (IkSolverPrioRMR.cpp:108-140): give it a controller that was created from a file */
+  char tmpName[] = "/tmp/rcsb_ref_controller_XXXXXX.xml";
+  const int fd = mkstemps(tmpName, 4);
+  if (fd < 0)
+  {
+    return -1.0;
+  }
+  FILE* tf = fdopen(fd, "w");
+  fputs(h->xml.c_str(), tf);
+  fclose(tf);
+  Rcs::ControllerBase* fileController = new Rcs::ControllerBase(std::string(tmpName), true);
+  const double secs = parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*fileController);
+    Rcs::IkSolverPrioRMR solver(&c);
+    RcsGraph* graph = c.getGraph();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    const unsigned int nTasks = c.getNumberOfTasks();
+    for (unsigned int t = 0; t < nTasks; ++t)
+    {
+      solver.setTaskPriority(t, priority[t]);
+    }
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* d1 = MatNd_create(dof, 1);
+    MatNd* d2 = MatNd_create(dof, 1);
+    MatNd* dn = MatNd_create(dof, 1);
+    MatNd* a = MatNd_create(nTasks, 1);
+    MatNd* xd = MatNd_create(nx, 1);
+    MatNd* dx = MatNd_create(nx, 1);
+    MatNd* dH = MatNd_create(1, nJ);
+    for (unsigned int t = 0; t < nTasks; ++t)
+    {
+      a->ele[t] = activation ? activation[t] : 1.0;
+    }
+    sliceReady();
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, dof, q + i * dof, NULL);
+      memcpy(xd->ele, xDes + (size_t) i * nx, sizeof(double) * nx);
+      bool ok = true;
+      for (int it = 0; it < iters; ++it)
+      {
+        MatNd_reshape(dx, nx, 1);
+        c.computeDX(dx, xd);
+        c.computeJointlimitGradient(dH);
+        MatNd_constMulSelf(dH, alpha);
+        MatNd_reshape(d1, dof, 1);
+        MatNd_reshape(d2, dof, 1);
+        MatNd_reshape(dn, dof, 1);
+        ok = solver.solve(d1, d2, dn, dx, dH, a, lambda);
+        MatNd_addSelf(graph->q, d1);
+        MatNd_addSelf(graph->q, d2);
+        MatNd_addSelf(graph->q, dn);
+        RcsGraph_setState(graph, NULL, NULL);
+      }
+      memcpy(q + i * dof, graph->q->ele, sizeof(double) * dof);
+      if (dq1Out)
+      {
+        memcpy(dq1Out + (size_t) i * dof, d1->ele, sizeof(double) * dof);
+      }
+      if (dq2Out)
+      {
+        memcpy(dq2Out + (size_t) i * dof, d2->ele, sizeof(double) * dof);
+      }
+      if (dqNsOut)
+      {
+        memcpy(dqNsOut + (size_t) i * dof, dn->ele, sizeof(double) * dof);
+      }
+      if (okOut)
+      {
+        okOut[i] = ok ? 1.0 : 0.0;
+      }
+    }
+    sliceDone();
+    MatNd_destroy(qv);
+    MatNd_destroy(d1);
+    MatNd_destroy(d2);
+    MatNd_destroy(dn);
+    MatNd_destroy(a);
+    MatNd_destroy(xd);
+    MatNd_destroy(dx);
+    MatNd_destroy(dH);
+  });
+  delete fileController;
+  unlink(tmpName);
+  return secs;
 }
 
 }   // extern "C"

@@ -133,6 +133,8 @@ def lib() -> ctypes.CDLL:
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_rmr_ex", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_void, ctypes.c_uint, c_void)
+    sig("rcsb_ik_prio_rmr", c_int, c_void, c_int, c_void, c_void, c_void, c_long, c_dbl_p, c_dbl_p,
+        ctypes.c_double, ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
     sig("rcsb_group_create", c_int, c_void, c_int, c_void, ctypes.POINTER(c_void))
     sig("rcsb_group_destroy", None, c_void)
@@ -563,6 +565,38 @@ class Model:
             a.ptr(out.get("det"), "det"), ctypes.byref(opt),
             a.flags() | (_IK_LEFT_INVERSE if left_inverse else 0), a.stream())
         _err(rc, "rcsb_ik_rmr_ex")
+        return out
+
+    def ik_prio_rmr(self, tasks: Sequence, priority: Sequence[int], q, x_des, activation=None, lam=1.0e-8,
+                    alpha=0.05, iters=1, want=("dq1", "dq2", "dq_ns", "ok"), out=None):
+        """rcsb_ik_prio_rmr: IkSolverPrioRMR::solve steps with two priority levels + null space."""
+        N, qdim = self._batch(q)
+        if qdim != self.dof:
+            raise RcsbError("ik_prio_rmr: q must be N x dof")
+        if len(priority) != len(tasks):
+            raise RcsbError("ik_prio_rmr: one priority level per task")
+        nx_all = sum(6 if int(k) == TASK_XYZABC else 3 for k, _ in tasks)
+        if tuple(x_des.shape) != (N, nx_all):
+            raise RcsbError(f"ik_prio_rmr: x_des must be {N} x {nx_all}")
+        shapes = {"dq1": (N, self.dof), "dq2": (N, self.dof), "dq_ns": (N, self.dof), "ok": (N,)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        tarr = (_RcsbTask * max(len(tasks), 1))(*[_RcsbTask(int(k), int(e)) for k, e in tasks])
+        prio = (ctypes.c_int * len(priority))(*[int(p) for p in priority])
+        act = None
+        if activation is not None:
+            act_np = np.ascontiguousarray(activation, dtype=np.float64)
+            if act_np.shape != (len(tasks),):
+                raise RcsbError("ik_prio_rmr: one activation per task")
+            act = ctypes.c_void_p(act_np.ctypes.data)
+        a = _Args(self)
+        rc = lib().rcsb_ik_prio_rmr(
+            self._h, len(tasks), tarr, prio, act, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam),
+            float(alpha), int(iters), a.ptr(out.get("dq1"), "dq1"), a.ptr(out.get("dq2"), "dq2"),
+            a.ptr(out.get("dq_ns"), "dq_ns"), a.ptr(out.get("ok"), "ok"), a.flags(), a.stream())
+        _err(rc, "rcsb_ik_prio_rmr")
         return out
 
     def ik_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1,

@@ -1329,6 +1329,19 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
 
 }   // namespace
 
+/* unconstrained joints that are kinematically coupled slaves (RcsGraph_countCoupledJoints, Rcs_graph.c:2804) */
+static int RcsGraph_countCoupledColumns(const RcsbModel* m)
+{
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* jntCpl = m->iarr(RCSB_A_JNT_CPL);
+  int n = 0;
+  for (int j = 0; j < m->hdr.dof; ++j)
+  {
+    n += (jntJacobi[j] >= 0 && jntCpl[j] >= 0) ? 1 : 0;
+  }
+  return n;
+}
+
 static int taskDim(int kind)
 {
   return kind == RCSB_TASK_XYZABC ? 6 : 3;
@@ -1474,6 +1487,165 @@ extern "C" int rcsb_ik_rmr_ex(const RcsbModel* cm, int nTasks, const RcsbTask* t
     local.dqNs = dv(I_NS, ex.dqNs);
     return ikDevice(m, plan, n, arr[I_QIN].dev, arr[I_X].dev, lambda, alpha, iters,
                     dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), left, st, useEx ? &local : nullptr, slot);
+  });
+}
+
+extern "C" int rcsb_ik_prio_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, const int* priority,
+                                const double* activation, long N, double* q, const double* xDes,
+                                double lambda, double alpha, int iters, double* dq1, double* dq2,
+                                double* dqNs, double* ok, unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  if (!m || N < 0 || (N > 0 && (!q || !xDes)) || iters < 0 || nTasks <= 0 || !tasks || !priority)
+  {
+    rcsb_set_error("rcsb_ik_prio_rmr: invalid arguments");
+    return RCSB_EINVAL;
+  }
+  /* tasks that take part (level 0 or 1, active), their x_des columns and levels per plan task */
+  std::vector<RcsbTask> active;
+  IkEx ex;
+  int levels[4] = {-1, -1, -1, -1};
+  int planTask = 0, col = 0;
+  bool all = true;
+  for (int t = 0; t < nTasks; ++t)
+  {
+    const int dim = taskDim(tasks[t].kind);
+    const double act = activation ? activation[t] : 1.0;
+    if (act > 0.0 && (priority[t] == 0 || priority[t] == 1))
+    {
+      active.push_back(tasks[t]);
+      for (int k = 0; k < dim; ++k)
+      {
+        ex.xMap.push_back(col + k);
+      }
+      for (int k = 0; k < dim / 3; ++k, ++planTask)
+      {
+        if (planTask < 4)
+        {
+          levels[planTask] = priority[t];
+        }
+      }
+    }
+    else
+    {
+      all = false;
+    }
+    col += dim;
+  }
+  ex.nxAll = col;
+  if (all)
+  {
+    ex.xMap.clear();
+  }
+  if (active.empty() || planTask > 4)
+  {
+    rcsb_set_error("rcsb_ik_prio_rmr: needs 1 to 4 three-dimensional tasks on the two priority levels (%d)",
+                   planTask);
+    return active.empty() ? RCSB_EINVAL : RCSB_EUNSUPPORTED;
+  }
+  const DevicePlan* plan = nullptr;
+  int rc = buildIkPlan(m, (int) active.size(), active.data(), &plan);
+  if (rc != RCSB_OK)
+  {
+    return rc;
+  }
+  if (RcsGraph_countCoupledColumns(m) > 0)
+  {
+    rcsb_set_error("rcsb_ik_prio_rmr: kinematically coupled unconstrained joints are not supported");
+    return RCSB_EUNSUPPORTED;
+  }
+  if (N == 0)
+  {
+    return RCSB_OK;
+  }
+
+  auto launch = [&](long n, double* dq_, const double* dx_, double* o1, double* o2, double* on, double* ook,
+                    cudaStream_t st, int ws) -> int {
+    rcsb::IkArgs a;
+    memset(&a, 0, sizeof(a));
+    RCSB_CUDA(cudaSetDevice(m->device));
+    const double* xd = dx_;
+    if (!ex.xMap.empty())
+    {
+      const int nxAct = (int) ex.xMap.size();
+      const size_t need = (size_t) n * nxAct * sizeof(double) + 256;
+      {
+        std::lock_guard<std::recursive_mutex> lock(m->mtx);
+        if (m->ikScratchBytes[ws] < need)
+        {
+          if (m->ikScratch[ws])
+          {
+            RCSB_CUDA(cudaFree(m->ikScratch[ws]));
+            m->ikScratch[ws] = nullptr;
+            m->ikScratchBytes[ws] = 0;
+          }
+          RCSB_CUDA(cudaMalloc(&m->ikScratch[ws], need));
+          m->ikScratchBytes[ws] = need;
+        }
+      }
+      int* dMap = reinterpret_cast<int*>(m->ikScratch[ws]);
+      double* dX = reinterpret_cast<double*>(m->ikScratch[ws] + 256);
+      RCSB_CUDA(cudaMemcpyAsync(dMap, ex.xMap.data(), sizeof(int) * (size_t) nxAct, cudaMemcpyHostToDevice, st));
+      long blocks = (n * nxAct + 255) / 256;
+      const long cap = (long) m->smCount * 8;
+      blocks = blocks < cap ? blocks : cap;
+      ikGatherKernel<<<(unsigned int) (blocks > 0 ? blocks : 1), 256, 0, st>>>(dx_, dX, n, ex.nxAll, nxAct, dMap);
+      RCSB_CUDA(cudaGetLastError());
+      g_launches.fetch_add(1);
+      xd = dX;
+    }
+    a.model = m->dev;
+    a.plan = plan->dev;
+    a.modelBytes = m->hdr.totalBytes;
+    a.planBytes = plan->bytes;
+    a.N = n;
+    a.q = dq_;
+    a.xDes = xd;
+    a.lambda = lambda;
+    a.alpha = alpha;
+    a.iters = iters;
+    a.extended = 0;
+    a.dq = o1;
+    a.dqTs = o2;
+    a.dqNs = on;
+    a.det = ook;
+    memcpy(a.taskLevel, levels, sizeof(levels));
+    for (int t = 0; t < 4; ++t)
+    {
+      a.taskScale[t] = 1.0;
+      a.taskAct[t] = 1.0;
+    }
+    cudaError_t e = rcsb_launch_ik_prio(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, st);
+    if (e == cudaErrorInvalidValue)
+    {
+      cudaGetLastError();
+      rcsb_set_error("rcsb_ik_prio_rmr: problem too large (nx %d, nJ %d, dof %d; limits 12 / 40 / 72)",
+                     plan->aux0, m->hdr.nJ, m->hdr.dof);
+      return RCSB_EUNSUPPORTED;
+    }
+    RCSB_CUDA(e);
+    g_launches.fetch_add(1);
+    return RCSB_OK;
+  };
+
+  if (!(flags & RCSB_HOST_PTRS))
+  {
+    return launch(N, q, xDes, dq1, dq2, dqNs, ok, static_cast<cudaStream_t>(stream), 0);
+  }
+  const size_t dof = (size_t) m->hdr.dof;
+  std::vector<StagedArray> arr;
+  enum { I_QIN, I_X, I_QOUT, I_D1, I_D2, I_DN, I_OK };
+  arr.push_back({q, nullptr, dof, nullptr});
+  arr.push_back({xDes, nullptr, (size_t) col, nullptr});
+  arr.push_back({nullptr, q, dof, nullptr});
+  arr.push_back({nullptr, dq1, dq1 ? dof : 0, nullptr});
+  arr.push_back({nullptr, dq2, dq2 ? dof : 0, nullptr});
+  arr.push_back({nullptr, dqNs, dqNs ? dof : 0, nullptr});
+  arr.push_back({nullptr, ok, (size_t) (ok ? 1 : 0), nullptr});
+  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1, -1}, [&](long n, cudaStream_t st, int slot) {
+    auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    return launch(n, arr[I_QIN].dev, arr[I_X].dev, dv(I_D1, dq1), dv(I_D2, dq2), dv(I_DN, dqNs), dv(I_OK, ok),
+                  st, slot);
   });
 }
 

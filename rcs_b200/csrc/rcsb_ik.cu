@@ -922,6 +922,345 @@ ikKernel(const IkArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Prioritised solver                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* J# = W J^T (J W J^T + lambda 1)^-1 for a small row-major J [mr x n] (MatNd_rwPinv,
+ * src/RcsCore/Rcs_MatNd.c:1833: explicit inverse from the Banachiewicz Cholesky factor,
+ * Rcs_linAlg.c:66-300). P [n x mr] receives J#; A, Ai are mr x mr work arrays. Returns the
+ * determinant (0: singular, P zeroed; mr == 0: 1, as the reference). */
+__device__ __noinline__ double rwPinvSmall(const double* J, int mr, int n, const double* w, double lambda,
+                                           double* P, double* A, double* Ai)
+{
+  if (mr == 0)
+  {
+    return 1.0;
+  }
+  for (int i = 0; i < n; ++i)
+  {
+    for (int k = 0; k < mr; ++k)
+    {
+      P[i * mr + k] = w[i] * J[k * n + i];
+    }
+  }
+  for (int r = 0; r < mr; ++r)
+  {
+    for (int c = 0; c < mr; ++c)
+    {
+      double sum = 0.0;
+      for (int i = 0; i < n; ++i)
+      {
+        sum += J[r * n + i] * P[i * mr + c];
+      }
+      A[r * mr + c] = sum + (r == c ? lambda : 0.0);
+    }
+  }
+  double det = 1.0;
+  for (int i = 0; i < mr && det != 0.0; ++i)
+  {
+    for (int k = 0; k <= i; ++k)
+    {
+      double sum = A[i * mr + k];
+      for (int t = 0; t < k; ++t)
+      {
+        sum -= A[i * mr + t] * A[k * mr + t];
+      }
+      if (i > k)
+      {
+        A[i * mr + k] = sum / A[k * mr + k];
+      }
+      else if (sum > 0.0)
+      {
+        A[i * mr + i] = sqrt(sum);
+        det *= A[i * mr + i] * A[i * mr + i];
+      }
+      else
+      {
+        det = 0.0;
+        break;
+      }
+    }
+  }
+  if (det == 0.0)
+  {
+    for (int i = 0; i < n * mr; ++i)
+    {
+      P[i] = 0.0;
+    }
+    return 0.0;
+  }
+  for (int k = 0; k < mr; ++k)
+  {
+    A[k * mr + k] = 1.0 / A[k * mr + k];
+    for (int i = k + 1; i < mr; ++i)
+    {
+      double sum = 0.0;
+      for (int t = k; t < i; ++t)
+      {
+        sum += A[i * mr + t] * A[t * mr + k];
+      }
+      A[i * mr + k] = -sum / A[i * mr + i];
+    }
+  }
+  for (int r = 0; r < mr; ++r)
+  {
+    for (int c = r; c < mr; ++c)
+    {
+      double sum = 0.0;
+      for (int t = c; t < mr; ++t)
+      {
+        sum += A[t * mr + r] * A[t * mr + c];
+      }
+      Ai[r * mr + c] = sum;
+      Ai[c * mr + r] = sum;
+    }
+  }
+  /* P <- (W J^T) inverse, row by row (A is free again: one row of scratch) */
+  for (int i = 0; i < n; ++i)
+  {
+    for (int k = 0; k < mr; ++k)
+    {
+      A[k] = P[i * mr + k];
+    }
+    for (int c = 0; c < mr; ++c)
+    {
+      double sum = 0.0;
+      for (int k = 0; k < mr; ++k)
+      {
+        sum += A[k] * Ai[k * mr + c];
+      }
+      P[i * mr + c] = sum;
+    }
+  }
+  return det;
+}
+
+/* N = 1 - J# J (MatNd_nullspace, Rcs_MatNd.c:3758), n x n */
+__device__ __noinline__ void nullspaceSmall(double* N, const double* P, const double* J, int mr, int n)
+{
+  for (int i = 0; i < n; ++i)
+  {
+    for (int j = 0; j < n; ++j)
+    {
+      double sum = 0.0;
+      for (int k = 0; k < mr; ++k)
+      {
+        sum += P[i * mr + k] * J[k * n + j];
+      }
+      N[i * n + j] = (i == j) ? (1.0 - sum) : (-sum);
+    }
+  }
+}
+
+/*
+ * IkSolverPrioRMR::solve (src/RcsCore/IkSolverPrioRMR.cpp:178-420), iterated like the loop of
+ * examples/ExampleIK.cpp: tasks of priority level 0 are solved first, tasks of level 1 in the null
+ * space of the first, the joint-limit gradient in the null space of both:
+ *   dq1 = J1# dx1,  N1 = 1 - J1# J1,  dq2 = (J2 N1)# (dx2 - J2 J1# dx1),
+ *   dq_ns = -N1 (1 - (J2 N1)# J2 N1) invWq (alpha dH);   q += dq1 + dq2 + dq_ns.
+ * A singular projection (det <= 0) zeroes all three. One thread per state, literal algebra of the
+ * reference in thread-local arrays (models without kinematically coupled unconstrained joints).
+ */
+template <int MAXNX, int MAXNJ, int MAXDOF, int NSLOTS>
+__global__ void __launch_bounds__(RCSB_IK_THREADS)
+ikPrioKernel(const IkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
+
+  ModelView m;
+  m.bind(sModel);
+  IkPlanView p;
+  p.bind(sPlan);
+
+  const long s = (long) blockIdx.x * RCSB_IK_THREADS + threadIdx.x;
+  if (s >= a.N)
+  {
+    return;
+  }
+  const int dof = m.hdr->dof;
+  const int nJ = p.hdr->nJ;
+  const int nx = p.hdr->nx;
+  const int nTasks = p.hdr->nTasks;
+  constexpr int MAXT = MAXNX / 3;
+
+  double qv[MAXDOF];
+  double ja[6 * MAXNJ];
+  double ef[12 * MAXT];
+  double J[MAXNX * MAXNJ];
+  double dx[MAXNX], g[MAXNJ];
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
+  double J1[MAXNX * MAXNJ], J2[MAXNX * MAXNJ], P1[MAXNJ * MAXNX], P2[MAXNJ * MAXNX];
+  double N1[MAXNJ * MAXNJ], N2[MAXNJ * MAXNJ];
+  double A[MAXNX * MAXNX], Ai[MAXNX * MAXNX];
+  double dx1[MAXNX], dx2[MAXNX], dq1[MAXNJ], dq2[MAXNJ], dqn[MAXNJ], tmp[MAXNJ > MAXNX ? MAXNJ : MAXNX];
+  bool ok = true;
+
+  for (int j = 0; j < dof; ++j)
+  {
+    qv[j] = a.q[s * dof + j];
+  }
+  for (int i = 0; i < nJ; ++i)
+  {
+    dq1[i] = dq2[i] = dqn[i] = 0.0;
+  }
+  const int nCpl = m.hdr->nCpl;
+  auto updateSlaves = [&]() {
+    for (int c = 0; c < nCpl; ++c)
+    {
+      qv[m.cpl[c].slave] = slaveAngle(m.cpl[c], qv[m.cpl[c].master]);
+    }
+  };
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    updateSlaves();
+    ikStateKinematics<MAXNX, MAXNJ, MAXDOF, NSLOTS>(m, p, a, s, qv, stk, ja, ef, J, dx, g);
+
+    /* rows of the two priority levels */
+    int n1 = 0, n2 = 0;
+    for (int t = 0; t < nTasks; ++t)
+    {
+      const int lvl = t < 4 ? a.taskLevel[t] : -1;
+      for (int r = 0; r < 3; ++r)
+      {
+        const double* src = J + (3 * t + r) * nJ;
+        if (lvl == 0)
+        {
+          for (int i = 0; i < nJ; ++i)
+          {
+            J1[n1 * nJ + i] = src[i];
+          }
+          dx1[n1++] = dx[3 * t + r];
+        }
+        else if (lvl == 1)
+        {
+          for (int i = 0; i < nJ; ++i)
+          {
+            J2[n2 * nJ + i] = src[i];
+          }
+          dx2[n2++] = dx[3 * t + r];
+        }
+      }
+    }
+
+    const double det1 = rwPinvSmall(J1, n1, nJ, p.invWq, a.lambda, P1, A, Ai);
+    for (int i = 0; i < nJ; ++i)
+    {
+      double sum = 0.0;
+      for (int k = 0; k < n1; ++k)
+      {
+        sum += P1[i * n1 + k] * dx1[k];
+      }
+      dq1[i] = sum;
+    }
+    nullspaceSmall(N1, P1, J1, n1, nJ);
+    /* J2 N1, in place of J (free from here on) */
+    for (int r = 0; r < n2; ++r)
+    {
+      for (int c = 0; c < nJ; ++c)
+      {
+        double sum = 0.0;
+        for (int i = 0; i < nJ; ++i)
+        {
+          sum += J2[r * nJ + i] * N1[i * nJ + c];
+        }
+        J[r * nJ + c] = sum;
+      }
+    }
+    const double det2 = rwPinvSmall(J, n2, nJ, p.invWq, a.lambda, P2, A, Ai);
+    ok = det1 > 0.0 && det2 > 0.0;
+    /* (J2 J1#) dx1, the matrix first as in the reference */
+    for (int r = 0; r < n2; ++r)
+    {
+      double acc = 0.0;
+      for (int c = 0; c < n1; ++c)
+      {
+        double sum = 0.0;
+        for (int i = 0; i < nJ; ++i)
+        {
+          sum += J2[r * nJ + i] * P1[i * n1 + c];
+        }
+        acc += sum * dx1[c];
+      }
+      tmp[r] = dx2[r] - acc;
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      double sum = 0.0;
+      for (int k = 0; k < n2; ++k)
+      {
+        sum += P2[i * n2 + k] * tmp[k];
+      }
+      dq2[i] = sum;
+    }
+    /* null space of both levels: N1 (1 - (J2 N1)# J2 N1) applied to invWq (-alpha dH) */
+    nullspaceSmall(N2, P2, J, n2, nJ);
+    for (int i = 0; i < nJ; ++i)
+    {
+      tmp[i] = p.invWq[i] * (-g[i]);       /* dHA = invWq o (alpha dH); g = -alpha dH */
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      double sum = 0.0;
+      for (int c = 0; c < nJ; ++c)
+      {
+        double nn = 0.0;
+        for (int k = 0; k < nJ; ++k)
+        {
+          nn += N1[i * nJ + k] * N2[k * nJ + c];
+        }
+        sum += nn * tmp[c];
+      }
+      dqn[i] = -1.0 * sum;
+    }
+    if (!ok)
+    {
+      for (int i = 0; i < nJ; ++i)
+      {
+        dq1[i] = dq2[i] = dqn[i] = 0.0;
+      }
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      qv[p.colJoint[i]] += (dq1[i] + dq2[i]) + dqn[i];
+    }
+  }
+  updateSlaves();
+
+  for (int j = 0; j < dof; ++j)
+  {
+    a.q[s * dof + j] = qv[j];
+    const int c = m.jntJacobi[j];
+    if (a.dq)
+    {
+      a.dq[s * dof + j] = c >= 0 ? dq1[c] : 0.0;
+    }
+    if (a.dqTs)
+    {
+      a.dqTs[s * dof + j] = c >= 0 ? dq2[c] : 0.0;
+    }
+    if (a.dqNs)
+    {
+      a.dqNs[s * dof + j] = c >= 0 ? dqn[c] : 0.0;
+    }
+  }
+  if (a.dx)
+  {
+    for (int i = 0; i < nx; ++i)
+    {
+      a.dx[s * nx + i] = dx[i];
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = ok ? 1.0 : 0.0;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Single-chain fast path                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -2351,7 +2690,54 @@ static cudaError_t launchIk(const IkArgs& a, int nSlots, cudaStream_t stream)
 #undef RCSB_LAUNCH
 }
 
+template <int MAXNX, int MAXNJ, int MAXDOF>
+static cudaError_t launchIkPrio(const IkArgs& a, int nSlots, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes;
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
+#define RCSB_LAUNCH(NS)                                                                        \
+  {                                                                                            \
+    auto k = ikPrioKernel<MAXNX, MAXNJ, MAXDOF, NS>;                                           \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);                                        \
+    return cudaGetLastError();                                                                 \
+  }
+  if (nSlots <= 0)
+  {
+    RCSB_LAUNCH(0)
+  }
+  else
+  {
+    RCSB_LAUNCH(RCSB_MAX_FRAME_SLOTS)
+  }
+#undef RCSB_LAUNCH
+}
+
 }   // namespace rcsb
+
+extern "C" cudaError_t rcsb_launch_ik_prio(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
+                                           cudaStream_t stream)
+{
+  using namespace rcsb;
+  if (a->N <= 0)
+  {
+    return cudaSuccess;
+  }
+  if (nx <= 6 && nJ <= 8 && dof <= 8)
+  {
+    return launchIkPrio<6, 8, 8>(*a, nSlots, stream);
+  }
+  if (nx <= 12 && nJ <= 40 && dof <= 72)
+  {
+    return launchIkPrio<12, 40, 72>(*a, nSlots, stream);
+  }
+  return cudaErrorInvalidValue;
+}
 
 extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
                                       int chainNc, int multiNu, int nEffs, int nTasks,

@@ -106,7 +106,8 @@ struct IkArgs
   double lambdaRow[12];
   double taskScale[4]; /* dx rows of task t are multiplied by it (ControllerBase::computeDX with a_des) */
   double taskAct[4];   /* activation of task t (blending weights) */
-  double* dqTs;        /* N x dof: task-space part of the last step */
+  int taskLevel[4];    /* prioritised solver: priority level of plan task t (0, 1; else ignored) */
+  double* dqTs;        /* N x dof: task-space part of the last step (prioritised solver: dq2) */
   double* dqNs;        /* N x dof: null-space part of the last step */
 };
 
@@ -120,6 +121,8 @@ cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nJ2, i
 /* maximum dynamic shared memory of the assembly kernel for a record of recDoubles (plan checks) */
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            int multiNu, int nEffs, int nTasks, cudaStream_t stream);
+cudaError_t rcsb_launch_ik_prio(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
+                                cudaStream_t stream);
 }
 
 #endif
