@@ -38,7 +38,8 @@ def _conds(rik, q, rows1, rows2, lam):
     N1 = np.eye(J.shape[2])[None] - np.einsum("njk,nki->nji", P1, J1)
     J2N1 = np.einsum("nij,njk->nik", J2, N1)
     A2 = np.einsum("nij,j,nkj->nik", J2N1, w, J2N1) + lam * np.eye(len(rows2))
-    return np.maximum(np.linalg.cond(A1), 1.0) * np.maximum(np.linalg.cond(A2), 1.0)
+    c2 = np.linalg.cond(A2) if len(rows2) else np.ones(len(q))
+    return np.maximum(np.linalg.cond(A1), 1.0) * np.maximum(c2, 1.0)
 
 
 def _close(ours, ref, cond, what, mult=1.0):
