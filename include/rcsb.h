@@ -264,6 +264,42 @@ int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, 
                      double alpha, int iters, double* dq1, double* dq2, double* dqNs, double* ok,
                      unsigned flags, void* stream);
 
+/*
+ * Resolved-motion-rate steps over ANY stack of the task kinds below, with reference bodies and
+ * frames: the controller side of the reference for task sets like GenericHumanoid/cAction.xml
+ * (hands XYZ, COGX / COGY, feet XYZABC relative to the Heel; BASELINE.json configs[4]), solved
+ * with IkSolverRMR::solveRightInverse (IkSolverRMR.cpp:415) and looped like examples/ExampleIK.cpp.
+ *   XYZ     TaskPosition3D (TaskPosition3D.cpp:127, :207): position of `effector` relative to refBdy,
+ *           in the coordinates of refFrame; Jacobian RcsGraph_3dPosJacobian (Rcs_kinematics.c:566)
+ *   ABC     TaskEuler3D (TaskEuler3D.cpp:110-262): x-y-z Euler angles of the rotation of `effector`
+ *           relative to refBdy; Jacobian RcsGraph_3dOmegaJacobian (Rcs_kinematics.c:789)
+ *   XYZABC  TaskPose6D: XYZ followed by ABC with the same bodies
+ *   COGX / COGY / COGZ   TaskCOM1D (TaskCOM1D.cpp:105-125): one component of the centre of gravity of
+ *           the subtree of `effector` (-1: the whole graph, RcsGraph_COG / RcsGraph_COGJacobian,
+ *           Rcs_kinematics.c:904-1036); no reference body
+ *   JOINT   TaskJoint (TaskJoint.cpp:227-265): the value of joint `effector` (a jointIndex; the
+ *           joint must be unconstrained)
+ * effector / refBdy / refFrame: depth-first body indices, -1 = none; refFrame = -1 with a refBdy
+ * means refFrame = refBdy, as the reference's XML constructor does (Task.cpp:160). xDes [N x nx],
+ * nx = sum of the task dimensions (3, 3, 6, 1, 1). Outputs of the last iteration (may be NULL):
+ * dx [N x nx], dq [N x dof], det [N]. One thread per state, the reference's literal algebra;
+ * up to 24 rows; models with kinematically coupled unconstrained joints are not supported here.
+ */
+#define RCSB_TASK_COGX 4
+#define RCSB_TASK_COGY 5
+#define RCSB_TASK_COGZ 6
+#define RCSB_TASK_JOINT 7
+typedef struct
+{
+  int kind;         /* RCSB_TASK_* */
+  int effector;
+  int refBdy;
+  int refFrame;
+} RcsbTaskSpec;
+int rcsb_ik_tasks_rmr(const RcsbModel* model, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
+                      const double* xDes, double lambda, double alpha, int iters, double* dx, double* dq,
+                      double* det, unsigned flags, void* stream);
+
 /* ---- multi-GPU summary statistics ------------------------------------------------------- */
 
 /*

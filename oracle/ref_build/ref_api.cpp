@@ -754,8 +754,15 @@ void* ref_ik_create(const char* graphFile, const char* taskSpec)
     }
     if (f.size() >= 2)
     {
-      x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << f[0] << "\" effector=\"" << f[1]
-        << "\"";
+      x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << f[0] << "\"";
+      if (f[0] == "Joint")
+      {
+        x << " jnt=\"" << f[1] << "\"";       /* TaskJoint: the second field is the joint's name */
+      }
+      else if (!f[1].empty())
+      {
+        x << " effector=\"" << f[1] << "\"";
+      }
       if (f.size() >= 3 && !f[2].empty())
       {
         x << " refBdy=\"" << f[2] << "\"";

@@ -14,6 +14,10 @@ from .api import (  # noqa: F401
     Model,
     RcsbError,
     TASK_ABC,
+    TASK_COGX,
+    TASK_COGY,
+    TASK_COGZ,
+    TASK_JOINT,
     TASK_XYZ,
     TASK_XYZABC,
     bind_host_to_device,
@@ -34,6 +38,10 @@ __all__ = [
     "Model",
     "RcsbError",
     "TASK_ABC",
+    "TASK_COGX",
+    "TASK_COGY",
+    "TASK_COGZ",
+    "TASK_JOINT",
     "TASK_XYZ",
     "TASK_XYZABC",
     "bind_host_to_device",

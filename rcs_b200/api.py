@@ -69,6 +69,12 @@ class _RcsbIkOptions(ctypes.Structure):
 
 
 BLEND_BINARY, BLEND_LINEAR, BLEND_APPROXIMATE = 0, 1, 2
+TASK_COGX, TASK_COGY, TASK_COGZ, TASK_JOINT = 4, 5, 6, 7
+
+
+class _RcsbTaskSpec(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("effector", ctypes.c_int), ("refBdy", ctypes.c_int),
+                ("refFrame", ctypes.c_int)]
 
 
 def lib() -> ctypes.CDLL:
@@ -135,6 +141,8 @@ def lib() -> ctypes.CDLL:
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_void, ctypes.c_uint, c_void)
     sig("rcsb_ik_prio_rmr", c_int, c_void, c_int, c_void, c_void, c_void, c_long, c_dbl_p, c_dbl_p,
         ctypes.c_double, ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_ik_tasks_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
+        ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
     sig("rcsb_group_create", c_int, c_void, c_int, c_void, ctypes.POINTER(c_void))
     sig("rcsb_group_destroy", None, c_void)
@@ -565,6 +573,31 @@ class Model:
             a.ptr(out.get("det"), "det"), ctypes.byref(opt),
             a.flags() | (_IK_LEFT_INVERSE if left_inverse else 0), a.stream())
         _err(rc, "rcsb_ik_rmr_ex")
+        return out
+
+    def ik_tasks_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, want=("det",), out=None):
+        """rcsb_ik_tasks_rmr: RMR steps over any stack of task kinds with reference bodies / frames.
+        tasks: sequence of (kind, effector[, refBdy[, refFrame]]), -1 = none."""
+        N, qdim = self._batch(q)
+        if qdim != self.dof:
+            raise RcsbError("ik_tasks_rmr: q must be N x dof")
+        spec = [tuple(t) + (-1,) * (4 - len(t)) for t in tasks]
+        dims = {TASK_XYZ: 3, TASK_ABC: 3, TASK_XYZABC: 6, TASK_COGX: 1, TASK_COGY: 1, TASK_COGZ: 1, TASK_JOINT: 1}
+        nx = sum(dims.get(int(t[0]), 0) for t in spec)
+        if tuple(x_des.shape) != (N, nx):
+            raise RcsbError(f"ik_tasks_rmr: x_des must be {N} x {nx}")
+        shapes = {"dx": (N, nx), "dq": (N, self.dof), "det": (N,)}
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                out[k] = self._alloc(q, shapes[k])
+        tarr = (_RcsbTaskSpec * max(len(spec), 1))(*[_RcsbTaskSpec(*[int(v) for v in t]) for t in spec])
+        a = _Args(self)
+        rc = lib().rcsb_ik_tasks_rmr(
+            self._h, len(spec), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam), float(alpha),
+            int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"), a.ptr(out.get("det"), "det"),
+            a.flags(), a.stream())
+        _err(rc, "rcsb_ik_tasks_rmr")
         return out
 
     def ik_prio_rmr(self, tasks: Sequence, priority: Sequence[int], q, x_des, activation=None, lam=1.0e-8,

@@ -1490,6 +1490,289 @@ extern "C" int rcsb_ik_rmr_ex(const RcsbModel* cm, int nTasks, const RcsbTask* t
   });
 }
 
+static int RcsGraph_countCoupledColumns(const RcsbModel* m);
+
+/* ---- general task stacks (rcsb_ik_tasks_rmr) ------------------------------------------------ */
+
+static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* tasksIn, const DevicePlan** out)
+{
+  const int nb = m->hdr.nb, dof = m->hdr.dof, nJ = m->hdr.nJ;
+  const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+  const int* jntPrev = m->iarr(RCSB_A_JNT_PREV);
+  const int* bodyLastJnt = m->iarr(RCSB_A_BODY_LASTJNT);
+  const int* bodyParent = m->iarr(RCSB_A_BODY_PARENT);
+  if (nJ > 64)
+  {
+    rcsb_set_error("rcsb_ik_tasks_rmr: more than 64 Jacobian columns (%d)", nJ);
+    return RCSB_EUNSUPPORTED;
+  }
+  if (RcsGraph_countCoupledColumns(m) > 0)
+  {
+    rcsb_set_error("rcsb_ik_tasks_rmr: kinematically coupled unconstrained joints are not supported");
+    return RCSB_EUNSUPPORTED;
+  }
+  std::string key("T");
+  key.append(reinterpret_cast<const char*>(tasksIn), sizeof(RcsbTaskSpec) * (size_t) nTasksIn);
+  std::lock_guard<std::recursive_mutex> lock(m->mtx);
+  auto it = m->ikPlans.find(key);
+  if (it != m->ikPlans.end())
+  {
+    *out = &it->second;
+    return RCSB_OK;
+  }
+
+  /* frame slots: 0 = world, then one per distinct body */
+  std::vector<int> slotBody(1, -1), slotOfBody((size_t) nb, 0);
+  auto slot = [&](int b) {
+    if (b < 0)
+    {
+      return 0;
+    }
+    if (slotOfBody[(size_t) b] == 0)
+    {
+      slotOfBody[(size_t) b] = (int) slotBody.size();
+      slotBody.push_back(b);
+    }
+    return slotOfBody[(size_t) b];
+  };
+  std::vector<int> task;
+  int row = 0, cogRoot = -2;
+  for (int t = 0; t < nTasksIn; ++t)
+  {
+    const RcsbTaskSpec& ts = tasksIn[t];
+    auto bodyOk = [&](int b) { return b >= -1 && b < nb; };
+    if (ts.kind == RCSB_TASK_JOINT)
+    {
+      if (ts.effector < 0 || ts.effector >= dof || jntJacobi[ts.effector] < 0)
+      {
+        rcsb_set_error("task %d: joint %d is out of range or constrained", t, ts.effector);
+        return RCSB_EINVAL;
+      }
+      const int rec[8] = {ts.kind, row, 1, 0, 0, 0, jntJacobi[ts.effector], ts.effector};
+      task.insert(task.end(), rec, rec + 8);
+      row += 1;
+      continue;
+    }
+    if (ts.kind >= RCSB_TASK_COGX && ts.kind <= RCSB_TASK_COGZ)
+    {
+      if (!bodyOk(ts.effector) || ts.refBdy >= 0 || ts.refFrame >= 0)
+      {
+        rcsb_set_error("task %d: COG tasks take a subtree root (or -1) and no reference body", t);
+        return ts.refBdy >= 0 || ts.refFrame >= 0 ? RCSB_EUNSUPPORTED : RCSB_EINVAL;
+      }
+      if (cogRoot != -2 && cogRoot != ts.effector)
+      {
+        rcsb_set_error("task %d: all COG tasks of a call must refer to the same subtree", t);
+        return RCSB_EUNSUPPORTED;
+      }
+      cogRoot = ts.effector;
+      const int rec[8] = {ts.kind, row, 1, 0, 0, 0, ts.kind - RCSB_TASK_COGX, 0};
+      task.insert(task.end(), rec, rec + 8);
+      row += 1;
+      continue;
+    }
+    if (ts.kind != RCSB_TASK_XYZ && ts.kind != RCSB_TASK_ABC && ts.kind != RCSB_TASK_XYZABC)
+    {
+      rcsb_set_error("task %d: unknown kind %d", t, ts.kind);
+      return RCSB_EINVAL;
+    }
+    if (!bodyOk(ts.effector) || !bodyOk(ts.refBdy) || !bodyOk(ts.refFrame))
+    {
+      rcsb_set_error("task %d: body index out of range", t);
+      return RCSB_EINVAL;
+    }
+    const int frameBody = (ts.refFrame < 0 && ts.refBdy >= 0) ? ts.refBdy : ts.refFrame;   /* Task.cpp:160 */
+    const int sE = slot(ts.effector), sR = slot(ts.refBdy), sF = slot(frameBody);
+    if (ts.kind != RCSB_TASK_ABC)
+    {
+      const int rec[8] = {RCSB_TASK_XYZ, row, 3, sE, sR, sF, 0, 0};
+      task.insert(task.end(), rec, rec + 8);
+      row += 3;
+    }
+    if (ts.kind != RCSB_TASK_XYZ)
+    {
+      const int rec[8] = {RCSB_TASK_ABC, row, 3, sE, sR, sF, 0, 0};
+      task.insert(task.end(), rec, rec + 8);
+      row += 3;
+    }
+  }
+  const int nTasks = (int) task.size() / 8, nx = row, nSlotsF = (int) slotBody.size();
+  if (nx > 24 || nSlotsF > 24)
+  {
+    rcsb_set_error("rcsb_ik_tasks_rmr: at most 24 task rows and 23 distinct bodies (%d, %d)", nx, nSlotsF - 1);
+    return RCSB_EUNSUPPORTED;
+  }
+
+  std::vector<unsigned long long> slotMask((size_t) nSlotsF, 0ull);
+  std::vector<int> slotStart((size_t) nb + 1, 0), slotList((size_t) (nSlotsF > 1 ? nSlotsF - 1 : 1), 0);
+  for (int sIdx = 1; sIdx < nSlotsF; ++sIdx)
+  {
+    const int b = slotBody[(size_t) sIdx];
+    slotStart[(size_t) b + 1]++;
+    for (int j = bodyLastJnt[b]; j >= 0; j = jntPrev[j])
+    {
+      if (jntJacobi[j] >= 0)
+      {
+        slotMask[(size_t) sIdx] |= 1ull << jntJacobi[j];
+      }
+    }
+  }
+  for (int b = 0; b < nb; ++b)
+  {
+    slotStart[(size_t) b + 1] += slotStart[(size_t) b];
+  }
+  {
+    std::vector<int> fill(slotStart.begin(), slotStart.end() - 1);
+    for (int sIdx = 1; sIdx < nSlotsF; ++sIdx)
+    {
+      slotList[(size_t) fill[(size_t) slotBody[(size_t) sIdx]]++] = sIdx;
+    }
+  }
+  std::vector<unsigned char> inCog((size_t) nb, 0);
+  for (int b = 0; b < nb && cogRoot != -2; ++b)
+  {
+    bool in = cogRoot == -1;
+    for (int a = b; a >= 0 && !in; a = bodyParent[a])
+    {
+      in = (a == cogRoot);
+    }
+    inCog[(size_t) b] = in ? 1 : 0;
+  }
+  std::vector<int> colJoint((size_t) (nJ > 0 ? nJ : 1), 0);
+  std::vector<double> invWq((size_t) (nJ > 0 ? nJ : 1), 0.0), jlGain(invWq), q0c(invWq);
+  {
+    const double* qMin = m->darr(RCSB_A_JNT_QMIN);
+    const double* qMax = m->darr(RCSB_A_JNT_QMAX);
+    const double* q0 = m->darr(RCSB_A_JNT_Q0);
+    const double* wJL = m->darr(RCSB_A_JNT_WJL);
+    const double* wM = m->darr(RCSB_A_JNT_WMETRIC);
+    for (int j = 0; j < dof; ++j)
+    {
+      const int c = jntJacobi[j];
+      if (c < 0)
+      {
+        continue;
+      }
+      colJoint[(size_t) c] = j;
+      const double range = qMax[j] - qMin[j];
+      invWq[(size_t) c] = wM[j] * range;                              /* RcsGraph_getInvWq, Rcs_graph.c:1087 */
+      jlGain[(size_t) c] = range > 0.0 ? wJL[j] / (range * range) : 0.0;   /* Rcs_kinematics.c:1496 */
+      q0c[(size_t) c] = q0[j];
+    }
+  }
+
+  RcsbIkTasksPlanHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.nTasks = nTasks;
+  ph.nx = nx;
+  ph.nJ = nJ;
+  ph.nSlots = nSlotsF;
+  ph.cogRoot = cogRoot;
+  int off = align16((int) sizeof(ph));
+  auto place = [&](int& field, size_t bytes) {
+    field = off;
+    off = align16(off + (int) (bytes > 0 ? bytes : 4));
+  };
+  place(ph.offTask, task.size() * 4);
+  place(ph.offBodySlotStart, slotStart.size() * 4);
+  place(ph.offBodySlotList, slotList.size() * 4);
+  place(ph.offSlotMask, slotMask.size() * 8);
+  place(ph.offBodyInCog, inCog.size());
+  place(ph.offColJoint, colJoint.size() * 4);
+  place(ph.offInvWq, invWq.size() * 8);
+  place(ph.offJlGain, jlGain.size() * 8);
+  place(ph.offQ0, q0c.size() * 8);
+  ph.totalBytes = off;
+  std::vector<char> blob((size_t) ph.totalBytes, 0);
+  memcpy(blob.data(), &ph, sizeof(ph));
+  memcpy(blob.data() + ph.offTask, task.data(), task.size() * 4);
+  memcpy(blob.data() + ph.offBodySlotStart, slotStart.data(), slotStart.size() * 4);
+  memcpy(blob.data() + ph.offBodySlotList, slotList.data(), slotList.size() * 4);
+  memcpy(blob.data() + ph.offSlotMask, slotMask.data(), slotMask.size() * 8);
+  memcpy(blob.data() + ph.offBodyInCog, inCog.data(), inCog.size());
+  memcpy(blob.data() + ph.offColJoint, colJoint.data(), colJoint.size() * 4);
+  memcpy(blob.data() + ph.offInvWq, invWq.data(), invWq.size() * 8);
+  memcpy(blob.data() + ph.offJlGain, jlGain.data(), jlGain.size() * 8);
+  memcpy(blob.data() + ph.offQ0, q0c.data(), q0c.size() * 8);
+
+  DevicePlan dp;
+  RCSB_CUDA(cudaSetDevice(m->device));
+  RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
+  RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  RCSB_CUDA(cudaDeviceSynchronize());
+  dp.bytes = ph.totalBytes;
+  dp.aux0 = nx;
+  dp.aux1 = nSlotsF;
+  auto ins = m->ikPlans.emplace(key, dp);
+  *out = &ins.first->second;
+  return RCSB_OK;
+}
+
+extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
+                                 const double* xDes, double lambda, double alpha, int iters, double* dx,
+                                 double* dq, double* det, unsigned flags, void* stream)
+{
+  RcsbModel* m = const_cast<RcsbModel*>(cm);
+  if (!m || N < 0 || (N > 0 && (!q || !xDes)) || iters < 0 || nTasks <= 0 || !tasks)
+  {
+    rcsb_set_error("rcsb_ik_tasks_rmr: invalid arguments");
+    return RCSB_EINVAL;
+  }
+  const DevicePlan* plan = nullptr;
+  int rc = buildIkTasksPlan(m, nTasks, tasks, &plan);
+  if (rc != RCSB_OK || N == 0)
+  {
+    return rc;
+  }
+  auto launch = [&](long n, double* q_, const double* x_, double* dx_, double* dq_, double* det_,
+                    cudaStream_t st) -> int {
+    rcsb::IkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.model = m->dev;
+    a.plan = plan->dev;
+    a.modelBytes = m->hdr.totalBytes;
+    a.planBytes = plan->bytes;
+    a.N = n;
+    a.q = q_;
+    a.xDes = x_;
+    a.lambda = lambda;
+    a.alpha = alpha;
+    a.iters = iters;
+    a.dx = dx_;
+    a.dq = dq_;
+    a.det = det_;
+    RCSB_CUDA(cudaSetDevice(m->device));
+    cudaError_t e = rcsb_launch_ik_tasks(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, plan->aux1, st);
+    if (e == cudaErrorInvalidValue)
+    {
+      cudaGetLastError();
+      rcsb_set_error("rcsb_ik_tasks_rmr: problem too large (nx %d, nJ %d, dof %d; limits 24 / 40 / 72)",
+                     plan->aux0, m->hdr.nJ, m->hdr.dof);
+      return RCSB_EUNSUPPORTED;
+    }
+    RCSB_CUDA(e);
+    g_launches.fetch_add(1);
+    return RCSB_OK;
+  };
+  if (!(flags & RCSB_HOST_PTRS))
+  {
+    return launch(N, q, xDes, dx, dq, det, static_cast<cudaStream_t>(stream));
+  }
+  const size_t dof = (size_t) m->hdr.dof, nx = (size_t) plan->aux0;
+  std::vector<StagedArray> arr;
+  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET };
+  arr.push_back({q, nullptr, dof, nullptr});
+  arr.push_back({xDes, nullptr, nx, nullptr});
+  arr.push_back({nullptr, q, dof, nullptr});
+  arr.push_back({nullptr, dx, dx ? nx : 0, nullptr});
+  arr.push_back({nullptr, dq, dq ? dof : 0, nullptr});
+  arr.push_back({nullptr, det, (size_t) (det ? 1 : 0), nullptr});
+  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
+    auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
+    return launch(n, arr[I_QIN].dev, arr[I_X].dev, dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), st);
+  });
+}
+
 extern "C" int rcsb_ik_prio_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, const int* priority,
                                 const double* activation, long N, double* q, const double* xDes,
                                 double lambda, double alpha, int iters, double* dq1, double* dq2,

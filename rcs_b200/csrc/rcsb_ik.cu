@@ -1261,6 +1261,483 @@ ikPrioKernel(const IkArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* General task stacks                                                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+struct IkTasksPlanView
+{
+  const RcsbIkTasksPlanHeader* hdr;
+  const int* task;
+  const int* bodySlotStart;
+  const int* bodySlotList;
+  const unsigned long long* slotMask;
+  const unsigned char* bodyInCog;
+  const int* colJoint;
+  const double* invWq;
+  const double* jlGain;
+  const double* q0;
+
+  __device__ __forceinline__ void bind(const char* blob)
+  {
+    hdr = reinterpret_cast<const RcsbIkTasksPlanHeader*>(blob);
+    task = reinterpret_cast<const int*>(blob + hdr->offTask);
+    bodySlotStart = reinterpret_cast<const int*>(blob + hdr->offBodySlotStart);
+    bodySlotList = reinterpret_cast<const int*>(blob + hdr->offBodySlotList);
+    slotMask = reinterpret_cast<const unsigned long long*>(blob + hdr->offSlotMask);
+    bodyInCog = reinterpret_cast<const unsigned char*>(blob + hdr->offBodyInCog);
+    colJoint = reinterpret_cast<const int*>(blob + hdr->offColJoint);
+    invWq = reinterpret_cast<const double*>(blob + hdr->offInvWq);
+    jlGain = reinterpret_cast<const double*>(blob + hdr->offJlGain);
+    q0 = reinterpret_cast<const double*>(blob + hdr->offQ0);
+  }
+};
+
+/*
+ * rcsb_ik_tasks_rmr: one thread per state. Per iteration: forward kinematics of the whole tree
+ * (frames of the bodies the tasks refer to, axis and origin of every Jacobian column, centre of
+ * gravity and its Jacobian if a COG task asks for it), the task values, errors and Jacobian rows of
+ * every task in the reference's formulations (see rcsb.h), then dq = J# dx + (1 - J# J) invWq
+ * (-alpha dH) with J# from MatNd_rwPinv (IkSolverRMR.cpp:415-596), q += dq.
+ */
+template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT, int NSLOTS>
+__global__ void __launch_bounds__(RCSB_IK_THREADS)
+ikTasksKernel(const IkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sModel = smem;
+  char* sPlan = smem + a.modelBytes;
+  stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planBytes);
+
+  ModelView m;
+  m.bind(sModel);
+  IkTasksPlanView p;
+  p.bind(sPlan);
+
+  const long s = (long) blockIdx.x * RCSB_IK_THREADS + threadIdx.x;
+  if (s >= a.N)
+  {
+    return;
+  }
+  const int nb = m.hdr->nb;
+  const int dof = m.hdr->dof;
+  const int nJ = p.hdr->nJ;
+  const int nx = p.hdr->nx;
+  const int nTasks = p.hdr->nTasks;
+  const bool wantCog = p.hdr->cogRoot >= -1 && p.hdr->cogRoot != -2;
+
+  double qv[MAXDOF];
+  double ja[6 * MAXNJ];            /* axis, origin of every Jacobian column */
+  double fr[12 * MAXSLOT];         /* frames of the task bodies; slot 0 = world */
+  double J[MAXNX * MAXNJ], P[MAXNJ * MAXNX], A[MAXNX * MAXNX], Ai[MAXNX * MAXNX];
+  double Jc[3 * MAXNJ];            /* sum of m_b JT_b(COM_b) over the COG bodies */
+  double dx[MAXNX], g[MAXNJ], Jg[MAXNX], dq[MAXNJ];
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
+  double det = 0.0;
+
+  for (int j = 0; j < dof; ++j)
+  {
+    qv[j] = a.q[s * dof + j];
+  }
+  for (int i = 0; i < nJ; ++i)
+  {
+    dq[i] = 0.0;
+  }
+  for (int i = 0; i < nx; ++i)
+  {
+    dx[i] = 0.0;
+  }
+  {
+    Frame id;
+    setIdentity(id);
+    for (int i = 0; i < 3; ++i)
+    {
+      fr[i] = id.o[i];
+    }
+    for (int i = 0; i < 9; ++i)
+    {
+      fr[3 + i] = id.R[i];
+    }
+  }
+  const int nCpl = m.hdr->nCpl;
+  auto updateSlaves = [&]() {
+    for (int c = 0; c < nCpl; ++c)
+    {
+      qv[m.cpl[c].slave] = slaveAngle(m.cpl[c], qv[m.cpl[c].master]);
+    }
+  };
+
+  for (int it = 0; it < a.iters; ++it)
+  {
+    updateSlaves();
+    /* ---- forward kinematics --------------------------------------------------------------- */
+    double mTot = 0.0, mc[3] = {0.0, 0.0, 0.0};
+    if (wantCog)
+    {
+      for (int i = 0; i < 3 * nJ; ++i)
+      {
+        Jc[i] = 0.0;
+      }
+    }
+    Frame f, keep;
+    setIdentity(f);
+    keep = f;
+    for (int b = 0; b < nb; ++b)
+    {
+      const int ld = m.bodyLoad[b];
+      const int bflags = m.bodyFlags[b];
+      if (ld == RCSB_LOAD_IDENT)
+      {
+        setIdentity(f);
+      }
+      else if (NSLOTS > 0 && ld >= 0)
+      {
+        const double* sp = stk + ld * 12;
+        for (int i = 0; i < 3; ++i)
+        {
+          f.o[i] = sp[i];
+        }
+        for (int i = 0; i < 9; ++i)
+        {
+          f.R[i] = sp[3 + i];
+        }
+      }
+      if (bflags & RCSB_BF_LEAF)
+      {
+        keep = f;
+      }
+      const int j0 = m.bodyJntStart[b];
+      const int j1 = j0 + m.bodyJntCount[b];
+      for (int j = j0; j < j1; ++j)
+      {
+        const int jf = m.jntFlags[j];
+        if (jf & RCSB_JF_HAS_AJP)
+        {
+          applyRelF(f, m.jntAJP + 12 * j, jf);
+        }
+        const double qj = qv[j];
+        const int dir = m.jntType[j] % 3;
+        double ax[3];
+        if (jf & RCSB_JF_ROT)
+        {
+          double sn, cs;
+          sincos(qj, &sn, &cs);
+          rotateAboutAxis(f, dir, sn, cs);
+          axisOf(f, dir, ax);
+        }
+        else
+        {
+          axisOf(f, dir, ax);
+          f.o[0] += qj * ax[0];
+          f.o[1] += qj * ax[1];
+          f.o[2] += qj * ax[2];
+        }
+        const int col = m.jntJacobi[j];
+        if (col >= 0)
+        {
+          double* d = ja + 6 * col;
+          d[0] = ax[0];
+          d[1] = ax[1];
+          d[2] = ax[2];
+          d[3] = f.o[0];
+          d[4] = f.o[1];
+          d[5] = f.o[2];
+        }
+      }
+      if (bflags & RCSB_BF_HAS_ABP)
+      {
+        applyRelF(f, m.bodyABP + 12 * b, bflags);
+      }
+      if (NSLOTS > 0)
+      {
+        const int sv = m.bodySave[b];
+        if (sv >= 0)
+        {
+          double* sp = stk + sv * 12;
+          for (int i = 0; i < 3; ++i)
+          {
+            sp[i] = f.o[i];
+          }
+          for (int i = 0; i < 9; ++i)
+          {
+            sp[3 + i] = f.R[i];
+          }
+        }
+      }
+      for (int k = p.bodySlotStart[b]; k < p.bodySlotStart[b + 1]; ++k)
+      {
+        double* d = fr + 12 * p.bodySlotList[k];
+        for (int i = 0; i < 3; ++i)
+        {
+          d[i] = f.o[i];
+        }
+        for (int i = 0; i < 9; ++i)
+        {
+          d[3 + i] = f.R[i];
+        }
+      }
+      /* centre of gravity and sum_b m_b JT_b(COM_b) (RcsGraph_COG_Body / RcsGraph_COGJacobian_Body,
+       * Rcs_kinematics.c:938, :1004): the body's ancestor joints have all been visited */
+      if (wantCog && (bflags & RCSB_BF_HAS_MASS) && p.bodyInCog[b])
+      {
+        const double mass = m.bodyMass[b];
+        const double* cl = m.bodyCom + 3 * b;
+        const double* R = f.R;
+        const double c[3] = {f.o[0] + (R[0] * cl[0] + R[3] * cl[1] + R[6] * cl[2]),
+                             f.o[1] + (R[1] * cl[0] + R[4] * cl[1] + R[7] * cl[2]),
+                             f.o[2] + (R[2] * cl[0] + R[5] * cl[1] + R[8] * cl[2])};
+        mTot += mass;
+        mc[0] += mass * c[0];
+        mc[1] += mass * c[1];
+        mc[2] += mass * c[2];
+        for (int j = m.bodyLastJnt[b]; j >= 0; j = m.jntPrev[j])
+        {
+          const int col = m.jntJacobi[j];
+          if (col < 0)
+          {
+            continue;
+          }
+          const double* jc = ja + 6 * col;
+          if (m.jntFlags[j] & RCSB_JF_ROT)
+          {
+            const double d0 = c[0] - jc[3], d1 = c[1] - jc[4], d2 = c[2] - jc[5];
+            Jc[col] += mass * (jc[1] * d2 - jc[2] * d1);
+            Jc[nJ + col] += mass * (jc[2] * d0 - jc[0] * d2);
+            Jc[2 * nJ + col] += mass * (jc[0] * d1 - jc[1] * d0);
+          }
+          else
+          {
+            Jc[col] += mass * jc[0];
+            Jc[nJ + col] += mass * jc[1];
+            Jc[2 * nJ + col] += mass * jc[2];
+          }
+        }
+      }
+      if (bflags & RCSB_BF_LEAF)
+      {
+        f = keep;
+      }
+    }
+
+    /* ---- task values, errors and Jacobian rows --------------------------------------------- */
+    for (int i = 0; i < nx * nJ; ++i)
+    {
+      J[i] = 0.0;
+    }
+    const double invM = mTot > 0.0 ? 1.0 / mTot : 0.0;
+    for (int t = 0; t < nTasks; ++t)
+    {
+      const int* tk = p.task + 8 * t;
+      const int kind = tk[0], row = tk[1], sE = tk[3], sR = tk[4], sF = tk[5], aux = tk[6];
+      const double* xd = a.xDes + s * nx + row;
+      const double* fE = fr + 12 * sE;
+      const double* fR = fr + 12 * sR;
+      const double* fF = fr + 12 * sF;
+      double* Jr = J + row * nJ;
+      if (kind == RCSB_TASK_JOINT)
+      {
+        dx[row] = xd[0] - qv[tk[7]];
+        Jr[aux] = 1.0;
+        continue;
+      }
+      if (kind >= RCSB_TASK_COGX && kind <= RCSB_TASK_COGZ)
+      {
+        dx[row] = xd[0] - mc[aux] * invM;
+        for (int k = 0; k < nJ; ++k)
+        {
+          Jr[k] = Jc[aux * nJ + k] * invM;
+        }
+        continue;
+      }
+      const unsigned long long mE = p.slotMask[sE], mR = p.slotMask[sR], mF = p.slotMask[sF];
+      if (kind == RCSB_TASK_XYZ)
+      {
+        /* TaskPosition3D::computeX: I_r = o_E - o_R, rotated into refFrame (or refBdy) */
+        double r[3] = {fE[0], fE[1], fE[2]};
+        const double* Arot = nullptr;
+        if (sR > 0)
+        {
+          r[0] -= fR[0];
+          r[1] -= fR[1];
+          r[2] -= fR[2];
+          Arot = (sF > 0 && sF != sR) ? fF + 3 : fR + 3;
+        }
+        else if (sF > 0)
+        {
+          Arot = fF + 3;
+        }
+        double x[3] = {r[0], r[1], r[2]};
+        if (Arot)
+        {
+          x[0] = Arot[0] * r[0] + Arot[1] * r[1] + Arot[2] * r[2];
+          x[1] = Arot[3] * r[0] + Arot[4] * r[1] + Arot[5] * r[2];
+          x[2] = Arot[6] * r[0] + Arot[7] * r[1] + Arot[8] * r[2];
+        }
+        dx[row] = xd[0] - x[0];
+        dx[row + 1] = xd[1] - x[1];
+        dx[row + 2] = xd[2] - x[2];
+        /* RcsGraph_3dPosJacobian: JT_2, or A (JT_2 - JT_1 + r_12 x JR_3) */
+        for (int k = 0; k < nJ; ++k)
+        {
+          const double* jc = ja + 6 * k;
+          const bool isRot = (m.jntFlags[p.colJoint[k]] & RCSB_JF_ROT) != 0;
+          auto colT = [&](const double* fo, bool on, double (&c)[3]) {
+            c[0] = c[1] = c[2] = 0.0;
+            if (on)
+            {
+              if (isRot)
+              {
+                const double d0 = fo[0] - jc[3], d1 = fo[1] - jc[4], d2 = fo[2] - jc[5];
+                c[0] = jc[1] * d2 - jc[2] * d1;
+                c[1] = jc[2] * d0 - jc[0] * d2;
+                c[2] = jc[0] * d1 - jc[1] * d0;
+              }
+              else
+              {
+                c[0] = jc[0];
+                c[1] = jc[1];
+                c[2] = jc[2];
+              }
+            }
+          };
+          double v[3];
+          colT(fE, sE > 0 && ((mE >> k) & 1ull), v);
+          if (sR > 0)
+          {
+            double j1[3];
+            colT(fR, (mR >> k) & 1ull, j1);
+            v[0] -= j1[0];
+            v[1] -= j1[1];
+            v[2] -= j1[2];
+            if (sF > 0 && isRot && ((mF >> k) & 1ull))
+            {
+              const double w0 = jc[0], w1 = jc[1], w2 = jc[2];
+              v[0] += r[1] * w2 - r[2] * w1;
+              v[1] += -r[0] * w2 + r[2] * w0;
+              v[2] += r[0] * w1 - r[1] * w0;
+            }
+          }
+          if (Arot)
+          {
+            const double x0 = v[0], y0 = v[1], z0 = v[2];
+            v[0] = Arot[0] * x0 + Arot[1] * y0 + Arot[2] * z0;
+            v[1] = Arot[3] * x0 + Arot[4] * y0 + Arot[5] * z0;
+            v[2] = Arot[6] * x0 + Arot[7] * y0 + Arot[8] * z0;
+          }
+          Jr[k] = v[0];
+          Jr[nJ + k] = v[1];
+          Jr[2 * nJ + k] = v[2];
+        }
+        continue;
+      }
+      /* RCSB_TASK_ABC: Euler angles of A_ER = A_E A_R^T (Task::computeRelativeRotationMatrix,
+       * Task.cpp:1204), error as TaskEuler3D::computeDX */
+      {
+        double Aer[9];
+        const double* AE = fE + 3;
+        const double* AR = fR + 3;
+        for (int i = 0; i < 3; ++i)
+        {
+          for (int j = 0; j < 3; ++j)
+          {
+            Aer[3 * i + j] = AE[3 * i] * AR[3 * j] + AE[3 * i + 1] * AR[3 * j + 1] + AE[3 * i + 2] * AR[3 * j + 2];
+          }
+        }
+        double xc[3];
+        const double xdl[3] = {xd[0], xd[1], xd[2]};
+        toEuler(xc, Aer);
+        eulerTaskError(dx + row, xdl, xc);
+        /* RcsGraph_3dOmegaJacobian: JR_2, A_1 JR_2 (fixed reference), or A_3 (JR_2 - JR_1) */
+        const bool fixedRef = sR > 0 && sF == sR && mR == 0ull;
+        const bool relative = !(sR == 0 && sF == 0) && !fixedRef;
+        const double* Arot = fixedRef ? fR + 3 : ((relative && sF > 0) ? fF + 3 : nullptr);
+        for (int k = 0; k < nJ; ++k)
+        {
+          const double* jc = ja + 6 * k;
+          const bool isRot = (m.jntFlags[p.colJoint[k]] & RCSB_JF_ROT) != 0;
+          double sgn = (sE > 0 && isRot && ((mE >> k) & 1ull)) ? 1.0 : 0.0;
+          if (relative && sR > 0 && isRot && ((mR >> k) & 1ull))
+          {
+            sgn -= 1.0;
+          }
+          double v[3] = {sgn * jc[0], sgn * jc[1], sgn * jc[2]};
+          if (Arot)
+          {
+            const double x0 = v[0], y0 = v[1], z0 = v[2];
+            v[0] = Arot[0] * x0 + Arot[1] * y0 + Arot[2] * z0;
+            v[1] = Arot[3] * x0 + Arot[4] * y0 + Arot[5] * z0;
+            v[2] = Arot[6] * x0 + Arot[7] * y0 + Arot[8] * z0;
+          }
+          Jr[k] = v[0];
+          Jr[nJ + k] = v[1];
+          Jr[2 * nJ + k] = v[2];
+        }
+      }
+    }
+
+    /* ---- dq = J# dx + (1 - J# J) invWq (-alpha dH) ------------------------------------------ */
+    for (int i = 0; i < nJ; ++i)
+    {
+      const double delta = qv[p.colJoint[i]] - p.q0[i];
+      g[i] = p.invWq[i] * (-(a.alpha * (p.jlGain[i] * delta)));
+    }
+    det = rwPinvSmall(J, nx, nJ, p.invWq, a.lambda, P, A, Ai);
+    if (det == 0.0)
+    {
+      for (int i = 0; i < nJ; ++i)
+      {
+        dq[i] = 0.0;
+      }
+      continue;
+    }
+    for (int r = 0; r < nx; ++r)
+    {
+      double sum = 0.0;
+      for (int i = 0; i < nJ; ++i)
+      {
+        sum += J[r * nJ + i] * g[i];
+      }
+      Jg[r] = sum;
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      double ts = 0.0, ns = 0.0;
+      for (int c = 0; c < nx; ++c)
+      {
+        ts += P[i * nx + c] * dx[c];
+        ns += P[i * nx + c] * Jg[c];
+      }
+      dq[i] = ts + (g[i] - ns);
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      qv[p.colJoint[i]] += dq[i];
+    }
+  }
+  updateSlaves();
+
+  for (int j = 0; j < dof; ++j)
+  {
+    a.q[s * dof + j] = qv[j];
+    if (a.dq)
+    {
+      const int c = m.jntJacobi[j];
+      a.dq[s * dof + j] = c >= 0 ? dq[c] : 0.0;
+    }
+  }
+  if (a.dx)
+  {
+    for (int i = 0; i < nx; ++i)
+    {
+      a.dx[s * nx + i] = dx[i];
+    }
+  }
+  if (a.det)
+  {
+    a.det[s] = det;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Single-chain fast path                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -2719,6 +3196,51 @@ static cudaError_t launchIkPrio(const IkArgs& a, int nSlots, cudaStream_t stream
 }
 
 }   // namespace rcsb
+
+template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT>
+static cudaError_t launchIkTasks(const rcsb::IkArgs& a, int nSlots, cudaStream_t stream)
+{
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes;
+  const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
+  if (nSlots <= 0)
+  {
+    auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, 0>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes);
+    if (e != cudaSuccess)
+    {
+      return e;
+    }
+    k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);
+    return cudaGetLastError();
+  }
+  auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, RCSB_MAX_FRAME_SLOTS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes);
+  if (e != cudaSuccess)
+  {
+    return e;
+  }
+  k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
+                                            int nFrameSlots, cudaStream_t stream)
+{
+  using namespace rcsb;
+  if (a->N <= 0)
+  {
+    return cudaSuccess;
+  }
+  if (nx <= 12 && nJ <= 8 && dof <= 12 && nFrameSlots <= 12)
+  {
+    return launchIkTasks<12, 8, 12, 12>(*a, nSlots, stream);
+  }
+  if (nx <= 24 && nJ <= 40 && dof <= 72 && nFrameSlots <= 24)
+  {
+    return launchIkTasks<24, 40, 72, 24>(*a, nSlots, stream);
+  }
+  return cudaErrorInvalidValue;
+}
 
 extern "C" cudaError_t rcsb_launch_ik_prio(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
                                            cudaStream_t stream)

@@ -121,6 +121,8 @@ cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nJ2, i
 /* maximum dynamic shared memory of the assembly kernel for a record of recDoubles (plan checks) */
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            int multiNu, int nEffs, int nTasks, cudaStream_t stream);
+cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int nFrameSlots,
+                                 cudaStream_t stream);
 cudaError_t rcsb_launch_ik_prio(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
                                 cudaStream_t stream);
 }

@@ -276,6 +276,32 @@ typedef struct
   int pad;
 } RcsbIkPlanHeader;
 
+/*
+ * Plan of the general task-stack solver (rcsb_ik_tasks_rmr, ikTasksKernel): any mix of the task kinds
+ * of rcsb.h with reference bodies / frames. Bodies the tasks refer to get frame slots; slot 0 is
+ * reserved for "no body" (world: identity frame, no columns).
+ */
+typedef struct
+{
+  int nTasks;
+  int nx;               /* rows of the stacked Jacobian */
+  int nJ;
+  int totalBytes;
+  int nSlots;           /* frame slots incl. slot 0 */
+  int cogRoot;          /* body whose subtree the COG tasks refer to, -1 = the whole graph, -2 = no COG task */
+  int offTask;          /* int[nTasks][8]: {kind, row, dim, slotE, slotR, slotF, aux (joint column / COG
+                           component), jointIndex} */
+  int offBodySlotStart; /* int[nb + 1]: CSR over the frame slots of each body */
+  int offBodySlotList;  /* int[number of slots - 1] */
+  int offSlotMask;      /* unsigned long long[nSlots]: bit k set if column k moves the slot's body */
+  int offBodyInCog;     /* unsigned char[nb]: 1 if the body counts for the COG tasks */
+  int offColJoint;      /* int[nJ] */
+  int offInvWq;         /* double[nJ] */
+  int offJlGain;        /* double[nJ] */
+  int offQ0;            /* double[nJ] */
+  int pad;
+} RcsbIkTasksPlanHeader;
+
 #ifdef __cplusplus
 }
 #endif
