@@ -103,7 +103,7 @@ class Workload:
             self.per_gpu = 1 << 18
             self.scaling = "weak"
             self.bytes_per_unit = 2 * 65 * 8 + (34 * 34 + 2 * 34 + 1) * 8     # 10840
-            self.kernel = "rcsb kinetic-terms kernels (see DESIGN.md)"
+            self.kernel = "rcsb::ktWalkKernel<VEL> + rcsb::ktAssembleKernel<VEL>"
             self.desc = ("configs[2]: GenericHumanoid (dof 65, nJ 34, 63 bodies), "
                          "RcsGraph_computeKineticTerms M, h, F_gravity, E; q and q_dot uniformly sampled")
             self.l2 = "per-step working set 2.8 GB per GPU >> 126 MB L2 (no flush needed)"
@@ -124,7 +124,7 @@ class Workload:
             self.scaling = "weak"
             # q + 63 frames + 20 task rows x 34 + M
             self.bytes_per_unit = 65 * 8 + 63 * 96 + 20 * 34 * 8 + 34 * 34 * 8   # 21256
-            self.kernel = "rcsb whole-body kernels (see DESIGN.md)"
+            self.kernel = "rcsb::ktWalkKernel<WB> (frames + records) + rcsb::ktAssembleKernel (M, COG and task Jacobians)"
             self.desc = ("configs[4]: GenericHumanoid (dof 65, nJ 34, 63 bodies), FK of all 63 bodies + the task "
                          "Jacobians of cAction.xml's active set (hands XYZ, COG x/y, both feet XYZABC relative to "
                          "the Heel: nx 20) + mass matrix; N > 1: all-gather of both hand-tip frames (192 B per state)")
@@ -679,8 +679,14 @@ def measure_ours(name: str, args, ctx: Ctx, cpu_seconds: float = 4.0):
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         counters = profile_record(wl.name)
-        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` "
-                        "capture (profiles/kernel_counters.json), not measured in this run")
+        # the committed capture may cover fewer units than one step (whole-body: one pass of the
+        # kernel pair over 414,336 states): scale its DRAM bytes to the units of a step
+        if counters.get("dram_bytes_per_launch") and counters.get("units_per_launch"):
+            counters = dict(counters)
+            counters["dram_bytes_per_launch"] = counters["dram_bytes_per_launch"] * n / counters["units_per_launch"]
+        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` captures "
+                        "of this workload's kernels (profiles/kernel_counters.json, profiles/r02_*), per step; "
+                        "not measured in this run")
         if wl.name == "ik":
             peak, peak_src = fp64_peak_tflops()
             flops = counters.get("fp64_flops_per_unit")
@@ -755,10 +761,10 @@ def measure_group_abi(args, ctx: Ctx):
     out = {"devices": world, "api": "rcsb_group_fk_jacobians_mass / rcsb_group_ik_rmr (include/rcsb.h)"}
     steps = max(2, min(args.steps, 4))
 
-    # fkm: 1M states per device
+    # fkm: 256K states per device (host arrays of the whole batch: 0.5 GB of pinned memory per device)
     g = rcs_b200.Graph(Workload("fkm", world).graph_file)
     grp = rcs_b200.Group(g, list(range(world)))
-    n = (1 << 20) * world
+    n = (1 << 18) * world
     tip = g.body_index("BallTip")
     q = rcs_b200.pinned_empty((n, g.dof))
     q.copy_(torch.from_numpy(workload.sample_states(g.layout(), n)))
