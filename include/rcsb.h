@@ -37,7 +37,10 @@
  *    results are in host memory. Selector arrays (bodySel, effBody, effPt) are always small
  *    host arrays.
  *  - stream is a cudaStream_t (NULL = default stream). Device-pointer calls are
- *    asynchronous on that stream. A model is immutable and may be shared by threads.
+ *    asynchronous on that stream. A model is immutable and may be shared by threads; the
+ *    kinetic-terms, COG, direct-dynamics and whole-body calls keep one per-state record workspace
+ *    per model, so device-pointer calls of those four on ONE model must be issued on one stream
+ *    at a time (host-pointer calls serialise themselves).
  *  - There is no CPU fallback: without a CUDA device every compute call fails with
  *    RCSB_ENODEVICE.
  */

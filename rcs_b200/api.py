@@ -284,7 +284,11 @@ class Graph:
 
 
 def _is_torch(x) -> bool:
-    return x is not None and type(x).__module__.startswith("torch")
+    if x is None or not type(x).__module__.startswith("torch"):
+        return False
+    import torch
+
+    return isinstance(x, torch.Tensor)
 
 
 class _Args:
@@ -371,6 +375,14 @@ class Model:
         return np.empty(shape, dtype=np.float64)
 
     @staticmethod
+    def _check(what, arrays, shapes):
+        """Caller-supplied arrays must have exactly the shape the C call will read / write: the C
+        ABI trusts the sizes, a short buffer would be an out-of-bounds access on the device."""
+        for k, v in arrays.items():
+            if v is not None and k in shapes and tuple(v.shape) != tuple(shapes[k]):
+                raise RcsbError(f"{what}: {k} has shape {tuple(v.shape)}, expected {tuple(shapes[k])}")
+
+    @staticmethod
     def _batch(q):
         if q.ndim != 2:
             raise RcsbError("q must be N x qdim")
@@ -392,6 +404,7 @@ class Model:
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("fk", dict(out, qd=qd), dict(shapes, qd=(N, qdim)))
         a = _Args(self)
         sel, ns = _int_array(bodies)
         rc = lib().rcsb_fk(
@@ -416,6 +429,7 @@ class Model:
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("fk_jacobians", out, shapes)
         a = _Args(self)
         sel, ns = _int_array(bodies)
         eff, ne = _int_array(effectors)
@@ -486,6 +500,7 @@ class Model:
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("kinetic_terms", dict(out, qd=qd), dict(shapes, qd=(N, qdim)))
         a = _Args(self)
         if "cog" in out or "Jcog" in out:
             rc = lib().rcsb_kinetic_terms_cog(
@@ -511,6 +526,8 @@ class Model:
         for k in set(want) | {"qdd"}:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("direct_dynamics", dict(out, qd=qd, F_ext=F_ext, F_jnt=F_jnt),
+                    dict(shapes, qd=(N, qdim), F_ext=(N, self.nJ), F_jnt=(N, self.nJ)))
         a = _Args(self)
         rc = lib().rcsb_direct_dynamics(
             self._h, N, qdim, a.ptr(q, "q"), a.ptr(qd, "qd"), a.ptr(F_ext, "F_ext"),
@@ -527,6 +544,7 @@ class Model:
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("cog", out, shapes)
         a = _Args(self)
         rc = lib().rcsb_cog(self._h, N, qdim, a.ptr(q, "q"), a.ptr(out.get("cog"), "cog"),
                             a.ptr(out.get("Jcog"), "Jcog"), a.flags(), a.stream())
@@ -648,6 +666,7 @@ class Model:
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check("ik_rmr", dict(out, x_des=x_des), dict(shapes, x_des=(N, nx)))
         tarr = (_RcsbTask * max(len(tasks), 1))(*[_RcsbTask(int(k), int(e)) for k, e in tasks])
         a = _Args(self)
         rc = lib().rcsb_ik_rmr(

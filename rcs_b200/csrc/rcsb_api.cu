@@ -631,6 +631,9 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   RCSB_CUDA(cudaSetDevice(m->device));
   RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
   RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  /* pageable source: the call may return before the DMA has landed, and the first launch can
+   * follow on a non-blocking stream that is not ordered against it */
+  RCSB_CUDA(cudaDeviceSynchronize());
   dp.bytes = ph.totalBytes;
   dp.nScrRows = ph.nScrRows;
   dp.nSel = nOut;
@@ -822,6 +825,10 @@ extern "C" int rcsb_model_create(const RcsGraph* graph, int device, RcsbModel** 
   if (ce == cudaSuccess)
   {
     ce = cudaMemcpy(m->dev, m->host.data(), bytes, cudaMemcpyHostToDevice);
+  }
+  if (ce == cudaSuccess)
+  {
+    ce = cudaDeviceSynchronize();   /* pageable source: see buildFkPlan */
   }
   if (ce == cudaSuccess)
   {

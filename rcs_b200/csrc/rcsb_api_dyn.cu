@@ -1205,6 +1205,7 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   RCSB_CUDA(cudaSetDevice(m->device));
   RCSB_CUDA(cudaMalloc(&dp.dev, blob.size()));
   RCSB_CUDA(cudaMemcpy(dp.dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  RCSB_CUDA(cudaDeviceSynchronize());   /* pageable source: the plan must have landed before the first launch */
   dp.bytes = ph.totalBytes;
   dp.aux0 = ph.nx;
   dp.aux1 = ph.chainNc;
