@@ -23,6 +23,11 @@
  *                        (src/RcsCore/ControllerBase.cpp:776, :896, :1332) +
  *                        IkSolverRMR::solveRightInverse (src/RcsCore/IkSolverRMR.cpp:403)
  *                        iterated as in examples/ExampleIK.cpp:154-177
+ *   rcsb_ik_rmr_ex       the same with activations, lambda vector, dq_ts / dq_ns, left inverse with
+ *                        TaskSpaceBlender weights (IkSolverRMR.cpp:205-272, :385-596)
+ *   rcsb_ik_tasks_rmr    the same over XYZ / ABC / XYZABC with refBdy / refFrame, COGX/Y/Z, Joint, POLAR
+ *   rcsb_ik_prio_rmr     IkSolverPrioRMR::solve        src/RcsCore/IkSolverPrioRMR.cpp:178
+ *   rcsb_ik_constraint_rmr   IkSolverConstraintRMR::solveRightInverse  IkSolverConstraintRMR.cpp:156
  *
  * Conventions
  *  - Every call returns 0 on success, a negative RCSB_E* code otherwise; the message is
@@ -282,9 +287,15 @@ int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, 
  *           Rcs_kinematics.c:904-1036); no reference body
  *   JOINT   TaskJoint (TaskJoint.cpp:227-265): the value of joint `effector` (a jointIndex; the
  *           joint must be unconstrained)
+ *   POLARX / POLARY / POLARZ   TaskPolar2D (controlVariable "POLAR" with axisDirection "X" / "Y" /
+ *           "Z", the default; TaskPolar2D.cpp:131-290): the polar angles (phi, theta) of that axis
+ *           of the effector in the frame of refBdy (world if -1): x = Vec3d_getPolarAngles of the
+ *           axis' row of A_ER, dx = Vec3d_getPolarErrorFromDirection (Rcs_Vec3d.c:233), J = the two
+ *           rows of RcsGraph_3dOmegaJacobian(effector, refBdy, effector) across the axis; refFrame
+ *           is not used
  * effector / refBdy / refFrame: depth-first body indices, -1 = none; refFrame = -1 with a refBdy
  * means refFrame = refBdy, as the reference's XML constructor does (Task.cpp:160). xDes [N x nx],
- * nx = sum of the task dimensions (3, 3, 6, 1, 1). Outputs of the last iteration (may be NULL):
+ * nx = sum of the task dimensions (3, 3, 6, 1, 1, 2). Outputs of the last iteration (may be NULL):
  * dx [N x nx], dq [N x dof], det [N]. One thread per state, the reference's literal algebra;
  * up to 24 rows; models with kinematically coupled unconstrained joints are not supported here.
  */
@@ -292,6 +303,9 @@ int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, 
 #define RCSB_TASK_COGY 5
 #define RCSB_TASK_COGZ 6
 #define RCSB_TASK_JOINT 7
+#define RCSB_TASK_POLARX 8
+#define RCSB_TASK_POLARY 9
+#define RCSB_TASK_POLARZ 10
 typedef struct
 {
   int kind;         /* RCSB_TASK_* */
@@ -302,6 +316,22 @@ typedef struct
 int rcsb_ik_tasks_rmr(const RcsbModel* model, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
                       const double* xDes, double lambda, double alpha, int iters, double* dx, double* dq,
                       double* det, unsigned flags, void* stream);
+
+/*
+ * IkSolverConstraintRMR::solveRightInverse (src/RcsCore/IkSolverConstraintRMR.cpp:156-262), its
+ * joint-limit active set (no collision model): the step of rcsb_ik_tasks_rmr; then every
+ * unconstrained joint that this step would leave closer than 2 degrees to q_min / q_max, and that is
+ * not a JOINT task of its own, becomes a joint constraint (a unit row of J; target 0, or a tenth of
+ * 0.1 degrees back towards the margin if it is more than 0.1 degrees beyond it) and the step is
+ * solved once more with these rows appended in joint order; q += dq, `iters` times. Arguments as
+ * rcsb_ik_tasks_rmr (dx: the task rows); det is the determinant of the last solve; nViolations [N]
+ * (may be NULL) = number of joint constraints of the last iteration. Up to 16 rows in all for models
+ * with nJ <= 8, else up to 32; a state that would need more keeps the unconstrained step and
+ * reports -1.
+ */
+int rcsb_ik_constraint_rmr(const RcsbModel* model, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
+                           const double* xDes, double lambda, double alpha, int iters, double* dx, double* dq,
+                           double* det, double* nViolations, unsigned flags, void* stream);
 
 /* ---- multi-GPU summary statistics ------------------------------------------------------- */
 

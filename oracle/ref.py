@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
         L.ref_ik_rmr.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
         L.ref_ik_rmr_left.restype = cd
         L.ref_ik_rmr_left.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
+        L.ref_ik_constraint_rmr.restype = cd
+        L.ref_ik_constraint_rmr.argtypes = [vp, cl, vp, vp, cd, cd, ci, vp, vp, vp]
         L.ref_ik_rmr_ex.restype = cd
         L.ref_ik_rmr_ex.argtypes = [vp, cl, vp, vp, vp, ci, vp, ci, cd, cd, ci, ci, ci, vp, vp, vp, vp]
         L.ref_ik_prio_rmr.restype = cd
@@ -327,9 +329,10 @@ class RefIk:
                                                   float(alpha), int(iters), _p(d1), _p(d2), _p(dn), _p(ok))
         return dict(q=q, dq1=d1, dq2=d2, dq_ns=dn, ok=ok)
 
-    def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False):
+    def rmr(self, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, left=False, constraint=False):
         """Returns (q_after, dx_last, dq_last, det_last); loop of examples/ExampleIK.cpp with
-        solveRightInverse, or solveLeftInverse (IkSolverRMR.cpp:205) if `left`."""
+        solveRightInverse, or solveLeftInverse (IkSolverRMR.cpp:205) if `left`, or
+        IkSolverConstraintRMR::solveRightInverse (IkSolverConstraintRMR.cpp:156) if `constraint`."""
         q = _c(q).copy()
         x_des = _c(x_des)
         N = q.shape[0]
@@ -337,6 +340,8 @@ class RefIk:
         dq = np.empty((N, self.graph.dof))
         det = np.empty((N,))
         fn = lib().ref_ik_rmr_left if left else lib().ref_ik_rmr
+        if constraint:
+            fn = lib().ref_ik_constraint_rmr
         self.last_seconds = fn(
             self._h, N, _p(q), _p(x_des), float(lam), float(alpha), int(iters), _p(dx), _p(dq),
             _p(det))

@@ -34,6 +34,7 @@
 #include <ControllerBase.h>
 #include <IkSolverRMR.h>
 #include <IkSolverPrioRMR.h>
+#include <IkSolverConstraintRMR.h>
 
 #include <unistd.h>
 #include <chrono>
@@ -754,7 +755,18 @@ void* ref_ik_create(const char* graphFile, const char* taskSpec)
     }
     if (f.size() >= 2)
     {
+      /* POLARX / POLARY / POLARZ: TaskPolar2D with that axisDirection */
+      std::string polarAxis;
+      if (f[0].size() == 6 && f[0].compare(0, 5, "POLAR") == 0)
+      {
+        polarAxis = f[0].substr(5);
+        f[0] = "POLAR";
+      }
       x << "<Task name=\"t" << k++ << "\" controlVariable=\"" << f[0] << "\"";
+      if (!polarAxis.empty())
+      {
+        x << " axisDirection=\"" << polarAxis << "\"";
+      }
       if (f[0] == "Joint")
       {
         x << " jnt=\"" << f[1] << "\"";       /* TaskJoint: the second field is the joint's name */
@@ -893,6 +905,66 @@ double ref_ik_rmr(void* ik, long N, double* q, const double* xDes, double lambda
                   int iters, double* dxOut, double* dqOut, double* det)
 {
   return ikRmrImpl(ik, N, q, xDes, lambda, alpha, iters, dxOut, dqOut, det, false);
+}
+
+/*
+ * The same loop with IkSolverConstraintRMR::solveRightInverse (IkSolverConstraintRMR.cpp:156): the step
+ * of the user's tasks, then, if it leaves a joint closer than 2 degrees to a limit, once more with a
+ * joint constraint per such joint. No collision model, all user tasks active.
+ */
+double ref_ik_constraint_rmr(void* ik, long N, double* q, const double* xDes, double lambda, double alpha,
+                             int iters, double* dxOut, double* dqOut, double* det)
+{
+  IkHandle* h = (IkHandle*) ik;
+  return parallelSlices(N, [=](int, long lo, long hi)
+  {
+    Rcs::ControllerBase c(*h->controller);
+    Rcs::IkSolverConstraintRMR solver(&c);
+    RcsGraph* graph = c.getGraph();
+    const unsigned int dof = graph->dof, nJ = graph->nJ, nx = c.getTaskDim();
+    MatNd* qv = MatNd_create(dof, 1);
+    MatNd* dq = MatNd_create(dof, 1);
+    MatNd* a = MatNd_create(c.getNumberOfTasks(), 1);
+    MatNd* xd = MatNd_create(nx, 1);
+    MatNd* dx = MatNd_create(nx, 1);
+    MatNd* dH = MatNd_create(1, nJ);
+    MatNd_setElementsTo(a, 1.0);
+    sliceReady();
+    for (long i = lo; i < hi; ++i)
+    {
+      setQ(graph, qv, NULL, dof, q + i * dof, NULL);
+      memcpy(xd->ele, xDes + (size_t) i * nx, sizeof(double) * nx);
+      for (int it = 0; it < iters; ++it)
+      {
+        c.computeDX(dx, xd);
+        c.computeJointlimitGradient(dH);
+        MatNd_constMulSelf(dH, alpha);
+        solver.solveRightInverse(dq, dx, dH, a, lambda);
+        MatNd_addSelf(graph->q, dq);
+        RcsGraph_setState(graph, NULL, NULL);
+      }
+      memcpy(q + i * dof, graph->q->ele, sizeof(double) * dof);
+      if (dxOut)
+      {
+        memcpy(dxOut + (size_t) i * nx, dx->ele, sizeof(double) * nx);
+      }
+      if (dqOut)
+      {
+        memcpy(dqOut + (size_t) i * dof, dq->ele, sizeof(double) * dof);
+      }
+      if (det)
+      {
+        det[i] = solver.getDeterminant();
+      }
+    }
+    sliceDone();
+    MatNd_destroy(qv);
+    MatNd_destroy(dq);
+    MatNd_destroy(a);
+    MatNd_destroy(xd);
+    MatNd_destroy(dx);
+    MatNd_destroy(dH);
+  });
 }
 
 /* the same loop with IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205) */

@@ -18,6 +18,9 @@ from .api import (  # noqa: F401
     TASK_COGY,
     TASK_COGZ,
     TASK_JOINT,
+    TASK_POLARX,
+    TASK_POLARY,
+    TASK_POLARZ,
     TASK_XYZ,
     TASK_XYZABC,
     bind_host_to_device,
@@ -42,6 +45,9 @@ __all__ = [
     "TASK_COGY",
     "TASK_COGZ",
     "TASK_JOINT",
+    "TASK_POLARX",
+    "TASK_POLARY",
+    "TASK_POLARZ",
     "TASK_XYZ",
     "TASK_XYZABC",
     "bind_host_to_device",

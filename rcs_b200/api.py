@@ -70,6 +70,7 @@ class _RcsbIkOptions(ctypes.Structure):
 
 BLEND_BINARY, BLEND_LINEAR, BLEND_APPROXIMATE = 0, 1, 2
 TASK_COGX, TASK_COGY, TASK_COGZ, TASK_JOINT = 4, 5, 6, 7
+TASK_POLARX, TASK_POLARY, TASK_POLARZ = 8, 9, 10
 
 
 class _RcsbTaskSpec(ctypes.Structure):
@@ -143,6 +144,8 @@ def lib() -> ctypes.CDLL:
         ctypes.c_double, ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_ik_tasks_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
         ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
+    sig("rcsb_ik_constraint_rmr", c_int, c_void, c_int, c_void, c_long, c_dbl_p, c_dbl_p, ctypes.c_double,
+        ctypes.c_double, c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, ctypes.c_uint, c_void)
     sig("rcsb_summary_stats", c_int, c_dbl_p, c_long, c_long, c_dbl_p, c_void)
     sig("rcsb_group_create", c_int, c_void, c_int, c_void, ctypes.POINTER(c_void))
     sig("rcsb_group_destroy", None, c_void)
@@ -593,29 +596,40 @@ class Model:
         _err(rc, "rcsb_ik_rmr_ex")
         return out
 
-    def ik_tasks_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, want=("det",), out=None):
+    def ik_tasks_rmr(self, tasks: Sequence, q, x_des, lam=1.0e-8, alpha=0.05, iters=1, want=("det",), out=None,
+                     constraint=False):
         """rcsb_ik_tasks_rmr: RMR steps over any stack of task kinds with reference bodies / frames.
-        tasks: sequence of (kind, effector[, refBdy[, refFrame]]), -1 = none."""
+        tasks: sequence of (kind, effector[, refBdy[, refFrame]]), -1 = none. constraint=True:
+        rcsb_ik_constraint_rmr (IkSolverConstraintRMR's joint-limit active set); "n_violations" may then
+        be asked for."""
         N, qdim = self._batch(q)
+        who = "ik_constraint_rmr" if constraint else "ik_tasks_rmr"
         if qdim != self.dof:
-            raise RcsbError("ik_tasks_rmr: q must be N x dof")
+            raise RcsbError(f"{who}: q must be N x dof")
         spec = [tuple(t) + (-1,) * (4 - len(t)) for t in tasks]
-        dims = {TASK_XYZ: 3, TASK_ABC: 3, TASK_XYZABC: 6, TASK_COGX: 1, TASK_COGY: 1, TASK_COGZ: 1, TASK_JOINT: 1}
+        dims = {TASK_XYZ: 3, TASK_ABC: 3, TASK_XYZABC: 6, TASK_COGX: 1, TASK_COGY: 1, TASK_COGZ: 1, TASK_JOINT: 1,
+                TASK_POLARX: 2, TASK_POLARY: 2, TASK_POLARZ: 2}
         nx = sum(dims.get(int(t[0]), 0) for t in spec)
         if tuple(x_des.shape) != (N, nx):
-            raise RcsbError(f"ik_tasks_rmr: x_des must be {N} x {nx}")
-        shapes = {"dx": (N, nx), "dq": (N, self.dof), "det": (N,)}
+            raise RcsbError(f"{who}: x_des must be {N} x {nx}")
+        shapes = {"dx": (N, nx), "dq": (N, self.dof), "det": (N,), "n_violations": (N,)}
         out = dict(out or {})
         for k in want:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
+        self._check(who, out, shapes)
         tarr = (_RcsbTaskSpec * max(len(spec), 1))(*[_RcsbTaskSpec(*[int(v) for v in t]) for t in spec])
         a = _Args(self)
-        rc = lib().rcsb_ik_tasks_rmr(
-            self._h, len(spec), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam), float(alpha),
-            int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"), a.ptr(out.get("det"), "det"),
-            a.flags(), a.stream())
-        _err(rc, "rcsb_ik_tasks_rmr")
+        common = (self._h, len(spec), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam), float(alpha),
+                  int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"), a.ptr(out.get("det"), "det"))
+        if constraint:
+            rc = lib().rcsb_ik_constraint_rmr(*common, a.ptr(out.get("n_violations"), "n_violations"), a.flags(),
+                                              a.stream())
+        else:
+            if "n_violations" in out:
+                raise RcsbError("ik_tasks_rmr: n_violations needs constraint=True")
+            rc = lib().rcsb_ik_tasks_rmr(*common, a.flags(), a.stream())
+        _err(rc, "rcsb_" + who)
         return out
 
     def ik_prio_rmr(self, tasks: Sequence, priority: Sequence[int], q, x_des, activation=None, lam=1.0e-8,

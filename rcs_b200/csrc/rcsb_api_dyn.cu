@@ -1572,7 +1572,8 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
       row += 1;
       continue;
     }
-    if (ts.kind != RCSB_TASK_XYZ && ts.kind != RCSB_TASK_ABC && ts.kind != RCSB_TASK_XYZABC)
+    const bool polar = ts.kind >= RCSB_TASK_POLARX && ts.kind <= RCSB_TASK_POLARZ;
+    if (ts.kind != RCSB_TASK_XYZ && ts.kind != RCSB_TASK_ABC && ts.kind != RCSB_TASK_XYZABC && !polar)
     {
       rcsb_set_error("task %d: unknown kind %d", t, ts.kind);
       return RCSB_EINVAL;
@@ -1581,6 +1582,21 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
     {
       rcsb_set_error("task %d: body index out of range", t);
       return RCSB_EINVAL;
+    }
+    if (polar)
+    {
+      /* TaskPolar2D: the Jacobian is expressed in the effector's own frame (TaskPolar2D.cpp:213), a
+       * refFrame attribute plays no role */
+      if (ts.effector < 0)
+      {
+        rcsb_set_error("task %d: a POLAR task needs an effector", t);
+        return RCSB_EINVAL;
+      }
+      const int sE = slot(ts.effector), sR = slot(ts.refBdy);
+      const int rec[8] = {ts.kind, row, 2, sE, sR, sE, ts.kind - RCSB_TASK_POLARX, 0};
+      task.insert(task.end(), rec, rec + 8);
+      row += 2;
+      continue;
     }
     const int frameBody = (ts.refFrame < 0 && ts.refBdy >= 0) ? ts.refBdy : ts.refFrame;   /* Task.cpp:160 */
     const int sE = slot(ts.effector), sR = slot(ts.refBdy), sF = slot(frameBody);
@@ -1709,14 +1725,14 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
   return RCSB_OK;
 }
 
-extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
-                                 const double* xDes, double lambda, double alpha, int iters, double* dx,
-                                 double* dq, double* det, unsigned flags, void* stream)
+static int ikTasksImpl(const char* who, const RcsbModel* cm, int nTasks, const RcsbTaskSpec* tasks, long N,
+                       double* q, const double* xDes, double lambda, double alpha, int iters, double* dx,
+                       double* dq, double* det, bool constraint, double* nViol, unsigned flags, void* stream)
 {
   RcsbModel* m = const_cast<RcsbModel*>(cm);
   if (!m || N < 0 || (N > 0 && (!q || !xDes)) || iters < 0 || nTasks <= 0 || !tasks)
   {
-    rcsb_set_error("rcsb_ik_tasks_rmr: invalid arguments");
+    rcsb_set_error("%s: invalid arguments", who);
     return RCSB_EINVAL;
   }
   const DevicePlan* plan = nullptr;
@@ -1725,7 +1741,22 @@ extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTask
   {
     return rc;
   }
-  auto launch = [&](long n, double* q_, const double* x_, double* dx_, double* dq_, double* det_,
+  /* rows the constraint solver may add: one per unconstrained joint that is not a Joint task */
+  int nxCap = plan->aux0;
+  if (constraint)
+  {
+    const int* jntJacobi = m->iarr(RCSB_A_JNT_JACOBI);
+    for (int j = 0; j < m->hdr.dof; ++j)
+    {
+      bool own = false;
+      for (int t = 0; t < nTasks; ++t)
+      {
+        own = own || (tasks[t].kind == RCSB_TASK_JOINT && tasks[t].effector == j);
+      }
+      nxCap += (jntJacobi[j] >= 0 && !own) ? 1 : 0;
+    }
+  }
+  auto launch = [&](long n, double* q_, const double* x_, double* dx_, double* dq_, double* det_, double* nv_,
                     cudaStream_t st) -> int {
     rcsb::IkArgs a;
     memset(&a, 0, sizeof(a));
@@ -1742,13 +1773,16 @@ extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTask
     a.dx = dx_;
     a.dq = dq_;
     a.det = det_;
+    a.constraint = constraint ? 1 : 0;
+    a.nViol = nv_;
     RCSB_CUDA(cudaSetDevice(m->device));
-    cudaError_t e = rcsb_launch_ik_tasks(&a, m->hdr.nSlots, plan->aux0, m->hdr.nJ, m->hdr.dof, plan->aux1, st);
+    cudaError_t e = rcsb_launch_ik_tasks(&a, m->hdr.nSlots, plan->aux0, nxCap, m->hdr.nJ, m->hdr.dof, plan->aux1,
+                                         st);
     if (e == cudaErrorInvalidValue)
     {
       cudaGetLastError();
-      rcsb_set_error("rcsb_ik_tasks_rmr: problem too large (nx %d, nJ %d, dof %d; limits 24 / 40 / 72)",
-                     plan->aux0, m->hdr.nJ, m->hdr.dof);
+      rcsb_set_error("%s: problem too large (nx %d, nJ %d, dof %d; limits 24 / 40 / 72)", who, plan->aux0,
+                     m->hdr.nJ, m->hdr.dof);
       return RCSB_EUNSUPPORTED;
     }
     RCSB_CUDA(e);
@@ -1757,21 +1791,39 @@ extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTask
   };
   if (!(flags & RCSB_HOST_PTRS))
   {
-    return launch(N, q, xDes, dx, dq, det, static_cast<cudaStream_t>(stream));
+    return launch(N, q, xDes, dx, dq, det, nViol, static_cast<cudaStream_t>(stream));
   }
   const size_t dof = (size_t) m->hdr.dof, nx = (size_t) plan->aux0;
   std::vector<StagedArray> arr;
-  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET };
+  enum { I_QIN, I_X, I_QOUT, I_DX, I_DQ, I_DET, I_NV };
   arr.push_back({q, nullptr, dof, nullptr});
   arr.push_back({xDes, nullptr, nx, nullptr});
   arr.push_back({nullptr, q, dof, nullptr});
   arr.push_back({nullptr, dx, dx ? nx : 0, nullptr});
   arr.push_back({nullptr, dq, dq ? dof : 0, nullptr});
   arr.push_back({nullptr, det, (size_t) (det ? 1 : 0), nullptr});
-  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
+  arr.push_back({nullptr, nViol, (size_t) (nViol ? 1 : 0), nullptr});
+  return runStaged(m, N, arr, {-1, -1, I_QIN, -1, -1, -1, -1}, [&](long n, cudaStream_t st, int) {
     auto dv = [&](int i, const void* host) { return host ? arr[(size_t) i].dev : nullptr; };
-    return launch(n, arr[I_QIN].dev, arr[I_X].dev, dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), st);
+    return launch(n, arr[I_QIN].dev, arr[I_X].dev, dv(I_DX, dx), dv(I_DQ, dq), dv(I_DET, det), dv(I_NV, nViol), st);
   });
+}
+
+extern "C" int rcsb_ik_tasks_rmr(const RcsbModel* cm, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
+                                 const double* xDes, double lambda, double alpha, int iters, double* dx,
+                                 double* dq, double* det, unsigned flags, void* stream)
+{
+  return ikTasksImpl("rcsb_ik_tasks_rmr", cm, nTasks, tasks, N, q, xDes, lambda, alpha, iters, dx, dq, det, false,
+                     nullptr, flags, stream);
+}
+
+extern "C" int rcsb_ik_constraint_rmr(const RcsbModel* cm, int nTasks, const RcsbTaskSpec* tasks, long N,
+                                      double* q, const double* xDes, double lambda, double alpha, int iters,
+                                      double* dx, double* dq, double* det, double* nViolations, unsigned flags,
+                                      void* stream)
+{
+  return ikTasksImpl("rcsb_ik_constraint_rmr", cm, nTasks, tasks, N, q, xDes, lambda, alpha, iters, dx, dq, det,
+                     true, nViolations, flags, stream);
 }
 
 extern "C" int rcsb_ik_prio_rmr(const RcsbModel* cm, int nTasks, const RcsbTask* tasks, const int* priority,

@@ -284,6 +284,54 @@ __device__ __forceinline__ void eulerTaskError(double dx[3], const double xDes[3
   rotationTaskError(dx, Ad, Ac);
 }
 
+/* TaskPolar2D::computeDX (TaskPolar2D.cpp:286): Vec3d_getPolarErrorFromDirection (Rcs_Vec3d.c:233-340)
+ * of the desired polar angles (phi, theta) and row `direction` of A = A_ER. The current axis is turned
+ * onto the desired one about their common normal by phi = acos(a_curr . a_des); the result is that
+ * rotation vector in the effector frame without its component along the free axis. */
+__device__ __noinline__ void polarTaskError(double om[2], const double polarDes[2], const double A[9],
+                                            int direction)
+{
+  const double* ac = A + 3 * direction;
+  double sp, cp, st, ct;
+  sincos(polarDes[0], &sp, &cp);
+  sincos(polarDes[1], &st, &ct);
+  const double ad[3] = {ct * sp, st * sp, cp};
+  const double cosPhi = ac[0] * ad[0] + ac[1] * ad[1] + ac[2] * ad[2];
+  double n[3] = {ac[1] * ad[2] - ac[2] * ad[1], ac[2] * ad[0] - ac[0] * ad[2], ac[0] * ad[1] - ac[1] * ad[0]};
+  const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  if (len == 0.0)
+  {
+    if (cosPhi > 0.0)
+    {
+      om[0] = 0.0;
+      om[1] = 0.0;
+      return;
+    }
+    /* opposite axes: any normal will do, the reference takes a_curr x (next row of A) */
+    const double* o = A + 3 * ((direction + 1) % 3);
+    n[0] = ac[1] * o[2] - ac[2] * o[1];
+    n[1] = ac[2] * o[0] - ac[0] * o[2];
+    n[2] = ac[0] * o[1] - ac[1] * o[0];
+  }
+  else
+  {
+    const double inv = 1.0 / len;
+    n[0] *= inv;
+    n[1] *= inv;
+    n[2] *= inv;
+  }
+  const double phi = acos(fmin(1.0, fmax(-1.0, cosPhi)));   /* Math_acos */
+  /* e_omega = A_ES (0, phi, 0), A_ES = A A_SR^T: column 1 of A_ES is A n. The products with the zero
+   * entries of s_omega are kept out: they add exact zeros in the reference. */
+  double e[3];
+  for (int i = 0; i < 3; ++i)
+  {
+    e[i] = (A[3 * i] * n[0] + A[3 * i + 1] * n[1] + A[3 * i + 2] * n[2]) * phi;
+  }
+  om[0] = direction == 0 ? e[1] : e[0];
+  om[1] = direction == 2 ? e[1] : e[2];
+}
+
 /* One state of the general kernels, everything the solvers need from the graph: forward
  * kinematics (RcsGraph_setState), the task errors dx (ControllerBase::computeDX), the stacked task
  * Jacobian J [nx x nJ] (ControllerBase::computeJ) and the joint-limit gradient term g = -alpha dH
@@ -1299,7 +1347,7 @@ struct IkTasksPlanView
  * every task in the reference's formulations (see rcsb.h), then dq = J# dx + (1 - J# J) invWq
  * (-alpha dH) with J# from MatNd_rwPinv (IkSolverRMR.cpp:415-596), q += dq.
  */
-template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT, int NSLOTS>
+template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT, int NSLOTS, bool CONSTRAINT>
 __global__ void __launch_bounds__(RCSB_IK_THREADS)
 ikTasksKernel(const IkArgs a)
 {
@@ -1333,6 +1381,7 @@ ikTasksKernel(const IkArgs a)
   double dx[MAXNX], g[MAXNJ], Jg[MAXNX], dq[MAXNJ];
   double stk[(NSLOTS > 0 ? NSLOTS : 1) * 12];
   double det = 0.0;
+  int nViol = 0;
 
   for (int j = 0; j < dof; ++j)
   {
@@ -1346,6 +1395,38 @@ ikTasksKernel(const IkArgs a)
   {
     dx[i] = 0.0;
   }
+  /* dq = P dx + (g - P (J g)) for the first `rows` rows of J and dx */
+  auto solveStep = [&](int rows) -> double {
+    const double d = rwPinvSmall(J, rows, nJ, p.invWq, a.lambda, P, A, Ai);
+    if (d == 0.0)
+    {
+      for (int i = 0; i < nJ; ++i)
+      {
+        dq[i] = 0.0;
+      }
+      return d;
+    }
+    for (int r = 0; r < rows; ++r)
+    {
+      double sum = 0.0;
+      for (int i = 0; i < nJ; ++i)
+      {
+        sum += J[r * nJ + i] * g[i];
+      }
+      Jg[r] = sum;
+    }
+    for (int i = 0; i < nJ; ++i)
+    {
+      double ts = 0.0, ns = 0.0;
+      for (int c = 0; c < rows; ++c)
+      {
+        ts += P[i * rows + c] * dx[c];
+        ns += P[i * rows + c] * Jg[c];
+      }
+      dq[i] = ts + (g[i] - ns);
+    }
+    return d;
+  };
   {
     Frame id;
     setIdentity(id);
@@ -1629,8 +1710,8 @@ ikTasksKernel(const IkArgs a)
         }
         continue;
       }
-      /* RCSB_TASK_ABC: Euler angles of A_ER = A_E A_R^T (Task::computeRelativeRotationMatrix,
-       * Task.cpp:1204), error as TaskEuler3D::computeDX */
+      /* RCSB_TASK_ABC / POLAR*: A_ER = A_E A_R^T (Task::computeRelativeRotationMatrix, Task.cpp:1204);
+       * ABC: its Euler angles, error as TaskEuler3D::computeDX */
       {
         double Aer[9];
         const double* AE = fE + 3;
@@ -1642,10 +1723,21 @@ ikTasksKernel(const IkArgs a)
             Aer[3 * i + j] = AE[3 * i] * AR[3 * j] + AE[3 * i + 1] * AR[3 * j + 1] + AE[3 * i + 2] * AR[3 * j + 2];
           }
         }
-        double xc[3];
-        const double xdl[3] = {xd[0], xd[1], xd[2]};
-        toEuler(xc, Aer);
-        eulerTaskError(dx + row, xdl, xc);
+        const bool polar = kind >= RCSB_TASK_POLARX && kind <= RCSB_TASK_POLARZ;
+        if (polar)
+        {
+          /* TaskPolar2D: x = polar angles of row `aux` of A_ER, J = two rows of
+           * RcsGraph_3dOmegaJacobian(ef, refBdy, ef) (TaskPolar2D.cpp:207-243); sF is the effector */
+          const double xdl[2] = {xd[0], xd[1]};
+          polarTaskError(dx + row, xdl, Aer, aux);
+        }
+        else
+        {
+          double xc[3];
+          const double xdl[3] = {xd[0], xd[1], xd[2]};
+          toEuler(xc, Aer);
+          eulerTaskError(dx + row, xdl, xc);
+        }
         /* RcsGraph_3dOmegaJacobian: JR_2, A_1 JR_2 (fixed reference), or A_3 (JR_2 - JR_1) */
         const bool fixedRef = sR > 0 && sF == sR && mR == 0ull;
         const bool relative = !(sR == 0 && sF == 0) && !fixedRef;
@@ -1667,9 +1759,17 @@ ikTasksKernel(const IkArgs a)
             v[1] = Arot[3] * x0 + Arot[4] * y0 + Arot[5] * z0;
             v[2] = Arot[6] * x0 + Arot[7] * y0 + Arot[8] * z0;
           }
-          Jr[k] = v[0];
-          Jr[nJ + k] = v[1];
-          Jr[2 * nJ + k] = v[2];
+          if (polar)
+          {
+            Jr[k] = aux == 0 ? v[1] : v[0];
+            Jr[nJ + k] = aux == 2 ? v[1] : v[2];
+          }
+          else
+          {
+            Jr[k] = v[0];
+            Jr[nJ + k] = v[1];
+            Jr[2 * nJ + k] = v[2];
+          }
         }
       }
     }
@@ -1680,33 +1780,76 @@ ikTasksKernel(const IkArgs a)
       const double delta = qv[p.colJoint[i]] - p.q0[i];
       g[i] = p.invWq[i] * (-(a.alpha * (p.jlGain[i] * delta)));
     }
-    det = rwPinvSmall(J, nx, nJ, p.invWq, a.lambda, P, A, Ai);
+    det = solveStep(nx);
+    nViol = 0;
     if (det == 0.0)
     {
-      for (int i = 0; i < nJ; ++i)
-      {
-        dq[i] = 0.0;
-      }
       continue;
     }
-    for (int r = 0; r < nx; ++r)
+    if (CONSTRAINT)
     {
-      double sum = 0.0;
-      for (int i = 0; i < nJ; ++i)
+      /* IkSolverConstraintRMR::solveRightInverse (IkSolverConstraintRMR.cpp:156-262): every free joint
+       * that the step would leave closer than 2 degrees to a limit (and that is not a task of its
+       * own) becomes a joint constraint: a unit row with a target velocity of zero, or of a tenth of
+       * 0.1 degrees back towards the limit margin if it is deeper than that; then ONE more solve with
+       * these rows appended in joint order. */
+      const double margin = (3.14159265358979323846 / 180.0) * 2.0;
+      const double baumgarte = (3.14159265358979323846 / 180.0) * 0.1;
+      int rows = nx;
+      for (int j = 0; j < dof; ++j)
       {
-        sum += J[r * nJ + i] * g[i];
+        const int col = m.jntJacobi[j];
+        if (col < 0)
+        {
+          continue;
+        }
+        bool ownTask = false;
+        for (int t = 0; t < nTasks; ++t)
+        {
+          ownTask = ownTask || (p.task[8 * t] == RCSB_TASK_JOINT && p.task[8 * t + 7] == j);
+        }
+        if (ownTask)
+        {
+          continue;
+        }
+        const double x = qv[j] + dq[col];
+        const double lo = m.jntQMin[j] + margin, hi = m.jntQMax[j] - margin;
+        double target;
+        if (x < lo)
+        {
+          target = (lo - x > baumgarte) ? 0.1 * baumgarte : 0.0;
+        }
+        else if (x > hi)
+        {
+          target = (x - hi > baumgarte) ? -0.1 * baumgarte : 0.0;
+        }
+        else
+        {
+          continue;
+        }
+        ++nViol;
+        if (rows < MAXNX)
+        {
+          for (int k = 0; k < nJ; ++k)
+          {
+            J[rows * nJ + k] = 0.0;
+          }
+          J[rows * nJ + col] = 1.0;
+          dx[rows] = target;
+          ++rows;
+        }
       }
-      Jg[r] = sum;
-    }
-    for (int i = 0; i < nJ; ++i)
-    {
-      double ts = 0.0, ns = 0.0;
-      for (int c = 0; c < nx; ++c)
+      if (nViol > 0)
       {
-        ts += P[i * nx + c] * dx[c];
-        ns += P[i * nx + c] * Jg[c];
+        if (nx + nViol > MAXNX)
+        {
+          nViol = -1;      /* does not fit: the state keeps the unconstrained step and says so */
+        }
+        else
+        {
+          det = solveStep(rows);
+        }
       }
-      dq[i] = ts + (g[i] - ns);
     }
     for (int i = 0; i < nJ; ++i)
     {
@@ -1734,6 +1877,10 @@ ikTasksKernel(const IkArgs a)
   if (a.det)
   {
     a.det[s] = det;
+  }
+  if (CONSTRAINT && a.nViol)
+  {
+    a.nViol[s] = (double) nViol;
   }
 }
 
@@ -3197,14 +3344,14 @@ static cudaError_t launchIkPrio(const IkArgs& a, int nSlots, cudaStream_t stream
 
 }   // namespace rcsb
 
-template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT>
+template <int MAXNX, int MAXNJ, int MAXDOF, int MAXSLOT, bool CONSTRAINT>
 static cudaError_t launchIkTasks(const rcsb::IkArgs& a, int nSlots, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes;
   const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
   if (nSlots <= 0)
   {
-    auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, 0>;
+    auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, 0, CONSTRAINT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes);
     if (e != cudaSuccess)
     {
@@ -3213,7 +3360,7 @@ static cudaError_t launchIkTasks(const rcsb::IkArgs& a, int nSlots, cudaStream_t
     k<<<grid, RCSB_IK_THREADS, smemBytes, stream>>>(a);
     return cudaGetLastError();
   }
-  auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, RCSB_MAX_FRAME_SLOTS>;
+  auto k = rcsb::ikTasksKernel<MAXNX, MAXNJ, MAXDOF, MAXSLOT, RCSB_MAX_FRAME_SLOTS, CONSTRAINT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes);
   if (e != cudaSuccess)
   {
@@ -3223,21 +3370,39 @@ static cudaError_t launchIkTasks(const rcsb::IkArgs& a, int nSlots, cudaStream_t
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
-                                            int nFrameSlots, cudaStream_t stream)
+extern "C" cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nxCap, int nJ,
+                                            int dof, int nFrameSlots, cudaStream_t stream)
 {
   using namespace rcsb;
   if (a->N <= 0)
   {
     return cudaSuccess;
   }
+  if (a->constraint)
+  {
+    /* rows: the tasks' plus one per joint that can hit a limit; the large instantiation stops at 32
+     * rows and reports states that would need more */
+    if (nx > 24 || nFrameSlots > 24)
+    {
+      return cudaErrorInvalidValue;
+    }
+    if (nxCap <= 16 && nJ <= 8 && dof <= 12 && nFrameSlots <= 12)
+    {
+      return launchIkTasks<16, 8, 12, 12, true>(*a, nSlots, stream);
+    }
+    if (nJ <= 40 && dof <= 72)
+    {
+      return launchIkTasks<32, 40, 72, 24, true>(*a, nSlots, stream);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (nx <= 12 && nJ <= 8 && dof <= 12 && nFrameSlots <= 12)
   {
-    return launchIkTasks<12, 8, 12, 12>(*a, nSlots, stream);
+    return launchIkTasks<12, 8, 12, 12, false>(*a, nSlots, stream);
   }
   if (nx <= 24 && nJ <= 40 && dof <= 72 && nFrameSlots <= 24)
   {
-    return launchIkTasks<24, 40, 72, 24>(*a, nSlots, stream);
+    return launchIkTasks<24, 40, 72, 24, false>(*a, nSlots, stream);
   }
   return cudaErrorInvalidValue;
 }

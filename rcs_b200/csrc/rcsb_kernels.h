@@ -102,13 +102,14 @@ struct IkArgs
   int extended;        /* 1: any of the fields below is in use */
   int lambdaPerRow;    /* 1: lambdaRow[r] regularises row r of J W J^T (MatNd_addDiag, Rcs_MatNd.c:1872) */
   int blending;        /* left inverse: RCSB_BLEND_* task-space weights Wx (TaskSpaceBlender.cpp) */
-  int pad;
+  int constraint;      /* ikTasksKernel: 1 = IkSolverConstraintRMR's joint-limit active set */
   double lambdaRow[12];
   double taskScale[4]; /* dx rows of task t are multiplied by it (ControllerBase::computeDX with a_des) */
   double taskAct[4];   /* activation of task t (blending weights) */
   int taskLevel[4];    /* prioritised solver: priority level of plan task t (0, 1; else ignored) */
   double* dqTs;        /* N x dof: task-space part of the last step (prioritised solver: dq2) */
   double* dqNs;        /* N x dof: null-space part of the last step */
+  double* nViol;       /* N: joint-limit constraints added in the last step (constraint solver), -1 = too many */
 };
 
 }   // namespace rcsb
@@ -121,8 +122,9 @@ cudaError_t rcsb_launch_kt(const rcsb::KtArgs* a, int nSlots, int nJ, int nJ2, i
 /* maximum dynamic shared memory of the assembly kernel for a record of recDoubles (plan checks) */
 cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int chainNc,
                            int multiNu, int nEffs, int nTasks, cudaStream_t stream);
-cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof, int nFrameSlots,
-                                 cudaStream_t stream);
+/* nxCap: rows the solve may reach (nx, or nx + candidate joint constraints for the constraint solver) */
+cudaError_t rcsb_launch_ik_tasks(const rcsb::IkArgs* a, int nSlots, int nx, int nxCap, int nJ, int dof,
+                                 int nFrameSlots, cudaStream_t stream);
 cudaError_t rcsb_launch_ik_prio(const rcsb::IkArgs* a, int nSlots, int nx, int nJ, int dof,
                                 cudaStream_t stream);
 }

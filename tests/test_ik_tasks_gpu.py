@@ -6,13 +6,14 @@ import numpy as np
 import pytest
 
 import rcs_b200
-from rcs_b200 import (TASK_ABC, TASK_COGX, TASK_COGY, TASK_COGZ, TASK_JOINT, TASK_XYZ, TASK_XYZABC, workload)
+from rcs_b200 import (TASK_ABC, TASK_COGX, TASK_COGY, TASK_COGZ, TASK_JOINT, TASK_POLARX, TASK_POLARY, TASK_POLARZ,
+                      TASK_XYZ, TASK_XYZABC, workload)
 from conftest import assert_close, graph_file
 from test_ik_gpu import assert_step_close
 
 pytestmark = pytest.mark.gpu
 CODE = {"XYZ": TASK_XYZ, "ABC": TASK_ABC, "XYZABC": TASK_XYZABC, "COGX": TASK_COGX, "COGY": TASK_COGY,
-        "COGZ": TASK_COGZ, "Joint": TASK_JOINT}
+        "COGZ": TASK_COGZ, "Joint": TASK_JOINT, "POLARX": TASK_POLARX, "POLARY": TASK_POLARY, "POLARZ": TASK_POLARZ}
 
 
 def _spec(g, names):
@@ -82,6 +83,43 @@ def test_reference_bodies_frames_cog_and_joint_tasks(name, names, refmod, cuda_d
     whole graph and of a subtree, joint tasks."""
     r = _run(name, names, refmod, cuda_device, 300)
     _check(r)
+
+
+@pytest.mark.parametrize("name,names", [
+    ("wam_arm", [("POLARZ", "BallTip"), ("XYZ", "BallTip")]),
+    ("wam_arm", [("POLARX", "BallTip", "Link2"), ("Joint", "ArmJoint1")]),
+    ("wam_arm", [("XYZ", "Link4"), ("POLARY", "BallTip", "Base")]),
+    ("gantry", [("POLARZ", "Tool", "Trolley"), ("XYZ", "Camera")]),
+    ("humanoid", [("POLARZ", "RightHandTip", "Heel"), ("POLARX", "LeftHandTip"), ("COGX", "Heel"), ("COGY", "Heel")]),
+], ids=["polar-z-world", "polar-x-relative", "polar-y-fixed-reference", "gantry-polar", "humanoid-polar"])
+def test_polar_tasks(name, names, refmod, cuda_device):
+    """TaskPolar2D for every axisDirection, world / articulated / fixed reference body: polar-angle
+    targets, Vec3d_getPolarErrorFromDirection, rows of the effector-frame angular Jacobian. The start
+    states are 0.08 rad away from the goal states, so the angle between current and desired axis stays
+    away from 0 where its acos() is ill-conditioned in the reference itself."""
+    r = _run(name, names, refmod, cuda_device, 300)
+    _check(r)
+
+
+def test_polar_task_on_target_and_opposite_axis(refmod, cuda_device):
+    """Ends of the range of Vec3d_getPolarErrorFromDirection: on target the error is exactly 0; with the
+    desired axis (numerically almost) opposite to the current one the rotation axis is decided by
+    rounding noise in the reference itself, the angle is pi."""
+    names = [("POLARZ", "BallTip")]
+    g = rcs_b200.Graph(graph_file("wam_arm"))
+    m = rcs_b200.Model(g, cuda_device)
+    rik = refmod.RefIk(graph_file("wam_arm"), names)
+    q0 = np.zeros((2, g.dof))      # BallTip's z axis is the world's at q = 0: polar angles (0, 0)
+    x_cur, _ = rik.task_kinematics(q0)
+    assert np.all(x_cur == 0.0)
+    x_des = np.ascontiguousarray(x_cur)
+    x_des[1] = [np.pi, 0.0]
+    _, dx_ref, dq_ref, _ = rik.rmr(q0, x_des, lam=1e-6, iters=1)
+    q = q0.copy()
+    out = m.ik_tasks_rmr(_spec(g, names), q, x_des, lam=1e-6, iters=1, want=("dx", "dq"))
+    assert np.all(out["dx"][0] == 0.0) and np.all(dx_ref[0] == 0.0)
+    assert_close(out["dq"][0], dq_ref[0], what="dq on target")
+    assert abs(np.linalg.norm(out["dx"][1]) - np.pi) < 1e-12 and abs(np.linalg.norm(dx_ref[1]) - np.pi) < 1e-12
 
 
 def test_ten_iterations_of_a_mixed_stack_device_pointers(refmod, cuda_device):
