@@ -420,8 +420,9 @@ long ktChunk(const RcsbModel* m, int recDoubles)
     (void) m;
     chunk = (2L << 30) / ((long) recDoubles * (long) sizeof(double));
   }
-  chunk = chunk < RCSB_KT_WALK_THREADS ? RCSB_KT_WALK_THREADS : chunk;
-  return (chunk + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS * RCSB_KT_WALK_THREADS;
+  /* a multiple of both block sizes of the walk kernel (128, 192) */
+  chunk = chunk < 384 ? 384 : chunk;
+  return (chunk + 383) / 384 * 384;
 }
 
 }   // namespace
