@@ -10,6 +10,7 @@
 #include "rcsb_priv.h"
 
 #include <cctype>
+#include <cstdlib>
 
 extern "C" int rcsb_flatten(const RcsGraph* graph, void** blobOut, size_t* bytesOut);
 
@@ -68,7 +69,23 @@ static size_t carveBytes(size_t doubles)
   return (doubles * sizeof(double) + 255) & ~(size_t) 255;
 }
 
-static const long kStageChunk = 1L << 16;   /* states per pipeline stage */
+/* States per pipeline stage: at least 65,536 (smaller launches leave SMs idle), more for paths with
+ * little traffic per state so that a stage moves about 48 MiB (the 4M-target IK workload ran 64
+ * stages of 11 MB on two streams: 210 M solves/s end to end, 252 M with 262,144-state stages on
+ * three), at most 1M. A multiple of 384 (block
+ * sizes of the kernels). */
+static const long kStageChunkMin = 1L << 16;
+static long stageChunk(size_t bytesPerState)
+{
+  const char* env = getenv("RCSB_STAGE_CHUNK");   /* states per stage, for tests of the pipeline */
+  if (env && atol(env) > 0)
+  {
+    return atol(env);
+  }
+  long c = (long) ((48u << 20) / (bytesPerState ? bytesPerState : 1));
+  c = c < kStageChunkMin ? kStageChunkMin : (c > (1L << 20) ? (1L << 20) : c);
+  return (c + 383) / 384 * 384;
+}
 
 int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
               const std::vector<int>& aliasOutToIn,
@@ -77,7 +94,13 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
   std::lock_guard<std::recursive_mutex> lock(m->mtx);
   RCSB_CUDA(cudaSetDevice(m->device));
 
-  const long chunk = N < kStageChunk ? N : kStageChunk;
+  size_t bytesPerState = 0;
+  for (size_t i = 0; i < arrays.size(); ++i)
+  {
+    bytesPerState += arrays[i].perState * sizeof(double);
+  }
+  const long want = stageChunk(bytesPerState);
+  const long chunk = N < want ? N : want;
   std::vector<size_t> offs(arrays.size(), 0);
   size_t need = 0;
   for (size_t i = 0; i < arrays.size(); ++i)
@@ -94,8 +117,16 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
     }
   }
 
+  int nSlots = RCSB_PIPE_SLOTS;
+  {
+    const char* env = getenv("RCSB_STAGE_SLOTS");
+    if (env && atoi(env) >= 1 && atoi(env) <= RCSB_PIPE_SLOTS)
+    {
+      nSlots = atoi(env);
+    }
+  }
   int slot = 0;
-  for (long s0 = 0; s0 < N; s0 += chunk, slot ^= 1)
+  for (long s0 = 0; s0 < N; s0 += chunk, slot = (slot + 1) % nSlots)
   {
     const long n = (N - s0 < chunk) ? (N - s0) : chunk;
     int rc = pipeReserve(m, slot, need);
@@ -131,7 +162,7 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
       }
     }
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < RCSB_PIPE_SLOTS; ++i)
   {
     if (m->pipe.stream[i])
     {
@@ -865,11 +896,12 @@ extern "C" void rcsb_model_destroy(RcsbModel* m)
   {
     cudaFree(kv.second.dev);
   }
-  cudaFree(m->ktScratch[0]);
-  cudaFree(m->ktScratch[1]);
-  cudaFree(m->ikScratch[0]);
-  cudaFree(m->ikScratch[1]);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < RCSB_PIPE_SLOTS; ++i)
+  {
+    cudaFree(m->ktScratch[i]);
+    cudaFree(m->ikScratch[i]);
+  }
+  for (int i = 0; i < RCSB_PIPE_SLOTS; ++i)
   {
     if (m->pipe.buf[i])
     {

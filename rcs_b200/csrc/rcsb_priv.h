@@ -38,11 +38,14 @@ struct DevicePlan
 };
 
 /* double-buffered device workspace of the RCSB_HOST_PTRS path */
+/* stages of the host-buffer pipeline (and of every per-stage workspace of a model): three, so that
+ * the copy-in of one chunk, the kernels of the next and the copy-out of a third overlap */
+#define RCSB_PIPE_SLOTS 3
 struct StagePipe
 {
-  cudaStream_t stream[2] = {nullptr, nullptr};
-  char* buf[2] = {nullptr, nullptr};
-  size_t cap[2] = {0, 0};
+  cudaStream_t stream[RCSB_PIPE_SLOTS] = {};
+  char* buf[RCSB_PIPE_SLOTS] = {};
+  size_t cap[RCSB_PIPE_SLOTS] = {};
 };
 
 }   // namespace rcsbhost
@@ -61,10 +64,10 @@ struct RcsbModel
   rcsbhost::DevicePlan ktPlan[2];              /* kinetic-terms plans without / with velocities */
   std::map<std::string, rcsbhost::DevicePlan> wbPlans;   /* whole-body variants of the kinetic-terms plan */
   bool ktPlanBuilt[2] = {false, false};
-  double* ktScratch[2] = {nullptr, nullptr};
-  size_t ktScratchDoubles[2] = {0, 0};
-  char* ikScratch[2] = {nullptr, nullptr};      /* gathered x_des of masked IK calls, per staging slot */
-  size_t ikScratchBytes[2] = {0, 0};
+  double* ktScratch[RCSB_PIPE_SLOTS] = {};
+  size_t ktScratchDoubles[RCSB_PIPE_SLOTS] = {};
+  char* ikScratch[RCSB_PIPE_SLOTS] = {};      /* gathered x_des of masked IK calls, per staging slot */
+  size_t ikScratchBytes[RCSB_PIPE_SLOTS] = {};
   rcsbhost::StagePipe pipe;
 
   const int* iarr(int a) const

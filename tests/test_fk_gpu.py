@@ -263,3 +263,36 @@ def test_polynomial_couplings_inside_and_beyond_the_master_limits(refmod, cuda_d
     jo, jr = m.fk_jacobians(q, eff), r.fk_jacobians(q, eff)
     for k in ("JT", "JR"):
         assert_close(jo[k], jr[k], what=f"{name} {k}")
+
+
+def test_host_pointer_pipeline_many_stages(refmod, cuda_device, monkeypatch):
+    """The host-buffer path cuts a batch into stages that rotate over three streams / staging buffers /
+    workspaces (H2D, kernels, D2H of different stages overlap). With 300-state stages a 5,000-state
+    batch takes 17 of them: results must equal the device-pointer call bit for bit, for a path with
+    per-stage workspaces (kinetic terms), one with an in-out array (IK) and plain FK."""
+    import torch
+
+    monkeypatch.setenv("RCSB_STAGE_CHUNK", "300")
+    g, m, r = _models("wam_arm", refmod, cuda_device)
+    n = 5000
+    q, qd = workload.sample_states(g.layout(), n, first=3, with_velocity=True)
+    tq, tqd = torch.from_numpy(q).cuda(cuda_device), torch.from_numpy(qd).cuda(cuda_device)
+    host = m.fk(q, qd, want=("A_BI", "xdot"))
+    dev = m.fk(tq, tqd, want=("A_BI", "xdot"))
+    hk = m.kinetic_terms(q, qd)
+    dk = m.kinetic_terms(tq, tqd)
+    tip = g.body_index("BallTip")
+    x_des = np.ascontiguousarray(np.concatenate([host["A_BI"][:, tip, :3] + 0.01, np.zeros((n, 3))], axis=1))
+    tasks = [(rcs_b200.TASK_XYZ, tip), (rcs_b200.TASK_ABC, tip)]
+    qh = q.copy()
+    oh = m.ik_rmr(tasks, qh, x_des, lam=1e-6, iters=3, want=("dq", "det"))
+    qdv = tq.clone()
+    od = m.ik_rmr(tasks, qdv, torch.from_numpy(x_des).cuda(cuda_device), lam=1e-6, iters=3, want=("dq", "det"))
+    torch.cuda.synchronize()
+    for k in host:
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+    for k in hk:
+        assert np.array_equal(hk[k], dk[k].cpu().numpy()), k
+    assert np.array_equal(qh, qdv.cpu().numpy())
+    for k in oh:
+        assert np.array_equal(oh[k], od[k].cpu().numpy()), k
