@@ -201,6 +201,11 @@ void MatNd_reshapeAndSetZero(MatNd* self, unsigned int m, unsigned int n);
 /* src/RcsCore/Rcs_graph.c:398 — file name is searched as given, then relative to every
  * path added with Rcs_addResourcePath(). Returns NULL if the file cannot be loaded. */
 RcsGraph* RcsGraph_create(const char* xmlFile);
+/* src/RcsCore/Rcs_URDFParser.c:1152 — a URDF <robot> file (revolute, continuous, prismatic and fixed
+ * joints, any axis, mimic joints, <model_state>; box / cylinder / sphere shapes, mesh names only).
+ * URDF sub-trees inside a <Graph> file are loaded through its <URDF file= prev= suffix= transform=
+ * rigid_body_joints=> nodes (src/RcsCore/Rcs_graphParser.c:1438). */
+RcsGraph* RcsGraph_fromURDFFile(const char* urdfFile);
 /* src/RcsCore/Rcs_graph.c:366 (buffer variant of RcsGraph_create) */
 RcsGraph* RcsGraph_createFromBuffer(const char* buffer, unsigned int size);
 void RcsGraph_destroy(RcsGraph* self);

@@ -129,6 +129,13 @@ class RefGraph:
         L.ref_free(p)
         return json.loads(s)
 
+    def clone(self) -> "RefGraph":
+        """RcsGraph_clone (Rcs_graph.c:2193)"""
+        L = lib()
+        L.ref_graph_clone.restype = ctypes.c_void_p
+        L.ref_graph_clone.argtypes = [ctypes.c_void_p]
+        return RefGraph("", _handle=L.ref_graph_clone(self._h))
+
     def body_index(self, name: str) -> int:
         return lib().ref_body_index(self._h, name.encode())
 

@@ -35,6 +35,8 @@
 #include <IkSolverRMR.h>
 #include <IkSolverPrioRMR.h>
 #include <IkSolverConstraintRMR.h>
+#include <Rcs_URDFParser.h>
+#include <strings.h>
 
 #include <unistd.h>
 #include <chrono>
@@ -237,7 +239,19 @@ void ref_add_resource_path(const char* p)
 
 void* ref_graph_create(const char* xmlFile)
 {
+  /* URDF robots go through the reference's own URDF loader (Rcs_URDFParser.c:1152) */
+  const size_t len = strlen(xmlFile);
+  if (len > 5 && strcasecmp(xmlFile + len - 5, ".urdf") == 0)
+  {
+    return RcsGraph_fromURDFFile(xmlFile);
+  }
   return RcsGraph_create(xmlFile);
+}
+
+/* RcsGraph_clone (Rcs_graph.c:2193): the copy every worker thread of this driver evaluates on */
+void* ref_graph_clone(void* g)
+{
+  return RcsGraph_clone((RcsGraph*) g);
 }
 
 void ref_graph_destroy(void* g)

@@ -98,6 +98,7 @@ def lib() -> ctypes.CDLL:
         fn.argtypes = list(argtypes)
 
     sig("RcsGraph_create", c_void, ctypes.c_char_p)
+    sig("RcsGraph_fromURDFFile", c_void, ctypes.c_char_p)
     sig("RcsGraph_createFromBuffer", c_void, ctypes.c_char_p, ctypes.c_uint)
     sig("RcsGraph_destroy", None, c_void)
     sig("RcsGraph_clone", c_void, c_void)
@@ -217,14 +218,16 @@ def _err(rc: int, what: str) -> None:
 
 
 class Graph:
-    """An RcsGraph loaded by librcsb's own XML loader (host only, no GPU needed)."""
+    """An RcsGraph loaded by librcsb's own loaders (host only, no GPU needed): RcsGraph_create, or
+    RcsGraph_fromURDFFile for a file name ending in .urdf."""
 
     def __init__(self, source: str, _handle: Optional[int] = None):
         L = lib()
         if _handle is not None:
             self._h = _handle
         else:
-            self._h = L.RcsGraph_create(source.encode())
+            urdf = source.lower().endswith(".urdf")
+            self._h = (L.RcsGraph_fromURDFFile if urdf else L.RcsGraph_create)(source.encode())
         if not self._h:
             msg = L.rcsb_last_error()
             raise RcsbError(f"RcsGraph_create({source!r}) failed: {msg.decode() if msg else ''}")

@@ -81,6 +81,8 @@ unsigned int rcsb_xml_string(const RcsbXmlNode* n, const char* tag, char* str, u
 /* ---- graph internals --------------------------------------------------------------- */
 bool Rcs_getAbsoluteFileName(const char* fileName, char* absFileName);   /* 512 bytes */
 RcsGraph* RcsGraph_createFromXmlNode(const RcsbXmlNode* node);
+/* rcsb_urdf.c: RcsGraph_rootBodyFromURDFFile (src/RcsCore/Rcs_URDFParser.c:924) */
+RcsBody* rcsb_urdf_root_body(const char* filename, const char* suffix, const HTr* A_BP, unsigned int* dof);
 void RcsBody_computeInertiaTensor(const RcsBody* self, HTr* I);
 double RcsJoint_computeSlaveJointAngle(const RcsJoint* slave, double q_master);
 double RcsJoint_computeSlaveJointVelocity(const RcsJoint* slave, double q_master,

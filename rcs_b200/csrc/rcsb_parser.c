@@ -13,8 +13,8 @@
  *   model_state                    src/RcsCore/Rcs_graphParser.c:55-140
  * The rules that decide the integer layout are spelled out in SURVEY.md, appendix A.
  *
- * Not supported (not needed for the hot path; logged and skipped): <URDF>, <OpenRave>,
- * .bvh files, generic bodies, sensors, mesh volumes (MESH shapes count as zero volume,
+ * <URDF> nodes: rcsb_urdf.c. Not supported (not needed for the hot path; logged and skipped):
+ * <OpenRave>, .bvh files, generic bodies, sensors, mesh volumes (MESH shapes count as zero volume,
  * which is also what the reference computes when the mesh file is missing).
  */
 #include "rcsb_internal.h"
@@ -872,6 +872,153 @@ static RcsBody* bodyFromXML(RcsGraph* self, const RcsbXmlNode* node, const char*
 /* Siblings are processed by iteration, children of Graph / Group by recursion; the
  * firstInGroup flag is dropped once a body has been created or a nested <Graph> has
  * been left (src/RcsCore/Rcs_graphParser.c:1203-1635). */
+static void rewireJointChains(RcsBody* b)
+{
+  if (b->jnt)
+  {
+    b->jnt->prev = b->parent ? RcsBody_lastJointBeforeBody(b->parent) : NULL;
+  }
+  for (RcsBody* c = b->firstChild; c; c = c->next)
+  {
+    rewireJointChains(c);
+  }
+}
+
+/* <URDF file= prev= suffix= transform= rigid_body_joints=> (src/RcsCore/Rcs_graphParser.c:1438-1600):
+ * the URDF tree becomes the last child of `prev` (or a further root), optionally on six rigid-body
+ * joints */
+static void urdfFromXML(const RcsbXmlNode* node, RcsGraph* self, const char* suffix)
+{
+  char tmp[256] = "", filename[512] = "";
+  RcsBody* pB = NULL;
+  if (rcsb_xml_string(node, "prev", tmp, 256) > 0)
+  {
+    pB = RcsGraph_getBodyByName(self, tmp);
+    if (!pB)
+    {
+      RCSB_FATAL("Body \"%s\" not found, which was specified as prev for an URDF node", tmp);
+      return;
+    }
+  }
+  tmp[0] = '\0';
+  rcsb_xml_string(node, "file", tmp, 256);
+  if (!Rcs_getAbsoluteFileName(tmp, filename))
+  {
+    RCSB_FATAL("Couldn't open urdf file \"%s\"", tmp);
+    return;
+  }
+  char urdfSuffix[132] = "", ndExt[300];
+  rcsb_xml_string(node, "suffix", urdfSuffix, 132);
+  snprintf(ndExt, sizeof(ndExt), "%s%s", suffix, urdfSuffix);
+
+  HTr A_local;
+  HTr_setIdentity(&A_local);
+  rcsb_xml_htr(node, "transform", &A_local);
+  unsigned int dof = 0;
+  RcsBody* urdfRoot = rcsb_urdf_root_body(filename, ndExt, &A_local, &dof);
+  if (!urdfRoot)
+  {
+    RCSB_FATAL("Couldn't get URDF root from file \"%s\"", filename);
+    return;
+  }
+  self->dof += dof;
+  MatNd* q = MatNd_create(self->dof, 1);
+  if (self->q)
+  {
+    memcpy(q->ele, self->q->ele, sizeof(double) * self->q->m);
+    MatNd_destroy(self->q);
+  }
+  self->q = q;
+
+  double q_rbj[12];
+  memset(q_rbj, 0, sizeof(q_rbj));
+  unsigned int nStr = 0;
+  if (rcsb_xml_attr(node, "rigid_body_joints"))
+  {
+    urdfRoot->rigid_body_joints = true;
+    nStr = rcsb_xml_num_strings(node, "rigid_body_joints");
+    if (nStr == 1)
+    {
+      rcsb_xml_bool(node, "rigid_body_joints", &urdfRoot->rigid_body_joints);
+    }
+    else if (nStr == 6 || nStr == 12)
+    {
+      rcsb_xml_vecn(node, "rigid_body_joints", q_rbj, nStr);
+      for (int i = 3; i < 6; ++i)
+      {
+        q_rbj[i] *= M_PI / 180.0;
+      }
+    }
+    else
+    {
+      RCSB_FATAL("rigid_body_joints of body \"%s\" has %u entries", urdfRoot->name, nStr);
+    }
+  }
+  if (urdfRoot->rigid_body_joints)
+  {
+    /* the URDF root has no joints of its own: the six joints are its only ones */
+    RcsJoint* rbj0 = createRigidBodyJoints(self, urdfRoot, q_rbj);
+    if (nStr == 12)
+    {
+      int k = 0;
+      for (RcsJoint* j = rbj0; j; j = j->next)
+      {
+        j->weightMetric = q_rbj[6 + k++];
+      }
+    }
+    if (!HTr_isIdentity(&A_local))
+    {
+      rbj0->A_JP = HTr_clone(&A_local);
+      HTr_setIdentity(urdfRoot->A_BP);
+    }
+  }
+  else if (urdfRoot->physicsSim != RCSBODY_PHYSICS_NONE)
+  {
+    urdfRoot->physicsSim = (pB && (pB->physicsSim == RCSBODY_PHYSICS_DYNAMIC || pB->physicsSim == RCSBODY_PHYSICS_FIXED))
+                             ? RCSBODY_PHYSICS_FIXED : RCSBODY_PHYSICS_KINEMATIC;
+  }
+
+  /* attached last, as in the reference */
+  if (pB)
+  {
+    urdfRoot->parent = pB;
+    if (pB->firstChild)
+    {
+      pB->lastChild->next = urdfRoot;
+      urdfRoot->prev = pB->lastChild;
+      pB->lastChild = urdfRoot;
+    }
+    else
+    {
+      pB->firstChild = urdfRoot;
+      pB->lastChild = urdfRoot;
+    }
+  }
+  else if (!self->root)
+  {
+    self->root = urdfRoot;
+  }
+  else
+  {
+    RcsBody* b = self->root;
+    while (b->next)
+    {
+      b = b->next;
+    }
+    b->next = urdfRoot;
+    urdfRoot->prev = b;
+  }
+
+  /* The reference wires the joints of the URDF tree (and the rigid-body joints) while the tree has
+   * no parent, so in the graph it returns the backward joint chain (jnt->prev) of every URDF body
+   * ends at the URDF root: below an articulated `prev` body Jacobians and mass matrix lack the
+   * columns of the joints above (x_dot != J q_dot) — until the graph is cloned: RcsGraph_clone
+   * re-inserts every joint and wires the complete chains (the reference's controllers and solvers
+   * work on clones). Here the chains are complete from the start: the first joint of every body of
+   * the tree is re-wired now that the parent is known (tests/test_urdf_cpu.py, test_urdf_gpu.py). */
+  rewireJointChains(urdfRoot);
+}
+
 static void parseBodies(const RcsbXmlNode* node, RcsGraph* self, const char* suffix, HTr* A,
                         bool firstInGroup, int level, RcsBody* root[RCSGRAPH_MAX_GROUPDEPTH])
 {
@@ -922,7 +1069,11 @@ static void parseBodies(const RcsbXmlNode* node, RcsGraph* self, const char* suf
       }
       parseBodies(node->children, self, ndExt, &A_group, true, level + 1, root);
     }
-    else if (isTag(node, "URDF") || isTag(node, "OpenRave"))
+    else if (isTag(node, "URDF"))
+    {
+      urdfFromXML(node, self, suffix);
+    }
+    else if (isTag(node, "OpenRave"))
     {
       RCSB_LOG(1, "<%s> nodes are not supported by this loader - skipped", node->name);
     }
