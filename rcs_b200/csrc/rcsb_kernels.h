@@ -14,6 +14,7 @@
 #endif
 #define RCSB_FK_BLOCK(mass) ((mass) ? RCSB_FKM_THREADS : RCSB_FK_THREADS)
 #define RCSB_MAX_FRAME_SLOTS 8
+#define RCSB_KT_WALK_THREADS 128
 #define RCSB_KT_ASM_THREADS 128
 #define RCSB_IK_THREADS 128
 

@@ -108,39 +108,6 @@ struct Kin
   double ao[3];    /* bias acceleration of the point of the frame currently at f.o */
 };
 
-/* k = *sp if `on`, as predicated loads INTO the registers that hold k. Written as one asm statement
- * because every C++ formulation (branch, select) made the compiler keep two register sets for the
- * walk state and copy all of it from one to the other at the top and at the bottom of every body:
- * 96 moves per body, 11 % of the walk kernel's instructions (ncu source page, round 2). */
-template <bool VEL>
-__device__ __forceinline__ void loadKinIf(Kin& k, const double* sp, bool on)
-{
-  const int pr = on ? 1 : 0;
-  asm volatile(
-    "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %13, 0;\n\t"
-    "@p ld.f64 %0, [%12];\n\t@p ld.f64 %1, [%12+8];\n\t@p ld.f64 %2, [%12+16];\n\t"
-    "@p ld.f64 %3, [%12+24];\n\t@p ld.f64 %4, [%12+32];\n\t@p ld.f64 %5, [%12+40];\n\t"
-    "@p ld.f64 %6, [%12+48];\n\t@p ld.f64 %7, [%12+56];\n\t@p ld.f64 %8, [%12+64];\n\t"
-    "@p ld.f64 %9, [%12+72];\n\t@p ld.f64 %10, [%12+80];\n\t@p ld.f64 %11, [%12+88];\n\t}"
-    : "+d"(k.f.o[0]), "+d"(k.f.o[1]), "+d"(k.f.o[2]), "+d"(k.f.R[0]), "+d"(k.f.R[1]), "+d"(k.f.R[2]),
-      "+d"(k.f.R[3]), "+d"(k.f.R[4]), "+d"(k.f.R[5]), "+d"(k.f.R[6]), "+d"(k.f.R[7]), "+d"(k.f.R[8])
-    : "l"(sp), "r"(pr)
-    : "memory");
-  if (VEL)
-  {
-    asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %13, 0;\n\t"
-      "@p ld.f64 %0, [%12+96];\n\t@p ld.f64 %1, [%12+104];\n\t@p ld.f64 %2, [%12+112];\n\t"
-      "@p ld.f64 %3, [%12+120];\n\t@p ld.f64 %4, [%12+128];\n\t@p ld.f64 %5, [%12+136];\n\t"
-      "@p ld.f64 %6, [%12+144];\n\t@p ld.f64 %7, [%12+152];\n\t@p ld.f64 %8, [%12+160];\n\t"
-      "@p ld.f64 %9, [%12+168];\n\t@p ld.f64 %10, [%12+176];\n\t@p ld.f64 %11, [%12+184];\n\t}"
-      : "+d"(k.wik[0]), "+d"(k.wik[1]), "+d"(k.wik[2]), "+d"(k.wfl[0]), "+d"(k.wfl[1]), "+d"(k.wfl[2]),
-        "+d"(k.wd[0]), "+d"(k.wd[1]), "+d"(k.wd[2]), "+d"(k.ao[0]), "+d"(k.ao[1]), "+d"(k.ao[2])
-      : "l"(sp), "r"(pr)
-      : "memory");
-  }
-}
-
 __device__ __forceinline__ void addOffsetAccel(Kin& k, const double d[3])
 {
   /* point moves by d within the same rigid frame: a += wd x d + w x (w x d) */
@@ -171,15 +138,15 @@ __device__ __forceinline__ double pairing(const double* __restrict__ sj, const d
 /* WB (whole-body plans, rcsb_wholebody): the walk also stores the frames of the selected bodies
  * (A_BI: three 32-byte stores per frame like fkKernel) and emits the frames of the bodies the task
  * Jacobians refer to into the record. */
-template <bool VEL, int NSLOTS, bool WB, int T>
-__global__ void __launch_bounds__(T)
+template <bool VEL, int NSLOTS, bool WB>
+__global__ void __launch_bounds__(RCSB_KT_WALK_THREADS)
 ktWalkKernel(const KtArgs a)
 {
   extern __shared__ __align__(16) char smem[];
   char* sModel = smem;
   char* sPlan = smem + a.modelBytes;
   double* sWin = reinterpret_cast<double*>(sPlan + a.planWalkBytes);
-  double* sAcc = sWin + (T / 32) * 32 * 33;
+  double* sAcc = sWin + (RCSB_KT_WALK_THREADS / 32) * 32 * 33;
 
   stageBlobsTma(sModel, a.model, a.modelBytes, sPlan, a.plan, a.planWalkBytes);
 
@@ -188,6 +155,7 @@ ktWalkKernel(const KtArgs a)
   KtPlanView p;
   p.bind(sPlan);   /* only hdr, bodyLink, bodyEmit (and bodyOut, bodyFrameRec) are staged */
 
+  constexpr int T = RCSB_KT_WALK_THREADS;
   constexpr int LREC = RCSB_KT_LINK_REC_N(VEL), CREC = RCSB_KT_COL_REC_N(VEL);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -216,10 +184,7 @@ ktWalkKernel(const KtArgs a)
   rd.qd = VEL ? a.qd + sc * a.qdim : nullptr;
 
   constexpr int SLOT_DOUBLES = VEL ? 24 : 12;
-  /* frame stack of the branching points + a slot that parks the running state while a leaf body is
-   * evaluated + a slot holding the state of a root (world frame, at rest): every source of a body's
-   * start state is a slot, read by loadKinIf */
-  double stk[(NSLOTS + 2) * SLOT_DOUBLES];
+  double stk[(NSLOTS > 0 ? NSLOTS : 1) * SLOT_DOUBLES];
   const double grav = 9.81;
 
   /* mass properties of the bodies visited since the last emit (all of one link) */
@@ -240,37 +205,23 @@ ktWalkKernel(const KtArgs a)
     w.emitN(v);
   };
 
-  Kin k;
+  /* `keep` holds the running state while a leaf body is evaluated. The compiler answers with two
+   * register sets for the walk state and 2 x 48 moves per body (11 % of the kernel's instructions,
+   * ncu source page). Measured alternative (round 2): every start state of a body read from a
+   * frame-stack slot in local memory by predicated in-place loads, the leaf's parent parked there
+   * too - 250 -> 166 registers, 428 M -> 393 M warp instructions per 262,144 humanoid states, but the
+   * same 0.97 ms with velocities (the walk is latency-bound, not issue-bound), 1.57 -> 1.66 ms for
+   * the whole-body walk and 3 % more DRAM traffic (the stack lines are written back); 192-thread
+   * blocks, which the smaller footprint allows, are slower still (1.30 ms: less L1 next to the larger
+   * shared-memory carve-out). Not kept. */
+  Kin k, keep;
   setIdentity(k.f);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
   {
     k.wik[i] = k.wfl[i] = k.wd[i] = k.ao[i] = 0.0;
   }
-  auto park = [&](double* sp) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-    {
-      sp[i] = k.f.o[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-    {
-      sp[3 + i] = k.f.R[i];
-    }
-    if (VEL)
-    {
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-      {
-        sp[12 + i] = k.wik[i];
-        sp[15 + i] = k.wfl[i];
-        sp[18 + i] = k.wd[i];
-        sp[21 + i] = k.ao[i];
-      }
-    }
-  };
-  park(stk + (NSLOTS + 1) * SLOT_DOUBLES);
+  keep = k;
   double V = 0.0;
   double freeM[4] = {0.0, 0.0, 0.0, 0.0};   /* m, m c of massive bodies no joint moves */
   /* q / q_dot of the next RCSB_KT_PREFETCH joints are in flight while a joint is processed: the
@@ -301,13 +252,43 @@ ktWalkKernel(const KtArgs a)
 
     const int ld = m.bodyLoad[b];
     const int bflags = m.bodyFlags[b];
+    if (ld == RCSB_LOAD_IDENT)
     {
-      const int src = ld == RCSB_LOAD_IDENT ? NSLOTS + 1 : ld;
-      loadKinIf<VEL>(k, stk + (src > 0 ? src : 0) * SLOT_DOUBLES, src >= 0);
+      setIdentity(k.f);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        k.wik[i] = k.wfl[i] = k.wd[i] = k.ao[i] = 0.0;
+      }
+    }
+    else if (NSLOTS > 0 && ld >= 0)
+    {
+      const double* sp = stk + ld * SLOT_DOUBLES;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        k.f.o[i] = sp[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        k.f.R[i] = sp[3 + i];
+      }
+      if (VEL)
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          k.wik[i] = sp[12 + i];
+          k.wfl[i] = sp[15 + i];
+          k.wd[i] = sp[18 + i];
+          k.ao[i] = sp[21 + i];
+        }
+      }
     }
     if (bflags & RCSB_BF_LEAF)
     {
-      park(stk + NSLOTS * SLOT_DOUBLES);
+      keep = k;
     }
 
     const int j0 = m.bodyJntStart[b];
@@ -558,7 +539,10 @@ ktWalkKernel(const KtArgs a)
       }
     }
 
-    loadKinIf<VEL>(k, stk + NSLOTS * SLOT_DOUBLES, (bflags & RCSB_BF_LEAF) != 0);
+    if (bflags & RCSB_BF_LEAF)
+    {
+      k = keep;
+    }
   }
 
   if (p.bodyEmit[nb])
@@ -1121,53 +1105,38 @@ ktAssembleKernel(const KtArgs a, int groupStride)
   }
 }
 
-template <bool VEL, bool WB, int NS, int T>
-static cudaError_t launchWalkT(const KtArgs& a, cudaStream_t stream, bool probeOnly, int* threadsPerSm)
-{
-  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planWalkBytes +
-                           (size_t) (T / 32) * 32 * 33 * sizeof(double) +
-                           (size_t) RCSB_KT_LINK_REC_N(VEL) * T * sizeof(double);
-  auto k = ktWalkKernel<VEL, NS, WB, T>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes);
-  if (e != cudaSuccess)
-  {
-    return e;
-  }
-  if (probeOnly)
-  {
-    int perSm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k, T, smemBytes);
-    *threadsPerSm = e == cudaSuccess ? perSm * T : 0;
-    return e;
-  }
-  const dim3 grid((unsigned int) ((a.N + T - 1) / T));
-  k<<<grid, T, smemBytes, stream>>>(a);
-  return cudaGetLastError();
-}
-
-/* Block size: 128 threads, two blocks per SM. With the state loads of loadKinIf the kernel needs 166
- * registers (250 before), so 192-thread blocks fit twice as well (12 warps per SM instead of 8) —
- * measured SLOWER, 0.97 -> 1.30 ms per 262,144 humanoid states: the larger shared-memory carve-out
- * leaves the L1 half the room for the states' q / q_dot rows and frame stacks (their sectors are
- * re-fetched from L2), and 1366 blocks make 4.6 waves instead of 6.9. */
-template <bool VEL, bool WB, int NS>
-static cudaError_t launchWalkNs(const KtArgs& a, cudaStream_t stream)
-{
-  return launchWalkT<VEL, WB, NS, 128>(a, stream, false, nullptr);
-}
-
 template <bool VEL, bool WB>
 static cudaError_t launchWalk(const KtArgs& a, int nSlots, cudaStream_t stream)
 {
+  const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planWalkBytes +
+                           (size_t) (RCSB_KT_WALK_THREADS / 32) * 32 * 33 * sizeof(double) +
+                           (size_t) RCSB_KT_LINK_REC_N(VEL) * RCSB_KT_WALK_THREADS * sizeof(double);
+  const dim3 grid((unsigned int) ((a.N + RCSB_KT_WALK_THREADS - 1) / RCSB_KT_WALK_THREADS));
+#define RCSB_LAUNCH(NS)                                                                        \
+  {                                                                                            \
+    auto k = ktWalkKernel<VEL, NS, WB>;                                                            \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, RCSB_KT_WALK_THREADS, smemBytes, stream>>>(a);                                   \
+    return cudaGetLastError();                                                                 \
+  }
   if (nSlots <= 0)
   {
-    return launchWalkNs<VEL, WB, 0>(a, stream);
+    RCSB_LAUNCH(0)
   }
-  if (nSlots <= 2)
+  else if (nSlots <= 2)
   {
-    return launchWalkNs<VEL, WB, 2>(a, stream);
+    RCSB_LAUNCH(2)
   }
-  return launchWalkNs<VEL, WB, RCSB_MAX_FRAME_SLOTS>(a, stream);
+  else
+  {
+    RCSB_LAUNCH(RCSB_MAX_FRAME_SLOTS)
+  }
+#undef RCSB_LAUNCH
 }
 
 template <bool VEL, int LPS>
