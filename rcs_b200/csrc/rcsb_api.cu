@@ -87,6 +87,13 @@ static long stageChunk(size_t bytesPerState)
   return (c + 383) / 384 * 384;
 }
 
+static thread_local const StageTap* t_stageTap = nullptr;
+
+void setStageTap(const StageTap* tap)
+{
+  t_stageTap = tap;
+}
+
 int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
               const std::vector<int>& aliasOutToIn,
               const std::function<int(long n, cudaStream_t st, int slot)>& launch)
@@ -125,8 +132,25 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
       nSlots = atoi(env);
     }
   }
-  int slot = 0;
-  for (long s0 = 0; s0 < N; s0 += chunk, slot = (slot + 1) % nSlots)
+  const StageTap* tap = t_stageTap;
+  int tapArray = -1;
+  if (tap && tap->hostOut)
+  {
+    for (size_t i = 0; i < arrays.size(); ++i)
+    {
+      tapArray = (arrays[i].hostOut == tap->hostOut && arrays[i].perState > 0) ? (int) i : tapArray;
+    }
+    if (tapArray >= 0 && tap->begin)
+    {
+      const int rcTap = tap->begin((int) ((N + chunk - 1) / chunk));
+      if (rcTap != RCSB_OK)
+      {
+        return rcTap;
+      }
+    }
+  }
+  int slot = 0, stageIndex = 0;
+  for (long s0 = 0; s0 < N; s0 += chunk, slot = (slot + 1) % nSlots, ++stageIndex)
   {
     const long n = (N - s0 < chunk) ? (N - s0) : chunk;
     int rc = pipeReserve(m, slot, need);
@@ -150,6 +174,14 @@ int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
     if (rc != RCSB_OK)
     {
       return rc;
+    }
+    if (tapArray >= 0 && tap->stage)
+    {
+      rc = tap->stage(arrays[(size_t) tapArray].dev, s0, n, stageIndex, st);
+      if (rc != RCSB_OK)
+      {
+        return rc;
+      }
     }
     for (size_t i = 0; i < arrays.size(); ++i)
     {

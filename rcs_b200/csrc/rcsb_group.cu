@@ -93,20 +93,6 @@ struct RcsbGroup
 namespace
 {
 
-/* one array of a group call: `perState` doubles per state, host pointer of the WHOLE batch */
-struct GArray
-{
-  const double* in;
-  double* out;
-  size_t perState;
-  double* dev;                 /* device address of this member's slice (set per member) */
-};
-
-size_t carve(size_t doubles)
-{
-  return (doubles * sizeof(double) + 255) & ~(size_t) 255;
-}
-
 int reserve(Member& mb, size_t bytes)
 {
   if (mb.cap >= bytes)
@@ -125,16 +111,19 @@ int reserve(Member& mb, size_t bytes)
 }
 
 /*
- * Runs one call on every member: copy the member's slice of the inputs to its device, launch
- * (device-pointer entry point on the member's stream), reduce the statistics source, all-gather
- * the statistics over NCCL, copy the results back. `launch` returns the device address and
- * stride of the per-state value the statistics are taken of (or nullptr).
+ * Runs one call on every member, each on its own host thread: the member's slice goes through the
+ * host-pointer entry point of the single-device API (H2D, kernels and D2H of successive stages
+ * overlap on three streams, rcsb_api.cu), the summary statistics of the per-state value `statHost`
+ * names are reduced on the device stage by stage while the value is still there (StageTap), their
+ * partial results are merged, and the members all-gather the 5 doubles over NCCL.
+ *   call(mb, first, n)  the host-pointer call on the slice [first, first + n)
+ *   statHost            host address (whole batch) of the output the statistics are taken of, or NULL
+ *   statPerState        doubles per state of that output, statOffset the entry within a state's record
  */
-typedef std::function<int(Member& mb, long n, std::vector<GArray>& arr, const double** statSrc,
-                          long* statStride)> GroupLaunch;
+typedef std::function<int(Member& mb, long first, long n)> GroupCall;
 
-int runGroup(RcsbGroup* g, long N, const std::vector<GArray>& arrays, const GroupLaunch& launch,
-             double* statsOut)
+int runGroup(RcsbGroup* g, long N, const GroupCall& call, const double* statHost, size_t statPerState,
+             size_t statOffset, double* statsOut)
 {
   std::lock_guard<std::mutex> lock(g->mtx);
   const int R = (int) g->members.size();
@@ -147,54 +136,45 @@ int runGroup(RcsbGroup* g, long N, const std::vector<GArray>& arrays, const Grou
         long first = 0, n = 0;
         rcsb_group_slice(g, N, r, &first, &n);
         RCSB_CUDA(cudaSetDevice(mb.device));
-        std::vector<GArray> arr = arrays;
-        size_t need = 0;
-        for (GArray& a : arr)
+        int nStages = 0;
+        StageTap tap;
+        if (statHost && n > 0)
         {
-          need += carve((size_t) n * a.perState);
+          tap.hostOut = statHost + (size_t) first * statPerState;
+          tap.begin = [&](int stages) -> int {
+            nStages = stages;
+            return reserve(mb, (size_t) stages * 5 * sizeof(double));
+          };
+          tap.stage = [&](const double* dev, long, long cnt, int stageIndex, cudaStream_t st) -> int {
+            return rcsb_summary_stats(dev + statOffset, cnt, (long) statPerState,
+                                      reinterpret_cast<double*>(mb.buf) + 5 * stageIndex, st);
+          };
+          setStageTap(&tap);
         }
-        int rc = reserve(mb, need > 0 ? need : 256);
+        int rc = n > 0 ? call(mb, first, n) : RCSB_OK;
+        setStageTap(nullptr);
         if (rc != RCSB_OK)
         {
           return rc;
         }
-        size_t off = 0;
-        for (GArray& a : arr)
+        /* merge the stages' statistics (the call has synchronised its streams) */
+        double mine[5] = {0.0, 0.0, 0.0, 1.0 / 0.0, -1.0 / 0.0};
+        if (nStages > 0)
         {
-          a.dev = a.perState ? reinterpret_cast<double*>(mb.buf + off) : nullptr;
-          off += carve((size_t) n * a.perState);
-          if (a.in && a.perState && n > 0)
+          std::vector<double> part((size_t) nStages * 5);
+          RCSB_CUDA(cudaMemcpy(part.data(), mb.buf, part.size() * sizeof(double), cudaMemcpyDeviceToHost));
+          for (int k = 0; k < nStages; ++k)
           {
-            RCSB_CUDA(cudaMemcpyAsync(a.dev, a.in + (size_t) first * a.perState,
-                                      sizeof(double) * (size_t) n * a.perState, cudaMemcpyHostToDevice,
-                                      mb.stream));
+            const double* p5 = part.data() + 5 * k;
+            mine[0] += p5[0];
+            mine[1] += p5[1];
+            mine[2] += p5[2];
+            mine[3] = p5[3] < mine[3] ? p5[3] : mine[3];
+            mine[4] = p5[4] > mine[4] ? p5[4] : mine[4];
           }
         }
-        const double* statSrc = nullptr;
-        long statStride = 1;
-        if (n > 0)
-        {
-          rc = launch(mb, n, arr, &statSrc, &statStride);
-          if (rc != RCSB_OK)
-          {
-            return rc;
-          }
-        }
-        /* summary statistics of this rank, then the all-gather: every rank takes part, also one
-         * with an empty slice (count 0) */
-        if (statSrc && n > 0)
-        {
-          rc = rcsb_summary_stats(statSrc, n, statStride, mb.stats, mb.stream);
-          if (rc != RCSB_OK)
-          {
-            return rc;
-          }
-        }
-        else
-        {
-          const double empty[5] = {0.0, 0.0, 0.0, 1.0 / 0.0, -1.0 / 0.0};
-          RCSB_CUDA(cudaMemcpyAsync(mb.stats, empty, sizeof(empty), cudaMemcpyHostToDevice, mb.stream));
-        }
+        /* every rank takes part in the all-gather, also one with an empty slice (count 0) */
+        RCSB_CUDA(cudaMemcpyAsync(mb.stats, mine, sizeof(mine), cudaMemcpyHostToDevice, mb.stream));
         if (R > 1)
         {
           const ncclResult_t e = nccl().allGather(mb.stats, mb.stats + 5, 5, ncclDouble, mb.comm, mb.stream);
@@ -208,15 +188,6 @@ int runGroup(RcsbGroup* g, long N, const std::vector<GArray>& arrays, const Grou
         {
           RCSB_CUDA(cudaMemcpyAsync(mb.stats + 5, mb.stats, 5 * sizeof(double), cudaMemcpyDeviceToDevice,
                                     mb.stream));
-        }
-        for (GArray& a : arr)
-        {
-          if (a.out && a.perState && n > 0)
-          {
-            RCSB_CUDA(cudaMemcpyAsync(a.out + (size_t) first * a.perState, a.dev,
-                                      sizeof(double) * (size_t) n * a.perState, cudaMemcpyDeviceToHost,
-                                      mb.stream));
-          }
         }
         if (r == 0 && statsOut)
         {
@@ -245,6 +216,13 @@ int runGroup(RcsbGroup* g, long N, const std::vector<GArray>& arrays, const Grou
     }
   }
   return RCSB_OK;
+}
+
+/* host address of a member's slice of an array of the whole batch (NULL stays NULL) */
+template <typename T>
+T* sliceOf(T* base, long first, size_t perState)
+{
+  return base ? base + (size_t) first * perState : nullptr;
 }
 
 }   // namespace
@@ -398,23 +376,13 @@ extern "C" int rcsb_group_fk_jacobians_mass(RcsbGroup* g, long N, int qdim, cons
   }
   const RcsbModel* m0 = g->members[0].model;
   const size_t nJ = (size_t) m0->hdr.nJ, nOut = nSel > 0 ? (size_t) nSel : (size_t) m0->hdr.nb;
-  std::vector<GArray> arr;
-  enum { I_Q, I_A, I_JT, I_JR, I_M };
-  arr.push_back({q, nullptr, (size_t) qdim, nullptr});
-  arr.push_back({nullptr, A_BI, A_BI ? nOut * 12 : 0, nullptr});
-  arr.push_back({nullptr, JT, JT ? (size_t) nEff * 3 * nJ : 0, nullptr});
-  arr.push_back({nullptr, JR, JR ? (size_t) nEff * 3 * nJ : 0, nullptr});
-  arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
-  return runGroup(g, N, arr, [&](Member& mb, long n, std::vector<GArray>& a, const double** src, long* stride) {
-    /* statistics: height (world z) of the first selected frame */
-    if (a[I_A].dev)
-    {
-      *src = a[I_A].dev + 2;
-      *stride = (long) nOut * 12;
-    }
-    return rcsb_fk_jacobians_mass(mb.model, n, qdim, a[I_Q].dev, nSel, bodySel, a[I_A].dev, nEff, effBody,
-                                  effPt, a[I_JT].dev, a[I_JR].dev, a[I_M].dev, 0, mb.stream);
-  }, stats);
+  /* statistics: height (world z) of the first selected frame */
+  return runGroup(g, N, [&](Member& mb, long first, long n) {
+    return rcsb_fk_jacobians_mass(mb.model, n, qdim, sliceOf(q, first, (size_t) qdim), nSel, bodySel,
+                                  sliceOf(A_BI, first, nOut * 12), nEff, effBody, effPt,
+                                  sliceOf(JT, first, (size_t) nEff * 3 * nJ), sliceOf(JR, first, (size_t) nEff * 3 * nJ),
+                                  sliceOf(M, first, nJ * nJ), RCSB_HOST_PTRS, nullptr);
+  }, A_BI, nOut * 12, 2, stats);
 }
 
 extern "C" int rcsb_group_kinetic_terms(RcsbGroup* g, long N, int qdim, const double* q, const double* qd,
@@ -426,23 +394,12 @@ extern "C" int rcsb_group_kinetic_terms(RcsbGroup* g, long N, int qdim, const do
     return RCSB_EINVAL;
   }
   const size_t nJ = (size_t) g->members[0].model->hdr.nJ;
-  std::vector<GArray> arr;
-  enum { I_Q, I_QD, I_M, I_H, I_G, I_E };
-  arr.push_back({q, nullptr, (size_t) qdim, nullptr});
-  arr.push_back({qd, nullptr, qd ? (size_t) qdim : 0, nullptr});
-  arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
-  arr.push_back({nullptr, h, h ? nJ : 0, nullptr});
-  arr.push_back({nullptr, Fg, Fg ? nJ : 0, nullptr});
-  arr.push_back({nullptr, E, (size_t) (E ? 1 : 0), nullptr});
-  return runGroup(g, N, arr, [&](Member& mb, long n, std::vector<GArray>& a, const double** src, long* stride) {
-    if (a[I_E].dev)
-    {
-      *src = a[I_E].dev;     /* statistics: total energy */
-      *stride = 1;
-    }
-    return rcsb_kinetic_terms(mb.model, n, qdim, a[I_Q].dev, a[I_QD].dev, a[I_M].dev, a[I_H].dev, a[I_G].dev,
-                              a[I_E].dev, 0, mb.stream);
-  }, stats);
+  /* statistics: total energy */
+  return runGroup(g, N, [&](Member& mb, long first, long n) {
+    return rcsb_kinetic_terms(mb.model, n, qdim, sliceOf(q, first, (size_t) qdim), sliceOf(qd, first, (size_t) qdim),
+                              sliceOf(M, first, nJ * nJ), sliceOf(h, first, nJ), sliceOf(Fg, first, nJ),
+                              sliceOf(E, first, 1), RCSB_HOST_PTRS, nullptr);
+  }, E, 1, 0, stats);
 }
 
 extern "C" int rcsb_group_ik_rmr(RcsbGroup* g, int nTasks, const RcsbTask* tasks, long N, double* q,
@@ -460,19 +417,19 @@ extern "C" int rcsb_group_ik_rmr(RcsbGroup* g, int nTasks, const RcsbTask* tasks
   {
     nx += tasks[t].kind == RCSB_TASK_XYZABC ? 6 : 3;
   }
-  std::vector<GArray> arr;
-  enum { I_Q, I_X, I_DX, I_DQ, I_DET };
-  arr.push_back({q, q, dof, nullptr});          /* in-out */
-  arr.push_back({xDes, nullptr, nx, nullptr});
-  arr.push_back({nullptr, dx, dx ? nx : 0, nullptr});
-  arr.push_back({nullptr, dq, dq ? dof : 0, nullptr});
-  arr.push_back({nullptr, det, (size_t) 1, nullptr});   /* always computed: source of the statistics */
-  return runGroup(g, N, arr, [&](Member& mb, long n, std::vector<GArray>& a, const double** src, long* stride) {
-    *src = a[I_DET].dev;
-    *stride = 1;
-    return rcsb_ik_rmr(mb.model, nTasks, tasks, n, a[I_Q].dev, a[I_X].dev, lambda, alpha, iters, a[I_DX].dev,
-                       a[I_DQ].dev, a[I_DET].dev, 0, mb.stream);
-  }, stats);
+  /* statistics: det of the last iteration; always computed, into a scratch array if the caller
+   * does not ask for it */
+  std::vector<double> detScratch;
+  if (!det && N > 0)
+  {
+    detScratch.resize((size_t) N);
+    det = detScratch.data();
+  }
+  return runGroup(g, N, [&](Member& mb, long first, long n) {
+    return rcsb_ik_rmr(mb.model, nTasks, tasks, n, sliceOf(q, first, dof), sliceOf(xDes, first, nx), lambda, alpha,
+                       iters, sliceOf(dx, first, nx), sliceOf(dq, first, dof), sliceOf(det, first, 1),
+                       RCSB_HOST_PTRS, nullptr);
+  }, det, 1, 0, stats);
 }
 
 extern "C" int rcsb_group_wholebody(RcsbGroup* g, long N, int qdim, const double* q, int nSel,
@@ -486,20 +443,10 @@ extern "C" int rcsb_group_wholebody(RcsbGroup* g, long N, int qdim, const double
   }
   const RcsbModel* m0 = g->members[0].model;
   const size_t nJ = (size_t) m0->hdr.nJ, nOut = nSel > 0 ? (size_t) nSel : (size_t) m0->hdr.nb;
-  std::vector<GArray> arr;
-  enum { I_Q, I_A, I_J, I_M, I_JC };
-  arr.push_back({q, nullptr, (size_t) qdim, nullptr});
-  arr.push_back({nullptr, A_BI, A_BI ? nOut * 12 : 0, nullptr});
-  arr.push_back({nullptr, J, J ? (size_t) nJac * 3 * nJ : 0, nullptr});
-  arr.push_back({nullptr, M, M ? nJ * nJ : 0, nullptr});
-  arr.push_back({nullptr, Jcog, Jcog ? 3 * nJ : 0, nullptr});
-  return runGroup(g, N, arr, [&](Member& mb, long n, std::vector<GArray>& a, const double** src, long* stride) {
-    if (a[I_M].dev)
-    {
-      *src = a[I_M].dev;     /* statistics: M[0][0] */
-      *stride = (long) (nJ * nJ);
-    }
-    return rcsb_wholebody(mb.model, n, qdim, a[I_Q].dev, nSel, bodySel, a[I_A].dev, nJac, jac, a[I_J].dev,
-                          a[I_M].dev, a[I_JC].dev, 0, mb.stream);
-  }, stats);
+  /* statistics: M[0][0] */
+  return runGroup(g, N, [&](Member& mb, long first, long n) {
+    return rcsb_wholebody(mb.model, n, qdim, sliceOf(q, first, (size_t) qdim), nSel, bodySel,
+                          sliceOf(A_BI, first, nOut * 12), nJac, jac, sliceOf(J, first, (size_t) nJac * 3 * nJ),
+                          sliceOf(M, first, nJ * nJ), sliceOf(Jcog, first, 3 * nJ), RCSB_HOST_PTRS, nullptr);
+  }, M, nJ * nJ, 0, stats);
 }

@@ -132,15 +132,30 @@ struct StagedArray
 };
 
 /*
- * Runs `launch(n, stream)` over chunks of the batch: inputs are copied host -> device,
- * the kernel is enqueued, outputs are copied device -> host, alternating between two
- * streams so that the copies of one chunk overlap the kernel of the other. In-out arrays
+ * Runs `launch(n, stream)` over stages of the batch: inputs are copied host -> device,
+ * the kernel is enqueued, outputs are copied device -> host, rotating over RCSB_PIPE_SLOTS
+ * streams so that the copies of one stage overlap the kernels of the others. In-out arrays
  * are listed twice (once as input, once as output, same perState) and share a buffer when
  * `aliasOutToIn` names the input's index. Returns after all results are in host memory.
  */
 int runStaged(RcsbModel* m, long N, std::vector<StagedArray>& arrays,
               const std::vector<int>& aliasOutToIn,
               const std::function<int(long n, cudaStream_t st, int slot)>& launch);
+
+/*
+ * Per-stage hook of runStaged for the calling thread (device groups: the summary statistics of a
+ * per-state result are reduced on the device, stage by stage, while the result is still there).
+ * `hostOut` names the watched output array by the host address the caller passed for it; after the
+ * kernels of a stage `stage(dev, s0, n, stageIndex, stream)` is called with the device address of
+ * that stage's part of the array; `begin(nStages)` once before the first stage.
+ */
+struct StageTap
+{
+  const double* hostOut = nullptr;
+  std::function<int(int nStages)> begin;
+  std::function<int(const double* dev, long s0, long n, int stageIndex, cudaStream_t st)> stage;
+};
+void setStageTap(const StageTap* tap);   /* thread-local; nullptr clears it */
 
 /* Forward kinematics (+ Jacobians) behind rcsb_fk / rcsb_fk_jacobians and the single-state
  * RcsGraph_* wrappers; qdOut and noCoupling are only reachable from the latter. */

@@ -51,6 +51,23 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         res[name] = args.reps * n * 8 / dt / 1e9
+    # both directions at once, each on its own stream with its own buffers (PCIe is full duplex; what
+    # the host side sustains is the question)
+    dev2 = torch.empty(n, dtype=torch.float64, device=f"cuda:{local}")
+    host2 = torch.empty(n, dtype=torch.float64, pin_memory=True).zero_()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.reps):
+        with torch.cuda.stream(s_out):
+            host.copy_(dev, non_blocking=True)
+        with torch.cuda.stream(s_in):
+            dev2.copy_(host2, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res["duplex_each"] = args.reps * n * 8 / dt / 1e9
     gathered = [None] * world
     if world > 1:
         dist.all_gather_object(gathered, (local, res, info))
@@ -62,6 +79,7 @@ def main():
                "h2d_gbs_per_gpu": [round(g[1]["h2d"], 2) for g in gathered],
                "d2h_gbs_total": round(sum(g[1]["d2h"] for g in gathered), 2),
                "h2d_gbs_total": round(sum(g[1]["h2d"] for g in gathered), 2),
+               "duplex_gbs_each_direction_per_gpu": [round(g[1]["duplex_each"], 2) for g in gathered],
                "binding": [g[2] for g in gathered]}
         print(json.dumps(out))
     if world > 1:
