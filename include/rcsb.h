@@ -284,7 +284,8 @@ int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, 
  *   XYZABC  TaskPose6D: XYZ followed by ABC with the same bodies
  *   COGX / COGY / COGZ   TaskCOM1D (TaskCOM1D.cpp:105-125): one component of the centre of gravity of
  *           the subtree of `effector` (-1: the whole graph, RcsGraph_COG / RcsGraph_COGJacobian,
- *           Rcs_kinematics.c:904-1036); no reference body
+ *           Rcs_kinematics.c:904-1036), in world coordinates or, with refBdy, relative to that body
+ *           and in its frame (TaskCOM3D.cpp:101-165)
  *   JOINT   TaskJoint (TaskJoint.cpp:227-265): the value of joint `effector` (a jointIndex; the
  *           joint must be unconstrained)
  *   POLARX / POLARY / POLARZ   TaskPolar2D (controlVariable "POLAR" with axisDirection "X" / "Y" /

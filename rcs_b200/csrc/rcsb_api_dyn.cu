@@ -1557,10 +1557,11 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
     }
     if (ts.kind >= RCSB_TASK_COGX && ts.kind <= RCSB_TASK_COGZ)
     {
-      if (!bodyOk(ts.effector) || ts.refBdy >= 0 || ts.refFrame >= 0)
+      if (!bodyOk(ts.effector) || !bodyOk(ts.refBdy) || (ts.refFrame >= 0 && ts.refFrame != ts.refBdy))
       {
-        rcsb_set_error("task %d: COG tasks take a subtree root (or -1) and no reference body", t);
-        return ts.refBdy >= 0 || ts.refFrame >= 0 ? RCSB_EUNSUPPORTED : RCSB_EINVAL;
+        rcsb_set_error("task %d: COG tasks take a subtree root (or -1), optionally a reference body, and no "
+                       "separate reference frame", t);
+        return ts.refFrame >= 0 ? RCSB_EUNSUPPORTED : RCSB_EINVAL;
       }
       if (cogRoot != -2 && cogRoot != ts.effector)
       {
@@ -1568,7 +1569,8 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
         return RCSB_EUNSUPPORTED;
       }
       cogRoot = ts.effector;
-      const int rec[8] = {ts.kind, row, 1, 0, 0, 0, ts.kind - RCSB_TASK_COGX, 0};
+      /* TaskCOM3D with refBody (TaskCOM3D.cpp:101-105, :128-165): slot of the reference body */
+      const int rec[8] = {ts.kind, row, 1, 0, slot(ts.refBdy), 0, ts.kind - RCSB_TASK_COGX, 0};
       task.insert(task.end(), rec, rec + 8);
       row += 1;
       continue;

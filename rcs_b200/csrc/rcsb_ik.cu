@@ -1622,10 +1622,48 @@ ikTasksKernel(const IkArgs a)
       }
       if (kind >= RCSB_TASK_COGX && kind <= RCSB_TASK_COGZ)
       {
-        dx[row] = xd[0] - mc[aux] * invM;
+        if (sR == 0)
+        {
+          dx[row] = xd[0] - mc[aux] * invM;
+          for (int k = 0; k < nJ; ++k)
+          {
+            Jr[k] = Jc[aux * nJ + k] * invM;
+          }
+          continue;
+        }
+        /* relative to a reference body (TaskCOM3D::computeX / computeJ): x = A_R (c - o_R);
+         * J = A_R J_cog for a fixed reference, else A_R (J_cog - JT_R + (c - o_R) x JR_R[:, k]) */
+        const double* A = fR + 3 + 3 * aux;          /* row `aux` of A_R */
+        const double c[3] = {mc[0] * invM, mc[1] * invM, mc[2] * invM};
+        const double r[3] = {c[0] - fR[0], c[1] - fR[1], c[2] - fR[2]};
+        dx[row] = xd[0] - (A[0] * r[0] + A[1] * r[1] + A[2] * r[2]);
+        const unsigned long long mRc = p.slotMask[sR];
         for (int k = 0; k < nJ; ++k)
         {
-          Jr[k] = Jc[aux * nJ + k] * invM;
+          double v[3] = {Jc[k] * invM, Jc[nJ + k] * invM, Jc[2 * nJ + k] * invM};
+          if ((mRc >> k) & 1ull)
+          {
+            const double* jc = ja + 6 * k;
+            if (m.jntFlags[p.colJoint[k]] & RCSB_JF_ROT)
+            {
+              /* JT_R column: a x (o_R - o_k); MatNd_columnCrossProductSelf(JR_R, r): r x a (the frame
+               * of the reference turns under the centre of gravity) */
+              const double d0 = fR[0] - jc[3], d1 = fR[1] - jc[4], d2 = fR[2] - jc[5];
+              v[0] -= jc[1] * d2 - jc[2] * d1;
+              v[1] -= jc[2] * d0 - jc[0] * d2;
+              v[2] -= jc[0] * d1 - jc[1] * d0;
+              v[0] += r[1] * jc[2] - r[2] * jc[1];
+              v[1] += r[2] * jc[0] - r[0] * jc[2];
+              v[2] += r[0] * jc[1] - r[1] * jc[0];
+            }
+            else
+            {
+              v[0] -= jc[0];
+              v[1] -= jc[1];
+              v[2] -= jc[2];
+            }
+          }
+          Jr[k] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
         }
         continue;
       }

@@ -75,8 +75,11 @@ def test_cAction_task_set_of_the_humanoid(refmod, cuda_device):
     ("wam_arm", [("ABC", "BallTip", "Base", "Base"), ("XYZ", "Link4", "Base")]),
     ("gantry", [("XYZ", "Tool", "Trolley"), ("ABC", "Tool", "Quill", "Trolley"), ("COGY", "Quill")]),
     ("gantry", [("Joint", "WristYaw"), ("Joint", "GantryX"), ("XYZ", "Camera", "", "WristLink")]),
+    ("wam_arm", [("COGX", "", "Link3"), ("COGZ", "", "Link3"), ("XYZ", "BallTip")]),
+    ("wam_arm", [("COGY", "Link2", "Base"), ("COGX", "Link2", "Base"), ("ABC", "BallTip")]),
+    ("humanoid", [("COGX", "", "FootL"), ("COGY", "", "FootL"), ("XYZ", "RightHandTip", "FootL")]),
 ], ids=["rel-frames", "frame-only", "pose6d-cogz", "joint-xyz-subtree-cog", "fixed-reference", "gantry-rel",
-        "gantry-joints"])
+        "gantry-joints", "cog-rel-articulated", "cog-subtree-rel-fixed", "humanoid-cog-rel-foot"])
 def test_reference_bodies_frames_cog_and_joint_tasks(name, names, refmod, cuda_device):
     """Every branch of RcsGraph_3dPosJacobian / RcsGraph_3dOmegaJacobian (world, refFrame only,
     articulated refBdy, refFrame != refBdy, fixed reference body), relative Euler angles, COG of the
@@ -157,5 +160,5 @@ def test_task_stack_errors(cuda_device):
     m2 = rcs_b200.Model(g2, cuda_device)
     with pytest.raises(rcs_b200.RcsbError, match="same subtree"):
         m2.ik_tasks_rmr([(TASK_COGX, -1), (TASK_COGY, 3)], np.zeros((2, 7)), np.zeros((2, 2)))
-    with pytest.raises(rcs_b200.RcsbError, match="reference body"):
-        m2.ik_tasks_rmr([(TASK_COGX, -1, 2)], np.zeros((2, 7)), np.zeros((2, 1)))
+    with pytest.raises(rcs_b200.RcsbError, match="reference frame"):
+        m2.ik_tasks_rmr([(TASK_COGX, -1, 2, 3)], np.zeros((2, 7)), np.zeros((2, 1)))
