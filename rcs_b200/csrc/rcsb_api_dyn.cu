@@ -1213,6 +1213,14 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   dp.nEff = ph.multiNu;
   dp.nSel = ph.nEffs;
   dp.nScrRows = nTasks | (walkSlots << 8);
+  {
+    bool allRot = chainNc > 0;
+    for (int c = 0; c < chainNc; ++c)
+    {
+      allRot = allRot && (chainType[(size_t) c] & 15) < 3;
+    }
+    dp.aux2 = (allRot ? RCSB_IK_CHAIN_ALLROT : 0) | (kind[0] == RCSB_TASK_XYZ ? RCSB_IK_CHAIN_XYZ_FIRST : 0);
+  }
   auto ins = m->ikPlans.emplace(key, dp);
   *out = &ins.first->second;
   return RCSB_OK;
@@ -1308,6 +1316,7 @@ int ikDevice(RcsbModel* m, const DevicePlan* plan, long N, double* q, const doub
   a.alpha = alpha;
   a.iters = iters;
   a.leftInverse = leftInverse ? 1 : 0;
+  a.chainFlags = plan->aux2;
   a.dx = dx;
   a.dq = dq;
   a.det = det;

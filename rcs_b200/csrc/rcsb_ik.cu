@@ -2023,7 +2023,12 @@ __device__ __forceinline__ void chainStep(Frame& f, const int4 st, const double*
 /* LEFT: the step of IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) instead: with
  * J_r = J invWq, dq = invWq o (g + (J_r^T J_r + lambda 1)^-1 J_r^T (dx - J_r g)), the NC x NC
  * system factored like the NX x NX one of the right inverse. */
-template <int NC, int NX, bool LEFT = false>
+/* MODE 0: column types and the order of the two tasks are read from the plan at run time.
+ * MODE 1 / 2: every column is a rotation and the position task comes first / second (what the plan
+ * builder reports in IkArgs::chainFlags): no per-column type branches and no row selects — the
+ * merges behind those branches were 18 % of the executed instructions as register moves —, and the
+ * sines / cosines of all columns are evaluated together before the walk (sincosBatch). */
+template <int NC, int NX, bool LEFT = false, int MODE = 0>
 __global__ void __launch_bounds__(RCSB_IK_THREADS, RCSB_IK_CHAIN_MIN_BLOCKS)
 ikChainKernel(const IkArgs a)
 {
@@ -2047,8 +2052,9 @@ ikChainKernel(const IkArgs a)
 
   constexpr int NT = NX / 3;
   constexpr int NA = NX * (NX + 1) / 2;
+  constexpr bool ALLROT = MODE != 0;
   const int dof = m.hdr->dof;
-  const bool xyzFirst = p.taskKind[0] == RCSB_TASK_XYZ;
+  const bool xyzFirst = MODE == 0 ? (p.taskKind[0] == RCSB_TASK_XYZ) : (MODE == 1);
   const bool hasAbc = (NT == 2) || !xyzFirst;
   const bool hasXyz = (NT == 2) || xyzFirst;
   double* qRow = a.q + s * dof;
@@ -2104,6 +2110,19 @@ ikChainKernel(const IkArgs a)
     setIdentity(f);
     double ax[NC][3], jo[NC][3];
     bool isRot[NC];
+    double snAll[NC], csAll[NC];
+    if constexpr (ALLROT)
+    {
+      if (!sincosBatch<NC>(qc, snAll, csAll))
+      {
+        /* an argument beyond the fast range of the reduction (or not finite): the library's path */
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+        {
+          sincos(qc[c], &snAll[c], &csAll[c]);
+        }
+      }
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c)
     {
@@ -2111,12 +2130,20 @@ ikChainKernel(const IkArgs a)
       {
         chainStep<true>(f, p.prog[k], p.chainXf, qRow);
       }
-      const int ctype = p.chainType[c];
-      isRot[c] = (ctype & 15) < 3;
+      const int ctype = ALLROT ? 0 : p.chainType[c];
+      isRot[c] = ALLROT || (ctype & 15) < 3;
       if (isRot[c])
       {
         double sn, cs;
-        sincos(qc[c], &sn, &cs);
+        if (ALLROT)
+        {
+          sn = snAll[c];
+          cs = csAll[c];
+        }
+        else
+        {
+          sincos(qc[c], &sn, &cs);
+        }
         rotateRows01(f, sn, cs);
         ax[c][0] = f.R[6];         /* the axis of a rotation is row 2 of the shifted frame */
         ax[c][1] = f.R[7];
@@ -3290,13 +3317,13 @@ static cudaError_t launchMulti(const IkArgs& a, int nSlots, int nU, int nEffs, c
 #undef RCSB_LAUNCH
 }
 
-template <int NC, int NX, bool LEFT = false>
+template <int NC, int NX, bool LEFT = false, int MODE = 0>
 static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
 {
   const size_t smemBytes = (size_t) a.modelBytes + (size_t) a.planBytes +
                            9 * RCSB_IK_THREADS * sizeof(double);
   const dim3 grid((unsigned int) ((a.N + RCSB_IK_THREADS - 1) / RCSB_IK_THREADS));
-  auto k = ikChainKernel<NC, NX, LEFT>;
+  auto k = ikChainKernel<NC, NX, LEFT, MODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int) smemBytes);
   if (e != cudaSuccess)
@@ -3307,21 +3334,33 @@ static cudaError_t launchChain(const IkArgs& a, cudaStream_t stream)
   return cudaGetLastError();
 }
 
-template <int NX, bool LEFT = false>
+template <int NX, bool LEFT = false, int MODE = 0>
 static cudaError_t launchChainNc(const IkArgs& a, int nc, cudaStream_t stream)
 {
   switch (nc)
   {
-    case 1: return launchChain<1, NX, LEFT>(a, stream);
-    case 2: return launchChain<2, NX, LEFT>(a, stream);
-    case 3: return launchChain<3, NX, LEFT>(a, stream);
-    case 4: return launchChain<4, NX, LEFT>(a, stream);
-    case 5: return launchChain<5, NX, LEFT>(a, stream);
-    case 6: return launchChain<6, NX, LEFT>(a, stream);
-    case 7: return launchChain<7, NX, LEFT>(a, stream);
-    case 8: return launchChain<8, NX, LEFT>(a, stream);
+    case 1: return launchChain<1, NX, LEFT, MODE>(a, stream);
+    case 2: return launchChain<2, NX, LEFT, MODE>(a, stream);
+    case 3: return launchChain<3, NX, LEFT, MODE>(a, stream);
+    case 4: return launchChain<4, NX, LEFT, MODE>(a, stream);
+    case 5: return launchChain<5, NX, LEFT, MODE>(a, stream);
+    case 6: return launchChain<6, NX, LEFT, MODE>(a, stream);
+    case 7: return launchChain<7, NX, LEFT, MODE>(a, stream);
+    case 8: return launchChain<8, NX, LEFT, MODE>(a, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+/* right inverse: chains of rotations take the specialised instances (IkArgs::chainFlags) */
+template <int NX>
+static cudaError_t launchChainMode(const IkArgs& a, int nc, cudaStream_t stream)
+{
+  if (a.chainFlags & RCSB_IK_CHAIN_ALLROT)
+  {
+    return (a.chainFlags & RCSB_IK_CHAIN_XYZ_FIRST) ? launchChainNc<NX, false, 1>(a, nc, stream)
+                                                    : launchChainNc<NX, false, 2>(a, nc, stream);
+  }
+  return launchChainNc<NX, false, 0>(a, nc, stream);
 }
 
 template <int MAXNX, int MAXNJ, int MAXDOF, bool LEFT = false>
@@ -3492,7 +3531,7 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
   }
   if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
   {
-    return nx == 3 ? launchChainNc<3>(*a, chainNc, stream) : launchChainNc<6>(*a, chainNc, stream);
+    return nx == 3 ? launchChainMode<3>(*a, chainNc, stream) : launchChainMode<6>(*a, chainNc, stream);
   }
   if (chainNc > 8 && chainNc <= RCSB_IK_LOOP_MAX_NC && (nx == 3 || nx == 6))
   {

@@ -82,6 +82,8 @@ struct KtArgs
   int symmetric;       /* plan header's `symmetric` (shared-memory layout of the assembly kernel) */
 };
 
+#define RCSB_IK_CHAIN_ALLROT 1      /* every Jacobian column of the chain is a rotation */
+#define RCSB_IK_CHAIN_XYZ_FIRST 2   /* the position task is the first task of the plan */
 struct IkArgs
 {
   const char* model;
@@ -95,6 +97,7 @@ struct IkArgs
   double alpha;
   int iters;
   int leftInverse;     /* 1: IkSolverRMR::solveLeftInverse instead of solveRightInverse */
+  int chainFlags;      /* RCSB_IK_CHAIN_*: what the plan builder knows about the single-chain program */
   double* dx;
   double* dq;
   double* det;
