@@ -751,7 +751,7 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   const int* bodyFlags = m->iarr(RCSB_A_BODY_FLAGS);
   const int* jntType = m->iarr(RCSB_A_JNT_TYPE);
   std::vector<int> progStart, prog, chainType, chainJoint, otherJoint;
-  std::vector<double> chainXf;
+  std::vector<double> chainXf, segXf;
   std::vector<double> chainW, chainGain, chainQ0, otherW, otherGain, otherQ0;
   int chainNc = 0;
   {
@@ -942,6 +942,56 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
       chainXf.clear();
       chainType.clear();
       chainJoint.clear();
+    }
+    /* every segment of the program folded into one transform (RcsbIkPlanHeader::offSegXf): applying
+     * A then B is applying {A.org + A.rot^T B.org, B.rot A.rot}; exact whenever one of the two is a
+     * pure translation, a permutation or the identity */
+    if (chainNc > 0 && chainNc <= 8)
+    {
+      bool fold = true;
+      for (int c = 0; c < chainNc; ++c)
+      {
+        fold = fold && (chainType[(size_t) c] & 15) < 3;
+      }
+      for (size_t k = 0; fold && k < prog.size() / 4; ++k)
+      {
+        fold = prog[4 * k] != 1;
+      }
+      for (int c = 0; fold && c <= chainNc; ++c)
+      {
+        double X[12] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = progStart[(size_t) c]; k < progStart[(size_t) c + 1]; ++k)
+        {
+          double B[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          if (prog[4 * (size_t) k] == 0)
+          {
+            memcpy(B, chainXf.data() + 12 * (size_t) prog[4 * (size_t) k + 1], sizeof(B));
+          }
+          else
+          {
+            const int sh = prog[4 * (size_t) k + 1];   /* new row i = old row (i + sh) mod 3 */
+            for (int i = 0; i < 3; ++i)
+            {
+              B[3 + 3 * i + (i + sh) % 3] = 1.0;
+            }
+          }
+          double Y[12];
+          for (int i = 0; i < 3; ++i)
+          {
+            Y[i] = X[i] + (X[3 + i] * B[0] + X[6 + i] * B[1] + X[9 + i] * B[2]);
+            for (int j = 0; j < 3; ++j)
+            {
+              Y[3 + 3 * i + j] = B[3 + 3 * i] * X[3 + j] + B[3 + 3 * i + 1] * X[6 + j] + B[3 + 3 * i + 2] * X[9 + j];
+            }
+          }
+          memcpy(X, Y, sizeof(X));
+        }
+        segXf.insert(segXf.end(), X, X + 12);
+      }
+      if (!fold)
+      {
+        segXf.clear();
+      }
     }
     if (prog.empty())
     {
@@ -1144,6 +1194,11 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   place(ph.offProgStart, progStart.size() * 4);
   place(ph.offProg, prog.size() * 4);
   place(ph.offChainXf, atLeast1(chainXf.size()) * 8);
+  ph.offSegXf = 0;
+  if (!segXf.empty())
+  {
+    place(ph.offSegXf, segXf.size() * 8);
+  }
   place(ph.offChainType, atLeast1(chainType.size()) * 4);
   place(ph.offChainJoint, atLeast1(chainJoint.size()) * 4);
   place(ph.offChainW, atLeast1(chainW.size()) * 8);
@@ -1187,6 +1242,10 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   put(ph.offProgStart, progStart.data(), progStart.size() * 4);
   put(ph.offProg, prog.data(), prog.size() * 4);
   put(ph.offChainXf, chainXf.data(), chainXf.size() * 8);
+  if (!segXf.empty())
+  {
+    put(ph.offSegXf, segXf.data(), segXf.size() * 8);
+  }
   put(ph.offChainType, chainType.data(), chainType.size() * 4);
   put(ph.offChainJoint, chainJoint.data(), chainJoint.size() * 4);
   put(ph.offChainW, chainW.data(), chainW.size() * 8);
@@ -1214,12 +1273,8 @@ int buildIkPlan(RcsbModel* m, int nTasksIn, const RcsbTask* tasksIn, const Devic
   dp.nSel = ph.nEffs;
   dp.nScrRows = nTasks | (walkSlots << 8);
   {
-    bool allRot = chainNc > 0;
-    for (int c = 0; c < chainNc; ++c)
-    {
-      allRot = allRot && (chainType[(size_t) c] & 15) < 3;
-    }
-    dp.aux2 = (allRot ? RCSB_IK_CHAIN_ALLROT : 0) | (kind[0] == RCSB_TASK_XYZ ? RCSB_IK_CHAIN_XYZ_FIRST : 0);
+    /* the specialised chain instances: all columns rotations, no joint steps in the program */
+    dp.aux2 = (!segXf.empty() ? RCSB_IK_CHAIN_ALLROT : 0) | (kind[0] == RCSB_TASK_XYZ ? RCSB_IK_CHAIN_XYZ_FIRST : 0);
   }
   auto ins = m->ikPlans.emplace(key, dp);
   *out = &ins.first->second;

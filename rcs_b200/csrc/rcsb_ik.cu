@@ -62,6 +62,7 @@ struct IkPlanView
   const int4* prog;
   const int* chainType;
   const double* chainXf;
+  const double* segXf;
   const int* chainJoint;
   const double* chainW;
   const double* chainGain;
@@ -85,6 +86,7 @@ struct IkPlanView
     prog = reinterpret_cast<const int4*>(blob + hdr->offProg);
     chainType = reinterpret_cast<const int*>(blob + hdr->offChainType);
     chainXf = reinterpret_cast<const double*>(blob + hdr->offChainXf);
+    segXf = reinterpret_cast<const double*>(blob + hdr->offSegXf);
     chainJoint = reinterpret_cast<const int*>(blob + hdr->offChainJoint);
     chainW = reinterpret_cast<const double*>(blob + hdr->offChainW);
     chainGain = reinterpret_cast<const double*>(blob + hdr->offChainGain);
@@ -2023,11 +2025,13 @@ __device__ __forceinline__ void chainStep(Frame& f, const int4 st, const double*
 /* LEFT: the step of IkSolverRMR::solveLeftInverse (IkSolverRMR.cpp:205-272) instead: with
  * J_r = J invWq, dq = invWq o (g + (J_r^T J_r + lambda 1)^-1 J_r^T (dx - J_r g)), the NC x NC
  * system factored like the NX x NX one of the right inverse. */
-/* MODE 0: column types and the order of the two tasks are read from the plan at run time.
- * MODE 1 / 2: every column is a rotation and the position task comes first / second (what the plan
- * builder reports in IkArgs::chainFlags): no per-column type branches and no row selects — the
- * merges behind those branches were 18 % of the executed instructions as register moves —, and the
- * sines / cosines of all columns are evaluated together before the walk (sincosBatch). */
+/* MODE 0: column types, the order of the two tasks and the chain program are read from the plan at
+ * run time. MODE 1 / 2: every column is a rotation, the program has no joint steps and the position
+ * task comes first / second (what the plan builder reports in IkArgs::chainFlags): no per-column type
+ * branches and no row selects — the merges behind those branches were 18 % of the executed
+ * instructions as register moves —, the sines / cosines of all columns are evaluated together before
+ * the walk (sincosBatch), and the program is not interpreted: every segment is ONE relative transform
+ * folded on the host (RcsbIkPlanHeader::offSegXf), so the walk is straight-line code. */
 template <int NC, int NX, bool LEFT = false, int MODE = 0>
 __global__ void __launch_bounds__(RCSB_IK_THREADS, RCSB_IK_CHAIN_MIN_BLOCKS)
 ikChainKernel(const IkArgs a)
@@ -2126,9 +2130,16 @@ ikChainKernel(const IkArgs a)
 #pragma unroll
     for (int c = 0; c < NC; ++c)
     {
-      for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
+      if constexpr (ALLROT)
       {
-        chainStep<true>(f, p.prog[k], p.chainXf, qRow);
+        applyRel(f, p.segXf + 12 * c);   /* the segment's steps as one transform, no interpretation */
+      }
+      else
+      {
+        for (int k = p.progStart[c]; k < p.progStart[c + 1]; ++k)
+        {
+          chainStep<true>(f, p.prog[k], p.chainXf, qRow);
+        }
       }
       const int ctype = ALLROT ? 0 : p.chainType[c];
       isRot[c] = ALLROT || (ctype & 15) < 3;
@@ -2160,9 +2171,16 @@ ikChainKernel(const IkArgs a)
       jo[c][1] = f.o[1];
       jo[c][2] = f.o[2];
     }
-    for (int k = p.progStart[NC]; k < p.progStart[NC + 1]; ++k)
+    if constexpr (ALLROT)
     {
-      chainStep<true>(f, p.prog[k], p.chainXf, qRow);
+      applyRel(f, p.segXf + 12 * NC);
+    }
+    else
+    {
+      for (int k = p.progStart[NC]; k < p.progStart[NC + 1]; ++k)
+      {
+        chainStep<true>(f, p.prog[k], p.chainXf, qRow);
+      }
     }
 
     /* ---- task error (ControllerBase::computeDX) ---------------------------------------------- */

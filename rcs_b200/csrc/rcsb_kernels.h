@@ -82,7 +82,7 @@ struct KtArgs
   int symmetric;       /* plan header's `symmetric` (shared-memory layout of the assembly kernel) */
 };
 
-#define RCSB_IK_CHAIN_ALLROT 1      /* every Jacobian column of the chain is a rotation */
+#define RCSB_IK_CHAIN_ALLROT 1      /* every Jacobian column of the chain is a rotation and the program has no joint steps (offSegXf) */
 #define RCSB_IK_CHAIN_XYZ_FIRST 2   /* the position task is the first task of the plan */
 struct IkArgs
 {

@@ -273,7 +273,11 @@ typedef struct
   int nWalk;
   int walkSlots;        /* frame-stack slots the pruned walk needs */
   int offWalk;          /* int4[nWalk]: {body, load (RCSB_LOAD_* or slot), save slot or -1, 0} */
-  int pad;
+  int offSegXf;         /* double[chainNc + 1][12], 0 = none: the steps of every program segment folded
+                           into ONE relative transform (row shifts included as exact permutations,
+                           empty segments as the identity). Present when the program has no joint steps
+                           (op 1) and every column is a rotation: the specialised ikChainKernel instances
+                           walk the chain without interpreting the program. */
 } RcsbIkPlanHeader;
 
 /*
