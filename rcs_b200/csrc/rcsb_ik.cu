@@ -3369,16 +3369,16 @@ static cudaError_t launchChainNc(const IkArgs& a, int nc, cudaStream_t stream)
   }
 }
 
-/* right inverse: chains of rotations take the specialised instances (IkArgs::chainFlags) */
-template <int NX>
+/* chains of rotations without joint steps take the specialised instances (IkArgs::chainFlags) */
+template <int NX, bool LEFT = false>
 static cudaError_t launchChainMode(const IkArgs& a, int nc, cudaStream_t stream)
 {
   if (a.chainFlags & RCSB_IK_CHAIN_ALLROT)
   {
-    return (a.chainFlags & RCSB_IK_CHAIN_XYZ_FIRST) ? launchChainNc<NX, false, 1>(a, nc, stream)
-                                                    : launchChainNc<NX, false, 2>(a, nc, stream);
+    return (a.chainFlags & RCSB_IK_CHAIN_XYZ_FIRST) ? launchChainNc<NX, LEFT, 1>(a, nc, stream)
+                                                    : launchChainNc<NX, LEFT, 2>(a, nc, stream);
   }
-  return launchChainNc<NX, false, 0>(a, nc, stream);
+  return launchChainNc<NX, LEFT, 0>(a, nc, stream);
 }
 
 template <int MAXNX, int MAXNJ, int MAXDOF, bool LEFT = false>
@@ -3535,7 +3535,7 @@ extern "C" cudaError_t rcsb_launch_ik(const rcsb::IkArgs* a, int nSlots, int nx,
     /* solveLeftInverse: the register kernel for short single chains, else the general kernel */
     if (chainNc >= 1 && chainNc <= 8 && (nx == 3 || nx == 6))
     {
-      return nx == 3 ? launchChainNc<3, true>(*a, chainNc, stream) : launchChainNc<6, true>(*a, chainNc, stream);
+      return nx == 3 ? launchChainMode<3, true>(*a, chainNc, stream) : launchChainMode<6, true>(*a, chainNc, stream);
     }
     if (nx <= 6 && nJ <= 8 && dof <= 8)
     {
