@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GRAPH_DIR = os.path.join(ROOT, "tests", "golden", "graphs")
-GRAPHS = ["wam_arm", "wam_scenario", "humanoid", "dexbot", "husky", "schunk_sdh", "gantry", "polycoupled"]
+GRAPHS = ["wam_arm", "wam_scenario", "humanoid", "dexbot", "husky", "schunk_sdh", "gantry", "polycoupled", "wrist6"]
 REFERENCE_XML = "/root/reference/config/xml"
 
 

@@ -220,6 +220,44 @@ def test_chain_and_general_kernels_agree_over_ten_iterations(refmod, cuda_device
     assert_step_close(qa[ok] - q0[ok], qb[ok] - q0[ok], 10.0 * cond[ok], "q: chain vs general")
 
 
+@pytest.mark.parametrize("left", [False, True], ids=["right-inverse", "left-inverse"])
+@pytest.mark.parametrize("kinds", [("XYZ", "ABC"), ("ABC", "XYZ"), ("XYZ",), ("ABC",)])
+def test_chain_with_several_joint_axes_per_body(kinds, left, refmod, cuda_device):
+    """tests/golden/graphs/wrist6.xml: joints about different axes inside one body, separated by
+    translation-only transforms. The specialised chain instances walk such a chain through one
+    folded transform per stretch between two columns, the row shifts folded in as permutations
+    (RcsbIkPlanHeader::offSegXf); the general kernel evaluates the reference's algebra literally."""
+    g, m, rik, tasks = _setup("wrist6", "Tip", refmod, cuda_device, kinds)
+    q0, x_des = _targets(g, rik, 1500, seed_first=5, perturb=0.1)
+    lam = 1.0e-3 if left else 1.0e-8
+    if left:
+        q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1, lam=lam, left=True)
+    else:
+        q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q0, x_des, iters=1)
+    q = q0.copy()
+    out = m.ik_rmr(tasks, q, x_des, lam=lam, iters=1, left_inverse=left, want=("dx", "dq", "det"))
+    assert_close(out["dx"], dx_ref, what="dx")
+    cond = _left_condition(rik, q0, lam) if left else step_condition(rik, q0)
+    assert np.all(det_ref > 0.0)
+    assert_step_close(out["dq"], dq_ref, cond, "dq")
+    assert_step_close(q - q0, q_ref - q0, cond, "q")
+    rel = np.abs(out["det"] / det_ref - 1.0)
+    assert np.all(rel <= 1e-11 * np.maximum(1.0, cond / 100.0)), "det (relative, conditioned)"
+    # four iterations against the reference, on the states whose whole trajectory stays clear of
+    # singular configurations (the ball wrist has plenty)
+    q_run = q0.copy()
+    cond_max = np.zeros(len(q0))
+    for _ in range(4):
+        c = _left_condition(rik, q_run, lam) if left else step_condition(rik, q_run)
+        cond_max = np.maximum(cond_max, c)
+        q_run, _, _, _ = rik.rmr(q_run, x_des, lam=lam, iters=1, left=left)
+    q4 = q0.copy()
+    m.ik_rmr(tasks, q4, x_des, lam=lam, iters=4, left_inverse=left)
+    ok = cond_max < 1.0e6
+    assert ok.mean() > 0.3, float(np.median(cond_max))
+    assert_step_close(q4[ok] - q0[ok], q_run[ok] - q0[ok], 4.0 * cond_max[ok], "q after 4 iterations")
+
+
 @pytest.mark.parametrize("eff,kinds", [("Helmet", ("XYZ", "ABC")), ("FootL", ("ABC", "XYZ")),
                                        ("HeadPan", ("XYZ",))])
 def test_short_chains_on_the_humanoid(eff, kinds, refmod, cuda_device):

@@ -32,7 +32,7 @@ GRAPHS = {
 }
 # fixtures written by hand for this repository (not re-serialised): only their layout is recorded,
 # by the reference loader
-LOCAL = ["gantry", "polycoupled"]
+LOCAL = ["gantry", "polycoupled", "wrist6"]
 # layout keys that legitimately differ after export (shapes are dropped)
 IGNORE = {"nShapes"}
 
