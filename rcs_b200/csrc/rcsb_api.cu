@@ -625,6 +625,165 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   {
     visit.assign(4, 0);
   }
+
+  /* ---- serial chain of rotations: tables of the straight-line walk (RcsbFkPlanHeader::chainNc) ---- */
+  std::vector<double> chainG, chainX, chainMass;
+  std::vector<int> chainOutStart, chainOut, chainJoint;
+  if (!compact && nJ >= 1 && nJ <= 8 && dof == nJ && m->hdr.nCpl == 0 && (inPlace || nEff == 0))
+  {
+    const int* parent = m->iarr(RCSB_A_BODY_PARENT);
+    const int* jStart = m->iarr(RCSB_A_BODY_JNT_START);
+    const int* jCount = m->iarr(RCSB_A_BODY_JNT_COUNT);
+    const int* bodyFlags = m->iarr(RCSB_A_BODY_FLAGS);
+    const int* jntType = m->iarr(RCSB_A_JNT_TYPE);
+    const double* ajp = m->darr(RCSB_A_JNT_AJP);
+    const double* abp = m->darr(RCSB_A_BODY_ABP);
+    const double* mass = m->darr(RCSB_A_BODY_MASS);
+    const double* com = m->darr(RCSB_A_BODY_COM);
+    const double* inertia = m->darr(RCSB_A_BODY_INERTIA);
+    struct Xf
+    {
+      double v[12];
+    };
+    const Xf ident = {{0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    /* applying A, then B: {A.org + A.rot^T B.org, B.rot A.rot} */
+    auto compose = [](const Xf& A, const double* B) {
+      Xf Y;
+      for (int i = 0; i < 3; ++i)
+      {
+        Y.v[i] = A.v[i] + (A.v[3 + i] * B[0] + A.v[6 + i] * B[1] + A.v[9 + i] * B[2]);
+        for (int k = 0; k < 3; ++k)
+        {
+          Y.v[3 + 3 * i + k] = B[3 + 3 * i] * A.v[3 + k] + B[3 + 3 * i + 1] * A.v[6 + k] + B[3 + 3 * i + 2] * A.v[9 + k];
+        }
+      }
+      return Y;
+    };
+    /* rows / columns permuted for bases kept with shifted rows: in = shift of the base the transform
+     * starts from, out = shift of the frame it leads to */
+    auto permute = [](const Xf& A, int in, int out) {
+      Xf Y;
+      for (int i = 0; i < 3; ++i)
+      {
+        Y.v[i] = A.v[(i + in) % 3];
+        for (int k = 0; k < 3; ++k)
+        {
+          Y.v[3 + 3 * i + k] = A.v[3 + 3 * ((i + out) % 3) + (k + in) % 3];
+        }
+      }
+      return Y;
+    };
+    std::vector<int> lvl((size_t) nb, 0), shiftOf((size_t) nJ + 1, 0);   /* shiftOf[L]: shift of the base of level L */
+    std::vector<Xf> X((size_t) nb, ident), G((size_t) nJ, ident);
+    bool ok = true;
+    chainJoint.assign((size_t) nJ, -1);
+    for (int b = 0; b < nb && ok; ++b)
+    {
+      int L = parent[b] >= 0 ? lvl[(size_t) parent[b]] : 0;
+      Xf T = parent[b] >= 0 ? X[(size_t) parent[b]] : ident;
+      for (int j = jStart[b]; j < jStart[b] + jCount[b] && ok; ++j)
+      {
+        if (jntFlags[j] & RCSB_JF_HAS_AJP)
+        {
+          T = compose(T, ajp + 12 * j);
+        }
+        ok = (jntFlags[j] & RCSB_JF_ROT) && jntJacobi[j] == L && L < nJ;
+        if (ok)
+        {
+          G[(size_t) L] = T;
+          chainJoint[(size_t) L] = j;
+          shiftOf[(size_t) L + 1] = (jntType[j] % 3 + 1) % 3;   /* axis -> row 2 */
+          ++L;
+          T = ident;
+        }
+      }
+      if (bodyFlags[b] & RCSB_BF_HAS_ABP)
+      {
+        T = compose(T, abp + 12 * b);
+      }
+      lvl[(size_t) b] = L;
+      X[(size_t) b] = T;
+    }
+    for (int c = 0; c < nJ; ++c)
+    {
+      ok = ok && chainJoint[(size_t) c] >= 0;
+    }
+    if (ok)
+    {
+      for (int c = 0; c < nJ; ++c)
+      {
+        const Xf Gp = permute(G[(size_t) c], shiftOf[(size_t) c], shiftOf[(size_t) c + 1]);
+        chainG.insert(chainG.end(), Gp.v, Gp.v + 12);
+      }
+      chainMass.assign((size_t) (nJ + 1) * 10, 0.0);
+      chainOutStart.assign(1, 0);
+      for (int L = 0; L <= nJ; ++L)
+      {
+        const int sh = shiftOf[(size_t) L];
+        double* cm = chainMass.data() + 10 * (size_t) L;
+        for (int b = 0; b < nb; ++b)
+        {
+          if (lvl[(size_t) b] != L)
+          {
+            continue;
+          }
+          const Xf Xp = permute(X[(size_t) b], sh, 0);
+          bool rotIdent = true, noTrans = true;
+          for (int i = 0; i < 3; ++i)
+          {
+            noTrans = noTrans && Xp.v[i] == 0.0;
+            for (int k = 0; k < 3; ++k)
+            {
+              rotIdent = rotIdent && Xp.v[3 + 3 * i + k] == (i == k ? 1.0 : 0.0);
+            }
+          }
+          const bool needed = bodyOut[(size_t) b] >= 0 || effStart[(size_t) b + 1] > effStart[(size_t) b];
+          const int ent[4] = {b, bodyOut[(size_t) b],
+                              (rotIdent ? RCSB_REL_ROT_IDENT : 0) | (noTrans ? RCSB_REL_NO_TRANS : 0) | (needed ? 1 : 0), 0};
+          chainOut.insert(chainOut.end(), ent, ent + 4);
+          chainX.insert(chainX.end(), Xp.v, Xp.v + 12);
+          if (mass[b] > 0.0 && L > 0)
+          {
+            /* COM and inertia in the (shifted) coordinates of the level's base, about its origin */
+            const double* Xr = Xp.v + 3;
+            double c[3], Ic[9], t[9];
+            for (int i = 0; i < 3; ++i)
+            {
+              c[i] = Xp.v[i] + (Xr[i] * com[3 * b] + Xr[3 + i] * com[3 * b + 1] + Xr[6 + i] * com[3 * b + 2]);
+            }
+            for (int i = 0; i < 3; ++i)
+            {
+              for (int k = 0; k < 3; ++k)
+              {
+                t[3 * i + k] = inertia[9 * b + 3 * i] * Xr[k] + inertia[9 * b + 3 * i + 1] * Xr[3 + k] +
+                               inertia[9 * b + 3 * i + 2] * Xr[6 + k];
+              }
+            }
+            for (int i = 0; i < 3; ++i)
+            {
+              for (int k = 0; k < 3; ++k)
+              {
+                Ic[3 * i + k] = Xr[i] * t[k] + Xr[3 + i] * t[3 + k] + Xr[6 + i] * t[6 + k];
+              }
+            }
+            const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+            cm[0] += mass[b];
+            cm[1] += mass[b] * c[0];
+            cm[2] += mass[b] * c[1];
+            cm[3] += mass[b] * c[2];
+            cm[4] += Ic[0] + mass[b] * (cc - c[0] * c[0]);
+            cm[5] += Ic[1] - mass[b] * c[0] * c[1];
+            cm[6] += Ic[2] - mass[b] * c[0] * c[2];
+            cm[7] += Ic[4] + mass[b] * (cc - c[1] * c[1]);
+            cm[8] += Ic[5] - mass[b] * c[1] * c[2];
+            cm[9] += Ic[8] + mass[b] * (cc - c[2] * c[2]);
+          }
+        }
+        chainOutStart.push_back((int) chainOut.size() / 4);
+      }
+      ph.chainNc = nJ;
+    }
+  }
   ph.jacRecord = rec;
   ph.inPlace = inPlace ? 1 : 0;
   {
@@ -669,6 +828,21 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   off = align16(off + (int) visit.size() * 4);
   ph.offJntNext = off;
   off = align16(off + (int) jntNext.size() * 4);
+  if (ph.chainNc > 0)
+  {
+    ph.offChainG = off;
+    off = align16(off + (int) chainG.size() * 8);
+    ph.offChainX = off;
+    off = align16(off + (int) chainX.size() * 8);
+    ph.offChainOutStart = off;
+    off = align16(off + (int) chainOutStart.size() * 4);
+    ph.offChainOut = off;
+    off = align16(off + (int) chainOut.size() * 4);
+    ph.offChainMass = off;
+    off = align16(off + (int) chainMass.size() * 8);
+    ph.offChainJoint = off;
+    off = align16(off + (int) chainJoint.size() * 4);
+  }
   ph.totalBytes = off;
 
   std::vector<char> blob(ph.totalBytes, 0);
@@ -689,6 +863,15 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   memcpy(blob.data() + ph.offMassList, massList.data(), massList.size() * 4);
   memcpy(blob.data() + ph.offVisit, visit.data(), visit.size() * 4);
   memcpy(blob.data() + ph.offJntNext, jntNext.data(), jntNext.size() * 4);
+  if (ph.chainNc > 0)
+  {
+    memcpy(blob.data() + ph.offChainG, chainG.data(), chainG.size() * 8);
+    memcpy(blob.data() + ph.offChainX, chainX.data(), chainX.size() * 8);
+    memcpy(blob.data() + ph.offChainOutStart, chainOutStart.data(), chainOutStart.size() * 4);
+    memcpy(blob.data() + ph.offChainOut, chainOut.data(), chainOut.size() * 4);
+    memcpy(blob.data() + ph.offChainMass, chainMass.data(), chainMass.size() * 8);
+    memcpy(blob.data() + ph.offChainJoint, chainJoint.data(), chainJoint.size() * 4);
+  }
 
   DevicePlan dp;
   RCSB_CUDA(cudaSetDevice(m->device));
@@ -703,6 +886,7 @@ int buildFkPlan(RcsbModel* m, int nSel, const int* bodySel, int nEff, const int*
   dp.nEff = nEff;
   dp.aux0 = compact ? recCols : ph.massChain;   /* compact plans never carry the mass tables */
   dp.aux1 = ph.nVisit > 0 ? ph.prunedSlots + 1 : 0;   /* 0: no pruned walk */
+  dp.aux2 = ph.chainNc;                                /* > 0: the straight-line chain walk applies */
 
   auto ins = m->fkPlans.emplace(key, dp);
   *out = &ins.first->second;
@@ -749,6 +933,12 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   /* per-joint outputs and velocities need every body: the pruned walk serves frames and
    * Jacobians of a body selection only */
   a.pruned = (plan->aux1 > 0 && !A_JI && !qOut && !qd && !qdOut && !M) ? 1 : 0;
+  /* serial chains of rotations: the straight-line kernel serves frames, Jacobians and M */
+  {
+    const char* noChain = getenv("RCSB_FK_GENERAL");   /* force the interpreting kernel (tests) */
+    a.chainNc = (plan->aux2 > 0 && !(noChain && noChain[0] == '1') && !qd && !A_JI && !qOut && !qdOut &&
+                 qdim == m->hdr.dof) ? plan->aux2 : 0;
+  }
   a.scrDoubles = plan->nScrRows * (RCSB_FK_BLOCK(M != nullptr) + 1);
   RCSB_CUDA(cudaSetDevice(m->device));
   if (rcsbhost::fkSharedBytes(m, plan->bytes, plan->nScrRows, M != nullptr, qd != nullptr) > RCSB_SMEM_LIMIT)

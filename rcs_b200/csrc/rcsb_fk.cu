@@ -43,6 +43,12 @@ struct PlanView
   const int4* massList;
   const int4* visit;
   const int* jntNext;
+  const double* chainG;
+  const double* chainX;
+  const int* chainOutStart;
+  const int4* chainOut;
+  const double* chainMass;
+  const int* chainJoint;
 
   __device__ __forceinline__ void bind(const char* blob)
   {
@@ -60,8 +66,211 @@ struct PlanView
     massList = reinterpret_cast<const int4*>(blob + hdr->offMassList);
     visit = reinterpret_cast<const int4*>(blob + hdr->offVisit);
     jntNext = reinterpret_cast<const int*>(blob + hdr->offJntNext);
+    chainG = reinterpret_cast<const double*>(blob + hdr->offChainG);
+    chainX = reinterpret_cast<const double*>(blob + hdr->offChainX);
+    chainOutStart = reinterpret_cast<const int*>(blob + hdr->offChainOutStart);
+    chainOut = reinterpret_cast<const int4*>(blob + hdr->offChainOut);
+    chainMass = reinterpret_cast<const double*>(blob + hdr->offChainMass);
+    chainJoint = reinterpret_cast<const int*>(blob + hdr->offChainJoint);
   }
 };
+
+/* Jacobian records and mass matrices of a warp's 32 states leave through the shared-memory scratch
+ * (shared by fkKernel and fkChainKernel). On entry the scratch holds, per chain joint, axis and
+ * origin (MASS != 2) or the spatial axis (w, v) (MASS == 2), and the effector points. */
+template <int MASS>
+__device__ __forceinline__ void fkTail(const FkArgs& a, const PlanView& p, double* scr, const int scrStride,
+                                       const int nChain, const int tid, const long s,
+                                       const double (&Mv)[MASS ? 36 : 1])
+{
+  /* ---- Jacobians --------------------------------------------------------------------------- */
+  const int rec = p.hdr->jacRecord;
+  if (rec > 0 && (a.JT || a.JR))
+  {
+    const int rs = nChain * scrStride;
+    const bool inPlace = p.hdr->inPlace != 0;
+
+    if (inPlace)
+    {
+      /* own column: joint origin -> axis x (I_p - origin), or the axis for a translation */
+      for (int e = 0; e < p.hdr->nEff; ++e)
+      {
+        const double* pe = scr + (6 * nChain + 3 * e) * scrStride + tid;
+        const double px = pe[0], py = pe[scrStride], pz = pe[2 * scrStride];
+        for (int k = p.effChainStart[e]; k < p.effChainStart[e + 1]; ++k)
+        {
+          const int ent = p.effChain[k];
+          double* col = scr + (ent & 0xffff) * scrStride + tid;
+          const double a0 = col[0], a1 = col[rs], a2 = col[2 * rs];
+          if (MASS == 2)
+          {
+            /* (w, v) storage: column = w x I_p + v for both joint types */
+            col[3 * rs] += a1 * pz - a2 * py;
+            col[4 * rs] += a2 * px - a0 * pz;
+            col[5 * rs] += a0 * py - a1 * px;
+          }
+          else if (ent >> 16)
+          {
+            const double d0 = px - col[3 * rs], d1 = py - col[4 * rs], d2 = pz - col[5 * rs];
+            col[3 * rs] = a1 * d2 - a2 * d1;
+            col[4 * rs] = a2 * d0 - a0 * d2;
+            col[5 * rs] = a0 * d1 - a1 * d0;
+          }
+          else
+          {
+            col[3 * rs] = a0;
+            col[4 * rs] = a1;
+            col[5 * rs] = a2;
+          }
+        }
+      }
+    }
+
+    __syncwarp();
+    const int lane = tid & 31;
+    const long w0 = s - lane;                      /* first state of this warp */
+    long nv = a.N - w0;
+    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+    const int total = (int) nv * rec;
+    const float invRec = p.hdr->invJacRecord;
+    const double* scrWarp = scr + (tid - lane);
+    double* JTw = a.JT ? a.JT + w0 * rec : nullptr;
+    double* JRw = a.JR ? a.JR + w0 * rec : nullptr;
+
+    if (inPlace)
+    {
+      /* one record row per warp instruction: lane r owns element r of the record, so its
+       * scratch row is fixed (structural zeros read the zero row) and the loop over the
+       * warp's states is a shared-memory read and a global store with constant strides, no
+       * index arithmetic; the 32 records of the warp are contiguous in global memory */
+      const double* zero = scrWarp + p.hdr->zeroRow * scrStride;
+      for (int r0 = 0; r0 < rec; r0 += 32)
+      {
+        const int rem = r0 + lane;
+        if (rem < rec)
+        {
+          const int tT = p.jtab[rem], tR = p.jtabR[rem];
+          const double* srcT = tT >= 0 ? scrWarp + tT * scrStride : zero;
+          const double* srcR = tR >= 0 ? scrWarp + tR * scrStride : zero;
+          if (JTw && JRw)
+          {
+            double* dT = JTw + rem;
+            double* dR = JRw + rem;
+#pragma unroll 4
+            for (int sl = 0; sl < (int) nv; ++sl)
+            {
+              dT[(long) sl * rec] = srcT[sl];
+              dR[(long) sl * rec] = srcR[sl];
+            }
+          }
+          else
+          {
+            double* d = JTw ? JTw + rem : JRw + rem;
+            const double* src = JTw ? srcT : srcR;
+#pragma unroll 4
+            for (int sl = 0; sl < (int) nv; ++sl)
+            {
+              d[(long) sl * rec] = src[sl];
+            }
+          }
+        }
+      }
+    }
+    else
+    {
+      for (int e = lane; e < total; e += 32)
+      {
+        const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
+        const int rem = e - sl * rec;
+        const int t = p.jtab[rem];
+        double vT = 0.0, vR = 0.0;
+        if (t >= 0)
+        {
+          const int r = RCSB_JTAB_ROW(t);
+          const double* ja = scrWarp + RCSB_JTAB_SLOT(t) * scrStride + sl;
+          if (MASS == 2)
+          {
+            const int r1 = r == 2 ? 0 : r + 1;
+            const int r2 = r == 0 ? 2 : r - 1;
+            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
+            vT = ja[(3 + r) * rs] + (ja[r1 * rs] * pe[r2 * scrStride] - ja[r2 * rs] * pe[r1 * scrStride]);
+            vR = ja[r * rs];
+          }
+          else if (RCSB_JTAB_ISROT(t))
+          {
+            /* column = axis x (I_p - joint origin), component r */
+            const int r1 = r == 2 ? 0 : r + 1;
+            const int r2 = r == 0 ? 2 : r - 1;
+            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
+            const double a1 = ja[r1 * rs], a2 = ja[r2 * rs];
+            const double d1 = pe[r1 * scrStride] - ja[(3 + r1) * rs];
+            const double d2 = pe[r2 * scrStride] - ja[(3 + r2) * rs];
+            vT = a1 * d2 - a2 * d1;
+            vR = ja[r * rs];
+          }
+          else
+          {
+            vT = ja[r * rs];
+          }
+        }
+        if (JTw)
+        {
+          JTw[e] = vT;
+        }
+        if (JRw)
+        {
+          JRw[e] = vR;
+        }
+      }
+    }
+  }
+
+  if (MASS && a.M)
+  {
+    /* stage the matrices over the scratch rows the Jacobians have left, then copy out: the
+     * warp's 32 matrices are contiguous in global memory */
+    __syncwarp();
+    {
+      const int nJ = p.hdr->nJ;
+      double* st = scr + p.hdr->mStageRow * scrStride + tid;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+#pragma unroll
+        for (int i = 0; i <= k; ++i)
+        {
+          if (k < nJ)
+          {
+            st[(i * nJ + k) * scrStride] = Mv[k * (k + 1) / 2 + i];
+            st[(k * nJ + i) * scrStride] = Mv[k * (k + 1) / 2 + i];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int lane = tid & 31;
+    const long w0 = s - lane;
+    long nv = a.N - w0;
+    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+    const int nJ2 = p.hdr->nJ * p.hdr->nJ;
+    const double* stw = scr + p.hdr->mStageRow * scrStride + (tid - lane);
+    double* Mw = a.M + w0 * nJ2;
+    for (int r0 = 0; r0 < nJ2; r0 += 32)
+    {
+      const int rem = r0 + lane;
+      if (rem < nJ2)
+      {
+        const double* src = stw + rem * scrStride;
+        double* d = Mw + rem;
+#pragma unroll 4
+        for (int sl = 0; sl < (int) nv; ++sl)
+        {
+          d[(long) sl * nJ2] = src[sl];
+        }
+      }
+    }
+  }
+}
 
 /* MASS: additionally the joint-space mass matrix (RcsGraph_computeMassMatrix, Rcs_dynamics.c:
  * 610) for models with at most 8 Jacobian columns.
@@ -738,193 +947,211 @@ fkKernel(const FkArgs a)
     }
   }
 
-  /* ---- Jacobians --------------------------------------------------------------------------- */
-  const int rec = p.hdr->jacRecord;
-  if (rec > 0 && (a.JT || a.JR))
+  fkTail<MASS>(a, p, scr, scrStride, nChain, tid, s, Mv);
+}
+
+
+/*
+ * Serial chains of rotations (RcsbFkPlanHeader::chainNc): the same results as fkKernel<MASS = 0 / 2>
+ * from straight-line code. NC columns at compile time; per column ONE relative transform folded on
+ * the host (G_c) and one rotation about row 2 of the row-shifted base; the frames of the bodies of
+ * a level are side outputs X_b o base (they do not touch the running frame, so nothing merges); the
+ * sines / cosines of all columns come from one interleaved batch (sincosBatch). The flat model is
+ * not needed on the device at all - the plan carries every constant - and is not staged.
+ * MASS = 2: the matrix is built tip to root like in fkKernel, but without reading any frame back: the
+ * running base is taken back through the columns by the inverse transforms (R = G^T R', o = o' -
+ * R^T g, rotation by -q), and the massive bodies of a level enter as ONE composite whose mass, first
+ * moment and inertia in base coordinates are constants of the plan (offChainMass).
+ */
+template <bool ALIGNED32, int MASS, int NC>
+__global__ void __launch_bounds__(RCSB_FK_BLOCK(MASS), MASS ? RCSB_FKM_CHAIN_BLOCKS : 4)
+fkChainKernel(const FkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sPlan = smem;
+  double* scr = reinterpret_cast<double*>(sPlan + a.planBytes);
+  stageBlobsTma(sPlan, a.plan, a.planBytes, nullptr, nullptr, 0);
+  PlanView p;
+  p.bind(sPlan);
+
+  constexpr int THREADS = RCSB_FK_BLOCK(MASS);
+  const int tid = threadIdx.x;
+  const int scrStride = THREADS + 1;
+  if (p.hdr->jacRecord > 0)
   {
-    const int rs = nChain * scrStride;
-    const bool inPlace = p.hdr->inPlace != 0;
+    scr[p.hdr->zeroRow * scrStride + tid] = 0.0;
+  }
+  const long s = (long) blockIdx.x * THREADS + tid;
+  const bool active = s < a.N;
+  const long sc = active ? s : a.N - 1;
+  const int nSel = p.hdr->nSel;
+  const int nChain = p.hdr->nChain;
+  const int rs = nChain * scrStride;
 
-    if (inPlace)
+  double qv[NC], sn[NC], cs[NC];
+  {
+    const double* qRow = a.q + sc * a.qdim;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
     {
-      /* own column: joint origin -> axis x (I_p - origin), or the axis for a translation */
-      for (int e = 0; e < p.hdr->nEff; ++e)
-      {
-        const double* pe = scr + (6 * nChain + 3 * e) * scrStride + tid;
-        const double px = pe[0], py = pe[scrStride], pz = pe[2 * scrStride];
-        for (int k = p.effChainStart[e]; k < p.effChainStart[e + 1]; ++k)
-        {
-          const int ent = p.effChain[k];
-          double* col = scr + (ent & 0xffff) * scrStride + tid;
-          const double a0 = col[0], a1 = col[rs], a2 = col[2 * rs];
-          if (MASS == 2)
-          {
-            /* (w, v) storage: column = w x I_p + v for both joint types */
-            col[3 * rs] += a1 * pz - a2 * py;
-            col[4 * rs] += a2 * px - a0 * pz;
-            col[5 * rs] += a0 * py - a1 * px;
-          }
-          else if (ent >> 16)
-          {
-            const double d0 = px - col[3 * rs], d1 = py - col[4 * rs], d2 = pz - col[5 * rs];
-            col[3 * rs] = a1 * d2 - a2 * d1;
-            col[4 * rs] = a2 * d0 - a0 * d2;
-            col[5 * rs] = a0 * d1 - a1 * d0;
-          }
-          else
-          {
-            col[3 * rs] = a0;
-            col[4 * rs] = a1;
-            col[5 * rs] = a2;
-          }
-        }
-      }
+      qv[c] = qRow[p.chainJoint[c]];
     }
-
-    __syncwarp();
-    const int lane = tid & 31;
-    const long w0 = s - lane;                      /* first state of this warp */
-    long nv = a.N - w0;
-    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
-    const int total = (int) nv * rec;
-    const float invRec = p.hdr->invJacRecord;
-    const double* scrWarp = scr + (tid - lane);
-    double* JTw = a.JT ? a.JT + w0 * rec : nullptr;
-    double* JRw = a.JR ? a.JR + w0 * rec : nullptr;
-
-    if (inPlace)
+  }
+  if (!sincosBatch<NC>(qv, sn, cs))
+  {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
     {
-      /* one record row per warp instruction: lane r owns element r of the record, so its
-       * scratch row is fixed (structural zeros read the zero row) and the loop over the
-       * warp's states is a shared-memory read and a global store with constant strides, no
-       * index arithmetic; the 32 records of the warp are contiguous in global memory */
-      const double* zero = scrWarp + p.hdr->zeroRow * scrStride;
-      for (int r0 = 0; r0 < rec; r0 += 32)
-      {
-        const int rem = r0 + lane;
-        if (rem < rec)
-        {
-          const int tT = p.jtab[rem], tR = p.jtabR[rem];
-          const double* srcT = tT >= 0 ? scrWarp + tT * scrStride : zero;
-          const double* srcR = tR >= 0 ? scrWarp + tR * scrStride : zero;
-          if (JTw && JRw)
-          {
-            double* dT = JTw + rem;
-            double* dR = JRw + rem;
-#pragma unroll 4
-            for (int sl = 0; sl < (int) nv; ++sl)
-            {
-              dT[(long) sl * rec] = srcT[sl];
-              dR[(long) sl * rec] = srcR[sl];
-            }
-          }
-          else
-          {
-            double* d = JTw ? JTw + rem : JRw + rem;
-            const double* src = JTw ? srcT : srcR;
-#pragma unroll 4
-            for (int sl = 0; sl < (int) nv; ++sl)
-            {
-              d[(long) sl * rec] = src[sl];
-            }
-          }
-        }
-      }
-    }
-    else
-    {
-      for (int e = lane; e < total; e += 32)
-      {
-        const int sl = __float2int_rd(((float) e + 0.5f) * invRec);
-        const int rem = e - sl * rec;
-        const int t = p.jtab[rem];
-        double vT = 0.0, vR = 0.0;
-        if (t >= 0)
-        {
-          const int r = RCSB_JTAB_ROW(t);
-          const double* ja = scrWarp + RCSB_JTAB_SLOT(t) * scrStride + sl;
-          if (MASS == 2)
-          {
-            const int r1 = r == 2 ? 0 : r + 1;
-            const int r2 = r == 0 ? 2 : r - 1;
-            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
-            vT = ja[(3 + r) * rs] + (ja[r1 * rs] * pe[r2 * scrStride] - ja[r2 * rs] * pe[r1 * scrStride]);
-            vR = ja[r * rs];
-          }
-          else if (RCSB_JTAB_ISROT(t))
-          {
-            /* column = axis x (I_p - joint origin), component r */
-            const int r1 = r == 2 ? 0 : r + 1;
-            const int r2 = r == 0 ? 2 : r - 1;
-            const double* pe = scrWarp + (6 * nChain + 3 * RCSB_JTAB_EFF(t)) * scrStride + sl;
-            const double a1 = ja[r1 * rs], a2 = ja[r2 * rs];
-            const double d1 = pe[r1 * scrStride] - ja[(3 + r1) * rs];
-            const double d2 = pe[r2 * scrStride] - ja[(3 + r2) * rs];
-            vT = a1 * d2 - a2 * d1;
-            vR = ja[r * rs];
-          }
-          else
-          {
-            vT = ja[r * rs];
-          }
-        }
-        if (JTw)
-        {
-          JTw[e] = vT;
-        }
-        if (JRw)
-        {
-          JRw[e] = vR;
-        }
-      }
+      sincos(qv[c], &sn[c], &cs[c]);
     }
   }
 
-  if (MASS && a.M)
-  {
-    /* stage the matrices over the scratch rows the Jacobians have left, then copy out: the
-     * warp's 32 matrices are contiguous in global memory */
-    __syncwarp();
+  Frame f;
+  setIdentity(f);
+  /* frames of the bodies of level L (and the points of the effectors attached to them) */
+  auto outputs = [&](const int L) {
+    for (int k = p.chainOutStart[L]; k < p.chainOutStart[L + 1]; ++k)
     {
-      const int nJ = p.hdr->nJ;
-      double* st = scr + p.hdr->mStageRow * scrStride + tid;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
+      const int4 e = p.chainOut[k];
+      if (!(e.z & 1))
       {
-#pragma unroll
-        for (int i = 0; i <= k; ++i)
-        {
-          if (k < nJ)
-          {
-            st[(i * nJ + k) * scrStride] = Mv[k * (k + 1) / 2 + i];
-            st[(k * nJ + i) * scrStride] = Mv[k * (k + 1) / 2 + i];
-          }
-        }
+        continue;
+      }
+      Frame t = f;
+      applyRelF(t, p.chainX + 12 * k, e.z);
+      if (e.y >= 0 && active && a.A_BI)
+      {
+        storeFrame<ALIGNED32>(a.A_BI + (s * nSel + e.y) * 12, t);
+      }
+      for (int i = p.bodyEffStart[e.x]; i < p.bodyEffStart[e.x + 1]; ++i)
+      {
+        const int ef = p.bodyEffList[i];
+        const double* pt = a.effPtInline ? a.effPtArg + 3 * ef : p.effPt + 3 * ef;
+        double* col = scr + (6 * nChain + 3 * ef) * scrStride + tid;
+        col[0] = t.o[0] + (t.R[0] * pt[0] + t.R[3] * pt[1] + t.R[6] * pt[2]);
+        col[scrStride] = t.o[1] + (t.R[1] * pt[0] + t.R[4] * pt[1] + t.R[7] * pt[2]);
+        col[2 * scrStride] = t.o[2] + (t.R[2] * pt[0] + t.R[5] * pt[1] + t.R[8] * pt[2]);
       }
     }
-    __syncwarp();
-    const int lane = tid & 31;
-    const long w0 = s - lane;
-    long nv = a.N - w0;
-    nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
-    const int nJ2 = p.hdr->nJ * p.hdr->nJ;
-    const double* stw = scr + p.hdr->mStageRow * scrStride + (tid - lane);
-    double* Mw = a.M + w0 * nJ2;
-    for (int r0 = 0; r0 < nJ2; r0 += 32)
+  };
+
+  outputs(0);
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+  {
+    applyRel(f, p.chainG + 12 * c);
+    rotateRows01(f, sn[c], cs[c]);
+    const int slot = p.jntScr[p.chainJoint[c]];
+    if (slot >= 0)
     {
-      const int rem = r0 + lane;
-      if (rem < nJ2)
+      /* the column's axis is row 2 of the shifted base */
+      double* col = scr + slot * scrStride + tid;
+      col[0] = f.R[6];
+      col[rs] = f.R[7];
+      col[2 * rs] = f.R[8];
+      if (MASS == 2)
       {
-        const double* src = stw + rem * scrStride;
-        double* d = Mw + rem;
-#pragma unroll 4
-        for (int sl = 0; sl < (int) nv; ++sl)
+        col[3 * rs] = f.o[1] * f.R[8] - f.o[2] * f.R[7];
+        col[4 * rs] = f.o[2] * f.R[6] - f.o[0] * f.R[8];
+        col[5 * rs] = f.o[0] * f.R[7] - f.o[1] * f.R[6];
+      }
+      else
+      {
+        col[3 * rs] = f.o[0];
+        col[4 * rs] = f.o[1];
+        col[5 * rs] = f.o[2];
+      }
+    }
+    outputs(c + 1);
+  }
+
+  double Mv[MASS ? 36 : 1];
+  if (MASS == 2 && a.M)
+  {
+    /* composite about the world origin: mass, first moment, inertia (xx, xy, xz, yy, yz, zz) */
+    double cm = 0.0, ch[3] = {0.0, 0.0, 0.0}, cI[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = NC - 1; c >= 0; --c)
+    {
+      /* f: base of level c + 1 */
+      const double* K = p.chainMass + 10 * (c + 1);
+      const double mL = K[0];
+      const double* R = f.R;
+      const double H[3] = {R[0] * K[1] + R[3] * K[2] + R[6] * K[3], R[1] * K[1] + R[4] * K[2] + R[7] * K[3],
+                           R[2] * K[1] + R[5] * K[2] + R[8] * K[3]};
+      const double Ib[9] = {K[4], K[5], K[6], K[5], K[7], K[8], K[6], K[8], K[9]};
+      double t[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
         {
-          d[(long) sl * nJ2] = src[sl];
+          t[3 * i + jj] = Ib[3 * i] * R[jj] + Ib[3 * i + 1] * R[3 + jj] + Ib[3 * i + 2] * R[6 + jj];
         }
+      const double* o = f.o;
+      const double oo = mL * (o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) + 2.0 * (o[0] * H[0] + o[1] * H[1] + o[2] * H[2]);
+      cm += mL;
+      ch[0] += mL * o[0] + H[0];
+      ch[1] += mL * o[1] + H[1];
+      ch[2] += mL * o[2] + H[2];
+      cI[0] += (R[0] * t[0] + R[3] * t[3] + R[6] * t[6]) + (oo - (mL * o[0] * o[0] + 2.0 * o[0] * H[0]));
+      cI[1] += (R[0] * t[1] + R[3] * t[4] + R[6] * t[7]) - (mL * o[0] * o[1] + (o[0] * H[1] + H[0] * o[1]));
+      cI[2] += (R[0] * t[2] + R[3] * t[5] + R[6] * t[8]) - (mL * o[0] * o[2] + (o[0] * H[2] + H[0] * o[2]));
+      cI[3] += (R[1] * t[1] + R[4] * t[4] + R[7] * t[7]) + (oo - (mL * o[1] * o[1] + 2.0 * o[1] * H[1]));
+      cI[4] += (R[1] * t[2] + R[4] * t[5] + R[7] * t[8]) - (mL * o[1] * o[2] + (o[1] * H[2] + H[1] * o[2]));
+      cI[5] += (R[2] * t[2] + R[5] * t[5] + R[8] * t[8]) + (oo - (mL * o[2] * o[2] + 2.0 * o[2] * H[2]));
+
+      /* momentum of the composite under a unit rate of column c: p = m v + w x h, L = I w + h x v */
+      const double w[3] = {R[6], R[7], R[8]};
+      const double v[3] = {o[1] * w[2] - o[2] * w[1], o[2] * w[0] - o[0] * w[2], o[0] * w[1] - o[1] * w[0]};
+      const double pk[3] = {cm * v[0] + (w[1] * ch[2] - w[2] * ch[1]), cm * v[1] + (w[2] * ch[0] - w[0] * ch[2]),
+                            cm * v[2] + (w[0] * ch[1] - w[1] * ch[0])};
+      const double Lk[3] = {cI[0] * w[0] + cI[1] * w[1] + cI[2] * w[2] + (ch[1] * v[2] - ch[2] * v[1]),
+                            cI[1] * w[0] + cI[3] * w[1] + cI[4] * w[2] + (ch[2] * v[0] - ch[0] * v[2]),
+                            cI[2] * w[0] + cI[4] * w[1] + cI[5] * w[2] + (ch[0] * v[1] - ch[1] * v[0])};
+      Mv[c * (c + 1) / 2 + c] = (w[0] * Lk[0] + w[1] * Lk[1] + w[2] * Lk[2]) + (v[0] * pk[0] + v[1] * pk[1] + v[2] * pk[2]);
+#pragma unroll
+      for (int i = 0; i < c; ++i)
+      {
+        const double* ci = scr + i * scrStride + tid;
+        Mv[c * (c + 1) / 2 + i] = (ci[0] * Lk[0] + ci[rs] * Lk[1] + ci[2 * rs] * Lk[2]) +
+                                  (ci[3 * rs] * pk[0] + ci[4 * rs] * pk[1] + ci[5 * rs] * pk[2]);
+      }
+
+      if (c > 0)
+      {
+        /* back to the base of level c: undo the rotation about row 2, then G_c */
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+          const double ru = f.R[k], rv = f.R[3 + k];
+          f.R[k] = cs[c] * ru - sn[c] * rv;
+          f.R[3 + k] = sn[c] * ru + cs[c] * rv;
+        }
+        const double2* G2 = reinterpret_cast<const double2*>(p.chainG + 12 * c);
+        const double2 g0 = G2[0], g1 = G2[1], g2 = G2[2], g3 = G2[3], g4 = G2[4], g5 = G2[5];
+        const double ga[3] = {g0.x, g0.y, g1.x};
+        const double A[9] = {g1.y, g2.x, g2.y, g3.x, g3.y, g4.x, g4.y, g5.x, g5.y};
+        double n[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj)
+          {
+            n[3 * i + jj] = A[i] * f.R[jj] + A[3 + i] * f.R[3 + jj] + A[6 + i] * f.R[6 + jj];
+          }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+        {
+          f.R[i] = n[i];
+        }
+        f.o[0] -= f.R[0] * ga[0] + f.R[3] * ga[1] + f.R[6] * ga[2];
+        f.o[1] -= f.R[1] * ga[0] + f.R[4] * ga[1] + f.R[7] * ga[2];
+        f.o[2] -= f.R[2] * ga[0] + f.R[5] * ga[1] + f.R[8] * ga[2];
       }
     }
   }
+  fkTail<MASS>(a, p, scr, scrStride, nChain, tid, s, Mv);
 }
 
 template <bool VEL, bool ALIGNED32, int MASS, bool PRUNED = false>
@@ -958,6 +1185,40 @@ static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t sm
 #undef RCSB_LAUNCH
 }
 
+template <bool ALIGNED32, int MASS>
+static cudaError_t launchFkChain(const FkArgs& a, int nScrRows, cudaStream_t stream)
+{
+  constexpr int threads = RCSB_FK_BLOCK(MASS);
+  const size_t smemBytes = (size_t) a.planBytes + (size_t) nScrRows * (threads + 1) * sizeof(double);
+  const dim3 grid((unsigned int) ((a.N + threads - 1) / threads));
+#define RCSB_LAUNCH(NC)                                                                        \
+  case NC:                                                                                     \
+  {                                                                                            \
+    auto k = fkChainKernel<ALIGNED32, MASS, NC>;                                               \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, threads, smemBytes, stream>>>(a);                                                \
+    return cudaGetLastError();                                                                 \
+  }
+  switch (a.chainNc)
+  {
+    RCSB_LAUNCH(1)
+    RCSB_LAUNCH(2)
+    RCSB_LAUNCH(3)
+    RCSB_LAUNCH(4)
+    RCSB_LAUNCH(5)
+    RCSB_LAUNCH(6)
+    RCSB_LAUNCH(7)
+    RCSB_LAUNCH(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef RCSB_LAUNCH
+}
+
 }   // namespace rcsb
 
 extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows,
@@ -983,6 +1244,15 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
   const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &
                    31u) == 0;
 
+  if (a->chainNc > 0)
+  {
+    /* serial chain of rotations: straight-line walk, nothing of the model interpreted */
+    if (a->M)
+    {
+      return al ? launchFkChain<true, 2>(*a, nScrRows, stream) : launchFkChain<false, 2>(*a, nScrRows, stream);
+    }
+    return al ? launchFkChain<true, 0>(*a, nScrRows, stream) : launchFkChain<false, 0>(*a, nScrRows, stream);
+  }
   if (a->M && a->massMode == 2)
   {
     return al ? launchSlots<false, true, 2>(*a, nSlots, grid, smemBytes, stream)

@@ -1928,21 +1928,6 @@ ikTasksKernel(const IkArgs a)
 /* Single-chain fast path                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 
-/* The chain kernels keep the rows of the running rotation matrix cyclically shifted so that the
- * axis of the joint that comes next is row 2 and the two rows it mixes are rows 0 and 1 (the
- * shifts are folded into the plan's transforms, RcsbIkPlanHeader::offProg): every joint runs
- * the same code, u' = c u + s v, v' = -s u + c v as in rotateAboutAxis. */
-__device__ __forceinline__ void rotateRows01(Frame& f, double s, double c)
-{
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-  {
-    const double ru = f.R[k], rv = f.R[3 + k];
-    f.R[k] = c * ru + s * rv;
-    f.R[3 + k] = c * rv - s * ru;
-  }
-}
-
 /* One step of the root-to-effector program: a constant relative transform, or the motion of a
  * joint that is not a Jacobian column (constrained: its value never changes during the solve). */
 template <bool PERM>

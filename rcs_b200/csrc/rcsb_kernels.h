@@ -43,6 +43,7 @@ struct FkArgs
   int massMode;        /* 0: no M; 1: per-column momentum accumulators; 2: serial chain, composites */
   int pruned;          /* 1: walk the plan's sub-tree only (body selections without velocities) */
   int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
+  int chainNc;         /* > 0: fkChainKernel<..., chainNc> (RcsbFkPlanHeader::chainNc; frames, Jacobians, M only) */
   int scrDoubles;      /* doubles of the Jacobian scratch: nScrRows x (RCSB_FK_THREADS + 1) */
   /* body-fixed points of up to RCSB_FK_INLINE_PTS effectors travel with the launch, not with the
    * cached plan: a control loop that moves its points (RcsGraph_worldPointJacobian) neither

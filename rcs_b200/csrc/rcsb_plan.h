@@ -76,7 +76,26 @@ typedef struct
   int offJntNext;      /* int[dof]: joint visited after joint j, -1 = none */
   int firstJnt;        /* first joint of the pruned walk, -1 = none */
   int prunedSlots;     /* frame-stack depth of the pruned walk */
-  int pad[3];
+  /* Serial chains of rotations (fkKernel<..., CHAIN = nJ>): no constrained or coupled joint, every
+   * joint a rotation, every column an ancestor of the next one, nJ <= 8 - an arm with any number of
+   * joint-less side bodies. "Level" L of a body = number of columns that move it; its frame is a
+   * CONSTANT transform X_b away from the base of its level (the frame right after the rotation of
+   * column L - 1; the world frame for L = 0), and the base of column c is a constant transform G_c
+   * away from the previous base. The walk is then straight-line code over the columns (compile-time
+   * count) with the bodies of a level as side outputs; nothing of the flat model is interpreted.
+   * Bases are kept with their rows cyclically shifted so that the column's axis is row 2 (as in the
+   * IK chain kernels, RcsbIkPlanHeader::offProg): the shifts are folded into G_c / X_b / the mass
+   * constants on the host as exact permutations. */
+  int chainNc;          /* 0: not eligible */
+  int offChainG;        /* double[chainNc][12] */
+  int offChainX;        /* double[nb][12], in the order of offChainOut */
+  int offChainOutStart; /* int[chainNc + 2]: CSR over the levels 0 .. chainNc */
+  int offChainOut;      /* int4[nb]: {body, output slot or -1, RCSB_REL_* flags of X | 1 if the frame is
+                           needed (selected, or an effector is attached), 0} */
+  int offChainMass;     /* double[chainNc + 1][10]: mass, first moment (3) and inertia about the base
+                           origin (xx xy xz yy yz zz) of the massive bodies of level L, base coordinates */
+  int offChainJoint;    /* int[chainNc]: jointIndex of the column */
+  int pad[2];
 } RcsbFkPlanHeader;
 
 /*
