@@ -228,6 +228,47 @@ def test_unaligned_outputs_ragged_batches_and_body_selections(name, n, refmod, c
     assert_close(only.cpu().numpy(), ref["A_BI"][:, [g.n_bodies // 3]], what=f"{name}: one frame")
 
 
+@pytest.mark.parametrize("name,eff_name", [("wam_arm", "BallTip"), ("wam_arm", "Link4"), ("wrist6", "Tip"),
+                                           ("wrist6", "Fore")])
+def test_chain_walk_matches_the_interpreting_kernel_and_the_reference(name, eff_name, refmod, cuda_device,
+                                                                      monkeypatch):
+    """Serial chains of rotations take fkChainKernel (straight-line walk over folded transforms, the
+    mass matrix tip to root by inverse transforms, rcsb_plan.h: chainNc); RCSB_FK_GENERAL=1 forces
+    fkKernel, which interprets the flat model. Both against the reference: frames, Jacobians of a
+    body-fixed point, M; all bodies and a body selection; wrist6 has several joint axes per body, so
+    its bases carry row shifts."""
+    g, m, r = _models(name, refmod, cuda_device)
+    eff = [g.body_index(eff_name)]
+    pts = np.array([[0.03, -0.02, 0.05]])
+    q = workload.sample_states(g.layout(), 1500 + 7, first=13)
+    ref = r.fk_jacobians(q, eff, points=pts)
+    M_ref = r.mass_matrix(q)
+    sel = [g.n_bodies - 1, 1, eff[0]] if eff[0] not in (1, g.n_bodies - 1) else [g.n_bodies - 1, 1]
+    results = {}
+    for mode in ("chain", "general"):
+        if mode == "general":
+            monkeypatch.setenv("RCSB_FK_GENERAL", "1")
+        launches = rcs_b200.kernel_launch_count()
+        full = m.fk_jacobians(q, eff, points=pts, want=("A_BI", "JT", "JR", "M"))
+        assert rcs_b200.kernel_launch_count() - launches == 1
+        part = m.fk_jacobians(q, eff, points=pts, bodies=sel, want=("A_BI", "JT", "JR"))
+        only = m.fk(q, bodies=[g.n_bodies // 2])
+        results[mode] = (full, part, only)
+        for k in ("A_BI", "JT", "JR"):
+            assert_close(full[k], ref[k], what=f"{name}/{mode}:{k}")
+        assert_structural_zeros(full["JT"], ref["JT"], what=f"{name}/{mode}:JT")
+        assert_structural_zeros(full["JR"], ref["JR"], what=f"{name}/{mode}:JR")
+        assert_close(full["M"], M_ref, what=f"{name}/{mode}:M")
+        assert np.array_equal(full["M"], np.swapaxes(full["M"], 1, 2)), "M symmetric bit for bit"
+        assert_close(part["A_BI"], ref["A_BI"][:, sel], what=f"{name}/{mode}: selected frames")
+        assert_close(part["JT"], ref["JT"], what=f"{name}/{mode}: JT with a selection")
+        assert_close(only["A_BI"], ref["A_BI"][:, [g.n_bodies // 2]], what=f"{name}/{mode}: one frame")
+    # the two kernels agree far below the parity bar
+    for k in ("A_BI", "JT", "JR", "M"):
+        d = np.abs(results["chain"][0][k] - results["general"][0][k]).max()
+        assert d <= 1e-14 * max(1.0, np.abs(results["general"][0][k]).max()), (k, d)
+
+
 def test_polynomial_couplings_inside_and_beyond_the_master_limits(refmod, cuda_device):
     """5- and 9-coefficient coupled joints (RcsJoint_computeSlaveJointAngle / Velocity,
     src/RcsCore/Rcs_joint.c:375-462): inside the master's range the polynomial, beyond it the

@@ -17,7 +17,7 @@ cap() {   # name workload kernel-regex skip
     echo "$name: plain run FAILED"
   fi
 }
-cap fkm fkm fkKernel 2
+cap fkm fkm "fk(Chain)?Kernel" 2
 cap ik ik ikChainKernel 2
 cap ktwalk kinetic ktWalkKernel 2
 cap ktasm kinetic ktAssembleKernel 2
