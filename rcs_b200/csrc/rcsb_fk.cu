@@ -970,33 +970,42 @@ fkChainKernel(const FkArgs a)
   extern __shared__ __align__(16) char smem[];
   char* sPlan = smem;
   double* scr = reinterpret_cast<double*>(sPlan + a.planBytes);
-  stageBlobsTma(sPlan, a.plan, a.planBytes, nullptr, nullptr, 0);
-  PlanView p;
-  p.bind(sPlan);
-
   constexpr int THREADS = RCSB_FK_BLOCK(MASS);
   const int tid = threadIdx.x;
   const int scrStride = THREADS + 1;
-  if (p.hdr->jacRecord > 0)
-  {
-    scr[p.hdr->zeroRow * scrStride + tid] = 0.0;
-  }
   const long s = (long) blockIdx.x * THREADS + tid;
   const bool active = s < a.N;
   const long sc = active ? s : a.N - 1;
-  const int nSel = p.hdr->nSel;
-  const int nChain = p.hdr->nChain;
-  const int rs = nChain * scrStride;
 
+  /* every joint is a column (dof == nJ: column c is joint c): the joint values are requested before
+   * the plan arrives */
   double qv[NC], sn[NC], cs[NC];
   {
     const double* qRow = a.q + sc * a.qdim;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
     {
-      qv[c] = qRow[p.chainJoint[c]];
+      qv[c] = qRow[c];
     }
   }
+  stageBlobsTma(sPlan, a.plan, a.planBytes, nullptr, nullptr, 0);
+  PlanView p;
+  p.bind(sPlan);
+  if (p.hdr->jacRecord > 0)
+  {
+    scr[p.hdr->zeroRow * scrStride + tid] = 0.0;
+  }
+  const int nSel = p.hdr->nSel;
+  const int nChain = p.hdr->nChain;
+  const int rs = nChain * scrStride;
+  /* bodies per level: the bounds of the output loops, fetched once */
+  int outStart[NC + 2];
+#pragma unroll
+  for (int L = 0; L < NC + 2; ++L)
+  {
+    outStart[L] = p.chainOutStart[L];
+  }
+
   if (!sincosBatch<NC>(qv, sn, cs))
   {
 #pragma unroll
@@ -1009,10 +1018,12 @@ fkChainKernel(const FkArgs a)
   Frame f;
   setIdentity(f);
   /* frames of the bodies of level L (and the points of the effectors attached to them) */
-  auto outputs = [&](const int L) {
-    for (int k = p.chainOutStart[L]; k < p.chainOutStart[L + 1]; ++k)
+  auto outputs = [&](const int k0, const int k1) {
+    int4 eNext = p.chainOut[k0 < k1 ? k0 : 0];
+    for (int k = k0; k < k1; ++k)
     {
-      const int4 e = p.chainOut[k];
+      const int4 e = eNext;
+      eNext = p.chainOut[k + 1 < k1 ? k + 1 : k];   /* the next descriptor is in flight during this body */
       if (!(e.z & 1))
       {
         continue;
@@ -1035,13 +1046,13 @@ fkChainKernel(const FkArgs a)
     }
   };
 
-  outputs(0);
+  outputs(outStart[0], outStart[1]);
 #pragma unroll
   for (int c = 0; c < NC; ++c)
   {
     applyRel(f, p.chainG + 12 * c);
     rotateRows01(f, sn[c], cs[c]);
-    const int slot = p.jntScr[p.chainJoint[c]];
+    const int slot = p.jntScr[c];
     if (slot >= 0)
     {
       /* the column's axis is row 2 of the shifted base */
@@ -1062,7 +1073,7 @@ fkChainKernel(const FkArgs a)
         col[5 * rs] = f.o[2];
       }
     }
-    outputs(c + 1);
+    outputs(outStart[c + 1], outStart[c + 2]);
   }
 
   double Mv[MASS ? 36 : 1];
