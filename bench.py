@@ -8,7 +8,7 @@ north_star's target is quoted on:
   per state  in : q (7 doubles)
              out: A_BI of all 12 bodies (12 x 96 B) + JT, JR of BallTip (2 x 3 x 7 doubles)
                   + M(q) (7 x 7 doubles)
-             = 1936 algorithmic bytes; one fkKernel<MASS> launch per step and rank.
+             = 1936 algorithmic bytes; one fkChainKernel<MASS = 2, NC = 7> launch per step and rank.
 Under "secondary" the same line carries one complete record (value, roofline, e2e, cpu_baseline,
 clocks, launches) for each other configuration of BASELINE.json, measured in the same process
 right after the headline:
@@ -83,7 +83,7 @@ class Workload:
             self.per_gpu = 1 << 20
             self.scaling = "weak"
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8            # 1544
-            self.kernel = "rcsb::fkKernel"
+            self.kernel = "rcsb::fkChainKernel<MASS = 0, NC = 7> (serial chain of rotations: straight-line walk)"
             self.desc = ("configs[1] without M(q): WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all body frames "
                          "+ JT/JR of BallTip, uniformly sampled joint states")
             self.l2 = "per-step working set 1.6 GB per GPU >> 126 MB L2 (no flush needed)"
@@ -92,7 +92,7 @@ class Workload:
             self.per_gpu = 1 << 20
             self.scaling = "weak"
             self.bytes_per_unit = 7 * 8 + 12 * 96 + 2 * 3 * 7 * 8 + 7 * 7 * 8  # 1936
-            self.kernel = "rcsb::fkKernel<MASS = 2> (serial chain: composite inertias after the walk)"
+            self.kernel = "rcsb::fkChainKernel<MASS = 2, NC = 7> (serial chain of rotations: straight-line walk, M tip to root by inverse transforms)"
             self.desc = ("configs[1] + M(q), the configuration the metric and north_star's target are quoted "
                          "on: WAM 7-DoF arm (dof 7, nJ 7, 12 bodies), FK all 12 body frames + JT/JR of "
                          "BallTip + mass matrix M(q) from one launch (rcsb_fk_jacobians_mass), uniformly "
@@ -113,7 +113,7 @@ class Workload:
             self.per_gpu = total // world
             self.scaling = "strong"
             self.bytes_per_unit = 56 + 48 + 56 + 8                            # q in, x_des, q out, det
-            self.kernel = "rcsb::ikChainKernel<7, 6>"
+            self.kernel = "rcsb::ikChainKernel<7, 6, LEFT = 0, MODE = 1>"
             self.desc = ("configs[3]: WAM 7-DoF arm, IkSolverRMR right inverse, tasks XYZ + ABC on BallTip, "
                          f"lambda {IK_LAMBDA}, alpha {IK_ALPHA}, {IK_ITERS} iterations per target; targets = "
                          "poses of uniformly sampled states, start = goal state + U(-0.1, 0.1) rad")
