@@ -18,6 +18,7 @@ cap() {   # name workload kernel-regex skip
   fi
 }
 cap fkm fkm "fk(Chain)?Kernel" 2
+cap fk fk "fk(Chain)?Kernel" 2
 cap ik ik ikChainKernel 2
 cap ktwalk kinetic ktWalkKernel 2
 cap ktasm kinetic ktAssembleKernel 2
