@@ -152,6 +152,22 @@ def test_full_size_arm_batch_properties(cuda_device):
     ref = rcs_oracle.Oracle(lay).fk_jacobians(q[idx], [tip])
     for k in ("A_BI", "JT", "JR"):
         assert_close(out[k][idx].cpu().numpy(), ref[k], what=k)
+    # the headline launch (frames + Jacobians + M from fkChainKernel) on all states: the same frames and
+    # rotation Jacobians bit for bit, M symmetric bit for bit and positive definite everywhere, and equal to the
+    # matrix of the kinetic-terms kernels (another algorithm: walk + assembly) on a strided sample
+    fused = m.fk_jacobians(dq, [tip], want=("A_BI", "JT", "JR", "M"))
+    torch.cuda.synchronize()
+    assert torch.equal(fused["A_BI"], out["A_BI"]) and torch.equal(fused["JR"], out["JR"])
+    # with M the columns are kept as spatial axes (w, v = o x w), JT = w x p + v instead of w x (p - o)
+    assert float((fused["JT"] - out["JT"]).abs().max()) < 1e-14
+    M = fused["M"]
+    assert torch.equal(M, M.transpose(1, 2))
+    _, info = torch.linalg.cholesky_ex(M)
+    assert int(info.abs().max()) == 0
+    didx = torch.from_numpy(idx).cuda(cuda_device)
+    Mk = m.kinetic_terms(dq[didx].contiguous(), want=("M",))["M"]
+    assert float((M[didx] - Mk).abs().max()) < 1e-12 * max(1.0, float(Mk.abs().max()))
+    assert_close(M[didx].cpu().numpy(), rcs_oracle.Oracle(lay).kinetic_terms(q[idx], np.zeros_like(q[idx]))["M"], what="M")
 
 
 def test_full_size_humanoid_kinetic_terms_properties(cuda_device):
