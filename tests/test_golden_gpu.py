@@ -17,7 +17,7 @@ from conftest import GRAPH_DIR, ROOT, assert_close, assert_structural_zeros, gra
 from oracle import rcs_oracle
 
 pytestmark = pytest.mark.gpu
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled", "wrist6"]
 
 
 def _golden(name):
@@ -57,7 +57,7 @@ def test_fk_jacobians_kinetic_terms_match_golden(name, cuda_device):
     assert np.all(err <= tol), f"{name}: direct dynamics, worst err/tol {float((err / tol).max()):.2f}"
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "gantry"])
+@pytest.mark.parametrize("name", ["wam_arm", "gantry", "wrist6"])
 def test_fused_mass_matrix_and_left_inverse_match_golden(name, cuda_device):
     """The fused FK + Jacobians + M(q) launch (serial-chain variant on both graphs, the gantry with
     translational joints) and RCSB_IK_LEFT_INVERSE steps against vectors recorded from the
@@ -88,7 +88,7 @@ def test_fused_mass_matrix_and_left_inverse_match_golden(name, cuda_device):
     assert np.abs(q5 - z["ikl_q5"]).max() <= 1e-8
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry"])
+@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry", "wrist6"])
 def test_ik_matches_golden(name, cuda_device):
     z = _golden(name)
     g = rcs_b200.Graph(graph_file(name))

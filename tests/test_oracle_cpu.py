@@ -15,7 +15,7 @@ from conftest import GRAPH_DIR, GRAPHS, ROOT, assert_close, assert_structural_ze
 from oracle import rcs_oracle
 from rcs_b200 import workload
 
-GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled"]
+GOLDEN = ["wam_arm", "wam_scenario", "humanoid", "husky", "gantry", "polycoupled", "wrist6"]
 
 
 def layout(name):
@@ -78,7 +78,7 @@ def test_direct_dynamics_matches_golden(name):
     assert np.all(err <= tol), float((err / tol).max())
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "gantry"])
+@pytest.mark.parametrize("name", ["wam_arm", "gantry", "wrist6"])
 def test_left_inverse_and_mass_matrix_match_golden(name):
     """Recorded from the reference: IkSolverRMR::solveLeftInverse steps (lambda 1e-3) and
     RcsGraph_computeMassMatrix."""
@@ -96,7 +96,7 @@ def test_left_inverse_and_mass_matrix_match_golden(name):
     assert_close(o.kinetic_terms(z["q"])["M"], z["mass_M"], what="M")
 
 
-@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry"])
+@pytest.mark.parametrize("name", ["wam_arm", "humanoid", "gantry", "wrist6"])
 def test_ik_matches_golden(name):
     z, o = golden(name), rcs_oracle.Oracle(layout(name))
     tip = int(z["ik_tip"])

@@ -6,7 +6,7 @@ The reference itself has no stored vectors for this path, and /r
 does not exist on the GPU box; these small fixtures pin the numpy oracle and the CUDA path
 there. Re-run in the CPU container after changing graphs or cases:
 
-    python tools/make_golden.py
+    python tools/make_golden.py [case ...]
 """
 import os
 import sys
@@ -29,6 +29,9 @@ CASES = {
     # 5- and 9-coefficient polynomial couplings (Rcs_joint.c:318-462); a third of the states have
     # the master joints below, a third above their limits (tangent extension of the polynomial)
     "polycoupled": dict(n=24, effectors=["Tip", "Probe"], beyond=True),
+    # several joint axes per body behind translation-only transforms: the folded chain walks of
+    # fkChainKernel / ikChainKernel with row shifts
+    "wrist6": dict(n=24, effectors=["Tip", "Fore"]),
 }
 
 
@@ -46,7 +49,10 @@ def push_masters_beyond_limits(lay, q):
 
 def main():
     ref.set_threads(1)
+    only = sys.argv[1:]          # optional: names of the cases to (re)write
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         f = os.path.join(GRAPHS, name + ".xml")
         g = ref.RefGraph(f)
         lay = g.layout()
@@ -79,8 +85,8 @@ def main():
                    **{"kt_" + k: v for k, v in kt.items()})
         if g.nJ <= 8:
             out["mass_M"] = g.mass_matrix(q)          # RcsGraph_computeMassMatrix (fused FK + J + M launch)
-        if name in ("wam_arm", "humanoid", "gantry"):
-            tip = {"wam_arm": "BallTip", "humanoid": "RightHandTip", "gantry": "Tool"}[name]
+        if name in ("wam_arm", "humanoid", "gantry", "wrist6"):
+            tip = {"wam_arm": "BallTip", "humanoid": "RightHandTip", "gantry": "Tool", "wrist6": "Tip"}[name]
             ik = ref.RefIk(f, [("XYZ", tip), ("ABC", tip)])
             q_goal = workload.sample_states(lay, n, first=2000, margin=0.2)
             x_des, J = ik.task_kinematics(q_goal)
