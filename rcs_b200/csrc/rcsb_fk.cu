@@ -969,10 +969,17 @@ fkChainKernel(const FkArgs a)
 {
   extern __shared__ __align__(16) char smem[];
   char* sPlan = smem;
-  double* scr = reinterpret_cast<double*>(sPlan + a.planBytes);
   constexpr int THREADS = RCSB_FK_BLOCK(MASS);
   const int tid = threadIdx.x;
-  const int scrStride = THREADS + 1;
+  const int lane = tid & 31;
+  /* scratch: one private region per warp, row r of lane l at region[r * 33 + l] (fkKernel interleaves
+   * the warps of a block in 129-double rows); `scr` is shifted so that the shared expressions
+   * scr + row * scrStride + tid address it. A private region can be reused by its warp behind a warp
+   * barrier: the results leave it as bulk stores (below). */
+  constexpr int scrStride = 33;
+  const int regionDoubles = a.scrDoubles;
+  double* scrW = reinterpret_cast<double*>(sPlan + a.planBytes) + (tid >> 5) * regionDoubles;
+  double* scr = scrW - (tid - lane);
   const long s = (long) blockIdx.x * THREADS + tid;
   const bool active = s < a.N;
   const long sc = active ? s : a.N - 1;
@@ -1162,7 +1169,118 @@ fkChainKernel(const FkArgs a)
       }
     }
   }
-  fkTail<MASS>(a, p, scr, scrStride, nChain, tid, s, Mv);
+  /* ---- results of a full warp with one effector: Jacobians and M are laid out in the warp's region
+   * exactly as its 32 records lie in global memory ([state][element]) and leave as three bulk stores
+   * (cp.async.bulk.global.shared::cta), issued by lane 0: 42 + NC^2 shared-memory stores per thread
+   * instead of the transposing copy loops of fkTail (a quarter of the kernel's instructions) ---- */
+  constexpr int REC = 3 * NC, NJ2 = NC * NC;
+  const long w0 = s - lane;
+  const bool bulk = a.JT && a.JR && a.N - w0 >= 32 && p.hdr->nEff == 1 && p.hdr->jacRecord == REC &&
+                    p.hdr->inPlace != 0 && 64 * REC <= regionDoubles && 32 * NJ2 <= regionDoubles &&
+                    ((reinterpret_cast<uintptr_t>(a.JT) | reinterpret_cast<uintptr_t>(a.JR) |
+                      reinterpret_cast<uintptr_t>(a.M)) & 15u) == 0;
+  if (!bulk)
+  {
+    fkTail<MASS>(a, p, scr, scrStride, nChain, tid, s, Mv);
+    return;
+  }
+  double jt[REC], jr[REC];
+  {
+    const double* pe = scr + (6 * nChain) * scrStride + tid;
+    const double px = pe[0], py = pe[scrStride], pz = pe[2 * scrStride];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      const int tT = p.jtab[c];              /* row of the column's translation part, -1: not on the chain */
+      if (tT >= 0)
+      {
+        const double* col = scr + (tT - 3 * nChain) * scrStride + tid;
+        const double w[3] = {col[0], col[rs], col[2 * rs]};
+        const double u[3] = {col[3 * rs], col[4 * rs], col[5 * rs]};
+        if (MASS == 2)
+        {
+          /* (w, v): column = w x I_p + v */
+          jt[c] = u[0] + (w[1] * pz - w[2] * py);
+          jt[NC + c] = u[1] + (w[2] * px - w[0] * pz);
+          jt[2 * NC + c] = u[2] + (w[0] * py - w[1] * px);
+        }
+        else
+        {
+          /* (axis, origin): column = axis x (I_p - origin) */
+          const double d0 = px - u[0], d1 = py - u[1], d2 = pz - u[2];
+          jt[c] = w[1] * d2 - w[2] * d1;
+          jt[NC + c] = w[2] * d0 - w[0] * d2;
+          jt[2 * NC + c] = w[0] * d1 - w[1] * d0;
+        }
+        jr[c] = w[0];
+        jr[NC + c] = w[1];
+        jr[2 * NC + c] = w[2];
+      }
+      else
+      {
+        jt[c] = jt[NC + c] = jt[2 * NC + c] = 0.0;
+        jr[c] = jr[NC + c] = jr[2 * NC + c] = 0.0;
+      }
+    }
+  }
+  __syncwarp();   /* every lane has read its rows: the region is free */
+  {
+    double* stT = scrW + lane * REC;
+    double* stR = scrW + 32 * REC + lane * REC;
+#pragma unroll
+    for (int e = 0; e < REC; ++e)
+    {
+      stT[e] = jt[e];
+      stR[e] = jr[e];
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0)
+  {
+    const unsigned int srcT = (unsigned int) __cvta_generic_to_shared(scrW);
+    const unsigned int srcR = (unsigned int) __cvta_generic_to_shared(scrW + 32 * REC);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.JT + w0 * REC), "r"(srcT),
+                 "n"(32 * REC * 8)
+                 : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.JR + w0 * REC), "r"(srcR),
+                 "n"(32 * REC * 8)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  if (MASS == 2 && a.M)
+  {
+    if (lane == 0)
+    {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* the Jacobians have left the region */
+    }
+    __syncwarp();
+    double* stM = scrW + lane * NJ2;
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+    {
+#pragma unroll
+      for (int i = 0; i <= k; ++i)
+      {
+        stM[i * NC + k] = Mv[k * (k + 1) / 2 + i];
+        stM[k * NC + i] = Mv[k * (k + 1) / 2 + i];
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+    {
+      const unsigned int srcM = (unsigned int) __cvta_generic_to_shared(scrW);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.M + w0 * NJ2), "r"(srcM),
+                   "n"(32 * NJ2 * 8)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0)
+  {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   /* the region outlives the copies */
+  }
 }
 
 template <bool VEL, bool ALIGNED32, int MASS, bool PRUNED = false>
@@ -1200,7 +1318,10 @@ template <bool ALIGNED32, int MASS>
 static cudaError_t launchFkChain(const FkArgs& a, int nScrRows, cudaStream_t stream)
 {
   constexpr int threads = RCSB_FK_BLOCK(MASS);
-  const size_t smemBytes = (size_t) a.planBytes + (size_t) nScrRows * (threads + 1) * sizeof(double);
+  /* one scratch region per warp: nScrRows rows of 33 doubles, 16-byte multiple (FkArgs::scrDoubles) */
+  FkArgs b = a;
+  b.scrDoubles = (nScrRows * 33 + 1) & ~1;
+  const size_t smemBytes = (size_t) a.planBytes + (size_t) (threads / 32) * b.scrDoubles * sizeof(double);
   const dim3 grid((unsigned int) ((a.N + threads - 1) / threads));
 #define RCSB_LAUNCH(NC)                                                                        \
   case NC:                                                                                     \
@@ -1212,7 +1333,7 @@ static cudaError_t launchFkChain(const FkArgs& a, int nScrRows, cudaStream_t str
     {                                                                                          \
       return e;                                                                                \
     }                                                                                          \
-    k<<<grid, threads, smemBytes, stream>>>(a);                                                \
+    k<<<grid, threads, smemBytes, stream>>>(b);                                                \
     return cudaGetLastError();                                                                 \
   }
   switch (a.chainNc)
