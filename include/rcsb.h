@@ -287,7 +287,9 @@ int rcsb_ik_prio_rmr(const RcsbModel* model, int nTasks, const RcsbTask* tasks, 
  *           Rcs_kinematics.c:904-1036), in world coordinates or, with refBdy, relative to that body
  *           and in its frame (TaskCOM3D.cpp:101-165)
  *   JOINT   TaskJoint (TaskJoint.cpp:227-265): the value of joint `effector` (a jointIndex; the
- *           joint must be unconstrained)
+ *           joint must be unconstrained); with refBdy >= 0 (here: the jointIndex of an unconstrained
+ *           reference joint, the XML's refJnt) x = q_joint + refGain q_ref and J has refGain in the
+ *           reference joint's column (refGain: the XML default is 1)
  *   POLARX / POLARY / POLARZ   TaskPolar2D (controlVariable "POLAR" with axisDirection "X" / "Y" /
  *           "Z", the default; TaskPolar2D.cpp:131-290): the polar angles (phi, theta) of that axis
  *           of the effector in the frame of refBdy (world if -1): x = Vec3d_getPolarAngles of the
@@ -313,6 +315,7 @@ typedef struct
   int effector;
   int refBdy;
   int refFrame;
+  double refGain;   /* JOINT tasks with a reference joint only (TaskJoint::refGain); ignored otherwise */
 } RcsbTaskSpec;
 int rcsb_ik_tasks_rmr(const RcsbModel* model, int nTasks, const RcsbTaskSpec* tasks, long N, double* q,
                       const double* xDes, double lambda, double alpha, int iters, double* dx, double* dq,

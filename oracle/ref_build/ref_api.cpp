@@ -784,6 +784,15 @@ void* ref_ik_create(const char* graphFile, const char* taskSpec)
       if (f[0] == "Joint")
       {
         x << " jnt=\"" << f[1] << "\"";       /* TaskJoint: the second field is the joint's name */
+        if (f.size() >= 3 && !f[2].empty())
+        {
+          x << " refJnt=\"" << f[2] << "\"";   /* third: reference joint, fourth: refGain */
+          if (f.size() >= 4 && !f[3].empty())
+          {
+            x << " refGain=\"" << f[3] << "\"";
+          }
+        }
+        f.resize(2);
       }
       else if (!f[1].empty())
       {

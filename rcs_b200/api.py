@@ -75,7 +75,15 @@ TASK_POLARX, TASK_POLARY, TASK_POLARZ = 8, 9, 10
 
 class _RcsbTaskSpec(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("effector", ctypes.c_int), ("refBdy", ctypes.c_int),
-                ("refFrame", ctypes.c_int)]
+                ("refFrame", ctypes.c_int), ("refGain", ctypes.c_double)]
+
+    @classmethod
+    def of(cls, t):
+        """(kind, effector[, refBdy[, refFrame[, refGain]]]); refGain defaults to the reference's 1.0"""
+        t = tuple(t)
+        ints = [int(v) for v in t[:4]] + [-1] * (4 - min(len(t), 4))
+        ints[0], ints[1] = int(t[0]), int(t[1])
+        return cls(ints[0], ints[1], ints[2], ints[3], float(t[4]) if len(t) > 4 else 1.0)
 
 
 def lib() -> ctypes.CDLL:
@@ -621,7 +629,7 @@ class Model:
             if k not in out:
                 out[k] = self._alloc(q, shapes[k])
         self._check(who, out, shapes)
-        tarr = (_RcsbTaskSpec * max(len(spec), 1))(*[_RcsbTaskSpec(*[int(v) for v in t]) for t in spec])
+        tarr = (_RcsbTaskSpec * max(len(spec), 1))(*[_RcsbTaskSpec.of(t) for t in spec])
         a = _Args(self)
         common = (self._h, len(spec), tarr, N, a.ptr(q, "q"), a.ptr(x_des, "x_des"), float(lam), float(alpha),
                   int(iters), a.ptr(out.get("dx"), "dx"), a.ptr(out.get("dq"), "dq"), a.ptr(out.get("det"), "det"))

@@ -1614,7 +1614,21 @@ static int buildIkTasksPlan(RcsbModel* m, int nTasksIn, const RcsbTaskSpec* task
         rcsb_set_error("task %d: joint %d is out of range or constrained", t, ts.effector);
         return RCSB_EINVAL;
       }
-      const int rec[8] = {ts.kind, row, 1, 0, 0, 0, jntJacobi[ts.effector], ts.effector};
+      /* reference joint (TaskJoint.cpp:70-82: it must exist and be unconstrained): its jointIndex + 1
+       * in slot 3, the gain's bits in slots 4 / 5 */
+      int refJoint = 0, gainBits[2] = {0, 0};
+      if (ts.refBdy >= 0)
+      {
+        if (ts.refBdy >= dof || jntJacobi[ts.refBdy] < 0 || ts.refBdy == ts.effector)
+        {
+          rcsb_set_error("task %d: reference joint %d is out of range, constrained or the joint itself", t,
+                         ts.refBdy);
+          return RCSB_EINVAL;
+        }
+        refJoint = ts.refBdy + 1;
+        memcpy(gainBits, &ts.refGain, sizeof(double));
+      }
+      const int rec[8] = {ts.kind, row, 1, refJoint, gainBits[0], gainBits[1], jntJacobi[ts.effector], ts.effector};
       task.insert(task.end(), rec, rec + 8);
       row += 1;
       continue;

@@ -1618,8 +1618,16 @@ ikTasksKernel(const IkArgs a)
       double* Jr = J + row * nJ;
       if (kind == RCSB_TASK_JOINT)
       {
-        dx[row] = xd[0] - qv[tk[7]];
+        double x = qv[tk[7]];
         Jr[aux] = 1.0;
+        if (tk[3] > 0)
+        {
+          /* TaskJoint with a reference joint: x = q + refGain q_ref (TaskJoint.cpp:227-236, :256-265) */
+          const double gain = __hiloint2double(tk[5], tk[4]);
+          x += gain * qv[tk[3] - 1];
+          Jr[m.jntJacobi[tk[3] - 1]] = gain;
+        }
+        dx[row] = xd[0] - x;
         continue;
       }
       if (kind >= RCSB_TASK_COGX && kind <= RCSB_TASK_COGZ)

@@ -23,7 +23,10 @@ def _spec(g, names):
     out = []
     for t in names:
         if t[0] == "Joint":
-            out.append((CODE[t[0]], jidx[t[1]]))
+            if len(t) > 2:      # reference joint and gain (TaskJoint's refJnt / refGain)
+                out.append((CODE[t[0]], jidx[t[1]], jidx[t[2]], -1, float(t[3]) if len(t) > 3 else 1.0))
+            else:
+                out.append((CODE[t[0]], jidx[t[1]]))
         else:
             out.append(tuple([CODE[t[0]]] + [g.body_index(b) if b else -1 for b in t[1:]]))
     return out
@@ -86,6 +89,19 @@ def test_reference_bodies_frames_cog_and_joint_tasks(name, names, refmod, cuda_d
     whole graph and of a subtree, joint tasks."""
     r = _run(name, names, refmod, cuda_device, 300)
     _check(r)
+
+
+@pytest.mark.parametrize("name,names", [
+    ("wam_arm", [("Joint", "ArmJoint2", "ArmJoint4", "-0.5"), ("XYZ", "BallTip"), ("Joint", "ArmJoint6", "ArmJoint7")]),
+    ("gantry", [("Joint", "GantryX", "GantryY", "2.0"), ("XYZ", "Tool")]),
+], ids=["arm-gain-and-default-gain", "gantry-translational-joints"])
+def test_joint_tasks_with_a_reference_joint(name, names, refmod, cuda_device):
+    """TaskJoint with refJnt / refGain (TaskJoint.cpp:70-82, :227-265): x = q + refGain q_ref, the
+    Jacobian row carries refGain in the reference joint's column; refGain defaults to 1."""
+    r = _run(name, names, refmod, cuda_device, 300)
+    _check(r)
+    r3 = _run(name, names, refmod, cuda_device, 200, iters=3, first=5)
+    _check(r3, iters=3)
 
 
 @pytest.mark.parametrize("name,names", [
