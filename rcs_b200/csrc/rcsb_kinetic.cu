@@ -622,6 +622,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
     }
   };
   const bool earlyFetch = !stage && !a.cog && !a.Jcog;
+  const bool midFetch = !stage && !earlyFetch;   /* COG outputs: the composites are read once more after the columns */
   unsigned int phase = 0;
 
   /* all groups of a warp iterate together (warp-level barriers inside) */
@@ -933,6 +934,10 @@ ktAssembleKernel(const KtArgs a, int groupStride)
         }
       }
       __syncwarp();   /* the composites are overwritten by the matrix staging below */
+      if (midFetch && s + sStep < nGroupsTotal)
+      {
+        fetch(s + sStep);   /* the record region is dead from here on: the copy runs under the matrix phase */
+      }
     }
 
     /* ---- mass matrix: only the structurally non-zero pairs (ancestor i, column k) ----------
@@ -1107,7 +1112,7 @@ ktAssembleKernel(const KtArgs a, int groupStride)
       }
     }
     __syncwarp();
-    if (!earlyFetch && s + sStep < nGroupsTotal)
+    if (!earlyFetch && !midFetch && s + sStep < nGroupsTotal)
     {
       fetch(s + sStep);
     }
