@@ -34,11 +34,11 @@ BAR = 1.0e-12
 
 # (label, kernel, graph, tasks, left inverse, lambda, force general kernel, states)
 CASES = [
-    ("arm XYZ+ABC, right inverse", "ikChainKernel<7, 6>", "wam_arm", [("XYZ", "BallTip"), ("ABC", "BallTip")],
+    ("arm XYZ+ABC, right inverse", "ikChainKernel<7, 6, LEFT = 0, MODE = 1> (folded chain)", "wam_arm", [("XYZ", "BallTip"), ("ABC", "BallTip")],
      False, 1.0e-8, False, None),
     ("arm XYZ+ABC, right inverse, general kernel", "ikKernel", "wam_arm", [("XYZ", "BallTip"), ("ABC", "BallTip")],
      False, 1.0e-8, True, None),
-    ("arm XYZ+ABC, left inverse (lambda 1e-3)", "ikChainKernel<7, 6, LEFT>", "wam_arm",
+    ("arm XYZ+ABC, left inverse (lambda 1e-3)", "ikChainKernel<7, 6, LEFT = 1, MODE = 1> (folded chain)", "wam_arm",
      [("XYZ", "BallTip"), ("ABC", "BallTip")], True, 1.0e-3, False, None),
     ("arm XYZ+ABC, left inverse, general kernel", "ikKernel<LEFT>", "wam_arm",
      [("XYZ", "BallTip"), ("ABC", "BallTip")], True, 1.0e-3, True, None),
