@@ -269,6 +269,44 @@ def test_chain_walk_matches_the_interpreting_kernel_and_the_reference(name, eff_
         assert d <= 1e-14 * max(1.0, np.abs(results["general"][0][k]).max()), (k, d)
 
 
+def test_folded_kernels_with_angles_beyond_the_fast_sincos_range(refmod, cuda_device, monkeypatch):
+    """sincosBatch serves |q| < 2^31; beyond that (and for non-finite values) the folding kernels call the
+    library's sincos like the interpreting kernels do: same frames, Jacobians, M and IK step for joint
+    values of 3e9 and 1e15 rad as from the reference (libm), NaN in -> NaN out without a fault."""
+    from rcs_b200 import TASK_ABC, TASK_XYZ
+
+    g, m, r = _models("wam_arm", refmod, cuda_device)
+    tip = g.body_index("BallTip")
+    q = workload.sample_states(g.layout(), 96, first=3)
+    q[0::4, 2] = 3.0e9
+    q[1::4, 5] = -1.0e15
+    q[2::4, 0] = 2147483648.0
+    ref = r.fk_jacobians(q, [tip])
+    M_ref = r.mass_matrix(q)
+    res = {}
+    for mode in ("chain", "general"):
+        if mode == "general":
+            monkeypatch.setenv("RCSB_FK_GENERAL", "1")
+        res[mode] = m.fk_jacobians(q, [tip], want=("A_BI", "JT", "JR", "M"))
+        for k in ("A_BI", "JT", "JR"):
+            assert_close(res[mode][k], ref[k], what=f"{mode}:{k}")
+        assert_close(res[mode]["M"], M_ref, what=f"{mode}:M")
+    monkeypatch.delenv("RCSB_FK_GENERAL")
+    qn = q.copy()
+    qn[5, 3] = np.nan
+    out = m.fk_jacobians(qn, [tip], want=("A_BI", "JT", "JR", "M"))
+    assert np.isnan(out["A_BI"][5]).any() and np.isfinite(out["A_BI"][6]).all()
+    # one IK step from such states (targets: the effector poses of moderate states)
+    rik = refmod.RefIk(graph_file("wam_arm"), [("XYZ", "BallTip"), ("ABC", "BallTip")])
+    x_des, _ = rik.task_kinematics(workload.sample_states(g.layout(), 96, first=50, margin=0.2))
+    x_des = np.ascontiguousarray(x_des)
+    q_ref, dx_ref, dq_ref, det_ref = rik.rmr(q, x_des, lam=1.0e-3, iters=1)
+    qq = q.copy()
+    o = m.ik_rmr([(TASK_XYZ, tip), (TASK_ABC, tip)], qq, x_des, lam=1.0e-3, iters=1, want=("dx", "dq", "det"))
+    assert_close(o["dx"], dx_ref, what="dx from huge angles")
+    assert_close(o["dq"], dq_ref, tol=1e-9, what="dq from huge angles")
+
+
 def test_polynomial_couplings_inside_and_beyond_the_master_limits(refmod, cuda_device):
     """5- and 9-coefficient coupled joints (RcsJoint_computeSlaveJointAngle / Velocity,
     src/RcsCore/Rcs_joint.c:375-462): inside the master's range the polynomial, beyond it the
