@@ -936,8 +936,11 @@ int fkDevice(RcsbModel* m, const DevicePlan* plan, long N, int qdim, const doubl
   /* serial chains of rotations: the straight-line kernel serves frames, Jacobians and M */
   {
     const char* noChain = getenv("RCSB_FK_GENERAL");   /* force the interpreting kernel (tests) */
-    a.chainNc = (plan->aux2 > 0 && !(noChain && noChain[0] == '1') && !qd && !A_JI && !qOut && !qdOut &&
-                 qdim == m->hdr.dof) ? plan->aux2 : 0;
+    const bool chainOk = plan->aux2 > 0 && !(noChain && noChain[0] == '1') && !A_JI && !qOut && !qdOut &&
+                         qdim == m->hdr.dof;
+    /* with velocities: frames, x_dot, omega only (rcsb_fk); without: frames, Jacobians, M */
+    a.chainNc = chainOk && (qd ? (plan->nEff == 0 && !M && !JT && !JR) : true) ? plan->aux2 : 0;
+    a.velRecDoubles = 3 * plan->nSel;
   }
   a.scrDoubles = plan->nScrRows * (RCSB_FK_BLOCK(M != nullptr) + 1);
   RCSB_CUDA(cudaSetDevice(m->device));

@@ -1283,6 +1283,194 @@ fkChainKernel(const FkArgs a)
   }
 }
 
+
+/*
+ * fkChainKernel's walk with velocities (RcsGraph_setState(q, q_dot) on a serial chain of rotations:
+ * frames, x_dot, omega of the selected bodies; no Jacobians). The base carries its twist along: a
+ * constant transform moves the origin inside the same rigid frame (v += omega x (o' - o)), the
+ * column's rotation adds axis * q_dot to omega (the origin lies on the axis), and a body of the level
+ * has x_dot = v + omega x (o_b - o), omega_b = omega (Rcs_graph.c:150-226 sums the same terms joint by
+ * joint). Full warps stage x_dot [state][body][3] in their scratch region and hand it to the TMA engine
+ * as one bulk store, then omega (one value per level, kept in registers) the same way; the last,
+ * partial warp of a batch and unaligned outputs store directly.
+ */
+template <bool ALIGNED32, int NC>
+__global__ void __launch_bounds__(RCSB_FK_THREADS, 4)
+fkChainVelKernel(const FkArgs a)
+{
+  extern __shared__ __align__(16) char smem[];
+  char* sPlan = smem;
+  constexpr int THREADS = RCSB_FK_THREADS;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  double* region = reinterpret_cast<double*>(sPlan + a.planBytes) + (tid >> 5) * a.scrDoubles;
+  const long s = (long) blockIdx.x * THREADS + tid;
+  const bool active = s < a.N;
+  const long sc = active ? s : a.N - 1;
+  const long w0 = s - lane;
+
+  double qv[NC], qdv[NC], sn[NC], cs[NC];
+  {
+    const double* qRow = a.q + sc * a.qdim;
+    const double* qdRow = a.qd + sc * a.qdim;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      qv[c] = qRow[c];
+      qdv[c] = qdRow[c];
+    }
+  }
+  stageBlobsTma(sPlan, a.plan, a.planBytes, nullptr, nullptr, 0);
+  PlanView p;
+  p.bind(sPlan);
+  const int nSel = p.hdr->nSel;
+  const int rec = 3 * nSel;
+  int outStart[NC + 2];
+#pragma unroll
+  for (int L = 0; L < NC + 2; ++L)
+  {
+    outStart[L] = p.chainOutStart[L];
+  }
+  if (!sincosBatch<NC>(qv, sn, cs))
+  {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+    {
+      sincos(qv[c], &sn[c], &cs[c]);
+    }
+  }
+  const bool bulk = a.N - w0 >= 32 && 32 * rec <= a.scrDoubles &&
+                    ((reinterpret_cast<uintptr_t>(a.xdot) | reinterpret_cast<uintptr_t>(a.omega)) & 15u) == 0;
+
+  Frame f;
+  setIdentity(f);
+  double v[3] = {0.0, 0.0, 0.0}, om[3] = {0.0, 0.0, 0.0};
+  double omL[NC + 1][3];
+  auto outputs = [&](const int k0, const int k1) {
+    int4 eNext = p.chainOut[k0 < k1 ? k0 : 0];
+    for (int k = k0; k < k1; ++k)
+    {
+      const int4 e = eNext;
+      eNext = p.chainOut[k + 1 < k1 ? k + 1 : k];
+      if (e.y < 0)
+      {
+        continue;
+      }
+      Frame t = f;
+      applyRelF(t, p.chainX + 12 * k, e.z);
+      if (active && a.A_BI)
+      {
+        storeFrame<ALIGNED32>(a.A_BI + (s * nSel + e.y) * 12, t);
+      }
+      if (a.xdot)
+      {
+        const double d[3] = {t.o[0] - f.o[0], t.o[1] - f.o[1], t.o[2] - f.o[2]};
+        const double x[3] = {v[0] + (om[1] * d[2] - om[2] * d[1]), v[1] + (om[2] * d[0] - om[0] * d[2]),
+                             v[2] + (om[0] * d[1] - om[1] * d[0])};
+        if (bulk)
+        {
+          double* st = region + lane * rec + 3 * e.y;
+          st[0] = x[0];
+          st[1] = x[1];
+          st[2] = x[2];
+        }
+        else if (active)
+        {
+          double* dst = a.xdot + (s * nSel + e.y) * 3;
+          dst[0] = x[0];
+          dst[1] = x[1];
+          dst[2] = x[2];
+        }
+      }
+      if (a.omega && !bulk && active)
+      {
+        double* dst = a.omega + (s * nSel + e.y) * 3;
+        dst[0] = om[0];
+        dst[1] = om[1];
+        dst[2] = om[2];
+      }
+    }
+  };
+
+  omL[0][0] = omL[0][1] = omL[0][2] = 0.0;
+  outputs(outStart[0], outStart[1]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+  {
+    const double o0[3] = {f.o[0], f.o[1], f.o[2]};
+    applyRel(f, p.chainG + 12 * c);
+    {
+      const double d[3] = {f.o[0] - o0[0], f.o[1] - o0[1], f.o[2] - o0[2]};
+      v[0] += om[1] * d[2] - om[2] * d[1];
+      v[1] += om[2] * d[0] - om[0] * d[2];
+      v[2] += om[0] * d[1] - om[1] * d[0];
+    }
+    rotateRows01(f, sn[c], cs[c]);
+    om[0] += f.R[6] * qdv[c];
+    om[1] += f.R[7] * qdv[c];
+    om[2] += f.R[8] * qdv[c];
+    omL[c + 1][0] = om[0];
+    omL[c + 1][1] = om[1];
+    omL[c + 1][2] = om[2];
+    outputs(outStart[c + 1], outStart[c + 2]);
+  }
+
+  if (!bulk)
+  {
+    return;
+  }
+  const unsigned int src = (unsigned int) __cvta_generic_to_shared(region);
+  const unsigned int bytes = 32u * (unsigned int) rec * 8u;
+  if (a.xdot)
+  {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+    {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.xdot + w0 * rec), "r"(src),
+                   "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (a.omega)
+  {
+    if (lane == 0)
+    {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int L = 0; L < NC + 1; ++L)
+    {
+      for (int k = outStart[L]; k < outStart[L + 1]; ++k)
+      {
+        const int slot = p.chainOut[k].y;
+        if (slot >= 0)
+        {
+          double* st = region + lane * rec + 3 * slot;
+          st[0] = omL[L][0];
+          st[1] = omL[L][1];
+          st[2] = omL[L][2];
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+    {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.omega + w0 * rec), "r"(src),
+                   "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0)
+  {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 template <bool VEL, bool ALIGNED32, int MASS, bool PRUNED = false>
 static cudaError_t launchSlots(const FkArgs& a, int nSlots, dim3 grid, size_t smemBytes,
                                cudaStream_t stream)
@@ -1351,6 +1539,43 @@ static cudaError_t launchFkChain(const FkArgs& a, int nScrRows, cudaStream_t str
 #undef RCSB_LAUNCH
 }
 
+template <bool ALIGNED32>
+static cudaError_t launchFkChainVel(const FkArgs& a, cudaStream_t stream)
+{
+  constexpr int threads = RCSB_FK_THREADS;
+  /* one region per warp for the 32 x_dot / omega records of its states (FkArgs::velRecDoubles each) */
+  FkArgs b = a;
+  b.scrDoubles = (32 * a.velRecDoubles + 1) & ~1;
+  const size_t smemBytes = (size_t) a.planBytes + (size_t) (threads / 32) * b.scrDoubles * sizeof(double);
+  const dim3 grid((unsigned int) ((a.N + threads - 1) / threads));
+#define RCSB_LAUNCH(NC)                                                                        \
+  case NC:                                                                                     \
+  {                                                                                            \
+    auto k = fkChainVelKernel<ALIGNED32, NC>;                                                  \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) smemBytes);                                     \
+    if (e != cudaSuccess)                                                                      \
+    {                                                                                          \
+      return e;                                                                                \
+    }                                                                                          \
+    k<<<grid, threads, smemBytes, stream>>>(b);                                                \
+    return cudaGetLastError();                                                                 \
+  }
+  switch (a.chainNc)
+  {
+    RCSB_LAUNCH(1)
+    RCSB_LAUNCH(2)
+    RCSB_LAUNCH(3)
+    RCSB_LAUNCH(4)
+    RCSB_LAUNCH(5)
+    RCSB_LAUNCH(6)
+    RCSB_LAUNCH(7)
+    RCSB_LAUNCH(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef RCSB_LAUNCH
+}
+
 }   // namespace rcsb
 
 extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nScrRows,
@@ -1376,7 +1601,16 @@ extern "C" cudaError_t rcsb_launch_fk(const rcsb::FkArgs* a, int nSlots, int nSc
   const bool al = ((reinterpret_cast<uintptr_t>(a->A_BI) | reinterpret_cast<uintptr_t>(a->A_JI)) &
                    31u) == 0;
 
-  if (a->chainNc > 0)
+  if (a->chainNc > 0 && a->qd)
+  {
+    /* the same walk with velocities: frames, x_dot, omega (no Jacobians) */
+    /* (large body selections would not leave room for four blocks' record regions: fkKernel<VEL>) */
+    if ((size_t) a->planBytes + (size_t) (RCSB_FK_THREADS / 32) * ((32 * a->velRecDoubles + 1) & ~1) * 8 <= (size_t) 56 * 1024)
+    {
+      return al ? launchFkChainVel<true>(*a, stream) : launchFkChainVel<false>(*a, stream);
+    }
+  }
+  else if (a->chainNc > 0)
   {
     /* serial chain of rotations: straight-line walk, nothing of the model interpreted */
     if (a->M)

@@ -43,7 +43,9 @@ struct FkArgs
   int massMode;        /* 0: no M; 1: per-column momentum accumulators; 2: serial chain, composites */
   int pruned;          /* 1: walk the plan's sub-tree only (body selections without velocities) */
   int noCoupling;      /* 1: take slave joints from q as given (RcsGraph_computeForwardKinematics) */
-  int chainNc;         /* > 0: fkChainKernel<..., chainNc> (RcsbFkPlanHeader::chainNc; frames, Jacobians, M only) */
+  int chainNc;         /* > 0: fkChainKernel<..., chainNc> (RcsbFkPlanHeader::chainNc; frames, Jacobians, M) or, with qd,
+                          fkChainVelKernel (frames, x_dot, omega) */
+  int velRecDoubles;   /* 3 x selected bodies: doubles per state in xdot / omega */
   int scrDoubles;      /* doubles of the Jacobian scratch: nScrRows x (RCSB_FK_THREADS + 1) */
   /* body-fixed points of up to RCSB_FK_INLINE_PTS effectors travel with the launch, not with the
    * cached plan: a control loop that moves its points (RcsGraph_worldPointJacobian) neither

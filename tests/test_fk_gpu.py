@@ -269,6 +269,45 @@ def test_chain_walk_matches_the_interpreting_kernel_and_the_reference(name, eff_
         assert d <= 1e-14 * max(1.0, np.abs(results["general"][0][k]).max()), (k, d)
 
 
+@pytest.mark.parametrize("name,n", [("wam_arm", 1), ("wam_arm", 1000 + 13), ("wrist6", 777), ("wrist6", 64)])
+def test_chain_walk_with_velocities(name, n, refmod, cuda_device, monkeypatch):
+    """rcsb_fk with q_dot on a serial chain of rotations: fkChainVelKernel (the base carries its twist
+    through the folded transforms; x_dot / omega of full warps leave as bulk stores, the last partial
+    warp and unaligned outputs store directly) against fkKernel<VEL> (RCSB_FK_GENERAL=1) and the
+    reference; all bodies, a body selection in another order, device pointers 8 bytes off alignment."""
+    import torch
+
+    g, m, r = _models(name, refmod, cuda_device)
+    q, qd = workload.sample_states(g.layout(), n, first=7, with_velocity=True)
+    ref = r.fk(q, qd, want=("A_BI", "xdot", "omega"))
+    sel = [g.n_bodies - 1, 2, 1]
+    res = {}
+    for mode in ("chain", "general"):
+        if mode == "general":
+            monkeypatch.setenv("RCSB_FK_GENERAL", "1")
+        launches = rcs_b200.kernel_launch_count()
+        full = m.fk(q, qd, want=("A_BI", "xdot", "omega"))
+        assert rcs_b200.kernel_launch_count() - launches == 1
+        part = m.fk(q, qd, bodies=sel, want=("xdot", "omega", "A_BI"))
+        only_om = m.fk(q, qd, want=("omega",))
+        res[mode] = full
+        for k in ("A_BI", "xdot", "omega"):
+            assert_close(full[k], ref[k], what=f"{name}/{mode}:{k}")
+            assert_close(part[k], ref[k][:, sel], what=f"{name}/{mode}: selected {k}")
+        assert_close(only_om["omega"], ref["omega"], what=f"{name}/{mode}: omega alone")
+        # outputs that are only 8-byte aligned
+        dq_, dqd_ = torch.from_numpy(q).cuda(cuda_device), torch.from_numpy(qd).cuda(cuda_device)
+        flat = torch.zeros(n * g.n_bodies * 3 + 4, dtype=torch.float64, device=dq_.device)
+        xo = flat[1:1 + n * g.n_bodies * 3].view(n, g.n_bodies, 3)
+        m.fk(dq_, dqd_, want=("xdot",), out={"xdot": xo})
+        torch.cuda.synchronize()
+        assert_close(xo.cpu().numpy(), ref["xdot"], what=f"{name}/{mode}: xdot (unaligned)")
+    monkeypatch.delenv("RCSB_FK_GENERAL")
+    for k in ("xdot", "omega"):
+        d = np.abs(res["chain"][k] - res["general"][k]).max()
+        assert d <= 1e-13 * max(1.0, np.abs(res["general"][k]).max()), (k, d)
+
+
 def test_folded_kernels_with_angles_beyond_the_fast_sincos_range(refmod, cuda_device, monkeypatch):
     """sincosBatch serves |q| < 2^31; beyond that (and for non-finite values) the folding kernels call the
     library's sincos like the interpreting kernels do: same frames, Jacobians, M and IK step for joint
